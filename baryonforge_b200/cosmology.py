@@ -1,0 +1,116 @@
+"""
+Per-halo host scalars (R_200c, D_A) -- SURVEY §8a row 11: the two pyccl calls the reference makes per loop
+iteration (Runners/HealpixRunner.py:320-321, Map2DRunner.py:491,734, SnapshotRunner.py:226,
+Profiles/BaryonCorrection.py:399), vectorised once per process().
+
+If `pyccl` is importable it is used (so numbers are CCL's own); otherwise `Background`, a flat wCDM +
+photons + massless-neutrino background written from CCL's published formulas, stands in.  Either way the
+device path only ever sees the resulting arrays.
+"""
+import numpy as np
+from scipy import interpolate
+
+try:  # the reference's dependency; optional here
+    import pyccl as _ccl
+except Exception:  # pragma: no cover - depends on the environment
+    _ccl = None
+
+# CCL's constants (ccl_constants.h)
+_RHO_CRIT = 2.7753662724570803e11     # h^2 Msun / Mpc^3
+_CLIGHT_HMPC = 2997.92458
+_STBOLTZ, _CLIGHT, _SOLAR_MASS, _MPC = 5.670367e-8, 299792458.0, 1.988409870698051e30, 3.085677581491367e22
+_T_CMB, _T_NCDM, _NEFF = 2.7255, 0.71611, 3.044
+
+
+def have_pyccl():
+    return _ccl is not None
+
+
+class Background(object):
+    """Flat wCDM background used when pyccl is absent."""
+
+    def __init__(self, Omega_m, Omega_b, h, w0=-1.0, **unused):
+        self.Omega_m, self.Omega_b, self.h, self.w0 = Omega_m, Omega_b, h, w0
+        rho_g = 4 * _STBOLTZ / _CLIGHT ** 3 * _T_CMB ** 4
+        rho_c = _RHO_CRIT * h * h * _SOLAR_MASS / _MPC ** 3
+        self.Omega_g = rho_g / rho_c
+        self.Omega_r = self.Omega_g * (1 + _NEFF * 7.0 / 8.0 * _T_NCDM ** 4)
+        self.Omega_l = 1.0 - Omega_m - self.Omega_r
+
+    def E2(self, a):
+        a = np.asarray(a, dtype=np.float64)
+        return self.Omega_m * a ** -3 + self.Omega_r * a ** -4 + self.Omega_l * a ** (-3 * (1 + self.w0))
+
+    def rho_crit(self, a):
+        return _RHO_CRIT * self.h ** 2 * self.E2(a)
+
+    def rho_matter(self, a):
+        return _RHO_CRIT * self.h ** 2 * self.Omega_m * np.asarray(a, dtype=np.float64) ** -3
+
+    def comoving_distance(self, a):
+        a = np.atleast_1d(np.asarray(a, dtype=np.float64))
+        x, w = np.polynomial.legendre.leggauss(32)
+        nseg = 24
+        t = (np.arange(nseg + 1) / nseg)[None, :]
+        edges = a[:, None] + (1.0 - a[:, None]) * t                    # [n, nseg+1]
+        lo, hi = edges[:, :-1, None], edges[:, 1:, None]
+        aa = 0.5 * (hi - lo) * x + 0.5 * (hi + lo)
+        f = 1.0 / (aa * aa * np.sqrt(self.E2(aa)))
+        return np.sum(0.5 * (hi - lo) * w * f, axis=(1, 2)) * _CLIGHT_HMPC / self.h
+
+    def angular_diameter_distance(self, a):
+        a = np.atleast_1d(np.asarray(a, dtype=np.float64))
+        return self.comoving_distance(a) * a
+
+
+def runner_cosmology(cosmo_dict, with_w0):
+    """The cosmology object a runner builds at the top of process() (HealpixRunner.py:280-284 passes w0;
+    Map2DRunner.py:462-465 and SnapshotRunner.py:198-201 do not)."""
+    if _ccl is not None:
+        kw = dict(Omega_c=cosmo_dict['Omega_m'] - cosmo_dict['Omega_b'], Omega_b=cosmo_dict['Omega_b'],
+                  h=cosmo_dict['h'], sigma8=cosmo_dict['sigma8'], n_s=cosmo_dict['n_s'], matter_power_spectrum='linear')
+        if with_w0:
+            kw['w0'] = cosmo_dict['w0']
+        return _ccl.Cosmology(**kw)
+    return Background(cosmo_dict['Omega_m'], cosmo_dict['Omega_b'], cosmo_dict['h'],
+                      cosmo_dict['w0'] if with_w0 else -1.0)
+
+
+def _rho(cosmo, a, rho_type):
+    if isinstance(cosmo, Background):
+        return cosmo.rho_crit(a) if rho_type == 'critical' else cosmo.rho_matter(a)
+    return _ccl.rho_x(cosmo, a, rho_type) if hasattr(_ccl, 'rho_x') else cosmo.rho_x(a, rho_type)
+
+
+def radius_of_mass(cosmo, M, a, mass_def=None):
+    """mass_def.get_radius(cosmo, M, a), physical Mpc, vectorised over (M, a).  mass_def=None means 200c."""
+    M = np.asarray(M)
+    a = np.asarray(a, dtype=np.float64)
+    Delta, rho_type = 200, 'critical'
+    if mass_def is not None:
+        Delta, rho_type = mass_def.Delta, mass_def.rho_type
+        if not isinstance(Delta, (int, float)):
+            # 'vir' / 'fof': defer to the object, one call per distinct scale factor
+            out = np.empty(M.shape, dtype=np.float64)
+            ab = np.broadcast_to(a, M.shape)
+            for au in np.unique(ab):
+                sel = ab == au
+                out[sel] = mass_def.get_radius(cosmo, M[sel], float(au))
+            return out
+    return (M / (4.18879020479 * Delta * _rho(cosmo, a, rho_type))) ** (1. / 3.)
+
+
+def angular_diameter_distance(cosmo, a):
+    if isinstance(cosmo, Background):
+        return cosmo.angular_diameter_distance(a)
+    return _ccl.angular_diameter_distance(cosmo, a)
+
+
+def D_A_of_z(cosmo, z):
+    """The reference's D_a: CubicSpline over 1000 nodes in z in [0, zmax+0.1] (HealpixRunner.py:297-299)."""
+    z = np.asarray(z, dtype=np.float64)
+    z_m = np.max(z)
+    assert z_m <= 30, f"We assume max(z) = 30, but your catalog has max(z) = {z_m}"   # HealpixRunner.py:301
+    z_t = np.linspace(0, z_m + 0.1, 1000)
+    D_a = interpolate.CubicSpline(z_t, angular_diameter_distance(cosmo, 1 / (1 + z_t)))
+    return D_a(z)

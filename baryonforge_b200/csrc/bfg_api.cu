@@ -1,0 +1,197 @@
+// bfg_api.cu -- library plumbing of the C ABI: errors, device info, tables, small utilities.
+#include <stdarg.h>
+#include <string.h>
+#include <vector>
+#include <cmath>
+#include "bfg_common.cuh"
+
+namespace bfg {
+static thread_local char g_err[512] = "";
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+}  // namespace bfg
+
+using namespace bfg;
+
+extern "C" int bfg_abi_version(void) { return BFG_ABI_VERSION; }
+extern "C" const char *bfg_last_error(void) { return bfg::g_err; }
+
+extern "C" int bfg_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" int bfg_device_info(int device, int *sm_count, int64_t *mem_total, int64_t *mem_free) {
+    cudaDeviceProp p;
+    BFG_CUDA_OK(cudaGetDeviceProperties(&p, device));
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    int cur = 0;
+    BFG_CUDA_OK(cudaGetDevice(&cur));
+    BFG_CUDA_OK(cudaSetDevice(device));
+    size_t f = 0, t = 0;
+    BFG_CUDA_OK(cudaMemGetInfo(&f, &t));
+    BFG_CUDA_OK(cudaSetDevice(cur));
+    if (mem_total) *mem_total = (int64_t)t;
+    if (mem_free) *mem_free = (int64_t)f;
+    return BFG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ tables
+extern "C" int bfg_table_create(bfg_table **out, int ndim, const int64_t *shape, const double *const *h_axes,
+                                const double *h_values, int flags, int device) {
+    BFG_REQUIRE(out && shape && h_axes && h_values, "null argument");
+    BFG_REQUIRE(ndim >= 3 && ndim <= BFG_MAX_TABLE_DIM, "ndim must be 3..6 (ln(1+z), ln M, ln r, extras...)");
+    for (int d = 0; d < ndim; ++d) {
+        BFG_REQUIRE(shape[d] >= 2 && shape[d] < (1 << 30), "every axis needs >= 2 nodes");
+        for (int64_t i = 1; i < shape[d]; ++i) BFG_REQUIRE(h_axes[d][i] > h_axes[d][i - 1], "axes must be strictly ascending");
+    }
+    int cur = 0;
+    BFG_CUDA_OK(cudaGetDevice(&cur));
+    BFG_CUDA_OK(cudaSetDevice(device));
+    bfg_table *t = new bfg_table();
+    memset(t, 0, sizeof(*t));
+    t->device = device;
+    i64 total = 1;
+    for (int d = ndim - 1; d >= 0; --d) {
+        t->shape[d] = shape[d];
+        t->view.n[d] = (int)shape[d];
+        t->view.stride[d] = total;
+        total *= shape[d];
+    }
+    t->view.ndim = ndim;
+    t->view.flags = flags;
+    int rc = BFG_OK;
+    for (int d = 0; d < ndim && rc == BFG_OK; ++d) {
+        if (cudaMalloc(&t->d_axes[d], sizeof(double) * shape[d]) != cudaSuccess ||
+            cudaMemcpy(t->d_axes[d], h_axes[d], sizeof(double) * shape[d], cudaMemcpyHostToDevice) != cudaSuccess) {
+            set_error("bfg_table_create: axis upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = BFG_ERR_CUDA;
+        }
+        t->view.ax[d] = t->d_axes[d];
+    }
+    if (rc == BFG_OK) {
+        if (cudaMalloc(&t->d_values, sizeof(double) * total) != cudaSuccess ||
+            cudaMemcpy(t->d_values, h_values, sizeof(double) * total, cudaMemcpyHostToDevice) != cudaSuccess) {
+            set_error("bfg_table_create: value upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = BFG_ERR_CUDA;
+        }
+        t->view.v = t->d_values;
+    }
+    // radial axis: uniform in ln r (np.geomspace -> np.log) unlocks the closed-form cell index
+    const double *ar = h_axes[2];
+    int64_t nr = shape[2];
+    double step = (ar[nr - 1] - ar[0]) / (double)(nr - 1);
+    bool uni = true;
+    for (int64_t i = 0; i < nr; ++i)
+        if (std::fabs(ar[i] - (ar[0] + step * (double)i)) > 1e-12 * std::fabs(step)) { uni = false; break; }
+    t->view.uniform_r = uni ? 1 : 0;
+    t->view.r0 = ar[0];
+    t->view.r1 = ar[nr - 1];
+    t->view.inv_dr = 1.0 / step;
+    cudaSetDevice(cur);
+    if (rc != BFG_OK) { bfg_table_destroy(t); return rc; }
+    *out = t;
+    return BFG_OK;
+}
+
+extern "C" int bfg_table_destroy(bfg_table *t) {
+    if (!t) return BFG_OK;
+    int cur = 0;
+    cudaGetDevice(&cur);
+    cudaSetDevice(t->device);
+    for (int d = 0; d < BFG_MAX_TABLE_DIM; ++d)
+        if (t->d_axes[d]) cudaFree(t->d_axes[d]);
+    if (t->d_values) cudaFree(t->d_values);
+    cudaSetDevice(cur);
+    delete t;
+    return BFG_OK;
+}
+
+extern "C" int bfg_table_info(const bfg_table *t, int *ndim, int64_t *shape, int *flags, int *device, int *uniform_r) {
+    BFG_REQUIRE(t, "null table");
+    if (ndim) *ndim = t->view.ndim;
+    if (shape) for (int d = 0; d < t->view.ndim; ++d) shape[d] = t->shape[d];
+    if (flags) *flags = t->view.flags;
+    if (device) *device = t->device;
+    if (uniform_r) *uniform_r = t->view.uniform_r;
+    return BFG_OK;
+}
+
+// read-out test kernel: one block, blends the row for (lnz, lnM, extras) then evaluates n radial points
+struct ExtrasArg { double e[BFG_MAX_TABLE_DIM]; };
+
+__global__ void k_table_readout(TableView T, double lnz, double lnM, ExtrasArg ex, i64 n, const double *__restrict__ x,
+                                double *__restrict__ out) {
+    extern __shared__ double row[];
+    bool valid;
+    blend_row(T, lnz, lnM, ex.e, row, valid);
+    __syncthreads();
+    for (i64 i = threadIdx.x; i < n; i += blockDim.x) {
+        double v = T.uniform_r ? row_lookup<true>(T, row, x[i]) : row_lookup<false>(T, row, x[i]);
+        if (!valid) v = CUDART_NAN;
+        if (T.flags & BFG_TABLE_LOG_VALUES) v = exp(v);
+        out[i] = v;
+    }
+}
+
+extern "C" int bfg_table_readout(const bfg_table *t, double lnz, double lnM, const double *h_extras, int64_t n,
+                                 const double *d_x, double *d_out, void *stream) {
+    BFG_REQUIRE(t && d_x && d_out, "null argument");
+    ExtrasArg ex;
+    memset(&ex, 0, sizeof(ex));
+    for (int d = 3; d < t->view.ndim; ++d) {
+        BFG_REQUIRE(h_extras, "table has extra axes but no extras given");
+        ex.e[d - 3] = h_extras[d - 3];
+    }
+    size_t smem = sizeof(double) * t->view.n[2];
+    BFG_CUDA_OK(cudaFuncSetAttribute(k_table_readout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_table_readout<<<1, 256, smem, (cudaStream_t)stream>>>(t->view, lnz, lnM, ex, n, d_x, d_out);
+    BFG_CUDA_OK(cudaGetLastError());
+    return BFG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ utilities
+__global__ void k_sum_f64(const double *__restrict__ x, i64 n, double *out) {
+    double acc = 0.0;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) acc += x[i];
+    acc = warp_sum(acc);
+    __shared__ double part[32];
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) part[w] = acc;
+    __syncthreads();
+    if (w == 0) {
+        acc = (lane < (blockDim.x >> 5)) ? part[lane] : 0.0;
+        acc = warp_sum(acc);
+        if (lane == 0) atomicAdd(out, acc);
+    }
+}
+
+extern "C" int bfg_sum_f64(const double *d_x, int64_t n, double *d_out, void *stream) {
+    BFG_REQUIRE(d_out && (d_x || n == 0), "null argument");
+    BFG_CUDA_OK(cudaMemsetAsync(d_out, 0, sizeof(double), (cudaStream_t)stream));
+    if (n > 0) {
+        int blocks = (int)std::min<i64>((n + 1023) / 1024, 148 * 8);
+        k_sum_f64<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_x, n, d_out);
+        BFG_CUDA_OK(cudaGetLastError());
+    }
+    return BFG_OK;
+}
+
+__global__ void k_transpose_offsets(const double *__restrict__ in, double *__restrict__ out, i64 n, int nc) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x)
+        for (int c = 0; c < nc; ++c) out[i * nc + c] = in[(i64)c * n + i];
+}
+
+extern "C" int bfg_transpose_offsets(const double *d_in, double *d_out, int64_t n, int ncomp, void *stream) {
+    BFG_REQUIRE(d_in && d_out && ncomp >= 1 && ncomp <= 3, "bad argument");
+    if (n == 0) return BFG_OK;
+    int blocks = (int)std::min<i64>((n + 255) / 256, 148 * 16);
+    k_transpose_offsets<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_in, d_out, n, ncomp);
+    BFG_CUDA_OK(cudaGetLastError());
+    return BFG_OK;
+}

@@ -1,0 +1,429 @@
+// bfg_common.cuh -- shared device code of libbfg_b200.so (sm_100a only).
+//
+//  * error plumbing for the C ABI
+//  * TableView + per-halo row blending + radial read-out: the device form of
+//    scipy.interpolate.RegularGridInterpolator(method='linear', bounds_error=False, fill_value=nan) as used at
+//    BaryonForge/Profiles/BaryonCorrection.py:322,404-411 and BaryonForge/utils/Tabulate.py:270-271,318-319
+//  * HEALPix RING geometry as device functions (replaces healpy at BaryonForge/Runners/HealpixRunner.py:327-361)
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/bfg_b200.h"
+
+typedef long long i64;
+
+namespace bfg {
+
+void set_error(const char *fmt, ...);
+
+#define BFG_CUDA_OK(expr)                                                                  \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess) {                                                           \
+            bfg::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return BFG_ERR_CUDA;                                                           \
+        }                                                                                  \
+    } while (0)
+
+#define BFG_REQUIRE(cond, msg)                                    \
+    do {                                                          \
+        if (!(cond)) {                                            \
+            bfg::set_error("%s: %s", __func__, msg);              \
+            return BFG_ERR_INVALID;                               \
+        }                                                         \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// Table
+// ------------------------------------------------------------------------------------------------
+struct TableView {
+    int ndim;              // 3 .. BFG_MAX_TABLE_DIM ; axis 2 is radial
+    int flags;
+    int uniform_r;         // radial axis uniform to 1e-12*step -> closed-form cell index
+    int n[BFG_MAX_TABLE_DIM];
+    i64 stride[BFG_MAX_TABLE_DIM];  // in elements
+    const double *ax[BFG_MAX_TABLE_DIM];
+    const double *v;
+    double r0, r1, inv_dr;  // first/last radial node, 1/step
+};
+
+}  // namespace bfg
+
+struct bfg_table {
+    bfg::TableView view;
+    int device;
+    i64 shape[BFG_MAX_TABLE_DIM];
+    double *d_axes[BFG_MAX_TABLE_DIM];
+    double *d_values;
+};
+
+namespace bfg {
+
+// Cell index / normalised distance of one coordinate on one axis, scipy find_indices semantics:
+// ax[i] <= x < ax[i+1], last interval right-closed, index clipped to [0, n-2].  Returns false when x is outside
+// [ax[0], ax[n-1]] (RegularGridInterpolator then yields fill_value = nan).  NaN x is "inside" and propagates.
+__device__ __forceinline__ bool axis_cell(const double *__restrict__ ax, int n, double x, int &i, double &t) {
+    bool inside = !(x < ax[0]) && !(x > ax[n - 1]);
+    int lo = 0, hi = n - 1;  // invariant: ax[lo] <= x (or lo == 0), x < ax[hi] (or hi == n-1)
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (x >= ax[mid]) lo = mid; else hi = mid;
+    }
+    i = lo;
+    t = (x - ax[i]) / (ax[i + 1] - ax[i]);
+    return inside;
+}
+
+// Per-halo constants of the read-out: corner offsets/weights over every non-radial axis.
+struct HaloCell {
+    int ncorner;               // 2^(ndim-1)
+    bool valid;                // false -> every read-out is NaN (coordinate outside a non-radial axis)
+    i64 base[1 << (BFG_MAX_TABLE_DIM - 1)];
+    double w[1 << (BFG_MAX_TABLE_DIM - 1)];
+};
+
+// Blend the 2^(ndim-1) (z, M, extras) corner rows into ONE radial row in shared memory:
+//   row[k] = sum_c w_c * values[corner_c, k]
+// All corners are always multiplied in, like scipy's _evaluate_linear, so 0 * (-inf) = NaN survives.
+// Called by every thread of the block; caller __syncthreads() afterwards.
+__device__ __forceinline__ void blend_row(const TableView &T, double lnz, double lnM, const double *__restrict__ extras,
+                                          double *__restrict__ row, bool &valid) {
+    const int nd = T.ndim;
+    int idx[BFG_MAX_TABLE_DIM];
+    double tt[BFG_MAX_TABLE_DIM];
+    bool ok = true;
+    int e = 0;
+    for (int d = 0; d < nd; ++d) {
+        if (d == 2) continue;
+        double x = (d == 0) ? lnz : (d == 1) ? lnM : extras[e++];
+        ok &= axis_cell(T.ax[d], T.n[d], x, idx[d], tt[d]);
+    }
+    valid = ok;
+    const int nc = 1 << (nd - 1);
+    const int NR = T.n[2];
+    const i64 sr = T.stride[2];
+    for (int k = threadIdx.x; k < NR; k += blockDim.x) {
+        double acc = 0.0;
+        for (int c = 0; c < nc; ++c) {
+            i64 off = (i64)k * sr;
+            double w = 1.0;
+            int bit = 0;
+            for (int d = 0; d < nd; ++d) {
+                if (d == 2) continue;
+                int up = (c >> (nd - 2 - bit)) & 1;  // first axis = most significant, itertools.product order
+                ++bit;
+                off += (i64)(idx[d] + up) * T.stride[d];
+                w = w * (up ? tt[d] : (1.0 - tt[d]));
+            }
+            acc = acc + __ldg(T.v + off) * w;
+        }
+        row[k] = acc;
+    }
+}
+
+// Radial read-out of a blended row at x = ln r (or ln r/R): NaN outside [r0, r1]; (1-t)*v0 + t*v1 as scipy does.
+template <bool UNIFORM>
+__device__ __forceinline__ double row_lookup(const TableView &T, const double *__restrict__ row, double x) {
+    const int NR = T.n[2];
+    if (!(x >= T.r0) || !(x <= T.r1)) return (x != x) ? x : CUDART_NAN;
+    int k;
+    double t;
+    if (UNIFORM) {
+        double u = (x - T.r0) * T.inv_dr;
+        k = (int)u;
+        k = min(k, NR - 2);
+        t = u - (double)k;
+    } else {
+        const double *__restrict__ ax = T.ax[2];
+        int lo = 0, hi = NR - 1;
+        // closed-form guess then bounded correction (geomspace axes hit on the first try)
+        double u = (x - T.r0) * T.inv_dr;
+        int g = min(max((int)u, 0), NR - 2);
+        if (x >= __ldg(ax + g) && x < __ldg(ax + g + 1)) {
+            lo = g;
+        } else {
+            while (hi - lo > 1) {
+                int mid = (lo + hi) >> 1;
+                if (x >= __ldg(ax + mid)) lo = mid; else hi = mid;
+            }
+        }
+        k = lo;
+        double a0 = __ldg(ax + k), a1 = __ldg(ax + k + 1);
+        t = (x - a0) / (a1 - a0);
+    }
+    double v0 = row[k], v1 = row[k + 1];
+    return (1.0 - t) * v0 + t * v1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// HEALPix RING geometry (T_Healpix_Base algorithms, fp64/int64, written for the device)
+// ------------------------------------------------------------------------------------------------
+struct Hpx {
+    i64 nside, npix, ncap, nl4;
+    double fact1, fact2;
+    __host__ __device__ explicit Hpx(i64 ns) {
+        nside = ns;
+        npix = 12 * ns * ns;
+        ncap = 2 * ns * (ns - 1);
+        nl4 = 4 * ns;
+        fact2 = 4.0 / (double)npix;
+        fact1 = (double)(2 * ns) * fact2;
+    }
+};
+
+#define BFG_PI 3.141592653589793238462643383279502884197
+#define BFG_TWOPI 6.283185307179586476925286766559005768394
+#define BFG_HALFPI 1.570796326794896619231321691639751442099
+#define BFG_INV_TWOPI (1.0 / 6.283185307179586476925286766559005768394)
+#define BFG_INV_HALFPI 0.6366197723675813430755350534900574
+#define BFG_TWOTHIRD (2.0 / 3.0)
+
+__device__ __forceinline__ i64 isqrt_i64(i64 v) { return (i64)sqrt((double)v + 0.5); }  // exact for v < 2^50
+
+__device__ __forceinline__ i64 ring_above(const Hpx &h, double z) {
+    double az = fabs(z);
+    if (az <= BFG_TWOTHIRD) return (i64)((double)h.nside * (2.0 - 1.5 * z));
+    i64 ir = (i64)((double)h.nside * sqrt(3.0 * (1.0 - az)));
+    return (z > 0) ? ir : 4 * h.nside - ir - 1;
+}
+
+__device__ __forceinline__ double ring2z(const Hpx &h, i64 ring) {
+    if (ring < h.nside) return 1.0 - (double)(ring * ring) * h.fact2;
+    if (ring <= 3 * h.nside) return (double)(2 * h.nside - ring) * h.fact1;
+    i64 q = 4 * h.nside - ring;
+    return (double)(q * q) * h.fact2 - 1.0;
+}
+
+// first pixel, pixel count and half-pixel phase of a ring (1 <= ring <= 4 nside - 1)
+__device__ __forceinline__ void ring_info(const Hpx &h, i64 ring, i64 &start, i64 &nr, bool &shifted) {
+    if (ring < h.nside) {
+        shifted = true; nr = 4 * ring; start = 2 * ring * (ring - 1);
+    } else if (ring < 3 * h.nside) {
+        shifted = ((ring - h.nside) & 1) == 0; nr = h.nl4; start = h.ncap + (ring - h.nside) * h.nl4;
+    } else {
+        shifted = true; i64 q = 4 * h.nside - ring; nr = 4 * q; start = h.npix - 2 * q * (q + 1);
+    }
+}
+
+// colatitude-related quantities of a ring: z and sin(theta) with the polar-cap accurate form
+__device__ __forceinline__ void ring_z_sth(const Hpx &h, i64 ring, double &z, double &sth) {
+    if (ring < h.nside) {
+        double tmp = (double)(ring * ring) * h.fact2;
+        z = 1.0 - tmp;
+        sth = (z > 0.99) ? sqrt(tmp * (2.0 - tmp)) : sqrt((1.0 - z) * (1.0 + z));
+    } else if (ring <= 3 * h.nside) {
+        z = (double)(2 * h.nside - ring) * h.fact1;
+        sth = sqrt((1.0 - z) * (1.0 + z));
+    } else {
+        i64 q = 4 * h.nside - ring;
+        double tmp = (double)(q * q) * h.fact2;
+        z = tmp - 1.0;
+        sth = (z < -0.99) ? sqrt(tmp * (2.0 - tmp)) : sqrt((1.0 - z) * (1.0 + z));
+    }
+}
+
+// azimuth of pixel `ip` (0-based within its ring)
+__device__ __forceinline__ double ring_phi(const Hpx &h, i64 ring, i64 ip, bool shifted) {
+    if (ring < h.nside) return ((double)(ip + 1) - 0.5) * BFG_HALFPI / (double)ring;
+    if (ring < 3 * h.nside) return ((double)(ip + 1) - (shifted ? 0.5 : 1.0)) * BFG_PI * 0.75 * h.fact1;
+    return ((double)(ip + 1) - 0.5) * BFG_HALFPI / (double)(4 * h.nside - ring);
+}
+
+// ring number (1-based from the north pole) and in-ring index of a RING pixel
+__device__ __forceinline__ void pix2ring(const Hpx &h, i64 pix, i64 &ring, i64 &ip) {
+    if (pix < h.ncap) {
+        ring = (1 + isqrt_i64(1 + 2 * pix)) >> 1;
+        ip = pix - 2 * ring * (ring - 1);
+    } else if (pix < h.npix - h.ncap) {
+        i64 q = pix - h.ncap;
+        i64 t = q / h.nl4;
+        ring = t + h.nside;
+        ip = q - t * h.nl4;
+    } else {
+        i64 q = h.npix - pix;
+        i64 s = (1 + isqrt_i64(2 * q - 1)) >> 1;  // counted from the south pole
+        ring = 4 * h.nside - s;
+        ip = 4 * s - (q - 2 * s * (s - 1));
+    }
+}
+
+__device__ __forceinline__ void pix2vec(const Hpx &h, i64 pix, double &x, double &y, double &z) {
+    i64 ring, ip, start, nr;
+    bool shifted;
+    pix2ring(h, pix, ring, ip);
+    ring_info(h, ring, start, nr, shifted);
+    double sth;
+    ring_z_sth(h, ring, z, sth);
+    double s, c;
+    sincos(ring_phi(h, ring, ip, shifted), &s, &c);
+    x = sth * c;
+    y = sth * s;
+}
+
+// The rings a non-inclusive disc touches (query_disc_internal with fact = 0).
+struct DiscRings {
+    i64 irmin, irmax;  // rings that need the per-ring azimuth test
+    i64 ra, rb;        // full iteration range; rings in [ra, irmin) and (irmax, rb] are taken whole (pole inside)
+    double z0, xa, cosr, phi0;
+    bool all_sky;
+};
+
+__device__ __forceinline__ DiscRings disc_rings(const Hpx &h, double theta, double phi, double radius) {
+    DiscRings d;
+    d.phi0 = phi;
+    d.all_sky = false;
+    if (radius >= BFG_PI) {
+        d.all_sky = true;
+        d.ra = 1; d.rb = 4 * h.nside - 1; d.irmin = d.rb + 1; d.irmax = d.rb;
+        d.z0 = d.xa = d.cosr = 0;
+        return d;
+    }
+    d.cosr = cos(radius);
+    d.z0 = cos(theta);
+    d.xa = 1.0 / sqrt((1.0 - d.z0) * (1.0 + d.z0));
+    double rlat1 = theta - radius;
+    d.irmin = ring_above(h, cos(rlat1)) + 1;
+    d.ra = d.irmin;
+    if (rlat1 <= 0 && d.irmin > 1) d.ra = 1;
+    double rlat2 = theta + radius;
+    d.irmax = ring_above(h, cos(rlat2));
+    d.rb = d.irmax;
+    if (rlat2 >= BFG_PI && d.irmax + 1 < 4 * h.nside) d.rb = 4 * h.nside - 1;
+    return d;
+}
+
+// Pixels of ring `iz` inside the disc: in-ring indices (ip_lo + i) mod nr for i in [0, cnt).
+__device__ __forceinline__ void disc_ring_span(const Hpx &h, const DiscRings &d, i64 iz, i64 &start, i64 &nr,
+                                               bool &shifted, i64 &ip_lo, i64 &cnt) {
+    ring_info(h, iz, start, nr, shifted);
+    if (iz < d.irmin || iz > d.irmax) { ip_lo = 0; cnt = nr; return; }
+    double z = ring2z(h, iz);
+    double x = (d.cosr - z * d.z0) * d.xa;
+    double ysq = 1.0 - z * z - x * x;
+    cnt = 0; ip_lo = 0;
+    if (ysq <= 0) return;
+    double dphi = atan2(sqrt(ysq), x);
+    if (!(dphi > 0)) return;
+    double shift = shifted ? 0.5 : 0.0;
+    i64 lo = (i64)floor((double)nr * BFG_INV_TWOPI * (d.phi0 - dphi) - shift) + 1;
+    i64 hi = (i64)floor((double)nr * BFG_INV_TWOPI * (d.phi0 + dphi) - shift);
+    if (hi >= nr) { lo -= nr; hi -= nr; }
+    i64 c = hi - lo + 1;
+    if (c <= 0) return;
+    if (c > nr) c = nr;  // rangeset::append would have merged the overlap
+    if (lo < 0) lo += nr;
+    ip_lo = lo;
+    cnt = c;
+}
+
+// get_interpol: 4 neighbour pixels + bilinear weights of a direction (theta, phi)
+__device__ __forceinline__ void ring_theta_info(const Hpx &h, i64 ring, i64 &start, i64 &nr, double &theta, bool &shifted) {
+    i64 nring = (ring > 2 * h.nside) ? 4 * h.nside - ring : ring;
+    if (nring < h.nside) {
+        double tmp = (double)(nring * nring) * h.fact2;
+        theta = atan2(sqrt(tmp * (2.0 - tmp)), 1.0 - tmp);
+        nr = 4 * nring; shifted = true; start = 2 * nring * (nring - 1);
+    } else {
+        theta = acos((double)(2 * h.nside - nring) * h.fact1);
+        nr = h.nl4; shifted = ((nring - h.nside) & 1) == 0; start = h.ncap + (nring - h.nside) * nr;
+    }
+    if (nring != ring) { theta = BFG_PI - theta; start = h.npix - start - nr; }
+}
+
+__device__ __forceinline__ void ring_pair(i64 nr, bool shifted, i64 start, double phi, i64 &p0, i64 &p1, double &w1) {
+    double dphi = BFG_TWOPI / (double)nr;
+    double sh = shifted ? 0.5 : 0.0;
+    double tmp = phi / dphi - sh;
+    i64 i1 = (tmp < 0) ? (i64)tmp - 1 : (i64)tmp;
+    w1 = (phi - ((double)i1 + sh) * dphi) / dphi;
+    i64 i2 = i1 + 1;
+    if (i1 < 0) i1 += nr;
+    if (i2 >= nr) i2 -= nr;
+    p0 = start + i1;
+    p1 = start + i2;
+}
+
+__device__ __forceinline__ void get_interpol(const Hpx &h, double theta, double phi, i64 pix[4], double w[4]) {
+    double z = cos(theta);
+    i64 ir1 = ring_above(h, z), ir2 = ir1 + 1;
+    double th1 = 0, th2 = 0, w1;
+    i64 sp, nr;
+    bool sh;
+    pix[0] = pix[1] = pix[2] = pix[3] = 0;
+    w[0] = w[1] = w[2] = w[3] = 0;
+    if (ir1 > 0) {
+        ring_theta_info(h, ir1, sp, nr, th1, sh);
+        ring_pair(nr, sh, sp, phi, pix[0], pix[1], w1);
+        w[0] = 1.0 - w1; w[1] = w1;
+    }
+    if (ir2 < 4 * h.nside) {
+        ring_theta_info(h, ir2, sp, nr, th2, sh);
+        ring_pair(nr, sh, sp, phi, pix[2], pix[3], w1);
+        w[2] = 1.0 - w1; w[3] = w1;
+    }
+    if (ir1 == 0) {
+        double wt = theta / th2;
+        w[2] *= wt; w[3] *= wt;
+        double fac = (1.0 - wt) * 0.25;
+        w[0] = fac; w[1] = fac; w[2] += fac; w[3] += fac;
+        pix[0] = (pix[2] + 2) & 3;
+        pix[1] = (pix[3] + 2) & 3;
+    } else if (ir2 == 4 * h.nside) {
+        double wt = (theta - th1) / (BFG_PI - th1);
+        w[0] *= 1.0 - wt; w[1] *= 1.0 - wt;
+        double fac = wt * 0.25;
+        w[0] += fac; w[1] += fac; w[2] = fac; w[3] = fac;
+        pix[2] = ((pix[0] + 2) & 3) + h.npix - 4;
+        pix[3] = ((pix[1] + 2) & 3) + h.npix - 4;
+    } else {
+        double wt = (theta - th1) / (th2 - th1);
+        w[0] *= 1.0 - wt; w[1] *= 1.0 - wt;
+        w[2] *= wt; w[3] *= wt;
+    }
+}
+
+__device__ __forceinline__ double fmodulo(double v1, double v2) {
+    if (v1 >= 0) return (v1 < v2) ? v1 : fmod(v1, v2);
+    double tmp = fmod(v1, v2) + v2;
+    return (tmp == v2) ? 0.0 : tmp;
+}
+
+__device__ __forceinline__ i64 ang2pix_ring(const Hpx &h, double theta, double phi) {
+    double z = cos(theta);
+    bool have_sth = (theta < 0.01) || (theta > 3.14159 - 0.01);
+    double sth = have_sth ? sin(theta) : 0.0;
+    double za = fabs(z);
+    double tt = fmodulo(phi * BFG_INV_HALFPI, 4.0);
+    if (za <= BFG_TWOTHIRD) {
+        double t1 = (double)h.nside * (0.5 + tt), t2 = (double)h.nside * z * 0.75;
+        i64 jp = (i64)(t1 - t2), jm = (i64)(t1 + t2);
+        i64 ir = h.nside + 1 + jp - jm;
+        i64 ks = 1 - (ir & 1);
+        i64 q = jp + jm - h.nside + ks + 1 + h.nl4 + h.nl4;
+        i64 ip = (q >> 1) % h.nl4;
+        return h.ncap + (ir - 1) * h.nl4 + ip;
+    }
+    double tp = tt - (double)(i64)tt;
+    double tmp = ((za < 0.99) || !have_sth) ? (double)h.nside * sqrt(3.0 * (1.0 - za))
+                                            : (double)h.nside * sth / sqrt((1.0 + za) / 3.0);
+    i64 jp = (i64)(tp * tmp), jm = (i64)((1.0 - tp) * tmp);
+    i64 ir = jp + jm + 1;
+    i64 ip = (i64)(tt * (double)ir);
+    return (z > 0) ? 2 * ir * (ir - 1) + ip : h.npix - 2 * ir * (ir + 1) + ip;
+}
+
+// fp64 RED (no return value): RED.E.ADD.F64 on sm_100a
+__device__ __forceinline__ void red_add(double *addr, double v) { atomicAdd(addr, v); }
+
+__device__ __forceinline__ double warp_sum(double v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ i64 warp_sum_i64(i64 v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace bfg

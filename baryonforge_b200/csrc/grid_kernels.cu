@@ -1,0 +1,232 @@
+// grid_kernels.cu -- periodic 2-D / 3-D grid runners on sm_100a.
+//
+//   k_grid_halos<PAINT>  : halo loop of BaryonifyGrid.process     (BaryonForge/Runners/Map2DRunner.py:482-586)
+//                          and PaintProfilesGrid.process          (BaryonForge/Runners/Map2DRunner.py:725-821)
+//   k_grid_regrid        : re-binning                             (BaryonForge/Runners/Map2DRunner.py:589-613, :13-162)
+//
+// One CTA per halo; the cutout is walked with the last array axis fastest so a warp's REDs are contiguous.
+// The reference's coordinate conventions are kept literally:
+//   * cutout coordinates  x[i] = linspace(-Nsize/2, Nsize/2, Nsize)[i] * res   (stretched by Nsize/(Nsize-1))
+//   * meshgrid(indexing='xy'): element (i, j, k) of the cutout -- array axes 0, 1, 2 -- has
+//       gx = x[j] + dx,  gy = x[i] + dy,  gz = x[k] + dz        with dx = bins[x_cen] - x_j, ...
+//     and component 0 of the offset is gx/r, component 1 is gy/r.
+#include <algorithm>
+#include "bfg_common.cuh"
+
+using namespace bfg;
+
+namespace {
+
+constexpr int GRID_THREADS = 128;
+
+struct HaloBox {
+    double rq, lnz, lnM, rcut, lnRcom, d[3], paintcut;
+    int nsize, cen[3];
+};
+
+__device__ __forceinline__ HaloBox load_box(const double *__restrict__ H) {
+    HaloBox b;
+    b.rq = __ldg(H + BFG_HB_RQ);
+    b.nsize = (int)__ldg(H + BFG_HB_NSIZE);
+    b.cen[0] = (int)__ldg(H + BFG_HB_CX); b.cen[1] = (int)__ldg(H + BFG_HB_CY); b.cen[2] = (int)__ldg(H + BFG_HB_CZ);
+    b.lnz = __ldg(H + BFG_HB_LNZ); b.lnM = __ldg(H + BFG_HB_LNM);
+    b.rcut = __ldg(H + BFG_HB_RCUT); b.lnRcom = __ldg(H + BFG_HB_LNRCOM);
+    b.d[0] = __ldg(H + BFG_HB_DX); b.d[1] = __ldg(H + BFG_HB_DY); b.d[2] = __ldg(H + BFG_HB_DZ);
+    b.paintcut = __ldg(H + BFG_HB_PAINTCUT);
+    return b;
+}
+
+// np.linspace(-Ns/2, Ns/2, Ns)[i] * res, same operation order as numpy (arange*step + start, last = stop)
+__device__ __forceinline__ double cut_coord(int i, int ns, double res) {
+    double start = -0.5 * (double)ns, stop = 0.5 * (double)ns;
+    double step = (stop - start) / (double)(ns - 1);
+    double y = (i == ns - 1) ? stop : __dadd_rn(__dmul_rn((double)i, step), start);
+    return y * res;
+}
+
+__device__ __forceinline__ int wrap_idx(int c, int N) {   // pick_indices, Map2DRunner.py:400-429
+    if (c < 0) c += N;
+    if (c >= N) c -= N;
+    return c;
+}
+
+template <bool PAINT, bool UNIFORM, int NDIM>
+__global__ void __launch_bounds__(GRID_THREADS)
+k_grid_halos(TableView T, int N, double res, double scale, i64 n_halo, const double *__restrict__ halos,
+             const double *__restrict__ extras, int n_extra, double *__restrict__ out, int plane_lo, int plane_hi,
+             unsigned long long *nupd) {
+    extern __shared__ double row[];
+    const i64 plane = (NDIM == 3) ? (i64)N * N : (i64)N;       // cells per axis-0 plane
+    const i64 nloc = (i64)(plane_hi - plane_lo) * plane;
+    const double inv_res = 1.0 / res;
+    i64 done = 0;
+    for (i64 h = blockIdx.x; h < n_halo; h += gridDim.x) {
+        const HaloBox b = load_box(halos + h * BFG_HALO_STRIDE);
+        __syncthreads();
+        bool valid;
+        blend_row(T, b.lnz, b.lnM, extras ? extras + h * n_extra : nullptr, row, valid);
+        __syncthreads();
+        const int ns = b.nsize, cw = ns / 2;
+        const i64 inner = (NDIM == 3) ? (i64)ns * ns : (i64)ns;   // elements per axis-0 index
+        const i64 total = inner * ns;
+        for (i64 e = threadIdx.x; e < total; e += GRID_THREADS) {
+            int i = (int)(e / inner);
+            int rem = (int)(e - (i64)i * inner);
+            int j = (NDIM == 3) ? rem / ns : rem;
+            int k = (NDIM == 3) ? rem - j * ns : 0;
+            int c0 = wrap_idx(b.cen[0] - cw + i, N);
+            if (c0 < plane_lo || c0 >= plane_hi) continue;
+            int c1 = wrap_idx(b.cen[1] - cw + j, N);
+            int c2 = (NDIM == 3) ? wrap_idx(b.cen[2] - cw + k, N) : 0;
+            i64 cell = (NDIM == 3) ? ((i64)(c0 - plane_lo) * N + c1) * N + c2 : (i64)(c0 - plane_lo) * N + c1;
+            double gx = cut_coord(j, ns, res) + b.d[0];          // Map2DRunner.py:524-528 / :561-566
+            double gy = cut_coord(i, ns, res) + b.d[1];
+            double gz = (NDIM == 3) ? cut_coord(k, ns, res) + b.d[2] : 0.0;
+            double r = (NDIM == 3) ? sqrt(gx * gx + gy * gy + gz * gz) : sqrt(gx * gx + gy * gy);
+            double xq = log(r);
+            if (T.flags & BFG_TABLE_RDELTA) xq -= b.lnRcom;
+            double val = row_lookup<UNIFORM>(T, row, xq);
+            if (!valid) val = CUDART_NAN;
+            ++done;
+            if (PAINT) {
+                val = exp(val);                                  // Tabulate.py:319
+                if (!isfinite(val) || !(r < b.paintcut)) continue;   // Map2DRunner.py:814-818
+                val *= scale;                                    // :825 folded in
+                if (val != 0.0) red_add(out + cell, val);
+            } else {
+                val = (r < b.rcut) ? val : 0.0;                  // BaryonCorrection.py:410-411
+                double off = val * inv_res;                      // Map2DRunner.py:540/:583  (/ res)
+                if (off == 0.0 && r > 0.0) continue;             // adds exact zeros
+                red_add(out + cell, off * (gx / r));             // NaNs propagate (cleaned after the loop, :597/:607)
+                red_add(out + nloc + cell, off * (gy / r));
+                if (NDIM == 3) red_add(out + 2 * nloc + cell, off * (gz / r));
+            }
+        }
+    }
+    if (nupd) {
+        done = warp_sum_i64(done);
+        if ((threadIdx.x & 31) == 0 && done) atomicAdd(nupd, (unsigned long long)done);
+    }
+}
+
+// Python float modulo for a positive modulus
+__device__ __forceinline__ double pymod(double x, double n) {
+    double r = fmod(x, n);
+    if (r != 0.0 && r < 0.0) r += n;
+    return r;
+}
+
+// One axis of regrid_pixels_2D/3D: the two cells that overlap [xs, xs+1) and their overlap lengths.
+__device__ __forceinline__ void axis_deposit(double pos, int N, int c[2], double w[2]) {
+    double xs = pymod(pos, (double)N);
+    int f = (int)xs;                       // xs >= 0
+    double fp1 = (double)(f + 1);
+    w[0] = fp1 - xs;                       // min(f+1, xs+1) - max(f, xs)
+    w[1] = (xs + 1.0) - fp1;               // min(f+2, xs+1) - max(f+1, xs)
+    c[0] = f % N;
+    c[1] = (f + 1) % N;
+}
+
+template <int NDIM>
+__global__ void __launch_bounds__(256)
+k_grid_regrid(int N, const double *__restrict__ map_in, const double *__restrict__ off, double *__restrict__ map_out,
+              int plane_lo, int plane_hi) {
+    const i64 plane = (NDIM == 3) ? (i64)N * N : (i64)N;
+    const i64 nloc = (i64)(plane_hi - plane_lo) * plane;
+    for (i64 c = (i64)blockIdx.x * blockDim.x + threadIdx.x; c < nloc; c += (i64)gridDim.x * blockDim.x) {
+        double m = map_in[c];
+        int a0 = (int)(c / plane) + plane_lo;
+        i64 rem = c - (i64)(a0 - plane_lo) * plane;
+        int a1 = (NDIM == 3) ? (int)(rem / N) : (int)rem;
+        int a2 = (NDIM == 3) ? (int)(rem - (i64)a1 * N) : 0;
+        double o0 = off[c], o1 = off[nloc + c], o2 = (NDIM == 3) ? off[2 * nloc + c] : 0.0;
+        if (!isfinite(o0)) o0 = 0.0;       // Map2DRunner.py:597/:607, element-wise on the accumulated array
+        if (!isfinite(o1)) o1 = 0.0;
+        if (!isfinite(o2)) o2 = 0.0;
+        // xy-meshgrid: component 0 rides on array axis 1, component 1 on axis 0   (:595-599, :605-610)
+        int cx[2], cy[2], cz[2];
+        double wx[2], wy[2], wz[2];
+        axis_deposit(o0 + (double)a1, N, cx, wx);
+        axis_deposit(o1 + (double)a0, N, cy, wy);
+        if (NDIM == 3) axis_deposit(o2 + (double)a2, N, cz, wz);
+#pragma unroll
+        for (int iy = 0; iy < 2; ++iy) {
+            if (!(wy[iy] > 0)) continue;
+#pragma unroll
+            for (int ix = 0; ix < 2; ++ix) {
+                if (!(wx[ix] > 0)) continue;
+                if (NDIM == 2) {
+                    red_add(map_out + (i64)cy[iy] * N + cx[ix], (wx[ix] * wy[iy]) * m);       // grid[i=y, j=x]  :79-82
+                } else {
+#pragma unroll
+                    for (int iz = 0; iz < 2; ++iz) {
+                        if (!(wz[iz] > 0)) continue;
+                        red_add(map_out + ((i64)cy[iy] * N + cx[ix]) * N + cz[iz], ((wx[ix] * wy[iy]) * wz[iz]) * m);  // :158-162
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <bool PAINT>
+int launch_grid(const bfg_table *t, int ndim, i64 N, double res, double scale, i64 n_halo, const double *d_halos,
+                const double *d_extras, int n_extra, double *d_out, i64 plane_lo, i64 plane_hi, i64 *d_nupdates,
+                cudaStream_t st) {
+    BFG_REQUIRE(t && d_halos && d_out, "null argument");
+    BFG_REQUIRE(ndim == 2 || ndim == 3, "ndim must be 2 or 3");
+    BFG_REQUIRE(N >= 4 && N <= 32768, "N out of range (need 4 <= N <= 32768)");
+    BFG_REQUIRE(plane_lo >= 0 && plane_hi <= N && plane_lo <= plane_hi, "bad plane range");
+    BFG_REQUIRE(n_extra == t->view.ndim - 3, "n_extra must equal the table's extra axes");
+    BFG_REQUIRE(n_extra == 0 || d_extras, "extras missing");
+    BFG_REQUIRE(PAINT == ((t->view.flags & BFG_TABLE_LOG_VALUES) != 0),
+                "paint needs a log-profile table, baryonify a displacement table");
+    if (d_nupdates) BFG_CUDA_OK(cudaMemsetAsync(d_nupdates, 0, sizeof(i64), st));
+    if (n_halo == 0 || plane_lo == plane_hi) return BFG_OK;
+    size_t smem = sizeof(double) * t->view.n[2];
+    BFG_REQUIRE(smem <= 200 * 1024, "radial axis too long for the shared-memory row (max 25600 nodes)");
+    int blocks = (int)std::min<i64>(n_halo, (i64)1 << 30);
+    auto go = [&](auto kern) -> int {
+        BFG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<blocks, GRID_THREADS, smem, st>>>(t->view, (int)N, res, scale, n_halo, d_halos, d_extras, n_extra, d_out,
+                                                 (int)plane_lo, (int)plane_hi, (unsigned long long *)d_nupdates);
+        BFG_CUDA_OK(cudaGetLastError());
+        return BFG_OK;
+    };
+    const bool u = t->view.uniform_r != 0;
+    if (ndim == 3) return u ? go(k_grid_halos<PAINT, true, 3>) : go(k_grid_halos<PAINT, false, 3>);
+    return u ? go(k_grid_halos<PAINT, true, 2>) : go(k_grid_halos<PAINT, false, 2>);
+}
+
+}  // namespace
+
+extern "C" int bfg_grid_offsets(const bfg_table *t, int ndim, int64_t N, double res, int64_t n_halo,
+                                const double *d_halos, const double *d_extras, int n_extra, double *d_offsets,
+                                int64_t plane_lo, int64_t plane_hi, int64_t *d_nupdates, void *stream) {
+    return launch_grid<false>(t, ndim, N, res, 1.0, n_halo, d_halos, d_extras, n_extra, d_offsets, plane_lo, plane_hi,
+                              (i64 *)d_nupdates, (cudaStream_t)stream);
+}
+
+extern "C" int bfg_grid_paint(const bfg_table *t, int ndim, int64_t N, double res, double scale, int64_t n_halo,
+                              const double *d_halos, const double *d_extras, int n_extra, double *d_map,
+                              int64_t plane_lo, int64_t plane_hi, int64_t *d_nupdates, void *stream) {
+    return launch_grid<true>(t, ndim, N, res, scale, n_halo, d_halos, d_extras, n_extra, d_map, plane_lo, plane_hi,
+                             (i64 *)d_nupdates, (cudaStream_t)stream);
+}
+
+extern "C" int bfg_grid_regrid(int ndim, int64_t N, const double *d_map_in, const double *d_offsets, double *d_map_out,
+                               int64_t plane_lo, int64_t plane_hi, void *stream) {
+    BFG_REQUIRE(d_map_in && d_offsets && d_map_out, "null argument");
+    BFG_REQUIRE(ndim == 2 || ndim == 3, "ndim must be 2 or 3");
+    BFG_REQUIRE(N >= 4 && N <= 32768, "N out of range (need 4 <= N <= 32768)");
+    BFG_REQUIRE(plane_lo >= 0 && plane_hi <= N && plane_lo <= plane_hi, "bad plane range");
+    if (plane_lo == plane_hi) return BFG_OK;
+    i64 nloc = (plane_hi - plane_lo) * (ndim == 3 ? N * N : N);
+    int blocks = (int)std::max<i64>(1, std::min<i64>((nloc + 255) / 256, 148 * 32));
+    if (ndim == 3)
+        k_grid_regrid<3><<<blocks, 256, 0, (cudaStream_t)stream>>>((int)N, d_map_in, d_offsets, d_map_out, (int)plane_lo, (int)plane_hi);
+    else
+        k_grid_regrid<2><<<blocks, 256, 0, (cudaStream_t)stream>>>((int)N, d_map_in, d_offsets, d_map_out, (int)plane_lo, (int)plane_hi);
+    BFG_CUDA_OK(cudaGetLastError());
+    return BFG_OK;
+}

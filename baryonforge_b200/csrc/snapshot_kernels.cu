@@ -1,0 +1,282 @@
+// snapshot_kernels.cu -- particle-snapshot baryonification on sm_100a.
+//
+//   bfg_snap_build_cells : periodic cell list + cell-sorted particle copies; replaces the scipy KDTree built in
+//                          DefaultRunnerSnapshot.__init__ (BaryonForge/Runners/SnapshotRunner.py:95-100)
+//   k_snap_halos         : halo loop of BaryonifySnapshot.process (SnapshotRunner.py:217-260): ball query
+//                          (d <= R_q, periodic, inclusive like query_ball_point), minimum-image separation
+//                          (:103-158), table read-out, accumulate per-particle offsets
+//   k_snap_apply         : add offsets, single wrap (:263-273), un-permute to the caller's particle order
+//   k_deposit_ngp        : ParticleSnapshot.make_map == np.histogramdd NGP mass deposit (BaryonForge/utils/io.py:629-677)
+//
+// Particles are physically re-ordered by cell (counting sort), so that for a fixed (cx, cy) the run of z-cells a
+// halo touches is ONE contiguous range of the sorted arrays: lanes read consecutive particles (coalesced 8-byte
+// loads) and their REDs land on consecutive addresses of the cell-ordered offset array.
+#include <algorithm>
+#include <cub/device/device_scan.cuh>
+#include "bfg_common.cuh"
+
+using namespace bfg;
+
+namespace {
+
+constexpr int SNAP_THREADS = 128;
+
+__device__ __forceinline__ int cell_of(double x, double L, int nc) {
+    int c = (int)floor(x / L * (double)nc);
+    return min(max(c, 0), nc - 1);
+}
+
+template <int NDIM>
+__global__ void k_cell_count(i64 n, const double *__restrict__ x, const double *__restrict__ y,
+                             const double *__restrict__ z, double L, int nc, int *__restrict__ cell_id,
+                             unsigned long long *__restrict__ counts) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        int c = cell_of(x[i], L, nc) * nc + cell_of(y[i], L, nc);
+        if (NDIM == 3) c = c * nc + cell_of(z[i], L, nc);
+        cell_id[i] = c;
+        atomicAdd(counts + c, 1ULL);
+    }
+}
+
+template <int NDIM>
+__global__ void k_cell_fill(i64 n, const double *__restrict__ x, const double *__restrict__ y,
+                            const double *__restrict__ z, const int *__restrict__ cell_id,
+                            const i64 *__restrict__ cell_start, unsigned long long *__restrict__ cursor,
+                            i64 *__restrict__ order, double *__restrict__ xs, double *__restrict__ ys,
+                            double *__restrict__ zs) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        int c = cell_id[i];
+        i64 slot = cell_start[c] + (i64)atomicAdd(cursor + c, 1ULL);
+        order[slot] = i;
+        xs[slot] = x[i];
+        ys[slot] = y[i];
+        if (NDIM == 3) zs[slot] = z[i];
+    }
+}
+
+// SnapshotRunner.py:135-158 enforce_periodicity
+__device__ __forceinline__ double min_image(double dx, double L) {
+    if (dx > 0.5 * L) dx -= L;
+    if (dx < -0.5 * L) dx += L;
+    return dx;
+}
+
+struct HaloSnap {
+    double c[3], rq, lnz, lnM, rcut, lnRcom;
+};
+
+template <bool UNIFORM, int NDIM>
+__global__ void __launch_bounds__(SNAP_THREADS)
+k_snap_halos(TableView T, double L, int nc, const double *__restrict__ xs, const double *__restrict__ ys,
+             const double *__restrict__ zs, const i64 *__restrict__ cell_start, i64 n_part, i64 n_halo,
+             const double *__restrict__ halos, const double *__restrict__ extras, int n_extra,
+             double *__restrict__ tot, unsigned long long *npairs) {
+    extern __shared__ double row[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int NW = SNAP_THREADS / 32;
+    const double cell = L / (double)nc;
+    i64 done = 0;
+    for (i64 h = blockIdx.x; h < n_halo; h += gridDim.x) {
+        const double *H = halos + h * BFG_HALO_STRIDE;
+        HaloSnap s;
+        s.c[0] = __ldg(H + BFG_HB_X); s.c[1] = __ldg(H + BFG_HB_Y); s.c[2] = __ldg(H + BFG_HB_Z);
+        s.rq = __ldg(H + BFG_HB_RQ); s.lnz = __ldg(H + BFG_HB_LNZ); s.lnM = __ldg(H + BFG_HB_LNM);
+        s.rcut = __ldg(H + BFG_HB_RCUT); s.lnRcom = __ldg(H + BFG_HB_LNRCOM);
+        __syncthreads();
+        bool valid;
+        blend_row(T, s.lnz, s.lnM, extras ? extras + h * n_extra : nullptr, row, valid);
+        __syncthreads();
+        // cells covering [c - rq, c + rq] per axis (periodic); never more than nc of them
+        int lo[3], cnt[3];
+        for (int d = 0; d < 3; ++d) {
+            if (d >= NDIM) { lo[d] = 0; cnt[d] = 1; continue; }
+            int a = (int)floor((s.c[d] - s.rq) / cell), b = (int)floor((s.c[d] + s.rq) / cell);
+            int c = b - a + 1;
+            if (c >= nc) { a = 0; c = nc; }
+            lo[d] = a; cnt[d] = c;
+        }
+        const int last = NDIM - 1;                 // fastest-varying cell axis: runs along it are contiguous
+        const int nouter = (NDIM == 3) ? cnt[0] * cnt[1] : cnt[0];
+        // the run along the last axis, split where it wraps around the box
+        int z0 = ((lo[last] % nc) + nc) % nc;
+        int len0 = min(cnt[last], nc - z0), len1 = cnt[last] - len0;
+        for (int o = warp; o < nouter * 2; o += NW) {
+            int seg = o & 1, oo = o >> 1;
+            int zlo = seg ? 0 : z0, zlen = seg ? len1 : len0;
+            if (zlen <= 0) continue;
+            int cx = (NDIM == 3) ? oo / cnt[1] : oo;
+            int cy = (NDIM == 3) ? oo - cx * cnt[1] : 0;
+            int gx = (((lo[0] + cx) % nc) + nc) % nc;
+            i64 cbase;
+            if (NDIM == 3) {
+                int gy = (((lo[1] + cy) % nc) + nc) % nc;
+                cbase = ((i64)gx * nc + gy) * nc;
+            } else {
+                cbase = 0; zlo = seg ? 0 : z0;
+                // 2-D: the "last axis" is y; runs are over y for fixed x
+                cbase = (i64)gx * nc;
+            }
+            i64 p0 = cell_start[cbase + zlo], p1 = cell_start[cbase + zlo + zlen];
+            for (i64 p = p0 + lane; p < p1; p += 32) {
+                double dx = min_image(xs[p] - s.c[0], L);      // SnapshotRunner.py:248-251 / :103-132
+                double dy = min_image(ys[p] - s.c[1], L);
+                double dz = (NDIM == 3) ? min_image(zs[p] - s.c[2], L) : 0.0;
+                double d = (NDIM == 3) ? sqrt(dx * dx + dy * dy + dz * dz) : sqrt(dx * dx + dy * dy);
+                if (!(d <= s.rq)) continue;                    // query_ball_point: inclusive  (:232/:247)
+                ++done;
+                double xq = log(d);
+                if (T.flags & BFG_TABLE_RDELTA) xq -= s.lnRcom;
+                double val = row_lookup<UNIFORM>(T, row, xq);
+                if (!valid) val = CUDART_NAN;
+                val = (d < s.rcut) ? val : 0.0;                // BaryonCorrection.py:410-411
+                if (!isfinite(val)) val = 0.0;                 // SnapshotRunner.py:259
+                if (val == 0.0 && d > 0.0) continue;           // adds exact zeros
+                red_add(tot + p, val * (dx / d));              // :260 ; d == 0 -> NaN, as in the reference (§10 #11)
+                red_add(tot + n_part + p, val * (dy / d));
+                if (NDIM == 3) red_add(tot + 2 * n_part + p, val * (dz / d));
+            }
+        }
+    }
+    if (npairs) {
+        done = warp_sum_i64(done);
+        if (lane == 0 && done) atomicAdd(npairs, (unsigned long long)done);
+    }
+}
+
+__device__ __forceinline__ double wrap_once(double q, double L) {   // SnapshotRunner.py:272-273
+    if (q > L) q -= L;
+    if (q < 0) q += L;
+    return q;
+}
+
+template <int NDIM>
+__global__ void k_snap_apply(i64 n, const double *__restrict__ xs, const double *__restrict__ ys,
+                             const double *__restrict__ zs, const double *__restrict__ tot,
+                             const i64 *__restrict__ order, double L, double *__restrict__ xo, double *__restrict__ yo,
+                             double *__restrict__ zo) {
+    for (i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (i64)gridDim.x * blockDim.x) {
+        i64 i = order[p];
+        xo[i] = wrap_once(xs[p] + tot[p], L);
+        yo[i] = wrap_once(ys[p] + tot[n + p], L);
+        if (NDIM == 3) zo[i] = wrap_once(zs[p] + tot[2 * n + p], L);
+    }
+}
+
+// np.histogramdd bin of x on edges = np.linspace(0, L, N+1): searchsorted(side='right') - 1, x == L -> last bin
+__device__ __forceinline__ i64 ngp_bin(double x, double L, i64 N, double step) {
+    if (!(x >= 0.0) || !(x <= L)) return -1;
+    if (x == L) return N - 1;
+    i64 i = (i64)(x / step);
+    if (i > N - 1) i = N - 1;
+    // edge(i) = i*step as np.linspace computes it (arange*step), last edge exactly L
+    while (i > 0 && x < (double)i * step) --i;
+    while (i + 1 < N && x >= (double)(i + 1) * step) ++i;
+    return i;
+}
+
+template <int NDIM>
+__global__ void k_deposit_ngp(i64 n, const double *__restrict__ x, const double *__restrict__ y,
+                              const double *__restrict__ z, const double *__restrict__ m, double L, i64 N,
+                              double *__restrict__ grid) {
+    const double step = L / (double)N;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        i64 bx = ngp_bin(x[i], L, N, step), by = ngp_bin(y[i], L, N, step);
+        i64 bz = (NDIM == 3) ? ngp_bin(z[i], L, N, step) : 0;
+        if (bx < 0 || by < 0 || bz < 0) continue;
+        i64 c = (NDIM == 3) ? (bx * N + by) * N + bz : bx * N + by;
+        red_add(grid + c, m[i]);
+    }
+}
+
+int blocks_for(i64 n, int threads) { return (int)std::max<i64>(1, std::min<i64>((n + threads - 1) / threads, 148 * 32)); }
+
+}  // namespace
+
+extern "C" int bfg_snap_build_cells(int ndim, int64_t n_part, const double *d_x, const double *d_y, const double *d_z,
+                                    double L, int ncell, int64_t *d_cell_start, int64_t *d_order, double *d_xs,
+                                    double *d_ys, double *d_zs, void *stream) {
+    BFG_REQUIRE(ndim == 2 || ndim == 3, "ndim must be 2 or 3");
+    BFG_REQUIRE(d_x && d_y && (ndim == 2 || d_z) && d_cell_start && d_order && d_xs && d_ys && (ndim == 2 || d_zs), "null argument");
+    BFG_REQUIRE(ncell >= 1 && (ndim == 2 ? ncell <= 32768 : ncell <= 1024), "ncell out of range");
+    BFG_REQUIRE(L > 0, "L must be positive");
+    cudaStream_t st = (cudaStream_t)stream;
+    const i64 ncells = (ndim == 3) ? (i64)ncell * ncell * ncell : (i64)ncell * ncell;
+    int *cell_id = nullptr;
+    unsigned long long *counts = nullptr;
+    void *scan_tmp = nullptr;
+    size_t scan_bytes = 0;
+    BFG_CUDA_OK(cudaMallocAsync(&cell_id, sizeof(int) * std::max<i64>(n_part, 1), st));
+    BFG_CUDA_OK(cudaMallocAsync(&counts, sizeof(unsigned long long) * (ncells + 1), st));
+    BFG_CUDA_OK(cudaMemsetAsync(counts, 0, sizeof(unsigned long long) * (ncells + 1), st));
+    if (n_part > 0) {
+        if (ndim == 3) k_cell_count<3><<<blocks_for(n_part, 256), 256, 0, st>>>(n_part, d_x, d_y, d_z, L, ncell, cell_id, counts);
+        else k_cell_count<2><<<blocks_for(n_part, 256), 256, 0, st>>>(n_part, d_x, d_y, d_z, L, ncell, cell_id, counts);
+        BFG_CUDA_OK(cudaGetLastError());
+    }
+    BFG_CUDA_OK(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (const i64 *)counts, (i64 *)d_cell_start, ncells + 1, st));
+    BFG_CUDA_OK(cudaMallocAsync(&scan_tmp, scan_bytes, st));
+    BFG_CUDA_OK(cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, (const i64 *)counts, (i64 *)d_cell_start, ncells + 1, st));
+    BFG_CUDA_OK(cudaMemsetAsync(counts, 0, sizeof(unsigned long long) * (ncells + 1), st));
+    if (n_part > 0) {
+        if (ndim == 3) k_cell_fill<3><<<blocks_for(n_part, 256), 256, 0, st>>>(n_part, d_x, d_y, d_z, cell_id, (const i64 *)d_cell_start, counts, (i64 *)d_order, d_xs, d_ys, d_zs);
+        else k_cell_fill<2><<<blocks_for(n_part, 256), 256, 0, st>>>(n_part, d_x, d_y, d_z, cell_id, (const i64 *)d_cell_start, counts, (i64 *)d_order, d_xs, d_ys, d_zs);
+        BFG_CUDA_OK(cudaGetLastError());
+    }
+    BFG_CUDA_OK(cudaFreeAsync(scan_tmp, st));
+    BFG_CUDA_OK(cudaFreeAsync(counts, st));
+    BFG_CUDA_OK(cudaFreeAsync(cell_id, st));
+    return BFG_OK;
+}
+
+extern "C" int bfg_snap_offsets(const bfg_table *t, int ndim, int64_t n_part, const double *d_xs, const double *d_ys,
+                                const double *d_zs, double L, int ncell, const int64_t *d_cell_start, int64_t n_halo,
+                                const double *d_halos, const double *d_extras, int n_extra, double *d_tot,
+                                int64_t *d_npairs, void *stream) {
+    BFG_REQUIRE(t && d_xs && d_ys && (ndim == 2 || d_zs) && d_cell_start && d_tot && (d_halos || n_halo == 0), "null argument");
+    BFG_REQUIRE(ndim == 2 || ndim == 3, "ndim must be 2 or 3");
+    BFG_REQUIRE(n_extra == t->view.ndim - 3, "n_extra must equal the table's extra axes");
+    BFG_REQUIRE(n_extra == 0 || d_extras, "extras missing");
+    BFG_REQUIRE((t->view.flags & BFG_TABLE_LOG_VALUES) == 0, "snapshot baryonification needs a displacement table");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d_npairs) BFG_CUDA_OK(cudaMemsetAsync(d_npairs, 0, sizeof(i64), st));
+    if (n_halo == 0 || n_part == 0) return BFG_OK;
+    size_t smem = sizeof(double) * t->view.n[2];
+    BFG_REQUIRE(smem <= 200 * 1024, "radial axis too long for the shared-memory row (max 25600 nodes)");
+    int blocks = (int)std::min<i64>(n_halo, (i64)1 << 30);
+    auto go = [&](auto kern) -> int {
+        BFG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<blocks, SNAP_THREADS, smem, st>>>(t->view, L, ncell, d_xs, d_ys, d_zs, (const i64 *)d_cell_start, n_part, n_halo,
+                                                 d_halos, d_extras, n_extra, d_tot, (unsigned long long *)d_npairs);
+        BFG_CUDA_OK(cudaGetLastError());
+        return BFG_OK;
+    };
+    const bool u = t->view.uniform_r != 0;
+    if (ndim == 3) return u ? go(k_snap_halos<true, 3>) : go(k_snap_halos<false, 3>);
+    return u ? go(k_snap_halos<true, 2>) : go(k_snap_halos<false, 2>);
+}
+
+extern "C" int bfg_snap_apply(int ndim, int64_t n_part, const double *d_xs, const double *d_ys, const double *d_zs,
+                              const double *d_tot, const int64_t *d_order, double L, double *d_x_out, double *d_y_out,
+                              double *d_z_out, void *stream) {
+    BFG_REQUIRE(ndim == 2 || ndim == 3, "ndim must be 2 or 3");
+    BFG_REQUIRE(d_xs && d_ys && d_tot && d_order && d_x_out && d_y_out && (ndim == 2 || (d_zs && d_z_out)), "null argument");
+    if (n_part == 0) return BFG_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ndim == 3) k_snap_apply<3><<<blocks_for(n_part, 256), 256, 0, st>>>(n_part, d_xs, d_ys, d_zs, d_tot, (const i64 *)d_order, L, d_x_out, d_y_out, d_z_out);
+    else k_snap_apply<2><<<blocks_for(n_part, 256), 256, 0, st>>>(n_part, d_xs, d_ys, d_zs, d_tot, (const i64 *)d_order, L, d_x_out, d_y_out, d_z_out);
+    BFG_CUDA_OK(cudaGetLastError());
+    return BFG_OK;
+}
+
+extern "C" int bfg_snap_deposit_ngp(int ndim, int64_t n_part, const double *d_x, const double *d_y, const double *d_z,
+                                    const double *d_mass, double L, int64_t n_grid, double *d_grid, void *stream) {
+    BFG_REQUIRE(ndim == 2 || ndim == 3, "ndim must be 2 or 3");
+    BFG_REQUIRE(d_x && d_y && (ndim == 2 || d_z) && d_mass && d_grid, "null argument");
+    BFG_REQUIRE(n_grid >= 1 && L > 0, "bad grid");
+    if (n_part == 0) return BFG_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ndim == 3) k_deposit_ngp<3><<<blocks_for(n_part, 256), 256, 0, st>>>(n_part, d_x, d_y, d_z, d_mass, L, n_grid, d_grid);
+    else k_deposit_ngp<2><<<blocks_for(n_part, 256), 256, 0, st>>>(n_part, d_x, d_y, d_z, d_mass, L, n_grid, d_grid);
+    BFG_CUDA_OK(cudaGetLastError());
+    return BFG_OK;
+}

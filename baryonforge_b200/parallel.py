@@ -1,0 +1,138 @@
+"""
+Multi-GPU sharding of one map across the GPUs of a box -- the replacement for BaryonForge/utils/Parallelize.py
+(joblib/loky: SimpleParallel :8-113, SplitJoinParallel :116-320), SURVEY.md §8(e).
+
+One process per GPU (torch.distributed, NCCL over NVLink/NVSwitch):
+  * shells: the RING pixel index space is cut into `world` contiguous ranges of equal pixel count; rank r owns
+    pix_offsets[lo_r:hi_r].  Every halo whose disc touches a rank's rings is given to that rank (halo records are
+    128 B, so overlap halos are simply replicated) -- no communication in the halo loop.  The re-binning scatters
+    into a full-size partial map per rank; ONE all-reduce(sum, fp64) combines them (1.6 GB at NSIDE=4096).
+  * grids: the same with slabs of axis-0 planes.
+  * painting: each rank paints its own range; ranges are concatenated with all_gather.
+The reference can only split painting runs across halos and sums whole maps in the parent (Parallelize.py:318);
+results here are independent of the number of ranks up to fp64 summation order (§10 #14).
+"""
+import numpy as np
+
+__all__ = ['pixel_ranges', 'plane_ranges', 'ring_of_pixel', 'halos_touching_pixel_range', 'halos_touching_planes',
+           'reduce_partial_map', 'gather_owned_ranges', 'init_from_env']
+
+
+def pixel_ranges(nside, world):
+    """`world` contiguous RING ranges [lo, hi) of (nearly) equal pixel count covering the whole map."""
+    npix = 12 * nside * nside
+    edges = [(npix * r) // world for r in range(world + 1)]
+    return [(edges[r], edges[r + 1]) for r in range(world)]
+
+
+def plane_ranges(N, world):
+    edges = [(N * r) // world for r in range(world + 1)]
+    return [(edges[r], edges[r + 1]) for r in range(world)]
+
+
+def ring_of_pixel(nside, pix):
+    """Ring number (1 .. 4 nside - 1) of RING-ordered pixels (host copy of the device pix2ring)."""
+    pix = np.asarray(pix, dtype=np.int64)
+    npix, ncap = 12 * nside * nside, 2 * nside * (nside - 1)
+    ring = np.empty(pix.shape, dtype=np.int64)
+    north = pix < ncap
+    south = pix >= npix - ncap
+    eq = ~(north | south)
+    ring[north] = (1 + np.floor(np.sqrt(1 + 2 * pix[north] + 0.5)).astype(np.int64)) >> 1
+    ring[eq] = (pix[eq] - ncap) // (4 * nside) + nside
+    q = npix - pix[south]
+    ring[south] = 4 * nside - ((1 + np.floor(np.sqrt(2 * q - 1 + 0.5)).astype(np.int64)) >> 1)
+    return ring
+
+
+def _ring_z(nside, ring):
+    ring = np.asarray(ring, dtype=np.float64)
+    npix = 12.0 * nside * nside
+    f2 = 4.0 / npix
+    f1 = 2 * nside * f2
+    z = np.where(ring < nside, 1 - ring * ring * f2,
+                 np.where(ring <= 3 * nside, (2 * nside - ring) * f1, (4 * nside - ring) ** 2 * f2 - 1))
+    return z
+
+
+def halos_touching_pixel_range(nside, theta, radius, lo, hi, margin_rings=2):
+    """
+    Boolean mask of the halos whose disc (colatitude theta, angular radius) can contain a pixel of [lo, hi).
+    Conservative (a margin of rings each side): a halo given to a rank that owns none of its pixels costs only time.
+    """
+    if hi <= lo:
+        return np.zeros(np.shape(theta), dtype=bool)
+    r_top, r_bot = ring_of_pixel(nside, np.array([lo, hi - 1]))
+    r_top = max(1, int(r_top) - margin_rings)
+    r_bot = min(4 * nside - 1, int(r_bot) + margin_rings)
+    th_top = 0.0 if r_top == 1 else np.arccos(np.clip(_ring_z(nside, r_top), -1, 1))
+    th_bot = np.pi if r_bot == 4 * nside - 1 else np.arccos(np.clip(_ring_z(nside, r_bot), -1, 1))
+    theta, radius = np.asarray(theta), np.asarray(radius)
+    return (theta + radius >= th_top) & (theta - radius <= th_bot)
+
+
+def halos_touching_planes(N, centre, nsize, lo, hi):
+    """Mask of halos whose cutout [centre - nsize/2, centre + nsize/2) (periodic, axis 0) meets planes [lo, hi)."""
+    centre = np.asarray(centre, dtype=np.int64)
+    half = np.asarray(nsize, dtype=np.int64) // 2
+    start = centre - half
+    length = 2 * half
+    # distance from `start` forward (periodic) to the first owned plane
+    d = (lo - start) % N
+    return (d < length) | (((start - lo) % N) < (hi - lo))
+
+
+def init_from_env(backend=None):
+    """torch.distributed bootstrap from RANK / WORLD_SIZE / LOCAL_RANK / MASTER_* (torchrun)."""
+    import os
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29511")
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    elif torch.cuda.is_available():
+        torch.cuda.set_device(local)
+    return rank, world, local
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist if (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1) else None
+
+
+def reduce_partial_map(partial_full_map, owned_source_map):
+    """all-reduce(sum) of the per-rank partial full-size maps; also returns sum(original map) over all ranks."""
+    dist = _dist()
+    src_sum = owned_source_map.sum().reshape(1)
+    if dist is not None:
+        dist.all_reduce(partial_full_map, op=dist.ReduceOp.SUM)
+        dist.all_reduce(src_sum, op=dist.ReduceOp.SUM)
+    return partial_full_map, src_sum[0]
+
+
+def gather_owned_ranges(owned, total):
+    """Concatenate every rank's owned (contiguous, rank-ordered) slice into the full array on every rank."""
+    import torch
+    dist = _dist()
+    if dist is None:
+        assert owned.numel() == total
+        return owned
+    world = dist.get_world_size()
+    sizes = [torch.zeros(1, dtype=torch.int64, device=owned.device) for _ in range(world)]
+    dist.all_gather(sizes, torch.tensor([owned.numel()], dtype=torch.int64, device=owned.device))
+    sizes = [int(s.item()) for s in sizes]
+    assert sum(sizes) == total
+    pad = max(sizes)
+    buf = torch.zeros(pad, dtype=owned.dtype, device=owned.device)
+    buf[:owned.numel()] = owned
+    parts = [torch.empty(pad, dtype=owned.dtype, device=owned.device) for _ in range(world)]
+    dist.all_gather(parts, buf)
+    return torch.cat([p[:n] for p, n in zip(parts, sizes)])

@@ -1,0 +1,584 @@
+"""
+Runners: the drop-in mirror of BaryonForge/Runners (same class names, constructor signatures, attributes and
+process() return values), executing the per-halo loop and the re-binning on a B200 through libbfg_b200.so.
+
+    BaryonifyShell / PaintProfilesShell   <- BaryonForge/Runners/HealpixRunner.py:160-177, :252-373, :390-483
+    BaryonifyGrid / PaintProfilesGrid     <- BaryonForge/Runners/Map2DRunner.py:255-278, :431-621, :676-829
+    BaryonifySnapshot                     <- BaryonForge/Runners/SnapshotRunner.py:83-100, :176-274
+
+Host work per process(): the per-halo scalars the reference computes at the top of every loop iteration, done once
+with numpy (cosmology.py), packed into 128-byte halo records.  Everything per (halo, pixel|cell|particle) happens in
+CUDA.  PyTorch is used only for device memory, streams and (parallel.py) torch.distributed.
+There is no CPU fallback: without a GPU / the shared library, process() raises.
+"""
+import numpy as np
+
+from . import _lib, cosmology
+from .tables import displacement_table_of, profile_table_of
+
+__all__ = ['DefaultRunner', 'BaryonifyShell', 'PaintProfilesShell', 'DefaultRunnerGrid', 'BaryonifyGrid',
+           'PaintProfilesGrid', 'DefaultRunnerSnapshot', 'BaryonifySnapshot', 'deposit_ngp']
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise _lib.BFGError("baryonforge_b200 needs a CUDA device (B200); there is no CPU fallback")
+    return torch
+
+
+def _to_device(arr, device, dtype=None):
+    torch = _torch()
+    t = torch.from_numpy(np.ascontiguousarray(arr, dtype=dtype))
+    return t.to(device, non_blocking=True)
+
+
+def _check_keys(model, keys):
+    """HealpixRunner.py:304-311: p_keys need a table model that carries them."""
+    if len(keys) > 0 and not (hasattr(model, 'interp_d') or hasattr(model, 'interp2D')):
+        raise AssertionError(
+            f"You asked to use {keys} properties in Baryonification. You must pass a ParamTabulatedProfile "
+            f"or BaryonificationClass as the model. You have passed {type(model)} instead.")
+
+
+def _extras(cat, keys):
+    if len(keys) == 0:
+        return None
+    return np.ascontiguousarray(np.stack([np.asarray(cat[k], dtype=np.float64) for k in keys], axis=1))
+
+
+def _model_cosmo(model, fallback):
+    c = getattr(model, 'cosmo', None)
+    if c is None:
+        return fallback
+    if isinstance(c, dict):
+        return cosmology.runner_cosmology(c, True)
+    return c
+
+
+class _TableCache(object):
+    """Tables go to the device once per (model, table) and are re-used by later process() calls."""
+
+    def __init__(self):
+        self._key, self._table = None, None
+
+    def get(self, key, make):
+        if self._key != key:
+            if self._table is not None:
+                self._table.close()
+            self._table, self._key = make(), key
+        return self._table
+
+
+# =====================================================================================================================
+# HEALPix shells
+# =====================================================================================================================
+class DefaultRunner(object):
+    """Constructor contract of BaryonForge/Runners/HealpixRunner.py:160-177 (+ keyword-only GPU knobs)."""
+
+    def __init__(self, HaloLightConeCatalog, LightconeShell, epsilon_max, model, use_ellipticity=False,
+                 mass_def=None, include_pixel_size=False, verbose=True, *, device=None, pix_range=None):
+        self.HaloLightConeCatalog = HaloLightConeCatalog
+        self.LightconeShell = LightconeShell
+        self.cosmo = HaloLightConeCatalog.cosmology
+        self.model = model
+        self.epsilon_max = epsilon_max
+        self.mass_def = mass_def          # None == ccl.halos.massdef.MassDef(200, 'critical')
+        self.verbose = verbose
+        self.use_ellipticity = use_ellipticity
+        self.include_pixel_size = include_pixel_size
+        self.device = device
+        self.pix_range = pix_range        # (lo, hi) RING range owned by this rank (parallel.py); None = whole map
+        self.last_stats = {}
+        self._tables = _TableCache()
+        if use_ellipticity:
+            raise NotImplementedError("You have set use_ellipticity = True, but this not yet implemented for HealpixRunner")
+
+    # objects stay picklable for joblib-style drivers (utils/Parallelize.py:47-49)
+    def __getstate__(self):
+        d = dict(self.__dict__)
+        d['_tables'] = None
+        return d
+
+    def __setstate__(self, d):
+        self.__dict__.update(d)
+        self._tables = _TableCache()
+
+    def _device(self):
+        torch = _torch()
+        return torch.device('cuda', torch.cuda.current_device() if self.device is None else int(self.device))
+
+    def halo_records(self, paint):
+        """
+        The per-halo scalars of HealpixRunner.py:317-329 (+ BaryonCorrection.py:371,398-399,410), vectorised.
+        Returns (records[n,16] float64, extras[n,k] or None).
+        """
+        cat = self.HaloLightConeCatalog.cat
+        n = cat.size
+        cosmo = cosmology.runner_cosmology(self.cosmo, with_w0=True)          # :280-284
+        M, z = cat['M'], cat['z']
+        a = 1 / (1 + z)                                                        # :319
+        rec = np.zeros((n, _lib.HALO_STRIDE), dtype=np.float64)
+        if n == 0:
+            return rec, None
+        R = cosmology.radius_of_mass(cosmo, M, a, self.mass_def)               # :320 physical Mpc
+        D = cosmology.D_A_of_z(cosmo, z)                                       # :297-299,321
+        theta_ll, phi_ll = np.pi / 2.0 - np.radians(cat['dec']), np.radians(cat['ra'])   # healpy lonlat2thetaphi
+        st = np.sin(theta_ll)
+        vx, vy, vz = st * np.cos(phi_ll), st * np.sin(phi_ll), np.cos(theta_ll)          # hp.ang2vec :327
+        rec[:, _lib.HS_VX], rec[:, _lib.HS_VY], rec[:, _lib.HS_VZ] = vx, vy, vz
+        # pointing(vec) as healpy's query_disc wrapper builds it
+        rec[:, _lib.HS_THETA] = np.arctan2(np.sqrt(vx * vx + vy * vy), vz)
+        phi = np.arctan2(vy, vx)
+        rec[:, _lib.HS_PHI] = np.where(phi < 0, phi + 2 * np.pi, phi)
+        rec[:, _lib.HS_D] = D
+        rec[:, _lib.HS_A] = a
+        rec[:, _lib.HS_RADIUS] = R * self.epsilon_max / D                      # :329
+        rec[:, _lib.HS_LNZ] = np.log(1 / a)                                    # BaryonCorrection.py:371 / Tabulate.py:312
+        rec[:, _lib.HS_LNM] = np.log(M)                                        # BaryonCorrection.py:398 / Tabulate.py:317
+        if paint:
+            rec[:, _lib.HS_RCUT] = np.inf
+            pixarea = 4 * np.pi / self.LightconeShell.map.size
+            rec[:, _lib.HS_SCALE] = pixarea * D ** 2 if self.include_pixel_size else 1.0   # :478
+        else:
+            mcosmo = _model_cosmo(self.model, cosmo)
+            R_com = cosmology.radius_of_mass(mcosmo, M, a, getattr(self.model, 'mass_def', None)) / a   # BaryonCorrection.py:399
+            rec[:, _lib.HS_RCUT] = self.model.epsilon_max * R_com              # :410
+            rec[:, _lib.HS_LNRCOM] = np.log(R_com)                             # :408
+            rec[:, _lib.HS_SCALE] = 1.0
+        rec[:, _lib.HS_THETA_LL], rec[:, _lib.HS_PHI_LL] = theta_ll, phi_ll
+        self.last_scalars = dict(R_run=R, D_A=D, R_model_com=None if paint else R_com)
+        keys = list(vars(self.model).get('p_keys', []))                        # :304
+        _check_keys(self.model, keys)
+        return rec, _extras(cat, keys)
+
+    def _range(self, npix):
+        return (0, npix) if self.pix_range is None else (int(self.pix_range[0]), int(self.pix_range[1]))
+
+    def _owned_halos(self, rec, extras, nside, lo, hi):
+        """Ring-range sharding: keep the halos whose disc can touch this rank's pixel range (parallel.py)."""
+        if self.pix_range is None or rec.shape[0] == 0:
+            return rec, extras
+        from .parallel import halos_touching_pixel_range
+        keep = halos_touching_pixel_range(nside, rec[:, _lib.HS_THETA], rec[:, _lib.HS_RADIUS], lo, hi)
+        return np.ascontiguousarray(rec[keep]), (None if extras is None else np.ascontiguousarray(extras[keep]))
+
+
+class BaryonifyShell(DefaultRunner):
+    """BaryonForge/Runners/HealpixRunner.py:180-373."""
+
+    def offsets_on_device(self):
+        """Run the halo loop only; returns (offsets tensor [3, n_local] on the device, n_updates)."""
+        torch = _torch()
+        dev = self._device()
+        L = _lib.lib()
+        NSIDE = self.LightconeShell.NSIDE
+        npix = 12 * NSIDE * NSIDE
+        lo, hi = self._range(npix)
+        rec, extras = self.halo_records(paint=False)
+        rec, extras = self._owned_halos(rec, extras, NSIDE, lo, hi)
+        with torch.cuda.device(dev):
+            table = self._tables.get((id(self.model), id(self.model.interp_d) if hasattr(self.model, 'interp_d') else 0),
+                                     lambda: displacement_table_of(self.model, dev.index))
+            d_rec = _to_device(rec, dev)
+            d_ext = None if extras is None else _to_device(extras, dev)
+            d_off = torch.zeros((3, hi - lo), dtype=torch.float64, device=dev)
+            d_n = torch.zeros(1, dtype=torch.int64, device=dev)
+            _lib.check(L.bfg_shell_offsets(table.handle, NSIDE, rec.shape[0], _lib.ptr(d_rec), _lib.ptr(d_ext),
+                                           table.n_extra, _lib.ptr(d_off), lo, hi, _lib.ptr(d_n), _lib.current_stream()))
+        return d_off, d_n
+
+    def process(self):
+        torch = _torch()
+        orig_map = self.LightconeShell.map
+        NSIDE = self.LightconeShell.NSIDE
+        if np.allclose(orig_map, 0):                 # :293-294 returns the input object
+            return orig_map
+        dev = self._device()
+        L = _lib.lib()
+        npix = orig_map.size
+        lo, hi = self._range(npix)
+        with torch.cuda.device(dev):
+            d_map = _to_device(orig_map[lo:hi], dev, dtype=np.float64)
+            d_off, d_n = self.offsets_on_device()
+            d_new = torch.zeros(npix, dtype=torch.float64, device=dev)
+            st = _lib.current_stream()
+            _lib.check(L.bfg_shell_regrid(NSIDE, _lib.ptr(d_map), _lib.ptr(d_off), _lib.ptr(d_new), lo, hi, st))
+            del d_off
+            if self.pix_range is not None:
+                from .parallel import reduce_partial_map
+                d_new, d_map_sum = reduce_partial_map(d_new, d_map)
+            else:
+                d_map_sum = None
+            d_sums = torch.zeros(2, dtype=torch.float64, device=dev)
+            _lib.check(L.bfg_sum_f64(_lib.ptr(d_new), npix, _lib.ptr(d_sums), st))
+            if d_map_sum is None:
+                _lib.check(L.bfg_sum_f64(_lib.ptr(d_map), hi - lo, d_sums.data_ptr() + 8, st))
+            else:
+                d_sums[1] = d_map_sum
+            out = torch.empty(npix, dtype=torch.float64, pin_memory=True)
+            out.copy_(d_new, non_blocking=True)
+            sums = d_sums.cpu()
+            n_up = int(d_n.cpu()[0])
+            torch.cuda.current_stream().synchronize()
+        new_sum, old_sum = float(sums[0]), float(sums[1])
+        self.last_stats = dict(n_updates=n_up, new_sum=new_sum, old_sum=old_sum)
+        assert np.isclose(new_sum, old_sum), \
+            "ERROR in pixel regridding, sum(new_map) [%0.14e] != sum(oldmap) [%0.14e]" % (new_sum, old_sum)   # :368-370
+        return out.numpy()
+
+
+class PaintProfilesShell(DefaultRunner):
+    """BaryonForge/Runners/HealpixRunner.py:376-483."""
+
+    def process(self):
+        torch = _torch()
+        assert self.model is not None, "You must provide a model"
+        dev = self._device()
+        L = _lib.lib()
+        NSIDE = self.LightconeShell.NSIDE
+        npix = self.LightconeShell.map.size
+        lo, hi = self._range(npix)
+        rec, extras = self.halo_records(paint=True)
+        rec, extras = self._owned_halos(rec, extras, NSIDE, lo, hi)
+        with torch.cuda.device(dev):
+            table = self._tables.get((id(self.model), id(getattr(self.model, 'interp2D', None))),
+                                     lambda: profile_table_of(self.model, '2D', dev.index))
+            d_rec = _to_device(rec, dev)
+            d_ext = None if extras is None else _to_device(extras, dev)
+            d_new = torch.zeros(hi - lo, dtype=torch.float64, device=dev)
+            d_n = torch.zeros(1, dtype=torch.int64, device=dev)
+            _lib.check(L.bfg_shell_paint(table.handle, NSIDE, rec.shape[0], _lib.ptr(d_rec), _lib.ptr(d_ext),
+                                         table.n_extra, _lib.ptr(d_new), lo, hi, _lib.ptr(d_n), _lib.current_stream()))
+            if self.pix_range is not None:
+                from .parallel import gather_owned_ranges
+                d_new = gather_owned_ranges(d_new, npix)
+            out = torch.empty(npix, dtype=torch.float64, pin_memory=True)
+            out.copy_(d_new, non_blocking=True)
+            n_up = int(d_n.cpu()[0])
+            torch.cuda.current_stream().synchronize()
+        self.last_stats = dict(n_updates=n_up)
+        return out.numpy()
+
+
+# =====================================================================================================================
+# periodic grids
+# =====================================================================================================================
+def _nearest_bin(bins, x):
+    """np.argmin(np.abs(bins - x_j)) for every halo (Map2DRunner.py:512-513), without the n_halo x N matrix."""
+    N = bins.size
+    res = bins[1] - bins[0]
+    c = np.clip(np.floor((x - bins[0]) / res + 0.5), 0, N - 1).astype(np.int64)
+    best = np.clip(c - 1, 0, N - 1)
+    dbest = np.abs(bins[best] - x)
+    for o in (0, 1):                      # ascending index order + strict '<' == argmin's first-minimum rule
+        cand = np.clip(c + o, 0, N - 1)
+        d = np.abs(bins[cand] - x)
+        take = d < dbest
+        best = np.where(take, cand, best)
+        dbest = np.where(take, d, dbest)
+    return best
+
+
+class DefaultRunnerGrid(object):
+    """Constructor contract of BaryonForge/Runners/Map2DRunner.py:255-278 (+ keyword-only GPU knobs)."""
+
+    def __init__(self, HaloNDCatalog, GriddedMap, epsilon_max, model, use_ellipticity=False,
+                 mass_def=None, include_pixel_size=True, verbose=True, *, device=None, plane_range=None):
+        self.HaloNDCatalog = HaloNDCatalog
+        self.GriddedMap = GriddedMap
+        self.cosmo = HaloNDCatalog.cosmology
+        self.model = model
+        self.epsilon_max = epsilon_max
+        self.mass_def = mass_def
+        self.verbose = verbose
+        self.use_ellipticity = use_ellipticity
+        self.include_pixel_size = include_pixel_size
+        self.device = device
+        self.plane_range = plane_range    # (lo, hi) axis-0 planes owned by this rank; None = whole grid
+        self.last_stats = {}
+        self._tables = _TableCache()
+        if use_ellipticity:               # Map2DRunner.py:272-278
+            names = HaloNDCatalog.cat.dtype.names
+            assert 'q_ell' in names, "The 'q_ell' column is missing, but you set use_ellipticity = True"
+            if not GriddedMap.is2D:
+                assert 'c_ell' in names, "The 'c_ell' column is missing, but you set use_ellipticity = True"
+            assert 'A_ell' in names, "The 'A_ell' column is missing, but you set use_ellipticity = True"
+
+    __getstate__ = DefaultRunner.__getstate__
+    __setstate__ = DefaultRunner.__setstate__
+    _device = DefaultRunner._device
+
+    def _planes(self, N):
+        return (0, N) if self.plane_range is None else (int(self.plane_range[0]), int(self.plane_range[1]))
+
+    def halo_records(self, paint):
+        """Per-halo scalars of Map2DRunner.py:484-520 / :727-760 (+ BaryonCorrection.py:371,398-399,410), vectorised."""
+        if self.use_ellipticity:
+            if not self.GriddedMap.is2D:
+                raise NotImplementedError("Currently not able to ellipticities with 3D maps.")   # Map2DRunner.py:571
+            raise NotImplementedError("use_ellipticity is not implemented on the GPU path yet (SURVEY.md §8f item 2)")
+        cat = self.HaloNDCatalog.cat
+        n = cat.size
+        bins = np.asarray(self.GriddedMap.bins, dtype=np.float64)
+        res = self.GriddedMap.res
+        ndim = 2 if self.GriddedMap.is2D else 3
+        cosmo = cosmology.runner_cosmology(self.cosmo, with_w0=False)             # :462-465 (no w0)
+        M32 = cat['M'].astype('<f4')                                              # io.py:204-205
+        M = M32.astype(np.float64)
+        a = 1 / (1 + self.HaloNDCatalog.redshift)                                 # :490
+        rec = np.zeros((n, _lib.HALO_STRIDE), dtype=np.float64)
+        if n == 0:
+            return rec, None
+        R_phys = cosmology.radius_of_mass(cosmo, M, a, self.mass_def)             # :491
+        if paint:
+            R_com = R_phys / a                                                    # :734
+            Nf = 2 * self.epsilon_max * R_com / res                               # :740
+            rec[:, _lib.HB_PAINTCUT] = R_com * self.epsilon_max                   # :815
+            rec[:, _lib.HB_RQ] = R_com * self.epsilon_max
+            rec[:, _lib.HB_RCUT] = np.inf
+        else:
+            R_q = np.clip(self.epsilon_max * R_phys / a, 0, np.max(bins) / 2)     # :492-493
+            Nf = 2 * R_q / res                                                    # :500
+            rec[:, _lib.HB_RQ] = R_q
+            mcosmo = _model_cosmo(self.model, cosmo)
+            R_mod = cosmology.radius_of_mass(mcosmo, M, a, getattr(self.model, 'mass_def', None)) / a   # BaryonCorrection.py:399
+            rec[:, _lib.HB_RCUT] = self.model.epsilon_max * R_mod
+            rec[:, _lib.HB_LNRCOM] = np.log(R_mod)
+        self.last_scalars = dict(R_phys=R_phys, R_model_com=None if paint else R_mod)
+        Nsize = ((Nf // 2).astype(np.int64)) * 2                                  # :501
+        Nsize = np.clip(Nsize, 2, bins.size // 2)                                 # :503
+        rec[:, _lib.HB_NSIZE] = Nsize
+        rec[:, _lib.HB_LNZ] = np.log(1 / a)
+        rec[:, _lib.HB_LNM] = np.log(M32).astype(np.float64)                      # float32 log, §10 #8
+        for k, name in enumerate(['x', 'y', 'z'][:ndim]):
+            x = cat[name].astype('<f4').astype(np.float64)
+            cen = _nearest_bin(bins, x)
+            rec[:, _lib.HB_X + k] = x
+            rec[:, _lib.HB_CX + k] = cen
+            rec[:, _lib.HB_DX + k] = bins[cen] - x                                # :519-520
+        if ndim == 2:
+            dx, dy = rec[:, _lib.HB_DX], rec[:, _lib.HB_DY]
+            assert np.all((dx <= res) & (dy <= res)), "Halo offsets are larger than res"   # :522
+        keys = list(vars(self.model).get('p_keys', []))
+        _check_keys(self.model, keys)
+        return rec, _extras(cat, keys)
+
+
+class BaryonifyGrid(DefaultRunnerGrid):
+    """BaryonForge/Runners/Map2DRunner.py:353-621."""
+
+    def offsets_on_device(self):
+        torch = _torch()
+        dev = self._device()
+        L = _lib.lib()
+        gm = self.GriddedMap
+        ndim, N = (2 if gm.is2D else 3), gm.Npix
+        lo, hi = self._planes(N)
+        rec, extras = self.halo_records(paint=False)
+        with torch.cuda.device(dev):
+            table = self._tables.get((id(self.model), id(getattr(self.model, 'interp_d', None))),
+                                     lambda: displacement_table_of(self.model, dev.index))
+            d_rec = _to_device(rec, dev)
+            d_ext = None if extras is None else _to_device(extras, dev)
+            nloc = (hi - lo) * N ** (ndim - 1)
+            d_off = torch.zeros((ndim, nloc), dtype=torch.float64, device=dev)
+            d_n = torch.zeros(1, dtype=torch.int64, device=dev)
+            _lib.check(L.bfg_grid_offsets(table.handle, ndim, N, float(gm.res), rec.shape[0], _lib.ptr(d_rec),
+                                          _lib.ptr(d_ext), table.n_extra, _lib.ptr(d_off), lo, hi, _lib.ptr(d_n),
+                                          _lib.current_stream()))
+        return d_off, d_n
+
+    def process(self):
+        torch = _torch()
+        gm = self.GriddedMap
+        orig_map = gm.map
+        ndim, N = (2 if gm.is2D else 3), gm.Npix
+        lo, hi = self._planes(N)
+        dev = self._device()
+        L = _lib.lib()
+        with torch.cuda.device(dev):
+            d_map = _to_device(orig_map[lo:hi], dev, dtype=np.float64)
+            d_off, d_n = self.offsets_on_device()
+            d_new = torch.zeros(orig_map.size, dtype=torch.float64, device=dev)
+            st = _lib.current_stream()
+            _lib.check(L.bfg_grid_regrid(ndim, N, _lib.ptr(d_map), _lib.ptr(d_off), _lib.ptr(d_new), lo, hi, st))
+            del d_off
+            d_map_sum = None
+            if self.plane_range is not None:
+                from .parallel import reduce_partial_map
+                d_new, d_map_sum = reduce_partial_map(d_new, d_map)
+            d_sums = torch.zeros(2, dtype=torch.float64, device=dev)
+            _lib.check(L.bfg_sum_f64(_lib.ptr(d_new), orig_map.size, _lib.ptr(d_sums), st))
+            if d_map_sum is None:
+                _lib.check(L.bfg_sum_f64(_lib.ptr(d_map), d_map.numel(), d_sums.data_ptr() + 8, st))
+            else:
+                d_sums[1] = d_map_sum
+            out = torch.empty(orig_map.size, dtype=torch.float64, pin_memory=True)
+            out.copy_(d_new, non_blocking=True)
+            sums = d_sums.cpu()
+            n_up = int(d_n.cpu()[0])
+            torch.cuda.current_stream().synchronize()
+        new_sum, old_sum = float(sums[0]), float(sums[1])
+        self.last_stats = dict(n_updates=n_up, new_sum=new_sum, old_sum=old_sum)
+        assert np.isclose(new_sum, old_sum), \
+            "ERROR in pixel regridding, sum(new_map) [%0.14e] != sum(oldmap) [%0.14e]" % (new_sum, old_sum)   # :616-619
+        return out.numpy().reshape(orig_map.shape)
+
+
+class PaintProfilesGrid(DefaultRunnerGrid):
+    """BaryonForge/Runners/Map2DRunner.py:624-829."""
+
+    def process(self):
+        torch = _torch()
+        gm = self.GriddedMap
+        ndim, N = (2 if gm.is2D else 3), gm.Npix
+        lo, hi = self._planes(N)
+        dev = self._device()
+        L = _lib.lib()
+        rec, extras = self.halo_records(paint=True)
+        which = '2D' if gm.is2D else '3D'                                         # :763 projected / :792 real
+        dV = float(np.power(gm.res, ndim)) if self.include_pixel_size else 1.0    # :723,825
+        with torch.cuda.device(dev):
+            table = self._tables.get((id(self.model), which, id(getattr(self.model, 'interp' + which, None))),
+                                     lambda: profile_table_of(self.model, which, dev.index))
+            d_rec = _to_device(rec, dev)
+            d_ext = None if extras is None else _to_device(extras, dev)
+            nloc = (hi - lo) * N ** (ndim - 1)
+            d_new = torch.zeros(nloc, dtype=torch.float64, device=dev)
+            d_n = torch.zeros(1, dtype=torch.int64, device=dev)
+            _lib.check(L.bfg_grid_paint(table.handle, ndim, N, float(gm.res), dV, rec.shape[0], _lib.ptr(d_rec),
+                                        _lib.ptr(d_ext), table.n_extra, _lib.ptr(d_new), lo, hi, _lib.ptr(d_n),
+                                        _lib.current_stream()))
+            if self.plane_range is not None:
+                from .parallel import gather_owned_ranges
+                d_new = gather_owned_ranges(d_new, gm.map.size)
+            out = torch.empty(gm.map.size, dtype=torch.float64, pin_memory=True)
+            out.copy_(d_new, non_blocking=True)
+            n_up = int(d_n.cpu()[0])
+            torch.cuda.current_stream().synchronize()
+        self.last_stats = dict(n_updates=n_up)
+        return out.numpy().reshape(gm.map.shape)
+
+
+# =====================================================================================================================
+# particle snapshots
+# =====================================================================================================================
+class DefaultRunnerSnapshot(object):
+    """Constructor contract of BaryonForge/Runners/SnapshotRunner.py:83-100.  The periodic KD-tree of :100 is replaced
+    by a device cell list built inside process(); KDTree_kwargs is accepted and ignored."""
+
+    def __init__(self, HaloNDCatalog, ParticleSnapshot, epsilon_max, model, mass_def=None, verbose=True,
+                 KDTree_kwargs={}, *, device=None, ncell=None):
+        self.HaloNDCatalog = HaloNDCatalog
+        self.ParticleSnapshot = ParticleSnapshot
+        self.epsilon_max = epsilon_max
+        self.cosmo = HaloNDCatalog.cosmology
+        self.model = model
+        self.mass_def = mass_def
+        self.verbose = verbose
+        self.KDTree_kwargs = KDTree_kwargs
+        self.device = device
+        self.ncell = ncell
+        self.last_stats = {}
+        self._tables = _TableCache()
+
+    __getstate__ = DefaultRunner.__getstate__
+    __setstate__ = DefaultRunner.__setstate__
+    _device = DefaultRunner._device
+
+    def halo_records(self):
+        """Per-halo scalars of SnapshotRunner.py:219-228 (+ BaryonCorrection.py:371,398-399,410), vectorised."""
+        cat = self.HaloNDCatalog.cat
+        n = cat.size
+        Lbox = self.ParticleSnapshot.L
+        ndim = 2 if self.ParticleSnapshot.is2D else 3
+        cosmo = cosmology.runner_cosmology(self.cosmo, with_w0=False)             # :198-201 (no w0)
+        M32 = cat['M'].astype('<f4')
+        M = M32.astype(np.float64)
+        a = 1 / (1 + self.HaloNDCatalog.redshift)                                 # :225
+        rec = np.zeros((n, _lib.HALO_STRIDE), dtype=np.float64)
+        if n == 0:
+            return rec, None
+        R_phys = cosmology.radius_of_mass(cosmo, M, a, self.mass_def)             # :226
+        rec[:, _lib.HB_RQ] = np.clip(self.epsilon_max * R_phys / a, 0, Lbox / 2)  # :227-228
+        mcosmo = _model_cosmo(self.model, cosmo)
+        R_mod = cosmology.radius_of_mass(mcosmo, M, a, getattr(self.model, 'mass_def', None)) / a
+        rec[:, _lib.HB_RCUT] = self.model.epsilon_max * R_mod
+        rec[:, _lib.HB_LNRCOM] = np.log(R_mod)
+        rec[:, _lib.HB_LNZ] = np.log(1 / a)
+        rec[:, _lib.HB_LNM] = np.log(M32).astype(np.float64)
+        self.last_scalars = dict(R_phys=R_phys, R_model_com=R_mod)
+        for k, name in enumerate(['x', 'y', 'z'][:ndim]):
+            rec[:, _lib.HB_X + k] = cat[name].astype('<f4').astype(np.float64)
+        keys = list(vars(self.model).get('p_keys', []))
+        _check_keys(self.model, keys)
+        return rec, _extras(cat, keys)
+
+    def _pick_ncell(self, rq, n_part, ndim, Lbox):
+        if self.ncell is not None:
+            return int(self.ncell)
+        cap = 256 if ndim == 3 else 4096
+        by_count = int(max(1, (n_part / 8.0) ** (1.0 / ndim)))       # >= ~8 particles per cell
+        med = float(np.median(rq)) if rq.size else Lbox
+        by_radius = int(max(1, Lbox / max(0.5 * med, 1e-300)))       # cells about half a typical query radius
+        return int(max(1, min(cap, by_count, by_radius)))
+
+
+class BaryonifySnapshot(DefaultRunnerSnapshot):
+    """BaryonForge/Runners/SnapshotRunner.py:161-274."""
+
+    def process(self):
+        torch = _torch()
+        ps = self.ParticleSnapshot
+        ndim = 2 if ps.is2D else 3
+        n_part = len(ps.cat)
+        Lbox = float(ps.L)
+        dev = self._device()
+        L = _lib.lib()
+        rec, extras = self.halo_records()
+        ncell = self._pick_ncell(rec[:, _lib.HB_RQ], n_part, ndim, Lbox)
+        with torch.cuda.device(dev):
+            table = self._tables.get((id(self.model), id(getattr(self.model, 'interp_d', None))),
+                                     lambda: displacement_table_of(self.model, dev.index))
+            st = _lib.current_stream()
+            names = ['x', 'y', 'z'][:ndim]
+            d_p = [_to_device(ps.cat[k], dev, dtype=np.float64) for k in names] + ([None] if ndim == 2 else [])
+            d_s = [torch.empty(n_part, dtype=torch.float64, device=dev) for _ in names] + ([None] if ndim == 2 else [])
+            d_start = torch.empty(ncell ** ndim + 1, dtype=torch.int64, device=dev)
+            d_order = torch.empty(n_part, dtype=torch.int64, device=dev)
+            _lib.check(L.bfg_snap_build_cells(ndim, n_part, _lib.ptr(d_p[0]), _lib.ptr(d_p[1]), _lib.ptr(d_p[2]), Lbox,
+                                              ncell, _lib.ptr(d_start), _lib.ptr(d_order), _lib.ptr(d_s[0]),
+                                              _lib.ptr(d_s[1]), _lib.ptr(d_s[2]), st))
+            d_rec = _to_device(rec, dev)
+            d_ext = None if extras is None else _to_device(extras, dev)
+            d_tot = torch.zeros((ndim, n_part), dtype=torch.float64, device=dev)
+            d_n = torch.zeros(1, dtype=torch.int64, device=dev)
+            _lib.check(L.bfg_snap_offsets(table.handle, ndim, n_part, _lib.ptr(d_s[0]), _lib.ptr(d_s[1]), _lib.ptr(d_s[2]),
+                                          Lbox, ncell, _lib.ptr(d_start), rec.shape[0], _lib.ptr(d_rec), _lib.ptr(d_ext),
+                                          table.n_extra, _lib.ptr(d_tot), _lib.ptr(d_n), st))
+            # displaced positions overwrite the (no longer needed) unsorted device copies
+            _lib.check(L.bfg_snap_apply(ndim, n_part, _lib.ptr(d_s[0]), _lib.ptr(d_s[1]), _lib.ptr(d_s[2]), _lib.ptr(d_tot),
+                                        _lib.ptr(d_order), Lbox, _lib.ptr(d_p[0]), _lib.ptr(d_p[1]), _lib.ptr(d_p[2]), st))
+            new_cat = ps.cat.copy()                                               # :263
+            for k, name in enumerate(names):
+                new_cat[name] = d_p[k].cpu().numpy()
+            n_pairs = int(d_n.cpu()[0])
+        self.last_stats = dict(n_pairs=n_pairs, ncell=ncell)
+        return new_cat
+
+
+def deposit_ngp(coords, mass, L, N_grid, device=None):
+    """ParticleSnapshot.make_map (BaryonForge/utils/io.py:629-677) on the GPU: NGP mass histogram, float64."""
+    torch = _torch()
+    ndim = len(coords)
+    dev = torch.device('cuda', torch.cuda.current_device() if device is None else int(device))
+    with torch.cuda.device(dev):
+        d_p = [_to_device(c, dev, dtype=np.float64) for c in coords] + ([None] if ndim == 2 else [])
+        d_m = _to_device(mass, dev, dtype=np.float64)
+        d_grid = torch.zeros(int(N_grid) ** ndim, dtype=torch.float64, device=dev)
+        _lib.check(_lib.lib().bfg_snap_deposit_ngp(ndim, d_m.numel(), _lib.ptr(d_p[0]), _lib.ptr(d_p[1]), _lib.ptr(d_p[2]),
+                                                  _lib.ptr(d_m), float(L), int(N_grid), _lib.ptr(d_grid),
+                                                  _lib.current_stream()))
+        out = d_grid.cpu().numpy()
+    return out.reshape((int(N_grid),) * ndim)

@@ -1,0 +1,182 @@
+/*
+ * bfg_b200.h -- C ABI of libbfg_b200.so: the B200 (sm_100a) back-end of BaryonForge's runner hot path.
+ *
+ * The reference (DhayaaAnbajagane/BaryonForge) is pure Python and has no FFI; the boundary it offers for
+ * this path is the `Runners` classes' constructor + process().  Each entry point below replaces the body
+ * of one stage of those process() methods (cited per function as file:line under BaryonForge/); the thin
+ * Python mirror in baryonforge_b200/runners.py binds them with ctypes (see INTEGRATION.md for the stub a
+ * reference maintainer would add).
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes, no C++/torch types.  Every call returns 0 on success or a
+ *    negative bfg_status; bfg_last_error() gives the thread-local message.  Nothing throws.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls are asynchronous
+ *    with respect to the host unless the name ends in `_host`, and never allocate unless stated.
+ *  - Pointers named d_* are DEVICE pointers on the table's device; h_* are HOST pointers.
+ *  - Maps are HEALPix RING order float64 (LightconeShell.map, utils/io.py:290-379) or C-order float64
+ *    N^d grids (GriddedMap.map, utils/io.py:382-494).  Pixel / cell / particle ids are int64.
+ *  - Halo records are rows of BFG_HALO_STRIDE float64 (128 B, one cache line) -- the per-halo scalars the
+ *    reference computes at the top of each loop iteration (Runners/HealpixRunner.py:317-329,
+ *    Runners/Map2DRunner.py:484-503, Runners/SnapshotRunner.py:219-228), vectorised once on the host.
+ */
+#ifndef BFG_B200_H
+#define BFG_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BFG_ABI_VERSION 1
+
+typedef enum {
+    BFG_OK = 0,
+    BFG_ERR_INVALID = -1,   /* bad argument */
+    BFG_ERR_CUDA = -2,      /* CUDA runtime error, see bfg_last_error() */
+    BFG_ERR_UNSUPPORTED = -3,
+    BFG_ERR_NOMEM = -4
+} bfg_status;
+
+/* table flags */
+#define BFG_TABLE_LOG_VALUES 1      /* values are log(profile): read-out applies exp() (utils/Tabulate.py:270-271,318-319) */
+#define BFG_TABLE_RDELTA 2          /* radial axis is ln(r/R_delta) (Profiles/BaryonCorrection.py:407-408) */
+
+#define BFG_MAX_TABLE_DIM 6
+#define BFG_HALO_STRIDE 16
+
+/* ---- spherical-shell halo record (float64 fields) ----------------------------------------------- */
+enum {
+    BFG_HS_VX = 0, BFG_HS_VY = 1, BFG_HS_VZ = 2, /* hp.ang2vec(ra, dec, lonlat=True)           HealpixRunner.py:327 */
+    BFG_HS_THETA = 3, BFG_HS_PHI = 4,            /* pointing(vec): what query_disc works from   HealpixRunner.py:330 */
+    BFG_HS_D = 5,                                /* D_A(z_j), physical Mpc                      HealpixRunner.py:321 */
+    BFG_HS_A = 6,                                /* a_j = 1/(1+z_j)                             HealpixRunner.py:319 */
+    BFG_HS_RADIUS = 7,                           /* R_j*epsilon_max/D_j [rad]                   HealpixRunner.py:329 */
+    BFG_HS_LNZ = 8,                              /* np.log(1/a_j)                               BaryonCorrection.py:371 */
+    BFG_HS_LNM = 9,                              /* np.log(M_j)                                 BaryonCorrection.py:398 */
+    BFG_HS_RCUT = 10,                            /* model.epsilon_max * R_com (+inf for paint)  BaryonCorrection.py:399,410 */
+    BFG_HS_LNRCOM = 11,                          /* ln R_com, used when BFG_TABLE_RDELTA        BaryonCorrection.py:408 */
+    BFG_HS_SCALE = 12,                           /* paint: pixarea*D_j^2 or 1                   HealpixRunner.py:478 */
+    BFG_HS_THETA_LL = 13, BFG_HS_PHI_LL = 14,    /* pi/2-radians(dec), radians(ra): fallback    HealpixRunner.py:334 */
+    BFG_HS_RESERVED = 15
+};
+
+/* ---- box (grid / snapshot) halo record ----------------------------------------------------------- */
+enum {
+    BFG_HB_X = 0, BFG_HB_Y = 1, BFG_HB_Z = 2,    /* float32-rounded halo position [Mpc]         utils/io.py:204-205 */
+    BFG_HB_RQ = 3,                               /* clipped query radius, comoving              Map2DRunner.py:492-493, SnapshotRunner.py:227-228 */
+    BFG_HB_NSIZE = 4,                            /* grid: even cutout size (as float64)         Map2DRunner.py:500-503 */
+    BFG_HB_CX = 5, BFG_HB_CY = 6, BFG_HB_CZ = 7, /* grid: argmin|bins - x_j| centre cells       Map2DRunner.py:512-513,548-550 */
+    BFG_HB_LNZ = 8, BFG_HB_LNM = 9, BFG_HB_RCUT = 10, BFG_HB_LNRCOM = 11,
+    BFG_HB_DX = 12, BFG_HB_DY = 13, BFG_HB_DZ = 14, /* grid: bins[cen] - x_j                    Map2DRunner.py:519-520,557-559 */
+    BFG_HB_PAINTCUT = 15                         /* paint: R_com*epsilon_max mask radius        Map2DRunner.py:815 */
+};
+
+typedef struct bfg_table bfg_table; /* opaque: a (ln(1+z), ln M, ln r[, extras...]) table resident in HBM */
+
+/* ---- library ------------------------------------------------------------------------------------ */
+int bfg_abi_version(void);
+const char *bfg_last_error(void);
+int bfg_device_count(void);
+/* SM count, HBM bytes (total, free) of `device` */
+int bfg_device_info(int device, int *sm_count, int64_t *mem_total, int64_t *mem_free);
+
+/* ---- tables: RegularGridInterpolator((ln(1+z), ln M, ln r, *extras), values, bounds_error=False, fill=nan)
+ *      Profiles/BaryonCorrection.py:307-323 ; utils/Tabulate.py:261-271,582-590.
+ *      Axis 2 is the radial axis; axes 0,1,3.. are per-halo constants.  Copies host -> device once. */
+int bfg_table_create(bfg_table **out, int ndim, const int64_t *shape, const double *const *h_axes,
+                     const double *h_values, int flags, int device);
+int bfg_table_destroy(bfg_table *t);
+int bfg_table_info(const bfg_table *t, int *ndim, int64_t *shape, int *flags, int *device, int *uniform_r);
+
+/* Read-out only (unit-test entry): out[i] = table(lnz, lnM, x_i, extras) with scipy's N-linear rule, NaN outside,
+ * exp() when BFG_TABLE_LOG_VALUES.  Replaces BaryonificationClass._readout's `table(p_in)` (BaryonCorrection.py:404-408)
+ * and TabulatedProfile._readout (Tabulate.py:318-319).  d_x, d_out: device, n values.  */
+int bfg_table_readout(const bfg_table *t, double lnz, double lnM, const double *h_extras, int64_t n,
+                      const double *d_x, double *d_out, void *stream);
+
+/* ---- HEALPix RING geometry on the device (replaces healpy at HealpixRunner.py:330,334,336,357-361) -- */
+/* Per-halo disc size: d_npix[j] = |query_disc(nside, vec_j, radius_j, inclusive=False)| (before the <4 fallback). */
+int bfg_healpix_disc_counts(int nside, int64_t n_halo, const double *d_halos, int64_t *d_npix, void *stream);
+/* Pixel list of ONE halo record (ascending), for parity tests of the index sets: writes <= cap ids, returns
+ * the full count in *d_count. */
+int bfg_healpix_query_disc(int nside, const double *d_halo, int64_t *d_pix, int64_t cap, int64_t *d_count, void *stream);
+/* pix2vec over [pix_lo, pix_hi): d_xyz is [3][pix_hi-pix_lo]. */
+int bfg_healpix_pix2vec(int nside, int64_t pix_lo, int64_t pix_hi, double *d_xyz, void *stream);
+/* get_interp_weights(theta, phi): d_pix [4][n], d_w [4][n]. */
+int bfg_healpix_interp_weights(int nside, int64_t n, const double *d_theta, const double *d_phi, int64_t *d_pix,
+                               double *d_w, void *stream);
+/* ang2pix (RING), used for shard assignment. */
+int bfg_healpix_ang2pix(int nside, int64_t n, const double *d_theta, const double *d_phi, int64_t *d_pix, void *stream);
+
+/* ---- shells ------------------------------------------------------------------------------------- */
+/* Halo loop of BaryonifyShell.process (HealpixRunner.py:315-355): accumulates the unit-vector offsets of all
+ * halos into d_offsets, laid out [3][pix_hi-pix_lo] (component-major, so REDs of a warp are contiguous), for the
+ * owned RING range [pix_lo, pix_hi).  d_extras: [n_halo][n_extra] p_keys values or NULL.  d_offsets must be zeroed
+ * by the caller.  If d_nupdates != NULL it receives sum_j |pixind_j| restricted to the range (int64, device). */
+int bfg_shell_offsets(const bfg_table *t, int nside, int64_t n_halo, const double *d_halos, const double *d_extras,
+                      int n_extra, double *d_offsets, int64_t pix_lo, int64_t pix_hi, int64_t *d_nupdates,
+                      void *stream);
+/* Halo loop of PaintProfilesShell.process (HealpixRunner.py:449-481): d_map[pix - pix_lo] += profile. */
+int bfg_shell_paint(const bfg_table *t, int nside, int64_t n_halo, const double *d_halos, const double *d_extras,
+                    int n_extra, double *d_map, int64_t pix_lo, int64_t pix_hi, int64_t *d_nupdates, void *stream);
+/* Re-binning of BaryonifyShell.process (HealpixRunner.py:357-365 + regrid_pixels_hpix :17-71): for source pixels
+ * p in [pix_lo, pix_hi) with d_map_in[p - pix_lo] != 0, deposit onto the 4 interpolation neighbours of the displaced
+ * direction.  d_map_out is a FULL map (npix) that must be zeroed by the caller; d_offsets is [3][pix_hi-pix_lo]. */
+int bfg_shell_regrid(int nside, const double *d_map_in, const double *d_offsets, double *d_map_out, int64_t pix_lo,
+                     int64_t pix_hi, void *stream);
+
+/* ---- periodic grids (2-D / 3-D) ------------------------------------------------------------------- */
+/* Halo loop of BaryonifyGrid.process (Map2DRunner.py:482-586).  d_offsets is [ndim][N^ndim] in units of cells,
+ * restricted to axis-0 planes [plane_lo, plane_hi) (slab); NaNs propagate as in the reference. */
+int bfg_grid_offsets(const bfg_table *t, int ndim, int64_t N, double res, int64_t n_halo, const double *d_halos,
+                     const double *d_extras, int n_extra, double *d_offsets, int64_t plane_lo, int64_t plane_hi,
+                     int64_t *d_nupdates, void *stream);
+/* Halo loop of PaintProfilesGrid.process (Map2DRunner.py:725-821); `scale` folds in the final *res^d of :825
+ * (pass 1.0 when include_pixel_size is False). */
+int bfg_grid_paint(const bfg_table *t, int ndim, int64_t N, double res, double scale, int64_t n_halo,
+                   const double *d_halos, const double *d_extras, int n_extra, double *d_map, int64_t plane_lo,
+                   int64_t plane_hi, int64_t *d_nupdates, void *stream);
+/* Re-binning of BaryonifyGrid.process (Map2DRunner.py:589-613 + regrid_pixels_2D/3D :13-162): non-finite offsets -> 0,
+ * add cell coordinates (xy-meshgrid convention), periodic overlap deposit into the FULL grid d_map_out (zeroed by caller). */
+int bfg_grid_regrid(int ndim, int64_t N, const double *d_map_in, const double *d_offsets, double *d_map_out,
+                    int64_t plane_lo, int64_t plane_hi, void *stream);
+
+/* ---- particle snapshots --------------------------------------------------------------------------- */
+/* Cell list replacing scipy.spatial.KDTree (SnapshotRunner.py:95-100): counting-sorts n_part particles (0 <= x < L)
+ * into ncell^ndim cells.  Outputs: d_cell_start [ncell^ndim + 1], d_order [n_part] (sorted slot -> caller's index)
+ * and the cell-ordered copies d_xs/d_ys/d_zs.  Allocates stream-ordered scratch internally. */
+int bfg_snap_build_cells(int ndim, int64_t n_part, const double *d_x, const double *d_y, const double *d_z, double L,
+                         int ncell, int64_t *d_cell_start, int64_t *d_order, double *d_xs, double *d_ys, double *d_zs,
+                         void *stream);
+/* Halo loop of BaryonifySnapshot.process (SnapshotRunner.py:217-260) over the cell-ordered particles:
+ * d_tot [ndim][n_part] (cell order, zeroed by the caller) += displacement * unit vector. */
+int bfg_snap_offsets(const bfg_table *t, int ndim, int64_t n_part, const double *d_xs, const double *d_ys,
+                     const double *d_zs, double L, int ncell, const int64_t *d_cell_start, int64_t n_halo,
+                     const double *d_halos, const double *d_extras, int n_extra, double *d_tot, int64_t *d_npairs,
+                     void *stream);
+/* out[order[p]] = wrap_once(xs[p] + tot[p])  (SnapshotRunner.py:263-273), back in the caller's particle order. */
+int bfg_snap_apply(int ndim, int64_t n_part, const double *d_xs, const double *d_ys, const double *d_zs,
+                   const double *d_tot, const int64_t *d_order, double L, double *d_x_out, double *d_y_out,
+                   double *d_z_out, void *stream);
+/* NGP mass deposit = ParticleSnapshot.make_map / np.histogramdd (utils/io.py:629-677); d_grid zeroed by caller. */
+int bfg_snap_deposit_ngp(int ndim, int64_t n_part, const double *d_x, const double *d_y, const double *d_z,
+                         const double *d_mass, double L, int64_t n_grid, double *d_grid, void *stream);
+
+/* ---- small utilities ------------------------------------------------------------------------------ */
+/* *d_out (one double) = sum of n doubles (mass-conservation assert, HealpixRunner.py:368-370). */
+int bfg_sum_f64(const double *d_x, int64_t n, double *d_out, void *stream);
+/* out[i][c] = in[c][i] : component-major offsets -> the reference's (n, ncomp) layout, for tests. */
+int bfg_transpose_offsets(const double *d_in, double *d_out, int64_t n, int ncomp, void *stream);
+
+/* ---- host-buffer convenience calls (the end-to-end boundary; allocate, copy in, run, copy out, free) ---- */
+int bfg_shell_baryonify_host(const bfg_table *t, int nside, int64_t n_halo, const double *h_halos,
+                             const double *h_extras, int n_extra, const double *h_map_in, double *h_map_out,
+                             int64_t *h_nupdates, double *h_sums /* [2]: sum(new), sum(old) */);
+int bfg_shell_paint_host(const bfg_table *t, int nside, int64_t n_halo, const double *h_halos, const double *h_extras,
+                         int n_extra, double *h_map_out, int64_t *h_nupdates);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BFG_B200_H */

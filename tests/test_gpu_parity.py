@@ -1,0 +1,214 @@
+"""
+-m gpu parity tests: the CUDA path (through the ctypes C ABI and the reference-shaped runner classes) against
+  (1) the committed golden fixtures = outputs of the reference's own runner code (tests/golden, oracle/make_golden.py),
+  (2) the oracle port on fresh seeded inputs,
+to relative 1e-6 (fp64 path; BASELINE.json north_star), index sets bit-exact.
+"""
+import warnings
+
+import numpy as np
+import pytest
+
+from helpers import assert_close, golden_names, load, port_run, product_run
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", golden_names("shell_bary") + golden_names("shell_paint")
+                         + golden_names("grid_bary") + golden_names("grid_paint"))
+def test_map_runners_match_reference_fixture(name):
+    g = load(name)
+    got = product_run(g)
+    assert_close(got, g["out"], name)
+
+
+@pytest.mark.parametrize("name", golden_names("snap"))
+def test_snapshot_matches_reference_fixture(name):
+    g = load(name)
+    got = product_run(g)
+    want = [g["out_x"], g["out_y"]] + ([g["out_z"]] if int(g["ndim"]) == 3 else [])
+    for k, (a, b) in enumerate(zip(got, want)):
+        # positions: relative 1e-6 on the DISPLACEMENT (out - in), i.e. absolute on the position
+        src = [g["px"], g["py"], g["pz"]][k]
+        L = float(g["L"])
+        disp_w = (b - src + L / 2) % L - L / 2
+        disp_g = (a - src + L / 2) % L - L / 2
+        assert_close(disp_g, disp_w, f"{name} axis {k}", atol_scale=1e-7)
+        assert_close(a, b, f"{name} pos axis {k}", rtol=1e-12, atol_scale=1e-12)
+
+
+@pytest.mark.parametrize("name", golden_names("snap"))
+def test_ngp_deposit_matches_histogramdd(name):
+    import baryonforge_b200 as b
+    g = load(name)
+    ndim = int(g["ndim"])
+    px = [g["out_x"], g["out_y"]] + ([g["out_z"]] if ndim == 3 else [])
+    got = b.runners.deposit_ngp(px, g["pM"], float(g["L"]), 16)
+    assert np.array_equal(got, g["ngp"])     # integer multiples of one particle mass: bit-exact assignment
+    # edge semantics of np.histogramdd: x == L -> last bin, outside -> dropped, interior edge -> upper bin
+    L = 10.0
+    x = np.array([0.0, 2.5, 5.0, 10.0, 10.0000001, -1e-9, 7.5 - 1e-15])
+    y = np.full_like(x, 1.0)
+    want = np.histogramdd(np.vstack([x, y]).T, bins=(np.linspace(0, L, 5),) * 2, weights=np.ones_like(x))[0]
+    assert np.array_equal(b.runners.deposit_ngp([x, y], np.ones_like(x), L, 4), want)
+
+
+def test_healpix_device_geometry_matches_oracle():
+    from baryonforge_b200 import healpix as dh
+    from oracle import hpo
+    rng = np.random.default_rng(3)
+    for nside in (1, 2, 8, 64, 512):
+        npix = 12 * nside * nside
+        lo = 0 if nside <= 64 else npix // 2 - 5000
+        hi = npix if nside <= 64 else npix // 2 + 5000
+        want = np.stack(hpo.pix2vec_range(nside, lo, hi - lo))
+        got = dh.pix2vec(nside, lo, hi)
+        assert np.max(np.abs(got - want)) < 4e-16
+        th = np.arccos(rng.uniform(-1, 1, 4000)); ph = rng.uniform(0, 2 * np.pi, 4000)
+        th[:4] = [0.0, np.pi, 1e-9, np.pi - 1e-9]
+        assert np.array_equal(dh.ang2pix(nside, th, ph), hpo.ang2pix(nside, th, ph))
+        gp, gw = dh.interp_weights(nside, th, ph)
+        wp, ww = hpo.get_interpol(nside, th, ph)
+        # a direction within round-off of a pixel-centre meridian may pick the neighbouring pair with weight ~0
+        same = np.all(gp == wp, axis=0)
+        assert same.mean() > 0.999
+        assert np.max(np.abs(gw[:, same] - ww[:, same])) < 1e-9
+        assert np.allclose(gw.sum(axis=0), 1.0, atol=1e-12)
+
+
+def test_query_disc_index_sets_bit_exact():
+    from baryonforge_b200 import healpix as dh
+    from oracle import hpo
+    rng = np.random.default_rng(5)
+    n_diff = 0
+    n_tot = 0
+    for nside in (1, 4, 32, 256, 4096):
+        for k in range(60):
+            theta = np.arccos(rng.uniform(-1, 1)); phi = rng.uniform(0, 2 * np.pi)
+            if k % 6 == 0:
+                theta = rng.choice([1e-3, np.pi - 1e-3, 0.02, np.pi - 0.02])
+            rad = 10 ** rng.uniform(-3.5, 0.3) if nside < 4096 else 10 ** rng.uniform(-3.5, -1.8)
+            if k == 1:
+                rad = 3.2      # >= pi: the whole sphere
+            want = hpo.query_disc(nside, theta, phi, rad)
+            got = dh.query_disc(nside, theta, phi, rad)
+            n_tot += 1
+            if not np.array_equal(got, want):
+                # documented boundary ties: only pixels whose centre sits within round-off of the disc edge may differ
+                d = np.setxor1d(got, want)
+                assert d.size <= 2, (nside, k, d.size)
+                n_diff += 1
+    assert n_diff <= 1, f"{n_diff} of {n_tot} discs differ"
+
+
+def test_table_readout_matches_scipy():
+    import baryonforge_b200 as b
+    from baryonforge_b200 import healpix as dh, synth, _lib
+    from scipy.interpolate import RegularGridInterpolator as RGI
+    import torch
+    axes = synth.table_axes(nz=7, nM=9, nr=300)
+    vals = synth.displacement_values(axes, inject_nan=True)
+    extra = np.linspace(2.0, 12.0, 5)
+    vals4 = vals[..., None] * (1 + 0.1 * extra)[None, None, None, :]
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.uniform(axes[2][0] - 0.5, axes[2][-1] + 0.5, 3000), axes[2][[0, -1, 17]], [np.nan, -np.inf]])
+    dev = torch.cuda.current_device()
+    # 3-D, uniform ln r axis (closed-form cell index) and a perturbed axis (search path)
+    ax_nu = axes[2].copy(); ax_nu[1:-1] += rng.uniform(-0.2, 0.2, ax_nu.size - 2) * (ax_nu[1] - ax_nu[0])
+    for ax2 in (axes[2], ax_nu):
+        tab = b.DeviceTable((axes[0], axes[1], ax2), vals, 0, dev)
+        rgi = RGI((axes[0], axes[1], ax2), vals, bounds_error=False, fill_value=np.nan)
+        for lnz, lnM in [(axes[0][2] + 0.01, axes[1][3] + 0.2), (axes[0][0], axes[1][-1]), (axes[0][-1] + 1e-3, axes[1][1])]:
+            want = rgi((np.full_like(x, lnz), np.full_like(x, lnM), x))
+            got = dh.table_readout(tab, lnz, lnM, x)
+            assert_close(got, want, "readout3d", rtol=1e-12, atol_scale=1e-14)
+    # 4-D table with one extra (p_keys) axis, log-valued
+    with np.errstate(divide='ignore', invalid='ignore'):
+        pv = np.log(synth.profile_values(axes)[..., None] * (1 + 0.1 * extra)[None, None, None, :])
+    tab = b.DeviceTable((axes[0], axes[1], axes[2], extra), pv, _lib.TABLE_LOG_VALUES, dev)
+    rgi = RGI((axes[0], axes[1], axes[2], extra), pv, bounds_error=False)
+    lnz, lnM, e = axes[0][3] + 0.02, axes[1][4] + 0.3, 7.7
+    with np.errstate(invalid='ignore', over='ignore'):
+        want = np.exp(rgi((np.full_like(x, lnz), np.full_like(x, lnM), x, np.full_like(x, e))))
+    got = dh.table_readout(tab, lnz, lnM, x, extras=[e])
+    assert_close(got, want, "readout4d", rtol=1e-12, atol_scale=1e-14)
+
+
+def _fresh_shell_case(nside, n, seed, eps_run, eps_mod):
+    import baryonforge_b200 as b
+    from baryonforge_b200 import synth
+    ra, dec, M, z = synth.sky_halos(n, seed=seed)
+    axes = synth.table_axes()
+    vals = synth.displacement_values(axes)
+    cat = b.HaloLightConeCatalog(ra=ra, dec=dec, M=M, z=z, cosmo=synth.COSMO)
+    shell = b.LightconeShell(map=synth.shell_map(nside, seed=seed + 1), cosmo=synth.COSMO)
+    model = b.DisplacementModel(axes, vals, eps_mod, synth.COSMO)
+    return cat, shell, model, axes, vals
+
+
+def test_baryonify_shell_config1_vs_oracle_port():
+    """BASELINE.json configs[0]: NSIDE=256, 10^4 halos, table 10x10x500, epsilon_max=20 -- offsets, update count, map."""
+    import baryonforge_b200 as b
+    from oracle import runners_port as rp
+    nside, n = 256, 10000
+    cat, shell, model, axes, vals = _fresh_shell_case(nside, n, 42, 20, 20)
+    run = b.BaryonifyShell(cat, shell, 20, model, verbose=False)
+    rec, _ = run.halo_records(paint=False)
+    sc = run.last_scalars
+    tab = rp.DisplacementTable(axes, vals, 20)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        off_w, n_w = rp.shell_offsets(nside, cat.cat, sc["R_run"], sc["D_A"], sc["R_model_com"], 20, tab, warn=False)
+        map_w = rp.shell_regrid(nside, shell.map, off_w)
+    d_off, d_n = run.offsets_on_device()
+    assert int(d_n.cpu()[0]) == n_w            # sum_j |pixind_j| : index-set sizes bit-exact
+    assert_close(d_off.cpu().numpy().T, off_w, "pix_offsets")
+    got = run.process()
+    assert run.last_stats["n_updates"] == n_w
+    assert_close(got, map_w, "new_map")
+    assert np.isclose(got.sum(), shell.map.sum())
+
+
+def test_shell_invariants():
+    import baryonforge_b200 as b
+    from baryonforge_b200 import synth
+    nside = 128
+    cat, shell, model, axes, vals = _fresh_shell_case(nside, 2000, 9, 20, 20)
+    # zero table => identity map
+    zero = b.DisplacementModel(axes, np.zeros_like(vals), 20, synth.COSMO)
+    out = b.BaryonifyShell(cat, shell, 20, zero, verbose=False).process()
+    assert_close(out, shell.map, "identity", rtol=1e-12, atol_scale=1e-13)
+    # all-zero map is returned as the same object (HealpixRunner.py:293-294)
+    zshell = b.LightconeShell(map=np.zeros(12 * nside * nside), cosmo=synth.COSMO)
+    assert b.BaryonifyShell(cat, zshell, 20, model, verbose=False).process() is zshell.map
+    # empty catalogue
+    empty = b.HaloLightConeCatalog(ra=np.zeros(0), dec=np.zeros(0), M=np.zeros(0), z=np.zeros(0), cosmo=synth.COSMO)
+    out = b.BaryonifyShell(empty, shell, 20, model, verbose=False).process()
+    assert_close(out, shell.map, "empty catalogue", rtol=1e-12, atol_scale=1e-13)
+    # pixel-range split: two half-sky runs add up to the full run (what ring-range sharding relies on)
+    full, _ = b.BaryonifyShell(cat, shell, 20, model, verbose=False).offsets_on_device()
+    npix = 12 * nside * nside
+    cut = npix // 2 + 37
+    lo, _ = b.BaryonifyShell(cat, shell, 20, model, verbose=False, pix_range=(0, cut)).offsets_on_device()
+    hi, _ = b.BaryonifyShell(cat, shell, 20, model, verbose=False, pix_range=(cut, npix)).offsets_on_device()
+    import torch
+    both = torch.cat([lo, hi], dim=1)
+    assert_close(both.cpu().numpy(), full.cpu().numpy(), "range split", rtol=1e-9, atol_scale=1e-12)
+
+
+def test_error_behaviour_matches_reference():
+    import baryonforge_b200 as b
+    from baryonforge_b200 import synth
+    cat, shell, model, axes, vals = _fresh_shell_case(16, 10, 1, 20, 20)
+    with pytest.raises(NotImplementedError):
+        b.BaryonifyShell(cat, shell, 20, model, use_ellipticity=True)
+
+    class NoTable(object):
+        def setup_interpolator(self):
+            pass
+    with pytest.raises(NameError):
+        b.BaryonifyShell(cat, shell, 20, NoTable(), verbose=False).process()
+    with pytest.raises(TypeError):
+        b.PaintProfilesShell(cat, shell, 20, object(), verbose=False).process()
+    with pytest.raises(ValueError):
+        b.LightconeShell(map=np.zeros(12), cosmo=dict(Omega_m=0.3))
