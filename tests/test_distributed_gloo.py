@@ -1,0 +1,70 @@
+"""CPU, world_size 2 over gloo: the N>1 host logic (range ownership, partial-map reduce, range gather)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import warnings
+    from baryonforge_b200 import parallel, synth
+    from oracle import runners_port as rp
+    nside = 32
+    npix = 12 * nside * nside
+    lo, hi = parallel.pixel_ranges(nside, world)[rank]
+    # the oracle port plays the part of the per-rank kernel: each rank handles only the halos assigned to it
+    ra, dec, M, z = synth.sky_halos(120, seed=4, z=(0.05, 0.5))
+    axes = synth.table_axes()
+    tab = rp.DisplacementTable(axes, synth.displacement_values(axes), 20)
+    cat = dict(M=M, z=z, ra=ra, dec=dec)
+    R = 1.2 * (M / 1e14) ** (1 / 3.); D = 1200.0 * z / 0.45; Rc = R * (1 + z)
+    theta = np.pi / 2 - np.radians(dec)
+    keep = parallel.halos_touching_pixel_range(nside, theta, R * 20 / D, lo, hi)
+    sub = {k: v[keep] for k, v in cat.items()}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        off, _ = rp.shell_offsets(nside, sub, R[keep], D[keep], Rc[keep], 20, tab, warn=False)
+        full, _ = rp.shell_offsets(nside, cat, R, D, Rc, 20, tab, warn=False)
+    owned = torch.from_numpy(off[lo:hi, 0].copy())
+    gathered = parallel.gather_owned_ranges(owned, npix)
+    ok_gather = np.allclose(gathered.numpy(), full[:, 0], rtol=1e-12, atol=1e-18)
+    # partial full-size maps: all-reduce == sum
+    hmap = synth.shell_map(nside, seed=3)
+    part = np.zeros(npix); part[lo:hi] = hmap[lo:hi]
+    red, src_sum = parallel.reduce_partial_map(torch.from_numpy(part), torch.from_numpy(hmap[lo:hi].copy()))
+    ok_reduce = np.allclose(red.numpy(), hmap) and np.isclose(float(src_sum), hmap.sum())
+    q.put((rank, bool(ok_gather), bool(ok_reduce), int(keep.sum())))
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharding_over_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok_g, ok_r, nkeep in res:
+        assert ok_g and ok_r, (rank, ok_g, ok_r)
+        assert 0 < nkeep < 120      # each rank got a strict subset of the halos

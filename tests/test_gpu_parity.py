@@ -63,7 +63,7 @@ def test_healpix_device_geometry_matches_oracle():
         hi = npix if nside <= 64 else npix // 2 + 5000
         want = np.stack(hpo.pix2vec_range(nside, lo, hi - lo))
         got = dh.pix2vec(nside, lo, hi)
-        assert np.max(np.abs(got - want)) < 4e-16
+        assert np.max(np.abs(got - want)) < 2e-15      # CUDA vs glibc sincos: a few ulp
         th = np.arccos(rng.uniform(-1, 1, 4000)); ph = rng.uniform(0, 2 * np.pi, 4000)
         th[:4] = [0.0, np.pi, 1e-9, np.pi - 1e-9]
         assert np.array_equal(dh.ang2pix(nside, th, ph), hpo.ang2pix(nside, th, ph))

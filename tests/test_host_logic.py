@@ -1,0 +1,122 @@
+"""CPU: host-side mirror of the reference interface -- containers, per-halo scalar prep, sharding helpers."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import baryonforge_b200 as b
+from baryonforge_b200 import _lib, cosmology, parallel, synth
+from baryonforge_b200.runners import _nearest_bin
+from oracle import hpo
+
+
+def test_containers_mirror_reference_layouts():
+    ra, dec, M, z = synth.sky_halos(50)
+    dec[0] = 90.0
+    with pytest.warns(UserWarning):
+        cat = b.HaloLightConeCatalog(ra=ra, dec=dec, M=M, z=z, cosmo=synth.COSMO, cdelta=np.full(50, 7.0))
+    assert cat.cat.dtype.names == ('M', 'z', 'ra', 'dec', 'cdelta') and cat.cat['M'].dtype == np.float64
+    assert cat.cat['dec'][0] == 90 - 1e-8                      # io.py:65-68
+    assert len(cat[:10].cat) == 10 and cat[:10].cat['cdelta'][3] == 7.0
+    pos, Mb = synth.box_halos(20, 100.0)
+    nd = b.HaloNDCatalog(x=pos[0], y=pos[1], z=pos[2], M=Mb, redshift=0.2, cosmo=synth.COSMO)
+    assert nd.cat.dtype['M'].str == '>f4'                      # io.py:204-205 big-endian float32
+    with pytest.raises(ValueError):
+        b.HaloNDCatalog(x=pos[0], y=pos[1], M=Mb, redshift=0.2, cosmo=dict(h=0.7))
+    sh = b.LightconeShell(map=np.zeros(12 * 8 * 8), cosmo=synth.COSMO)
+    assert sh.NSIDE == 8
+    with pytest.raises(ValueError):
+        b.LightconeShell(cosmo=synth.COSMO)
+    N = 16
+    bins = (np.arange(N) + 0.5) * 100 / N
+    gm = b.GriddedMap(map=np.zeros((N, N, N)), redshift=0, bins=bins, cosmo=synth.COSMO)
+    assert (gm.Npix, gm.is2D) == (N, False) and np.isclose(gm.L, 100.0) and np.isclose(gm.res, 100 / N)
+    assert gm.inds.shape == (N, N, N) and len(gm.grid) == 3    # built lazily, same content as io.py:463-470
+    ps = b.ParticleSnapshot(x=pos[0], y=pos[1], M=1.0, L=100.0, redshift=0, cosmo=synth.COSMO)
+    assert ps.is2D and ps.cat.dtype['x'] == np.float64
+
+
+def test_nearest_bin_equals_argmin():
+    rng = np.random.default_rng(0)
+    N = 64
+    bins = (np.arange(N) + 0.5) * 200.0 / N
+    x = np.concatenate([rng.uniform(-5, 205, 5000), bins, bins + 200.0 / N / 2, [0.0, 200.0]]).astype('f4').astype('f8')
+    want = np.array([np.argmin(np.abs(bins - v)) for v in x])
+    assert np.array_equal(_nearest_bin(bins, x), want)
+
+
+def test_background_fallback_matches_pyccl_shim():
+    shim = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "shims")
+    sys.path.insert(0, shim)
+    try:
+        import pyccl as ccl
+    finally:
+        sys.path.remove(shim)
+    c = ccl.Cosmology(Omega_c=0.26, Omega_b=0.04, h=0.7, sigma8=0.8, n_s=0.96, w0=-1.0)
+    bg = cosmology.Background(0.30, 0.04, 0.7, -1.0)
+    a = 1 / (1 + np.linspace(0.0, 3.0, 40))
+    assert np.allclose(bg.angular_diameter_distance(a), ccl.angular_diameter_distance(c, a), rtol=1e-9)
+    M = np.geomspace(1e11, 1e16, 9)
+    want = np.array([ccl.halos.massdef.MassDef(200, 'critical').get_radius(c, m, 0.7) for m in M])
+    assert np.allclose(cosmology.radius_of_mass(bg, M, 0.7), want, rtol=1e-12)
+
+
+def test_shell_records_follow_the_reference_formulas():
+    ra, dec, M, z = synth.sky_halos(200)
+    cat = b.HaloLightConeCatalog(ra=ra, dec=dec, M=M, z=z, cosmo=synth.COSMO)
+    shell = b.LightconeShell(map=np.ones(12 * 16 * 16), cosmo=synth.COSMO)
+    axes = synth.table_axes()
+    model = b.DisplacementModel(axes, synth.displacement_values(axes), 7, dict(synth.COSMO, Omega_m=0.33))
+    run = b.BaryonifyShell(cat, shell, 20, model, verbose=False)
+    rec, ex = run.halo_records(paint=False)
+    assert ex is None and rec.shape == (200, _lib.HALO_STRIDE)
+    a = 1 / (1 + z)
+    assert np.array_equal(rec[:, _lib.HS_LNZ], np.log(1 / a)) and np.array_equal(rec[:, _lib.HS_LNM], np.log(M))
+    theta, phi = np.pi / 2 - np.radians(dec), np.radians(ra)
+    v = np.array([np.sin(theta) * np.cos(phi), np.sin(theta) * np.sin(phi), np.cos(theta)]).T
+    assert np.array_equal(rec[:, :3], v)
+    for j in (0, 17, 199):      # pointing(vec) as the healpy wrapper builds it
+        t, p = hpo.vec2pointing(v[j])
+        assert rec[j, _lib.HS_THETA] == t and rec[j, _lib.HS_PHI] == p
+    sc = run.last_scalars
+    assert np.array_equal(rec[:, _lib.HS_RADIUS], sc["R_run"] * 20 / sc["D_A"])
+    assert np.array_equal(rec[:, _lib.HS_RCUT], 7 * sc["R_model_com"])
+    assert not np.allclose(sc["R_model_com"] * a, sc["R_run"])     # two cosmologies -> two R200c (§10 #6)
+
+
+def test_pixel_ranges_and_halo_assignment_cover_everything():
+    nside = 32
+    npix = 12 * nside * nside
+    for world in (1, 2, 3, 8):
+        rng_ = parallel.pixel_ranges(nside, world)
+        assert rng_[0][0] == 0 and rng_[-1][1] == npix and all(a[1] == b_[0] for a, b_ in zip(rng_, rng_[1:]))
+    pix = np.arange(npix)
+    t, _ = hpo.pix2ang(nside, pix)
+    ring = parallel.ring_of_pixel(nside, pix)
+    z_ring = np.array([hpo.lib().hpo_ring2z(nside, int(r)) for r in range(1, 4 * nside)])
+    assert np.allclose(np.cos(t), z_ring[ring - 1], atol=1e-12)
+    # every (halo, pixel) pair of the full run is owned by a rank that was given the halo
+    rng = np.random.default_rng(2)
+    theta = np.arccos(rng.uniform(-1, 1, 300)); phi = rng.uniform(0, 2 * np.pi, 300)
+    rad = 10 ** rng.uniform(-2.5, -0.3, 300)
+    world = 4
+    masks = [parallel.halos_touching_pixel_range(nside, theta, rad, lo, hi) for lo, hi in parallel.pixel_ranges(nside, world)]
+    for j in range(300):
+        p = hpo.query_disc(nside, theta[j], phi[j], rad[j])
+        if p.size < 4:
+            p = np.union1d(p, hpo.get_interpol(nside, [theta[j]], [phi[j]])[0][:, 0])
+        for r, (lo, hi) in enumerate(parallel.pixel_ranges(nside, world)):
+            if np.any((p >= lo) & (p < hi)):
+                assert masks[r][j], (j, r)
+
+
+def test_plane_assignment():
+    N = 64
+    rng = np.random.default_rng(3)
+    cen = rng.integers(0, N, 500); ns = 2 * rng.integers(1, N // 4 + 1, 500)
+    for lo, hi in parallel.plane_ranges(N, 4):
+        m = parallel.halos_touching_planes(N, cen, ns, lo, hi)
+        for j in range(500):
+            planes = (np.arange(cen[j] - ns[j] // 2, cen[j] + ns[j] // 2)) % N
+            assert m[j] == bool(np.any((planes >= lo) & (planes < hi)))

@@ -1,0 +1,68 @@
+"""
+CPU: pins oracle/healpix_ring.c (the restated third-party HEALPix boundary).
+healpy is not installed, and the reference's own tests hold no golden vectors for it, so the pins are
+(a) the known-answer values printed in healpy's public docstrings (pix2ang / ang2pix / pix2vec / get_interp_weights /
+nside2resol / nside2pixarea), and (b) brute-force geometry.
+"""
+import numpy as np
+
+from oracle import hpo
+
+
+def test_healpy_docstring_known_answers():
+    t, p = hpo.pix2ang(16, [1440, 427, 1520, 0, 3068])
+    assert np.allclose(t, [1.52911759, 0.78550497, 1.57079633, 0.05103658, 3.09055608], atol=5e-9)
+    assert np.allclose(p[:4], [0.0, 0.78539816, 1.61988371, 0.78539816], atol=5e-9)
+    assert hpo.ang2pix(16, np.pi / 2, 0.0)[0] == 1440
+    got = hpo.ang2pix(16, [np.pi / 2, np.pi / 4, np.pi / 2, 0, np.pi], [0., np.pi / 4, np.pi / 2 + 1e-15, 0, 0])
+    assert list(got) == [1440, 427, 1520, 0, 3068]
+    x, y, z = hpo.pix2vec(16, 1504)
+    assert np.allclose([x[0], y[0], z[0]], [0.99879545620517241, 0.049067674327418015, 0.0], atol=1e-15)
+    x, y, z = hpo.pix2vec(16, [1440, 427])
+    assert np.allclose(x, [0.99913157, 0.5000534], atol=5e-9) and np.allclose(z, [0.04166667, 0.70703125], atol=5e-9)
+    # hp.get_interp_weights(1, 0, 0) and (1, [0, pi/2], 0)
+    pix, w = hpo.get_interpol(1, [0.0, np.pi / 2], [0.0, 0.0])
+    assert pix[:, 0].tolist() == [1, 2, 3, 0] and np.allclose(w[:, 0], 0.25)
+    assert pix[:, 1].tolist() == [4, 5, 11, 8] and np.allclose(w[:, 1], [1, 0, 0, 0])
+    # hp.get_interp_weights(1, 0): the centre of pixel 0
+    t0, p0 = hpo.pix2ang(1, [0])
+    pix, w = hpo.get_interpol(1, t0, p0)
+    assert pix[:, 0].tolist() == [0, 1, 4, 5] and np.allclose(w[:, 0], [1, 0, 0, 0])
+
+
+def test_roundtrip_and_weights():
+    rng = np.random.default_rng(0)
+    for nside in (1, 2, 3, 8, 64, 1024):
+        npix = 12 * nside * nside
+        pix = np.arange(npix) if npix < 60000 else rng.integers(0, npix, 50000)
+        t, p = hpo.pix2ang(nside, pix)
+        assert np.array_equal(hpo.ang2pix(nside, t, p), pix)
+        th = np.arccos(rng.uniform(-1, 1, 5000)); ph = rng.uniform(0, 2 * np.pi, 5000)
+        ip, w = hpo.get_interpol(nside, th, ph)
+        assert np.allclose(w.sum(axis=0), 1.0, atol=1e-12)
+        assert w.min() > -1e-12 and w.max() < 1 + 1e-12
+        assert ip.min() >= 0 and ip.max() < npix
+        # weight 1 at a pixel centre
+        ip, w = hpo.get_interpol(nside, t[:200], p[:200])
+        assert np.allclose(w.max(axis=0), 1.0, atol=1e-9)
+        assert np.array_equal(ip[np.argmax(w, axis=0), np.arange(ip.shape[1])], pix[:200])
+
+
+def test_query_disc_equals_brute_force():
+    rng = np.random.default_rng(1)
+    for nside in (1, 2, 4, 16, 64):
+        npix = 12 * nside * nside
+        V = np.stack(hpo.pix2vec(nside, np.arange(npix)), axis=1)
+        for k in range(250):
+            v = rng.normal(size=3)
+            if k % 8 == 0:
+                v = np.array([1e-3 * rng.normal(), 1e-3 * rng.normal(), rng.choice([-1.0, 1.0])])
+            v /= np.linalg.norm(v)
+            rad = 10 ** rng.uniform(-2.5, 0.55)
+            theta, phi = hpo.vec2pointing(v)
+            got = hpo.query_disc(nside, theta, phi, rad)
+            assert np.all(np.diff(got) > 0)            # ascending, no duplicates
+            ang = np.arccos(np.clip(V @ v, -1, 1))
+            want = np.where(ang < rad)[0]
+            d = np.setxor1d(got, want)
+            assert d.size == 0 or np.max(np.abs(ang[d] - rad)) < 1e-9   # only round-off ties may differ
