@@ -188,7 +188,7 @@ __global__ void k_transpose_offsets(const double *__restrict__ in, double *__res
 }
 
 extern "C" int bfg_transpose_offsets(const double *d_in, double *d_out, int64_t n, int ncomp, void *stream) {
-    BFG_REQUIRE(d_in && d_out && ncomp >= 1 && ncomp <= 3, "bad argument");
+    BFG_REQUIRE(d_in && d_out && ncomp >= 1 && ncomp <= 64, "bad argument");
     if (n == 0) return BFG_OK;
     int blocks = (int)std::min<i64>((n + 255) / 256, 148 * 16);
     k_transpose_offsets<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_in, d_out, n, ncomp);

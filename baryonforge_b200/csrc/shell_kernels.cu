@@ -16,6 +16,7 @@ using namespace bfg;
 namespace {
 
 constexpr int SHELL_THREADS = 128;
+constexpr int RING_CHUNK = SHELL_THREADS;   // ring segments staged in shared memory per pass (one per thread)
 
 struct HaloSph {
     double vx, vy, vz, theta, phi, D, a, radius, lnz, lnM, rcut, lnRcom, scale, theta_ll, phi_ll;
@@ -32,111 +33,161 @@ __device__ __forceinline__ HaloSph load_halo(const double *__restrict__ H) {
     return s;
 }
 
-// One (halo, pixel) update.  (x, y, z) is the pixel's unit vector.
+// Per-halo constants of the pixel update, hoisted out of the pixel loop.
+struct HaloUpd {
+    double D, a, pjx, pjy, pjz;   // pos_j = vec_j * D                            HealpixRunner.py:337
+    double ln_inv_a;              // ln(1/a): ln(r_sep/a) = 0.5 ln(r^2) + ln(1/a)  :345
+    double rcut2;                 // (model eps * R_com * a)^2 : r_com < rcut  <=>  r_sep^2 < rcut2   BaryonCorrection.py:410
+    double lnRcom, scale;
+};
+
+__device__ __forceinline__ HaloUpd make_upd(const HaloSph &s) {
+    HaloUpd u;
+    u.D = s.D; u.a = s.a;
+    u.pjx = s.vx * s.D; u.pjy = s.vy * s.D; u.pjz = s.vz * s.D;
+    u.ln_inv_a = s.lnz;           // the record's ln(1/a) is exactly this quantity
+    double rc = s.rcut * s.a;
+    u.rcut2 = rc * rc;
+    u.lnRcom = s.lnRcom; u.scale = s.scale;
+    return u;
+}
+
+// One (halo, pixel) update.  (x, y, z) = pixel unit vector; (px, py, pz) = (x, y, z) * D.
 template <bool PAINT, bool UNIFORM>
 __device__ __forceinline__ void shell_update(const TableView &T, const double *__restrict__ row, bool valid,
-                                             const HaloSph &s, double x, double y, double z, double *__restrict__ out,
-                                             i64 nloc, i64 lp) {
-    // HealpixRunner.py:337-341  pos = vec*D ; diff = pos - pos_j ; r_sep = sqrt(sum(diff^2))
-    double px = x * s.D, py = y * s.D, pz = z * s.D;
-    double dx = px - s.vx * s.D, dy = py - s.vy * s.D, dz = pz - s.vz * s.D;
-    double r_sep = sqrt(dx * dx + dy * dy + dz * dz);
-    double rc = r_sep / s.a;                       // :345 / :472 comoving radius handed to the model
-    double xq = log(rc);
-    if (T.flags & BFG_TABLE_RDELTA) xq -= s.lnRcom;
+                                             const HaloUpd &u, double x, double y, double z, double px, double py,
+                                             double pz, double *__restrict__ out, i64 nloc, i64 lp) {
+    // HealpixRunner.py:338-341  diff = pos - pos_j ; r_sep^2 = sum(diff^2)
+    double dx = px - u.pjx, dy = py - u.pjy, dz = pz - u.pjz;
+    double r2 = dx * dx + dy * dy + dz * dz;
+    // ln(r_sep / a) without the square root and the division  (:345 / :472)
+    double xq = 0.5 * log(r2) + u.ln_inv_a;
+    if (T.flags & BFG_TABLE_RDELTA) xq -= u.lnRcom;
     double val = row_lookup<UNIFORM>(T, row, xq);
     if (!valid) val = CUDART_NAN;
     if (PAINT) {
         val = exp(val);                            // Tabulate.py:319
         if (!isfinite(val)) return;                // HealpixRunner.py:473 (adds 0)
-        val *= s.scale;                            // :478
+        val *= u.scale;                            // :478
         if (val != 0.0) red_add(out + lp, val);    // :481
     } else {
-        val = (rc < s.rcut) ? val : 0.0;           // BaryonCorrection.py:410-411
-        double off = val * s.a;                    // HealpixRunner.py:345
-        double ox = off * (dx / r_sep), oy = off * (dy / r_sep), oz = off * (dz / r_sep);  // :346
-        if (!isfinite(ox)) ox = 0.0;               // :347, element-wise
-        if (!isfinite(oy)) oy = 0.0;
-        if (!isfinite(oz)) oz = 0.0;
-        if (ox == 0.0 && oy == 0.0 && oz == 0.0) return;   // delta would be round-off only
-        double nx = px + ox, ny = py + oy, nz = pz + oz;   // :350
-        double nn = sqrt(nx * nx + ny * ny + nz * nz);
-        red_add(out + lp, nx / nn - x);                    // :351-355
-        red_add(out + nloc + lp, ny / nn - y);
-        red_add(out + 2 * nloc + lp, nz / nn - z);
+        val = (r2 < u.rcut2) ? val : 0.0;          // BaryonCorrection.py:410-411
+        double sc = (val * u.a) * rsqrt(r2);       // offset / r_sep                 HealpixRunner.py:345-346
+        // :347 non-finite -> 0 (r_sep = 0, NaN/inf table value, outside the table); exact zeros add nothing
+        if (!isfinite(sc) || sc == 0.0) return;
+        double nx = px + sc * dx, ny = py + sc * dy, nz = pz + sc * dz;   // :350 nw_pos = pos + offset
+        double ninv = rsqrt(nx * nx + ny * ny + nz * nz);
+        red_add(out + lp, nx * ninv - x);                                 // :351-355
+        red_add(out + nloc + lp, ny * ninv - y);
+        red_add(out + 2 * nloc + lp, nz * ninv - z);
     }
 }
+
+// A (halo, ring) segment staged in shared memory by the thread that derived it.
+struct RingSeg {
+    i64 lbase;             // ring's first pixel - pix_lo
+    int nr, ip_lo, cnt, shifted;
+    double z, sth;         // ring z, sin(theta)
+    double rotS, rotC;     // sin / cos of 32 pixel steps in azimuth
+};
 
 template <bool PAINT, bool UNIFORM>
 __global__ void __launch_bounds__(SHELL_THREADS)
 k_shell_halos(TableView T, Hpx h, i64 n_halo, const double *__restrict__ halos, const double *__restrict__ extras,
               int n_extra, double *__restrict__ out, i64 pix_lo, i64 pix_hi, unsigned long long *nupd) {
     extern __shared__ double row[];
-    __shared__ i64 s_cnt[SHELL_THREADS / 32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    constexpr int NW = SHELL_THREADS / 32;
+    __shared__ RingSeg segs[RING_CHUNK];
+    __shared__ int s_next;
+    const int lane = threadIdx.x & 31;
     const i64 nloc = pix_hi - pix_lo;
     i64 done = 0;
 
     for (i64 j = blockIdx.x; j < n_halo; j += gridDim.x) {
         const HaloSph s = load_halo(halos + j * BFG_HALO_STRIDE);
-        __syncthreads();  // previous halo's row no longer in use
+        __syncthreads();  // previous halo's row / segments no longer in use
         bool valid;
         blend_row(T, s.lnz, s.lnM, extras ? extras + j * n_extra : nullptr, row, valid);
         const DiscRings d = disc_rings(h, s.theta, s.phi, s.radius);
+        const HaloUpd u = make_upd(s);
+        // `if pixind.size < 4` (HealpixRunner.py:333) can only trigger for discs of a few pixels (<= ~12 rings)
+        const bool tiny = !PAINT && (s.radius * s.radius * (double)h.npix * 0.25 < 64.0);
 
-        bool fallback = false;
-        if (!PAINT) {
-            // `if pixind.size < 4` (HealpixRunner.py:333): only discs of a few pixels can get there
-            double expect = s.radius * s.radius * (double)h.npix * 0.25;
-            if (expect < 64.0) {
-                i64 c = 0;
-                for (i64 iz = d.ra + threadIdx.x; iz <= d.rb; iz += SHELL_THREADS) {
+        for (i64 base = d.ra; base <= d.rb; base += RING_CHUNK) {
+            // ---- stage up to RING_CHUNK ring segments: one ring per thread ------------------------------
+            {
+                i64 iz = base + threadIdx.x;
+                RingSeg g;
+                g.cnt = 0; g.nr = 0;
+                if (iz <= d.rb) {
                     i64 start, nr, ip_lo, cnt; bool sh;
                     disc_ring_span(h, d, iz, start, nr, sh, ip_lo, cnt);
-                    c += cnt;
+                    g.cnt = (int)cnt;     // counted even when the ring is outside the owned range (fallback test)
+                    g.nr = 0;             // nr == 0 marks "nothing to do here"
+                    if (cnt > 0 && start < pix_hi && start + nr > pix_lo) {
+                        g.lbase = start - pix_lo;
+                        g.nr = (int)nr; g.ip_lo = (int)ip_lo; g.shifted = sh ? 1 : 0;
+                        ring_z_sth(h, iz, g.z, g.sth);
+                        sincospi(64.0 / (double)nr, &g.rotS, &g.rotC);   // 32 pixels * (2/nr) half-turns
+                    }
                 }
-                c = warp_sum_i64(c);
-                if (lane == 0) s_cnt[warp] = c;
-                __syncthreads();
-                i64 tot = 0;
-                for (int w = 0; w < NW; ++w) tot += s_cnt[w];
-                fallback = tot < 4;
+                segs[threadIdx.x] = g;
+                if (threadIdx.x == 0) s_next = 0;
             }
-        }
-        __syncthreads();  // row ready
+            __syncthreads();  // segments + row ready
+            const int nseg = (int)min((i64)RING_CHUNK, d.rb - base + 1);
 
-        if (fallback) {
-            if (threadIdx.x < 4) {
-                i64 pix[4]; double w[4];
-                get_interpol(h, s.theta_ll, s.phi_ll, pix, w);   // HealpixRunner.py:334
-                i64 p = pix[threadIdx.x];
-                if (p >= pix_lo && p < pix_hi) {
-                    double x, y, z;
-                    pix2vec(h, p, x, y, z);
-                    shell_update<PAINT, UNIFORM>(T, row, valid, s, x, y, z, out, nloc, p - pix_lo);
-                    ++done;
+            if (tiny) {   // whole disc is in this chunk: count it
+                int tot = 0;
+                for (int r = 0; r < nseg; ++r) tot += segs[r].cnt;
+                if (tot < 4) {
+                    if (threadIdx.x < 4) {
+                        i64 pix[4]; double w[4];
+                        get_interpol(h, s.theta_ll, s.phi_ll, pix, w);   // HealpixRunner.py:334
+                        i64 p = pix[threadIdx.x];
+                        if (p >= pix_lo && p < pix_hi) {
+                            double x, y, z;
+                            pix2vec(h, p, x, y, z);
+                            shell_update<PAINT, UNIFORM>(T, row, valid, u, x, y, z, x * u.D, y * u.D, z * u.D, out, nloc,
+                                                         p - pix_lo);
+                            ++done;
+                        }
+                    }
+                    break;   // uniform across the block
                 }
             }
-            continue;
-        }
 
-        for (i64 iz = d.ra + warp; iz <= d.rb; iz += NW) {
-            i64 start, nr, ip_lo, cnt; bool sh;
-            disc_ring_span(h, d, iz, start, nr, sh, ip_lo, cnt);
-            if (cnt == 0 || start >= pix_hi || start + nr <= pix_lo) continue;
-            double z, sth;
-            ring_z_sth(h, iz, z, sth);
-            for (i64 i = lane; i < cnt; i += 32) {
-                i64 ip = ip_lo + i;
+            // ---- warps pull ring segments; lanes walk consecutive pixels -------------------------------
+            for (;;) {
+                int r = 0;
+                if (lane == 0) r = atomicAdd(&s_next, 1);
+                r = __shfl_sync(0xffffffffu, r, 0);
+                if (r >= nseg) break;
+                const int cnt = segs[r].cnt;
+                const int nr = segs[r].nr;
+                if (cnt == 0 || nr == 0) continue;
+                const i64 lbase = segs[r].lbase;
+                const double z = segs[r].z, sth = segs[r].sth;
+                const double pz = z * u.D, sD = sth * u.D;
+                int ip = segs[r].ip_lo + lane;
                 if (ip >= nr) ip -= nr;
-                i64 p = start + ip;
-                if (p < pix_lo || p >= pix_hi) continue;
                 double sn, cs;
-                sincos(ring_phi(h, iz, ip, sh), &sn, &cs);
-                shell_update<PAINT, UNIFORM>(T, row, valid, s, sth * cs, sth * sn, z, out, nloc, p - pix_lo);
-                ++done;
+                sincospi(((double)ip + (segs[r].shifted ? 0.5 : 0.0)) * (2.0 / (double)nr), &sn, &cs);
+                const double rotS = segs[r].rotS, rotC = segs[r].rotC;
+                for (int i = lane; i < cnt; i += 32) {
+                    i64 lp = lbase + ip;
+                    if ((unsigned long long)lp < (unsigned long long)nloc) {
+                        shell_update<PAINT, UNIFORM>(T, row, valid, u, sth * cs, sth * sn, z, sD * cs, sD * sn, pz, out,
+                                                     nloc, lp);
+                        ++done;
+                    }
+                    ip += 32;
+                    if (ip >= nr) ip -= nr;
+                    double c2 = cs * rotC - sn * rotS;   // advance the azimuth by 32 pixels
+                    sn = sn * rotC + cs * rotS;
+                    cs = c2;
+                }
             }
+            __syncthreads();  // before the next chunk overwrites the segments
         }
     }
     if (nupd) {

@@ -1,0 +1,96 @@
+// sort_kernels.cu -- locality ordering of halo records ("halo batches sorted by sky or box cell", north_star (b)).
+//
+// The reference walks halos in catalogue order (Runners/HealpixRunner.py:315, Map2DRunner.py:482, SnapshotRunner.py:217);
+// the sums it accumulates are order-independent up to fp64 round-off.  On the GPU ~700 halos are in flight at once, so
+// putting sky/box neighbours next to each other keeps the pixels/cells/particles they share resident in the 126 MB L2:
+// the fp64 REDs then hit L2 instead of forcing an HBM read-modify-write per update.
+#include <cub/device/device_radix_sort.cuh>
+#include "bfg_common.cuh"
+
+using namespace bfg;
+
+namespace {
+
+// sky: colatitude bands of width `band`, serpentine in azimuth so consecutive bands join up
+__global__ void k_keys_sky(i64 n, const double *__restrict__ halos, double band, unsigned long long *__restrict__ keys,
+                           unsigned int *__restrict__ idx) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        double theta = halos[i * BFG_HALO_STRIDE + BFG_HS_THETA], phi = halos[i * BFG_HALO_STRIDE + BFG_HS_PHI];
+        unsigned long long b = (unsigned long long)fmin(fmax(theta / band, 0.0), 1048575.0);
+        double f = fmin(fmax(phi * BFG_INV_TWOPI, 0.0), 0.99999999);
+        unsigned long long q = (unsigned long long)(f * 16777216.0);   // 24 bits of azimuth
+        if (b & 1ULL) q = 16777215ULL - q;
+        keys[i] = (b << 24) | q;
+        idx[i] = (unsigned int)i;
+    }
+}
+
+// box: coarse raster cells of side L / nc, serpentine along the last axis
+__global__ void k_keys_box(i64 n, const double *__restrict__ halos, double L, int nc, int ndim,
+                           unsigned long long *__restrict__ keys, unsigned int *__restrict__ idx) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        unsigned long long key = 0;
+        for (int d = 0; d < ndim; ++d) {
+            double x = halos[i * BFG_HALO_STRIDE + BFG_HB_X + d];
+            int c = (int)floor(x / L * (double)nc);
+            c = min(max(c, 0), nc - 1);
+            if (d == ndim - 1 && (key & 1ULL)) c = nc - 1 - c;
+            key = key * (unsigned long long)nc + (unsigned long long)c;
+        }
+        keys[i] = key;
+        idx[i] = (unsigned int)i;
+    }
+}
+
+__global__ void k_gather_rows(i64 n, int width, const unsigned int *__restrict__ idx, const double *__restrict__ in,
+                              double *__restrict__ out) {
+    i64 total = n * width;
+    for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (i64)gridDim.x * blockDim.x) {
+        i64 r = t / width;
+        int c = (int)(t - r * width);
+        out[t] = in[(i64)idx[r] * width + c];
+    }
+}
+
+}  // namespace
+
+extern "C" int bfg_halo_sort(int mode, int64_t n_halo, const double *d_in, double *d_out, const double *d_extras_in,
+                             double *d_extras_out, int n_extra, double p0, double p1, int ndim, void *stream) {
+    BFG_REQUIRE(d_in && d_out && d_in != d_out, "need distinct in/out record buffers");
+    BFG_REQUIRE(mode == 0 || mode == 1, "mode: 0 = sky bands, 1 = box cells");
+    BFG_REQUIRE(n_halo >= 0 && n_halo < ((int64_t)1 << 32), "n_halo out of range");
+    BFG_REQUIRE(n_extra == 0 || (d_extras_in && d_extras_out), "extras missing");
+    if (n_halo == 0) return BFG_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long *keys = nullptr, *keys2 = nullptr;
+    unsigned int *idx = nullptr, *idx2 = nullptr;
+    void *tmp = nullptr;
+    size_t tmp_bytes = 0;
+    BFG_CUDA_OK(cudaMallocAsync(&keys, sizeof(unsigned long long) * n_halo * 2, st));
+    BFG_CUDA_OK(cudaMallocAsync(&idx, sizeof(unsigned int) * n_halo * 2, st));
+    keys2 = keys + n_halo;
+    idx2 = idx + n_halo;
+    int blocks = (int)std::max<i64>(1, std::min<i64>((n_halo + 255) / 256, 148 * 8));
+    int end_bit = 64;
+    if (mode == 0) {
+        BFG_REQUIRE(p0 > 0, "band width must be positive");
+        k_keys_sky<<<blocks, 256, 0, st>>>(n_halo, d_in, p0, keys, idx);
+        end_bit = 24 + 20;
+    } else {
+        BFG_REQUIRE(p0 > 0 && p1 >= 1 && p1 <= 1024 && (ndim == 2 || ndim == 3), "bad box parameters");
+        k_keys_box<<<blocks, 256, 0, st>>>(n_halo, d_in, p0, (int)p1, ndim, keys, idx);
+        end_bit = 32;
+    }
+    BFG_CUDA_OK(cudaGetLastError());
+    BFG_CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys2, idx, idx2, (int)n_halo, 0, end_bit, st));
+    BFG_CUDA_OK(cudaMallocAsync(&tmp, tmp_bytes, st));
+    BFG_CUDA_OK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys2, idx, idx2, (int)n_halo, 0, end_bit, st));
+    int gblocks = (int)std::max<i64>(1, std::min<i64>((n_halo * BFG_HALO_STRIDE + 255) / 256, 148 * 16));
+    k_gather_rows<<<gblocks, 256, 0, st>>>(n_halo, BFG_HALO_STRIDE, idx2, d_in, d_out);
+    if (n_extra) k_gather_rows<<<gblocks, 256, 0, st>>>(n_halo, n_extra, idx2, d_extras_in, d_extras_out);
+    BFG_CUDA_OK(cudaGetLastError());
+    BFG_CUDA_OK(cudaFreeAsync(tmp, st));
+    BFG_CUDA_OK(cudaFreeAsync(idx, st));
+    BFG_CUDA_OK(cudaFreeAsync(keys, st));
+    return BFG_OK;
+}

@@ -33,6 +33,42 @@ def _to_device(arr, device, dtype=None):
     return t.to(device, non_blocking=True)
 
 
+def _upload_records(rec, dev):
+    """Halo records to the device as [n][16].  `halo_records` builds them field-major (each field one contiguous numpy
+    vector); that buffer is copied as is and transposed on the device, which is much cheaper than 16 strided host writes."""
+    torch = _torch()
+    n = rec.shape[0]
+    if n > 0 and rec.T.flags.c_contiguous and not rec.flags.c_contiguous:
+        d_t = torch.from_numpy(rec.T).to(dev, non_blocking=True)
+        d_rec = torch.empty((n, _lib.HALO_STRIDE), dtype=torch.float64, device=dev)
+        _lib.check(_lib.lib().bfg_transpose_offsets(_lib.ptr(d_t), _lib.ptr(d_rec), n, _lib.HALO_STRIDE,
+                                                    _lib.current_stream()))
+        return d_rec
+    return _to_device(rec, dev)
+
+
+def _sort_records(d_rec, d_ext, mode, p0, p1=0.0, ndim=3):
+    """Locality ordering on the device (bfg_halo_sort); returns the re-ordered (records, extras)."""
+    torch = _torch()
+    n = d_rec.shape[0]
+    if n < 2:
+        return d_rec, d_ext
+    out = torch.empty_like(d_rec)
+    out_e = None if d_ext is None else torch.empty_like(d_ext)
+    _lib.check(_lib.lib().bfg_halo_sort(mode, n, _lib.ptr(d_rec), _lib.ptr(out), _lib.ptr(d_ext), _lib.ptr(out_e),
+                                        0 if d_ext is None else d_ext.shape[1], float(p0), float(p1), ndim,
+                                        _lib.current_stream()))
+    return out, out_e
+
+
+def _all_close_to_zero(a):
+    """np.allclose(a, 0) (HealpixRunner.py:293) without scanning a 1.6 GB map when its first entries already say no."""
+    head = a.reshape(-1)[:4096]
+    if head.size and not np.all(np.abs(head) <= 1e-8):
+        return False
+    return bool(np.allclose(a, 0))
+
+
 def _check_keys(model, keys):
     """HealpixRunner.py:304-311: p_keys need a table model that carries them."""
     if len(keys) > 0 and not (hasattr(model, 'interp_d') or hasattr(model, 'interp2D')):
@@ -56,6 +92,9 @@ def _model_cosmo(model, fallback):
     return c
 
 
+SKY_BAND_RAD = 0.04     # colatitude band width of the sky ordering (~160 pixels at NSIDE=4096)
+
+
 class _TableCache(object):
     """Tables go to the device once per (model, table) and are re-used by later process() calls."""
 
@@ -77,7 +116,8 @@ class DefaultRunner(object):
     """Constructor contract of BaryonForge/Runners/HealpixRunner.py:160-177 (+ keyword-only GPU knobs)."""
 
     def __init__(self, HaloLightConeCatalog, LightconeShell, epsilon_max, model, use_ellipticity=False,
-                 mass_def=None, include_pixel_size=False, verbose=True, *, device=None, pix_range=None):
+                 mass_def=None, include_pixel_size=False, verbose=True, *, device=None, pix_range=None,
+                 sort_halos=True):
         self.HaloLightConeCatalog = HaloLightConeCatalog
         self.LightconeShell = LightconeShell
         self.cosmo = HaloLightConeCatalog.cosmology
@@ -89,6 +129,7 @@ class DefaultRunner(object):
         self.include_pixel_size = include_pixel_size
         self.device = device
         self.pix_range = pix_range        # (lo, hi) RING range owned by this rank (parallel.py); None = whole map
+        self.sort_halos = sort_halos      # order halos by sky cell on the device before the halo loop (L2 locality)
         self.last_stats = {}
         self._tables = _TableCache()
         if use_ellipticity:
@@ -118,7 +159,7 @@ class DefaultRunner(object):
         cosmo = cosmology.runner_cosmology(self.cosmo, with_w0=True)          # :280-284
         M, z = cat['M'], cat['z']
         a = 1 / (1 + z)                                                        # :319
-        rec = np.zeros((n, _lib.HALO_STRIDE), dtype=np.float64)
+        rec = np.zeros((_lib.HALO_STRIDE, n), dtype=np.float64).T              # field-major storage, [n,16] view
         if n == 0:
             return rec, None
         R = cosmology.radius_of_mass(cosmo, M, a, self.mass_def)               # :320 physical Mpc
@@ -161,6 +202,8 @@ class DefaultRunner(object):
             return rec, extras
         from .parallel import halos_touching_pixel_range
         keep = halos_touching_pixel_range(nside, rec[:, _lib.HS_THETA], rec[:, _lib.HS_RADIUS], lo, hi)
+        if keep.all():
+            return rec, extras
         return np.ascontiguousarray(rec[keep]), (None if extras is None else np.ascontiguousarray(extras[keep]))
 
 
@@ -175,13 +218,16 @@ class BaryonifyShell(DefaultRunner):
         NSIDE = self.LightconeShell.NSIDE
         npix = 12 * NSIDE * NSIDE
         lo, hi = self._range(npix)
+        with torch.cuda.device(dev):   # table first: a model without one fails here, as in the reference
+            table = self._tables.get((id(self.model), id(self.model.interp_d) if hasattr(self.model, 'interp_d') else 0),
+                                     lambda: displacement_table_of(self.model, dev.index))
         rec, extras = self.halo_records(paint=False)
         rec, extras = self._owned_halos(rec, extras, NSIDE, lo, hi)
         with torch.cuda.device(dev):
-            table = self._tables.get((id(self.model), id(self.model.interp_d) if hasattr(self.model, 'interp_d') else 0),
-                                     lambda: displacement_table_of(self.model, dev.index))
-            d_rec = _to_device(rec, dev)
+            d_rec = _upload_records(rec, dev)
             d_ext = None if extras is None else _to_device(extras, dev)
+            if self.sort_halos:
+                d_rec, d_ext = _sort_records(d_rec, d_ext, 0, SKY_BAND_RAD)
             d_off = torch.zeros((3, hi - lo), dtype=torch.float64, device=dev)
             d_n = torch.zeros(1, dtype=torch.int64, device=dev)
             _lib.check(L.bfg_shell_offsets(table.handle, NSIDE, rec.shape[0], _lib.ptr(d_rec), _lib.ptr(d_ext),
@@ -192,7 +238,7 @@ class BaryonifyShell(DefaultRunner):
         torch = _torch()
         orig_map = self.LightconeShell.map
         NSIDE = self.LightconeShell.NSIDE
-        if np.allclose(orig_map, 0):                 # :293-294 returns the input object
+        if _all_close_to_zero(orig_map):             # :293-294 returns the input object
             return orig_map
         dev = self._device()
         L = _lib.lib()
@@ -239,13 +285,16 @@ class PaintProfilesShell(DefaultRunner):
         NSIDE = self.LightconeShell.NSIDE
         npix = self.LightconeShell.map.size
         lo, hi = self._range(npix)
-        rec, extras = self.halo_records(paint=True)
-        rec, extras = self._owned_halos(rec, extras, NSIDE, lo, hi)
         with torch.cuda.device(dev):
             table = self._tables.get((id(self.model), id(getattr(self.model, 'interp2D', None))),
                                      lambda: profile_table_of(self.model, '2D', dev.index))
-            d_rec = _to_device(rec, dev)
+        rec, extras = self.halo_records(paint=True)
+        rec, extras = self._owned_halos(rec, extras, NSIDE, lo, hi)
+        with torch.cuda.device(dev):
+            d_rec = _upload_records(rec, dev)
             d_ext = None if extras is None else _to_device(extras, dev)
+            if self.sort_halos:
+                d_rec, d_ext = _sort_records(d_rec, d_ext, 0, SKY_BAND_RAD)
             d_new = torch.zeros(hi - lo, dtype=torch.float64, device=dev)
             d_n = torch.zeros(1, dtype=torch.int64, device=dev)
             _lib.check(L.bfg_shell_paint(table.handle, NSIDE, rec.shape[0], _lib.ptr(d_rec), _lib.ptr(d_ext),
@@ -327,7 +376,7 @@ class DefaultRunnerGrid(object):
         M32 = cat['M'].astype('<f4')                                              # io.py:204-205
         M = M32.astype(np.float64)
         a = 1 / (1 + self.HaloNDCatalog.redshift)                                 # :490
-        rec = np.zeros((n, _lib.HALO_STRIDE), dtype=np.float64)
+        rec = np.zeros((_lib.HALO_STRIDE, n), dtype=np.float64).T
         if n == 0:
             return rec, None
         R_phys = cosmology.radius_of_mass(cosmo, M, a, self.mass_def)             # :491
@@ -379,8 +428,9 @@ class BaryonifyGrid(DefaultRunnerGrid):
         with torch.cuda.device(dev):
             table = self._tables.get((id(self.model), id(getattr(self.model, 'interp_d', None))),
                                      lambda: displacement_table_of(self.model, dev.index))
-            d_rec = _to_device(rec, dev)
+            d_rec = _upload_records(rec, dev)
             d_ext = None if extras is None else _to_device(extras, dev)
+            d_rec, d_ext = _sort_records(d_rec, d_ext, 1, float(gm.L), 16, ndim)
             nloc = (hi - lo) * N ** (ndim - 1)
             d_off = torch.zeros((ndim, nloc), dtype=torch.float64, device=dev)
             d_n = torch.zeros(1, dtype=torch.int64, device=dev)
@@ -442,8 +492,9 @@ class PaintProfilesGrid(DefaultRunnerGrid):
         with torch.cuda.device(dev):
             table = self._tables.get((id(self.model), which, id(getattr(self.model, 'interp' + which, None))),
                                      lambda: profile_table_of(self.model, which, dev.index))
-            d_rec = _to_device(rec, dev)
+            d_rec = _upload_records(rec, dev)
             d_ext = None if extras is None else _to_device(extras, dev)
+            d_rec, d_ext = _sort_records(d_rec, d_ext, 1, float(gm.L), 16, ndim)
             nloc = (hi - lo) * N ** (ndim - 1)
             d_new = torch.zeros(nloc, dtype=torch.float64, device=dev)
             d_n = torch.zeros(1, dtype=torch.int64, device=dev)
@@ -497,7 +548,7 @@ class DefaultRunnerSnapshot(object):
         M32 = cat['M'].astype('<f4')
         M = M32.astype(np.float64)
         a = 1 / (1 + self.HaloNDCatalog.redshift)                                 # :225
-        rec = np.zeros((n, _lib.HALO_STRIDE), dtype=np.float64)
+        rec = np.zeros((_lib.HALO_STRIDE, n), dtype=np.float64).T
         if n == 0:
             return rec, None
         R_phys = cosmology.radius_of_mass(cosmo, M, a, self.mass_def)             # :226
@@ -550,8 +601,9 @@ class BaryonifySnapshot(DefaultRunnerSnapshot):
             _lib.check(L.bfg_snap_build_cells(ndim, n_part, _lib.ptr(d_p[0]), _lib.ptr(d_p[1]), _lib.ptr(d_p[2]), Lbox,
                                               ncell, _lib.ptr(d_start), _lib.ptr(d_order), _lib.ptr(d_s[0]),
                                               _lib.ptr(d_s[1]), _lib.ptr(d_s[2]), st))
-            d_rec = _to_device(rec, dev)
+            d_rec = _upload_records(rec, dev)
             d_ext = None if extras is None else _to_device(extras, dev)
+            d_rec, d_ext = _sort_records(d_rec, d_ext, 1, Lbox, 16, ndim)
             d_tot = torch.zeros((ndim, n_part), dtype=torch.float64, device=dev)
             d_n = torch.zeros(1, dtype=torch.int64, device=dev)
             _lib.check(L.bfg_snap_offsets(table.handle, ndim, n_part, _lib.ptr(d_s[0]), _lib.ptr(d_s[1]), _lib.ptr(d_s[2]),

