@@ -52,6 +52,7 @@ _SIGNATURES = {
     "bfg_snap_apply": ([C.c_int, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr], C.c_int),
     "bfg_snap_deposit_ngp": ([C.c_int, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_dbl, c_i64, c_ptr, c_ptr], C.c_int),
     "bfg_halo_sort": ([C.c_int, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, c_dbl, c_dbl, C.c_int, c_ptr], C.c_int),
+    "bfg_test_fast_log2": ([c_i64, c_ptr, c_ptr, c_ptr], C.c_int),
     "bfg_sum_f64": ([c_ptr, c_i64, c_ptr, c_ptr], C.c_int),
     "bfg_transpose_offsets": ([c_ptr, c_ptr, c_i64, C.c_int, c_ptr], C.c_int),
     "bfg_shell_baryonify_host": ([c_ptr, C.c_int, c_i64, c_ptr, c_ptr, C.c_int, c_ptr, c_ptr, C.POINTER(c_i64),

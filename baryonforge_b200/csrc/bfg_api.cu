@@ -3,6 +3,7 @@
 #include <string.h>
 #include <vector>
 #include <cmath>
+#include <algorithm>
 #include "bfg_common.cuh"
 
 namespace bfg {
@@ -16,6 +17,48 @@ void set_error(const char *fmt, ...) {
 }  // namespace bfg
 
 using namespace bfg;
+
+namespace bfg {
+int get_log2_table(const double2 **d_tab) {
+    static double2 *tabs[64] = {nullptr};
+    int dev = 0;
+    BFG_CUDA_OK(cudaGetDevice(&dev));
+    BFG_REQUIRE(dev >= 0 && dev < 64, "device index out of range");
+    if (!tabs[dev]) {
+        double2 h[BFG_LOG2_TAB];
+        for (int i = 0; i < BFG_LOG2_TAB; ++i) {
+            long double c = 1.0L + ((long double)i + 0.5L) / (long double)BFG_LOG2_TAB;
+            double rc = (double)(1.0L / c);
+            h[i].x = rc;
+            h[i].y = (double)(-log2l((long double)rc));   // consistent with the ROUNDED reciprocal
+        }
+        double2 *d = nullptr;
+        BFG_CUDA_OK(cudaMalloc(&d, sizeof(h)));
+        BFG_CUDA_OK(cudaMemcpy(d, h, sizeof(h), cudaMemcpyHostToDevice));
+        tabs[dev] = d;
+    }
+    *d_tab = tabs[dev];
+    return BFG_OK;
+}
+}  // namespace bfg
+
+// test entry: out[i] = fast_log2(x[i])
+__global__ void k_fast_log2(i64 n, const double2 *__restrict__ g_tab, const double *__restrict__ x, double *__restrict__ out) {
+    __shared__ double2 tab[BFG_LOG2_TAB];
+    load_log2_table(tab, g_tab);
+    __syncthreads();
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) out[i] = fast_log2(x[i], tab);
+}
+
+extern "C" int bfg_test_fast_log2(int64_t n, const double *d_x, double *d_out, void *stream) {
+    BFG_REQUIRE(d_x && d_out, "null argument");
+    const double2 *g_tab = nullptr;
+    if (int rc = get_log2_table(&g_tab)) return rc;
+    if (n == 0) return BFG_OK;
+    k_fast_log2<<<(int)std::min<i64>((n + 255) / 256, 148 * 8), 256, 0, (cudaStream_t)stream>>>(n, g_tab, d_x, d_out);
+    BFG_CUDA_OK(cudaGetLastError());
+    return BFG_OK;
+}
 
 extern "C" int bfg_abi_version(void) { return BFG_ABI_VERSION; }
 extern "C" const char *bfg_last_error(void) { return bfg::g_err; }

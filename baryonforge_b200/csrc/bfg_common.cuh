@@ -414,6 +414,40 @@ __device__ __forceinline__ i64 ang2pix_ring(const Hpx &h, double theta, double p
     return (z > 0) ? 2 * ir * (ir - 1) + ip : h.npix - 2 * ir * (ir + 1) + ip;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Table-driven log2 for the pixel loops (the CUDA libm log() costs ~60 instructions; this one ~18).
+//   x = 2^e * m, m in [1,2);  idx = top 7 mantissa bits;  rc = 1/c_idx (c_idx = bucket centre), f = m*rc - 1,
+//   |f| <= 2^-8;  log2(x) = e + lt[idx] + log2(1+f),  lt = -log2(rc) tabulated, log2(1+f) by a degree-5 series.
+// Absolute error < 2e-15 (tests/test_gpu_parity.py::test_fast_log2).  Zero / denormal / inf / NaN / negative inputs
+// (never a finite, in-table radius) return NaN.  tab = 128 x (rc, lt) in shared memory.
+// ------------------------------------------------------------------------------------------------
+#define BFG_LOG2_TAB 128
+// host: per-device global copy of the table (allocated and filled once); kernels stage it into shared memory
+int get_log2_table(const double2 **d_tab);
+
+__device__ __forceinline__ void load_log2_table(double2 *tab, const double2 *__restrict__ g_tab) {
+    for (int i = threadIdx.x; i < BFG_LOG2_TAB; i += blockDim.x) tab[i] = g_tab[i];
+}
+
+__device__ __forceinline__ double fast_log2(double x, const double2 *__restrict__ tab) {
+    const int hi = __double2hiint(x);
+    // zero / denormal / negative / inf / NaN: every caller turns log(0) = -inf, log(inf) and NaN alike into an
+    // out-of-table read-out (NaN -> contribution 0), so one NaN stands for all of them
+    if ((unsigned)(hi - 0x00100000) >= (unsigned)(0x7ff00000 - 0x00100000)) return CUDART_NAN;
+    const int idx = (hi >> 13) & (BFG_LOG2_TAB - 1);
+    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
+    const double2 t = tab[idx];
+    const double f = fma(m, t.x, -1.0);
+    // log2(1+f) = f * (c1 + f (c2 + f (c3 + f (c4 + f c5)))),  c_k = (-1)^(k+1) / (k ln 2)
+    double p = fma(f, 0.28853900817779268, -0.36067376022224085);
+    p = fma(f, p, 0.48089834696298783);
+    p = fma(f, p, -0.72134752044448170);
+    p = fma(f, p, 1.4426950408889634);
+    // exponent as a double without I2F: 2^52 + 2^31 + (e + 1023) trick
+    const double ed = __hiloint2double(0x43300000, (hi >> 20) ^ 0x80000000) - 4503601774854144.0 - 1023.0;
+    return fma(f, p, t.y) + ed;
+}
+
 // fp64 RED (no return value): RED.E.ADD.F64 on sm_100a
 __device__ __forceinline__ void red_add(double *addr, double v) { atomicAdd(addr, v); }
 

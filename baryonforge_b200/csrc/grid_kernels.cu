@@ -173,7 +173,7 @@ template <bool PAINT>
 int launch_grid(const bfg_table *t, int ndim, i64 N, double res, double scale, i64 n_halo, const double *d_halos,
                 const double *d_extras, int n_extra, double *d_out, i64 plane_lo, i64 plane_hi, i64 *d_nupdates,
                 cudaStream_t st) {
-    BFG_REQUIRE(t && d_halos && d_out, "null argument");
+    BFG_REQUIRE(t && (d_halos || n_halo == 0) && d_out, "null argument");
     BFG_REQUIRE(ndim == 2 || ndim == 3, "ndim must be 2 or 3");
     BFG_REQUIRE(N >= 4 && N <= 32768, "N out of range (need 4 <= N <= 32768)");
     BFG_REQUIRE(plane_lo >= 0 && plane_hi <= N && plane_lo <= plane_hi, "bad plane range");

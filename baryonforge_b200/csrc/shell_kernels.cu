@@ -16,6 +16,7 @@ using namespace bfg;
 namespace {
 
 constexpr int SHELL_THREADS = 128;
+constexpr int SHELL_MIN_CTAS = 6;            // caps registers at 85/thread: 24 warps/SM hide the fp64 latency
 constexpr int RING_CHUNK = SHELL_THREADS;   // ring segments staged in shared memory per pass (one per thread)
 
 struct HaloSph {
@@ -56,12 +57,13 @@ __device__ __forceinline__ HaloUpd make_upd(const HaloSph &s) {
 template <bool PAINT, bool UNIFORM>
 __device__ __forceinline__ void shell_update(const TableView &T, const double *__restrict__ row, bool valid,
                                              const HaloUpd &u, double x, double y, double z, double px, double py,
-                                             double pz, double *__restrict__ out, i64 nloc, i64 lp) {
+                                             double pz, double *__restrict__ out, i64 nloc, i64 lp,
+                                             const double2 *__restrict__ l2tab) {
     // HealpixRunner.py:338-341  diff = pos - pos_j ; r_sep^2 = sum(diff^2)
     double dx = px - u.pjx, dy = py - u.pjy, dz = pz - u.pjz;
     double r2 = dx * dx + dy * dy + dz * dz;
-    // ln(r_sep / a) without the square root and the division  (:345 / :472)
-    double xq = 0.5 * log(r2) + u.ln_inv_a;
+    // ln(r_sep / a) = 0.5 ln2 log2(r^2) + ln(1/a): no square root, no division, table-driven log2  (:345 / :472)
+    double xq = fma(fast_log2(r2, l2tab), 0.34657359027997264, u.ln_inv_a);
     if (T.flags & BFG_TABLE_RDELTA) xq -= u.lnRcom;
     double val = row_lookup<UNIFORM>(T, row, xq);
     if (!valid) val = CUDART_NAN;
@@ -92,12 +94,15 @@ struct RingSeg {
 };
 
 template <bool PAINT, bool UNIFORM>
-__global__ void __launch_bounds__(SHELL_THREADS)
+__global__ void __launch_bounds__(SHELL_THREADS, SHELL_MIN_CTAS)
 k_shell_halos(TableView T, Hpx h, i64 n_halo, const double *__restrict__ halos, const double *__restrict__ extras,
-              int n_extra, double *__restrict__ out, i64 pix_lo, i64 pix_hi, unsigned long long *nupd) {
+              int n_extra, double *__restrict__ out, i64 pix_lo, i64 pix_hi, unsigned long long *nupd,
+              const double2 *__restrict__ g_l2tab) {
     extern __shared__ double row[];
     __shared__ RingSeg segs[RING_CHUNK];
+    __shared__ double2 l2tab[BFG_LOG2_TAB];
     __shared__ int s_next;
+    load_log2_table(l2tab, g_l2tab);   // visible after the first __syncthreads() below
     const int lane = threadIdx.x & 31;
     const i64 nloc = pix_hi - pix_lo;
     i64 done = 0;
@@ -111,6 +116,36 @@ k_shell_halos(TableView T, Hpx h, i64 n_halo, const double *__restrict__ halos, 
         const HaloUpd u = make_upd(s);
         // `if pixind.size < 4` (HealpixRunner.py:333) can only trigger for discs of a few pixels (<= ~12 rings)
         const bool tiny = !PAINT && (s.radius * s.radius * (double)h.npix * 0.25 < 64.0);
+
+        if (tiny) {   // count the disc (block-wide); discs with no pixel centre at all land here too
+            __shared__ int s_cnt[SHELL_THREADS / 32];
+            int c = 0;
+            for (i64 iz = d.ra + threadIdx.x; iz <= d.rb; iz += SHELL_THREADS) {
+                i64 start, nr, ip_lo, cnt; bool sh;
+                disc_ring_span(h, d, iz, start, nr, sh, ip_lo, cnt);
+                c += (int)cnt;
+            }
+            c = (int)warp_sum_i64(c);
+            if (lane == 0) s_cnt[threadIdx.x >> 5] = c;
+            __syncthreads();   // also: row ready
+            int tot = 0;
+            for (int w = 0; w < SHELL_THREADS / 32; ++w) tot += s_cnt[w];
+            if (tot < 4) {
+                if (threadIdx.x < 4) {
+                    i64 pix[4]; double w[4];
+                    get_interpol(h, s.theta_ll, s.phi_ll, pix, w);   // HealpixRunner.py:334
+                    i64 p = pix[threadIdx.x];
+                    if (p >= pix_lo && p < pix_hi) {
+                        double x, y, z;
+                        pix2vec(h, p, x, y, z);
+                        shell_update<PAINT, UNIFORM>(T, row, valid, u, x, y, z, x * u.D, y * u.D, z * u.D, out, nloc,
+                                                     p - pix_lo, l2tab);
+                        ++done;
+                    }
+                }
+                continue;   // uniform across the block
+            }
+        }
 
         for (i64 base = d.ra; base <= d.rb; base += RING_CHUNK) {
             // ---- stage up to RING_CHUNK ring segments: one ring per thread ------------------------------
@@ -136,26 +171,6 @@ k_shell_halos(TableView T, Hpx h, i64 n_halo, const double *__restrict__ halos, 
             __syncthreads();  // segments + row ready
             const int nseg = (int)min((i64)RING_CHUNK, d.rb - base + 1);
 
-            if (tiny) {   // whole disc is in this chunk: count it
-                int tot = 0;
-                for (int r = 0; r < nseg; ++r) tot += segs[r].cnt;
-                if (tot < 4) {
-                    if (threadIdx.x < 4) {
-                        i64 pix[4]; double w[4];
-                        get_interpol(h, s.theta_ll, s.phi_ll, pix, w);   // HealpixRunner.py:334
-                        i64 p = pix[threadIdx.x];
-                        if (p >= pix_lo && p < pix_hi) {
-                            double x, y, z;
-                            pix2vec(h, p, x, y, z);
-                            shell_update<PAINT, UNIFORM>(T, row, valid, u, x, y, z, x * u.D, y * u.D, z * u.D, out, nloc,
-                                                         p - pix_lo);
-                            ++done;
-                        }
-                    }
-                    break;   // uniform across the block
-                }
-            }
-
             // ---- warps pull ring segments; lanes walk consecutive pixels -------------------------------
             for (;;) {
                 int r = 0;
@@ -177,7 +192,7 @@ k_shell_halos(TableView T, Hpx h, i64 n_halo, const double *__restrict__ halos, 
                     i64 lp = lbase + ip;
                     if ((unsigned long long)lp < (unsigned long long)nloc) {
                         shell_update<PAINT, UNIFORM>(T, row, valid, u, sth * cs, sth * sn, z, sD * cs, sD * sn, pz, out,
-                                                     nloc, lp);
+                                                     nloc, lp, l2tab);
                         ++done;
                     }
                     ip += 32;
@@ -293,7 +308,7 @@ int grid_for(i64 n, int threads, int max_blocks = 148 * 32) {
 template <bool PAINT>
 int launch_shell(const bfg_table *t, int nside, i64 n_halo, const double *d_halos, const double *d_extras, int n_extra,
                  double *d_out, i64 pix_lo, i64 pix_hi, i64 *d_nupdates, cudaStream_t st) {
-    BFG_REQUIRE(t && d_halos && d_out, "null argument");
+    BFG_REQUIRE(t && (d_halos || n_halo == 0) && (d_out || pix_lo == pix_hi), "null argument");
     if (int rc = check_nside(nside)) return rc;
     Hpx h(nside);
     BFG_REQUIRE(pix_lo >= 0 && pix_hi <= h.npix && pix_lo <= pix_hi, "bad pixel range");
@@ -306,10 +321,12 @@ int launch_shell(const bfg_table *t, int nside, i64 n_halo, const double *d_halo
     size_t smem = sizeof(double) * t->view.n[2];
     BFG_REQUIRE(smem <= 200 * 1024, "radial axis too long for the shared-memory row (max 25600 nodes)");
     int blocks = (int)std::min<i64>(n_halo, (i64)1 << 30);
+    const double2 *g_l2tab = nullptr;
+    if (int rc = get_log2_table(&g_l2tab)) return rc;
     auto go = [&](auto kern) -> int {
         BFG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<blocks, SHELL_THREADS, smem, st>>>(t->view, h, n_halo, d_halos, d_extras, n_extra, d_out, pix_lo, pix_hi,
-                                                  (unsigned long long *)d_nupdates);
+                                                  (unsigned long long *)d_nupdates, g_l2tab);
         BFG_CUDA_OK(cudaGetLastError());
         return BFG_OK;
     };

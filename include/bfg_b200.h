@@ -175,6 +175,8 @@ int bfg_halo_sort(int mode, int64_t n_halo, const double *d_in, double *d_out, c
 /* ---- small utilities ------------------------------------------------------------------------------ */
 /* *d_out (one double) = sum of n doubles (mass-conservation assert, HealpixRunner.py:368-370). */
 int bfg_sum_f64(const double *d_x, int64_t n, double *d_out, void *stream);
+/* Unit-test entry for the table-driven log2 used inside the pixel loops: d_out[i] = log2(d_x[i]). */
+int bfg_test_fast_log2(int64_t n, const double *d_x, double *d_out, void *stream);
 /* out[i][c] = in[c][i] : component-major offsets -> the reference's (n, ncomp) layout, for tests. */
 int bfg_transpose_offsets(const double *d_in, double *d_out, int64_t n, int ncomp, void *stream);
 

@@ -212,3 +212,21 @@ def test_error_behaviour_matches_reference():
         b.PaintProfilesShell(cat, shell, 20, object(), verbose=False).process()
     with pytest.raises(ValueError):
         b.LightconeShell(map=np.zeros(12), cosmo=dict(Omega_m=0.3))
+
+
+def test_fast_log2():
+    """The table-driven log2 of the pixel loops: absolute error < 2e-15 over the radii range; non-normal -> NaN."""
+    import torch
+    from baryonforge_b200 import _lib
+    rng = np.random.default_rng(0)
+    x = np.concatenate([10 ** rng.uniform(-30, 30, 200000), 1 + rng.uniform(-1e-3, 1e-3, 1000), 2.0 ** np.arange(-40, 40),
+                        np.nextafter(2.0 ** np.arange(-5, 5), 0), [1e-310, 0.0, np.inf, np.nan, -1.0]])
+    d_x = torch.from_numpy(x).cuda()
+    d_o = torch.empty_like(d_x)
+    _lib.check(_lib.lib().bfg_test_fast_log2(x.size, d_x.data_ptr(), d_o.data_ptr(), _lib.current_stream()))
+    got = d_o.cpu().numpy()
+    ok = np.isfinite(x) & (x >= 2.3e-308)
+    want = np.log2(x[ok].astype(np.longdouble)).astype(np.float64)
+    err = np.abs(got[ok] - want)
+    assert err.max() < 2e-15 + 2.3e-16 * np.abs(want).max(), err.max()
+    assert np.all(np.isnan(got[~ok]))
