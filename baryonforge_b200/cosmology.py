@@ -106,6 +106,14 @@ def angular_diameter_distance(cosmo, a):
     return _ccl.angular_diameter_distance(cosmo, a)
 
 
+def D_A_spline(cosmo, z):
+    """The CubicSpline object itself (HealpixRunner.py:297-299), for chunked evaluation."""
+    z_m = np.max(z)
+    assert z_m <= 30, f"We assume max(z) = 30, but your catalog has max(z) = {z_m}"   # HealpixRunner.py:301
+    z_t = np.linspace(0, z_m + 0.1, 1000)
+    return interpolate.CubicSpline(z_t, angular_diameter_distance(cosmo, 1 / (1 + z_t)))
+
+
 def D_A_of_z(cosmo, z):
     """The reference's D_a: CubicSpline over 1000 nodes in z in [0, zmax+0.1] (HealpixRunner.py:297-299)."""
     z = np.asarray(z, dtype=np.float64)

@@ -54,11 +54,15 @@ template <bool PAINT, bool UNIFORM, int NDIM>
 __global__ void __launch_bounds__(GRID_THREADS)
 k_grid_halos(TableView T, int N, double res, double scale, i64 n_halo, const double *__restrict__ halos,
              const double *__restrict__ extras, int n_extra, double *__restrict__ out, int plane_lo, int plane_hi,
-             unsigned long long *nupd) {
+             unsigned long long *nupd, const double2 *__restrict__ g_l2tab) {
     extern __shared__ double row[];
+    __shared__ double2 l2tab[BFG_LOG2_TAB];
+    load_log2_table(l2tab, g_l2tab);
     const i64 plane = (NDIM == 3) ? (i64)N * N : (i64)N;       // cells per axis-0 plane
     const i64 nloc = (i64)(plane_hi - plane_lo) * plane;
     const double inv_res = 1.0 / res;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int NW = GRID_THREADS / 32;
     i64 done = 0;
     for (i64 h = blockIdx.x; h < n_halo; h += gridDim.x) {
         const HaloBox b = load_box(halos + h * BFG_HALO_STRIDE);
@@ -67,45 +71,52 @@ k_grid_halos(TableView T, int N, double res, double scale, i64 n_halo, const dou
         blend_row(T, b.lnz, b.lnM, extras ? extras + h * n_extra : nullptr, row, valid);
         __syncthreads();
         const int ns = b.nsize, cw = ns / 2;
-        const i64 inner = (NDIM == 3) ? (i64)ns * ns : (i64)ns;   // elements per axis-0 index
-        const i64 total = inner * ns;
-        for (i64 e = threadIdx.x; e < total; e += GRID_THREADS) {
-            int i = (int)(e / inner);
-            int rem = (int)(e - (i64)i * inner);
-            int j = (NDIM == 3) ? rem / ns : rem;
-            int k = (NDIM == 3) ? rem - j * ns : 0;
-            int c0 = wrap_idx(b.cen[0] - cw + i, N);
+        const double cut2 = PAINT ? b.paintcut * b.paintcut : b.rcut * b.rcut;
+        // Rows of the cutout = every index but the last array axis; a warp owns a row, lanes walk the last axis, so the
+        // REDs of a warp are contiguous in memory (the last axis is the fastest one of the C-order grid).
+        const int nrows = (NDIM == 3) ? ns * ns : ns;
+        for (int rw = warp; rw < nrows; rw += NW) {
+            const int i = (NDIM == 3) ? rw / ns : rw;            // cutout index along array axis 0
+            const int j = (NDIM == 3) ? rw - i * ns : 0;         // 3-D: cutout index along array axis 1
+            const int c0 = wrap_idx(b.cen[0] - cw + i, N);
             if (c0 < plane_lo || c0 >= plane_hi) continue;
-            int c1 = wrap_idx(b.cen[1] - cw + j, N);
-            int c2 = (NDIM == 3) ? wrap_idx(b.cen[2] - cw + k, N) : 0;
-            i64 cell = (NDIM == 3) ? ((i64)(c0 - plane_lo) * N + c1) * N + c2 : (i64)(c0 - plane_lo) * N + c1;
-            double gx = cut_coord(j, ns, res) + b.d[0];          // Map2DRunner.py:524-528 / :561-566
-            double gy = cut_coord(i, ns, res) + b.d[1];
-            double gz = (NDIM == 3) ? cut_coord(k, ns, res) + b.d[2] : 0.0;
-            double r = (NDIM == 3) ? sqrt(gx * gx + gy * gy + gz * gz) : sqrt(gx * gx + gy * gy);
-            double xq = log(r);
-            if (T.flags & BFG_TABLE_RDELTA) xq -= b.lnRcom;
-            double val = row_lookup<UNIFORM>(T, row, xq);
-            if (!valid) val = CUDART_NAN;
-            ++done;
-            if (PAINT) {
-                val = exp(val);                                  // Tabulate.py:319
-                if (!isfinite(val) || !(r < b.paintcut)) continue;   // Map2DRunner.py:814-818
-                val *= scale;                                    // :825 folded in
-                if (val != 0.0) red_add(out + cell, val);
-            } else {
-                val = (r < b.rcut) ? val : 0.0;                  // BaryonCorrection.py:410-411
-                double off = val * inv_res;                      // Map2DRunner.py:540/:583  (/ res)
-                if (off == 0.0 && r > 0.0) continue;             // adds exact zeros
-                red_add(out + cell, off * (gx / r));             // NaNs propagate (cleaned after the loop, :597/:607)
-                red_add(out + nloc + cell, off * (gy / r));
-                if (NDIM == 3) red_add(out + 2 * nloc + cell, off * (gz / r));
+            // element (i, j, k): gx = x[j] + dx, gy = x[i] + dy, gz = x[k] + dz   (Map2DRunner.py:524-528 / :561-566)
+            // 2-D: the last axis is j itself, so gx varies along the row and gy is the row constant.
+            const double gy = cut_coord(i, ns, res) + b.d[1];
+            const double gx_row = (NDIM == 3) ? cut_coord(j, ns, res) + b.d[0] : 0.0;
+            const double row2 = (NDIM == 3) ? gx_row * gx_row + gy * gy : 0.0;
+            const int c1 = (NDIM == 3) ? wrap_idx(b.cen[1] - cw + j, N) : 0;
+            const i64 base = (NDIM == 3) ? ((i64)(c0 - plane_lo) * N + c1) * N : (i64)(c0 - plane_lo) * N;
+            const int clast0 = b.cen[NDIM - 1] - cw;
+            for (int k = lane; k < ns; k += 32) {
+                const double gl = cut_coord(k, ns, res) + b.d[NDIM == 3 ? 2 : 0];   // coordinate along the last axis
+                const double gx = (NDIM == 3) ? gx_row : gl;
+                const double r2 = (NDIM == 3) ? row2 + gl * gl : gl * gl + gy * gy;
+                const i64 cell = base + wrap_idx(clast0 + k, N);
+                double xq = fast_log2(r2, l2tab) * 0.34657359027997264;           // ln r = 0.5 ln2 log2(r^2)
+                if (T.flags & BFG_TABLE_RDELTA) xq -= b.lnRcom;
+                double val = row_lookup<UNIFORM>(T, row, xq);
+                if (!valid) val = CUDART_NAN;
+                ++done;
+                if (PAINT) {
+                    val = exp(val);                                  // Tabulate.py:319
+                    if (!isfinite(val) || !(r2 < cut2)) continue;    // Map2DRunner.py:814-818
+                    val *= scale;                                    // :825 folded in
+                    if (val != 0.0) red_add(out + cell, val);
+                } else {
+                    val = (r2 < cut2) ? val : 0.0;                   // BaryonCorrection.py:410-411
+                    const double sc = (val * inv_res) * rsqrt(r2);   // offset / res / r   (Map2DRunner.py:540/:583)
+                    if (sc == 0.0) continue;                         // adds exact zeros; NaN (r = 0, outside table) goes on
+                    red_add(out + cell, sc * gx);                    // NaNs propagate (cleaned after the loop, :597/:607)
+                    red_add(out + nloc + cell, sc * gy);
+                    if (NDIM == 3) red_add(out + 2 * nloc + cell, sc * gl);
+                }
             }
         }
     }
     if (nupd) {
         done = warp_sum_i64(done);
-        if ((threadIdx.x & 31) == 0 && done) atomicAdd(nupd, (unsigned long long)done);
+        if (lane == 0 && done) atomicAdd(nupd, (unsigned long long)done);
     }
 }
 
@@ -186,10 +197,12 @@ int launch_grid(const bfg_table *t, int ndim, i64 N, double res, double scale, i
     size_t smem = sizeof(double) * t->view.n[2];
     BFG_REQUIRE(smem <= 200 * 1024, "radial axis too long for the shared-memory row (max 25600 nodes)");
     int blocks = (int)std::min<i64>(n_halo, (i64)1 << 30);
+    const double2 *g_l2tab = nullptr;
+    if (int rc = get_log2_table(&g_l2tab)) return rc;
     auto go = [&](auto kern) -> int {
         BFG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<blocks, GRID_THREADS, smem, st>>>(t->view, (int)N, res, scale, n_halo, d_halos, d_extras, n_extra, d_out,
-                                                 (int)plane_lo, (int)plane_hi, (unsigned long long *)d_nupdates);
+                                                 (int)plane_lo, (int)plane_hi, (unsigned long long *)d_nupdates, g_l2tab);
         BFG_CUDA_OK(cudaGetLastError());
         return BFG_OK;
     };

@@ -70,8 +70,10 @@ __global__ void __launch_bounds__(SNAP_THREADS)
 k_snap_halos(TableView T, double L, int nc, const double *__restrict__ xs, const double *__restrict__ ys,
              const double *__restrict__ zs, const i64 *__restrict__ cell_start, i64 n_part, i64 n_halo,
              const double *__restrict__ halos, const double *__restrict__ extras, int n_extra,
-             double *__restrict__ tot, unsigned long long *npairs) {
+             double *__restrict__ tot, unsigned long long *npairs, const double2 *__restrict__ g_l2tab) {
     extern __shared__ double row[];
+    __shared__ double2 l2tab[BFG_LOG2_TAB];
+    load_log2_table(l2tab, g_l2tab);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int NW = SNAP_THREADS / 32;
     const double cell = L / (double)nc;
@@ -86,6 +88,7 @@ k_snap_halos(TableView T, double L, int nc, const double *__restrict__ xs, const
         bool valid;
         blend_row(T, s.lnz, s.lnM, extras ? extras + h * n_extra : nullptr, row, valid);
         __syncthreads();
+        const double rq2 = s.rq * s.rq, rcut2 = s.rcut * s.rcut;
         // cells covering [c - rq, c + rq] per axis (periodic); never more than nc of them
         int lo[3], cnt[3];
         for (int d = 0; d < 3; ++d) {
@@ -121,19 +124,20 @@ k_snap_halos(TableView T, double L, int nc, const double *__restrict__ xs, const
                 double dx = min_image(xs[p] - s.c[0], L);      // SnapshotRunner.py:248-251 / :103-132
                 double dy = min_image(ys[p] - s.c[1], L);
                 double dz = (NDIM == 3) ? min_image(zs[p] - s.c[2], L) : 0.0;
-                double d = (NDIM == 3) ? sqrt(dx * dx + dy * dy + dz * dz) : sqrt(dx * dx + dy * dy);
-                if (!(d <= s.rq)) continue;                    // query_ball_point: inclusive  (:232/:247)
+                double d2 = (NDIM == 3) ? dx * dx + dy * dy + dz * dz : dx * dx + dy * dy;
+                if (!(d2 <= rq2)) continue;                    // query_ball_point: d <= R_q, inclusive  (:232/:247)
                 ++done;
-                double xq = log(d);
+                double xq = fast_log2(d2, l2tab) * 0.34657359027997264;   // ln d = 0.5 ln2 log2(d^2)
                 if (T.flags & BFG_TABLE_RDELTA) xq -= s.lnRcom;
                 double val = row_lookup<UNIFORM>(T, row, xq);
                 if (!valid) val = CUDART_NAN;
-                val = (d < s.rcut) ? val : 0.0;                // BaryonCorrection.py:410-411
+                val = (d2 < rcut2) ? val : 0.0;                // BaryonCorrection.py:410-411
                 if (!isfinite(val)) val = 0.0;                 // SnapshotRunner.py:259
-                if (val == 0.0 && d > 0.0) continue;           // adds exact zeros
-                red_add(tot + p, val * (dx / d));              // :260 ; d == 0 -> NaN, as in the reference (§10 #11)
-                red_add(tot + n_part + p, val * (dy / d));
-                if (NDIM == 3) red_add(tot + 2 * n_part + p, val * (dz / d));
+                if (val == 0.0 && d2 > 0.0) continue;          // adds exact zeros
+                const double sc = val * rsqrt(d2);             // d == 0 -> 0 * inf = NaN, as in the reference (§10 #11)
+                red_add(tot + p, sc * dx);                     // :260
+                red_add(tot + n_part + p, sc * dy);
+                if (NDIM == 3) red_add(tot + 2 * n_part + p, sc * dz);
             }
         }
     }
@@ -243,10 +247,12 @@ extern "C" int bfg_snap_offsets(const bfg_table *t, int ndim, int64_t n_part, co
     size_t smem = sizeof(double) * t->view.n[2];
     BFG_REQUIRE(smem <= 200 * 1024, "radial axis too long for the shared-memory row (max 25600 nodes)");
     int blocks = (int)std::min<i64>(n_halo, (i64)1 << 30);
+    const double2 *g_l2tab = nullptr;
+    if (int rc = get_log2_table(&g_l2tab)) return rc;
     auto go = [&](auto kern) -> int {
         BFG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<blocks, SNAP_THREADS, smem, st>>>(t->view, L, ncell, d_xs, d_ys, d_zs, (const i64 *)d_cell_start, n_part, n_halo,
-                                                 d_halos, d_extras, n_extra, d_tot, (unsigned long long *)d_npairs);
+                                                 d_halos, d_extras, n_extra, d_tot, (unsigned long long *)d_npairs, g_l2tab);
         BFG_CUDA_OK(cudaGetLastError());
         return BFG_OK;
     };

@@ -61,6 +61,20 @@ def _sort_records(d_rec, d_ext, mode, p0, p1=0.0, ndim=3):
     return out, out_e
 
 
+def _parallel_chunks(fn, n, chunk=65536):
+    """Run fn(slice) over [0, n) in chunks on a small thread pool (BFG_HOST_THREADS, default min(16, cores))."""
+    import os
+    nthreads = int(os.environ.get("BFG_HOST_THREADS", min(16, os.cpu_count() or 1)))
+    slices = [slice(i, min(i + chunk, n)) for i in range(0, n, chunk)]
+    if nthreads <= 1 or len(slices) <= 1:
+        for sl in slices:
+            fn(sl)
+        return
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=nthreads) as ex:
+        list(ex.map(fn, slices))
+
+
 def _all_close_to_zero(a):
     """np.allclose(a, 0) (HealpixRunner.py:293) without scanning a 1.6 GB map when its first entries already say no."""
     head = a.reshape(-1)[:4096]
@@ -157,37 +171,47 @@ class DefaultRunner(object):
         cat = self.HaloLightConeCatalog.cat
         n = cat.size
         cosmo = cosmology.runner_cosmology(self.cosmo, with_w0=True)          # :280-284
-        M, z = cat['M'], cat['z']
-        a = 1 / (1 + z)                                                        # :319
         rec = np.zeros((_lib.HALO_STRIDE, n), dtype=np.float64).T              # field-major storage, [n,16] view
         if n == 0:
             return rec, None
-        R = cosmology.radius_of_mass(cosmo, M, a, self.mass_def)               # :320 physical Mpc
-        D = cosmology.D_A_of_z(cosmo, z)                                       # :297-299,321
-        theta_ll, phi_ll = np.pi / 2.0 - np.radians(cat['dec']), np.radians(cat['ra'])   # healpy lonlat2thetaphi
-        st = np.sin(theta_ll)
-        vx, vy, vz = st * np.cos(phi_ll), st * np.sin(phi_ll), np.cos(theta_ll)          # hp.ang2vec :327
-        rec[:, _lib.HS_VX], rec[:, _lib.HS_VY], rec[:, _lib.HS_VZ] = vx, vy, vz
-        # pointing(vec) as healpy's query_disc wrapper builds it
-        rec[:, _lib.HS_THETA] = np.arctan2(np.sqrt(vx * vx + vy * vy), vz)
-        phi = np.arctan2(vy, vx)
-        rec[:, _lib.HS_PHI] = np.where(phi < 0, phi + 2 * np.pi, phi)
-        rec[:, _lib.HS_D] = D
-        rec[:, _lib.HS_A] = a
-        rec[:, _lib.HS_RADIUS] = R * self.epsilon_max / D                      # :329
-        rec[:, _lib.HS_LNZ] = np.log(1 / a)                                    # BaryonCorrection.py:371 / Tabulate.py:312
-        rec[:, _lib.HS_LNM] = np.log(M)                                        # BaryonCorrection.py:398 / Tabulate.py:317
-        if paint:
-            rec[:, _lib.HS_RCUT] = np.inf
-            pixarea = 4 * np.pi / self.LightconeShell.map.size
-            rec[:, _lib.HS_SCALE] = pixarea * D ** 2 if self.include_pixel_size else 1.0   # :478
-        else:
-            mcosmo = _model_cosmo(self.model, cosmo)
-            R_com = cosmology.radius_of_mass(mcosmo, M, a, getattr(self.model, 'mass_def', None)) / a   # BaryonCorrection.py:399
-            rec[:, _lib.HS_RCUT] = self.model.epsilon_max * R_com              # :410
-            rec[:, _lib.HS_LNRCOM] = np.log(R_com)                             # :408
-            rec[:, _lib.HS_SCALE] = 1.0
-        rec[:, _lib.HS_THETA_LL], rec[:, _lib.HS_PHI_LL] = theta_ll, phi_ll
+        D_of_z = cosmology.D_A_spline(cosmo, cat['z'])                         # :297-299
+        mcosmo = None if paint else _model_cosmo(self.model, cosmo)
+        R = np.empty(n)
+        D = np.empty(n)
+        R_com = None if paint else np.empty(n)
+        pixarea = 4 * np.pi / self.LightconeShell.map.size
+        eps_model = None if paint else self.model.epsilon_max
+
+        def fill(sl):   # numpy releases the GIL inside these ufuncs, so chunks run on several host cores
+            M, z = cat['M'][sl], cat['z'][sl]
+            r = rec[sl]
+            a = 1 / (1 + z)                                                    # :319
+            R[sl] = cosmology.radius_of_mass(cosmo, M, a, self.mass_def)       # :320 physical Mpc
+            D[sl] = D_of_z(z)                                                  # :321
+            theta_ll, phi_ll = np.pi / 2.0 - np.radians(cat['dec'][sl]), np.radians(cat['ra'][sl])   # lonlat2thetaphi
+            st = np.sin(theta_ll)
+            vx, vy, vz = st * np.cos(phi_ll), st * np.sin(phi_ll), np.cos(theta_ll)      # hp.ang2vec :327
+            r[:, _lib.HS_VX], r[:, _lib.HS_VY], r[:, _lib.HS_VZ] = vx, vy, vz
+            # pointing(vec) as healpy's query_disc wrapper builds it
+            r[:, _lib.HS_THETA] = np.arctan2(np.sqrt(vx * vx + vy * vy), vz)
+            phi = np.arctan2(vy, vx)
+            r[:, _lib.HS_PHI] = np.where(phi < 0, phi + 2 * np.pi, phi)
+            r[:, _lib.HS_D] = D[sl]
+            r[:, _lib.HS_A] = a
+            r[:, _lib.HS_RADIUS] = R[sl] * self.epsilon_max / D[sl]            # :329
+            r[:, _lib.HS_LNZ] = np.log(1 / a)                                  # BaryonCorrection.py:371 / Tabulate.py:312
+            r[:, _lib.HS_LNM] = np.log(M)                                      # BaryonCorrection.py:398 / Tabulate.py:317
+            if paint:
+                r[:, _lib.HS_RCUT] = np.inf
+                r[:, _lib.HS_SCALE] = pixarea * D[sl] ** 2 if self.include_pixel_size else 1.0   # :478
+            else:
+                R_com[sl] = cosmology.radius_of_mass(mcosmo, M, a, getattr(self.model, 'mass_def', None)) / a   # BaryonCorrection.py:399
+                r[:, _lib.HS_RCUT] = eps_model * R_com[sl]                     # :410
+                r[:, _lib.HS_LNRCOM] = np.log(R_com[sl])                       # :408
+                r[:, _lib.HS_SCALE] = 1.0
+            r[:, _lib.HS_THETA_LL], r[:, _lib.HS_PHI_LL] = theta_ll, phi_ll
+
+        _parallel_chunks(fill, n)
         self.last_scalars = dict(R_run=R, D_A=D, R_model_com=None if paint else R_com)
         keys = list(vars(self.model).get('p_keys', []))                        # :304
         _check_keys(self.model, keys)
@@ -221,8 +245,11 @@ class BaryonifyShell(DefaultRunner):
         with torch.cuda.device(dev):   # table first: a model without one fails here, as in the reference
             table = self._tables.get((id(self.model), id(self.model.interp_d) if hasattr(self.model, 'interp_d') else 0),
                                      lambda: displacement_table_of(self.model, dev.index))
+        import time
+        t0 = time.perf_counter()
         rec, extras = self.halo_records(paint=False)
         rec, extras = self._owned_halos(rec, extras, NSIDE, lo, hi)
+        self.last_timing = dict(host_prep_s=time.perf_counter() - t0)
         with torch.cuda.device(dev):
             d_rec = _upload_records(rec, dev)
             d_ext = None if extras is None else _to_device(extras, dev)

@@ -324,7 +324,8 @@ def run_b200(args):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {"value": n_up / float(tt[0]), "unit": "halo-pixel updates/s",
                "h2d_bytes_per_step": int((hi - lo) * 8 + rec.size * 8), "d2h_bytes_per_step": int(npix * 8),
-               "ms_per_step": 1e3 * float(tt[0]),
+               "ms_per_step": 1e3 * float(tt[0]), "host_prep_ms": 1e3 * runner.last_timing.get("host_prep_s", 0.0),
+               "host_threads": int(os.environ.get("BFG_HOST_THREADS", min(16, os.cpu_count() or 1))),
                "includes": "host per-halo scalar prep, H2D (pinned map + halo records), kernels, NCCL reduce (N>1), D2H"}
         del out
 
