@@ -388,6 +388,16 @@ class DefaultRunnerGrid(object):
     def _planes(self, N):
         return (0, N) if self.plane_range is None else (int(self.plane_range[0]), int(self.plane_range[1]))
 
+    def _owned_halos(self, rec, extras, N, lo, hi):
+        """Slab sharding: keep the halos whose cutout touches this rank's axis-0 planes (parallel.py)."""
+        if self.plane_range is None or rec.shape[0] == 0:
+            return rec, extras
+        from .parallel import halos_touching_planes
+        keep = halos_touching_planes(N, rec[:, _lib.HB_CX], rec[:, _lib.HB_NSIZE], lo, hi)
+        if keep.all():
+            return rec, extras
+        return np.ascontiguousarray(rec[keep]), (None if extras is None else np.ascontiguousarray(extras[keep]))
+
     def halo_records(self, paint):
         """Per-halo scalars of Map2DRunner.py:484-520 / :727-760 (+ BaryonCorrection.py:371,398-399,410), vectorised."""
         if self.use_ellipticity:
@@ -451,10 +461,12 @@ class BaryonifyGrid(DefaultRunnerGrid):
         gm = self.GriddedMap
         ndim, N = (2 if gm.is2D else 3), gm.Npix
         lo, hi = self._planes(N)
-        rec, extras = self.halo_records(paint=False)
         with torch.cuda.device(dev):
             table = self._tables.get((id(self.model), id(getattr(self.model, 'interp_d', None))),
                                      lambda: displacement_table_of(self.model, dev.index))
+        rec, extras = self.halo_records(paint=False)
+        rec, extras = self._owned_halos(rec, extras, N, lo, hi)
+        with torch.cuda.device(dev):
             d_rec = _upload_records(rec, dev)
             d_ext = None if extras is None else _to_device(extras, dev)
             d_rec, d_ext = _sort_records(d_rec, d_ext, 1, float(gm.L), 16, ndim)
@@ -514,6 +526,7 @@ class PaintProfilesGrid(DefaultRunnerGrid):
         dev = self._device()
         L = _lib.lib()
         rec, extras = self.halo_records(paint=True)
+        rec, extras = self._owned_halos(rec, extras, N, lo, hi)
         which = '2D' if gm.is2D else '3D'                                         # :763 projected / :792 real
         dV = float(np.power(gm.res, ndim)) if self.include_pixel_size else 1.0    # :723,825
         with torch.cuda.device(dev):
