@@ -329,7 +329,11 @@ def run_b200(args):
                "includes": "host per-halo scalar prep, H2D (pinned map + halo records), kernels, NCCL reduce (N>1), D2H"}
         del out
 
+    if world > 1:
+        dist.barrier()
     if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
         return
     peak, peak_src = peaks()
     achieved = ALG_BYTES_PER_UPDATE * (n_up_local if world == 1 else n_up / world) / (ms_kernel * 1e-3) / 1e9
@@ -348,6 +352,8 @@ def run_b200(args):
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, cat, model, axes, vals, args.cpu_sample)
     print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def main():
