@@ -271,9 +271,16 @@ class BaryonifyShell(DefaultRunner):
         L = _lib.lib()
         npix = orig_map.size
         lo, hi = self._range(npix)
+        import os, time
+        prof = os.environ.get("BFG_PROFILE_E2E") == "1"
+        t_start = time.perf_counter()
         with torch.cuda.device(dev):
             d_map = _to_device(orig_map[lo:hi], dev, dtype=np.float64)
+            if prof:
+                torch.cuda.synchronize(); t_h2d = time.perf_counter()
             d_off, d_n = self.offsets_on_device()
+            if prof:
+                torch.cuda.synchronize(); t_loop = time.perf_counter()
             d_new = torch.zeros(npix, dtype=torch.float64, device=dev)
             st = _lib.current_stream()
             _lib.check(L.bfg_shell_regrid(NSIDE, _lib.ptr(d_map), _lib.ptr(d_off), _lib.ptr(d_new), lo, hi, st))
@@ -289,13 +296,22 @@ class BaryonifyShell(DefaultRunner):
                 _lib.check(L.bfg_sum_f64(_lib.ptr(d_map), hi - lo, d_sums.data_ptr() + 8, st))
             else:
                 d_sums[1] = d_map_sum
+            if prof:
+                torch.cuda.synchronize(); t_regrid = time.perf_counter()
             out = torch.empty(npix, dtype=torch.float64, pin_memory=True)
+            if prof:
+                t_alloc = time.perf_counter()
             out.copy_(d_new, non_blocking=True)
             sums = d_sums.cpu()
             n_up = int(d_n.cpu()[0])
             torch.cuda.current_stream().synchronize()
         new_sum, old_sum = float(sums[0]), float(sums[1])
         self.last_stats = dict(n_updates=n_up, new_sum=new_sum, old_sum=old_sum)
+        if prof:
+            t_end = time.perf_counter()
+            self.last_timing.update(h2d_map_s=t_h2d - t_start, halo_loop_total_s=t_loop - t_h2d,
+                                    regrid_reduce_s=t_regrid - t_loop, pinned_alloc_s=t_alloc - t_regrid,
+                                    d2h_s=t_end - t_alloc, total_s=t_end - t_start)
         assert np.isclose(new_sum, old_sum), \
             "ERROR in pixel regridding, sum(new_map) [%0.14e] != sum(oldmap) [%0.14e]" % (new_sum, old_sum)   # :368-370
         return out.numpy()

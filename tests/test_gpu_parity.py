@@ -230,3 +230,74 @@ def test_fast_log2():
     err = np.abs(got[ok] - want)
     assert err.max() < 2e-15 + 2.3e-16 * np.abs(want).max(), err.max()
     assert np.all(np.isnan(got[~ok]))
+
+
+def test_param_tables_p_keys_vs_oracle_port():
+    """4-D tables with a per-halo extra column (`p_keys`, e.g. cdelta): BaryonCorrection.py:211-212,307-322 /
+    Tabulate.py:553-590 semantics, shell baryonify + shell paint, CUDA vs the oracle port."""
+    import baryonforge_b200 as b
+    from baryonforge_b200 import synth
+    from oracle import runners_port as rp
+    nside, n = 64, 300
+    ra, dec, M, z = synth.sky_halos(n, seed=77, z=(0.05, 0.5))
+    rng = np.random.default_rng(78)
+    cd = rng.uniform(3.0, 11.0, n)
+    cd[:5] = [2.0, 12.5, 3.0, 11.0, 7.0]          # two outside the extra axis -> NaN -> zero; two on its edges
+    axes = synth.table_axes(nz=8, nM=9, nr=300)
+    cax = np.linspace(3.0, 11.0, 5)
+    d4 = synth.displacement_values(axes)[..., None] * (0.5 + 0.1 * cax)[None, None, None, :]
+    p4 = synth.profile_values(axes)[..., None] * (0.5 + 0.1 * cax)[None, None, None, :]
+    cat = b.HaloLightConeCatalog(ra=ra, dec=dec, M=M, z=z, cosmo=synth.COSMO, cdelta=cd)
+    shell = b.LightconeShell(map=synth.shell_map(nside, seed=79), cosmo=synth.COSMO)
+    dmodel = b.DisplacementModel(axes + (cax,), d4, 20, synth.COSMO, p_keys=['cdelta'])
+    run = b.BaryonifyShell(cat, shell, 20, dmodel, verbose=False)
+    d_off, d_n = run.offsets_on_device()
+    sc = run.last_scalars
+    tab = rp.DisplacementTable(axes + (cax,), d4, 20, p_keys=['cdelta'])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        off_w, n_w = rp.shell_offsets(nside, cat.cat, sc["R_run"], sc["D_A"], sc["R_model_com"], 20, tab,
+                                      extras=dict(cdelta=cd), warn=False)
+    assert int(d_n.cpu()[0]) == n_w
+    assert_close(d_off.cpu().numpy().T, off_w, "4-D displacement offsets")
+    pmodel = b.ProfileModel(axes + (cax,), p4 * 3, p4, p_keys=['cdelta'])
+    prun = b.PaintProfilesShell(cat, shell, 20, pmodel, verbose=False)
+    got = prun.process()
+    sc = prun.last_scalars
+    ptab = rp.ProfileTable(axes + (cax,), p4 * 3, p4, p_keys=['cdelta'])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want, n_w = rp.paint_shell(nside, cat.cat, sc["R_run"], sc["D_A"], 20, ptab, extras=dict(cdelta=cd))
+    assert prun.last_stats["n_updates"] == n_w
+    assert_close(got, want, "4-D painted map")
+
+
+def test_full_size_subdomain_parity_nside4096():
+    """Parity at BASELINE's full map size: a few hundred halos on the NSIDE=4096 sphere (incl. both poles), CUDA offsets
+    vs the oracle port on every touched pixel; update counts bit-exact (SURVEY.md §8d 'parity at scale')."""
+    import baryonforge_b200 as b
+    from baryonforge_b200 import synth
+    from oracle import runners_port as rp
+    nside, n = 4096, 160
+    ra, dec, M, z = synth.sky_halos(n, seed=4096)
+    dec[:4] = [89.999, -89.9995, 89.9, -89.95]
+    M[:4] = 10 ** 14.8
+    axes = synth.table_axes()
+    vals = synth.displacement_values(axes)
+    cat = b.HaloLightConeCatalog(ra=ra, dec=dec, M=M, z=z, cosmo=synth.COSMO)
+    shell = b.LightconeShell(map=np.broadcast_to(np.ones(1), (12 * nside * nside,)), cosmo=synth.COSMO)
+    model = b.DisplacementModel(axes, vals, 20, synth.COSMO)
+    run = b.BaryonifyShell(cat, shell, 20, model, verbose=False)
+    d_off, d_n = run.offsets_on_device()
+    sc = run.last_scalars
+    tab = rp.DisplacementTable(axes, vals, 20)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        off_w, n_w = rp.shell_offsets(nside, cat.cat, sc["R_run"], sc["D_A"], sc["R_model_com"], 20, tab, warn=False)
+    assert int(d_n.cpu()[0]) == n_w
+    touched = np.flatnonzero(np.any(off_w != 0, axis=1))
+    import torch
+    got = d_off[:, torch.from_numpy(touched).to(d_off.device)].cpu().numpy().T
+    assert_close(got, off_w[touched], "NSIDE=4096 offsets on touched pixels")
+    # nothing outside the touched set
+    assert int((d_off != 0).any(dim=0).sum().item()) <= touched.size
