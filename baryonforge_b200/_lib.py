@@ -73,11 +73,12 @@ def lib():
     """Load libbfg_b200.so; raises (never falls back) when it is missing."""
     global _LIB
     if _LIB is None:
-        if not os.path.exists(LIB_PATH):
+        path = os.environ.get("BFG_LIB", LIB_PATH)   # BFG_LIB: an alternative build of the same ABI (kernel tuning runs)
+        if not os.path.exists(path):
             raise BFGError(
-                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(nvcc, sm_100a). baryonforge_b200 has no CPU fallback.")
-        L = C.CDLL(LIB_PATH)
+        L = C.CDLL(path)
         for name, (args, res) in _SIGNATURES.items():
             fn = getattr(L, name)
             fn.argtypes = args

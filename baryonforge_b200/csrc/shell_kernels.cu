@@ -16,7 +16,10 @@ using namespace bfg;
 namespace {
 
 constexpr int SHELL_THREADS = 128;
-constexpr int SHELL_MIN_CTAS = 6;            // caps registers at 85/thread: 24 warps/SM hide the fp64 latency
+#ifndef BFG_SHELL_MIN_CTAS
+#define BFG_SHELL_MIN_CTAS 6
+#endif
+constexpr int SHELL_MIN_CTAS = BFG_SHELL_MIN_CTAS;   // 6 -> registers capped at 80/thread: 24 warps/SM hide the fp64 latency
 constexpr int RING_CHUNK = SHELL_THREADS;   // ring segments staged in shared memory per pass (one per thread)
 
 struct HaloSph {
@@ -37,61 +40,104 @@ __device__ __forceinline__ HaloSph load_halo(const double *__restrict__ H) {
 // Per-halo constants of the pixel update, hoisted out of the pixel loop.
 struct HaloUpd {
     double D, a, pjx, pjy, pjz;   // pos_j = vec_j * D                            HealpixRunner.py:337
-    double ln_inv_a;              // ln(1/a): ln(r_sep/a) = 0.5 ln(r^2) + ln(1/a)  :345
     double rcut2;                 // (model eps * R_com * a)^2 : r_com < rcut  <=>  r_sep^2 < rcut2   BaryonCorrection.py:410
-    double lnRcom, scale;
+    double scale;
+    double xq0;                   // ln(r_sep/a) [- ln R_com] = 0.5 ln2 log2(r^2) + xq0              :345, BaryonCorrection.py:408
+    double uA, uB, uMax;          // uniform ln r axis: cell coordinate u = log2(r^2) * uA + uB in [0, NR-1]
 };
 
-__device__ __forceinline__ HaloUpd make_upd(const HaloSph &s) {
+__device__ __forceinline__ HaloUpd make_upd(const TableView &T, const HaloSph &s) {
     HaloUpd u;
     u.D = s.D; u.a = s.a;
     u.pjx = s.vx * s.D; u.pjy = s.vy * s.D; u.pjz = s.vz * s.D;
-    u.ln_inv_a = s.lnz;           // the record's ln(1/a) is exactly this quantity
     double rc = s.rcut * s.a;
     u.rcut2 = rc * rc;
-    u.lnRcom = s.lnRcom; u.scale = s.scale;
+    u.scale = s.scale;
+    u.xq0 = s.lnz - ((T.flags & BFG_TABLE_RDELTA) ? s.lnRcom : 0.0);   // the record's ln(1/a) is s.lnz
+    u.uA = 0.34657359027997264 * T.inv_dr;
+    u.uB = (u.xq0 - T.r0) * T.inv_dr;
+    u.uMax = (double)(T.n[2] - 1);
     return u;
 }
 
-// One (halo, pixel) update.  (x, y, z) = pixel unit vector; (px, py, pz) = (x, y, z) * D.
+// Table value at squared separation r2 (NaN when outside the table / not a positive normal number).
+template <bool UNIFORM>
+__device__ __forceinline__ double table_at(const TableView &T, const double *__restrict__ row, const HaloUpd &u,
+                                           double r2, const double2 *__restrict__ l2tab) {
+    const double l2 = fast_log2(r2, l2tab);
+    if (UNIFORM) {
+        const int NR = T.n[2];
+        const double uu = fma(l2, u.uA, u.uB);                      // (ln r - r0) / step
+        if (!(uu >= 0.0) || !(uu <= u.uMax)) return CUDART_NAN;
+        const int k = min((int)uu, NR - 2);
+        const double t = uu - (double)k;
+        return fma(t, row[k + 1], (1.0 - t) * row[k]);              // (1-t) v0 + t v1, as scipy
+    }
+    return row_lookup<false>(T, row, fma(l2, 0.34657359027997264, u.xq0));
+}
+
+// One (halo, pixel) update.  (x, y, z) = pixel unit vector; (px, py, pz) = (x, y, z) * D; p0/p1/p2 = the pixel's slots
+// in the three offset components (paint: p0 only).
 template <bool PAINT, bool UNIFORM>
-__device__ __forceinline__ void shell_update(const TableView &T, const double *__restrict__ row, bool valid,
-                                             const HaloUpd &u, double x, double y, double z, double px, double py,
-                                             double pz, double *__restrict__ out, i64 nloc, i64 lp,
+__device__ __forceinline__ void shell_update(const TableView &T, const double *__restrict__ row, const HaloUpd &u,
+                                             double x, double y, double z, double px, double py, double pz,
+                                             double *__restrict__ p0, double *__restrict__ p1, double *__restrict__ p2,
                                              const double2 *__restrict__ l2tab) {
     // HealpixRunner.py:338-341  diff = pos - pos_j ; r_sep^2 = sum(diff^2)
-    double dx = px - u.pjx, dy = py - u.pjy, dz = pz - u.pjz;
-    double r2 = dx * dx + dy * dy + dz * dz;
-    // ln(r_sep / a) = 0.5 ln2 log2(r^2) + ln(1/a): no square root, no division, table-driven log2  (:345 / :472)
-    double xq = fma(fast_log2(r2, l2tab), 0.34657359027997264, u.ln_inv_a);
-    if (T.flags & BFG_TABLE_RDELTA) xq -= u.lnRcom;
-    double val = row_lookup<UNIFORM>(T, row, xq);
-    if (!valid) val = CUDART_NAN;
+    const double dx = px - u.pjx, dy = py - u.pjy, dz = pz - u.pjz;
+    const double r2 = dx * dx + dy * dy + dz * dz;
+    double val = table_at<UNIFORM>(T, row, u, r2, l2tab);          // :345 / :472 via ln(r_sep/a), no sqrt, no division
     if (PAINT) {
         val = exp(val);                            // Tabulate.py:319
         if (!isfinite(val)) return;                // HealpixRunner.py:473 (adds 0)
         val *= u.scale;                            // :478
-        if (val != 0.0) red_add(out + lp, val);    // :481
+        if (val != 0.0) red_add(p0, val);          // :481
     } else {
-        val = (r2 < u.rcut2) ? val : 0.0;          // BaryonCorrection.py:410-411
-        double sc = (val * u.a) * rsqrt(r2);       // offset / r_sep                 HealpixRunner.py:345-346
+        if (!(r2 < u.rcut2)) return;               // BaryonCorrection.py:410-411: zero beyond the model's cut
+        const double sc = (val * u.a) * rsqrt(r2); // offset / r_sep                 HealpixRunner.py:345-346
         // :347 non-finite -> 0 (r_sep = 0, NaN/inf table value, outside the table); exact zeros add nothing
         if (!isfinite(sc) || sc == 0.0) return;
-        double nx = px + sc * dx, ny = py + sc * dy, nz = pz + sc * dz;   // :350 nw_pos = pos + offset
-        double ninv = rsqrt(nx * nx + ny * ny + nz * nz);
-        red_add(out + lp, nx * ninv - x);                                 // :351-355
-        red_add(out + nloc + lp, ny * ninv - y);
-        red_add(out + 2 * nloc + lp, nz * ninv - z);
+        const double nx = fma(sc, dx, px), ny = fma(sc, dy, py), nz = fma(sc, dz, pz);   // :350 nw_pos = pos + offset
+        const double ninv = rsqrt(nx * nx + ny * ny + nz * nz);
+        red_add(p0, fma(nx, ninv, -x));            // :351-355
+        red_add(p1, fma(ny, ninv, -y));
+        red_add(p2, fma(nz, ninv, -z));
     }
 }
 
-// A (halo, ring) segment staged in shared memory by the thread that derived it.
-struct RingSeg {
+// A (halo, ring) segment staged in shared memory by the thread that derived it (the warp loop then pays LDS only).
+struct __align__(16) RingSeg {
     i64 lbase;             // ring's first pixel - pix_lo
-    int nr, ip_lo, cnt, shifted;
+    int nr, ip_lo;
+    int cnt, flags;        // flags: 1 = ring straddles the owned pixel range, 2 = equatorial ring (nr = 4 nside)
+    int active, pad;
     double z, sth;         // ring z, sin(theta)
-    double rotS, rotC;     // sin / cos of 32 pixel steps in azimuth
+    double pz, sD;         // z * D, sin(theta) * D
+    double phase0, inv2nr; // azimuth of pixel ip_lo in half-turns, 2 / nr
+    double c0, s0;         // cos / sin of phase0 (equatorial rings)
+    double rotC, rotS;     // cos / sin of a 32-pixel azimuth step
 };
+
+template <bool PAINT, bool UNIFORM, bool CHECK>
+__device__ __forceinline__ void ring_pixels(const TableView &T, const double *__restrict__ row, const HaloUpd &u,
+                                            const RingSeg &g, double cs, double sn, int lane, double *__restrict__ out,
+                                            i64 nloc, const double2 *__restrict__ l2tab) {
+    const int cnt = g.cnt, nr = g.nr;
+    const double z = g.z, sth = g.sth, pz = g.pz, sD = g.sD, rotC = g.rotC, rotS = g.rotS;
+    double *__restrict__ b0 = out + g.lbase;
+    int ip = g.ip_lo + lane;
+    if (ip >= nr) ip -= nr;
+    for (int i = lane; i < cnt; i += 32) {
+        if (!CHECK || (unsigned long long)(g.lbase + ip) < (unsigned long long)nloc)
+            shell_update<PAINT, UNIFORM>(T, row, u, sth * cs, sth * sn, z, sD * cs, sD * sn, pz, b0 + ip, b0 + nloc + ip,
+                                         b0 + 2 * nloc + ip, l2tab);
+        ip += 32;
+        if (ip >= nr) ip -= nr;
+        const double c2 = cs * rotC - sn * rotS;   // advance the azimuth by 32 pixels
+        sn = fma(sn, rotC, cs * rotS);
+        cs = c2;
+    }
+}
 
 template <bool PAINT, bool UNIFORM>
 __global__ void __launch_bounds__(SHELL_THREADS, SHELL_MIN_CTAS)
@@ -102,9 +148,13 @@ k_shell_halos(TableView T, Hpx h, i64 n_halo, const double *__restrict__ halos, 
     __shared__ RingSeg segs[RING_CHUNK];
     __shared__ double2 l2tab[BFG_LOG2_TAB];
     __shared__ int s_next;
+    __shared__ int s_cnt[SHELL_THREADS / 32];
     load_log2_table(l2tab, g_l2tab);   // visible after the first __syncthreads() below
     const int lane = threadIdx.x & 31;
     const i64 nloc = pix_hi - pix_lo;
+    // azimuth of `lane` pixels on an equatorial ring (every equatorial ring has 4 nside pixels): computed once
+    double eqC, eqS;
+    sincospi((double)lane * (2.0 / (double)h.nl4), &eqS, &eqC);
     i64 done = 0;
 
     for (i64 j = blockIdx.x; j < n_halo; j += gridDim.x) {
@@ -113,12 +163,11 @@ k_shell_halos(TableView T, Hpx h, i64 n_halo, const double *__restrict__ halos, 
         bool valid;
         blend_row(T, s.lnz, s.lnM, extras ? extras + j * n_extra : nullptr, row, valid);
         const DiscRings d = disc_rings(h, s.theta, s.phi, s.radius);
-        const HaloUpd u = make_upd(s);
+        const HaloUpd u = make_upd(T, s);
         // `if pixind.size < 4` (HealpixRunner.py:333) can only trigger for discs of a few pixels (<= ~12 rings)
         const bool tiny = !PAINT && (s.radius * s.radius * (double)h.npix * 0.25 < 64.0);
 
         if (tiny) {   // count the disc (block-wide); discs with no pixel centre at all land here too
-            __shared__ int s_cnt[SHELL_THREADS / 32];
             int c = 0;
             for (i64 iz = d.ra + threadIdx.x; iz <= d.rb; iz += SHELL_THREADS) {
                 i64 start, nr, ip_lo, cnt; bool sh;
@@ -136,11 +185,14 @@ k_shell_halos(TableView T, Hpx h, i64 n_halo, const double *__restrict__ halos, 
                     get_interpol(h, s.theta_ll, s.phi_ll, pix, w);   // HealpixRunner.py:334
                     i64 p = pix[threadIdx.x];
                     if (p >= pix_lo && p < pix_hi) {
-                        double x, y, z;
-                        pix2vec(h, p, x, y, z);
-                        shell_update<PAINT, UNIFORM>(T, row, valid, u, x, y, z, x * u.D, y * u.D, z * u.D, out, nloc,
-                                                     p - pix_lo, l2tab);
                         ++done;
+                        if (valid) {
+                            double x, y, z;
+                            pix2vec(h, p, x, y, z);
+                            double *q = out + (p - pix_lo);
+                            shell_update<PAINT, UNIFORM>(T, row, u, x, y, z, x * u.D, y * u.D, z * u.D, q, q + nloc,
+                                                         q + 2 * nloc, l2tab);
+                        }
                     }
                 }
                 continue;   // uniform across the block
@@ -152,17 +204,21 @@ k_shell_halos(TableView T, Hpx h, i64 n_halo, const double *__restrict__ halos, 
             {
                 i64 iz = base + threadIdx.x;
                 RingSeg g;
-                g.cnt = 0; g.nr = 0;
+                g.cnt = 0; g.active = 0;
                 if (iz <= d.rb) {
                     i64 start, nr, ip_lo, cnt; bool sh;
                     disc_ring_span(h, d, iz, start, nr, sh, ip_lo, cnt);
-                    g.cnt = (int)cnt;     // counted even when the ring is outside the owned range (fallback test)
-                    g.nr = 0;             // nr == 0 marks "nothing to do here"
                     if (cnt > 0 && start < pix_hi && start + nr > pix_lo) {
+                        g.active = 1;
                         g.lbase = start - pix_lo;
-                        g.nr = (int)nr; g.ip_lo = (int)ip_lo; g.shifted = sh ? 1 : 0;
+                        g.nr = (int)nr; g.ip_lo = (int)ip_lo; g.cnt = (int)cnt;
+                        g.flags = ((start < pix_lo || start + nr > pix_hi) ? 1 : 0) | ((nr == h.nl4) ? 2 : 0);
                         ring_z_sth(h, iz, g.z, g.sth);
-                        sincospi(64.0 / (double)nr, &g.rotS, &g.rotC);   // 32 pixels * (2/nr) half-turns
+                        g.pz = g.z * u.D; g.sD = g.sth * u.D;
+                        g.inv2nr = 2.0 / (double)nr;
+                        g.phase0 = ((double)ip_lo + (sh ? 0.5 : 0.0)) * g.inv2nr;
+                        sincospi(g.phase0, &g.s0, &g.c0);
+                        sincospi(32.0 * g.inv2nr, &g.rotS, &g.rotC);
                     }
                 }
                 segs[threadIdx.x] = g;
@@ -177,30 +233,31 @@ k_shell_halos(TableView T, Hpx h, i64 n_halo, const double *__restrict__ halos, 
                 if (lane == 0) r = atomicAdd(&s_next, 1);
                 r = __shfl_sync(0xffffffffu, r, 0);
                 if (r >= nseg) break;
-                const int cnt = segs[r].cnt;
-                const int nr = segs[r].nr;
-                if (cnt == 0 || nr == 0) continue;
-                const i64 lbase = segs[r].lbase;
-                const double z = segs[r].z, sth = segs[r].sth;
-                const double pz = z * u.D, sD = sth * u.D;
-                int ip = segs[r].ip_lo + lane;
-                if (ip >= nr) ip -= nr;
-                double sn, cs;
-                sincospi(((double)ip + (segs[r].shifted ? 0.5 : 0.0)) * (2.0 / (double)nr), &sn, &cs);
-                const double rotS = segs[r].rotS, rotC = segs[r].rotC;
-                for (int i = lane; i < cnt; i += 32) {
-                    i64 lp = lbase + ip;
-                    if ((unsigned long long)lp < (unsigned long long)nloc) {
-                        shell_update<PAINT, UNIFORM>(T, row, valid, u, sth * cs, sth * sn, z, sD * cs, sD * sn, pz, out,
-                                                     nloc, lp, l2tab);
-                        ++done;
+                const RingSeg &g = segs[r];
+                if (!g.active) continue;
+                const int cnt = g.cnt;
+                // updates of this ring owned by this lane (the pixel loop itself carries no counter)
+                if (!(g.flags & 1)) {
+                    done += (cnt > lane) ? ((cnt - lane + 31) >> 5) : 0;
+                } else {
+                    int ip = g.ip_lo + lane;
+                    if (ip >= g.nr) ip -= g.nr;
+                    for (int i = lane; i < cnt; i += 32) {
+                        done += ((unsigned long long)(g.lbase + ip) < (unsigned long long)nloc) ? 1 : 0;
+                        ip += 32;
+                        if (ip >= g.nr) ip -= g.nr;
                     }
-                    ip += 32;
-                    if (ip >= nr) ip -= nr;
-                    double c2 = cs * rotC - sn * rotS;   // advance the azimuth by 32 pixels
-                    sn = sn * rotC + cs * rotS;
-                    cs = c2;
                 }
+                if (!valid) continue;   // halo outside the table in (z, M, extras): every read-out is NaN -> adds nothing
+                double cs, sn;
+                if (g.flags & 2) {      // equatorial: rotate the staged (c0, s0) by this lane's cached step
+                    cs = g.c0 * eqC - g.s0 * eqS;
+                    sn = fma(g.s0, eqC, g.c0 * eqS);
+                } else {
+                    sincospi(fma((double)lane, g.inv2nr, g.phase0), &sn, &cs);
+                }
+                if (g.flags & 1) ring_pixels<PAINT, UNIFORM, true>(T, row, u, g, cs, sn, lane, out, nloc, l2tab);
+                else ring_pixels<PAINT, UNIFORM, false>(T, row, u, g, cs, sn, lane, out, nloc, l2tab);
             }
             __syncthreads();  // before the next chunk overwrites the segments
         }
