@@ -17,9 +17,9 @@ namespace {
 
 constexpr int SHELL_THREADS = 128;
 #ifndef BFG_SHELL_MIN_CTAS
-#define BFG_SHELL_MIN_CTAS 6
+#define BFG_SHELL_MIN_CTAS 8
 #endif
-constexpr int SHELL_MIN_CTAS = BFG_SHELL_MIN_CTAS;   // 6 -> registers capped at 80/thread: 24 warps/SM hide the fp64 latency
+constexpr int SHELL_MIN_CTAS = BFG_SHELL_MIN_CTAS;   // 8 -> 64 registers/thread, 32 warps/SM: measured best (profiles/README.md, occupancy sweep)
 constexpr int RING_CHUNK = SHELL_THREADS;   // ring segments staged in shared memory per pass (one per thread)
 
 struct HaloSph {

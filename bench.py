@@ -315,9 +315,12 @@ def run_b200(args):
         barrier()
         t0 = time.perf_counter()
         n_e2e = 3
+        iter_ms = []
         for _ in range(n_e2e):
+            ti = time.perf_counter()
             out = runner.process()
             del out   # a held result keeps its pinned buffer; the next call would then pin a fresh 1.6 GB (~0.8 s)
+            iter_ms.append(round(1e3 * (time.perf_counter() - ti), 1))
         barrier()
         dt = (time.perf_counter() - t0) / n_e2e
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
@@ -327,6 +330,7 @@ def run_b200(args):
                "h2d_bytes_per_step": int((hi - lo) * 8 + rec.size * 8), "d2h_bytes_per_step": int(npix * 8),
                "ms_per_step": 1e3 * float(tt[0]), "host_prep_ms": 1e3 * runner.last_timing.get("host_prep_s", 0.0),
                "host_threads": int(os.environ.get("BFG_HOST_THREADS", min(16, os.cpu_count() or 1))),
+               "iter_ms": iter_ms, "phases_ms": {k: round(1e3 * v, 2) for k, v in runner.last_timing.items()},
                "includes": "host per-halo scalar prep, H2D (pinned map + halo records), kernels, NCCL reduce (N>1), D2H"}
 
     if world > 1:
