@@ -61,6 +61,28 @@ def _sort_records(d_rec, d_ext, mode, p0, p1=0.0, ndim=3):
     return out, out_e
 
 
+_PINNED_FREE = {}      # numel -> list of idle pinned float64 tensors
+
+
+def _pinned_result(numel):
+    """
+    A float64 pinned host buffer for a D2H result, as (tensor, numpy view).  Buffers are recycled as soon as the numpy
+    array handed to the caller (and every view of it) is garbage-collected, so steady-state calls never pay the ~0.5 s/GB
+    page-locking of a fresh allocation; a caller that keeps N results alive simply owns N buffers.
+    """
+    import weakref
+    torch = _torch()
+    free = _PINNED_FREE.setdefault(numel, [])
+    t = free.pop() if free else torch.empty(numel, dtype=torch.float64, pin_memory=True)
+    arr = t.numpy()
+
+    def _recycle(tensor=t, bucket=free):
+        if len(bucket) < 4:
+            bucket.append(tensor)
+    weakref.finalize(arr, _recycle)
+    return t, arr
+
+
 def _parallel_chunks(fn, n, chunk=65536):
     """Run fn(slice) over [0, n) in chunks on a small thread pool (BFG_HOST_THREADS, default min(16, cores))."""
     import os
@@ -163,17 +185,16 @@ class DefaultRunner(object):
         torch = _torch()
         return torch.device('cuda', torch.cuda.current_device() if self.device is None else int(self.device))
 
-    def halo_records(self, paint):
+    def _record_plan(self, paint):
         """
-        The per-halo scalars of HealpixRunner.py:317-329 (+ BaryonCorrection.py:371,398-399,410), vectorised.
-        Returns (records[n,16] float64, extras[n,k] or None).
+        The per-halo scalars of HealpixRunner.py:317-329 (+ BaryonCorrection.py:371,398-399,410), vectorised, as a plan:
+        returns (n, fill) where fill(dst, sl) writes the records of halos `sl` into dst, an [m, 16] float64 view.
         """
         cat = self.HaloLightConeCatalog.cat
         n = cat.size
         cosmo = cosmology.runner_cosmology(self.cosmo, with_w0=True)          # :280-284
-        rec = np.zeros((_lib.HALO_STRIDE, n), dtype=np.float64).T              # field-major storage, [n,16] view
         if n == 0:
-            return rec, None
+            return 0, None
         D_of_z = cosmology.D_A_spline(cosmo, cat['z'])                         # :297-299
         mcosmo = None if paint else _model_cosmo(self.model, cosmo)
         R = np.empty(n)
@@ -181,10 +202,10 @@ class DefaultRunner(object):
         R_com = None if paint else np.empty(n)
         pixarea = 4 * np.pi / self.LightconeShell.map.size
         eps_model = None if paint else self.model.epsilon_max
+        self.last_scalars = dict(R_run=R, D_A=D, R_model_com=R_com)
 
-        def fill(sl):   # numpy releases the GIL inside these ufuncs, so chunks run on several host cores
+        def fill(r, sl):   # numpy releases the GIL inside these ufuncs, so chunks run on several host cores
             M, z = cat['M'][sl], cat['z'][sl]
-            r = rec[sl]
             a = 1 / (1 + z)                                                    # :319
             R[sl] = cosmology.radius_of_mass(cosmo, M, a, self.mass_def)       # :320 physical Mpc
             D[sl] = D_of_z(z)                                                  # :321
@@ -210,12 +231,65 @@ class DefaultRunner(object):
                 r[:, _lib.HS_LNRCOM] = np.log(R_com[sl])                       # :408
                 r[:, _lib.HS_SCALE] = 1.0
             r[:, _lib.HS_THETA_LL], r[:, _lib.HS_PHI_LL] = theta_ll, phi_ll
+        return n, fill
 
-        _parallel_chunks(fill, n)
-        self.last_scalars = dict(R_run=R, D_A=D, R_model_com=None if paint else R_com)
+    def halo_records(self, paint):
+        """All halo records at once: (records[n,16] float64 (field-major storage), extras[n,k] or None)."""
+        n, fill = self._record_plan(paint)
+        rec = np.zeros((_lib.HALO_STRIDE, n), dtype=np.float64).T
         keys = list(vars(self.model).get('p_keys', []))                        # :304
         _check_keys(self.model, keys)
-        return rec, _extras(cat, keys)
+        if n == 0:
+            return rec, None
+        _parallel_chunks(lambda sl: fill(rec[sl], sl), n)
+        return rec, _extras(self.HaloLightConeCatalog.cat, keys)
+
+    def _halo_loop(self, paint, table, launch, NSIDE, lo, hi, dev):
+        """
+        Host prep -> upload -> sky sort -> `launch(d_rec, d_ext, n, k)` in up to 4 batches: numpy prepares batch k+1 on the
+        host cores while the GPU runs the halo loop of batch k (the sums are order-independent, so batching is free).
+        """
+        import time
+        from concurrent.futures import ThreadPoolExecutor
+        import os
+        torch = _torch()
+        t0 = time.perf_counter()
+        n, fill = self._record_plan(paint)
+        keys = list(vars(self.model).get('p_keys', []))                        # :304
+        _check_keys(self.model, keys)
+        if n == 0:
+            self.last_timing = dict(host_prep_s=0.0)
+            return 0
+        cat = self.HaloLightConeCatalog.cat
+        extras_all = _extras(cat, keys)
+        nb = 4 if n >= (1 << 18) else 1
+        bounds = [(n * b) // nb for b in range(nb + 1)]
+        chunk = 65536
+        nthreads = int(os.environ.get("BFG_HOST_THREADS", min(16, os.cpu_count() or 1)))
+        host_s = 0.0
+        with ThreadPoolExecutor(max_workers=max(1, nthreads)) as ex:
+            batches = []
+            for b in range(nb):
+                b0, b1 = bounds[b], bounds[b + 1]
+                buf = np.zeros((_lib.HALO_STRIDE, b1 - b0), dtype=np.float64).T
+                futs = [ex.submit(fill, buf[i - b0:min(i + chunk, b1) - b0], slice(i, min(i + chunk, b1)))
+                        for i in range(b0, b1, chunk)]
+                batches.append((b0, b1, buf, futs))
+            for k, (b0, b1, buf, futs) in enumerate(batches):
+                tw = time.perf_counter()
+                for f in futs:
+                    f.result()
+                host_s += time.perf_counter() - tw
+                ext = None if extras_all is None else extras_all[b0:b1]
+                rec, ext = self._owned_halos(buf, ext, NSIDE, lo, hi)
+                with torch.cuda.device(dev):
+                    d_rec = _upload_records(rec, dev)
+                    d_ext = None if ext is None else _to_device(ext, dev)
+                    if self.sort_halos:
+                        d_rec, d_ext = _sort_records(d_rec, d_ext, 0, SKY_BAND_RAD)
+                    launch(d_rec, d_ext, rec.shape[0], k)
+        self.last_timing = dict(host_prep_s=time.perf_counter() - t0, host_wait_s=host_s, batches=nb)
+        return nb
 
     def _range(self, npix):
         return (0, npix) if self.pix_range is None else (int(self.pix_range[0]), int(self.pix_range[1]))
@@ -245,20 +319,15 @@ class BaryonifyShell(DefaultRunner):
         with torch.cuda.device(dev):   # table first: a model without one fails here, as in the reference
             table = self._tables.get((id(self.model), id(self.model.interp_d) if hasattr(self.model, 'interp_d') else 0),
                                      lambda: displacement_table_of(self.model, dev.index))
-        import time
-        t0 = time.perf_counter()
-        rec, extras = self.halo_records(paint=False)
-        rec, extras = self._owned_halos(rec, extras, NSIDE, lo, hi)
-        self.last_timing = dict(host_prep_s=time.perf_counter() - t0)
         with torch.cuda.device(dev):
-            d_rec = _upload_records(rec, dev)
-            d_ext = None if extras is None else _to_device(extras, dev)
-            if self.sort_halos:
-                d_rec, d_ext = _sort_records(d_rec, d_ext, 0, SKY_BAND_RAD)
             d_off = torch.zeros((3, hi - lo), dtype=torch.float64, device=dev)
-            d_n = torch.zeros(1, dtype=torch.int64, device=dev)
-            _lib.check(L.bfg_shell_offsets(table.handle, NSIDE, rec.shape[0], _lib.ptr(d_rec), _lib.ptr(d_ext),
-                                           table.n_extra, _lib.ptr(d_off), lo, hi, _lib.ptr(d_n), _lib.current_stream()))
+            d_nb = torch.zeros(4, dtype=torch.int64, device=dev)
+
+        def launch(d_rec, d_ext, n, k):
+            _lib.check(L.bfg_shell_offsets(table.handle, NSIDE, n, _lib.ptr(d_rec), _lib.ptr(d_ext), table.n_extra,
+                                           _lib.ptr(d_off), lo, hi, d_nb.data_ptr() + 8 * k, _lib.current_stream()))
+        self._halo_loop(False, table, launch, NSIDE, lo, hi, dev)
+        d_n = d_nb.sum().reshape(1)
         return d_off, d_n
 
     def process(self):
@@ -298,7 +367,7 @@ class BaryonifyShell(DefaultRunner):
                 d_sums[1] = d_map_sum
             if prof:
                 torch.cuda.synchronize(); t_regrid = time.perf_counter()
-            out = torch.empty(npix, dtype=torch.float64, pin_memory=True)
+            out, out_np = _pinned_result(npix)
             if prof:
                 t_alloc = time.perf_counter()
             out.copy_(d_new, non_blocking=True)
@@ -314,7 +383,7 @@ class BaryonifyShell(DefaultRunner):
                                     d2h_s=t_end - t_alloc, total_s=t_end - t_start)
         assert np.isclose(new_sum, old_sum), \
             "ERROR in pixel regridding, sum(new_map) [%0.14e] != sum(oldmap) [%0.14e]" % (new_sum, old_sum)   # :368-370
-        return out.numpy()
+        return out_np
 
 
 class PaintProfilesShell(DefaultRunner):
@@ -331,26 +400,25 @@ class PaintProfilesShell(DefaultRunner):
         with torch.cuda.device(dev):
             table = self._tables.get((id(self.model), id(getattr(self.model, 'interp2D', None))),
                                      lambda: profile_table_of(self.model, '2D', dev.index))
-        rec, extras = self.halo_records(paint=True)
-        rec, extras = self._owned_halos(rec, extras, NSIDE, lo, hi)
         with torch.cuda.device(dev):
-            d_rec = _upload_records(rec, dev)
-            d_ext = None if extras is None else _to_device(extras, dev)
-            if self.sort_halos:
-                d_rec, d_ext = _sort_records(d_rec, d_ext, 0, SKY_BAND_RAD)
             d_new = torch.zeros(hi - lo, dtype=torch.float64, device=dev)
-            d_n = torch.zeros(1, dtype=torch.int64, device=dev)
-            _lib.check(L.bfg_shell_paint(table.handle, NSIDE, rec.shape[0], _lib.ptr(d_rec), _lib.ptr(d_ext),
-                                         table.n_extra, _lib.ptr(d_new), lo, hi, _lib.ptr(d_n), _lib.current_stream()))
+            d_nb = torch.zeros(4, dtype=torch.int64, device=dev)
+
+        def launch(d_rec, d_ext, n, k):
+            _lib.check(L.bfg_shell_paint(table.handle, NSIDE, n, _lib.ptr(d_rec), _lib.ptr(d_ext), table.n_extra,
+                                         _lib.ptr(d_new), lo, hi, d_nb.data_ptr() + 8 * k, _lib.current_stream()))
+        self._halo_loop(True, table, launch, NSIDE, lo, hi, dev)
+        with torch.cuda.device(dev):
+            d_n = d_nb.sum().reshape(1)
             if self.pix_range is not None:
                 from .parallel import gather_owned_ranges
                 d_new = gather_owned_ranges(d_new, npix)
-            out = torch.empty(npix, dtype=torch.float64, pin_memory=True)
+            out, out_np = _pinned_result(npix)
             out.copy_(d_new, non_blocking=True)
             n_up = int(d_n.cpu()[0])
             torch.cuda.current_stream().synchronize()
         self.last_stats = dict(n_updates=n_up)
-        return out.numpy()
+        return out_np
 
 
 # =====================================================================================================================
@@ -519,7 +587,7 @@ class BaryonifyGrid(DefaultRunnerGrid):
                 _lib.check(L.bfg_sum_f64(_lib.ptr(d_map), d_map.numel(), d_sums.data_ptr() + 8, st))
             else:
                 d_sums[1] = d_map_sum
-            out = torch.empty(orig_map.size, dtype=torch.float64, pin_memory=True)
+            out, out_np = _pinned_result(orig_map.size)
             out.copy_(d_new, non_blocking=True)
             sums = d_sums.cpu()
             n_up = int(d_n.cpu()[0])
@@ -528,7 +596,7 @@ class BaryonifyGrid(DefaultRunnerGrid):
         self.last_stats = dict(n_updates=n_up, new_sum=new_sum, old_sum=old_sum)
         assert np.isclose(new_sum, old_sum), \
             "ERROR in pixel regridding, sum(new_map) [%0.14e] != sum(oldmap) [%0.14e]" % (new_sum, old_sum)   # :616-619
-        return out.numpy().reshape(orig_map.shape)
+        return out_np.reshape(orig_map.shape)
 
 
 class PaintProfilesGrid(DefaultRunnerGrid):
@@ -560,12 +628,12 @@ class PaintProfilesGrid(DefaultRunnerGrid):
             if self.plane_range is not None:
                 from .parallel import gather_owned_ranges
                 d_new = gather_owned_ranges(d_new, gm.map.size)
-            out = torch.empty(gm.map.size, dtype=torch.float64, pin_memory=True)
+            out, out_np = _pinned_result(gm.map.size)
             out.copy_(d_new, non_blocking=True)
             n_up = int(d_n.cpu()[0])
             torch.cuda.current_stream().synchronize()
         self.last_stats = dict(n_updates=n_up)
-        return out.numpy().reshape(gm.map.shape)
+        return out_np.reshape(gm.map.shape)
 
 
 # =====================================================================================================================
