@@ -19,6 +19,19 @@ void set_error(const char *fmt, ...) {
 using namespace bfg;
 
 namespace bfg {
+int retain_async_pool() {
+    static bool done[64] = {false};
+    int dev = 0;
+    BFG_CUDA_OK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || done[dev]) return BFG_OK;
+    cudaMemPool_t pool;
+    BFG_CUDA_OK(cudaDeviceGetDefaultMemPool(&pool, dev));
+    unsigned long long keep = ~0ULL;
+    BFG_CUDA_OK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    done[dev] = true;
+    return BFG_OK;
+}
+
 int get_log2_table(const double2 **d_tab) {
     static double2 *tabs[64] = {nullptr};
     int dev = 0;

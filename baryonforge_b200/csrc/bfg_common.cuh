@@ -17,6 +17,9 @@ typedef long long i64;
 namespace bfg {
 
 void set_error(const char *fmt, ...);
+// Keep stream-ordered scratch (cudaMallocAsync) cached in the device's default pool instead of handing it back to
+// the OS at every synchronisation (the default release threshold is 0).  Idempotent per device.
+int retain_async_pool();
 
 #define BFG_CUDA_OK(expr)                                                                  \
     do {                                                                                   \

@@ -203,6 +203,7 @@ extern "C" int bfg_snap_build_cells(int ndim, int64_t n_part, const double *d_x,
     BFG_REQUIRE(d_x && d_y && (ndim == 2 || d_z) && d_cell_start && d_order && d_xs && d_ys && (ndim == 2 || d_zs), "null argument");
     BFG_REQUIRE(ncell >= 1 && (ndim == 2 ? ncell <= 32768 : ncell <= 1024), "ncell out of range");
     BFG_REQUIRE(L > 0, "L must be positive");
+    if (int rc = retain_async_pool()) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const i64 ncells = (ndim == 3) ? (i64)ncell * ncell * ncell : (i64)ncell * ncell;
     int *cell_id = nullptr;

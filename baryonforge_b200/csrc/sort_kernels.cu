@@ -61,6 +61,7 @@ extern "C" int bfg_halo_sort(int mode, int64_t n_halo, const double *d_in, doubl
     BFG_REQUIRE(n_halo >= 0 && n_halo < ((int64_t)1 << 32), "n_halo out of range");
     BFG_REQUIRE(n_extra == 0 || (d_extras_in && d_extras_out), "extras missing");
     if (n_halo == 0) return BFG_OK;
+    if (int rc = retain_async_pool()) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     unsigned long long *keys = nullptr, *keys2 = nullptr;
     unsigned int *idx = nullptr, *idx2 = nullptr;

@@ -264,9 +264,9 @@ class DefaultRunner(object):
         extras_all = _extras(cat, keys)
         nb = 4 if n >= (1 << 18) else 1
         bounds = [(n * b) // nb for b in range(nb + 1)]
-        chunk = 65536
+        chunk = 16384          # small enough that batch 0 is complete long before the last batch
         nthreads = int(os.environ.get("BFG_HOST_THREADS", min(16, os.cpu_count() or 1)))
-        host_s = 0.0
+        host_s = gpu_issue_s = 0.0
         with ThreadPoolExecutor(max_workers=max(1, nthreads)) as ex:
             batches = []
             for b in range(nb):
@@ -279,7 +279,8 @@ class DefaultRunner(object):
                 tw = time.perf_counter()
                 for f in futs:
                     f.result()
-                host_s += time.perf_counter() - tw
+                tg = time.perf_counter()
+                host_s += tg - tw
                 ext = None if extras_all is None else extras_all[b0:b1]
                 rec, ext = self._owned_halos(buf, ext, NSIDE, lo, hi)
                 with torch.cuda.device(dev):
@@ -288,7 +289,9 @@ class DefaultRunner(object):
                     if self.sort_halos:
                         d_rec, d_ext = _sort_records(d_rec, d_ext, 0, SKY_BAND_RAD)
                     launch(d_rec, d_ext, rec.shape[0], k)
-        self.last_timing = dict(host_prep_s=time.perf_counter() - t0, host_wait_s=host_s, batches=nb)
+                gpu_issue_s += time.perf_counter() - tg
+        self.last_timing = dict(host_prep_s=time.perf_counter() - t0, host_wait_s=host_s, gpu_issue_s=gpu_issue_s,
+                                batches=nb * 1e-3)
         return nb
 
     def _range(self, npix):
