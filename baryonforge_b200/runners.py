@@ -39,7 +39,7 @@ def _upload_records(rec, dev):
     torch = _torch()
     n = rec.shape[0]
     if n > 0 and rec.T.flags.c_contiguous and not rec.flags.c_contiguous:
-        d_t = torch.from_numpy(rec.T).to(dev, non_blocking=True)
+        d_t = torch.from_numpy(rec.T).to(dev, non_blocking=True)   # asynchronous when the storage is pinned
         d_rec = torch.empty((n, _lib.HALO_STRIDE), dtype=torch.float64, device=dev)
         _lib.check(_lib.lib().bfg_transpose_offsets(_lib.ptr(d_t), _lib.ptr(d_rec), n, _lib.HALO_STRIDE,
                                                     _lib.current_stream()))
@@ -81,6 +81,22 @@ def _pinned_result(numel):
             bucket.append(tensor)
     weakref.finalize(arr, _recycle)
     return t, arr
+
+
+_PINNED_SCRATCH = {}   # numel -> list of idle pinned float64 staging tensors (halo-record batches)
+
+
+def _take_scratch(numel):
+    torch = _torch()
+    free = _PINNED_SCRATCH.setdefault(numel, [])
+    return free.pop() if free else torch.empty(numel, dtype=torch.float64, pin_memory=True)
+
+
+def _give_scratch(tensors):
+    for t in tensors:
+        bucket = _PINNED_SCRATCH.setdefault(t.numel(), [])
+        if len(bucket) < 8:
+            bucket.append(t)
 
 
 def _parallel_chunks(fn, n, chunk=65536):
@@ -175,6 +191,7 @@ class DefaultRunner(object):
     def __getstate__(self):
         d = dict(self.__dict__)
         d['_tables'] = None
+        d.pop('_scratch_inflight', None)
         return d
 
     def __setstate__(self, d):
@@ -260,6 +277,11 @@ class DefaultRunner(object):
         if n == 0:
             self.last_timing = dict(host_prep_s=0.0)
             return 0
+        # staging buffers of the previous call may still feed an un-synchronised stream (offsets_on_device callers)
+        if getattr(self, '_scratch_inflight', None):
+            torch.cuda.current_stream().synchronize()
+            _give_scratch(self._scratch_inflight)
+        self._scratch_inflight = []
         cat = self.HaloLightConeCatalog.cat
         extras_all = _extras(cat, keys)
         nb = 4 if n >= (1 << 18) else 1
@@ -271,7 +293,12 @@ class DefaultRunner(object):
             batches = []
             for b in range(nb):
                 b0, b1 = bounds[b], bounds[b + 1]
-                buf = np.zeros((_lib.HALO_STRIDE, b1 - b0), dtype=np.float64).T
+                # pinned, field-major staging: the H2D copy is then truly asynchronous (a pageable source would make the
+                # host wait for the previous batch's kernel, serialising prep and GPU work)
+                stage = _take_scratch(_lib.HALO_STRIDE * (b1 - b0))
+                self._scratch_inflight.append(stage)
+                buf = stage.numpy().reshape(_lib.HALO_STRIDE, b1 - b0).T
+                buf[:, _lib.HS_RESERVED] = 0.0
                 futs = [ex.submit(fill, buf[i - b0:min(i + chunk, b1) - b0], slice(i, min(i + chunk, b1)))
                         for i in range(b0, b1, chunk)]
                 batches.append((b0, b1, buf, futs))
@@ -377,6 +404,8 @@ class BaryonifyShell(DefaultRunner):
             sums = d_sums.cpu()
             n_up = int(d_n.cpu()[0])
             torch.cuda.current_stream().synchronize()
+        _give_scratch(getattr(self, '_scratch_inflight', []))
+        self._scratch_inflight = []
         new_sum, old_sum = float(sums[0]), float(sums[1])
         self.last_stats = dict(n_updates=n_up, new_sum=new_sum, old_sum=old_sum)
         if prof:
@@ -420,6 +449,8 @@ class PaintProfilesShell(DefaultRunner):
             out.copy_(d_new, non_blocking=True)
             n_up = int(d_n.cpu()[0])
             torch.cuda.current_stream().synchronize()
+        _give_scratch(getattr(self, '_scratch_inflight', []))
+        self._scratch_inflight = []
         self.last_stats = dict(n_updates=n_up)
         return out_np
 
