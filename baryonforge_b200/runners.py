@@ -284,7 +284,7 @@ class DefaultRunner(object):
         self._scratch_inflight = []
         cat = self.HaloLightConeCatalog.cat
         extras_all = _extras(cat, keys)
-        nb = 4 if n >= (1 << 18) else 1
+        nb = 4 if n >= getattr(self, 'batch_min_halos', 1 << 18) else 1
         bounds = [(n * b) // nb for b in range(nb + 1)]
         chunk = 16384          # small enough that batch 0 is complete long before the last batch
         nthreads = int(os.environ.get("BFG_HOST_THREADS", min(16, os.cpu_count() or 1)))
@@ -318,7 +318,7 @@ class DefaultRunner(object):
                     launch(d_rec, d_ext, rec.shape[0], k)
                 gpu_issue_s += time.perf_counter() - tg
         self.last_timing = dict(host_prep_s=time.perf_counter() - t0, host_wait_s=host_s, gpu_issue_s=gpu_issue_s,
-                                batches=nb * 1e-3)
+                                batches=float(nb))
         return nb
 
     def _range(self, npix):

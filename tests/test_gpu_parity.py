@@ -301,3 +301,18 @@ def test_full_size_subdomain_parity_nside4096():
     assert_close(got, off_w[touched], "NSIDE=4096 offsets on touched pixels")
     # nothing outside the touched set
     assert int((d_off != 0).any(dim=0).sum().item()) <= touched.size
+
+
+def test_batched_halo_loop_equals_single_batch():
+    """The pipelined 4-batch halo loop (used for >= 262144 halos) gives the single-batch answer."""
+    import baryonforge_b200 as b
+    cat, shell, model, axes, vals = _fresh_shell_case(128, 5000, 21, 20, 20)
+    one = b.BaryonifyShell(cat, shell, 20, model, verbose=False)
+    four = b.BaryonifyShell(cat, shell, 20, model, verbose=False)
+    four.batch_min_halos = 1000
+    a, na = one.offsets_on_device()
+    c, nc = four.offsets_on_device()
+    assert four.last_timing["batches"] == 4.0 and one.last_timing["batches"] == 1.0
+    assert int(na.cpu()[0]) == int(nc.cpu()[0])
+    assert_close(c.cpu().numpy(), a.cpu().numpy(), "batched offsets", rtol=1e-9, atol_scale=1e-12)
+    assert_close(four.process(), one.process(), "batched map", rtol=1e-9, atol_scale=1e-12)
