@@ -43,6 +43,13 @@ _SIGNATURES = {
     "bfg_shell_offsets": ([c_ptr, C.c_int, c_i64, c_ptr, c_ptr, C.c_int, c_ptr, c_i64, c_i64, c_ptr, c_ptr], C.c_int),
     "bfg_shell_paint": ([c_ptr, C.c_int, c_i64, c_ptr, c_ptr, C.c_int, c_ptr, c_i64, c_i64, c_ptr, c_ptr], C.c_int),
     "bfg_shell_regrid": ([C.c_int, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_ptr], C.c_int),
+    "bfg_shell_regrid_p2p": ([C.c_int, c_ptr, c_ptr, c_i64, c_i64, C.c_int, C.c_int, C.POINTER(c_i64), C.POINTER(c_ptr),
+                              c_ptr, c_ptr], C.c_int),
+    "bfg_shared_alloc": ([C.POINTER(c_ptr), c_i64, C.c_int], C.c_int),
+    "bfg_shared_free": ([c_ptr], C.c_int),
+    "bfg_ipc_export": ([c_ptr, c_ptr], C.c_int),
+    "bfg_ipc_import": ([c_ptr, C.POINTER(c_ptr)], C.c_int),
+    "bfg_ipc_close": ([c_ptr], C.c_int),
     "bfg_grid_offsets": ([c_ptr, C.c_int, c_i64, c_dbl, c_i64, c_ptr, c_ptr, C.c_int, c_ptr, c_i64, c_i64, c_ptr, c_ptr], C.c_int),
     "bfg_grid_paint": ([c_ptr, C.c_int, c_i64, c_dbl, c_dbl, c_i64, c_ptr, c_ptr, C.c_int, c_ptr, c_i64, c_i64, c_ptr, c_ptr], C.c_int),
     "bfg_grid_regrid": ([C.c_int, c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_ptr], C.c_int),

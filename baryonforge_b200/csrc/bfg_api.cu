@@ -251,3 +251,42 @@ extern "C" int bfg_transpose_offsets(const double *d_in, double *d_out, int64_t 
     BFG_CUDA_OK(cudaGetLastError());
     return BFG_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ peer memory (IPC)
+extern "C" int bfg_shared_alloc(void **d_ptr, int64_t bytes, int device) {
+    BFG_REQUIRE(d_ptr && bytes >= 0, "bad argument");
+    int cur = 0;
+    BFG_CUDA_OK(cudaGetDevice(&cur));
+    BFG_CUDA_OK(cudaSetDevice(device));
+    cudaError_t e = cudaMalloc(d_ptr, (size_t)(bytes > 0 ? bytes : 8));
+    cudaSetDevice(cur);
+    if (e != cudaSuccess) { set_error("bfg_shared_alloc: %s", cudaGetErrorString(e)); return BFG_ERR_NOMEM; }
+    return BFG_OK;
+}
+
+extern "C" int bfg_shared_free(void *d_ptr) {
+    if (d_ptr) BFG_CUDA_OK(cudaFree(d_ptr));
+    return BFG_OK;
+}
+
+extern "C" int bfg_ipc_export(const void *d_ptr, unsigned char *handle64) {
+    BFG_REQUIRE(d_ptr && handle64, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t hdl;
+    BFG_CUDA_OK(cudaIpcGetMemHandle(&hdl, const_cast<void *>(d_ptr)));
+    memcpy(handle64, &hdl, 64);
+    return BFG_OK;
+}
+
+extern "C" int bfg_ipc_import(const unsigned char *handle64, void **d_peer_ptr) {
+    BFG_REQUIRE(handle64 && d_peer_ptr, "null argument");
+    cudaIpcMemHandle_t hdl;
+    memcpy(&hdl, handle64, 64);
+    BFG_CUDA_OK(cudaIpcOpenMemHandle(d_peer_ptr, hdl, cudaIpcMemLazyEnablePeerAccess));
+    return BFG_OK;
+}
+
+extern "C" int bfg_ipc_close(void *d_peer_ptr) {
+    if (d_peer_ptr) BFG_CUDA_OK(cudaIpcCloseMemHandle(d_peer_ptr));
+    return BFG_OK;
+}

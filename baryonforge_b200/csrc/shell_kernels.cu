@@ -547,3 +547,77 @@ extern "C" int bfg_shell_paint_host(const bfg_table *t, int nside, int64_t n_hal
     if (h_nupdates) *h_nupdates = n_up;
     return BFG_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ multi-GPU regrid
+// Re-binning fused with the exchange step of ring-range sharding: every rank owns a slice of the NEW map in memory the
+// other ranks of the box have mapped through CUDA IPC; a displaced pixel is deposited straight into the owner's slice
+// (fp64 RED over NVLink peer memory for the few deposits that cross a range border), so no full-size partial map and
+// no all-reduce are needed (SURVEY.md §8e option B; BaryonForge/utils/Parallelize.py:318 sums whole maps instead).
+namespace {
+struct OwnerTable {
+    int world;
+    i64 bounds[9];        // bounds[r] .. bounds[r+1] = pixels owned by rank r
+    double *slice[8];     // slice[r][p - bounds[r]] ; slice[self] is local memory, the others are peer mappings
+    int self;
+};
+
+__global__ void __launch_bounds__(256)
+k_shell_regrid_p2p(Hpx h, const double *__restrict__ map_in, const double *__restrict__ off, OwnerTable own, i64 pix_lo,
+                   i64 pix_hi, unsigned long long *remote_count) {
+    const i64 nloc = pix_hi - pix_lo;
+    const double inv_span = (double)own.world / (double)h.npix;
+    unsigned long long nrem = 0;
+    for (i64 lp = (i64)blockIdx.x * blockDim.x + threadIdx.x; lp < nloc; lp += (i64)gridDim.x * blockDim.x) {
+        double m = map_in[lp];
+        if (m == 0.0) continue;                                  // HealpixRunner.py:359
+        double x, y, z;
+        pix2vec(h, pix_lo + lp, x, y, z);
+        x += off[lp]; y += off[nloc + lp]; z += off[2 * nloc + lp];   // :357
+        double dn = sqrt(x * x + y * y + z * z);
+        double theta = acos(z / dn);
+        double phi = atan2(y, x);
+        if (phi < 0) phi += BFG_TWOPI;
+        double lon = phi * (180.0 / BFG_PI), lat = 90.0 - theta * (180.0 / BFG_PI);   // :358
+        double th2 = BFG_HALFPI - lat * (BFG_PI / 180.0), ph2 = lon * (BFG_PI / 180.0);
+        i64 pix[4]; double w[4];
+        get_interpol(h, th2, ph2, pix, w);                       // :361
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const i64 p = pix[k];
+            int r = min(own.world - 1, (int)((double)p * inv_span));
+            while (p < own.bounds[r]) --r;
+            while (p >= own.bounds[r + 1]) ++r;
+            double *dst = own.slice[r] + (p - own.bounds[r]);
+            if (r == own.self) {
+                red_add(dst, w[k] * m);                          // :17-71
+            } else {
+                atomicAdd_system(dst, w[k] * m);                 // owner's HBM through NVLink
+                ++nrem;
+            }
+        }
+    }
+    if (remote_count && nrem) atomicAdd(remote_count, nrem);
+}
+}  // namespace
+
+extern "C" int bfg_shell_regrid_p2p(int nside, const double *d_map_in, const double *d_offsets, int64_t pix_lo,
+                                    int64_t pix_hi, int world, int self, const int64_t *h_bounds,
+                                    double *const *h_slices, int64_t *d_remote_count, void *stream) {
+    BFG_REQUIRE(d_map_in && d_offsets && h_bounds && h_slices, "null argument");
+    BFG_REQUIRE(world >= 1 && world <= 8 && self >= 0 && self < world, "world must be 1..8");
+    if (int rc = check_nside(nside)) return rc;
+    Hpx h(nside);
+    BFG_REQUIRE(pix_lo >= 0 && pix_hi <= h.npix && pix_lo <= pix_hi, "bad pixel range");
+    BFG_REQUIRE(h_bounds[0] == 0 && h_bounds[world] == h.npix, "bounds must cover the map");
+    OwnerTable own;
+    own.world = world; own.self = self;
+    for (int r = 0; r <= world; ++r) own.bounds[r] = h_bounds[r];
+    for (int r = world + 1; r < 9; ++r) own.bounds[r] = h.npix;
+    for (int r = 0; r < 8; ++r) own.slice[r] = (r < world) ? h_slices[r] : nullptr;
+    if (d_remote_count) BFG_CUDA_OK(cudaMemsetAsync(d_remote_count, 0, sizeof(i64), (cudaStream_t)stream));
+    if (pix_lo == pix_hi) return BFG_OK;
+    k_shell_regrid_p2p<<<grid_for(pix_hi - pix_lo, 256), 256, 0, (cudaStream_t)stream>>>(
+        h, d_map_in, d_offsets, own, pix_lo, pix_hi, (unsigned long long *)d_remote_count);
+    BFG_CUDA_OK(cudaGetLastError());
+    return BFG_OK;
+}

@@ -136,3 +136,62 @@ def gather_owned_ranges(owned, total):
     parts = [torch.empty(pad, dtype=owned.dtype, device=owned.device) for _ in range(world)]
     dist.all_gather(parts, buf)
     return torch.cat([p[:n] for p, n in zip(parts, sizes)])
+
+
+class PeerSlices(object):
+    """
+    Each rank's slice of a sharded output map, allocated IPC-exportable and mapped into every other process of the box, so
+    a kernel can deposit straight into the owner's HBM over NVLink (bfg_shell_regrid_p2p).  One process per GPU.
+    """
+
+    def __init__(self, bounds, rank, world, device):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        from . import _lib
+        L = _lib.lib()
+        self.bounds, self.rank, self.world, self.device = list(bounds), rank, world, device
+        self.n_own = bounds[rank + 1] - bounds[rank]
+        own = C.c_void_p()
+        _lib.check(L.bfg_shared_alloc(C.byref(own), 8 * max(self.n_own, 1), device))
+        self._own = own
+        handle = (C.c_ubyte * 64)()
+        _lib.check(L.bfg_ipc_export(own, handle))
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=torch.device('cuda', device))
+        allh = [torch.empty(64, dtype=torch.uint8, device=mine.device) for _ in range(world)]
+        dist.all_gather(allh, mine)
+        self._peers = []
+        ptrs = []
+        for r in range(world):
+            if r == rank:
+                ptrs.append(own.value)
+                continue
+            raw = bytes(allh[r].cpu().tolist())
+            buf = (C.c_ubyte * 64).from_buffer_copy(raw)
+            p = C.c_void_p()
+            _lib.check(L.bfg_ipc_import(buf, C.byref(p)))
+            self._peers.append(p)
+            ptrs.append(p.value)
+        self.h_bounds = (C.c_int64 * (world + 1))(*self.bounds)
+        self.h_slices = (C.c_void_p * world)(*ptrs)
+
+    def own_tensor(self):
+        """The owned slice as a torch tensor (no copy) -- for zeroing, summing, gathering."""
+        import torch
+
+        class _Arr(object):
+            pass
+        a = _Arr()
+        a.__cuda_array_interface__ = dict(shape=(self.n_own,), typestr='<f8', data=(self._own.value, False), version=3,
+                                          strides=None)
+        return torch.as_tensor(a, device=torch.device('cuda', self.device))
+
+    def close(self):
+        from . import _lib
+        L = _lib.lib()
+        for p in self._peers:
+            L.bfg_ipc_close(p)
+        self._peers = []
+        if self._own is not None:
+            L.bfg_shared_free(self._own)
+            self._own = None

@@ -192,6 +192,7 @@ class DefaultRunner(object):
         d = dict(self.__dict__)
         d['_tables'] = None
         d.pop('_scratch_inflight', None)
+        d.pop('_peers', None)
         return d
 
     def __setstate__(self, d):
@@ -338,6 +339,30 @@ class DefaultRunner(object):
 class BaryonifyShell(DefaultRunner):
     """BaryonForge/Runners/HealpixRunner.py:180-373."""
 
+    def _peer_slices(self, npix, dev):
+        """Peer-mapped owned slices for the fused regrid + exchange (needs an initialised NCCL group whose ranks use the
+        ranges of parallel.pixel_ranges); None -> fall back to full-size partial maps + all-reduce."""
+        import os
+        import torch.distributed as dist
+        if os.environ.get("BFG_EXCHANGE", "p2p") != "p2p":
+            return None
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() < 2 or dist.get_world_size() > 8:
+            return None
+        if dist.get_backend() != "nccl":
+            return None
+        from .parallel import pixel_ranges, PeerSlices
+        world, rank = dist.get_world_size(), dist.get_rank()
+        ranges = pixel_ranges(self.LightconeShell.NSIDE, world)
+        if tuple(ranges[rank]) != tuple(int(v) for v in self.pix_range):
+            return None
+        key = (npix, world, rank, dev.index)
+        if getattr(self, '_peers', None) is None or self._peers[0] != key:
+            if getattr(self, '_peers', None) is not None:
+                self._peers[1].close()
+            bounds = [r[0] for r in ranges] + [npix]
+            self._peers = (key, PeerSlices(bounds, rank, world, dev.index))
+        return self._peers[1]
+
     def offsets_on_device(self):
         """Run the halo loop only; returns (offsets tensor [3, n_local] on the device, n_updates)."""
         torch = _torch()
@@ -380,15 +405,34 @@ class BaryonifyShell(DefaultRunner):
             d_off, d_n = self.offsets_on_device()
             if prof:
                 torch.cuda.synchronize(); t_loop = time.perf_counter()
-            d_new = torch.zeros(npix, dtype=torch.float64, device=dev)
             st = _lib.current_stream()
-            _lib.check(L.bfg_shell_regrid(NSIDE, _lib.ptr(d_map), _lib.ptr(d_off), _lib.ptr(d_new), lo, hi, st))
-            del d_off
-            if self.pix_range is not None:
-                from .parallel import reduce_partial_map
-                d_new, d_map_sum = reduce_partial_map(d_new, d_map)
+            d_map_sum = None
+            peers = self._peer_slices(npix, dev) if self.pix_range is not None else None
+            if peers is not None:
+                # fused re-binning + exchange: deposits go straight to the owning rank's slice over NVLink peer memory
+                import torch.distributed as dist
+                from .parallel import gather_owned_ranges
+                own = peers.own_tensor()
+                own.zero_()
+                token = torch.zeros(1, device=dev)
+                dist.all_reduce(token)               # stream-ordered barrier: every slice is zero before any deposit
+                d_rem = torch.zeros(1, dtype=torch.int64, device=dev)
+                _lib.check(L.bfg_shell_regrid_p2p(NSIDE, _lib.ptr(d_map), _lib.ptr(d_off), lo, hi, peers.world, peers.rank,
+                                                  peers.h_bounds, peers.h_slices, _lib.ptr(d_rem), st))
+                del d_off
+                dist.all_reduce(token)               # ... and every rank's deposits have landed before the gather
+                d_new = gather_owned_ranges(own, npix)
+                d_map_sum = d_map.sum().reshape(1)
+                dist.all_reduce(d_map_sum)
+                d_map_sum = d_map_sum[0]
+                self.last_stats_remote = int(d_rem.cpu()[0])
             else:
-                d_map_sum = None
+                d_new = torch.zeros(npix, dtype=torch.float64, device=dev)
+                _lib.check(L.bfg_shell_regrid(NSIDE, _lib.ptr(d_map), _lib.ptr(d_off), _lib.ptr(d_new), lo, hi, st))
+                del d_off
+                if self.pix_range is not None:
+                    from .parallel import reduce_partial_map
+                    d_new, d_map_sum = reduce_partial_map(d_new, d_map)
             d_sums = torch.zeros(2, dtype=torch.float64, device=dev)
             _lib.check(L.bfg_sum_f64(_lib.ptr(d_new), npix, _lib.ptr(d_sums), st))
             if d_map_sum is None:

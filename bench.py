@@ -241,6 +241,9 @@ def run_b200(args):
     d_map = pinned_map[lo:hi].to(dev)
     d_off = torch.empty((3, hi - lo), dtype=torch.float64, device=dev)
     d_new = torch.empty(npix, dtype=torch.float64, device=dev)
+    peers = runner._peer_slices(npix, dev) if world > 1 else None
+    own = peers.own_tensor() if peers is not None else None
+    token = torch.zeros(1, device=dev)
     d_n = torch.zeros(1, dtype=torch.int64, device=dev)
     d_sums = torch.zeros(2, dtype=torch.float64, device=dev)
     st = torch.cuda.current_stream().cuda_stream
@@ -249,7 +252,10 @@ def run_b200(args):
 
     def step(timed_kernel=None):
         d_off.zero_()
-        d_new.zero_()
+        if peers is None:
+            d_new.zero_()
+        else:
+            own.zero_()
         if args.no_sort:
             d_use = d_rec
         else:   # locality ordering of the halo records is part of the step
@@ -263,10 +269,19 @@ def run_b200(args):
                                        lo, hi, d_n.data_ptr(), st))
         if timed_kernel is not None:
             timed_kernel[1].record()
-        _lib.check(L.bfg_shell_regrid(nside, d_map.data_ptr(), d_off.data_ptr(), d_new.data_ptr(), lo, hi, st))
-        if world > 1:
-            dist.all_reduce(d_new, op=dist.ReduceOp.SUM)
-        _lib.check(L.bfg_sum_f64(d_new.data_ptr(), npix, d_sums.data_ptr(), st))
+        if peers is not None:
+            # fused re-binning + exchange over NVLink peer memory, then the owned slices are gathered into the full map
+            dist.all_reduce(token)
+            _lib.check(L.bfg_shell_regrid_p2p(nside, d_map.data_ptr(), d_off.data_ptr(), lo, hi, world, rank, peers.h_bounds,
+                                              peers.h_slices, None, st))
+            dist.all_reduce(token)
+            full = parallel.gather_owned_ranges(own, npix)
+            _lib.check(L.bfg_sum_f64(full.data_ptr(), npix, d_sums.data_ptr(), st))
+        else:
+            _lib.check(L.bfg_shell_regrid(nside, d_map.data_ptr(), d_off.data_ptr(), d_new.data_ptr(), lo, hi, st))
+            if world > 1:
+                dist.all_reduce(d_new, op=dist.ReduceOp.SUM)
+            _lib.check(L.bfg_sum_f64(d_new.data_ptr(), npix, d_sums.data_ptr(), st))
         _lib.check(L.bfg_sum_f64(d_map.data_ptr(), hi - lo, d_sums.data_ptr() + 8, st))
         launches[0] += 4
 
@@ -346,7 +361,10 @@ def run_b200(args):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args), "n_updates_per_step": int(n_up),
                        "l2_policy": "working set (4.8 GB offsets + 3.2 GB maps per step) >> 126 MB L2; no flush needed",
-                       "sharding": "none" if world == 1 else f"RING pixel ranges x{world}, overlap halos replicated, NCCL all-reduce of partial maps"},
+                       "sharding": "none" if world == 1 else (
+                           f"RING pixel ranges x{world}, overlap halos replicated, " + (
+                               "re-binning fused with the exchange (fp64 REDs into the owner's slice over NVLink peer memory) + NCCL all-gather of slices"
+                               if peers is not None else "NCCL all-reduce of partial maps"))},
             "clocks": clocks, "gpu_launches": n_launch,
             "roofline": {"bound": "hbm", "kernel": "k_shell_halos<baryonify> (fused disc/separation/table/accumulate)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -126,6 +126,23 @@ int bfg_shell_paint(const bfg_table *t, int nside, int64_t n_halo, const double 
 int bfg_shell_regrid(int nside, const double *d_map_in, const double *d_offsets, double *d_map_out, int64_t pix_lo,
                      int64_t pix_hi, void *stream);
 
+/* Multi-GPU form of bfg_shell_regrid (one process per GPU, ring-range sharding): the re-binning fused with its exchange
+ * step.  h_slices[r] points at rank r's owned slice [h_bounds[r], h_bounds[r+1]) of the NEW map -- local memory for
+ * r == self, CUDA-IPC peer mappings otherwise (bfg_shared_alloc / bfg_ipc_export / bfg_ipc_import) -- and every deposit
+ * goes straight to its owner (fp64 RED over NVLink for the few that cross a range border).  Replaces "each worker holds a
+ * full map, the parent sums them" (utils/Parallelize.py:318).  Slices must be zeroed and all ranks synchronised before,
+ * and synchronised again after, the call.  *d_remote_count (optional) receives the number of cross-GPU deposits. */
+int bfg_shell_regrid_p2p(int nside, const double *d_map_in, const double *d_offsets, int64_t pix_lo, int64_t pix_hi,
+                         int world, int self, const int64_t *h_bounds, double *const *h_slices,
+                         int64_t *d_remote_count, void *stream);
+
+/* ---- peer memory between the processes of one box (CUDA IPC) --------------------------------------------------------- */
+int bfg_shared_alloc(void **d_ptr, int64_t bytes, int device);            /* cudaMalloc'd, exportable */
+int bfg_shared_free(void *d_ptr);
+int bfg_ipc_export(const void *d_ptr, unsigned char *handle64);           /* 64-byte handle to ship to the peers */
+int bfg_ipc_import(const unsigned char *handle64, void **d_peer_ptr);     /* maps a peer's allocation, enables P2P */
+int bfg_ipc_close(void *d_peer_ptr);
+
 /* ---- periodic grids (2-D / 3-D) ------------------------------------------------------------------- */
 /* Halo loop of BaryonifyGrid.process (Map2DRunner.py:482-586).  d_offsets is [ndim][N^ndim] in units of cells,
  * restricted to axis-0 planes [plane_lo, plane_hi) (slab); NaNs propagate as in the reference. */
