@@ -5,8 +5,11 @@ Multi-GPU sharding of one map across the GPUs of a box -- the replacement for Ba
 One process per GPU (torch.distributed, NCCL over NVLink/NVSwitch):
   * shells: the RING pixel index space is cut into `world` contiguous ranges of equal pixel count; rank r owns
     pix_offsets[lo_r:hi_r].  Every halo whose disc touches a rank's rings is given to that rank (halo records are
-    128 B, so overlap halos are simply replicated) -- no communication in the halo loop.  The re-binning scatters
-    into a full-size partial map per rank; ONE all-reduce(sum, fp64) combines them (1.6 GB at NSIDE=4096).
+    128 B, so overlap halos are simply replicated) -- no communication in the halo loop.  The re-binning is fused
+    with its exchange step: each rank owns a slice of the new map that its peers have mapped through CUDA IPC
+    (PeerSlices), and bfg_shell_regrid_p2p deposits every displaced pixel straight into the owner's slice (fp64 REDs
+    over NVLink for the few that cross a range border); an all_gather then assembles the full map.  Fallback
+    (BFG_EXCHANGE=allreduce, gloo, >8 ranks): full-size partial maps + ONE all-reduce(sum, fp64).
   * grids: the same with slabs of axis-0 planes.
   * painting: each rank paints its own range; ranges are concatenated with all_gather.
 The reference can only split painting runs across halos and sums whole maps in the parent (Parallelize.py:318);
@@ -126,6 +129,11 @@ def gather_owned_ranges(owned, total):
         assert owned.numel() == total
         return owned
     world = dist.get_world_size()
+    if total % world == 0 and owned.numel() * world == total:
+        # pixel_ranges / plane_ranges give equal slices whenever `world` divides the map: one collective, no staging
+        full = torch.empty(total, dtype=owned.dtype, device=owned.device)
+        dist.all_gather_into_tensor(full, owned.contiguous())
+        return full
     sizes = [torch.zeros(1, dtype=torch.int64, device=owned.device) for _ in range(world)]
     dist.all_gather(sizes, torch.tensor([owned.numel()], dtype=torch.int64, device=owned.device))
     sizes = [int(s.item()) for s in sizes]
