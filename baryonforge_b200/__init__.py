@@ -9,6 +9,7 @@ Tables are still built on the host by the reference's pyccl code; see tables.py.
 from .io import *            # noqa: F401,F403
 from .runners import *       # noqa: F401,F403
 from .tables import DeviceTable, DisplacementModel, ProfileModel   # noqa: F401
-from . import _lib, cosmology, io, runners, synth, tables          # noqa: F401
+from .parallel import SimpleParallel, SplitJoinParallel             # noqa: F401
+from . import _lib, cosmology, io, parallel, runners, synth, tables   # noqa: F401
 
 __version__ = "0.1.0"

@@ -18,7 +18,8 @@ results here are independent of the number of ranks up to fp64 summation order (
 import numpy as np
 
 __all__ = ['pixel_ranges', 'plane_ranges', 'ring_of_pixel', 'halos_touching_pixel_range', 'halos_touching_planes',
-           'reduce_partial_map', 'gather_owned_ranges', 'init_from_env']
+           'reduce_partial_map', 'gather_owned_ranges', 'init_from_env', 'PeerSlices', 'SimpleParallel',
+           'SplitJoinParallel', 'snapshot_slab', 'deposit_ngp_all']
 
 
 def pixel_ranges(nside, world):
@@ -203,3 +204,118 @@ class PeerSlices(object):
         if self._own is not None:
             L.bfg_shared_free(self._own)
             self._own = None
+
+
+# =====================================================================================================================
+# Drop-in mirrors of BaryonForge/utils/Parallelize.py, so user scripts that wrap runners in them keep running
+# =====================================================================================================================
+class SimpleParallel(object):
+    """
+    BaryonForge/utils/Parallelize.py:8-113: run a list of independent runners, return their outputs in input order.
+    The reference forks one joblib/loky process per runner; here the runners execute one after another on the GPU(s)
+    of this process (round-robin over `devices` if given) -- each `process()` is already parallel inside.
+    Under torch.distributed (one process per GPU) the list is split across ranks and outputs are exchanged, so every
+    rank returns the full ordered list.
+    """
+
+    def __init__(self, Runner_list, njobs=-1, devices=None):
+        self.Runner_list = Runner_list
+        self.njobs = len(Runner_list) if njobs == -1 else min(njobs, len(Runner_list))
+        self.devices = devices
+
+    def single_run(self, i, Runner):
+        return i, Runner.process()
+
+    def process(self):
+        dist = _dist()
+        rank, world = (dist.get_rank(), dist.get_world_size()) if dist is not None else (0, 1)
+        mine = {}
+        for i, Runner in enumerate(self.Runner_list):
+            if i % world != rank:
+                continue
+            if self.devices:
+                Runner.device = self.devices[i % len(self.devices)]
+            mine[i] = Runner.process()
+        if dist is None:
+            return [mine[i] for i in range(len(self.Runner_list))]
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        merged = {}
+        for g in gathered:
+            merged.update(g)
+        return [merged[i] for i in range(len(self.Runner_list))]
+
+
+class SplitJoinParallel(object):
+    """
+    BaryonForge/utils/Parallelize.py:116-320: split a PAINTING runner's halo catalogue into `njobs` chunks, paint each on
+    an empty shell and sum the maps.  Kept for API compatibility: on the GPU the split buys nothing (the halo loop is
+    already data-parallel), so the chunks run back to back and are summed exactly as the reference sums them --
+    including its quirks: halos are reshuffled with default_rng(seed), `include_pixel_size` is not forwarded (:271), and
+    Baryonify* runners are refused (:206-209).
+    """
+
+    def __init__(self, Runner, njobs=-1, seed=42):
+        from .runners import BaryonifyShell, BaryonifyGrid, BaryonifySnapshot
+        text = f"Runner of type {type(Runner)} is not supported for SplitJoinParallel."
+        assert not isinstance(Runner, (BaryonifyGrid, BaryonifyShell, BaryonifySnapshot)), text
+        self.Runner = Runner
+        self.seed = seed
+        self.njobs = 1 if njobs == -1 else njobs
+        self.Runner_list = self.split_run(self.Runner)
+
+    def split_run(self, Runner):
+        HaloCat, Shell = Runner.HaloLightConeCatalog, Runner.LightconeShell
+        Ntotal = len(HaloCat.cat)
+        Npersplit = int(np.ceil(Ntotal / self.njobs))
+        HaloCat = HaloCat[np.random.default_rng(self.seed).choice(Ntotal, size=Ntotal, replace=False)]
+        empty_shell = type(Shell)(map=np.zeros_like(Shell.map), cosmo=Runner.cosmo)
+        out = []
+        for i in range(self.njobs):
+            sub = HaloCat[i * Npersplit:(i + 1) * Npersplit]
+            out.append(type(Runner)(sub, empty_shell, Runner.epsilon_max, Runner.model, Runner.use_ellipticity,
+                                    Runner.mass_def, verbose=False))
+        return out
+
+    def single_run(self, Runner):
+        return Runner.process()
+
+    def process(self):
+        outputs = [np.array(r.process()) for r in self.Runner_list]
+        return np.sum(outputs, axis=0)
+
+
+# =====================================================================================================================
+# particle snapshots across ranks (BASELINE config 4): slabs in x by particle position
+# =====================================================================================================================
+def snapshot_slab(ps, rank, world):
+    """
+    The particles of `ps` (a ParticleSnapshot) whose x lies in this rank's slab [rank, rank+1) * L / world, as a new
+    ParticleSnapshot of the SAME periodic box, plus their indices in the original arrays.  Every halo within reach of a
+    slab is needed by that rank; BaryonifySnapshot simply gets the whole (small) halo catalogue -- halos far from the slab
+    find empty cells.  Particles are displaced by at most the table's range, so no particle exchange happens before the
+    displacement is applied; the NGP deposit of the displaced particles is summed over ranks (deposit_ngp_all).
+    """
+    from .io import ParticleSnapshot
+    L = ps.L
+    x = ps.cat['x']
+    lo, hi = L * rank / world, L * (rank + 1) / world
+    sel = np.flatnonzero((x >= lo) & (x < hi) if rank < world - 1 else (x >= lo))
+    sub = ParticleSnapshot(x=ps.cat['x'][sel], y=ps.cat['y'][sel], z=None if ps.is2D else ps.cat['z'][sel],
+                           M=ps.cat['M'][sel], L=L, redshift=ps.redshift, cosmo=ps.cosmo)
+    return sub, sel
+
+
+def deposit_ngp_all(coords, mass, L, N_grid, device=None):
+    """NGP deposit of this rank's particles followed by an all-reduce(sum) of the partial grids over the ranks."""
+    import torch
+    from .runners import deposit_ngp
+    grid = deposit_ngp(coords, mass, L, N_grid, device=device)
+    dist = _dist()
+    if dist is None:
+        return grid
+    dev = torch.device('cuda', torch.cuda.current_device() if device is None else int(device)) \
+        if dist.get_backend() == "nccl" else torch.device('cpu')
+    t = torch.from_numpy(np.ascontiguousarray(grid)).to(dev)
+    dist.all_reduce(t)
+    return t.cpu().numpy()

@@ -40,6 +40,7 @@ def _inputs():
 
 def _worker(rank, world, port, q):
     sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                       LOCAL_RANK=str(rank))
     import torch
@@ -52,8 +53,22 @@ def _worker(rank, world, port, q):
     out2 = b.PaintProfilesShell(cat, shell, 20, pmodel, verbose=False, device=rank, pix_range=pr).process()
     out3 = b.BaryonifyGrid(gcat, gm, 6, gmodel, verbose=False, device=rank,
                            plane_range=parallel.plane_ranges(N, world)[rank]).process()
+    # snapshot: x-slabs of particles, every rank displaces its own, NGP grids are summed
+    from helpers import load
+    g = load("snap_3d")
+    ps = b.ParticleSnapshot(x=g["px"], y=g["py"], z=g["pz"], M=g["pM"], L=float(g["L"]), redshift=g["redshift"],
+                            cosmo=b.synth.COSMO)
+    hc = b.HaloNDCatalog(x=g["x"], y=g["y"], z=g["z"], M=g["M"], redshift=g["redshift"], cosmo=b.synth.COSMO)
+    mc = dict(Omega_m=0.32, Omega_b=0.05, h=0.68, sigma8=0.82, n_s=0.97, w0=-1.0)
+    smodel = b.DisplacementModel((g["ax0"], g["ax1"], g["ax2"]), g["values"], g["eps_mod"], mc)
+    sub, sel = parallel.snapshot_slab(ps, rank, world)
+    moved = b.BaryonifySnapshot(hc, sub, g["eps_run"], smodel, verbose=False, device=rank).process()
+    ngp = parallel.deposit_ngp_all([moved["x"], moved["y"], moved["z"]], moved["M"], float(g["L"]), 16, device=rank)
+    err = float(np.max(np.abs(moved["x"] - g["out_x"][sel]))) if sel.size else 0.0
     if rank == 0:
-        q.put((out1, out2, out3))
+        q.put((out1, out2, out3, ngp, err))
+    else:
+        q.put(("err", err))
     torch.distributed.barrier()
     torch.distributed.destroy_process_group()
 
@@ -75,10 +90,16 @@ def test_sharded_runs_match_single_gpu():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    got1, got2, got3 = q.get(timeout=300)
+    items = [q.get(timeout=300) for _ in procs]
+    main = [it for it in items if not isinstance(it[0], str)][0]
+    got1, got2, got3, ngp, err0 = main
+    errs = [err0] + [it[1] for it in items if isinstance(it[0], str)]
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
     assert_close(got1, want1, "sharded BaryonifyShell", rtol=1e-9, atol_scale=1e-12)
     assert_close(got2, want2, "sharded PaintProfilesShell", rtol=1e-9, atol_scale=1e-12)
     assert_close(got3, want3, "sharded BaryonifyGrid", rtol=1e-9, atol_scale=1e-12)
+    from helpers import load
+    assert max(errs) < 1e-9                                     # each slab reproduces the reference's displaced positions
+    assert np.array_equal(ngp, load("snap_3d")["ngp"])          # summed NGP grid == the reference's make_map

@@ -316,3 +316,21 @@ def test_batched_halo_loop_equals_single_batch():
     assert int(na.cpu()[0]) == int(nc.cpu()[0])
     assert_close(c.cpu().numpy(), a.cpu().numpy(), "batched offsets", rtol=1e-9, atol_scale=1e-12)
     assert_close(four.process(), one.process(), "batched map", rtol=1e-9, atol_scale=1e-12)
+
+
+def test_parallelize_mirrors():
+    """SimpleParallel / SplitJoinParallel (utils/Parallelize.py) keep their contracts on the GPU path."""
+    import baryonforge_b200 as b
+    from baryonforge_b200 import synth
+    cat, shell, model, axes, vals = _fresh_shell_case(64, 800, 31, 20, 20)
+    pmodel = b.ProfileModel(axes, synth.profile_values(axes) * 3, synth.profile_values(axes))
+    paint = b.PaintProfilesShell(cat, shell, 20, pmodel, verbose=False)
+    bary = b.BaryonifyShell(cat, shell, 20, model, verbose=False)
+    outs = b.SimpleParallel([paint, bary, paint]).process()
+    assert len(outs) == 3
+    assert_close(outs[0], paint.process(), "SimpleParallel[0]", rtol=1e-9, atol_scale=1e-12)
+    assert_close(outs[1], bary.process(), "SimpleParallel[1]", rtol=1e-9, atol_scale=1e-12)
+    joined = b.SplitJoinParallel(paint, njobs=3).process()
+    assert_close(joined, outs[0], "SplitJoinParallel", rtol=1e-9, atol_scale=1e-12)
+    with pytest.raises(AssertionError):
+        b.SplitJoinParallel(bary, njobs=2)      # Parallelize.py:206-209
