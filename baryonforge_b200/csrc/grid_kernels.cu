@@ -50,7 +50,9 @@ __device__ __forceinline__ int wrap_idx(int c, int N) {   // pick_indices, Map2D
     return c;
 }
 
-template <bool PAINT, bool UNIFORM, int NDIM>
+// ELL (2-D only): the last 4 columns of `extras` hold the halo's shear matrix Rmat (Map2DRunner.py:281-350, build_Rmat);
+// the radius handed to the table is |(gx, gy) @ Rmat| while the direction stays (gx, gy)/r   (:531-536, :769-774).
+template <bool PAINT, bool UNIFORM, int NDIM, bool ELL>
 __global__ void __launch_bounds__(GRID_THREADS)
 k_grid_halos(TableView T, int N, double res, double scale, i64 n_halo, const double *__restrict__ halos,
              const double *__restrict__ extras, int n_extra, double *__restrict__ out, int plane_lo, int plane_hi,
@@ -72,6 +74,11 @@ k_grid_halos(TableView T, int N, double res, double scale, i64 n_halo, const dou
         __syncthreads();
         const int ns = b.nsize, cw = ns / 2;
         const double cut2 = PAINT ? b.paintcut * b.paintcut : b.rcut * b.rcut;
+        double R00 = 1.0, R01 = 0.0, R10 = 0.0, R11 = 1.0;
+        if (ELL) {
+            const double *e = extras + h * n_extra + (n_extra - 4);
+            R00 = __ldg(e); R01 = __ldg(e + 1); R10 = __ldg(e + 2); R11 = __ldg(e + 3);
+        }
         // Rows of the cutout = every index but the last array axis; a warp owns a row, lanes walk the last axis, so the
         // REDs of a warp are contiguous in memory (the last axis is the fastest one of the C-order grid).
         const int nrows = (NDIM == 3) ? ns * ns : ns;
@@ -93,18 +100,23 @@ k_grid_halos(TableView T, int N, double res, double scale, i64 n_halo, const dou
                 const double gx = (NDIM == 3) ? gx_row : gl;
                 const double r2 = (NDIM == 3) ? row2 + gl * gl : gl * gl + gy * gy;
                 const i64 cell = base + wrap_idx(clast0 + k, N);
-                double xq = fast_log2(r2, l2tab) * 0.34657359027997264;           // ln r = 0.5 ln2 log2(r^2)
+                double rt2 = r2;                                                   // radius^2 the table / cuts see
+                if (ELL) {
+                    const double ex = gx * R00 + gy * R10, ey = gx * R01 + gy * R11;   // (x, y) @ Rmat
+                    rt2 = ex * ex + ey * ey;
+                }
+                double xq = fast_log2(rt2, l2tab) * 0.34657359027997264;          // ln r = 0.5 ln2 log2(r^2)
                 if (T.flags & BFG_TABLE_RDELTA) xq -= b.lnRcom;
                 double val = row_lookup<UNIFORM>(T, row, xq);
                 if (!valid) val = CUDART_NAN;
                 ++done;
                 if (PAINT) {
                     val = exp(val);                                  // Tabulate.py:319
-                    if (!isfinite(val) || !(r2 < cut2)) continue;    // Map2DRunner.py:814-818
+                    if (!isfinite(val) || !(rt2 < cut2)) continue;   // Map2DRunner.py:814-818
                     val *= scale;                                    // :825 folded in
                     if (val != 0.0) red_add(out + cell, val);
                 } else {
-                    val = (r2 < cut2) ? val : 0.0;                   // BaryonCorrection.py:410-411
+                    val = (rt2 < cut2) ? val : 0.0;                  // BaryonCorrection.py:410-411
                     const double sc = (val * inv_res) * rsqrt(r2);   // offset / res / r   (Map2DRunner.py:540/:583)
                     if (sc == 0.0) continue;                         // adds exact zeros; NaN (r = 0, outside table) goes on
                     red_add(out + cell, sc * gx);                    // NaNs propagate (cleaned after the loop, :597/:607)
@@ -182,13 +194,15 @@ k_grid_regrid(int N, const double *__restrict__ map_in, const double *__restrict
 
 template <bool PAINT>
 int launch_grid(const bfg_table *t, int ndim, i64 N, double res, double scale, i64 n_halo, const double *d_halos,
-                const double *d_extras, int n_extra, double *d_out, i64 plane_lo, i64 plane_hi, i64 *d_nupdates,
-                cudaStream_t st) {
+                const double *d_extras, int n_extra, int use_ell, double *d_out, i64 plane_lo, i64 plane_hi,
+                i64 *d_nupdates, cudaStream_t st) {
     BFG_REQUIRE(t && (d_halos || n_halo == 0) && d_out, "null argument");
     BFG_REQUIRE(ndim == 2 || ndim == 3, "ndim must be 2 or 3");
     BFG_REQUIRE(N >= 4 && N <= 32768, "N out of range (need 4 <= N <= 32768)");
     BFG_REQUIRE(plane_lo >= 0 && plane_hi <= N && plane_lo <= plane_hi, "bad plane range");
-    BFG_REQUIRE(n_extra == t->view.ndim - 3, "n_extra must equal the table's extra axes");
+    BFG_REQUIRE(!use_ell || ndim == 2, "ellipticity exists for 2-D maps only (Map2DRunner.py:571,801)");
+    BFG_REQUIRE(n_extra == t->view.ndim - 3 + (use_ell ? 4 : 0),
+                "n_extra must equal the table's extra axes (+4 shear-matrix columns when use_ell)");
     BFG_REQUIRE(n_extra == 0 || d_extras, "extras missing");
     BFG_REQUIRE(PAINT == ((t->view.flags & BFG_TABLE_LOG_VALUES) != 0),
                 "paint needs a log-profile table, baryonify a displacement table");
@@ -207,24 +221,25 @@ int launch_grid(const bfg_table *t, int ndim, i64 N, double res, double scale, i
         return BFG_OK;
     };
     const bool u = t->view.uniform_r != 0;
-    if (ndim == 3) return u ? go(k_grid_halos<PAINT, true, 3>) : go(k_grid_halos<PAINT, false, 3>);
-    return u ? go(k_grid_halos<PAINT, true, 2>) : go(k_grid_halos<PAINT, false, 2>);
+    if (ndim == 3) return u ? go(k_grid_halos<PAINT, true, 3, false>) : go(k_grid_halos<PAINT, false, 3, false>);
+    if (use_ell) return u ? go(k_grid_halos<PAINT, true, 2, true>) : go(k_grid_halos<PAINT, false, 2, true>);
+    return u ? go(k_grid_halos<PAINT, true, 2, false>) : go(k_grid_halos<PAINT, false, 2, false>);
 }
 
 }  // namespace
 
 extern "C" int bfg_grid_offsets(const bfg_table *t, int ndim, int64_t N, double res, int64_t n_halo,
-                                const double *d_halos, const double *d_extras, int n_extra, double *d_offsets,
-                                int64_t plane_lo, int64_t plane_hi, int64_t *d_nupdates, void *stream) {
-    return launch_grid<false>(t, ndim, N, res, 1.0, n_halo, d_halos, d_extras, n_extra, d_offsets, plane_lo, plane_hi,
-                              (i64 *)d_nupdates, (cudaStream_t)stream);
+                                const double *d_halos, const double *d_extras, int n_extra, int use_ell,
+                                double *d_offsets, int64_t plane_lo, int64_t plane_hi, int64_t *d_nupdates, void *stream) {
+    return launch_grid<false>(t, ndim, N, res, 1.0, n_halo, d_halos, d_extras, n_extra, use_ell, d_offsets, plane_lo,
+                              plane_hi, (i64 *)d_nupdates, (cudaStream_t)stream);
 }
 
 extern "C" int bfg_grid_paint(const bfg_table *t, int ndim, int64_t N, double res, double scale, int64_t n_halo,
-                              const double *d_halos, const double *d_extras, int n_extra, double *d_map,
+                              const double *d_halos, const double *d_extras, int n_extra, int use_ell, double *d_map,
                               int64_t plane_lo, int64_t plane_hi, int64_t *d_nupdates, void *stream) {
-    return launch_grid<true>(t, ndim, N, res, scale, n_halo, d_halos, d_extras, n_extra, d_map, plane_lo, plane_hi,
-                             (i64 *)d_nupdates, (cudaStream_t)stream);
+    return launch_grid<true>(t, ndim, N, res, scale, n_halo, d_halos, d_extras, n_extra, use_ell, d_map, plane_lo,
+                             plane_hi, (i64 *)d_nupdates, (cudaStream_t)stream);
 }
 
 extern "C" int bfg_grid_regrid(int ndim, int64_t N, const double *d_map_in, const double *d_offsets, double *d_map_out,

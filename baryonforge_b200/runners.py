@@ -562,10 +562,10 @@ class DefaultRunnerGrid(object):
 
     def halo_records(self, paint):
         """Per-halo scalars of Map2DRunner.py:484-520 / :727-760 (+ BaryonCorrection.py:371,398-399,410), vectorised."""
-        if self.use_ellipticity:
-            if not self.GriddedMap.is2D:
-                raise NotImplementedError("Currently not able to ellipticities with 3D maps.")   # Map2DRunner.py:571
-            raise NotImplementedError("use_ellipticity is not implemented on the GPU path yet (SURVEY.md §8f item 2)")
+        if self.use_ellipticity and not self.GriddedMap.is2D:
+            if paint:
+                raise ValueError("use_ellipticity is not implemented for 3D maps")               # Map2DRunner.py:801
+            raise NotImplementedError("Currently not able to ellipticities with 3D maps.")       # Map2DRunner.py:571
         cat = self.HaloNDCatalog.cat
         n = cat.size
         bins = np.asarray(self.GriddedMap.bins, dtype=np.float64)
@@ -610,7 +610,34 @@ class DefaultRunnerGrid(object):
             assert np.all((dx <= res) & (dy <= res)), "Halo offsets are larger than res"   # :522
         keys = list(vars(self.model).get('p_keys', []))
         _check_keys(self.model, keys)
-        return rec, _extras(cat, keys)
+        extras = _extras(cat, keys)
+        if self.use_ellipticity:
+            Rmat = self.shear_matrices()
+            extras = Rmat if extras is None else np.ascontiguousarray(np.hstack([extras, Rmat]))
+        return rec, extras
+
+    def shear_matrices(self):
+        """
+        build_Rmat(A_ell, q_ell) of every halo (Map2DRunner.py:281-350,495-498,533), row-major [n, 4], with the reference's
+        float32 arithmetic (HaloNDCatalog columns are float32): A normalised twice in float32, beta = arccos(A_x),
+        eta = -log(q) and eta2g in float32, then g = eta2g*eta*exp(2i beta) in complex128.
+        """
+        cat = self.HaloNDCatalog.cat
+        q = cat['q_ell'].astype('<f4')
+        assert np.all(q > 0), "The axis ratio of a halo is not positive"                       # Map2DRunner.py:532
+        A = cat['A_ell'].astype('<f4')
+        A = A / np.sqrt(np.sum(A ** 2, axis=1))[:, None]                                       # :497
+        A = A / np.sqrt(np.sum(A * A, axis=1))[:, None]                                        # A /= np.linalg.norm(A) :310
+        beta = np.arccos(A[:, 0].astype(np.float64))                                           # arccos(dot(A, [1, 0]))
+        eta = -np.log(q)
+        with np.errstate(divide='ignore', invalid='ignore'):
+            etasq = eta * eta
+            eta2g = np.where(eta > 1e-4, np.tanh(np.float32(0.5) * eta) / eta,
+                             np.float32(0.5) + etasq * (np.float32(-1 / 24) + etasq * np.float32(1 / 240)))
+        g = (eta2g * eta).astype(np.float64) * np.exp(2j * beta)
+        g1, g2 = g.real, g.imag
+        det = np.sqrt(1 - np.abs(g) ** 2)
+        return np.ascontiguousarray(np.stack([(1 + g1) / det, g2 / det, g2 / det, (1 - g1) / det], axis=1))
 
 
 class BaryonifyGrid(DefaultRunnerGrid):
@@ -635,9 +662,10 @@ class BaryonifyGrid(DefaultRunnerGrid):
             nloc = (hi - lo) * N ** (ndim - 1)
             d_off = torch.zeros((ndim, nloc), dtype=torch.float64, device=dev)
             d_n = torch.zeros(1, dtype=torch.int64, device=dev)
+            n_cols = 0 if d_ext is None else d_ext.shape[1]
             _lib.check(L.bfg_grid_offsets(table.handle, ndim, N, float(gm.res), rec.shape[0], _lib.ptr(d_rec),
-                                          _lib.ptr(d_ext), table.n_extra, _lib.ptr(d_off), lo, hi, _lib.ptr(d_n),
-                                          _lib.current_stream()))
+                                          _lib.ptr(d_ext), n_cols, 1 if self.use_ellipticity else 0, _lib.ptr(d_off), lo, hi,
+                                          _lib.ptr(d_n), _lib.current_stream()))
         return d_off, d_n
 
     def process(self):
@@ -700,9 +728,10 @@ class PaintProfilesGrid(DefaultRunnerGrid):
             nloc = (hi - lo) * N ** (ndim - 1)
             d_new = torch.zeros(nloc, dtype=torch.float64, device=dev)
             d_n = torch.zeros(1, dtype=torch.int64, device=dev)
+            n_cols = 0 if d_ext is None else d_ext.shape[1]
             _lib.check(L.bfg_grid_paint(table.handle, ndim, N, float(gm.res), dV, rec.shape[0], _lib.ptr(d_rec),
-                                        _lib.ptr(d_ext), table.n_extra, _lib.ptr(d_new), lo, hi, _lib.ptr(d_n),
-                                        _lib.current_stream()))
+                                        _lib.ptr(d_ext), n_cols, 1 if self.use_ellipticity else 0, _lib.ptr(d_new), lo, hi,
+                                        _lib.ptr(d_n), _lib.current_stream()))
             if self.plane_range is not None:
                 from .parallel import gather_owned_ranges
                 d_new = gather_owned_ranges(d_new, gm.map.size)

@@ -145,15 +145,17 @@ int bfg_ipc_close(void *d_peer_ptr);
 
 /* ---- periodic grids (2-D / 3-D) ------------------------------------------------------------------- */
 /* Halo loop of BaryonifyGrid.process (Map2DRunner.py:482-586).  d_offsets is [ndim][N^ndim] in units of cells,
- * restricted to axis-0 planes [plane_lo, plane_hi) (slab); NaNs propagate as in the reference. */
+ * restricted to axis-0 planes [plane_lo, plane_hi) (slab); NaNs propagate as in the reference.
+ * use_ell (2-D only, Map2DRunner.py:281-350,531-536): d_extras rows carry, after the table's p_keys values, the 4 entries
+ * (row-major) of the halo's shear matrix build_Rmat(A_ell, q_ell); n_extra counts them. */
 int bfg_grid_offsets(const bfg_table *t, int ndim, int64_t N, double res, int64_t n_halo, const double *d_halos,
-                     const double *d_extras, int n_extra, double *d_offsets, int64_t plane_lo, int64_t plane_hi,
-                     int64_t *d_nupdates, void *stream);
+                     const double *d_extras, int n_extra, int use_ell, double *d_offsets, int64_t plane_lo,
+                     int64_t plane_hi, int64_t *d_nupdates, void *stream);
 /* Halo loop of PaintProfilesGrid.process (Map2DRunner.py:725-821); `scale` folds in the final *res^d of :825
  * (pass 1.0 when include_pixel_size is False). */
 int bfg_grid_paint(const bfg_table *t, int ndim, int64_t N, double res, double scale, int64_t n_halo,
-                   const double *d_halos, const double *d_extras, int n_extra, double *d_map, int64_t plane_lo,
-                   int64_t plane_hi, int64_t *d_nupdates, void *stream);
+                   const double *d_halos, const double *d_extras, int n_extra, int use_ell, double *d_map,
+                   int64_t plane_lo, int64_t plane_hi, int64_t *d_nupdates, void *stream);
 /* Re-binning of BaryonifyGrid.process (Map2DRunner.py:589-613 + regrid_pixels_2D/3D :13-162): non-finite offsets -> 0,
  * add cell coordinates (xy-meshgrid convention), periodic overlap deposit into the FULL grid d_map_out (zeroed by caller). */
 int bfg_grid_regrid(int ndim, int64_t N, const double *d_map_in, const double *d_offsets, double *d_map_out,

@@ -181,26 +181,33 @@ def main():
     gd[:, :, :] *= 25.0                                    # cell-scale displacements at res ~ 1.5 Mpc
     gp = synth.profile_values(gaxes)
 
-    def grid_case(name, ndim, N, Lbox, n, seed, eps_run, eps_mod, redshift, paint):
+    def grid_case(name, ndim, N, Lbox, n, seed, eps_run, eps_mod, redshift, paint, ell=False):
         pos, M = synth.box_halos(n, Lbox, seed=seed, ndim=ndim)
         M[0] = 3e11                                        # outside the table: NaN-poisons its cells (§10 #5)
         pos[:, 1] = 0.01 * Lbox / N                        # hugging the box corner: periodic wrap of the cutout
         pos[:, 2] = Lbox * (1 - 1e-3)
         bins = (np.arange(N) + 0.5) * Lbox / N
         gmap = np.random.default_rng(seed + 1).uniform(0, 10, (N,) * ndim)
-        cat = HaloNDCatalog(x=pos[0], y=pos[1], z=pos[2] if ndim == 3 else None, M=M, redshift=redshift, cosmo=cosmo)
+        ekw = {}
+        if ell:
+            erng = np.random.default_rng(seed + 7)
+            ekw = dict(q_ell=erng.uniform(0.4, 1.0, n), A_ell=erng.normal(size=(n, 2)))
+            ekw['q_ell'][1] = 1.0 - 1e-6                       # the small-eta series branch of build_Rmat
+        cat = HaloNDCatalog(x=pos[0], y=pos[1], z=pos[2] if ndim == 3 else None, M=M, redshift=redshift, cosmo=cosmo, **ekw)
         gm = GriddedMap(map=gmap, redshift=redshift, bins=bins, cosmo=cosmo)
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
             if paint:
                 model = ref_profile_model(gaxes, gp * 3.0, gp)
-                out = PaintProfilesGrid(cat, gm, eps_run, model, verbose=False).process()
+                out = PaintProfilesGrid(cat, gm, eps_run, model, use_ellipticity=ell, verbose=False).process()
                 R_phys, R_mod = per_halo_scalars_box(ccl, cosmo, None, cat.cat['M'], redshift)
             else:
                 model = ref_displacement_model(gaxes, gd, eps_mod, '2D' if ndim == 2 else '3D')
-                out = BaryonifyGrid(cat, gm, eps_run, model, verbose=False).process()
+                out = BaryonifyGrid(cat, gm, eps_run, model, use_ellipticity=ell, verbose=False).process()
                 R_phys, R_mod = per_halo_scalars_box(ccl, cosmo, model, cat.cat['M'], redshift)
         extra = dict(raw2D=gp, raw3D=gp * 3.0) if paint else dict(values=gd, R_mod=R_mod, eps_mod=eps_mod)
+        if ell:
+            extra.update(q_ell=cat.cat['q_ell'].astype('<f4'), A_ell=cat.cat['A_ell'].astype('<f4'))
         save(name, kind="grid_paint" if paint else "grid_bary", ndim=ndim, N=N, L=Lbox, redshift=redshift,
              M=cat.cat['M'].astype('<f4'), x=cat.cat['x'].astype('<f4'), y=cat.cat['y'].astype('<f4'),
              z=cat.cat['z'].astype('<f4'), map=gmap, ax0=gaxes[0], ax1=gaxes[1], ax2=gaxes[2], eps_run=eps_run,
@@ -210,6 +217,8 @@ def main():
     grid_case("grid_bary_3d", 3, 40, 80.0, 50, 32, 6, 4, 0.3, False)
     grid_case("grid_paint_2d", 2, 128, 200.0, 150, 33, 6, None, 0.3, True)
     grid_case("grid_paint_3d", 3, 40, 80.0, 50, 34, 4, None, 0.0, True)
+    grid_case("grid_bary_2d_ell", 2, 96, 150.0, 100, 35, 10, 5, 0.3, False, ell=True)
+    grid_case("grid_paint_2d_ell", 2, 96, 150.0, 100, 36, 6, None, 0.3, True, ell=True)
 
     # ---------------- snapshots
     def snap_case(name, ndim, n_part, Lbox, n, seed, eps_run, eps_mod, redshift):

@@ -264,6 +264,32 @@ def _flat_inds(N, ndim, *axis_inds):
     return ((axis_inds[0][:, None, None] * N + axis_inds[1][None, :, None]) * N + axis_inds[2][None, None, :]).ravel()
 
 
+def build_Rmat(A, q):
+    """DefaultRunnerGrid.build_Rmat, 2-D branch (Map2DRunner.py:281-350), literal."""
+    A = A / np.linalg.norm(A)            # the reference does this in place (:310)
+    ref = np.array([1., 0.])
+    beta = np.arccos(np.dot(A, ref))
+    eta = -np.log(q)
+    if eta > 1e-4:
+        eta2g = np.tanh(0.5 * eta) / eta
+    else:
+        etasq = eta * eta
+        eta2g = 0.5 + etasq * ((-1 / 24) + etasq * (1 / 240))
+    g = eta2g * eta * np.exp(2j * beta)
+    g1, g2 = g.real, g.imag
+    det = np.sqrt(1 - np.abs(g) ** 2)
+    return np.array([[1 + g1, g2], [g2, 1 - g1]]) / det
+
+
+def _ell_radius(grids, d, A_j, q_j):
+    """Map2DRunner.py:531-536 / :769-774: r of the sheared coordinates."""
+    A_j = A_j / np.sqrt(np.sum(A_j ** 2))                               # :497
+    Rmat = build_Rmat(A_j, q_j)
+    xy = np.vstack([(grids[0] + d[0]).flatten(), (grids[1] + d[1]).flatten()]).T   # coord_array
+    xe, ye = (xy @ Rmat).T
+    return np.sqrt(xe ** 2 + ye ** 2)
+
+
 def _cutout(bins, res, Nfloat, pos):
     """Map2DRunner.py:500-528 / :548-566 -- shared cutout construction.  pos = (x_j, y_j[, z_j])."""
     Nsize = int(Nfloat // 2) * 2
@@ -278,7 +304,7 @@ def _cutout(bins, res, Nfloat, pos):
 
 
 def grid_offsets(shape, bins, cat, a, R_phys, R_model_com, eps_runner, table, extras=None, warn=True,
-                 count_only=False):
+                 count_only=False, ell=None):
     """
     Halo loop of BaryonifyGrid.process (/root/reference/BaryonForge/Runners/Map2DRunner.py:474-586).
     cat has float32 fields 'M','x','y','z' (HaloNDCatalog).  R_phys = get_radius(cosmo, M, a) (physical).
@@ -304,6 +330,8 @@ def grid_offsets(shape, bins, cat, a, R_phys, R_model_com, eps_runner, table, ex
         with np.errstate(divide='ignore', invalid='ignore'):
             r_grid = np.sqrt(sum((g + dd) ** 2 for g, dd in zip(grids, d)))
             hats = [(g + dd) / r_grid for g, dd in zip(grids, d)]
+            if ell is not None:                                                # (q_ell, A_ell) columns, 2-D only
+                r_grid = _ell_radius(grids, d, ell[1][j], ell[0][j])
             offset = table.displacement(r_grid.flatten(), M_j, a, R_model_com[j], warn=warn, **o_j) / res   # :540/:583
             for k in range(ndim):
                 pix_offsets[inds, k] += offset * hats[k].flatten()
@@ -330,12 +358,12 @@ def grid_regrid(orig_map, pix_offsets):
     return new_map
 
 
-def baryonify_grid(orig_map, bins, cat, a, R_phys, R_model_com, eps_runner, table, extras=None, warn=True):
-    off, _ = grid_offsets(orig_map.shape, bins, cat, a, R_phys, R_model_com, eps_runner, table, extras, warn)
+def baryonify_grid(orig_map, bins, cat, a, R_phys, R_model_com, eps_runner, table, extras=None, warn=True, ell=None):
+    off, _ = grid_offsets(orig_map.shape, bins, cat, a, R_phys, R_model_com, eps_runner, table, extras, warn, ell=ell)
     return grid_regrid(orig_map, off)
 
 
-def paint_grid(shape, bins, cat, a, R_com, eps_runner, table, include_pixel_size=True, extras=None):
+def paint_grid(shape, bins, cat, a, R_com, eps_runner, table, include_pixel_size=True, extras=None, ell=None):
     """PaintProfilesGrid.process (Map2DRunner.py:676-829).  R_com = get_radius(cosmo, M, a)/a.  Returns (map, n_updates)."""
     ndim = len(shape)
     N = shape[0]
@@ -354,6 +382,8 @@ def paint_grid(shape, bins, cat, a, R_com, eps_runner, table, include_pixel_size
         n_updates += Nsize ** ndim
         inds = _flat_inds(N, ndim, *axis_inds)
         r_grid = np.sqrt(sum((g + dd) ** 2 for g, dd in zip(grids, d)))
+        if ell is not None:
+            r_grid = _ell_radius(grids, d, ell[1][j], ell[0][j])
         with np.errstate(divide='ignore', invalid='ignore'):
             Painting = profile(r_grid.flatten(), M_j, a, **o_j)           # :812
         mask = np.isfinite(Painting)

@@ -60,11 +60,12 @@ def port_run(g):
             bins = (np.arange(N) + 0.5) * L / N
             a = 1 / (1 + g["redshift"])
             cat = dict(M=g["M"], x=g["x"], y=g["y"], z=g["z"])
+            ell = (g["q_ell"], g["A_ell"]) if "q_ell" in g else None
             if kind == "grid_bary":
                 tab = rp.DisplacementTable((g["ax0"], g["ax1"], g["ax2"]), g["values"], g["eps_mod"])
-                return rp.baryonify_grid(g["map"], bins, cat, a, g["R_phys"], g["R_mod"], g["eps_run"], tab)
+                return rp.baryonify_grid(g["map"], bins, cat, a, g["R_phys"], g["R_mod"], g["eps_run"], tab, ell=ell)
             tab = rp.ProfileTable((g["ax0"], g["ax1"], g["ax2"]), g["raw3D"], g["raw2D"])
-            return rp.paint_grid((N,) * ndim, bins, cat, a, g["R_phys"] / a, g["eps_run"], tab)[0]
+            return rp.paint_grid((N,) * ndim, bins, cat, a, g["R_phys"] / a, g["eps_run"], tab, ell=ell)[0]
         if kind == "snap":
             ndim = int(g["ndim"])
             a = 1 / (1 + g["redshift"])
@@ -104,14 +105,18 @@ def product_run(g, **gpu_kwargs):
         if kind in ("grid_bary", "grid_paint"):
             ndim, N, L = int(g["ndim"]), int(g["N"]), float(g["L"])
             bins = (np.arange(N) + 0.5) * L / N
+            ell = "q_ell" in g
+            ekw = dict(q_ell=g["q_ell"], A_ell=g["A_ell"]) if ell else {}
             cat = b.HaloNDCatalog(x=g["x"], y=g["y"], z=g["z"] if ndim == 3 else None, M=g["M"],
-                                  redshift=g["redshift"], cosmo=cosmo)
+                                  redshift=g["redshift"], cosmo=cosmo, **ekw)
             gm = b.GriddedMap(map=g["map"], redshift=g["redshift"], bins=bins, cosmo=cosmo)
             if kind == "grid_bary":
                 model = b.DisplacementModel(axes, g["values"], g["eps_mod"], mc)
-                return b.BaryonifyGrid(cat, gm, g["eps_run"], model, verbose=False, **gpu_kwargs).process()
+                return b.BaryonifyGrid(cat, gm, g["eps_run"], model, use_ellipticity=ell, verbose=False,
+                                       **gpu_kwargs).process()
             model = b.ProfileModel(axes, g["raw3D"], g["raw2D"])
-            return b.PaintProfilesGrid(cat, gm, g["eps_run"], model, verbose=False, **gpu_kwargs).process()
+            return b.PaintProfilesGrid(cat, gm, g["eps_run"], model, use_ellipticity=ell, verbose=False,
+                                       **gpu_kwargs).process()
         if kind == "snap":
             ndim = int(g["ndim"])
             cat = b.HaloNDCatalog(x=g["x"], y=g["y"], z=g["z"] if ndim == 3 else None, M=g["M"],

@@ -101,7 +101,7 @@ def main():
 
         def f1():
             d_off.zero_()
-            _lib.check(L.bfg_grid_offsets(tab.handle, 3, N, float(gm.res), n, d_rec.data_ptr(), None, 0, d_off.data_ptr(), 0, N,
+            _lib.check(L.bfg_grid_offsets(tab.handle, 3, N, float(gm.res), n, d_rec.data_ptr(), None, 0, 0, d_off.data_ptr(), 0, N,
                                           d_n.data_ptr(), st))
 
         def f2():
