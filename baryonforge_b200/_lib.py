@@ -42,7 +42,12 @@ _SIGNATURES = {
     "bfg_healpix_ang2pix": ([C.c_int, c_i64, c_ptr, c_ptr, c_ptr, c_ptr], C.c_int),
     "bfg_shell_offsets": ([c_ptr, C.c_int, c_i64, c_ptr, c_ptr, C.c_int, c_ptr, c_i64, c_i64, c_ptr, c_ptr], C.c_int),
     "bfg_shell_paint": ([c_ptr, C.c_int, c_i64, c_ptr, c_ptr, C.c_int, c_ptr, c_i64, c_i64, c_ptr, c_ptr], C.c_int),
+    "bfg_shell_paint_anis": ([c_ptr, c_ptr, C.c_int, c_i64, c_ptr, c_ptr, C.c_int, c_ptr, c_dbl, c_ptr, c_ptr, c_i64, c_i64,
+                              c_ptr, c_ptr], C.c_int),
+    "bfg_anis_background": ([c_i64, c_ptr, c_dbl, c_ptr, c_dbl, c_dbl, c_ptr, c_ptr], C.c_int),
     "bfg_shell_regrid": ([C.c_int, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_ptr], C.c_int),
+    "bfg_shell_records": ([c_i64, c_ptr, C.c_int, c_dbl, c_dbl, c_dbl, C.c_int, c_ptr, c_ptr, C.c_int, c_ptr, c_ptr, c_ptr,
+                           c_ptr, c_ptr, c_ptr], C.c_int),
     "bfg_shell_regrid_p2p": ([C.c_int, c_ptr, c_ptr, c_i64, c_i64, C.c_int, C.c_int, C.POINTER(c_i64), C.POINTER(c_ptr),
                               c_ptr, c_ptr], C.c_int),
     "bfg_shared_alloc": ([C.POINTER(c_ptr), c_i64, C.c_int], C.c_int),

@@ -106,12 +106,34 @@ def angular_diameter_distance(cosmo, a):
     return _ccl.angular_diameter_distance(cosmo, a)
 
 
+def D_A_spline_to(cosmo, z_m):
+    """CubicSpline of D_A over 1000 nodes in z in [0, z_m + 0.1] (HealpixRunner.py:296-299)."""
+    z_t = np.linspace(0, z_m + 0.1, 1000)
+    return interpolate.CubicSpline(z_t, angular_diameter_distance(cosmo, 1 / (1 + z_t)))
+
+
 def D_A_spline(cosmo, z):
     """The CubicSpline object itself (HealpixRunner.py:297-299), for chunked evaluation."""
     z_m = np.max(z)
     assert z_m <= 30, f"We assume max(z) = 30, but your catalog has max(z) = {z_m}"   # HealpixRunner.py:301
-    z_t = np.linspace(0, z_m + 0.1, 1000)
-    return interpolate.CubicSpline(z_t, angular_diameter_distance(cosmo, 1 / (1 + z_t)))
+    return D_A_spline_to(cosmo, z_m)
+
+
+RADIUS_SPLINE_NODES = 2048
+
+
+def radius_factor_spline(cosmo, mass_def, z_m):
+    """
+    g(u), u = ln(1+z), with mass_def.get_radius(cosmo, M, a) = cbrt(M) * g(u) (physical Mpc): every spherical-overdensity
+    definition has R = (M / (4 pi/3 Delta(a) rho(a)))^(1/3).  Tabulated from the cosmology object in use on 2048 nodes
+    up to z_m + 0.1 and splined; in u the integrand is close to exp(-u), so the spline error is ~ du^4/384 < 1e-13.
+    The device record kernel (bfg_shell_records) evaluates it per halo.
+    """
+    u = np.linspace(0, np.log(1 + z_m + 0.1), RADIUS_SPLINE_NODES)
+    a = np.exp(-u)
+    a[0] = 1.0
+    g = radius_of_mass(cosmo, np.ones_like(a), a, mass_def)
+    return interpolate.CubicSpline(u, g)
 
 
 def D_A_of_z(cosmo, z):

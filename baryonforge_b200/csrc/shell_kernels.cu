@@ -9,6 +9,7 @@
 // with lanes over consecutive pixels of the ring, so the fp64 REDs of a warp hit consecutive addresses of the
 // component-major offsets array.
 #include <algorithm>
+#include <string.h>
 #include "bfg_common.cuh"
 
 using namespace bfg;
@@ -62,9 +63,8 @@ __device__ __forceinline__ HaloUpd make_upd(const TableView &T, const HaloSph &s
 
 // Table value at squared separation r2 (NaN when outside the table / not a positive normal number).
 template <bool UNIFORM>
-__device__ __forceinline__ double table_at(const TableView &T, const double *__restrict__ row, const HaloUpd &u,
-                                           double r2, const double2 *__restrict__ l2tab) {
-    const double l2 = fast_log2(r2, l2tab);
+__device__ __forceinline__ double table_at_l2(const TableView &T, const double *__restrict__ row, const HaloUpd &u,
+                                              double l2) {
     if (UNIFORM) {
         const int NR = T.n[2];
         const double uu = fma(l2, u.uA, u.uB);                      // (ln r - r0) / step
@@ -76,18 +76,51 @@ __device__ __forceinline__ double table_at(const TableView &T, const double *__r
     return row_lookup<false>(T, row, fma(l2, 0.34657359027997264, u.xq0));
 }
 
+template <bool UNIFORM>
+__device__ __forceinline__ double table_at(const TableView &T, const double *__restrict__ row, const HaloUpd &u,
+                                           double r2, const double2 *__restrict__ l2tab) {
+    return table_at_l2<UNIFORM>(T, row, u, fast_log2(r2, l2tab));
+}
+
+// MODE of the halo loop: the three shell runners share geometry and differ in the per-pixel update
+constexpr int MODE_BARYONIFY = 0;   // BaryonifyShell          HealpixRunner.py:315-355
+constexpr int MODE_PAINT = 1;       // PaintProfilesShell      HealpixRunner.py:449-481
+constexpr int MODE_ANIS = 2;        // PaintProfilesAnisShell  HealpixRunner.py:589-631
+
+// Extra inputs of the anisotropic painter: the tracer ("canvas") table and two map-shaped gathers.
+struct AnisArgs {
+    TableView T2;            // Tracer_model.projected table (log values)
+    const double *mtot;      // halo part of the total-mass map, owned range (HealpixRunner.py:565-570)
+    const double *orig;      // LightconeShell.map, owned range
+    double mtot_add;         // dV * drho_m: the uniform background added to every pixel of Mtot_map (:582)
+};
+
 // One (halo, pixel) update.  (x, y, z) = pixel unit vector; (px, py, pz) = (x, y, z) * D; p0/p1/p2 = the pixel's slots
 // in the three offset components (paint: p0 only).
-template <bool PAINT, bool UNIFORM>
+template <int MODE, bool UNIFORM>
 __device__ __forceinline__ void shell_update(const TableView &T, const double *__restrict__ row, const HaloUpd &u,
                                              double x, double y, double z, double px, double py, double pz,
                                              double *__restrict__ p0, double *__restrict__ p1, double *__restrict__ p2,
-                                             const double2 *__restrict__ l2tab) {
+                                             const double2 *__restrict__ l2tab, const AnisArgs &A,
+                                             const double *__restrict__ row2, const HaloUpd &u2) {
     // HealpixRunner.py:338-341  diff = pos - pos_j ; r_sep^2 = sum(diff^2)
     const double dx = px - u.pjx, dy = py - u.pjy, dz = pz - u.pjz;
     const double r2 = dx * dx + dy * dy + dz * dz;
+    if (MODE == MODE_ANIS) {
+        // p1 / p2 point at this pixel's Mtot_map / orig_map entries
+        const double l2 = fast_log2(r2, l2tab);
+        const double P = exp(table_at_l2<UNIFORM>(T, row, u, l2));        // Painting  :610
+        if (!isfinite(P)) return;                                         // :611 -> 0
+        const double C = exp(table_at_l2<UNIFORM>(A.T2, row2, u2, l2));   // Canvas    :612
+        if (!isfinite(C)) return;                                         // :613 -> 0
+        const double m = *p1 + A.mtot_add;                                // Mtot_map[pixind] (halos + background)
+        if (!(m > 0.0)) return;                                           // np.divide(..., where = Mtot > 0)  :614
+        const double add = (P * u.scale) * ((C / m) * *p2);               // :615-623
+        if (add != 0.0) red_add(p0, add);
+        return;
+    }
     double val = table_at<UNIFORM>(T, row, u, r2, l2tab);          // :345 / :472 via ln(r_sep/a), no sqrt, no division
-    if (PAINT) {
+    if (MODE == MODE_PAINT) {
         val = exp(val);                            // Tabulate.py:319
         if (!isfinite(val)) return;                // HealpixRunner.py:473 (adds 0)
         val *= u.scale;                            // :478
@@ -118,19 +151,26 @@ struct __align__(16) RingSeg {
     double rotC, rotS;     // cos / sin of a 32-pixel azimuth step
 };
 
-template <bool PAINT, bool UNIFORM, bool CHECK>
+template <int MODE, bool UNIFORM, bool CHECK>
 __device__ __forceinline__ void ring_pixels(const TableView &T, const double *__restrict__ row, const HaloUpd &u,
                                             const RingSeg &g, double cs, double sn, int lane, double *__restrict__ out,
-                                            i64 nloc, const double2 *__restrict__ l2tab) {
+                                            i64 nloc, const double2 *__restrict__ l2tab, const AnisArgs &A,
+                                            const double *__restrict__ row2, const HaloUpd &u2) {
     const int cnt = g.cnt, nr = g.nr;
     const double z = g.z, sth = g.sth, pz = g.pz, sD = g.sD, rotC = g.rotC, rotS = g.rotS;
     double *__restrict__ b0 = out + g.lbase;
     int ip = g.ip_lo + lane;
     if (ip >= nr) ip -= nr;
     for (int i = lane; i < cnt; i += 32) {
-        if (!CHECK || (unsigned long long)(g.lbase + ip) < (unsigned long long)nloc)
-            shell_update<PAINT, UNIFORM>(T, row, u, sth * cs, sth * sn, z, sD * cs, sD * sn, pz, b0 + ip, b0 + nloc + ip,
-                                         b0 + 2 * nloc + ip, l2tab);
+        if (!CHECK || (unsigned long long)(g.lbase + ip) < (unsigned long long)nloc) {
+            if (MODE == MODE_ANIS)
+                shell_update<MODE, UNIFORM>(T, row, u, sth * cs, sth * sn, z, sD * cs, sD * sn, pz, b0 + ip,
+                                            const_cast<double *>(A.mtot) + g.lbase + ip,
+                                            const_cast<double *>(A.orig) + g.lbase + ip, l2tab, A, row2, u2);
+            else
+                shell_update<MODE, UNIFORM>(T, row, u, sth * cs, sth * sn, z, sD * cs, sD * sn, pz, b0 + ip,
+                                            b0 + nloc + ip, b0 + 2 * nloc + ip, l2tab, A, row2, u2);
+        }
         ip += 32;
         if (ip >= nr) ip -= nr;
         const double c2 = cs * rotC - sn * rotS;   // advance the azimuth by 32 pixels
@@ -139,12 +179,14 @@ __device__ __forceinline__ void ring_pixels(const TableView &T, const double *__
     }
 }
 
-template <bool PAINT, bool UNIFORM>
+template <int MODE, bool UNIFORM>
 __global__ void __launch_bounds__(SHELL_THREADS, SHELL_MIN_CTAS)
 k_shell_halos(TableView T, Hpx h, i64 n_halo, const double *__restrict__ halos, const double *__restrict__ extras,
               int n_extra, double *__restrict__ out, i64 pix_lo, i64 pix_hi, unsigned long long *nupd,
-              const double2 *__restrict__ g_l2tab) {
+              const double2 *__restrict__ g_l2tab, AnisArgs A) {
+    constexpr bool PAINT = (MODE != MODE_BARYONIFY);
     extern __shared__ double row[];
+    const double *row2 = row + ((MODE == MODE_ANIS) ? T.n[2] : 0);   // anis: the tracer row follows the paint row
     __shared__ RingSeg segs[RING_CHUNK];
     __shared__ double2 l2tab[BFG_LOG2_TAB];
     __shared__ int s_next;
@@ -156,14 +198,28 @@ k_shell_halos(TableView T, Hpx h, i64 n_halo, const double *__restrict__ halos, 
     double eqC, eqS;
     sincospi((double)lane * (2.0 / (double)h.nl4), &eqS, &eqC);
     i64 done = 0;
+    const bool sharded = pix_lo > 0 || pix_hi < h.npix;
 
     for (i64 j = blockIdx.x; j < n_halo; j += gridDim.x) {
         const HaloSph s = load_halo(halos + j * BFG_HALO_STRIDE);
+        const DiscRings d = disc_rings(h, s.theta, s.phi, s.radius);
+        if (sharded) {   // ring-range sharding: a halo whose rings (+2 for the <4-pixel fallback) miss the owned range
+            i64 st0, nr0, st1, nr1; bool sh0;
+            ring_info(h, min(4 * h.nside - 1, max((i64)1, d.ra - 2)), st0, nr0, sh0);
+            ring_info(h, max((i64)1, min(4 * h.nside - 1, d.rb + 2)), st1, nr1, sh0);
+            if (st0 >= pix_hi || st1 + nr1 <= pix_lo) continue;   // uniform across the block
+        }
         __syncthreads();  // previous halo's row / segments no longer in use
         bool valid;
         blend_row(T, s.lnz, s.lnM, extras ? extras + j * n_extra : nullptr, row, valid);
-        const DiscRings d = disc_rings(h, s.theta, s.phi, s.radius);
         const HaloUpd u = make_upd(T, s);
+        HaloUpd u2 = u;
+        if (MODE == MODE_ANIS) {
+            bool valid2;
+            blend_row(A.T2, s.lnz, s.lnM, extras ? extras + j * n_extra : nullptr, row + T.n[2], valid2);
+            valid = valid && valid2;   // a NaN Painting or a NaN Canvas both contribute nothing
+            u2 = make_upd(A.T2, s);
+        }
         // `if pixind.size < 4` (HealpixRunner.py:333) can only trigger for discs of a few pixels (<= ~12 rings)
         const bool tiny = !PAINT && (s.radius * s.radius * (double)h.npix * 0.25 < 64.0);
 
@@ -190,8 +246,8 @@ k_shell_halos(TableView T, Hpx h, i64 n_halo, const double *__restrict__ halos, 
                             double x, y, z;
                             pix2vec(h, p, x, y, z);
                             double *q = out + (p - pix_lo);
-                            shell_update<PAINT, UNIFORM>(T, row, u, x, y, z, x * u.D, y * u.D, z * u.D, q, q + nloc,
-                                                         q + 2 * nloc, l2tab);
+                            shell_update<MODE, UNIFORM>(T, row, u, x, y, z, x * u.D, y * u.D, z * u.D, q, q + nloc,
+                                                        q + 2 * nloc, l2tab, A, row2, u2);
                         }
                     }
                 }
@@ -256,8 +312,8 @@ k_shell_halos(TableView T, Hpx h, i64 n_halo, const double *__restrict__ halos, 
                 } else {
                     sincospi(fma((double)lane, g.inv2nr, g.phase0), &sn, &cs);
                 }
-                if (g.flags & 1) ring_pixels<PAINT, UNIFORM, true>(T, row, u, g, cs, sn, lane, out, nloc, l2tab);
-                else ring_pixels<PAINT, UNIFORM, false>(T, row, u, g, cs, sn, lane, out, nloc, l2tab);
+                if (g.flags & 1) ring_pixels<MODE, UNIFORM, true>(T, row, u, g, cs, sn, lane, out, nloc, l2tab, A, row2, u2);
+                else ring_pixels<MODE, UNIFORM, false>(T, row, u, g, cs, sn, lane, out, nloc, l2tab, A, row2, u2);
             }
             __syncthreads();  // before the next chunk overwrites the segments
         }
@@ -362,10 +418,22 @@ int grid_for(i64 n, int threads, int max_blocks = 148 * 32) {
     return (int)std::max<i64>(1, std::min<i64>((n + threads - 1) / threads, max_blocks));
 }
 
-template <bool PAINT>
+template <int MODE>
 int launch_shell(const bfg_table *t, int nside, i64 n_halo, const double *d_halos, const double *d_extras, int n_extra,
-                 double *d_out, i64 pix_lo, i64 pix_hi, i64 *d_nupdates, cudaStream_t st) {
+                 double *d_out, i64 pix_lo, i64 pix_hi, i64 *d_nupdates, cudaStream_t st,
+                 const bfg_table *t2 = nullptr, const double *d_mtot = nullptr, const double *d_orig = nullptr,
+                 double mtot_add = 0.0) {
+    constexpr bool PAINT = (MODE != MODE_BARYONIFY);
     BFG_REQUIRE(t && (d_halos || n_halo == 0) && (d_out || pix_lo == pix_hi), "null argument");
+    AnisArgs A;
+    memset(&A, 0, sizeof(A));
+    if (MODE == MODE_ANIS) {
+        BFG_REQUIRE(t2 && (pix_lo == pix_hi || (d_mtot && d_orig)), "anisotropic paint needs the tracer table and both maps");
+        BFG_REQUIRE(t2->view.ndim == t->view.ndim && (t2->view.flags & BFG_TABLE_LOG_VALUES),
+                    "tracer table must be a log-profile table with the paint table's extra axes");
+        BFG_REQUIRE(t2->device == t->device, "tables live on different devices");
+        A.T2 = t2->view; A.mtot = d_mtot; A.orig = d_orig; A.mtot_add = mtot_add;
+    }
     if (int rc = check_nside(nside)) return rc;
     Hpx h(nside);
     BFG_REQUIRE(pix_lo >= 0 && pix_hi <= h.npix && pix_lo <= pix_hi, "bad pixel range");
@@ -375,7 +443,7 @@ int launch_shell(const bfg_table *t, int nside, i64 n_halo, const double *d_halo
                 "paint needs a log-profile table, baryonify a displacement table");
     if (d_nupdates) BFG_CUDA_OK(cudaMemsetAsync(d_nupdates, 0, sizeof(i64), st));
     if (n_halo == 0 || pix_lo == pix_hi) return BFG_OK;
-    size_t smem = sizeof(double) * t->view.n[2];
+    size_t smem = sizeof(double) * (t->view.n[2] + (MODE == MODE_ANIS ? t2->view.n[2] : 0));
     BFG_REQUIRE(smem <= 200 * 1024, "radial axis too long for the shared-memory row (max 25600 nodes)");
     int blocks = (int)std::min<i64>(n_halo, (i64)1 << 30);
     const double2 *g_l2tab = nullptr;
@@ -383,11 +451,12 @@ int launch_shell(const bfg_table *t, int nside, i64 n_halo, const double *d_halo
     auto go = [&](auto kern) -> int {
         BFG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<blocks, SHELL_THREADS, smem, st>>>(t->view, h, n_halo, d_halos, d_extras, n_extra, d_out, pix_lo, pix_hi,
-                                                  (unsigned long long *)d_nupdates, g_l2tab);
+                                                  (unsigned long long *)d_nupdates, g_l2tab, A);
         BFG_CUDA_OK(cudaGetLastError());
         return BFG_OK;
     };
-    return t->view.uniform_r ? go(k_shell_halos<PAINT, true>) : go(k_shell_halos<PAINT, false>);
+    const bool uni = t->view.uniform_r && (MODE != MODE_ANIS || t2->view.uniform_r);
+    return uni ? go(k_shell_halos<MODE, true>) : go(k_shell_halos<MODE, false>);
 }
 
 }  // namespace
@@ -395,15 +464,48 @@ int launch_shell(const bfg_table *t, int nside, i64 n_halo, const double *d_halo
 extern "C" int bfg_shell_offsets(const bfg_table *t, int nside, int64_t n_halo, const double *d_halos,
                                  const double *d_extras, int n_extra, double *d_offsets, int64_t pix_lo, int64_t pix_hi,
                                  int64_t *d_nupdates, void *stream) {
-    return launch_shell<false>(t, nside, n_halo, d_halos, d_extras, n_extra, d_offsets, pix_lo, pix_hi,
+    return launch_shell<MODE_BARYONIFY>(t, nside, n_halo, d_halos, d_extras, n_extra, d_offsets, pix_lo, pix_hi,
                                (i64 *)d_nupdates, (cudaStream_t)stream);
 }
 
 extern "C" int bfg_shell_paint(const bfg_table *t, int nside, int64_t n_halo, const double *d_halos,
                                const double *d_extras, int n_extra, double *d_map, int64_t pix_lo, int64_t pix_hi,
                                int64_t *d_nupdates, void *stream) {
-    return launch_shell<true>(t, nside, n_halo, d_halos, d_extras, n_extra, d_map, pix_lo, pix_hi, (i64 *)d_nupdates,
+    return launch_shell<MODE_PAINT>(t, nside, n_halo, d_halos, d_extras, n_extra, d_map, pix_lo, pix_hi, (i64 *)d_nupdates,
                               (cudaStream_t)stream);
+}
+
+extern "C" int bfg_shell_paint_anis(const bfg_table *t_paint, const bfg_table *t_tracer, int nside, int64_t n_halo,
+                                    const double *d_halos, const double *d_extras, int n_extra, const double *d_mtot,
+                                    double mtot_add, const double *d_orig, double *d_map, int64_t pix_lo,
+                                    int64_t pix_hi, int64_t *d_nupdates, void *stream) {
+    return launch_shell<MODE_ANIS>(t_paint, nside, n_halo, d_halos, d_extras, n_extra, d_map, pix_lo, pix_hi,
+                                   (i64 *)d_nupdates, (cudaStream_t)stream, t_tracer, d_mtot, d_orig, mtot_add);
+}
+
+namespace {
+// new_map = (new_map + coef * (bg / Mtot where Mtot > 0 else 0) * orig) * final_scale
+//   HealpixRunner.py:633-636 (final_scale = 1) ; Map2DRunner.py:1004-1015 (final_scale = res^2 when include_pixel_size)
+__global__ void __launch_bounds__(256)
+k_anis_background(i64 n, const double *__restrict__ mtot, double mtot_add, const double *__restrict__ orig, double coef,
+                  double final_scale, double *__restrict__ map) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        const double m = mtot[i] + mtot_add;
+        double f = (m > 0.0) ? mtot_add / m : 0.0;
+        f *= orig[i];
+        map[i] = (map[i] + coef * f) * final_scale;
+    }
+}
+}  // namespace
+
+extern "C" int bfg_anis_background(int64_t n, const double *d_mtot, double mtot_add, const double *d_orig, double coef,
+                                   double final_scale, double *d_map, void *stream) {
+    BFG_REQUIRE(n >= 0 && (n == 0 || (d_mtot && d_orig && d_map)), "null argument");
+    if (n == 0) return BFG_OK;
+    k_anis_background<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(n, d_mtot, mtot_add, d_orig, coef, final_scale,
+                                                                         d_map);
+    BFG_CUDA_OK(cudaGetLastError());
+    return BFG_OK;
 }
 
 extern "C" int bfg_shell_regrid(int nside, const double *d_map_in, const double *d_offsets, double *d_map_out,

@@ -61,6 +61,18 @@ def _sort_records(d_rec, d_ext, mode, p0, p1=0.0, ndim=3):
     return out, out_e
 
 
+_SIDE_STREAMS = {}
+
+
+def _side_stream(dev):
+    """One copy stream per device (H2D of the map underneath the halo loop)."""
+    torch = _torch()
+    key = dev.index
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _SIDE_STREAMS[key]
+
+
 _PINNED_FREE = {}      # numel -> list of idle pinned float64 tensors
 
 
@@ -183,6 +195,7 @@ class DefaultRunner(object):
         self.pix_range = pix_range        # (lo, hi) RING range owned by this rank (parallel.py); None = whole map
         self.sort_halos = sort_halos      # order halos by sky cell on the device before the halo loop (L2 locality)
         self.last_stats = {}
+        self._last_scalars, self._d_aux, self._aux_paint = None, None, False
         self._tables = _TableCache()
         if use_ellipticity:
             raise NotImplementedError("You have set use_ellipticity = True, but this not yet implemented for HealpixRunner")
@@ -191,8 +204,8 @@ class DefaultRunner(object):
     def __getstate__(self):
         d = dict(self.__dict__)
         d['_tables'] = None
-        d.pop('_scratch_inflight', None)
-        d.pop('_peers', None)
+        for k in ('_scratch_inflight', '_peers', '_d_aux', '_spl_cache'):
+            d.pop(k, None)
         return d
 
     def __setstate__(self, d):
@@ -262,17 +275,100 @@ class DefaultRunner(object):
         _parallel_chunks(lambda sl: fill(rec[sl], sl), n)
         return rec, _extras(self.HaloLightConeCatalog.cat, keys)
 
+    # ---- device-side scalar prep ---------------------------------------------------------------------------
+    @property
+    def last_scalars(self):
+        """R_run (physical), D_A, R_model_com of the last halo_records()/process() call, in catalogue order."""
+        if self._last_scalars is None and getattr(self, '_d_aux', None) is not None:
+            aux = self._d_aux.cpu().numpy()
+            self._last_scalars = dict(R_run=aux[0], D_A=aux[1], R_model_com=None if self._aux_paint else aux[2])
+        return self._last_scalars
+
+    @last_scalars.setter
+    def last_scalars(self, value):
+        self._last_scalars = value
+
+    def _spline_pack(self, paint, z_max):
+        """
+        The three per-process() splines the record kernel evaluates, packed as one float64 vector:
+        D_A(z) -- the reference's own CubicSpline (HealpixRunner.py:297-299) -- and the radius factors g(ln(1+z)) with
+        R_delta = cbrt(M) g for the runner's cosmology/mass_def (HealpixRunner.py:320) and the model's
+        (BaryonCorrection.py:399).  Cached on (cosmology, z_max, mass definitions).
+        """
+        mcos = None if paint else getattr(self.model, 'cosmo', None)
+        key = (paint, float(z_max), tuple(sorted(self.cosmo.items())), id(self.mass_def), id(mcos),
+               tuple(sorted(mcos.items())) if isinstance(mcos, dict) else None,
+               None if paint else id(getattr(self.model, 'mass_def', None)))
+        if getattr(self, '_spl_cache', None) is not None and self._spl_cache[0] == key:
+            return self._spl_cache[1]
+        cosmo = cosmology.runner_cosmology(self.cosmo, with_w0=True)          # :280-284
+        DA = cosmology.D_A_spline_to(cosmo, z_max)
+        g_run = cosmology.radius_factor_spline(cosmo, self.mass_def, z_max)
+        parts = [DA.x, DA.c.reshape(-1), g_run.x, g_run.c.reshape(-1)]
+        if not paint:
+            g_mod = cosmology.radius_factor_spline(_model_cosmo(self.model, cosmo),
+                                                   getattr(self.model, 'mass_def', None), z_max)
+            parts.append(g_mod.c.reshape(-1))
+        pack = (np.ascontiguousarray(np.concatenate(parts)), DA.x.size, g_run.x.size)
+        self._spl_cache = (key, pack)
+        return pack
+
+    def device_records(self, paint, dev=None):
+        """
+        Halo records built ON THE DEVICE (bfg_shell_records): the host only stages the raw catalogue columns plus
+        numpy's ln(1+z) and ln M into pinned memory; returns the [n, 16] device tensor (catalogue order).
+        """
+        torch = _torch()
+        dev = self._device() if dev is None else dev
+        cat = self.HaloLightConeCatalog.cat
+        n = cat.size
+        self._last_scalars, self._d_aux, self._aux_paint = None, None, paint
+        with torch.cuda.device(dev):
+            d_rec = torch.empty((n, _lib.HALO_STRIDE), dtype=torch.float64, device=dev)
+            if n == 0:
+                return d_rec
+            z_all = cat['z']
+            z_max = float(np.max(z_all))
+            assert z_max <= 30, f"We assume max(z) = 30, but your catalog has max(z) = {z_max}"   # HealpixRunner.py:301
+            pack, n_DA, n_g = self._spline_pack(paint, z_max)
+            stage = _take_scratch(6 * n)
+            self._scratch_inflight = getattr(self, '_scratch_inflight', None) or []
+            self._scratch_inflight.append(stage)
+            cols = stage.numpy().reshape(6, n)
+
+            def fill(sl):   # numpy releases the GIL inside these ufuncs/copies
+                M, z = cat['M'][sl], cat['z'][sl]
+                cols[0, sl], cols[1, sl], cols[2, sl], cols[3, sl] = M, z, cat['ra'][sl], cat['dec'][sl]
+                np.log(1 / (1 / (1 + z)), out=cols[4, sl])                     # np.log(1/a_j)  BaryonCorrection.py:371
+                np.log(M, out=cols[5, sl])                                     # np.log(M_j)    BaryonCorrection.py:398
+            _parallel_chunks(fill, n)
+            d_cols = stage.to(dev, non_blocking=True)
+            d_pack = torch.from_numpy(pack).to(dev, non_blocking=True)
+            d_aux = torch.empty((3, n), dtype=torch.float64, device=dev)
+            base = d_pack.data_ptr()
+            o_DAc = 8 * n_DA
+            o_gx = o_DAc + 8 * 4 * (n_DA - 1)
+            o_grun = o_gx + 8 * n_g
+            o_gmod = o_grun + 8 * 4 * (n_g - 1)
+            pixarea = 4 * np.pi / self.LightconeShell.map.size
+            _lib.check(_lib.lib().bfg_shell_records(
+                n, d_cols.data_ptr(), 1 if paint else 0, float(self.epsilon_max),
+                0.0 if paint else float(self.model.epsilon_max), pixarea if (paint and self.include_pixel_size) else 0.0,
+                n_DA, base, base + o_DAc, n_g, base + o_gx, base + o_grun, None if paint else base + o_gmod,
+                d_rec.data_ptr(), d_aux.data_ptr(), _lib.current_stream()))
+            self._d_aux = d_aux
+        return d_rec
+
     def _halo_loop(self, paint, table, launch, NSIDE, lo, hi, dev):
         """
-        Host prep -> upload -> sky sort -> `launch(d_rec, d_ext, n, k)` in up to 4 batches: numpy prepares batch k+1 on the
-        host cores while the GPU runs the halo loop of batch k (the sums are order-independent, so batching is free).
+        Stage raw columns -> device scalar prep -> sky sort -> `launch(d_rec, d_ext, n, 0)`.  Nothing here waits for the
+        GPU; halos that cannot touch [lo, hi) are skipped inside the halo-loop kernel (ring-range sharding).
         """
         import time
-        from concurrent.futures import ThreadPoolExecutor
-        import os
         torch = _torch()
         t0 = time.perf_counter()
-        n, fill = self._record_plan(paint)
+        cat = self.HaloLightConeCatalog.cat
+        n = cat.size
         keys = list(vars(self.model).get('p_keys', []))                        # :304
         _check_keys(self.model, keys)
         if n == 0:
@@ -283,44 +379,15 @@ class DefaultRunner(object):
             torch.cuda.current_stream().synchronize()
             _give_scratch(self._scratch_inflight)
         self._scratch_inflight = []
-        cat = self.HaloLightConeCatalog.cat
-        extras_all = _extras(cat, keys)
-        nb = 4 if n >= getattr(self, 'batch_min_halos', 1 << 18) else 1
-        bounds = [(n * b) // nb for b in range(nb + 1)]
-        chunk = 16384          # small enough that batch 0 is complete long before the last batch
-        nthreads = int(os.environ.get("BFG_HOST_THREADS", min(16, os.cpu_count() or 1)))
-        host_s = gpu_issue_s = 0.0
-        with ThreadPoolExecutor(max_workers=max(1, nthreads)) as ex:
-            batches = []
-            for b in range(nb):
-                b0, b1 = bounds[b], bounds[b + 1]
-                # pinned, field-major staging: the H2D copy is then truly asynchronous (a pageable source would make the
-                # host wait for the previous batch's kernel, serialising prep and GPU work)
-                stage = _take_scratch(_lib.HALO_STRIDE * (b1 - b0))
-                self._scratch_inflight.append(stage)
-                buf = stage.numpy().reshape(_lib.HALO_STRIDE, b1 - b0).T
-                buf[:, _lib.HS_RESERVED] = 0.0
-                futs = [ex.submit(fill, buf[i - b0:min(i + chunk, b1) - b0], slice(i, min(i + chunk, b1)))
-                        for i in range(b0, b1, chunk)]
-                batches.append((b0, b1, buf, futs))
-            for k, (b0, b1, buf, futs) in enumerate(batches):
-                tw = time.perf_counter()
-                for f in futs:
-                    f.result()
-                tg = time.perf_counter()
-                host_s += tg - tw
-                ext = None if extras_all is None else extras_all[b0:b1]
-                rec, ext = self._owned_halos(buf, ext, NSIDE, lo, hi)
-                with torch.cuda.device(dev):
-                    d_rec = _upload_records(rec, dev)
-                    d_ext = None if ext is None else _to_device(ext, dev)
-                    if self.sort_halos:
-                        d_rec, d_ext = _sort_records(d_rec, d_ext, 0, SKY_BAND_RAD)
-                    launch(d_rec, d_ext, rec.shape[0], k)
-                gpu_issue_s += time.perf_counter() - tg
-        self.last_timing = dict(host_prep_s=time.perf_counter() - t0, host_wait_s=host_s, gpu_issue_s=gpu_issue_s,
-                                batches=float(nb))
-        return nb
+        with torch.cuda.device(dev):
+            d_rec = self.device_records(paint, dev)
+            ext = _extras(cat, keys)
+            d_ext = None if ext is None else _to_device(ext, dev)
+            if self.sort_halos:
+                d_rec, d_ext = _sort_records(d_rec, d_ext, 0, SKY_BAND_RAD)
+            launch(d_rec, d_ext, n, 0)
+        self.last_timing = dict(host_prep_s=time.perf_counter() - t0)
+        return 1
 
     def _range(self, npix):
         return (0, npix) if self.pix_range is None else (int(self.pix_range[0]), int(self.pix_range[1]))
@@ -399,12 +466,18 @@ class BaryonifyShell(DefaultRunner):
         prof = os.environ.get("BFG_PROFILE_E2E") == "1"
         t_start = time.perf_counter()
         with torch.cuda.device(dev):
-            d_map = _to_device(orig_map[lo:hi], dev, dtype=np.float64)
-            if prof:
-                torch.cuda.synchronize(); t_h2d = time.perf_counter()
+            # the halo loop is enqueued first; the map is only needed by the re-binning, so its H2D copy runs on a side
+            # stream underneath the halo loop (a pageable source blocks the host, not the GPU)
             d_off, d_n = self.offsets_on_device()
             if prof:
                 torch.cuda.synchronize(); t_loop = time.perf_counter()
+            side = _side_stream(dev)
+            with torch.cuda.stream(side):
+                d_map = _to_device(orig_map[lo:hi], dev, dtype=np.float64)
+            torch.cuda.current_stream().wait_stream(side)
+            d_map.record_stream(torch.cuda.current_stream())
+            if prof:
+                torch.cuda.synchronize(); t_h2d = time.perf_counter()
             st = _lib.current_stream()
             d_map_sum = None
             peers = self._peer_slices(npix, dev) if self.pix_range is not None else None
@@ -454,8 +527,8 @@ class BaryonifyShell(DefaultRunner):
         self.last_stats = dict(n_updates=n_up, new_sum=new_sum, old_sum=old_sum)
         if prof:
             t_end = time.perf_counter()
-            self.last_timing.update(h2d_map_s=t_h2d - t_start, halo_loop_total_s=t_loop - t_h2d,
-                                    regrid_reduce_s=t_regrid - t_loop, pinned_alloc_s=t_alloc - t_regrid,
+            self.last_timing.update(halo_loop_total_s=t_loop - t_start, h2d_map_s=t_h2d - t_loop,
+                                    regrid_reduce_s=t_regrid - t_h2d, pinned_alloc_s=t_alloc - t_regrid,
                                     d2h_s=t_end - t_alloc, total_s=t_end - t_start)
         assert np.isclose(new_sum, old_sum), \
             "ERROR in pixel regridding, sum(new_map) [%0.14e] != sum(oldmap) [%0.14e]" % (new_sum, old_sum)   # :368-370

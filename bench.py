@@ -231,12 +231,11 @@ def run_b200(args):
                               pix_range=None if world == 1 else (lo, hi), sort_halos=not args.no_sort)
 
     # ---- device-resident step ------------------------------------------------------------------------------
-    rec, extras = runner.halo_records(paint=False)
-    if world > 1:
-        keep = parallel.halos_touching_pixel_range(nside, rec[:, _lib.HS_THETA], rec[:, _lib.HS_RADIUS], lo, hi)
-        rec = np.ascontiguousarray(rec[keep])
+    # halo records: per-halo scalars computed on the device (bfg_shell_records); every rank holds the whole catalogue
+    # (128 B per halo) and the halo-loop kernel skips the halos whose disc cannot touch its pixel range
+    d_rec = runner.device_records(paint=False, dev=dev)
+    n_rec = d_rec.shape[0]
     table = displacement_table_of(model, local)
-    d_rec = torch.from_numpy(np.ascontiguousarray(rec)).to(dev)
     d_rec_sorted = torch.empty_like(d_rec)
     d_map = pinned_map[lo:hi].to(dev)
     d_off = torch.empty((3, hi - lo), dtype=torch.float64, device=dev)
@@ -259,13 +258,13 @@ def run_b200(args):
         if args.no_sort:
             d_use = d_rec
         else:   # locality ordering of the halo records is part of the step
-            _lib.check(L.bfg_halo_sort(0, rec.shape[0], d_rec.data_ptr(), d_rec_sorted.data_ptr(), None, None, 0,
+            _lib.check(L.bfg_halo_sort(0, n_rec, d_rec.data_ptr(), d_rec_sorted.data_ptr(), None, None, 0,
                                        b.runners.SKY_BAND_RAD, 0.0, 3, st))
             d_use = d_rec_sorted
             launches[0] += 2
         if timed_kernel is not None:
             timed_kernel[0].record()
-        _lib.check(L.bfg_shell_offsets(table.handle, nside, rec.shape[0], d_use.data_ptr(), None, 0, d_off.data_ptr(),
+        _lib.check(L.bfg_shell_offsets(table.handle, nside, n_rec, d_use.data_ptr(), None, 0, d_off.data_ptr(),
                                        lo, hi, d_n.data_ptr(), st))
         if timed_kernel is not None:
             timed_kernel[1].record()
@@ -342,11 +341,11 @@ def run_b200(args):
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {"value": n_up / float(tt[0]), "unit": "halo-pixel updates/s",
-               "h2d_bytes_per_step": int((hi - lo) * 8 + rec.size * 8), "d2h_bytes_per_step": int(npix * 8),
+               "h2d_bytes_per_step": int((hi - lo) * 8 + 6 * n_rec * 8), "d2h_bytes_per_step": int(npix * 8),
                "ms_per_step": 1e3 * float(tt[0]), "host_prep_ms": 1e3 * runner.last_timing.get("host_prep_s", 0.0),
                "host_threads": int(os.environ.get("BFG_HOST_THREADS", min(16, os.cpu_count() or 1))),
                "iter_ms": iter_ms, "phases_ms": {k: round(1e3 * v, 2) for k, v in runner.last_timing.items()},
-               "includes": "host per-halo scalar prep, H2D (pinned map + halo records), kernels, NCCL reduce (N>1), D2H"}
+               "includes": "host staging of raw catalogue columns + numpy ln(1+z), ln M; H2D (pinned map + 6 columns); device scalar prep, sort, halo loop, re-binning, exchange (N>1); D2H of the new map"}
 
     if world > 1:
         dist.barrier()

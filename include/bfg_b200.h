@@ -110,6 +110,19 @@ int bfg_healpix_interp_weights(int nside, int64_t n, const double *d_theta, cons
 int bfg_healpix_ang2pix(int nside, int64_t n, const double *d_theta, const double *d_phi, int64_t *d_pix, void *stream);
 
 /* ---- shells ------------------------------------------------------------------------------------- */
+/* Per-halo scalars of the shell runners on the device (HealpixRunner.py:317-329, :451-462; BaryonCorrection.py:371,
+ * 398-399,410): fills n_halo shell records from the raw catalogue columns.
+ *   d_cols        [6][n_halo] float64: M, z, ra [deg], dec [deg], np.log(1/a), np.log(M) (the two logs come from the host
+ *                 so that halos exactly on a table edge land on the reference's side)
+ *   D_A spline    the reference's CubicSpline(z_t, D_A) (HealpixRunner.py:297-299) as scipy PPoly: n_DA breakpoints
+ *                 d_DA_x, coefficients d_DA_c [4][n_DA-1]; evaluated in scipy's operation order (bit-identical D_j)
+ *   radius splines g(u), u = ln(1+z): R_delta(M, a) = cbrt(M) * g(u) (physical Mpc) for the runner's cosmology/mass_def
+ *                 (d_g_run_c) and the model's (d_g_mod_c, NULL for paint), sharing the breakpoints d_g_x [n_g]
+ *   paint != 0    PaintProfilesShell records: RCUT = +inf, SCALE = pixarea * D^2 when pixarea > 0 (:478) else 1
+ *   d_aux         optional [3][n_halo]: R_j (physical), D_j, R_com of the model (NaN for paint) -- for parity tests. */
+int bfg_shell_records(int64_t n_halo, const double *d_cols, int paint, double eps_run, double eps_model, double pixarea,
+                      int n_DA, const double *d_DA_x, const double *d_DA_c, int n_g, const double *d_g_x,
+                      const double *d_g_run_c, const double *d_g_mod_c, double *d_halos, double *d_aux, void *stream);
 /* Halo loop of BaryonifyShell.process (HealpixRunner.py:315-355): accumulates the unit-vector offsets of all
  * halos into d_offsets, laid out [3][pix_hi-pix_lo] (component-major, so REDs of a warp are contiguous), for the
  * owned RING range [pix_lo, pix_hi).  d_extras: [n_halo][n_extra] p_keys values or NULL.  d_offsets must be zeroed
@@ -120,6 +133,21 @@ int bfg_shell_offsets(const bfg_table *t, int nside, int64_t n_halo, const doubl
 /* Halo loop of PaintProfilesShell.process (HealpixRunner.py:449-481): d_map[pix - pix_lo] += profile. */
 int bfg_shell_paint(const bfg_table *t, int nside, int64_t n_halo, const double *d_halos, const double *d_extras,
                     int n_extra, double *d_map, int64_t pix_lo, int64_t pix_hi, int64_t *d_nupdates, void *stream);
+/* Halo loop of PaintProfilesAnisShell.process (HealpixRunner.py:589-631): per (halo, pixel)
+ *   d_map[p] += Paint(r) * SCALE * ( Tracer(r) / (d_mtot[p] + mtot_add)  if that total mass > 0 else 0 ) * d_orig[p]
+ * with non-finite Paint / Tracer read-outs contributing nothing.  t_paint = model.projected table, t_tracer =
+ * Tracer_model.projected table (both log-profile tables with the same extra axes); d_mtot = the halo part of Mtot_map
+ * (a PaintProfilesShell pass of Mtot_model with include_pixel_size, :565-570), mtot_add = dV * drho_m (:582); d_orig =
+ * LightconeShell.map.  d_mtot, d_orig, d_map cover the owned range [pix_lo, pix_hi). */
+int bfg_shell_paint_anis(const bfg_table *t_paint, const bfg_table *t_tracer, int nside, int64_t n_halo,
+                         const double *d_halos, const double *d_extras, int n_extra, const double *d_mtot,
+                         double mtot_add, const double *d_orig, double *d_map, int64_t pix_lo, int64_t pix_hi,
+                         int64_t *d_nupdates, void *stream);
+/* Uniform-background term and final scaling of the anisotropic painters (HealpixRunner.py:633-636,
+ * Map2DRunner.py:1004-1015):  d_map[i] = (d_map[i] + coef * (mtot_add / (d_mtot[i] + mtot_add) if > 0 else 0) * d_orig[i])
+ * * final_scale, coef = background_val * global_tracer_fraction. */
+int bfg_anis_background(int64_t n, const double *d_mtot, double mtot_add, const double *d_orig, double coef,
+                        double final_scale, double *d_map, void *stream);
 /* Re-binning of BaryonifyShell.process (HealpixRunner.py:357-365 + regrid_pixels_hpix :17-71): for source pixels
  * p in [pix_lo, pix_hi) with d_map_in[p - pix_lo] != 0, deposit onto the 4 interpolation neighbours of the displaced
  * direction.  d_map_out is a FULL map (npix) that must be zeroed by the caller; d_offsets is [3][pix_hi-pix_lo]. */

@@ -303,19 +303,39 @@ def test_full_size_subdomain_parity_nside4096():
     assert int((d_off != 0).any(dim=0).sum().item()) <= touched.size
 
 
-def test_batched_halo_loop_equals_single_batch():
-    """The pipelined 4-batch halo loop (used for >= 262144 halos) gives the single-batch answer."""
+def test_device_scalar_prep_matches_host_formulas():
+    """bfg_shell_records (device-side per-halo scalars) vs the numpy restatement of
+    HealpixRunner.py:317-329 in halo_records(): D_A bit-identical (scipy PPoly order), logs bit-identical (host numpy),
+    radii to 1e-12 (spline of the radius factor), angles to a few ulp (CUDA vs glibc sincos/atan2)."""
     import baryonforge_b200 as b
-    cat, shell, model, axes, vals = _fresh_shell_case(128, 5000, 21, 20, 20)
-    one = b.BaryonifyShell(cat, shell, 20, model, verbose=False)
-    four = b.BaryonifyShell(cat, shell, 20, model, verbose=False)
-    four.batch_min_halos = 1000
-    a, na = one.offsets_on_device()
-    c, nc = four.offsets_on_device()
-    assert four.last_timing["batches"] == 4.0 and one.last_timing["batches"] == 1.0
-    assert int(na.cpu()[0]) == int(nc.cpu()[0])
-    assert_close(c.cpu().numpy(), a.cpu().numpy(), "batched offsets", rtol=1e-9, atol_scale=1e-12)
-    assert_close(four.process(), one.process(), "batched map", rtol=1e-9, atol_scale=1e-12)
+    from baryonforge_b200 import _lib, synth
+    cat, shell, model, axes, vals = _fresh_shell_case(64, 5000, 21, 20, 7)
+    model.cosmo = dict(synth.COSMO, Omega_m=0.33)            # two cosmologies -> two R200c (SURVEY §10 #6)
+    cat.cat['z'][:3] = [0.0, 0.4, 0.5]
+    cat.cat['dec'][:4] = [90.0, -90.0, 89.9999, 0.0]
+    cat.cat['ra'][:4] = [0.0, 359.9999, 180.0, 0.0]
+    pm = b.ProfileModel(axes, synth.profile_values(axes) * 3, synth.profile_values(axes))
+    for paint, run in ((False, b.BaryonifyShell(cat, shell, 20, model, verbose=False)),
+                       (True, b.PaintProfilesShell(cat, shell, 20, pm, include_pixel_size=True, verbose=False)),
+                       (True, b.PaintProfilesShell(cat, shell, 20, pm, include_pixel_size=False, verbose=False))):
+        want, _ = run.halo_records(paint=paint)
+        sc_w = run.last_scalars
+        got = run.device_records(paint).cpu().numpy()
+        sc_g = run.last_scalars
+        assert np.array_equal(got[:, _lib.HS_D], want[:, _lib.HS_D])            # D_a(z_j): same PPoly, same op order
+        assert np.array_equal(got[:, _lib.HS_LNZ], want[:, _lib.HS_LNZ])
+        assert np.array_equal(got[:, _lib.HS_LNM], want[:, _lib.HS_LNM])
+        assert np.array_equal(got[:, _lib.HS_A], want[:, _lib.HS_A])
+        for f in (_lib.HS_RADIUS, _lib.HS_RCUT, _lib.HS_SCALE, _lib.HS_LNRCOM):
+            assert np.allclose(got[:, f], want[:, f], rtol=1e-12, atol=1e-13), f
+        for f in (_lib.HS_VX, _lib.HS_VY, _lib.HS_VZ, _lib.HS_THETA, _lib.HS_PHI, _lib.HS_THETA_LL, _lib.HS_PHI_LL):
+            d = np.abs(got[:, f] - want[:, f])
+            if f == _lib.HS_PHI:      # at the poles the azimuth of the vector is round-off dominated
+                d = np.minimum(d, 2 * np.pi - d)[4:]
+            assert d.max() < 1e-14, (f, d.max())
+        assert np.allclose(sc_g["R_run"], sc_w["R_run"], rtol=1e-12) and np.array_equal(sc_g["D_A"], sc_w["D_A"])
+        if not paint:
+            assert np.allclose(sc_g["R_model_com"], sc_w["R_model_com"], rtol=1e-12)
 
 
 def test_parallelize_mirrors():
