@@ -59,6 +59,8 @@ _SIGNATURES = {
                           c_ptr], C.c_int),
     "bfg_grid_paint": ([c_ptr, C.c_int, c_i64, c_dbl, c_dbl, c_i64, c_ptr, c_ptr, C.c_int, C.c_int, c_ptr, c_i64, c_i64,
                         c_ptr, c_ptr], C.c_int),
+    "bfg_grid_paint_anis": ([c_ptr, c_ptr, c_i64, c_dbl, c_i64, c_ptr, c_ptr, C.c_int, C.c_int, c_ptr, c_dbl, c_ptr, c_ptr,
+                             c_i64, c_i64, c_ptr, c_ptr], C.c_int),
     "bfg_grid_regrid": ([C.c_int, c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_ptr], C.c_int),
     "bfg_snap_build_cells": ([C.c_int, c_i64, c_ptr, c_ptr, c_ptr, c_dbl, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr], C.c_int),
     "bfg_snap_offsets": ([c_ptr, C.c_int, c_i64, c_ptr, c_ptr, c_ptr, c_dbl, C.c_int, c_ptr, c_i64, c_ptr, c_ptr, C.c_int,

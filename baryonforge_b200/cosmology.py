@@ -82,6 +82,16 @@ def _rho(cosmo, a, rho_type):
     return _ccl.rho_x(cosmo, a, rho_type) if hasattr(_ccl, 'rho_x') else cosmo.rho_x(a, rho_type)
 
 
+def rho_matter(cosmo, a, is_comoving=False):
+    """cosmo.rho_x(a, species='matter', is_comoving=...) (HealpixRunner.py:580, Map2DRunner.py:886), Msun / Mpc^3."""
+    if isinstance(cosmo, Background):
+        r = cosmo.rho_matter(a)
+        return r * np.asarray(a, dtype=np.float64) ** 3 if is_comoving else r
+    if hasattr(cosmo, 'rho_x'):
+        return cosmo.rho_x(a, 'matter', is_comoving=is_comoving)
+    return _ccl.rho_x(cosmo, a, 'matter', is_comoving=is_comoving)
+
+
 def radius_of_mass(cosmo, M, a, mass_def=None):
     """mass_def.get_radius(cosmo, M, a), physical Mpc, vectorised over (M, a).  mass_def=None means 200c."""
     M = np.asarray(M)

@@ -11,6 +11,7 @@
 //       gx = x[j] + dx,  gy = x[i] + dy,  gz = x[k] + dz        with dx = bins[x_cen] - x_j, ...
 //     and component 0 of the offset is gx/r, component 1 is gy/r.
 #include <algorithm>
+#include <string.h>
 #include "bfg_common.cuh"
 
 using namespace bfg;
@@ -52,12 +53,25 @@ __device__ __forceinline__ int wrap_idx(int c, int N) {   // pick_indices, Map2D
 
 // ELL (2-D only): the last 4 columns of `extras` hold the halo's shear matrix Rmat (Map2DRunner.py:281-350, build_Rmat);
 // the radius handed to the table is |(gx, gy) @ Rmat| while the direction stays (gx, gy)/r   (:531-536, :769-774).
-template <bool PAINT, bool UNIFORM, int NDIM, bool ELL>
+constexpr int MODE_BARYONIFY = 0;   // BaryonifyGrid          Map2DRunner.py:482-586
+constexpr int MODE_PAINT = 1;       // PaintProfilesGrid      Map2DRunner.py:725-821
+constexpr int MODE_ANIS = 2;        // PaintProfilesAnisGrid  Map2DRunner.py:895-1001 (2-D maps only, :847)
+
+struct AnisArgs {
+    TableView T2;            // Tracer_model.projected table (log values)
+    const double *mtot;      // halo part of Mtot_map, owned planes (Map2DRunner.py:866-871)
+    const double *orig;      // GriddedMap.map, owned planes
+    double mtot_add;         // dV * drho_m (:888)
+};
+
+template <int MODE, bool UNIFORM, int NDIM, bool ELL>
 __global__ void __launch_bounds__(GRID_THREADS)
 k_grid_halos(TableView T, int N, double res, double scale, i64 n_halo, const double *__restrict__ halos,
              const double *__restrict__ extras, int n_extra, double *__restrict__ out, int plane_lo, int plane_hi,
-             unsigned long long *nupd, const double2 *__restrict__ g_l2tab) {
+             unsigned long long *nupd, const double2 *__restrict__ g_l2tab, AnisArgs A) {
+    constexpr bool PAINT = (MODE != MODE_BARYONIFY);
     extern __shared__ double row[];
+    const double *trow = row + ((MODE == MODE_ANIS) ? T.n[2] : 0);   // anis: tracer row after the paint row
     __shared__ double2 l2tab[BFG_LOG2_TAB];
     load_log2_table(l2tab, g_l2tab);
     const i64 plane = (NDIM == 3) ? (i64)N * N : (i64)N;       // cells per axis-0 plane
@@ -71,6 +85,8 @@ k_grid_halos(TableView T, int N, double res, double scale, i64 n_halo, const dou
         __syncthreads();
         bool valid;
         blend_row(T, b.lnz, b.lnM, extras ? extras + h * n_extra : nullptr, row, valid);
+        bool valid2 = true;
+        if (MODE == MODE_ANIS) blend_row(A.T2, b.lnz, b.lnM, extras ? extras + h * n_extra : nullptr, row + T.n[2], valid2);
         __syncthreads();
         const int ns = b.nsize, cw = ns / 2;
         const double cut2 = PAINT ? b.paintcut * b.paintcut : b.rcut * b.rcut;
@@ -110,6 +126,17 @@ k_grid_halos(TableView T, int N, double res, double scale, i64 n_halo, const dou
                 double val = row_lookup<UNIFORM>(T, row, xq);
                 if (!valid) val = CUDART_NAN;
                 ++done;
+                if (MODE == MODE_ANIS) {
+                    const double P = exp(val);                                   // Painting  :981
+                    if (!isfinite(P) || !(rt2 < cut2)) continue;                 // mask      :987-992
+                    double C = exp(row_lookup<UNIFORM>(A.T2, trow, xq));         // Canvas    :982
+                    if (!valid2 || !isfinite(C)) continue;                       // :983 -> 0
+                    const double m = A.mtot[cell] + A.mtot_add;                  // Mtot_map[inds]
+                    if (!(m > 0.0)) continue;                                    // np.divide(..., where = Mtot > 0)  :984
+                    const double add = P * ((C / m) * A.orig[cell]);             // :985, :996
+                    if (add != 0.0) red_add(out + cell, add);
+                    continue;
+                }
                 if (PAINT) {
                     val = exp(val);                                  // Tabulate.py:319
                     if (!isfinite(val) || !(rt2 < cut2)) continue;   // Map2DRunner.py:814-818
@@ -192,11 +219,23 @@ k_grid_regrid(int N, const double *__restrict__ map_in, const double *__restrict
     }
 }
 
-template <bool PAINT>
+template <int MODE>
 int launch_grid(const bfg_table *t, int ndim, i64 N, double res, double scale, i64 n_halo, const double *d_halos,
                 const double *d_extras, int n_extra, int use_ell, double *d_out, i64 plane_lo, i64 plane_hi,
-                i64 *d_nupdates, cudaStream_t st) {
+                i64 *d_nupdates, cudaStream_t st, const bfg_table *t2 = nullptr, const double *d_mtot = nullptr,
+                const double *d_orig = nullptr, double mtot_add = 0.0) {
+    constexpr bool PAINT = (MODE != MODE_BARYONIFY);
     BFG_REQUIRE(t && (d_halos || n_halo == 0) && d_out, "null argument");
+    AnisArgs A;
+    memset(&A, 0, sizeof(A));
+    if (MODE == MODE_ANIS) {
+        BFG_REQUIRE(ndim == 2, "Can only paint anisotropic profiles on 2D maps (Map2DRunner.py:847)");
+        BFG_REQUIRE(t2 && d_mtot && d_orig, "anisotropic paint needs the tracer table and both maps");
+        BFG_REQUIRE(t2->view.ndim == t->view.ndim && (t2->view.flags & BFG_TABLE_LOG_VALUES),
+                    "tracer table must be a log-profile table with the paint table's extra axes");
+        BFG_REQUIRE(t2->device == t->device, "tables live on different devices");
+        A.T2 = t2->view; A.mtot = d_mtot; A.orig = d_orig; A.mtot_add = mtot_add;
+    }
     BFG_REQUIRE(ndim == 2 || ndim == 3, "ndim must be 2 or 3");
     BFG_REQUIRE(N >= 4 && N <= 32768, "N out of range (need 4 <= N <= 32768)");
     BFG_REQUIRE(plane_lo >= 0 && plane_hi <= N && plane_lo <= plane_hi, "bad plane range");
@@ -208,7 +247,7 @@ int launch_grid(const bfg_table *t, int ndim, i64 N, double res, double scale, i
                 "paint needs a log-profile table, baryonify a displacement table");
     if (d_nupdates) BFG_CUDA_OK(cudaMemsetAsync(d_nupdates, 0, sizeof(i64), st));
     if (n_halo == 0 || plane_lo == plane_hi) return BFG_OK;
-    size_t smem = sizeof(double) * t->view.n[2];
+    size_t smem = sizeof(double) * (t->view.n[2] + (MODE == MODE_ANIS ? t2->view.n[2] : 0));
     BFG_REQUIRE(smem <= 200 * 1024, "radial axis too long for the shared-memory row (max 25600 nodes)");
     int blocks = (int)std::min<i64>(n_halo, (i64)1 << 30);
     const double2 *g_l2tab = nullptr;
@@ -216,14 +255,19 @@ int launch_grid(const bfg_table *t, int ndim, i64 N, double res, double scale, i
     auto go = [&](auto kern) -> int {
         BFG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<blocks, GRID_THREADS, smem, st>>>(t->view, (int)N, res, scale, n_halo, d_halos, d_extras, n_extra, d_out,
-                                                 (int)plane_lo, (int)plane_hi, (unsigned long long *)d_nupdates, g_l2tab);
+                                                 (int)plane_lo, (int)plane_hi, (unsigned long long *)d_nupdates, g_l2tab, A);
         BFG_CUDA_OK(cudaGetLastError());
         return BFG_OK;
     };
-    const bool u = t->view.uniform_r != 0;
-    if (ndim == 3) return u ? go(k_grid_halos<PAINT, true, 3, false>) : go(k_grid_halos<PAINT, false, 3, false>);
-    if (use_ell) return u ? go(k_grid_halos<PAINT, true, 2, true>) : go(k_grid_halos<PAINT, false, 2, true>);
-    return u ? go(k_grid_halos<PAINT, true, 2, false>) : go(k_grid_halos<PAINT, false, 2, false>);
+    const bool u = t->view.uniform_r != 0 && (MODE != MODE_ANIS || t2->view.uniform_r != 0);
+    if (MODE == MODE_ANIS) {   // 2-D only
+        if (use_ell) return u ? go(k_grid_halos<MODE_ANIS, true, 2, true>) : go(k_grid_halos<MODE_ANIS, false, 2, true>);
+        return u ? go(k_grid_halos<MODE_ANIS, true, 2, false>) : go(k_grid_halos<MODE_ANIS, false, 2, false>);
+    }
+    constexpr int M = (MODE == MODE_ANIS) ? MODE_PAINT : MODE;   // keeps 3-D anis variants from being instantiated
+    if (ndim == 3) return u ? go(k_grid_halos<M, true, 3, false>) : go(k_grid_halos<M, false, 3, false>);
+    if (use_ell) return u ? go(k_grid_halos<M, true, 2, true>) : go(k_grid_halos<M, false, 2, true>);
+    return u ? go(k_grid_halos<M, true, 2, false>) : go(k_grid_halos<M, false, 2, false>);
 }
 
 }  // namespace
@@ -231,15 +275,23 @@ int launch_grid(const bfg_table *t, int ndim, i64 N, double res, double scale, i
 extern "C" int bfg_grid_offsets(const bfg_table *t, int ndim, int64_t N, double res, int64_t n_halo,
                                 const double *d_halos, const double *d_extras, int n_extra, int use_ell,
                                 double *d_offsets, int64_t plane_lo, int64_t plane_hi, int64_t *d_nupdates, void *stream) {
-    return launch_grid<false>(t, ndim, N, res, 1.0, n_halo, d_halos, d_extras, n_extra, use_ell, d_offsets, plane_lo,
+    return launch_grid<MODE_BARYONIFY>(t, ndim, N, res, 1.0, n_halo, d_halos, d_extras, n_extra, use_ell, d_offsets, plane_lo,
                               plane_hi, (i64 *)d_nupdates, (cudaStream_t)stream);
 }
 
 extern "C" int bfg_grid_paint(const bfg_table *t, int ndim, int64_t N, double res, double scale, int64_t n_halo,
                               const double *d_halos, const double *d_extras, int n_extra, int use_ell, double *d_map,
                               int64_t plane_lo, int64_t plane_hi, int64_t *d_nupdates, void *stream) {
-    return launch_grid<true>(t, ndim, N, res, scale, n_halo, d_halos, d_extras, n_extra, use_ell, d_map, plane_lo,
+    return launch_grid<MODE_PAINT>(t, ndim, N, res, scale, n_halo, d_halos, d_extras, n_extra, use_ell, d_map, plane_lo,
                              plane_hi, (i64 *)d_nupdates, (cudaStream_t)stream);
+}
+
+extern "C" int bfg_grid_paint_anis(const bfg_table *t_paint, const bfg_table *t_tracer, int64_t N, double res,
+                                   int64_t n_halo, const double *d_halos, const double *d_extras, int n_extra, int use_ell,
+                                   const double *d_mtot, double mtot_add, const double *d_orig, double *d_map,
+                                   int64_t plane_lo, int64_t plane_hi, int64_t *d_nupdates, void *stream) {
+    return launch_grid<MODE_ANIS>(t_paint, 2, N, res, 1.0, n_halo, d_halos, d_extras, n_extra, use_ell, d_map, plane_lo,
+                                  plane_hi, (i64 *)d_nupdates, (cudaStream_t)stream, t_tracer, d_mtot, d_orig, mtot_add);
 }
 
 extern "C" int bfg_grid_regrid(int ndim, int64_t N, const double *d_map_in, const double *d_offsets, double *d_map_out,

@@ -122,6 +122,14 @@ def reduce_partial_map(partial_full_map, owned_source_map):
     return partial_full_map, src_sum[0]
 
 
+def all_reduce_sum(t):
+    """In-place sum of a small device tensor over the ranks (no-op without an initialised process group)."""
+    dist = _dist()
+    if dist is not None and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t
+
+
 def gather_owned_ranges(owned, total):
     """Concatenate every rank's owned (contiguous, rank-ordered) slice into the full array on every rank."""
     import torch

@@ -14,10 +14,11 @@ There is no CPU fallback: without a GPU / the shared library, process() raises.
 import numpy as np
 
 from . import _lib, cosmology
-from .tables import displacement_table_of, profile_table_of
+from .tables import displacement_table_of, get_parameter, profile_table_of
 
-__all__ = ['DefaultRunner', 'BaryonifyShell', 'PaintProfilesShell', 'DefaultRunnerGrid', 'BaryonifyGrid',
-           'PaintProfilesGrid', 'DefaultRunnerSnapshot', 'BaryonifySnapshot', 'deposit_ngp']
+__all__ = ['DefaultRunner', 'BaryonifyShell', 'PaintProfilesShell', 'PaintProfilesAnisShell', 'DefaultRunnerGrid',
+           'BaryonifyGrid', 'PaintProfilesGrid', 'PaintProfilesAnisGrid', 'DefaultRunnerSnapshot', 'BaryonifySnapshot',
+           'deposit_ngp']
 
 
 def _torch():
@@ -538,6 +539,29 @@ class BaryonifyShell(DefaultRunner):
 class PaintProfilesShell(DefaultRunner):
     """BaryonForge/Runners/HealpixRunner.py:376-483."""
 
+    def paint_on_device(self):
+        """The halo loop only: returns (painted map of the owned range on the device, update-count tensor)."""
+        torch = _torch()
+        assert self.model is not None, "You must provide a model"
+        dev = self._device()
+        L = _lib.lib()
+        NSIDE = self.LightconeShell.NSIDE
+        npix = self.LightconeShell.map.size
+        lo, hi = self._range(npix)
+        with torch.cuda.device(dev):
+            table = self._tables.get((id(self.model), id(getattr(self.model, 'interp2D', None))),
+                                     lambda: profile_table_of(self.model, '2D', dev.index))
+        with torch.cuda.device(dev):
+            d_new = torch.zeros(hi - lo, dtype=torch.float64, device=dev)
+            d_nb = torch.zeros(4, dtype=torch.int64, device=dev)
+
+        def launch(d_rec, d_ext, n, k):
+            _lib.check(L.bfg_shell_paint(table.handle, NSIDE, n, _lib.ptr(d_rec), _lib.ptr(d_ext), table.n_extra,
+                                         _lib.ptr(d_new), lo, hi, d_nb.data_ptr() + 8 * k, _lib.current_stream()))
+        self._halo_loop(True, table, launch, NSIDE, lo, hi, dev)
+        with torch.cuda.device(dev):
+            return d_new, d_nb.sum().reshape(1)
+
     def process(self):
         torch = _torch()
         assert self.model is not None, "You must provide a model"
@@ -570,6 +594,106 @@ class PaintProfilesShell(DefaultRunner):
         self._scratch_inflight = []
         self.last_stats = dict(n_updates=n_up)
         return out_np
+
+
+class PaintProfilesAnisShell(DefaultRunner):
+    """
+    BaryonForge/Runners/HealpixRunner.py:484-640: paints `model` weighted by the share of each pixel's total mass that
+    the halo's `Tracer_model` profile accounts for, times the input map; mass not in halos is a uniform background.
+    Three tables are needed on the device: model.interp2D, Tracer_model.interp2D and Mtot_model.interp2D.
+    """
+
+    def __init__(self, HaloLightConeCatalog, LightConeShell, epsilon_max, model, Tracer_model, Mtot_model,
+                 background_val, global_tracer_fraction, mass_def=None, include_pixel_size=False, use_ellipticity=False,
+                 verbose=True, *, device=None, pix_range=None, sort_halos=True):
+        self.Tracer_model = Tracer_model
+        self.Mtot_model = Mtot_model
+        self.background_val = background_val
+        self.global_tracer_fraction = global_tracer_fraction
+        super().__init__(HaloLightConeCatalog, LightConeShell, epsilon_max, model, use_ellipticity, mass_def,
+                         include_pixel_size, verbose, device=device, pix_range=pix_range, sort_halos=sort_halos)
+        self._tables2 = _TableCache()
+
+    def __setstate__(self, d):
+        super().__setstate__(d)
+        self._tables2 = _TableCache()
+
+    def __getstate__(self):
+        d = super().__getstate__()
+        d['_tables2'] = None
+        return d
+
+    def process(self):
+        import warnings
+        torch = _torch()
+        dev = self._device()
+        L = _lib.lib()
+        cosmo = cosmology.runner_cosmology(self.cosmo, with_w0=True)               # :535-540
+        orig_map = self.LightconeShell.map
+        NSIDE = self.LightconeShell.NSIDE
+        npix = orig_map.size
+        pixarea = 4 * np.pi / npix                                                 # :545
+        lo, hi = self._range(npix)
+        cat = self.HaloLightConeCatalog.cat
+        keys = list(vars(self.model).get('p_keys', []))                            # :552
+        _check_keys(self.model, keys)
+        # total-mass map of the halos (:565-570): a PaintProfilesShell pass of Mtot_model, kept on the device
+        mrun = PaintProfilesShell(self.HaloLightConeCatalog, self.LightconeShell, self.epsilon_max, self.Mtot_model,
+                                  self.use_ellipticity, self.mass_def, True, self.verbose, device=self.device,
+                                  pix_range=self.pix_range, sort_halos=self.sort_halos)
+        d_mtot, _ = mrun.paint_on_device()
+        dL = 2 * get_parameter(self.Mtot_model, 'proj_cutoff')                     # :573
+        z_m = float(np.max(cat['z'])) if cat.size else 0.0
+        dD = float(cosmology.D_A_spline_to(cosmo, z_m)(self.LightconeShell.redshift))   # :546-549, :574
+        dV = pixarea * ((dD + dL) ** 3 - dD ** 3)                                  # :575
+        with torch.cuda.device(dev):
+            d_s = torch.zeros(1, dtype=torch.float64, device=dev)
+            _lib.check(L.bfg_sum_f64(_lib.ptr(d_mtot), hi - lo, _lib.ptr(d_s), _lib.current_stream()))
+            if self.pix_range is not None:
+                from .parallel import all_reduce_sum
+                all_reduce_sum(d_s)
+            mtot_sum = float(d_s.cpu()[0])
+        rho_halos = mtot_sum / (dV * npix)                                         # :576
+        rho_m = float(cosmology.rho_matter(cosmo, 1 / (self.LightconeShell.redshift + 1), is_comoving=False))   # :580
+        drho_m = float(np.clip(rho_m - rho_halos, 0, None))                        # :581
+        mtot_add = dV * drho_m                                                     # :582
+        if self.verbose:
+            print(f"Inputted halos contribute {100*(rho_halos/rho_m):0.2f}% of the total matter density.")
+            print(f"Remaining density is assigned to a uniform background.")
+        if rho_halos > rho_m:
+            warnings.warn("Inputted halos contribute more mass than is available for this mean matter density."
+                          "Your Mtot_model profiles are either too extended or you are using the wrong cosmology.")
+        with torch.cuda.device(dev):
+            t_paint = self._tables.get((id(self.model), id(getattr(self.model, 'interp2D', None))),
+                                       lambda: profile_table_of(self.model, '2D', dev.index))
+            t_tracer = self._tables2.get((id(self.Tracer_model), id(getattr(self.Tracer_model, 'interp2D', None))),
+                                         lambda: profile_table_of(self.Tracer_model, '2D', dev.index))
+            d_orig = _to_device(orig_map[lo:hi], dev, dtype=np.float64)
+            d_new = torch.zeros(hi - lo, dtype=torch.float64, device=dev)
+            d_nb = torch.zeros(4, dtype=torch.int64, device=dev)
+
+        def launch(d_rec, d_ext, n, k):
+            _lib.check(L.bfg_shell_paint_anis(t_paint.handle, t_tracer.handle, NSIDE, n, _lib.ptr(d_rec), _lib.ptr(d_ext),
+                                              t_paint.n_extra, _lib.ptr(d_mtot), float(mtot_add), _lib.ptr(d_orig),
+                                              _lib.ptr(d_new), lo, hi, d_nb.data_ptr() + 8 * k, _lib.current_stream()))
+        self._halo_loop(True, t_paint, launch, NSIDE, lo, hi, dev)
+        with torch.cuda.device(dev):
+            # uniform-background term (:633-636)
+            _lib.check(L.bfg_anis_background(hi - lo, _lib.ptr(d_mtot), float(mtot_add), _lib.ptr(d_orig),
+                                             float(self.background_val * self.global_tracer_fraction), 1.0,
+                                             _lib.ptr(d_new), _lib.current_stream()))
+            d_n = d_nb.sum().reshape(1)
+            if self.pix_range is not None:
+                from .parallel import gather_owned_ranges
+                d_new = gather_owned_ranges(d_new, npix)
+            out, out_np = _pinned_result(npix)
+            out.copy_(d_new, non_blocking=True)
+            n_up = int(d_n.cpu()[0])
+            torch.cuda.current_stream().synchronize()
+        _give_scratch(getattr(self, '_scratch_inflight', []))
+        self._scratch_inflight = []
+        self.last_stats = dict(n_updates=n_up, rho_halos=rho_halos, rho_m=rho_m, dV=dV, dD=dD)
+        return out_np.reshape(orig_map.shape)
 
 
 # =====================================================================================================================
@@ -781,30 +905,48 @@ class BaryonifyGrid(DefaultRunnerGrid):
 class PaintProfilesGrid(DefaultRunnerGrid):
     """BaryonForge/Runners/Map2DRunner.py:624-829."""
 
-    def process(self):
+    def _device_records(self, dev):
+        """Halo records (+ extras) of the owned planes on the device, box-cell ordered."""
+        gm = self.GriddedMap
+        ndim, N = (2 if gm.is2D else 3), gm.Npix
+        lo, hi = self._planes(N)
+        rec, extras = self.halo_records(paint=True)
+        rec, extras = self._owned_halos(rec, extras, N, lo, hi)
+        d_rec = _upload_records(rec, dev)
+        d_ext = None if extras is None else _to_device(extras, dev)
+        d_rec, d_ext = _sort_records(d_rec, d_ext, 1, float(gm.L), 16, ndim)
+        return d_rec, d_ext, rec.shape[0]
+
+    def paint_on_device(self):
+        """The halo loop only: returns (painted owned planes on the device, flat; update-count tensor)."""
         torch = _torch()
         gm = self.GriddedMap
         ndim, N = (2 if gm.is2D else 3), gm.Npix
         lo, hi = self._planes(N)
         dev = self._device()
         L = _lib.lib()
-        rec, extras = self.halo_records(paint=True)
-        rec, extras = self._owned_halos(rec, extras, N, lo, hi)
         which = '2D' if gm.is2D else '3D'                                         # :763 projected / :792 real
         dV = float(np.power(gm.res, ndim)) if self.include_pixel_size else 1.0    # :723,825
         with torch.cuda.device(dev):
+            d_rec, d_ext, n = self._device_records(dev)
             table = self._tables.get((id(self.model), which, id(getattr(self.model, 'interp' + which, None))),
                                      lambda: profile_table_of(self.model, which, dev.index))
-            d_rec = _upload_records(rec, dev)
-            d_ext = None if extras is None else _to_device(extras, dev)
-            d_rec, d_ext = _sort_records(d_rec, d_ext, 1, float(gm.L), 16, ndim)
             nloc = (hi - lo) * N ** (ndim - 1)
             d_new = torch.zeros(nloc, dtype=torch.float64, device=dev)
             d_n = torch.zeros(1, dtype=torch.int64, device=dev)
             n_cols = 0 if d_ext is None else d_ext.shape[1]
-            _lib.check(L.bfg_grid_paint(table.handle, ndim, N, float(gm.res), dV, rec.shape[0], _lib.ptr(d_rec),
+            _lib.check(L.bfg_grid_paint(table.handle, ndim, N, float(gm.res), dV, n, _lib.ptr(d_rec),
                                         _lib.ptr(d_ext), n_cols, 1 if self.use_ellipticity else 0, _lib.ptr(d_new), lo, hi,
                                         _lib.ptr(d_n), _lib.current_stream()))
+        return d_new, d_n
+
+    def process(self):
+        torch = _torch()
+        gm = self.GriddedMap
+        ndim, N = (2 if gm.is2D else 3), gm.Npix
+        dev = self._device()
+        d_new, d_n = self.paint_on_device()
+        with torch.cuda.device(dev):
             if self.plane_range is not None:
                 from .parallel import gather_owned_ranges
                 d_new = gather_owned_ranges(d_new, gm.map.size)
@@ -814,6 +956,93 @@ class PaintProfilesGrid(DefaultRunnerGrid):
             torch.cuda.current_stream().synchronize()
         self.last_stats = dict(n_updates=n_up)
         return out_np.reshape(gm.map.shape)
+
+
+class PaintProfilesAnisGrid(PaintProfilesGrid):
+    """BaryonForge/Runners/Map2DRunner.py:833-1015 (2-D maps only, :847)."""
+
+    def __init__(self, HaloNDCatalog, GriddedMap, epsilon_max, model, Tracer_model, Mtot_model, background_val,
+                 global_tracer_fraction, mass_def=None, include_pixel_size=True, use_ellipticity=False, verbose=True, *,
+                 device=None, plane_range=None):
+        self.Tracer_model = Tracer_model
+        self.Mtot_model = Mtot_model
+        self.background_val = background_val
+        self.global_tracer_fraction = global_tracer_fraction
+        super().__init__(HaloNDCatalog, GriddedMap, epsilon_max, model, use_ellipticity, mass_def, include_pixel_size,
+                         verbose, device=device, plane_range=plane_range)
+        self._tables2 = _TableCache()
+
+    def __setstate__(self, d):
+        super().__setstate__(d)
+        self._tables2 = _TableCache()
+
+    def __getstate__(self):
+        d = super().__getstate__()
+        d['_tables2'] = None
+        return d
+
+    def process(self):
+        import warnings
+        torch = _torch()
+        gm = self.GriddedMap
+        assert gm.is2D == True, "Can only paint tSZ on 2D maps. You have passed a 3D Map"   # noqa: E712  (:847)
+        dev = self._device()
+        L = _lib.lib()
+        cosmo = cosmology.runner_cosmology(self.cosmo, with_w0=False)             # :849-853
+        orig_map = gm.map
+        N, res = gm.Npix, gm.res
+        lo, hi = self._planes(N)
+        nloc = (hi - lo) * N
+        # total-mass map of the halos (:866-871): a PaintProfilesGrid pass of Mtot_model without the pixel size
+        mrun = PaintProfilesGrid(self.HaloNDCatalog, gm, self.epsilon_max, self.Mtot_model, self.use_ellipticity,
+                                 self.mass_def, False, self.verbose, device=self.device, plane_range=self.plane_range)
+        d_mtot, _ = mrun.paint_on_device()
+        dL = 2 * get_parameter(self.Mtot_model, 'proj_cutoff')                    # :877
+        dV = np.power(res, 2) * dL                                                # :878
+        with torch.cuda.device(dev):
+            d_s = torch.zeros(1, dtype=torch.float64, device=dev)
+            _lib.check(L.bfg_sum_f64(_lib.ptr(d_mtot), nloc, _lib.ptr(d_s), _lib.current_stream()))
+            if self.plane_range is not None:
+                from .parallel import all_reduce_sum
+                all_reduce_sum(d_s)
+            mtot_sum = float(d_s.cpu()[0])
+        rho_halos = (mtot_sum / orig_map.size) / dL                               # :879 np.average(Mtot_map) / dL
+        rho_m = float(cosmology.rho_matter(cosmo, 1 / (self.HaloNDCatalog.redshift + 1), is_comoving=True))   # :886
+        drho_m = float(np.clip(rho_m - rho_halos, 0, None))                       # :887
+        mtot_add = float(dV * drho_m)                                             # :888
+        if self.verbose:
+            print(f"Inputted halos contribute {100*(rho_halos/rho_m):0.2f}% of the total matter density.")
+            print(f"Remaining density is assigned to a uniform background.")
+        if rho_halos > rho_m:
+            warnings.warn("Inputted halos contribute more mass than is available for this mean matter density."
+                          "Your Mtot_model profiles are either too extended or you are using the wrong cosmology.")
+        final = float(np.power(res, 2)) if self.include_pixel_size else 1.0       # :1012-1015
+        with torch.cuda.device(dev):
+            t_paint = self._tables.get((id(self.model), '2D', id(getattr(self.model, 'interp2D', None))),
+                                       lambda: profile_table_of(self.model, '2D', dev.index))
+            t_tracer = self._tables2.get((id(self.Tracer_model), id(getattr(self.Tracer_model, 'interp2D', None))),
+                                         lambda: profile_table_of(self.Tracer_model, '2D', dev.index))
+            d_rec, d_ext, n = self._device_records(dev)
+            d_orig = _to_device(orig_map[lo:hi], dev, dtype=np.float64)
+            d_new = torch.zeros(nloc, dtype=torch.float64, device=dev)
+            d_n = torch.zeros(1, dtype=torch.int64, device=dev)
+            n_cols = 0 if d_ext is None else d_ext.shape[1]
+            st = _lib.current_stream()
+            _lib.check(L.bfg_grid_paint_anis(t_paint.handle, t_tracer.handle, N, float(res), n, _lib.ptr(d_rec),
+                                             _lib.ptr(d_ext), n_cols, 1 if self.use_ellipticity else 0, _lib.ptr(d_mtot),
+                                             mtot_add, _lib.ptr(d_orig), _lib.ptr(d_new), lo, hi, _lib.ptr(d_n), st))
+            _lib.check(L.bfg_anis_background(nloc, _lib.ptr(d_mtot), mtot_add, _lib.ptr(d_orig),
+                                             float(self.background_val * self.global_tracer_fraction), final,
+                                             _lib.ptr(d_new), st))
+            if self.plane_range is not None:
+                from .parallel import gather_owned_ranges
+                d_new = gather_owned_ranges(d_new, orig_map.size)
+            out, out_np = _pinned_result(orig_map.size)
+            out.copy_(d_new, non_blocking=True)
+            n_up = int(d_n.cpu()[0])
+            torch.cuda.current_stream().synchronize()
+        self.last_stats = dict(n_updates=n_up, rho_halos=rho_halos, rho_m=rho_m, dV=float(dV))
+        return out_np.reshape(orig_map.shape)
 
 
 # =====================================================================================================================

@@ -16,7 +16,8 @@ import numpy as np
 
 from . import _lib
 
-__all__ = ['DeviceTable', 'DisplacementModel', 'ProfileModel', 'displacement_table_of', 'profile_table_of']
+__all__ = ['DeviceTable', 'DisplacementModel', 'ProfileModel', 'displacement_table_of', 'profile_table_of',
+           'get_parameter']
 
 
 class _Grid(object):
@@ -44,12 +45,38 @@ class DisplacementModel(object):
 class ProfileModel(object):
     """Carries what TabulatedProfile.setup_interpolator stores (Tabulate.py:261-271): interp2D/3D over log(table)."""
 
-    def __init__(self, axes, raw3D=None, raw2D=None, mass_def=None, p_keys=()):
+    def __init__(self, axes, raw3D=None, raw2D=None, mass_def=None, p_keys=(), proj_cutoff=None):
         with np.errstate(divide='ignore', invalid='ignore'):
             self.interp3D = None if raw3D is None else _Grid(axes, np.log(np.asarray(raw3D, dtype=np.float64)))
             self.interp2D = None if raw2D is None else _Grid(axes, np.log(np.asarray(raw2D, dtype=np.float64)))
         self.mass_def = mass_def
         self.p_keys = list(p_keys)
+        if proj_cutoff is not None:     # the wrapped profile's line-of-sight half-length (Profiles/Base.py), read by the
+            self.proj_cutoff = proj_cutoff   # anisotropic painters through _get_parameter
+
+
+def get_parameter(obj, key, _depth=0):
+    """
+    utils/Tabulate.py:66-96 `_get_parameter`: the first attribute called `key` on `obj` or, recursively, on the halo
+    profiles it wraps (TabulatedProfile.model, ...).  Without pyccl a "profile" is anything exposing real/projected.
+    """
+    try:
+        import pyccl as ccl
+        is_profile = lambda v: isinstance(v, ccl.halos.profiles.HaloProfile)    # noqa: E731
+    except Exception:
+        is_profile = lambda v: hasattr(v, 'projected') and hasattr(v, 'real')   # noqa: E731
+    for k in dir(obj):
+        if k == key:
+            return getattr(obj, key)
+        if k.startswith('__') or _depth > 8:
+            continue
+        try:
+            v = getattr(obj, k)
+        except Exception:
+            continue
+        if is_profile(v):
+            return get_parameter(v, key, _depth + 1)
+    return None
 
 
 class DeviceTable(object):

@@ -184,6 +184,15 @@ int bfg_grid_offsets(const bfg_table *t, int ndim, int64_t N, double res, int64_
 int bfg_grid_paint(const bfg_table *t, int ndim, int64_t N, double res, double scale, int64_t n_halo,
                    const double *d_halos, const double *d_extras, int n_extra, int use_ell, double *d_map,
                    int64_t plane_lo, int64_t plane_hi, int64_t *d_nupdates, void *stream);
+/* Halo loop of PaintProfilesAnisGrid.process (Map2DRunner.py:895-1001, 2-D maps only :847): per (halo, cell) with a finite
+ * Paint read-out and r < R_com*epsilon_max,
+ *   d_map[c] += Paint(r) * ( Tracer(r) / (d_mtot[c] + mtot_add) if that total mass > 0 else 0 ) * d_orig[c].
+ * d_mtot = halo part of Mtot_map (a PaintProfilesGrid pass of Mtot_model with include_pixel_size=False, :866-871),
+ * mtot_add = dV * drho_m (:888).  The background term and the final *res^2 are bfg_anis_background. */
+int bfg_grid_paint_anis(const bfg_table *t_paint, const bfg_table *t_tracer, int64_t N, double res, int64_t n_halo,
+                        const double *d_halos, const double *d_extras, int n_extra, int use_ell, const double *d_mtot,
+                        double mtot_add, const double *d_orig, double *d_map, int64_t plane_lo, int64_t plane_hi,
+                        int64_t *d_nupdates, void *stream);
 /* Re-binning of BaryonifyGrid.process (Map2DRunner.py:589-613 + regrid_pixels_2D/3D :13-162): non-finite offsets -> 0,
  * add cell coordinates (xy-meshgrid convention), periodic overlap deposit into the FULL grid d_map_out (zeroed by caller). */
 int bfg_grid_regrid(int ndim, int64_t N, const double *d_map_in, const double *d_offsets, double *d_map_out,

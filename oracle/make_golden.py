@@ -7,6 +7,7 @@ synthetic inputs and stores inputs + outputs.  The reference tree does not exist
 are what pins oracle/runners_port.py and the CUDA path there.
 
     python oracle/make_golden.py            # rewrites every fixture (needs /root/reference)
+    python oracle/make_golden.py anis       # only the fixtures whose name contains 'anis'
 
 Inputs follow SURVEY.md §8(d) (distributions of the reference's tests/test_healpix.py:29-55, tests/defaults.py:5).
 The reference objects that need real pyccl to be *built* (Baryonification2D/3D, TabulatedProfile) are created
@@ -117,6 +118,9 @@ def per_halo_scalars_box(ccl, cosmo_dict, model, M32, redshift):
 
 
 def save(name, **arrays):
+    only = sys.argv[1:]                      # optional name filters: python oracle/make_golden.py anis
+    if only and not any(f in name for f in only):
+        return
     out = os.path.join(ROOT, "tests", "golden", name + ".npz")
     np.savez_compressed(out, **arrays)
     print("wrote", out, "%.1f KB" % (os.path.getsize(out) / 1024))
@@ -175,6 +179,49 @@ def main():
     shell_paint("shell_paint_n64", 64, 400, 21, 20, False)
     shell_paint("shell_paint_n32_pixsize", 32, 150, 22, 10, True)
 
+    # ---------------- anisotropic shell painter (HealpixRunner.py:484-640)
+    def shell_anis(name, nside, n, seed, eps_run, pixsize, halo_fraction, z_shell, proj_cutoff=50.0):
+        """halo_fraction: target rho_halos / rho_m -- < 1 leaves a uniform background, > 1 leaves none (and pixels
+        no halo reaches keep Mtot = 0, the `where = Mtot > 0` branch)."""
+        from BaryonForge.Runners import PaintProfilesAnisShell
+        from scipy import interpolate
+        ra, dec, M, z = shell_catalog(n, seed)
+        cat = HaloLightConeCatalog(ra=ra, dec=dec, M=M, z=z, cosmo=cosmo)
+        hmap = synth.shell_map(nside, seed=seed + 1, lo=0.0, hi=10.0)
+        shell = LightconeShell(map=hmap, cosmo=cosmo, redshift=z_shell)
+        ccosmo = ccl.Cosmology(Omega_c=cosmo['Omega_m'] - cosmo['Omega_b'], Omega_b=cosmo['Omega_b'], h=cosmo['h'],
+                               sigma8=cosmo['sigma8'], n_s=cosmo['n_s'], w0=cosmo['w0'], matter_power_spectrum='linear')
+        z_t = np.linspace(0, np.max(cat.cat['z']) + 0.1, 1000)
+        dD = float(interpolate.CubicSpline(z_t, ccl.angular_diameter_distance(ccosmo, 1 / (1 + z_t)))(z_shell))
+        rho_m = float(ccosmo.rho_x(1 / (z_shell + 1), species='matter', is_comoving=False))
+        # scale the total-mass table so that the halos carry `halo_fraction` of the mean matter density
+        mt0 = ref_profile_model(axes, pvals * 3.0, pvals)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            m0 = PaintProfilesShell(cat, shell, eps_run, mt0, include_pixel_size=True, verbose=False).process()
+        pixarea = 4 * np.pi / m0.size
+        dV = pixarea * ((dD + 2 * proj_cutoff) ** 3 - dD ** 3)
+        amp = halo_fraction * rho_m * dV * m0.size / np.sum(m0)
+        mtot2D = pvals * amp
+        tracer2D = pvals ** 0.8 * 40.0                      # a different radial shape than the painted profile
+        mtot = ref_profile_model(axes, mtot2D * 3.0, mtot2D)
+        mtot.proj_cutoff = proj_cutoff
+        tracer = ref_profile_model(axes, tracer2D * 3.0, tracer2D)
+        paint2D = pvals * 1e24                              # halo term of the same order as the background term
+        model = ref_profile_model(axes, paint2D * 3.0, paint2D)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            out = PaintProfilesAnisShell(cat, shell, eps_run, model, tracer, mtot, 2.5, 0.3,
+                                         include_pixel_size=pixsize, verbose=False).process()
+        R_run, D_A, _ = per_halo_scalars_shell(ccl, cosmo, None, cat.cat['M'], cat.cat['z'])
+        save(name, kind="shell_anis", nside=nside, ra=cat.cat['ra'], dec=cat.cat['dec'], M=cat.cat['M'], z=cat.cat['z'],
+             map=hmap, ax0=axes[0], ax1=axes[1], ax2=axes[2], raw2D=paint2D, tracer2D=tracer2D, mtot2D=mtot2D,
+             eps_run=eps_run, pixsize=pixsize, z_shell=z_shell, proj_cutoff=proj_cutoff, background_val=2.5,
+             global_tracer_fraction=0.3, dD=dD, rho_m=rho_m, R_run=R_run, D_A=D_A, out=out)
+
+    shell_anis("shell_anis_n32_background", 32, 150, 51, 10, False, 0.35, 0.3)
+    shell_anis("shell_anis_n32_overfull", 32, 150, 52, 6, True, 2.0, 0.25)
+
     # ---------------- grids
     gaxes = synth.table_axes(nz=6, nM=10, nr=300, z_min=0.0, z_max=1.0, z_linear=True, r_min=1e-2, r_max=2e2)
     gd = synth.displacement_values(gaxes, inject_nan=False)
@@ -219,6 +266,54 @@ def main():
     grid_case("grid_paint_3d", 3, 40, 80.0, 50, 34, 4, None, 0.0, True)
     grid_case("grid_bary_2d_ell", 2, 96, 150.0, 100, 35, 10, 5, 0.3, False, ell=True)
     grid_case("grid_paint_2d_ell", 2, 96, 150.0, 100, 36, 6, None, 0.3, True, ell=True)
+
+    # ---------------- anisotropic grid painter (Map2DRunner.py:833-1015), 2-D maps only
+    def grid_anis(name, N, Lbox, n, seed, eps_run, redshift, pixsize, halo_fraction, ell=False, proj_cutoff=40.0):
+        from BaryonForge.Runners import PaintProfilesAnisGrid
+        pos, M = synth.box_halos(n, Lbox, seed=seed, ndim=2)
+        M[0] = 3e11
+        pos[:, 1] = 0.01 * Lbox / N
+        pos[:, 2] = Lbox * (1 - 1e-3)
+        bins = (np.arange(N) + 0.5) * Lbox / N
+        gmap = np.random.default_rng(seed + 1).uniform(0, 10, (N, N))
+        ekw = {}
+        if ell:
+            erng = np.random.default_rng(seed + 7)
+            ekw = dict(q_ell=erng.uniform(0.4, 1.0, n), A_ell=erng.normal(size=(n, 2)))
+        cat = HaloNDCatalog(x=pos[0], y=pos[1], z=None, M=M, redshift=redshift, cosmo=cosmo, **ekw)
+        gm = GriddedMap(map=gmap, redshift=redshift, bins=bins, cosmo=cosmo)
+        ccosmo = ccl.Cosmology(Omega_c=cosmo['Omega_m'] - cosmo['Omega_b'], Omega_b=cosmo['Omega_b'], h=cosmo['h'],
+                               sigma8=cosmo['sigma8'], n_s=cosmo['n_s'], matter_power_spectrum='linear')
+        rho_m = float(ccosmo.rho_x(1 / (redshift + 1), species='matter', is_comoving=True))
+        mt0 = ref_profile_model(gaxes, gp * 3.0, gp)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            m0 = PaintProfilesGrid(cat, gm, eps_run, mt0, use_ellipticity=ell, include_pixel_size=False,
+                                   verbose=False).process()
+        amp = halo_fraction * rho_m * (2 * proj_cutoff) / np.average(m0)
+        mtot2D = gp * amp
+        tracer2D = gp ** 0.8 * 40.0
+        mtot = ref_profile_model(gaxes, mtot2D * 3.0, mtot2D)
+        mtot.proj_cutoff = proj_cutoff
+        tracer = ref_profile_model(gaxes, tracer2D * 3.0, tracer2D)
+        paint2D = gp * 1e18                                 # halo term of the same order as the background term
+        model = ref_profile_model(gaxes, paint2D * 3.0, paint2D)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            out = PaintProfilesAnisGrid(cat, gm, eps_run, model, tracer, mtot, 2.5, 0.3, include_pixel_size=pixsize,
+                                        use_ellipticity=ell, verbose=False).process()
+        R_phys, _ = per_halo_scalars_box(ccl, cosmo, None, cat.cat['M'], redshift)
+        extra = {}
+        if ell:
+            extra.update(q_ell=cat.cat['q_ell'].astype('<f4'), A_ell=cat.cat['A_ell'].astype('<f4'))
+        save(name, kind="grid_anis", ndim=2, N=N, L=Lbox, redshift=redshift, M=cat.cat['M'].astype('<f4'),
+             x=cat.cat['x'].astype('<f4'), y=cat.cat['y'].astype('<f4'), z=cat.cat['z'].astype('<f4'), map=gmap,
+             ax0=gaxes[0], ax1=gaxes[1], ax2=gaxes[2], raw2D=paint2D, tracer2D=tracer2D, mtot2D=mtot2D, eps_run=eps_run,
+             pixsize=pixsize, proj_cutoff=proj_cutoff, background_val=2.5, global_tracer_fraction=0.3, rho_m=rho_m,
+             R_phys=R_phys, out=out, **extra)
+
+    grid_anis("grid_anis_2d_background", 96, 150.0, 100, 61, 6, 0.3, True, 0.35)
+    grid_anis("grid_anis_2d_overfull_ell", 96, 150.0, 100, 62, 4, 0.3, False, 2.0, ell=True)
 
     # ---------------- snapshots
     def snap_case(name, ndim, n_part, Lbox, n, seed, eps_run, eps_mod, redshift):

@@ -246,6 +246,56 @@ def paint_shell(nside, cat, R_run, D_A, eps_runner, table, include_pixel_size=Fa
     return new_map, n_updates
 
 
+def paint_anis_shell(nside, orig_map, cat, R_run, D_A, eps_runner, table, tracer_table, mtot_table, dD, rho_m,
+                     proj_cutoff, background_val, global_tracer_fraction, include_pixel_size=False, extras=None,
+                     mtot_extras=None):
+    """
+    PaintProfilesAnisShell.process (/root/reference/BaryonForge/Runners/HealpixRunner.py:510-640).
+    Third-party scalars are inputs: dD = D_a(LightconeShell.redshift) (:574), rho_m = cosmo.rho_x(a, 'matter',
+    is_comoving=False) (:580).  Returns (new_map, n_updates, Mtot_map incl. background).
+    """
+    npix = 12 * nside * nside
+    new_map = np.zeros(npix, dtype=np.float64)
+    pixarea = 4 * np.pi / npix
+    Mtot_map, _ = paint_shell(nside, cat, R_run, D_A, eps_runner, mtot_table, True, extras=mtot_extras)   # :565-570
+    dL = 2 * proj_cutoff                                                   # :573
+    dV = pixarea * ((dD + dL) ** 3 - dD ** 3)                              # :575
+    rho_halos = np.sum(Mtot_map) / (dV * Mtot_map.size)                    # :576
+    drho_m = np.clip(rho_m - rho_halos, 0, None)                           # :581
+    Mtot_map += dV * drho_m                                                # :582
+    n_updates = 0
+    keys = table.p_keys
+    for j in range(len(cat['M'])):
+        M_j = cat['M'][j]
+        z_j = cat['z'][j]
+        a_j = 1 / (1 + z_j)
+        R_j, D_j = R_run[j], D_A[j]
+        o_j = {key: extras[key][j] for key in keys}
+        vec_j = _ang2vec_lonlat(cat['ra'][j], cat['dec'][j])
+        radius = R_j * eps_runner / D_j
+        pixind = _query_disc_vec(nside, vec_j, radius)
+        n_updates += pixind.size
+        vec = np.stack(hpo.pix2vec(nside, pixind), axis=1)
+        pos_j = vec_j * D_j
+        pos = vec * D_j
+        diff = pos - pos_j
+        r_sep = np.sqrt(np.sum(diff ** 2, axis=1))
+        with np.errstate(divide='ignore', invalid='ignore'):
+            Painting = table.projected(r_sep / a_j, M_j, a_j, **o_j)       # :610
+            Painting = np.where(np.isfinite(Painting), Painting, 0)        # :611
+            Canvas = tracer_table.projected(r_sep / a_j, M_j, a_j, **o_j)  # :612
+        Canvas = np.where(np.isfinite(Canvas) & np.invert(np.isnan(Canvas)), Canvas, 0)   # :613
+        Mfrac = np.divide(Canvas, Mtot_map[pixind], out=np.zeros_like(Canvas), where=Mtot_map[pixind] > 0)   # :614
+        Mfrac *= orig_map[pixind]                                          # :615
+        if include_pixel_size:
+            Painting = Painting * (pixarea * D_j ** 2)                     # :620
+        new_map[pixind] += Painting * Mfrac                                # :623
+    Mfrac = np.divide(dV * drho_m, Mtot_map, out=np.zeros_like(Mtot_map), where=Mtot_map > 0)   # :626
+    Mfrac *= orig_map
+    new_map += background_val * global_tracer_fraction * Mfrac             # :628
+    return new_map.reshape(orig_map.shape), n_updates, Mtot_map
+
+
 # ------------------------------------------------------------------------------------------------
 # periodic grids
 # ------------------------------------------------------------------------------------------------
@@ -395,6 +445,61 @@ def paint_grid(shape, bins, cat, a, R_com, eps_runner, table, include_pixel_size
     if include_pixel_size:
         new_map *= dV                                                     # :825
     return new_map.reshape(shape), n_updates
+
+
+def paint_anis_grid(orig_map, bins, cat, a, R_com, eps_runner, table, tracer_table, mtot_table, rho_m, proj_cutoff,
+                    background_val, global_tracer_fraction, include_pixel_size=True, extras=None, mtot_extras=None,
+                    ell=None):
+    """
+    PaintProfilesAnisGrid.process (/root/reference/BaryonForge/Runners/Map2DRunner.py:845-1017), 2-D maps only (:847).
+    rho_m = cosmo.rho_x(a, 'matter', is_comoving=True) (:886) is an input.  Returns (new_map, n_updates).
+    """
+    assert orig_map.ndim == 2, "Can only paint tSZ on 2D maps. You have passed a 3D Map"
+    shape = orig_map.shape
+    N = shape[0]
+    res = bins[1] - bins[0]
+    new_map = np.zeros(orig_map.size, dtype=np.float64)
+    flat = orig_map.flatten()
+    Mtot_map, _ = paint_grid(shape, bins, cat, a, R_com, eps_runner, mtot_table, include_pixel_size=False,
+                             extras=mtot_extras, ell=ell)                  # :866-871
+    Mtot_map = Mtot_map.flatten()
+    dL = 2 * proj_cutoff                                                   # :877
+    dV = np.power(res, 2) * dL
+    rho_halos = np.average(Mtot_map) / dL
+    drho_m = np.clip(rho_m - rho_halos, 0, None)                           # :887
+    Mtot_map += dV * drho_m
+    n_updates = 0
+    keys = table.p_keys
+    for j in range(len(cat['M'])):
+        M_j = cat['M'][j]
+        pos = [cat['x'][j], cat['y'][j]]
+        o_j = {key: extras[key][j] for key in keys}
+        R_j = R_com[j]
+        Nsize, axis_inds, d, grids = _cutout(bins, res, 2 * eps_runner * R_j / res, pos)   # :907-915
+        n_updates += Nsize ** 2
+        inds = _flat_inds(N, 2, *axis_inds)
+        r_grid = np.sqrt(sum((g + dd) ** 2 for g, dd in zip(grids, d)))
+        if ell is not None:
+            r_grid = _ell_radius(grids, d, ell[1][j], ell[0][j])
+        with np.errstate(divide='ignore', invalid='ignore'):
+            Painting = table.projected(r_grid.flatten(), M_j, a, **o_j)    # :981
+            Canvas = tracer_table.projected(r_grid.flatten(), M_j, a, **o_j)
+        Canvas = np.where(np.isfinite(Canvas) & np.invert(np.isnan(Canvas)), Canvas, 0)        # :983
+        Mfrac = np.divide(Canvas, Mtot_map[inds], out=np.zeros_like(Canvas), where=Mtot_map[inds] > 0)
+        Mfrac *= flat[inds]
+        mask = np.isfinite(Painting) & np.invert(np.isnan(Painting))       # :987
+        mask = mask & (r_grid.flatten() < R_j * eps_runner)
+        if mask.sum() == 0:
+            continue
+        Painting = np.where(mask, Painting, 0)
+        new_map[inds] += Painting * Mfrac                                  # :996
+    Mfrac = np.divide(dV * drho_m, Mtot_map, out=np.zeros_like(Mtot_map), where=Mtot_map > 0)   # :1004
+    Mfrac *= flat
+    new_map += background_val * global_tracer_fraction * Mfrac
+    new_map = new_map.reshape(shape)
+    if include_pixel_size:
+        new_map *= np.power(res, 2)                                        # :1012-1015
+    return new_map, n_updates
 
 
 # ------------------------------------------------------------------------------------------------

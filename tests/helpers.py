@@ -66,6 +66,26 @@ def port_run(g):
                 return rp.baryonify_grid(g["map"], bins, cat, a, g["R_phys"], g["R_mod"], g["eps_run"], tab, ell=ell)
             tab = rp.ProfileTable((g["ax0"], g["ax1"], g["ax2"]), g["raw3D"], g["raw2D"])
             return rp.paint_grid((N,) * ndim, bins, cat, a, g["R_phys"] / a, g["eps_run"], tab, ell=ell)[0]
+        if kind == "shell_anis":
+            axes = (g["ax0"], g["ax1"], g["ax2"])
+            cat = dict(M=g["M"], z=g["z"], ra=g["ra"], dec=g["dec"])
+            return rp.paint_anis_shell(int(g["nside"]), g["map"], cat, g["R_run"], g["D_A"], g["eps_run"],
+                                       rp.ProfileTable(axes, None, g["raw2D"]), rp.ProfileTable(axes, None, g["tracer2D"]),
+                                       rp.ProfileTable(axes, None, g["mtot2D"]), float(g["dD"]), float(g["rho_m"]),
+                                       float(g["proj_cutoff"]), float(g["background_val"]),
+                                       float(g["global_tracer_fraction"]), bool(g["pixsize"]))[0]
+        if kind == "grid_anis":
+            axes = (g["ax0"], g["ax1"], g["ax2"])
+            N, L = int(g["N"]), float(g["L"])
+            bins = (np.arange(N) + 0.5) * L / N
+            a = 1 / (1 + g["redshift"])
+            cat = dict(M=g["M"], x=g["x"], y=g["y"], z=g["z"])
+            ell = (g["q_ell"], g["A_ell"]) if "q_ell" in g else None
+            return rp.paint_anis_grid(g["map"], bins, cat, a, g["R_phys"] / a, g["eps_run"],
+                                      rp.ProfileTable(axes, None, g["raw2D"]), rp.ProfileTable(axes, None, g["tracer2D"]),
+                                      rp.ProfileTable(axes, None, g["mtot2D"]), float(g["rho_m"]), float(g["proj_cutoff"]),
+                                      float(g["background_val"]), float(g["global_tracer_fraction"]), bool(g["pixsize"]),
+                                      ell=ell)[0]
         if kind == "snap":
             ndim = int(g["ndim"])
             a = 1 / (1 + g["redshift"])
@@ -117,6 +137,28 @@ def product_run(g, **gpu_kwargs):
             model = b.ProfileModel(axes, g["raw3D"], g["raw2D"])
             return b.PaintProfilesGrid(cat, gm, g["eps_run"], model, use_ellipticity=ell, verbose=False,
                                        **gpu_kwargs).process()
+        if kind == "shell_anis":
+            model = b.ProfileModel(axes, None, g["raw2D"])
+            tracer = b.ProfileModel(axes, None, g["tracer2D"])
+            mtot = b.ProfileModel(axes, None, g["mtot2D"], proj_cutoff=float(g["proj_cutoff"]))
+            cat = b.HaloLightConeCatalog(ra=g["ra"], dec=g["dec"], M=g["M"], z=g["z"], cosmo=cosmo)
+            shell = b.LightconeShell(map=g["map"], cosmo=cosmo, redshift=float(g["z_shell"]))
+            return b.PaintProfilesAnisShell(cat, shell, g["eps_run"], model, tracer, mtot, float(g["background_val"]),
+                                            float(g["global_tracer_fraction"]), include_pixel_size=bool(g["pixsize"]),
+                                            verbose=False, **gpu_kwargs).process()
+        if kind == "grid_anis":
+            N, L = int(g["N"]), float(g["L"])
+            bins = (np.arange(N) + 0.5) * L / N
+            ell = "q_ell" in g
+            ekw = dict(q_ell=g["q_ell"], A_ell=g["A_ell"]) if ell else {}
+            model = b.ProfileModel(axes, None, g["raw2D"])
+            tracer = b.ProfileModel(axes, None, g["tracer2D"])
+            mtot = b.ProfileModel(axes, None, g["mtot2D"], proj_cutoff=float(g["proj_cutoff"]))
+            cat = b.HaloNDCatalog(x=g["x"], y=g["y"], z=None, M=g["M"], redshift=g["redshift"], cosmo=cosmo, **ekw)
+            gm = b.GriddedMap(map=g["map"], redshift=g["redshift"], bins=bins, cosmo=cosmo)
+            return b.PaintProfilesAnisGrid(cat, gm, g["eps_run"], model, tracer, mtot, float(g["background_val"]),
+                                           float(g["global_tracer_fraction"]), include_pixel_size=bool(g["pixsize"]),
+                                           use_ellipticity=ell, verbose=False, **gpu_kwargs).process()
         if kind == "snap":
             ndim = int(g["ndim"])
             cat = b.HaloNDCatalog(x=g["x"], y=g["y"], z=g["z"] if ndim == 3 else None, M=g["M"],

@@ -14,8 +14,8 @@ from helpers import assert_close, golden_names, load, port_run, product_run
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("name", golden_names("shell_bary") + golden_names("shell_paint")
-                         + golden_names("grid_bary") + golden_names("grid_paint"))
+@pytest.mark.parametrize("name", golden_names("shell_bary") + golden_names("shell_paint") + golden_names("shell_anis")
+                         + golden_names("grid_bary") + golden_names("grid_paint") + golden_names("grid_anis"))
 def test_map_runners_match_reference_fixture(name):
     g = load(name)
     got = product_run(g)
