@@ -20,7 +20,7 @@ TABLE_RDELTA = 2
 
 # shell record fields (include/bfg_b200.h)
 HS_VX, HS_VY, HS_VZ, HS_THETA, HS_PHI, HS_D, HS_A, HS_RADIUS, HS_LNZ, HS_LNM, HS_RCUT, HS_LNRCOM, HS_SCALE, \
-    HS_THETA_LL, HS_PHI_LL, HS_RESERVED = range(16)
+    HS_THETA_LL, HS_PHI_LL, HS_SKIP = range(16)
 # box record fields
 HB_X, HB_Y, HB_Z, HB_RQ, HB_NSIZE, HB_CX, HB_CY, HB_CZ, HB_LNZ, HB_LNM, HB_RCUT, HB_LNRCOM, HB_DX, HB_DY, HB_DZ, \
     HB_PAINTCUT = range(16)
@@ -68,6 +68,7 @@ _SIGNATURES = {
     "bfg_snap_apply": ([C.c_int, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr], C.c_int),
     "bfg_snap_deposit_ngp": ([C.c_int, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_dbl, c_i64, c_ptr, c_ptr], C.c_int),
     "bfg_halo_sort": ([C.c_int, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, c_dbl, c_dbl, C.c_int, c_ptr], C.c_int),
+    "bfg_halo_sort_owned": ([C.c_int, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, c_dbl, c_ptr], C.c_int),
     "bfg_test_fast_log2": ([c_i64, c_ptr, c_ptr, c_ptr], C.c_int),
     "bfg_sum_f64": ([c_ptr, c_i64, c_ptr, c_ptr], C.c_int),
     "bfg_transpose_offsets": ([c_ptr, c_ptr, c_i64, C.c_int, c_ptr], C.c_int),

@@ -297,6 +297,16 @@ __device__ __forceinline__ DiscRings disc_rings(const Hpx &h, double theta, doub
     return d;
 }
 
+// Ring-range sharding: can the disc (its rings +-2, which also covers the 4 interpolation neighbours of the <4-pixel
+// fallback, HealpixRunner.py:333-334) contain a pixel of [pix_lo, pix_hi)?
+__device__ __forceinline__ bool disc_touches_range(const Hpx &h, const DiscRings &d, i64 pix_lo, i64 pix_hi) {
+    i64 st0, nr0, st1, nr1;
+    bool sh;
+    ring_info(h, min(4 * h.nside - 1, max((i64)1, d.ra - 2)), st0, nr0, sh);
+    ring_info(h, max((i64)1, min(4 * h.nside - 1, d.rb + 2)), st1, nr1, sh);
+    return !(st0 >= pix_hi || st1 + nr1 <= pix_lo);
+}
+
 // Pixels of ring `iz` inside the disc: in-ring indices (ip_lo + i) mod nr for i in [0, cnt).
 __device__ __forceinline__ void disc_ring_span(const Hpx &h, const DiscRings &d, i64 iz, i64 &start, i64 &nr,
                                                bool &shifted, i64 &ip_lo, i64 &cnt) {

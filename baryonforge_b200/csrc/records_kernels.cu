@@ -94,7 +94,7 @@ k_shell_records(i64 n, const double *__restrict__ cols, RecParams P, double *__r
             H[BFG_HS_SCALE] = 1.0;
         }
         H[BFG_HS_THETA_LL] = theta_ll; H[BFG_HS_PHI_LL] = phi_ll;
-        H[BFG_HS_RESERVED] = 0.0;
+        H[BFG_HS_SKIP] = 0.0;
         if (aux) { aux[j] = R; aux[n + j] = D; aux[2 * n + j] = Rcom; }
     }
 }

@@ -24,7 +24,7 @@ constexpr int SHELL_MIN_CTAS = BFG_SHELL_MIN_CTAS;   // 8 -> 64 registers/thread
 constexpr int RING_CHUNK = SHELL_THREADS;   // ring segments staged in shared memory per pass (one per thread)
 
 struct HaloSph {
-    double vx, vy, vz, theta, phi, D, a, radius, lnz, lnM, rcut, lnRcom, scale, theta_ll, phi_ll;
+    double vx, vy, vz, theta, phi, D, a, radius, lnz, lnM, rcut, lnRcom, scale, theta_ll, phi_ll, skip;
 };
 
 __device__ __forceinline__ HaloSph load_halo(const double *__restrict__ H) {
@@ -35,6 +35,7 @@ __device__ __forceinline__ HaloSph load_halo(const double *__restrict__ H) {
     s.lnz = __ldg(H + BFG_HS_LNZ); s.lnM = __ldg(H + BFG_HS_LNM); s.rcut = __ldg(H + BFG_HS_RCUT);
     s.lnRcom = __ldg(H + BFG_HS_LNRCOM); s.scale = __ldg(H + BFG_HS_SCALE);
     s.theta_ll = __ldg(H + BFG_HS_THETA_LL); s.phi_ll = __ldg(H + BFG_HS_PHI_LL);
+    s.skip = __ldg(H + BFG_HS_SKIP);
     return s;
 }
 
@@ -183,9 +184,10 @@ template <int MODE, bool UNIFORM>
 __global__ void __launch_bounds__(SHELL_THREADS, SHELL_MIN_CTAS)
 k_shell_halos(TableView T, Hpx h, i64 n_halo, const double *__restrict__ halos, const double *__restrict__ extras,
               int n_extra, double *__restrict__ out, i64 pix_lo, i64 pix_hi, unsigned long long *nupd,
-              const double2 *__restrict__ g_l2tab, AnisArgs A) {
+              const double2 *__restrict__ g_l2tab, AnisArgs A, unsigned long long *queue) {
     constexpr bool PAINT = (MODE != MODE_BARYONIFY);
     extern __shared__ double row[];
+    __shared__ i64 s_j;
     const double *row2 = row + ((MODE == MODE_ANIS) ? T.n[2] : 0);   // anis: the tracer row follows the paint row
     __shared__ RingSeg segs[RING_CHUNK];
     __shared__ double2 l2tab[BFG_LOG2_TAB];
@@ -200,16 +202,18 @@ k_shell_halos(TableView T, Hpx h, i64 n_halo, const double *__restrict__ halos, 
     i64 done = 0;
     const bool sharded = pix_lo > 0 || pix_hi < h.npix;
 
-    for (i64 j = blockIdx.x; j < n_halo; j += gridDim.x) {
+    // Persistent CTAs (8 per SM) pull halos from a global queue: consecutive halos of the sky-sorted batch go to whichever
+    // CTA is free, so the halos in flight stay neighbours on the sky (L2 locality) and the tail is balanced.
+    for (;;) {
+        __syncthreads();  // previous halo's row / segments / s_j no longer in use
+        if (threadIdx.x == 0) s_j = (i64)atomicAdd(queue, 1ULL);
+        __syncthreads();
+        const i64 j = s_j;
+        if (j >= n_halo) break;
         const HaloSph s = load_halo(halos + j * BFG_HALO_STRIDE);
+        if (s.skip != 0.0) break;   // bfg_halo_sort_owned puts the halos of other ranks last and marks them
         const DiscRings d = disc_rings(h, s.theta, s.phi, s.radius);
-        if (sharded) {   // ring-range sharding: a halo whose rings (+2 for the <4-pixel fallback) miss the owned range
-            i64 st0, nr0, st1, nr1; bool sh0;
-            ring_info(h, min(4 * h.nside - 1, max((i64)1, d.ra - 2)), st0, nr0, sh0);
-            ring_info(h, max((i64)1, min(4 * h.nside - 1, d.rb + 2)), st1, nr1, sh0);
-            if (st0 >= pix_hi || st1 + nr1 <= pix_lo) continue;   // uniform across the block
-        }
-        __syncthreads();  // previous halo's row / segments no longer in use
+        if (sharded && !disc_touches_range(h, d, pix_lo, pix_hi)) continue;   // uniform across the block
         bool valid;
         blend_row(T, s.lnz, s.lnM, extras ? extras + j * n_extra : nullptr, row, valid);
         const HaloUpd u = make_upd(T, s);
@@ -445,14 +449,21 @@ int launch_shell(const bfg_table *t, int nside, i64 n_halo, const double *d_halo
     if (n_halo == 0 || pix_lo == pix_hi) return BFG_OK;
     size_t smem = sizeof(double) * (t->view.n[2] + (MODE == MODE_ANIS ? t2->view.n[2] : 0));
     BFG_REQUIRE(smem <= 200 * 1024, "radial axis too long for the shared-memory row (max 25600 nodes)");
-    int blocks = (int)std::min<i64>(n_halo, (i64)1 << 30);
+    int sms = 148;
+    BFG_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, t->device));
+    int blocks = (int)std::min<i64>(n_halo, (i64)sms * SHELL_MIN_CTAS);   // persistent: every CTA resident
     const double2 *g_l2tab = nullptr;
     if (int rc = get_log2_table(&g_l2tab)) return rc;
+    if (int rc = retain_async_pool()) return rc;
+    unsigned long long *queue = nullptr;   // halo queue head (stream-ordered scratch)
+    BFG_CUDA_OK(cudaMallocAsync(&queue, sizeof(unsigned long long), st));
+    BFG_CUDA_OK(cudaMemsetAsync(queue, 0, sizeof(unsigned long long), st));
     auto go = [&](auto kern) -> int {
         BFG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<blocks, SHELL_THREADS, smem, st>>>(t->view, h, n_halo, d_halos, d_extras, n_extra, d_out, pix_lo, pix_hi,
-                                                  (unsigned long long *)d_nupdates, g_l2tab, A);
+                                                  (unsigned long long *)d_nupdates, g_l2tab, A, queue);
         BFG_CUDA_OK(cudaGetLastError());
+        BFG_CUDA_OK(cudaFreeAsync(queue, st));
         return BFG_OK;
     };
     const bool uni = t->view.uniform_r && (MODE != MODE_ANIS || t2->view.uniform_r);

@@ -25,6 +25,26 @@ __global__ void k_keys_sky(i64 n, const double *__restrict__ halos, double band,
     }
 }
 
+// sky + ownership (ring-range sharding): as k_keys_sky, but halos whose disc cannot touch [pix_lo, pix_hi) get bit 44 set,
+// so they sort behind every owned halo
+constexpr int SKIP_BIT = 44;
+__global__ void k_keys_sky_owned(i64 n, const double *__restrict__ halos, double band, Hpx h, i64 pix_lo, i64 pix_hi,
+                                 unsigned long long *__restrict__ keys, unsigned int *__restrict__ idx) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        const double *H = halos + i * BFG_HALO_STRIDE;
+        double theta = H[BFG_HS_THETA], phi = H[BFG_HS_PHI];
+        unsigned long long b = (unsigned long long)fmin(fmax(theta / band, 0.0), 1048575.0);
+        double f = fmin(fmax(phi * BFG_INV_TWOPI, 0.0), 0.99999999);
+        unsigned long long q = (unsigned long long)(f * 16777216.0);
+        if (b & 1ULL) q = 16777215ULL - q;
+        unsigned long long key = (b << 24) | q;
+        const DiscRings d = disc_rings(h, theta, phi, H[BFG_HS_RADIUS]);
+        if (!disc_touches_range(h, d, pix_lo, pix_hi)) key |= 1ULL << SKIP_BIT;
+        keys[i] = key;
+        idx[i] = (unsigned int)i;
+    }
+}
+
 // box: coarse raster cells of side L / nc, serpentine along the last axis
 __global__ void k_keys_box(i64 n, const double *__restrict__ halos, double L, int nc, int ndim,
                            unsigned long long *__restrict__ keys, unsigned int *__restrict__ idx) {
@@ -52,12 +72,20 @@ __global__ void k_gather_rows(i64 n, int width, const unsigned int *__restrict__
     }
 }
 
+// halo records of other ranks (sorted last): mark them so the halo loop stops there
+__global__ void k_mark_skipped(i64 n, const unsigned long long *__restrict__ sorted_keys, double *__restrict__ out) {
+    for (i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (i64)gridDim.x * blockDim.x)
+        if ((sorted_keys[r] >> SKIP_BIT) & 1ULL) out[r * BFG_HALO_STRIDE + BFG_HS_SKIP] = 1.0;
+}
+
 }  // namespace
 
-extern "C" int bfg_halo_sort(int mode, int64_t n_halo, const double *d_in, double *d_out, const double *d_extras_in,
-                             double *d_extras_out, int n_extra, double p0, double p1, int ndim, void *stream) {
+namespace {
+int halo_sort_impl(int mode, int64_t n_halo, const double *d_in, double *d_out, const double *d_extras_in,
+                   double *d_extras_out, int n_extra, double p0, double p1, int ndim, int nside, i64 pix_lo, i64 pix_hi,
+                   void *stream) {
     BFG_REQUIRE(d_in && d_out && d_in != d_out, "need distinct in/out record buffers");
-    BFG_REQUIRE(mode == 0 || mode == 1, "mode: 0 = sky bands, 1 = box cells");
+    BFG_REQUIRE(mode == 0 || mode == 1 || mode == 2, "mode: 0 = sky bands, 1 = box cells, 2 = sky bands + ownership");
     BFG_REQUIRE(n_halo >= 0 && n_halo < ((int64_t)1 << 32), "n_halo out of range");
     BFG_REQUIRE(n_extra == 0 || (d_extras_in && d_extras_out), "extras missing");
     if (n_halo == 0) return BFG_OK;
@@ -77,6 +105,11 @@ extern "C" int bfg_halo_sort(int mode, int64_t n_halo, const double *d_in, doubl
         BFG_REQUIRE(p0 > 0, "band width must be positive");
         k_keys_sky<<<blocks, 256, 0, st>>>(n_halo, d_in, p0, keys, idx);
         end_bit = 24 + 20;
+    } else if (mode == 2) {
+        BFG_REQUIRE(p0 > 0, "band width must be positive");
+        BFG_REQUIRE(nside >= 1 && nside <= (1 << 24), "nside out of range");
+        k_keys_sky_owned<<<blocks, 256, 0, st>>>(n_halo, d_in, p0, Hpx(nside), pix_lo, pix_hi, keys, idx);
+        end_bit = SKIP_BIT + 1;
     } else {
         BFG_REQUIRE(p0 > 0 && p1 >= 1 && p1 <= 1024 && (ndim == 2 || ndim == 3), "bad box parameters");
         k_keys_box<<<blocks, 256, 0, st>>>(n_halo, d_in, p0, (int)p1, ndim, keys, idx);
@@ -89,9 +122,25 @@ extern "C" int bfg_halo_sort(int mode, int64_t n_halo, const double *d_in, doubl
     int gblocks = (int)std::max<i64>(1, std::min<i64>((n_halo * BFG_HALO_STRIDE + 255) / 256, 148 * 16));
     k_gather_rows<<<gblocks, 256, 0, st>>>(n_halo, BFG_HALO_STRIDE, idx2, d_in, d_out);
     if (n_extra) k_gather_rows<<<gblocks, 256, 0, st>>>(n_halo, n_extra, idx2, d_extras_in, d_extras_out);
+    if (mode == 2) k_mark_skipped<<<blocks, 256, 0, st>>>(n_halo, keys2, d_out);
     BFG_CUDA_OK(cudaGetLastError());
     BFG_CUDA_OK(cudaFreeAsync(tmp, st));
     BFG_CUDA_OK(cudaFreeAsync(idx, st));
     BFG_CUDA_OK(cudaFreeAsync(keys, st));
     return BFG_OK;
+}
+}  // namespace
+
+extern "C" int bfg_halo_sort(int mode, int64_t n_halo, const double *d_in, double *d_out, const double *d_extras_in,
+                             double *d_extras_out, int n_extra, double p0, double p1, int ndim, void *stream) {
+    BFG_REQUIRE(mode == 0 || mode == 1, "mode: 0 = sky bands, 1 = box cells");
+    return halo_sort_impl(mode, n_halo, d_in, d_out, d_extras_in, d_extras_out, n_extra, p0, p1, ndim, 0, 0, 0, stream);
+}
+
+extern "C" int bfg_halo_sort_owned(int nside, int64_t pix_lo, int64_t pix_hi, int64_t n_halo, const double *d_in,
+                                   double *d_out, const double *d_extras_in, double *d_extras_out, int n_extra,
+                                   double band, void *stream) {
+    BFG_REQUIRE(pix_lo >= 0 && pix_lo <= pix_hi, "bad pixel range");
+    return halo_sort_impl(2, n_halo, d_in, d_out, d_extras_in, d_extras_out, n_extra, band, 0.0, 3, nside, pix_lo, pix_hi,
+                          stream);
 }

@@ -48,14 +48,24 @@ def _upload_records(rec, dev):
     return _to_device(rec, dev)
 
 
-def _sort_records(d_rec, d_ext, mode, p0, p1=0.0, ndim=3):
-    """Locality ordering on the device (bfg_halo_sort); returns the re-ordered (records, extras)."""
+def _sort_records(d_rec, d_ext, mode, p0, p1=0.0, ndim=3, owned=None):
+    """Locality ordering on the device (bfg_halo_sort); returns the re-ordered (records, extras).
+    owned = (nside, pix_lo, pix_hi): sky ordering that also moves the halos of other ranks behind the owned ones and
+    marks them (bfg_halo_sort_owned), so the halo loop of a sharded run stops there."""
     torch = _torch()
     n = d_rec.shape[0]
-    if n < 2:
+    if n < 2 and owned is None:
+        return d_rec, d_ext
+    if n == 0:
         return d_rec, d_ext
     out = torch.empty_like(d_rec)
     out_e = None if d_ext is None else torch.empty_like(d_ext)
+    if owned is not None:
+        _lib.check(_lib.lib().bfg_halo_sort_owned(int(owned[0]), int(owned[1]), int(owned[2]), n, _lib.ptr(d_rec),
+                                                  _lib.ptr(out), _lib.ptr(d_ext), _lib.ptr(out_e),
+                                                  0 if d_ext is None else d_ext.shape[1], float(p0),
+                                                  _lib.current_stream()))
+        return out, out_e
     _lib.check(_lib.lib().bfg_halo_sort(mode, n, _lib.ptr(d_rec), _lib.ptr(out), _lib.ptr(d_ext), _lib.ptr(out_e),
                                         0 if d_ext is None else d_ext.shape[1], float(p0), float(p1), ndim,
                                         _lib.current_stream()))
@@ -385,7 +395,8 @@ class DefaultRunner(object):
             ext = _extras(cat, keys)
             d_ext = None if ext is None else _to_device(ext, dev)
             if self.sort_halos:
-                d_rec, d_ext = _sort_records(d_rec, d_ext, 0, SKY_BAND_RAD)
+                owned = None if self.pix_range is None else (NSIDE, lo, hi)
+                d_rec, d_ext = _sort_records(d_rec, d_ext, 0, SKY_BAND_RAD, owned=owned)
             launch(d_rec, d_ext, n, 0)
         self.last_timing = dict(host_prep_s=time.perf_counter() - t0)
         return 1

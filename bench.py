@@ -258,10 +258,14 @@ def run_b200(args):
         if args.no_sort:
             d_use = d_rec
         else:   # locality ordering of the halo records is part of the step
-            _lib.check(L.bfg_halo_sort(0, n_rec, d_rec.data_ptr(), d_rec_sorted.data_ptr(), None, None, 0,
-                                       b.runners.SKY_BAND_RAD, 0.0, 3, st))
+            if world == 1:
+                _lib.check(L.bfg_halo_sort(0, n_rec, d_rec.data_ptr(), d_rec_sorted.data_ptr(), None, None, 0,
+                                           b.runners.SKY_BAND_RAD, 0.0, 3, st))
+            else:   # + per-rank compaction: the halos of other ranks go last and end the halo loop
+                _lib.check(L.bfg_halo_sort_owned(nside, lo, hi, n_rec, d_rec.data_ptr(), d_rec_sorted.data_ptr(), None,
+                                                 None, 0, b.runners.SKY_BAND_RAD, st))
             d_use = d_rec_sorted
-            launches[0] += 2
+            launches[0] += 2 if world == 1 else 3   # own kernels only: keys, gather (+ mark); CUB's radix passes not counted
         if timed_kernel is not None:
             timed_kernel[0].record()
         _lib.check(L.bfg_shell_offsets(table.handle, nside, n_rec, d_use.data_ptr(), None, 0, d_off.data_ptr(),

@@ -58,7 +58,8 @@ enum {
     BFG_HS_LNRCOM = 11,                          /* ln R_com, used when BFG_TABLE_RDELTA        BaryonCorrection.py:408 */
     BFG_HS_SCALE = 12,                           /* paint: pixarea*D_j^2 or 1                   HealpixRunner.py:478 */
     BFG_HS_THETA_LL = 13, BFG_HS_PHI_LL = 14,    /* pi/2-radians(dec), radians(ra): fallback    HealpixRunner.py:334 */
-    BFG_HS_RESERVED = 15
+    BFG_HS_SKIP = 15                             /* 0; set != 0 by bfg_halo_sort_owned on the halos of OTHER ranks, which it
+                                                    puts last: the halo-loop kernels stop at the first such record */
 };
 
 /* ---- box (grid / snapshot) halo record ----------------------------------------------------------- */
@@ -227,6 +228,12 @@ int bfg_snap_deposit_ngp(int ndim, int64_t n_part, const double *d_x, const doub
  * of coarse cells per side, ndim = 2|3.  d_out must not alias d_in.  Uses stream-ordered scratch. */
 int bfg_halo_sort(int mode, int64_t n_halo, const double *d_in, double *d_out, const double *d_extras_in,
                   double *d_extras_out, int n_extra, double p0, double p1, int ndim, void *stream);
+
+/* Sky ordering + ownership for ring-range sharding: as mode 0 with band width `band`, and the halos whose disc cannot
+ * touch the RING range [pix_lo, pix_hi) are put LAST with BFG_HS_SKIP set, so bfg_shell_offsets / _paint / _paint_anis
+ * stop at the first of them -- the catalogue is compacted per rank on the device, without a host round trip. */
+int bfg_halo_sort_owned(int nside, int64_t pix_lo, int64_t pix_hi, int64_t n_halo, const double *d_in, double *d_out,
+                        const double *d_extras_in, double *d_extras_out, int n_extra, double band, void *stream);
 
 /* ---- small utilities ------------------------------------------------------------------------------ */
 /* *d_out (one double) = sum of n doubles (mass-conservation assert, HealpixRunner.py:368-370). */
