@@ -55,6 +55,9 @@ _SIGNATURES = {
     "bfg_ipc_export": ([c_ptr, c_ptr], C.c_int),
     "bfg_ipc_import": ([c_ptr, C.POINTER(c_ptr)], C.c_int),
     "bfg_ipc_close": ([c_ptr], C.c_int),
+    "bfg_host_register": ([c_ptr, c_i64], C.c_int),
+    "bfg_host_unregister": ([c_ptr], C.c_int),
+    "bfg_copy_to_host_async": ([c_ptr, c_ptr, c_i64, c_ptr], C.c_int),
     "bfg_grid_offsets": ([c_ptr, C.c_int, c_i64, c_dbl, c_i64, c_ptr, c_ptr, C.c_int, C.c_int, c_ptr, c_i64, c_i64, c_ptr,
                           c_ptr], C.c_int),
     "bfg_grid_paint": ([c_ptr, C.c_int, c_i64, c_dbl, c_dbl, c_i64, c_ptr, c_ptr, C.c_int, C.c_int, c_ptr, c_i64, c_i64,

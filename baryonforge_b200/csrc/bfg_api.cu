@@ -290,3 +290,23 @@ extern "C" int bfg_ipc_close(void *d_peer_ptr) {
     if (d_peer_ptr) BFG_CUDA_OK(cudaIpcCloseMemHandle(d_peer_ptr));
     return BFG_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ shared host maps
+// Page-locks a host range that several processes of the box have mapped (memfd / POSIX shared memory), so each rank
+// can copy its owned slice of a result map straight into ONE host map at full PCIe speed (parallel.SharedHostMaps).
+extern "C" int bfg_host_register(void *h_ptr, int64_t bytes) {
+    BFG_REQUIRE(h_ptr && bytes > 0, "bad argument");
+    BFG_CUDA_OK(cudaHostRegister(h_ptr, (size_t)bytes, cudaHostRegisterPortable));
+    return BFG_OK;
+}
+
+extern "C" int bfg_host_unregister(void *h_ptr) {
+    if (h_ptr) BFG_CUDA_OK(cudaHostUnregister(h_ptr));
+    return BFG_OK;
+}
+
+extern "C" int bfg_copy_to_host_async(void *h_dst, const void *d_src, int64_t bytes, void *stream) {
+    BFG_REQUIRE(bytes >= 0 && (bytes == 0 || (h_dst && d_src)), "bad argument");
+    if (bytes) BFG_CUDA_OK(cudaMemcpyAsync(h_dst, d_src, (size_t)bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return BFG_OK;
+}

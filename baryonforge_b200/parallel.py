@@ -18,7 +18,7 @@ results here are independent of the number of ranks up to fp64 summation order (
 import numpy as np
 
 __all__ = ['pixel_ranges', 'plane_ranges', 'ring_of_pixel', 'halos_touching_pixel_range', 'halos_touching_planes',
-           'reduce_partial_map', 'gather_owned_ranges', 'init_from_env', 'PeerSlices', 'SimpleParallel',
+           'reduce_partial_map', 'gather_owned_ranges', 'init_from_env', 'PeerSlices', 'SharedHostMaps', 'SimpleParallel',
            'SplitJoinParallel', 'snapshot_slab', 'deposit_ngp_all']
 
 
@@ -212,6 +212,85 @@ class PeerSlices(object):
         if self._own is not None:
             L.bfg_shared_free(self._own)
             self._own = None
+
+
+class SharedHostMaps(object):
+    """
+    Result maps in host memory that EVERY process of the box has mapped (memfd, page-locked through bfg_host_register):
+    each rank copies only its owned slice device -> host, in parallel over its own PCIe link, and after a barrier all
+    ranks hold the complete map without a device all-gather and without N full-size D2H copies.  Replaces the parent
+    process summing whole maps returned by pickling (utils/Parallelize.py:315-318).
+
+    A segment is handed out again once the numpy array given to the caller (and every view of it) has been garbage-
+    collected on ALL ranks; acquire() is collective.
+    """
+
+    MAX_SEGMENTS = 6
+
+    def __init__(self, numel, rank, world, device):
+        self.numel, self.rank, self.world, self.device = int(numel), rank, world, device
+        self.segs = []        # dicts: mm (mmap), addr, free (bool, local view)
+
+    def _new_segment(self):
+        import ctypes as C
+        import mmap
+        import os
+        import torch.distributed as dist
+        from . import _lib
+        nbytes = 8 * self.numel
+        info = [None, None]
+        fd = -1
+        if self.rank == 0:
+            fd = os.memfd_create("bfg_b200_map")
+            os.ftruncate(fd, nbytes)
+            info = [os.getpid(), fd]
+        dist.broadcast_object_list(info, src=0)
+        if self.rank != 0:
+            fd = os.open(f"/proc/{info[0]}/fd/{info[1]}", os.O_RDWR)
+        mm = mmap.mmap(fd, nbytes)          # MAP_SHARED; mmap keeps its own duplicate of the descriptor
+        dist.barrier()                      # everybody has opened rank 0's descriptor
+        os.close(fd)
+        addr = C.addressof(C.c_char.from_buffer(mm))
+        _lib.check(_lib.lib().bfg_host_register(addr, nbytes))
+        self.segs.append(dict(mm=mm, addr=addr, free=True))
+        return len(self.segs) - 1
+
+    def acquire(self):
+        """Collective: pick a segment no rank still exposes to its caller; returns (index, host address)."""
+        import torch
+        import torch.distributed as dist
+        flags = torch.zeros(self.MAX_SEGMENTS, dtype=torch.int32, device=torch.device('cuda', self.device))
+        mine = [1 if (i < len(self.segs) and self.segs[i]['free']) else 0 for i in range(self.MAX_SEGMENTS)]
+        flags.copy_(torch.tensor(mine, dtype=torch.int32))
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+        common = flags.cpu().tolist()
+        idx = next((i for i, f in enumerate(common) if f), None)
+        if idx is None:
+            if len(self.segs) >= self.MAX_SEGMENTS:
+                raise RuntimeError(f"{self.MAX_SEGMENTS} result maps of earlier process() calls are still referenced")
+            idx = self._new_segment()
+        self.segs[idx]['free'] = False
+        return idx, self.segs[idx]['addr']
+
+    def export(self, idx, shape=None):
+        """The whole segment as a numpy array; the segment returns to the pool when the array and its views are gone."""
+        import ctypes as C
+        import weakref
+        seg = self.segs[idx]
+        owner = (C.c_double * self.numel).from_buffer(seg['mm'])
+        weakref.finalize(owner, seg.__setitem__, 'free', True)
+        arr = np.frombuffer(owner, dtype=np.float64)
+        return arr if shape is None else arr.reshape(shape)
+
+    def close(self):
+        from . import _lib
+        for seg in self.segs:
+            try:
+                _lib.lib().bfg_host_unregister(seg['addr'])
+                seg['mm'].close()
+            except Exception:
+                pass            # a caller still holds the map: the mapping stays valid until it is dropped
+        self.segs = []
 
 
 # =====================================================================================================================

@@ -215,7 +215,7 @@ class DefaultRunner(object):
     def __getstate__(self):
         d = dict(self.__dict__)
         d['_tables'] = None
-        for k in ('_scratch_inflight', '_peers', '_d_aux', '_spl_cache'):
+        for k in ('_scratch_inflight', '_peers', '_d_aux', '_spl_cache', '_host_maps'):
             d.pop(k, None)
         return d
 
@@ -442,6 +442,21 @@ class BaryonifyShell(DefaultRunner):
             self._peers = (key, PeerSlices(bounds, rank, world, dev.index))
         return self._peers[1]
 
+    def _shared_host(self, npix, peers):
+        """Shared page-locked host maps for the result (parallel.SharedHostMaps); None -> per-rank full-map D2H."""
+        import os
+        if os.environ.get("BFG_HOST_GATHER", "shared") != "shared":
+            return None
+        key = (npix, peers.world, peers.rank)
+        cur = getattr(self, '_host_maps', None)
+        if cur is None or cur[0] != key:
+            if cur is not None and cur[1] is not None:
+                cur[1].close()
+            from .parallel import SharedHostMaps
+            ok = hasattr(os, 'memfd_create')
+            self._host_maps = (key, SharedHostMaps(npix, peers.rank, peers.world, peers.device) if ok else None)
+        return self._host_maps[1]
+
     def offsets_on_device(self):
         """Run the halo loop only; returns (offsets tensor [3, n_local] on the device, n_updates)."""
         torch = _torch()
@@ -506,6 +521,29 @@ class BaryonifyShell(DefaultRunner):
                                                   peers.h_bounds, peers.h_slices, _lib.ptr(d_rem), st))
                 del d_off
                 dist.all_reduce(token)               # ... and every rank's deposits have landed before the gather
+                host = self._shared_host(npix, peers)
+                if host is not None:
+                    # every rank copies ITS slice into one page-locked host map all ranks have mapped: no device
+                    # all-gather, npix*8 bytes over PCIe in total (not per rank), all links in parallel
+                    seg, addr = host.acquire()
+                    _lib.check(L.bfg_copy_to_host_async(addr + 8 * lo, own.data_ptr(), 8 * (hi - lo), st))
+                    d_sums = torch.zeros(2, dtype=torch.float64, device=dev)
+                    _lib.check(L.bfg_sum_f64(own.data_ptr(), hi - lo, _lib.ptr(d_sums), st))
+                    _lib.check(L.bfg_sum_f64(_lib.ptr(d_map), hi - lo, d_sums.data_ptr() + 8, st))
+                    d_cnt = torch.stack([d_n.reshape(()), d_rem.reshape(())])
+                    dist.all_reduce(d_sums)
+                    sums = d_sums.cpu()
+                    cnt = d_cnt.cpu()
+                    torch.cuda.current_stream().synchronize()
+                    dist.barrier()                   # every slice has landed in the shared host map
+                    _give_scratch(getattr(self, '_scratch_inflight', []))
+                    self._scratch_inflight = []
+                    new_sum, old_sum = float(sums[0]), float(sums[1])
+                    self.last_stats = dict(n_updates=int(cnt[0]), new_sum=new_sum, old_sum=old_sum)
+                    self.last_stats_remote = int(cnt[1])
+                    assert np.isclose(new_sum, old_sum), \
+                        "ERROR in pixel regridding, sum(new_map) [%0.14e] != sum(oldmap) [%0.14e]" % (new_sum, old_sum)
+                    return host.export(seg, orig_map.shape)
                 d_new = gather_owned_ranges(own, npix)
                 d_map_sum = d_map.sum().reshape(1)
                 dist.all_reduce(d_map_sum)

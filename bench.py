@@ -345,7 +345,8 @@ def run_b200(args):
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {"value": n_up / float(tt[0]), "unit": "halo-pixel updates/s",
-               "h2d_bytes_per_step": int((hi - lo) * 8 + 6 * n_rec * 8), "d2h_bytes_per_step": int(npix * 8),
+               "h2d_bytes_per_step": int(npix * 8 + world * 6 * n_rec * 8), "d2h_bytes_per_step": int(npix * 8),
+               "bytes_note": "whole job: every rank uploads its map slice + the 6 catalogue columns and downloads its slice of the new map",
                "ms_per_step": 1e3 * float(tt[0]), "host_prep_ms": 1e3 * runner.last_timing.get("host_prep_s", 0.0),
                "host_threads": int(os.environ.get("BFG_HOST_THREADS", min(16, os.cpu_count() or 1))),
                "iter_ms": iter_ms, "phases_ms": {k: round(1e3 * v, 2) for k, v in runner.last_timing.items()},

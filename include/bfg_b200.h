@@ -172,6 +172,13 @@ int bfg_ipc_export(const void *d_ptr, unsigned char *handle64);           /* 64-
 int bfg_ipc_import(const unsigned char *handle64, void **d_peer_ptr);     /* maps a peer's allocation, enables P2P */
 int bfg_ipc_close(void *d_peer_ptr);
 
+/* Page-lock / release a host range shared by the processes of the box (memfd mapping), and a stream-ordered D2H copy into
+ * it: every rank copies its owned slice of a result map into ONE host map (replaces the parent-side `sum(outputs)` of
+ * utils/Parallelize.py:318 and the per-rank full-map D2H). */
+int bfg_host_register(void *h_ptr, int64_t bytes);
+int bfg_host_unregister(void *h_ptr);
+int bfg_copy_to_host_async(void *h_dst, const void *d_src, int64_t bytes, void *stream);
+
 /* ---- periodic grids (2-D / 3-D) ------------------------------------------------------------------- */
 /* Halo loop of BaryonifyGrid.process (Map2DRunner.py:482-586).  d_offsets is [ndim][N^ndim] in units of cells,
  * restricted to axis-0 planes [plane_lo, plane_hi) (slab); NaNs propagate as in the reference.
