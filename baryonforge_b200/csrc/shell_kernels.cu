@@ -143,13 +143,14 @@ __device__ __forceinline__ void shell_update(const TableView &T, const double *_
 struct __align__(16) RingSeg {
     i64 lbase;             // ring's first pixel - pix_lo
     int nr, ip_lo;
-    int cnt, flags;        // flags: 1 = ring straddles the owned pixel range, 2 = equatorial ring (nr = 4 nside)
+    int cnt, flags;        // flags: 1 = ring straddles the owned pixel range, 2 = equatorial ring (nr = 4 nside), 4 = shifted
     int active, pad;
     double z, sth;         // ring z, sin(theta)
     double pz, sD;         // z * D, sin(theta) * D
     double phase0, inv2nr; // azimuth of pixel ip_lo in half-turns, 2 / nr
     double c0, s0;         // cos / sin of phase0 (equatorial rings)
     double rotC, rotS;     // cos / sin of a 32-pixel azimuth step
+    double dz, dz2;        // fast path: z - vz of the halo and its square (unit-sphere chord, see ring_pixels_fast)
 };
 
 template <int MODE, bool UNIFORM, bool CHECK>
@@ -180,6 +181,127 @@ __device__ __forceinline__ void ring_pixels(const TableView &T, const double *__
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Fast pixel loop of the headline case (BaryonifyShell, uniform ln r axis, ring wholly inside the owned range).
+// Same arithmetic as shell_update<MODE_BARYONIFY>, reorganised so that the loop is bounded by the FP64 pipe instead of
+// by instruction issue:
+//   * everything is done on the UNIT sphere: with pos = D vec, the chord is diff = D (vec - vec_j) =: D d, so
+//       ln r_sep = ln D + 0.5 ln |d|^2            (ln D folded into the per-halo table offset)
+//       nw_vec   = normalise(vec + sc d),  sc = displacement a / r_sep = (val a / D) rsqrt(|d|^2)
+//     D drops out of the new direction, and dz = z - vz is a per-ring constant;
+//   * shared memory is addressed with 32-bit shared-window addresses (ld.shared), polynomial constants sit in the
+//     constant bank, rsqrt is MUFU.RSQ64H + one cubic iteration without the denormal/inf slow path (|d|^2 = 0 or a
+//     non-finite value ends up non-finite and is dropped by the same test as before), the invalid-input test of
+//     fast_log2 is subsumed by the table-range test, and a span never wraps (a wrapping ring is walked as two spans).
+// ------------------------------------------------------------------------------------------------------------------
+__constant__ double c_l2p[5] = {0.28853900817779268, -0.36067376022224085, 0.48089834696298783, -0.72134752044448170,
+                                1.4426950408889634};
+
+__device__ __forceinline__ double2 lds_f64x2(unsigned addr) {
+    double2 v;
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+    double v;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+// 1/sqrt(x) for positive normal x (full double precision: MUFU seed 2^-22, one cubic step); x = 0 -> NaN, never trapped
+__device__ __forceinline__ double rsqrt_pos(double x) {
+    double y0;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+    const double e = fma(-x, y0 * y0, 1.0);
+    const double p = fma(e, 0.375, 0.5);
+    return fma(p, y0 * e, y0);
+}
+
+struct FastHalo {
+    double vx, vy;        // halo unit vector (vz enters through RingSeg.dz)
+    double rcut2;         // (model eps * R_com * a / D)^2  on the unit sphere
+    double aD;            // a / D
+    double uA, uB;        // cell coordinate u = log2(|d|^2) * uA + uB   (uB includes ln D and ln(1/a) [- ln R_com])
+    double uMax;          // NR - 1
+    int nrm2;             // NR - 2
+    unsigned row_s, l2_s; // shared-window addresses of the blended row and of the log2 table
+};
+
+__device__ __forceinline__ FastHalo make_fast(const TableView &T, const HaloSph &s, const HaloUpd &u, const double *row,
+                                              const double2 *l2tab) {
+    FastHalo f;
+    f.vx = s.vx; f.vy = s.vy;
+    const double rc = s.rcut * s.a / s.D;
+    f.rcut2 = rc * rc;
+    f.aD = s.a / s.D;
+    f.uA = u.uA;
+    f.uB = fma(2.0 * log2(s.D), u.uA, u.uB);      // log2 r_sep^2 = log2 |d|^2 + 2 log2 D
+    f.uMax = u.uMax;
+    f.nrm2 = T.n[2] - 2;
+    f.row_s = (unsigned)__cvta_generic_to_shared(row);
+    f.l2_s = (unsigned)__cvta_generic_to_shared(l2tab);
+    // Launder the values the compiler could re-derive from kernel parameters through a warp shuffle (every lane holds the
+    // same value): otherwise ptxas rematerialises them INSIDE the pixel loop (LDC + I2F + DMUL + the 6-instruction
+    // generic->shared conversion per pixel) instead of keeping them in registers.
+    f.nrm2 = __shfl_sync(0xffffffffu, f.nrm2, 0);
+    f.row_s = __shfl_sync(0xffffffffu, f.row_s, 0);
+    f.uMax = __shfl_sync(0xffffffffu, f.uMax, 0);
+    f.uA = __shfl_sync(0xffffffffu, f.uA, 0);
+    return f;
+}
+
+// One contiguous span of a ring (no wrap): lane handles pixels p0, p0 + 32, ... < pend;  (cs, sn) = azimuth of *p0.
+// p0 / pend point into component 0 of the offsets; components 1, 2 live nloc8 and 2 nloc8 bytes further.
+// CHECK: the ring straddles the owned pixel range [own_lo, own_hi) (ring-range sharding) -- same arithmetic, so results
+// do not depend on how the map is sharded.
+template <bool CHECK>
+__device__ __forceinline__ void span_pixels_fast(const FastHalo &f, const RingSeg &g, double cs, double sn,
+                                                 double *__restrict__ p0, const double *__restrict__ pend, i64 nloc8,
+                                                 const double *own_lo = nullptr, const double *own_hi = nullptr) {
+    const double z = g.z, sth = g.sth, dz = g.dz, dz2 = g.dz2, rotC = g.rotC, rotS = g.rotS;
+    for (; p0 < pend; p0 += 32) {
+        const double x = sth * cs, y = sth * sn;
+        const double dx = x - f.vx, dy = y - f.vy;
+        const double r2 = fma(dx, dx, fma(dy, dy, dz2));             // |vec - vec_j|^2   HealpixRunner.py:338-341
+        // log2(r2): table-driven, as fast_log2 (the non-normal inputs fall out of the table range below)
+        const int hi = __double2hiint(r2);
+        const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(r2));
+        const double2 t = lds_f64x2(f.l2_s + (((unsigned)hi >> 9) & 0x7f0u));
+        const double fr = fma(m, t.x, -1.0);
+        double p = fma(fr, c_l2p[0], c_l2p[1]);
+        p = fma(fr, p, c_l2p[2]);
+        p = fma(fr, p, c_l2p[3]);
+        p = fma(fr, p, c_l2p[4]);
+        const double ed = __hiloint2double(0x43300000, (hi >> 20) ^ 0x80000000) - 4503601774855167.0;   // e (unbiased)
+        const double l2 = fma(fr, p, t.y) + ed;
+        const double uu = fma(l2, f.uA, f.uB);                       // (ln(r_sep / a) [- ln R_com] - r0) / step
+        int k = __double2int_rd(uu);
+        bool ok = true;
+        if (__builtin_expect((unsigned)k > (unsigned)f.nrm2, 0)) {   // outside the table, or exactly on its last node
+            ok = (uu == f.uMax);
+            k = f.nrm2;
+        }
+        const double tt = uu - (double)k;
+        const unsigned ra = f.row_s + ((unsigned)k << 3);
+        const double v0 = lds_f64(ra);
+        const double val = fma(tt, lds_f64(ra + 8) - v0, v0);        // v0 + t (v1 - v0); non-finite nodes end up dropped below
+        const double sc = (val * f.aD) * rsqrt_pos(r2);              // offset / r_sep   HealpixRunner.py:345-346
+        // BaryonCorrection.py:410-411 zero beyond the model's cut; HealpixRunner.py:347 non-finite -> 0; exact zeros (and
+        // denormal-sized offsets) add nothing: one integer test on the exponent field covers NaN, inf and 0
+        ok = ok && (r2 < f.rcut2) && ((((unsigned)__double2hiint(sc) & 0x7fffffffu) - 1u) < 0x7fefffffu);
+        if (CHECK) ok = ok && (p0 >= own_lo) && (p0 < own_hi);
+        const double nx = fma(sc, dx, x), ny = fma(sc, dy, y), nz = fma(sc, dz, z);      // :350 (direction of nw_pos)
+        const double ninv = rsqrt_pos(fma(nx, nx, fma(ny, ny, nz * nz)));
+        if (ok) {
+            red_add(p0, fma(nx, ninv, -x));                          // :351-355
+            red_add((double *)((char *)p0 + nloc8), fma(ny, ninv, -y));
+            red_add((double *)((char *)p0 + 2 * nloc8), fma(nz, ninv, -z));
+        }
+        const double c2 = cs * rotC - sn * rotS;                     // advance the azimuth by 32 pixels
+        sn = fma(sn, rotC, cs * rotS);
+        cs = c2;
+    }
+}
+
 template <int MODE, bool UNIFORM>
 __global__ void __launch_bounds__(SHELL_THREADS, SHELL_MIN_CTAS)
 k_shell_halos(TableView T, Hpx h, i64 n_halo, const double *__restrict__ halos, const double *__restrict__ extras,
@@ -196,6 +318,8 @@ k_shell_halos(TableView T, Hpx h, i64 n_halo, const double *__restrict__ halos, 
     load_log2_table(l2tab, g_l2tab);   // visible after the first __syncthreads() below
     const int lane = threadIdx.x & 31;
     const i64 nloc = pix_hi - pix_lo;
+    i64 nloc8 = nloc * 8;
+    asm volatile("" : "+l"(nloc8));   // keep the component stride in a register pair (else recomputed per pixel)
     // azimuth of `lane` pixels on an equatorial ring (every equatorial ring has 4 nside pixels): computed once
     double eqC, eqS;
     sincospi((double)lane * (2.0 / (double)h.nl4), &eqS, &eqC);
@@ -224,6 +348,8 @@ k_shell_halos(TableView T, Hpx h, i64 n_halo, const double *__restrict__ halos, 
             valid = valid && valid2;   // a NaN Painting or a NaN Canvas both contribute nothing
             u2 = make_upd(A.T2, s);
         }
+        FastHalo fh;
+        if (MODE == MODE_BARYONIFY && UNIFORM) fh = make_fast(T, s, u, row, l2tab);
         // `if pixind.size < 4` (HealpixRunner.py:333) can only trigger for discs of a few pixels (<= ~12 rings)
         const bool tiny = !PAINT && (s.radius * s.radius * (double)h.npix * 0.25 < 64.0);
 
@@ -272,9 +398,10 @@ k_shell_halos(TableView T, Hpx h, i64 n_halo, const double *__restrict__ halos, 
                         g.active = 1;
                         g.lbase = start - pix_lo;
                         g.nr = (int)nr; g.ip_lo = (int)ip_lo; g.cnt = (int)cnt;
-                        g.flags = ((start < pix_lo || start + nr > pix_hi) ? 1 : 0) | ((nr == h.nl4) ? 2 : 0);
+                        g.flags = ((start < pix_lo || start + nr > pix_hi) ? 1 : 0) | ((nr == h.nl4) ? 2 : 0) | (sh ? 4 : 0);
                         ring_z_sth(h, iz, g.z, g.sth);
                         g.pz = g.z * u.D; g.sD = g.sth * u.D;
+                        g.dz = g.z - s.vz; g.dz2 = g.dz * g.dz;
                         g.inv2nr = 2.0 / (double)nr;
                         g.phase0 = ((double)ip_lo + (sh ? 0.5 : 0.0)) * g.inv2nr;
                         sincospi(g.phase0, &g.s0, &g.c0);
@@ -316,8 +443,29 @@ k_shell_halos(TableView T, Hpx h, i64 n_halo, const double *__restrict__ halos, 
                 } else {
                     sincospi(fma((double)lane, g.inv2nr, g.phase0), &sn, &cs);
                 }
-                if (g.flags & 1) ring_pixels<MODE, UNIFORM, true>(T, row, u, g, cs, sn, lane, out, nloc, l2tab, A, row2, u2);
-                else ring_pixels<MODE, UNIFORM, false>(T, row, u, g, cs, sn, lane, out, nloc, l2tab, A, row2, u2);
+                if (MODE == MODE_BARYONIFY && UNIFORM) {
+                    // span A: [ip_lo, min(ip_lo + cnt, nr)); span B (disc straddles phi = 0): [0, ip_lo + cnt - nr)
+                    const int endA = min(g.ip_lo + cnt, g.nr);
+                    const int endB = g.ip_lo + cnt - g.nr;
+                    double *rb = out + g.lbase;
+                    if (!(g.flags & 1)) {
+                        span_pixels_fast<false>(fh, g, cs, sn, rb + g.ip_lo + lane, rb + endA, nloc8);
+                        if (endB > 0) {
+                            sincospi(((double)lane + ((g.flags & 4) ? 0.5 : 0.0)) * g.inv2nr, &sn, &cs);
+                            span_pixels_fast<false>(fh, g, cs, sn, rb + lane, rb + endB, nloc8);
+                        }
+                    } else {
+                        span_pixels_fast<true>(fh, g, cs, sn, rb + g.ip_lo + lane, rb + endA, nloc8, out, out + nloc);
+                        if (endB > 0) {
+                            sincospi(((double)lane + ((g.flags & 4) ? 0.5 : 0.0)) * g.inv2nr, &sn, &cs);
+                            span_pixels_fast<true>(fh, g, cs, sn, rb + lane, rb + endB, nloc8, out, out + nloc);
+                        }
+                    }
+                } else if (g.flags & 1) {
+                    ring_pixels<MODE, UNIFORM, true>(T, row, u, g, cs, sn, lane, out, nloc, l2tab, A, row2, u2);
+                } else {
+                    ring_pixels<MODE, UNIFORM, false>(T, row, u, g, cs, sn, lane, out, nloc, l2tab, A, row2, u2);
+                }
             }
             __syncthreads();  // before the next chunk overwrites the segments
         }
