@@ -107,6 +107,25 @@ __device__ __forceinline__ void blend_row(const TableView &T, double lnz, double
     const int nc = 1 << (nd - 1);
     const int NR = T.n[2];
     const i64 sr = T.stride[2];
+    if (nd == 3) {   // the common (z, M, r) table: corner rows and weights hoisted out of the radial loop
+        const double *__restrict__ v00 = T.v + (i64)idx[0] * T.stride[0] + (i64)idx[1] * T.stride[1];
+        const double *__restrict__ v01 = v00 + T.stride[1];
+        const double *__restrict__ v10 = v00 + T.stride[0];
+        const double *__restrict__ v11 = v10 + T.stride[1];
+        // itertools.product order (z, M) = (0,0), (0,1), (1,0), (1,1); weight = w_z * w_M, summed in that order
+        const double w00 = (1.0 - tt[0]) * (1.0 - tt[1]), w01 = (1.0 - tt[0]) * tt[1];
+        const double w10 = tt[0] * (1.0 - tt[1]), w11 = tt[0] * tt[1];
+        for (int k = threadIdx.x; k < NR; k += blockDim.x) {
+            const i64 o = (i64)k * sr;
+            double acc = 0.0;
+            acc = acc + __ldg(v00 + o) * w00;
+            acc = acc + __ldg(v01 + o) * w01;
+            acc = acc + __ldg(v10 + o) * w10;
+            acc = acc + __ldg(v11 + o) * w11;
+            row[k] = acc;
+        }
+        return;
+    }
     for (int k = threadIdx.x; k < NR; k += blockDim.x) {
         double acc = 0.0;
         for (int c = 0; c < nc; ++c) {

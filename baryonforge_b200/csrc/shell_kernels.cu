@@ -313,7 +313,6 @@ k_shell_halos(TableView T, Hpx h, i64 n_halo, const double *__restrict__ halos, 
     const double *row2 = row + ((MODE == MODE_ANIS) ? T.n[2] : 0);   // anis: the tracer row follows the paint row
     __shared__ RingSeg segs[RING_CHUNK];
     __shared__ double2 l2tab[BFG_LOG2_TAB];
-    __shared__ int s_next;
     __shared__ int s_cnt[SHELL_THREADS / 32];
     load_log2_table(l2tab, g_l2tab);   // visible after the first __syncthreads() below
     const int lane = threadIdx.x & 31;
@@ -409,17 +408,14 @@ k_shell_halos(TableView T, Hpx h, i64 n_halo, const double *__restrict__ halos, 
                     }
                 }
                 segs[threadIdx.x] = g;
-                if (threadIdx.x == 0) s_next = 0;
             }
             __syncthreads();  // segments + row ready
             const int nseg = (int)min((i64)RING_CHUNK, d.rb - base + 1);
 
             // ---- warps pull ring segments; lanes walk consecutive pixels -------------------------------
-            for (;;) {
-                int r = 0;
-                if (lane == 0) r = atomicAdd(&s_next, 1);
-                r = __shfl_sync(0xffffffffu, r, 0);
-                if (r >= nseg) break;
+            // static round-robin: neighbouring rings have neighbouring lengths, so the 4 warps stay balanced without a
+            // shared work counter (whose atomic + shuffle latency was ~12 % of the kernel's stall samples)
+            for (int r = threadIdx.x >> 5; r < nseg; r += SHELL_THREADS / 32) {
                 const RingSeg &g = segs[r];
                 if (!g.active) continue;
                 const int cnt = g.cnt;
