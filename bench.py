@@ -211,6 +211,9 @@ def run_reference(args):
 # GPU arm
 # ---------------------------------------------------------------------------------------------------------------
 def run_b200(args):
+    # stdout carries exactly ONE JSON line: NCCL's own banner ("NCCL version ...", printed when the box sets NCCL_DEBUG)
+    # goes to stderr instead
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     import torch.distributed as dist
     import baryonforge_b200 as b
