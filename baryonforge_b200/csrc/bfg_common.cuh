@@ -480,6 +480,80 @@ __device__ __forceinline__ double fast_log2(double x, const double2 *__restrict_
     return fma(f, p, t.y) + ed;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Lean building blocks of the pixel / cell / particle loops (the loops sit on the FP64 pipe; everything here exists to
+// keep non-FP64 instructions out of them): polynomial constants in the constant bank, shared memory addressed by
+// 32-bit shared-window addresses, reciprocal square root without the denormal / inf slow path.
+// ------------------------------------------------------------------------------------------------
+static __constant__ double c_l2p[5] = {0.28853900817779268, -0.36067376022224085, 0.48089834696298783, -0.72134752044448170,
+                                1.4426950408889634};
+
+__device__ __forceinline__ double2 lds_f64x2(unsigned addr) {
+    double2 v;
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+    double v;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+// 1/sqrt(x) for positive normal x (full double precision: MUFU seed 2^-22, one cubic step); x = 0 -> NaN, never trapped
+__device__ __forceinline__ double rsqrt_pos(double x) {
+    double y0;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+    const double e = fma(-x, y0 * y0, 1.0);
+    const double p = fma(e, 0.375, 0.5);
+    return fma(p, y0 * e, y0);
+}
+
+
+// Per-halo constants of a read-out by SQUARED radius from a blended row with a uniform ln r axis:
+//   cell coordinate u = log2(r^2) * uA + uB,  uA = 0.5 ln2 / step,  uB = (offset - r0) / step.
+struct RowLookup {
+    double uA, uB, uMax;   // uMax = NR - 1
+    int nrm2;              // NR - 2
+    unsigned row_s, l2_s;  // shared-window addresses of the blended row and of the log2 table
+};
+
+// Launder values the compiler could re-derive from kernel parameters through a warp shuffle (every lane holds the same
+// value): otherwise ptxas rematerialises them INSIDE the inner loop (LDC + I2F + DMUL + the 6-instruction
+// generic->shared conversion per element) instead of keeping them in registers.
+__device__ __forceinline__ void launder(RowLookup &f) {
+    f.nrm2 = __shfl_sync(0xffffffffu, f.nrm2, 0);
+    f.row_s = __shfl_sync(0xffffffffu, f.row_s, 0);
+    f.l2_s = __shfl_sync(0xffffffffu, f.l2_s, 0);
+    f.uMax = __shfl_sync(0xffffffffu, f.uMax, 0);
+    f.uA = __shfl_sync(0xffffffffu, f.uA, 0);
+}
+
+// Table value at squared radius r2: v0 + t (v1 - v0) in the cell of u (scipy's (1-t) v0 + t v1 up to round-off; a
+// non-finite node makes the result non-finite either way).  ok = false outside [r0, r1] (scipy: fill_value = nan);
+// r2 = 0, inf, NaN fall outside.  log2 is the table-driven one of fast_log2 without its input test.
+__device__ __forceinline__ double row_at_r2(const RowLookup &f, double r2, bool &ok) {
+    const int hi = __double2hiint(r2);
+    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(r2));
+    const double2 t = lds_f64x2(f.l2_s + (((unsigned)hi >> 9) & 0x7f0u));
+    const double fr = fma(m, t.x, -1.0);
+    double p = fma(fr, c_l2p[0], c_l2p[1]);
+    p = fma(fr, p, c_l2p[2]);
+    p = fma(fr, p, c_l2p[3]);
+    p = fma(fr, p, c_l2p[4]);
+    const double ed = __hiloint2double(0x43300000, (hi >> 20) ^ 0x80000000) - 4503601774855167.0;   // unbiased exponent
+    const double l2 = fma(fr, p, t.y) + ed;
+    const double uu = fma(l2, f.uA, f.uB);
+    int k = __double2int_rd(uu);
+    ok = true;
+    if (__builtin_expect((unsigned)k > (unsigned)f.nrm2, 0)) {   // outside the table, or exactly on its last node
+        ok = (uu == f.uMax);
+        k = f.nrm2;
+    }
+    const double tt = uu - (double)k;
+    const unsigned ra = f.row_s + ((unsigned)k << 3);
+    const double v0 = lds_f64(ra);
+    return fma(tt, lds_f64(ra + 8) - v0, v0);
+}
+
 // fp64 RED (no return value): RED.E.ADD.F64 on sm_100a
 __device__ __forceinline__ void red_add(double *addr, double v) { atomicAdd(addr, v); }
 

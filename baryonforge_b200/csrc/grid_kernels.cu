@@ -76,6 +76,8 @@ k_grid_halos(TableView T, int N, double res, double scale, i64 n_halo, const dou
     load_log2_table(l2tab, g_l2tab);
     const i64 plane = (NDIM == 3) ? (i64)N * N : (i64)N;       // cells per axis-0 plane
     const i64 nloc = (i64)(plane_hi - plane_lo) * plane;
+    i64 nloc8 = nloc * 8;
+    nloc8 = ((i64)__shfl_sync(0xffffffffu, (int)(nloc8 >> 32), 0) << 32) | (unsigned)__shfl_sync(0xffffffffu, (int)nloc8, 0);
     const double inv_res = 1.0 / res;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int NW = GRID_THREADS / 32;
@@ -90,6 +92,18 @@ k_grid_halos(TableView T, int N, double res, double scale, i64 n_halo, const dou
         __syncthreads();
         const int ns = b.nsize, cw = ns / 2;
         const double cut2 = PAINT ? b.paintcut * b.paintcut : b.rcut * b.rcut;
+        // lean read-out (uniform ln r axis): cell coordinate u = log2(r^2) * uA + uB, see row_at_r2
+        constexpr bool LEAN = (MODE == MODE_BARYONIFY) && UNIFORM;
+        RowLookup rl;
+        if (LEAN) {
+            rl.uA = 0.34657359027997264 * T.inv_dr;
+            rl.uB = (((T.flags & BFG_TABLE_RDELTA) ? -b.lnRcom : 0.0) - T.r0) * T.inv_dr;
+            rl.uMax = (double)(T.n[2] - 1);
+            rl.nrm2 = T.n[2] - 2;
+            rl.row_s = (unsigned)__cvta_generic_to_shared(row);
+            rl.l2_s = (unsigned)__cvta_generic_to_shared(l2tab);
+            launder(rl);
+        }
         double R00 = 1.0, R01 = 0.0, R10 = 0.0, R11 = 1.0;
         if (ELL) {
             const double *e = extras + h * n_extra + (n_extra - 4);
@@ -120,6 +134,22 @@ k_grid_halos(TableView T, int N, double res, double scale, i64 n_halo, const dou
                 if (ELL) {
                     const double ex = gx * R00 + gy * R10, ey = gx * R01 + gy * R11;   // (x, y) @ Rmat
                     rt2 = ex * ex + ey * ey;
+                }
+                if (LEAN) {
+                    // BaryonifyGrid, uniform ln r: FP64-lean update (same arithmetic as the generic branch below up to
+                    // round-off; NaN / inf offsets propagate and are cleaned after the loop, Map2DRunner.py:597/:607)
+                    bool ok;
+                    double val = row_at_r2(rl, rt2, ok);
+                    if (!ok || !valid) val = CUDART_NAN;                          // outside the table: fill_value = nan
+                    if (!(rt2 < cut2)) val = 0.0;                                 // BaryonCorrection.py:410-411
+                    ++done;
+                    const double sc = (val * inv_res) * rsqrt_pos(r2);            // offset / res / r   (:540/:583)
+                    if (sc == 0.0) continue;                                      // exact zeros add nothing
+                    double *q = out + cell;
+                    red_add(q, sc * gx);
+                    red_add((double *)((char *)q + nloc8), sc * gy);
+                    if (NDIM == 3) red_add((double *)((char *)q + 2 * nloc8), sc * gl);
+                    continue;
                 }
                 double xq = fast_log2(rt2, l2tab) * 0.34657359027997264;          // ln r = 0.5 ln2 log2(r^2)
                 if (T.flags & BFG_TABLE_RDELTA) xq -= b.lnRcom;

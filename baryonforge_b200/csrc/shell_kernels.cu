@@ -194,36 +194,11 @@ __device__ __forceinline__ void ring_pixels(const TableView &T, const double *__
 //     non-finite value ends up non-finite and is dropped by the same test as before), the invalid-input test of
 //     fast_log2 is subsumed by the table-range test, and a span never wraps (a wrapping ring is walked as two spans).
 // ------------------------------------------------------------------------------------------------------------------
-__constant__ double c_l2p[5] = {0.28853900817779268, -0.36067376022224085, 0.48089834696298783, -0.72134752044448170,
-                                1.4426950408889634};
-
-__device__ __forceinline__ double2 lds_f64x2(unsigned addr) {
-    double2 v;
-    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ double lds_f64(unsigned addr) {
-    double v;
-    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
-    return v;
-}
-// 1/sqrt(x) for positive normal x (full double precision: MUFU seed 2^-22, one cubic step); x = 0 -> NaN, never trapped
-__device__ __forceinline__ double rsqrt_pos(double x) {
-    double y0;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
-    const double e = fma(-x, y0 * y0, 1.0);
-    const double p = fma(e, 0.375, 0.5);
-    return fma(p, y0 * e, y0);
-}
-
 struct FastHalo {
     double vx, vy;        // halo unit vector (vz enters through RingSeg.dz)
     double rcut2;         // (model eps * R_com * a / D)^2  on the unit sphere
     double aD;            // a / D
-    double uA, uB;        // cell coordinate u = log2(|d|^2) * uA + uB   (uB includes ln D and ln(1/a) [- ln R_com])
-    double uMax;          // NR - 1
-    int nrm2;             // NR - 2
-    unsigned row_s, l2_s; // shared-window addresses of the blended row and of the log2 table
+    RowLookup t;          // cell coordinate u = log2(|d|^2) * uA + uB   (uB includes ln D and ln(1/a) [- ln R_com])
 };
 
 __device__ __forceinline__ FastHalo make_fast(const TableView &T, const HaloSph &s, const HaloUpd &u, const double *row,
@@ -233,19 +208,13 @@ __device__ __forceinline__ FastHalo make_fast(const TableView &T, const HaloSph 
     const double rc = s.rcut * s.a / s.D;
     f.rcut2 = rc * rc;
     f.aD = s.a / s.D;
-    f.uA = u.uA;
-    f.uB = fma(2.0 * log2(s.D), u.uA, u.uB);      // log2 r_sep^2 = log2 |d|^2 + 2 log2 D
-    f.uMax = u.uMax;
-    f.nrm2 = T.n[2] - 2;
-    f.row_s = (unsigned)__cvta_generic_to_shared(row);
-    f.l2_s = (unsigned)__cvta_generic_to_shared(l2tab);
-    // Launder the values the compiler could re-derive from kernel parameters through a warp shuffle (every lane holds the
-    // same value): otherwise ptxas rematerialises them INSIDE the pixel loop (LDC + I2F + DMUL + the 6-instruction
-    // generic->shared conversion per pixel) instead of keeping them in registers.
-    f.nrm2 = __shfl_sync(0xffffffffu, f.nrm2, 0);
-    f.row_s = __shfl_sync(0xffffffffu, f.row_s, 0);
-    f.uMax = __shfl_sync(0xffffffffu, f.uMax, 0);
-    f.uA = __shfl_sync(0xffffffffu, f.uA, 0);
+    f.t.uA = u.uA;
+    f.t.uB = fma(2.0 * log2(s.D), u.uA, u.uB);      // log2 r_sep^2 = log2 |d|^2 + 2 log2 D
+    f.t.uMax = u.uMax;
+    f.t.nrm2 = T.n[2] - 2;
+    f.t.row_s = (unsigned)__cvta_generic_to_shared(row);
+    f.t.l2_s = (unsigned)__cvta_generic_to_shared(l2tab);
+    launder(f.t);
     return f;
 }
 
@@ -262,28 +231,8 @@ __device__ __forceinline__ void span_pixels_fast(const FastHalo &f, const RingSe
         const double x = sth * cs, y = sth * sn;
         const double dx = x - f.vx, dy = y - f.vy;
         const double r2 = fma(dx, dx, fma(dy, dy, dz2));             // |vec - vec_j|^2   HealpixRunner.py:338-341
-        // log2(r2): table-driven, as fast_log2 (the non-normal inputs fall out of the table range below)
-        const int hi = __double2hiint(r2);
-        const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(r2));
-        const double2 t = lds_f64x2(f.l2_s + (((unsigned)hi >> 9) & 0x7f0u));
-        const double fr = fma(m, t.x, -1.0);
-        double p = fma(fr, c_l2p[0], c_l2p[1]);
-        p = fma(fr, p, c_l2p[2]);
-        p = fma(fr, p, c_l2p[3]);
-        p = fma(fr, p, c_l2p[4]);
-        const double ed = __hiloint2double(0x43300000, (hi >> 20) ^ 0x80000000) - 4503601774855167.0;   // e (unbiased)
-        const double l2 = fma(fr, p, t.y) + ed;
-        const double uu = fma(l2, f.uA, f.uB);                       // (ln(r_sep / a) [- ln R_com] - r0) / step
-        int k = __double2int_rd(uu);
-        bool ok = true;
-        if (__builtin_expect((unsigned)k > (unsigned)f.nrm2, 0)) {   // outside the table, or exactly on its last node
-            ok = (uu == f.uMax);
-            k = f.nrm2;
-        }
-        const double tt = uu - (double)k;
-        const unsigned ra = f.row_s + ((unsigned)k << 3);
-        const double v0 = lds_f64(ra);
-        const double val = fma(tt, lds_f64(ra + 8) - v0, v0);        // v0 + t (v1 - v0); non-finite nodes end up dropped below
+        bool ok;
+        const double val = row_at_r2(f.t, r2, ok);                   // :345 via ln(r_sep / a) [- ln R_com], no sqrt / division
         const double sc = (val * f.aD) * rsqrt_pos(r2);              // offset / r_sep   HealpixRunner.py:345-346
         // BaryonCorrection.py:410-411 zero beyond the model's cut; HealpixRunner.py:347 non-finite -> 0; exact zeros (and
         // denormal-sized offsets) add nothing: one integer test on the exponent field covers NaN, inf and 0

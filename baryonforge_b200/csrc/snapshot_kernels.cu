@@ -38,19 +38,31 @@ __global__ void k_cell_count(i64 n, const double *__restrict__ x, const double *
     }
 }
 
+// Scatter stage of the counting sort.  A particle is moved as ONE 32-byte record {x, y, z, original index}: the scattered
+// write then covers exactly one full DRAM sector (4 separate 8-byte writes to 4 arrays cost 4 partial sectors and ran at
+// a fifth of the HBM rate).  k_unpack_records turns the records back into the SoA arrays with coalesced traffic.
 template <int NDIM>
 __global__ void k_cell_fill(i64 n, const double *__restrict__ x, const double *__restrict__ y,
                             const double *__restrict__ z, const int *__restrict__ cell_id,
                             const i64 *__restrict__ cell_start, unsigned long long *__restrict__ cursor,
-                            i64 *__restrict__ order, double *__restrict__ xs, double *__restrict__ ys,
-                            double *__restrict__ zs) {
+                            double4 *__restrict__ rec) {
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
         int c = cell_id[i];
         i64 slot = cell_start[c] + (i64)atomicAdd(cursor + c, 1ULL);
-        order[slot] = i;
-        xs[slot] = x[i];
-        ys[slot] = y[i];
-        if (NDIM == 3) zs[slot] = z[i];
+        double4 r;
+        r.x = x[i]; r.y = y[i]; r.z = (NDIM == 3) ? z[i] : 0.0; r.w = __longlong_as_double(i);
+        rec[slot] = r;
+    }
+}
+
+template <int NDIM>
+__global__ void k_unpack_records(i64 n, const double4 *__restrict__ rec, i64 *__restrict__ order,
+                                 double *__restrict__ xs, double *__restrict__ ys, double *__restrict__ zs) {
+    for (i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (i64)gridDim.x * blockDim.x) {
+        const double4 r = rec[p];
+        xs[p] = r.x; ys[p] = r.y;
+        if (NDIM == 3) zs[p] = r.z;
+        if (order) order[p] = __double_as_longlong(r.w);
     }
 }
 
@@ -89,6 +101,16 @@ k_snap_halos(TableView T, double L, int nc, const double *__restrict__ xs, const
         blend_row(T, s.lnz, s.lnM, extras ? extras + h * n_extra : nullptr, row, valid);
         __syncthreads();
         const double rq2 = s.rq * s.rq, rcut2 = s.rcut * s.rcut;
+        RowLookup rl;
+        if (UNIFORM) {   // lean read-out: cell coordinate u = log2(d^2) * uA + uB (row_at_r2)
+            rl.uA = 0.34657359027997264 * T.inv_dr;
+            rl.uB = (((T.flags & BFG_TABLE_RDELTA) ? -s.lnRcom : 0.0) - T.r0) * T.inv_dr;
+            rl.uMax = (double)(T.n[2] - 1);
+            rl.nrm2 = T.n[2] - 2;
+            rl.row_s = (unsigned)__cvta_generic_to_shared(row);
+            rl.l2_s = (unsigned)__cvta_generic_to_shared(l2tab);
+            launder(rl);
+        }
         // cells covering [c - rq, c + rq] per axis (periodic); never more than nc of them
         int lo[3], cnt[3];
         for (int d = 0; d < 3; ++d) {
@@ -127,14 +149,21 @@ k_snap_halos(TableView T, double L, int nc, const double *__restrict__ xs, const
                 double d2 = (NDIM == 3) ? dx * dx + dy * dy + dz * dz : dx * dx + dy * dy;
                 if (!(d2 <= rq2)) continue;                    // query_ball_point: d <= R_q, inclusive  (:232/:247)
                 ++done;
-                double xq = fast_log2(d2, l2tab) * 0.34657359027997264;   // ln d = 0.5 ln2 log2(d^2)
-                if (T.flags & BFG_TABLE_RDELTA) xq -= s.lnRcom;
-                double val = row_lookup<UNIFORM>(T, row, xq);
+                double val;
+                if (UNIFORM) {
+                    bool ok;
+                    val = row_at_r2(rl, d2, ok);
+                    if (!ok) val = CUDART_NAN;
+                } else {
+                    double xq = fast_log2(d2, l2tab) * 0.34657359027997264;   // ln d = 0.5 ln2 log2(d^2)
+                    if (T.flags & BFG_TABLE_RDELTA) xq -= s.lnRcom;
+                    val = row_lookup<false>(T, row, xq);
+                }
                 if (!valid) val = CUDART_NAN;
                 val = (d2 < rcut2) ? val : 0.0;                // BaryonCorrection.py:410-411
                 if (!isfinite(val)) val = 0.0;                 // SnapshotRunner.py:259
                 if (val == 0.0 && d2 > 0.0) continue;          // adds exact zeros
-                const double sc = val * rsqrt(d2);             // d == 0 -> 0 * inf = NaN, as in the reference (§10 #11)
+                const double sc = val * rsqrt_pos(d2);         // d == 0 -> NaN, as in the reference's 0/0 (§10 #11)
                 red_add(tot + p, sc * dx);                     // :260
                 red_add(tot + n_part + p, sc * dy);
                 if (NDIM == 3) red_add(tot + 2 * n_part + p, sc * dz);
@@ -153,16 +182,19 @@ __device__ __forceinline__ double wrap_once(double q, double L) {   // SnapshotR
     return q;
 }
 
+// Displaced position of every particle, scattered back to the caller's order as one full-sector 32-byte record; then
+// k_unpack_records writes the three output arrays coalesced.
 template <int NDIM>
 __global__ void k_snap_apply(i64 n, const double *__restrict__ xs, const double *__restrict__ ys,
                              const double *__restrict__ zs, const double *__restrict__ tot,
-                             const i64 *__restrict__ order, double L, double *__restrict__ xo, double *__restrict__ yo,
-                             double *__restrict__ zo) {
+                             const i64 *__restrict__ order, double L, double4 *__restrict__ rec) {
     for (i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (i64)gridDim.x * blockDim.x) {
-        i64 i = order[p];
-        xo[i] = wrap_once(xs[p] + tot[p], L);
-        yo[i] = wrap_once(ys[p] + tot[n + p], L);
-        if (NDIM == 3) zo[i] = wrap_once(zs[p] + tot[2 * n + p], L);
+        double4 r;
+        r.x = wrap_once(xs[p] + tot[p], L);
+        r.y = wrap_once(ys[p] + tot[n + p], L);
+        r.z = (NDIM == 3) ? wrap_once(zs[p] + tot[2 * n + p], L) : 0.0;
+        r.w = 0.0;
+        rec[order[p]] = r;
     }
 }
 
@@ -223,9 +255,17 @@ extern "C" int bfg_snap_build_cells(int ndim, int64_t n_part, const double *d_x,
     BFG_CUDA_OK(cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, (const i64 *)counts, (i64 *)d_cell_start, ncells + 1, st));
     BFG_CUDA_OK(cudaMemsetAsync(counts, 0, sizeof(unsigned long long) * (ncells + 1), st));
     if (n_part > 0) {
-        if (ndim == 3) k_cell_fill<3><<<blocks_for(n_part, 256), 256, 0, st>>>(n_part, d_x, d_y, d_z, cell_id, (const i64 *)d_cell_start, counts, (i64 *)d_order, d_xs, d_ys, d_zs);
-        else k_cell_fill<2><<<blocks_for(n_part, 256), 256, 0, st>>>(n_part, d_x, d_y, d_z, cell_id, (const i64 *)d_cell_start, counts, (i64 *)d_order, d_xs, d_ys, d_zs);
+        double4 *rec = nullptr;   // 32-byte particle records (stream-ordered scratch)
+        BFG_CUDA_OK(cudaMallocAsync(&rec, sizeof(double4) * n_part, st));
+        if (ndim == 3) {
+            k_cell_fill<3><<<blocks_for(n_part, 256), 256, 0, st>>>(n_part, d_x, d_y, d_z, cell_id, (const i64 *)d_cell_start, counts, rec);
+            k_unpack_records<3><<<blocks_for(n_part, 256), 256, 0, st>>>(n_part, rec, (i64 *)d_order, d_xs, d_ys, d_zs);
+        } else {
+            k_cell_fill<2><<<blocks_for(n_part, 256), 256, 0, st>>>(n_part, d_x, d_y, d_z, cell_id, (const i64 *)d_cell_start, counts, rec);
+            k_unpack_records<2><<<blocks_for(n_part, 256), 256, 0, st>>>(n_part, rec, (i64 *)d_order, d_xs, d_ys, d_zs);
+        }
         BFG_CUDA_OK(cudaGetLastError());
+        BFG_CUDA_OK(cudaFreeAsync(rec, st));
     }
     BFG_CUDA_OK(cudaFreeAsync(scan_tmp, st));
     BFG_CUDA_OK(cudaFreeAsync(counts, st));
@@ -269,9 +309,18 @@ extern "C" int bfg_snap_apply(int ndim, int64_t n_part, const double *d_xs, cons
     BFG_REQUIRE(d_xs && d_ys && d_tot && d_order && d_x_out && d_y_out && (ndim == 2 || (d_zs && d_z_out)), "null argument");
     if (n_part == 0) return BFG_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    if (ndim == 3) k_snap_apply<3><<<blocks_for(n_part, 256), 256, 0, st>>>(n_part, d_xs, d_ys, d_zs, d_tot, (const i64 *)d_order, L, d_x_out, d_y_out, d_z_out);
-    else k_snap_apply<2><<<blocks_for(n_part, 256), 256, 0, st>>>(n_part, d_xs, d_ys, d_zs, d_tot, (const i64 *)d_order, L, d_x_out, d_y_out, d_z_out);
+    if (int rc = retain_async_pool()) return rc;
+    double4 *rec = nullptr;
+    BFG_CUDA_OK(cudaMallocAsync(&rec, sizeof(double4) * n_part, st));
+    if (ndim == 3) {
+        k_snap_apply<3><<<blocks_for(n_part, 256), 256, 0, st>>>(n_part, d_xs, d_ys, d_zs, d_tot, (const i64 *)d_order, L, rec);
+        k_unpack_records<3><<<blocks_for(n_part, 256), 256, 0, st>>>(n_part, rec, nullptr, d_x_out, d_y_out, d_z_out);
+    } else {
+        k_snap_apply<2><<<blocks_for(n_part, 256), 256, 0, st>>>(n_part, d_xs, d_ys, d_zs, d_tot, (const i64 *)d_order, L, rec);
+        k_unpack_records<2><<<blocks_for(n_part, 256), 256, 0, st>>>(n_part, rec, nullptr, d_x_out, d_y_out, d_z_out);
+    }
     BFG_CUDA_OK(cudaGetLastError());
+    BFG_CUDA_OK(cudaFreeAsync(rec, st));
     return BFG_OK;
 }
 
