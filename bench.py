@@ -52,6 +52,9 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-sort", action="store_true", help="skip the device-side sky ordering of halos (L2 locality)")
     ap.add_argument("--mass-function", action="store_true", help="steeper dn/dlogM ~ M^-0.9 catalogue variant")
+    ap.add_argument("--no-particles", action="store_true",
+                    help="skip the secondary metric (BaryonifySnapshot particles displaced/s, weak scaling)")
+    ap.add_argument("--particles-per-gpu", type=int, default=250000000)
     return ap.parse_args()
 
 
@@ -358,6 +361,31 @@ def run_b200(args):
                "iter_ms": iter_ms, "phases_ms": {k: round(1e3 * v, 2) for k, v in runner.last_timing.items()},
                "includes": "host staging of raw catalogue columns + numpy ln(1+z), ln M; H2D (pinned map + 6 columns); device scalar prep, sort, halo loop, re-binning, exchange (N>1); D2H of the new map"}
 
+    # ---- secondary metric of BASELINE.json: particles displaced/s (BaryonifySnapshot + NGP deposit) ---------------
+    # weak scaling: every rank owns one x-slab share of the 2e9-particle box (configs[3]: 2.5e8 particles per GPU at N = 8)
+    particles = None
+    if not args.no_particles:
+        del d_off, d_new, d_map, d_rec_sorted
+        torch.cuda.empty_cache()
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_configs
+        pk, _ = peaks()
+        barrier()
+        c4 = bench_configs.snapshot_pipeline(args.particles_per_gpu, 5.0, local, 2, pk)
+        tot_ms = c4["build_cells_ms"] + c4["halo_loop_ms"] + c4["apply_deposit_ms"]
+        tp = torch.tensor([tot_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+        particles = {"metric": "particles displaced/s (BaryonifySnapshot + NGP deposit)",
+                     "value": world * args.particles_per_gpu / (float(tp[0]) * 1e-3), "unit": "particles/s",
+                     "scaling": "weak", "ms_per_pass": float(tp[0]),
+                     "config": {"workload": f"BaryonifySnapshot {args.particles_per_gpu} particles per GPU (uniform, L = "
+                                            f"{c4['L']:.0f} Mpc slab share of 2e9 in (1000 Mpc)^3), {c4['halos']} halos per GPU, "
+                                            f"epsilon_max=5, cell list {c4['ncell']}^3, NGP deposit 512^3; device-resident, "
+                                            "CUDA events, max over ranks"},
+                     "phases_ms_rank0": {k: c4[k] for k in ("build_cells_ms", "halo_loop_ms", "apply_deposit_ms")},
+                     "pairs_per_s_rank0": c4["pairs_per_s"], "halo_loop_alg_frac_rank0": c4["halo_loop_frac"]}
+
     if world > 1:
         dist.barrier()
     if rank != 0:
@@ -389,7 +417,7 @@ def run_b200(args):
                                  "sky-ordered halos ~93 % of those REDs are absorbed by the 126 MB L2 (ncu traffic 60.5 GB vs "
                                  "852 GB algorithmic), so frac can exceed 1 and the kernel's real limiter is the FP64 pipe "
                                  "(50.6 % active, 45 FP64 instructions per update) + issue slots (67.5 %); see profiles/README.md"},
-            "e2e": e2e}
+            "e2e": e2e, "particles": particles}
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, cat, model, axes, vals, args.cpu_sample)
     print(json.dumps(line))

@@ -31,6 +31,76 @@ def events(fn, warm=1, reps=3):
     return float(np.median(ts))
 
 
+def snapshot_pipeline(n_part, snap_eps=5.0, device=0, reps=2, peak=6650.0):
+    """
+    C4 (one GPU's share): BaryonifySnapshot on n_part uniform particles + halos at the number density of 3e6 per
+    (1000 Mpc)^3 (M = 10^U(12,15.5)), then the NGP deposit -- cell list, halo loop, apply + un-permute, deposit, all through
+    the C ABI with device-resident inputs.  Returns per-phase CUDA-event times and particles/s.
+    """
+    import torch
+    import baryonforge_b200 as b
+    from baryonforge_b200 import _lib, synth
+    from baryonforge_b200.runners import _upload_records, _sort_records
+    from baryonforge_b200.tables import displacement_table_of
+    L = _lib.lib()
+    dev = torch.device("cuda", device)
+    st = torch.cuda.current_stream().cuda_stream
+    n_part = int(n_part)
+    dens = 2e9 / 1000.0 ** 3
+    Lbox = (n_part / dens) ** (1 / 3.)
+    n_halo = int(3e6 * (Lbox / 1000.0) ** 3)
+    pos, M = synth.box_halos(n_halo, Lbox, seed=42)
+    gaxes = synth.table_axes(nz=10, nM=10, nr=500, z_min=0.0, z_max=1.0, z_linear=True, r_min=1e-3, r_max=3e2)
+    model = b.DisplacementModel(gaxes, synth.displacement_values(gaxes), snap_eps, synth.COSMO)
+    cat = b.HaloNDCatalog(x=pos[0], y=pos[1], z=pos[2], M=M, redshift=0.3, cosmo=synth.COSMO)
+    ps = b.ParticleSnapshot(x=np.zeros(1), y=np.zeros(1), z=np.zeros(1), M=1.0, L=Lbox, redshift=0.3, cosmo=synth.COSMO)
+    run = b.BaryonifySnapshot(cat, ps, snap_eps, model, verbose=False)
+    rec, _ = run.halo_records()
+    ncell = run._pick_ncell(rec[:, _lib.HB_RQ], n_part, 3, Lbox)
+    tab = displacement_table_of(model, device)
+    d_rec = _upload_records(rec, dev)
+    d_rec, _ = _sort_records(d_rec, None, 1, Lbox, 16, 3)
+    g = torch.Generator(device=dev); g.manual_seed(1)
+    d_p = [torch.rand(n_part, dtype=torch.float64, device=dev, generator=g) * Lbox for _ in range(3)]
+    d_s = [torch.empty(n_part, dtype=torch.float64, device=dev) for _ in range(3)]
+    d_start = torch.empty(ncell ** 3 + 1, dtype=torch.int64, device=dev)
+    d_order = torch.empty(n_part, dtype=torch.int64, device=dev)
+    d_tot = torch.zeros((3, n_part), dtype=torch.float64, device=dev)
+    d_n = torch.zeros(1, dtype=torch.int64, device=dev)
+    d_m = torch.ones(n_part, dtype=torch.float64, device=dev)
+    Ng = 512
+    d_grid = torch.zeros(Ng ** 3, dtype=torch.float64, device=dev)
+
+    def build():
+        _lib.check(L.bfg_snap_build_cells(3, n_part, d_p[0].data_ptr(), d_p[1].data_ptr(), d_p[2].data_ptr(), Lbox, ncell,
+                                          d_start.data_ptr(), d_order.data_ptr(), d_s[0].data_ptr(), d_s[1].data_ptr(),
+                                          d_s[2].data_ptr(), st))
+
+    def halos():
+        d_tot.zero_()
+        _lib.check(L.bfg_snap_offsets(tab.handle, 3, n_part, d_s[0].data_ptr(), d_s[1].data_ptr(), d_s[2].data_ptr(), Lbox,
+                                      ncell, d_start.data_ptr(), n_halo, d_rec.data_ptr(), None, 0, d_tot.data_ptr(),
+                                      d_n.data_ptr(), st))
+    d_o = [torch.empty(n_part, dtype=torch.float64, device=dev) for _ in range(3)]
+
+    def apply_dep():
+        _lib.check(L.bfg_snap_apply(3, n_part, d_s[0].data_ptr(), d_s[1].data_ptr(), d_s[2].data_ptr(), d_tot.data_ptr(),
+                                    d_order.data_ptr(), Lbox, d_o[0].data_ptr(), d_o[1].data_ptr(), d_o[2].data_ptr(), st))
+        d_grid.zero_()
+        _lib.check(L.bfg_snap_deposit_ngp(3, n_part, d_o[0].data_ptr(), d_o[1].data_ptr(), d_o[2].data_ptr(), d_m.data_ptr(),
+                                          Lbox, Ng, d_grid.data_ptr(), st))
+    ms_b = events(build, warm=1, reps=reps)
+    ms_h = events(halos, warm=1, reps=reps)
+    ms_a = events(apply_dep, warm=1, reps=reps)
+    npairs = int(d_n.cpu()[0])
+    tot_ms = ms_b + ms_h + ms_a
+    return dict(n_part=n_part, L=Lbox, halos=n_halo, ncell=ncell, eps=snap_eps, pairs=npairs,
+                              build_cells_ms=ms_b, halo_loop_ms=ms_h, apply_deposit_ms=ms_a,
+                              particles_per_s=n_part / tot_ms * 1e3, pairs_per_s=npairs / ms_h * 1e3,
+                              halo_loop_alg_GBs=72 * npairs / ms_h / 1e6, halo_loop_frac=72 * npairs / ms_h / 1e6 / peak,
+                              deposited_mass=float(d_grid.sum().item()))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--which", default="c2,c3,c4")
@@ -121,60 +191,8 @@ def main():
         del d_off, d_map, d_new
 
     if "c4" in args.which:
-        n_part = args.npart
-        dens = 2e9 / 1000.0 ** 3
-        Lbox = (n_part / dens) ** (1 / 3.)
-        n_halo = int(3e6 * (Lbox / 1000.0) ** 3)
-        pos, M = synth.box_halos(n_halo, Lbox, seed=42)
-        gaxes = synth.table_axes(nz=10, nM=10, nr=500, z_min=0.0, z_max=1.0, z_linear=True, r_min=1e-3, r_max=3e2)
-        model = b.DisplacementModel(gaxes, synth.displacement_values(gaxes), args.snap_eps, synth.COSMO)
-        cat = b.HaloNDCatalog(x=pos[0], y=pos[1], z=pos[2], M=M, redshift=0.3, cosmo=synth.COSMO)
-        ps = b.ParticleSnapshot(x=np.zeros(1), y=np.zeros(1), z=np.zeros(1), M=1.0, L=Lbox, redshift=0.3, cosmo=synth.COSMO)
-        run = b.BaryonifySnapshot(cat, ps, args.snap_eps, model, verbose=False)
-        rec, _ = run.halo_records()
-        ncell = run._pick_ncell(rec[:, _lib.HB_RQ], n_part, 3, Lbox)
-        tab = displacement_table_of(model, 0)
-        d_rec = _upload_records(rec, dev)
-        d_rec, _ = _sort_records(d_rec, None, 1, Lbox, 16, 3)
-        g = torch.Generator(device=dev); g.manual_seed(1)
-        d_p = [torch.rand(n_part, dtype=torch.float64, device=dev, generator=g) * Lbox for _ in range(3)]
-        d_s = [torch.empty(n_part, dtype=torch.float64, device=dev) for _ in range(3)]
-        d_start = torch.empty(ncell ** 3 + 1, dtype=torch.int64, device=dev)
-        d_order = torch.empty(n_part, dtype=torch.int64, device=dev)
-        d_tot = torch.zeros((3, n_part), dtype=torch.float64, device=dev)
-        d_n = torch.zeros(1, dtype=torch.int64, device=dev)
-        d_m = torch.ones(n_part, dtype=torch.float64, device=dev)
-        Ng = 512
-        d_grid = torch.zeros(Ng ** 3, dtype=torch.float64, device=dev)
+        out["c4_snapshot"] = snapshot_pipeline(args.npart, args.snap_eps, 0, 2, peak)
 
-        def build():
-            _lib.check(L.bfg_snap_build_cells(3, n_part, d_p[0].data_ptr(), d_p[1].data_ptr(), d_p[2].data_ptr(), Lbox, ncell,
-                                              d_start.data_ptr(), d_order.data_ptr(), d_s[0].data_ptr(), d_s[1].data_ptr(),
-                                              d_s[2].data_ptr(), st))
-
-        def halos():
-            d_tot.zero_()
-            _lib.check(L.bfg_snap_offsets(tab.handle, 3, n_part, d_s[0].data_ptr(), d_s[1].data_ptr(), d_s[2].data_ptr(), Lbox,
-                                          ncell, d_start.data_ptr(), n_halo, d_rec.data_ptr(), None, 0, d_tot.data_ptr(),
-                                          d_n.data_ptr(), st))
-        d_o = [torch.empty(n_part, dtype=torch.float64, device=dev) for _ in range(3)]
-
-        def apply_dep():
-            _lib.check(L.bfg_snap_apply(3, n_part, d_s[0].data_ptr(), d_s[1].data_ptr(), d_s[2].data_ptr(), d_tot.data_ptr(),
-                                        d_order.data_ptr(), Lbox, d_o[0].data_ptr(), d_o[1].data_ptr(), d_o[2].data_ptr(), st))
-            d_grid.zero_()
-            _lib.check(L.bfg_snap_deposit_ngp(3, n_part, d_o[0].data_ptr(), d_o[1].data_ptr(), d_o[2].data_ptr(), d_m.data_ptr(),
-                                              Lbox, Ng, d_grid.data_ptr(), st))
-        ms_b = events(build, warm=1, reps=2)
-        ms_h = events(halos, warm=1, reps=2)
-        ms_a = events(apply_dep, warm=1, reps=2)
-        npairs = int(d_n.cpu()[0])
-        tot_ms = ms_b + ms_h + ms_a
-        out["c4_snapshot"] = dict(n_part=n_part, L=Lbox, halos=n_halo, ncell=ncell, eps=args.snap_eps, pairs=npairs,
-                                  build_cells_ms=ms_b, halo_loop_ms=ms_h, apply_deposit_ms=ms_a,
-                                  particles_per_s=n_part / tot_ms * 1e3, pairs_per_s=npairs / ms_h * 1e3,
-                                  halo_loop_alg_GBs=72 * npairs / ms_h / 1e6, halo_loop_frac=72 * npairs / ms_h / 1e6 / peak,
-                                  deposited_mass=float(d_grid.sum().item()))
     print(json.dumps(out))
 
 
