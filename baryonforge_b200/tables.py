@@ -64,7 +64,7 @@ def get_parameter(obj, key, _depth=0):
         import pyccl as ccl
         is_profile = lambda v: isinstance(v, ccl.halos.profiles.HaloProfile)    # noqa: E731
     except Exception:
-        is_profile = lambda v: hasattr(v, 'projected') and hasattr(v, 'real')   # noqa: E731
+        is_profile = lambda v: (hasattr(v, 'projected') and hasattr(v, 'real')) or hasattr(v, 'interp2D')   # noqa: E731
     for k in dir(obj):
         if k == key:
             return getattr(obj, key)

@@ -120,3 +120,55 @@ def test_plane_assignment():
         for j in range(500):
             planes = (np.arange(cen[j] - ns[j] // 2, cen[j] + ns[j] // 2)) % N
             assert m[j] == bool(np.any((planes >= lo) & (planes < hi)))
+
+
+def test_radius_factor_spline_reproduces_get_radius():
+    """The spline the device record kernel evaluates: R_delta(M, a) = cbrt(M) * g(ln(1+z)) to < 1e-12 (z_max = 30)."""
+    bg = cosmology.runner_cosmology(synth.COSMO, with_w0=True)
+    rng = np.random.default_rng(4)
+    for z_max in (0.5, 3.0, 30.0):
+        g = cosmology.radius_factor_spline(bg, None, z_max)
+        z = np.concatenate([rng.uniform(0, z_max, 20000), [0.0, z_max]])
+        M = 10 ** rng.uniform(11, 16, z.size)
+        a = 1 / (1 + z)
+        want = cosmology.radius_of_mass(bg, M, a)
+        got = np.cbrt(M) * g(np.log(1 / a))
+        assert np.max(np.abs(got / want - 1)) < 2e-12
+    # matter density helper of the anisotropic painters (HealpixRunner.py:580 / Map2DRunner.py:886)
+    assert np.isclose(cosmology.rho_matter(bg, 0.5, is_comoving=True), cosmology.rho_matter(bg, 1.0))
+    assert np.isclose(cosmology.rho_matter(bg, 0.5), 8 * cosmology.rho_matter(bg, 1.0))
+
+
+def test_get_parameter_and_runner_pickling():
+    """utils/Tabulate.py:66-96 `_get_parameter` on the stand-in models; runners stay picklable (Parallelize.py:47-49)."""
+    import pickle
+    from baryonforge_b200.tables import get_parameter
+    axes = synth.table_axes()
+    inner = b.ProfileModel(axes, None, synth.profile_values(axes), proj_cutoff=37.5)
+    assert get_parameter(inner, 'proj_cutoff') == 37.5 and get_parameter(inner, 'no_such_key') is None
+
+    class Wrapper(object):            # a profile wrapping another profile, like TabulatedProfile(model=...)
+        def __init__(self, m):
+            self.model = m
+
+        def real(self):
+            pass
+
+        def projected(self):
+            pass
+    assert get_parameter(Wrapper(inner), 'proj_cutoff') == 37.5
+    ra, dec, M, z = synth.sky_halos(20)
+    cat = b.HaloLightConeCatalog(ra=ra, dec=dec, M=M, z=z, cosmo=synth.COSMO)
+    shell = b.LightconeShell(map=np.ones(12 * 4 * 4), cosmo=synth.COSMO, redshift=0.3)
+    run = b.PaintProfilesAnisShell(cat, shell, 5, inner, inner, inner, 1.5, 0.2, verbose=False)
+    back = pickle.loads(pickle.dumps(run))
+    assert back.background_val == 1.5 and back.global_tracer_fraction == 0.2 and back.epsilon_max == 5
+    assert type(back).__mro__[1].__name__ == 'DefaultRunner'
+    with pytest.raises(NotImplementedError):
+        b.PaintProfilesAnisShell(cat, shell, 5, inner, inner, inner, 1.5, 0.2, use_ellipticity=True)
+    pos, Mb = synth.box_halos(5, 50.0)
+    nd = b.HaloNDCatalog(x=pos[0], y=pos[1], z=pos[2], M=Mb, redshift=0.2, cosmo=synth.COSMO)
+    gm3 = b.GriddedMap(map=np.ones((8, 8, 8)), redshift=0.2, bins=(np.arange(8) + 0.5) * 50 / 8, cosmo=synth.COSMO)
+    grid_run = pickle.loads(pickle.dumps(b.PaintProfilesAnisGrid(nd, gm3, 5, inner, inner, inner, 1.0, 0.1, verbose=False)))
+    with pytest.raises(AssertionError, match="2D maps"):      # Map2DRunner.py:847, raised before any GPU work
+        grid_run.process()
