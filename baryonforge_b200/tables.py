@@ -60,11 +60,14 @@ def get_parameter(obj, key, _depth=0):
     utils/Tabulate.py:66-96 `_get_parameter`: the first attribute called `key` on `obj` or, recursively, on the halo
     profiles it wraps (TabulatedProfile.model, ...).  Without pyccl a "profile" is anything exposing real/projected.
     """
-    try:
-        import pyccl as ccl
-        is_profile = lambda v: isinstance(v, ccl.halos.profiles.HaloProfile)    # noqa: E731
-    except Exception:
-        is_profile = lambda v: (hasattr(v, 'projected') and hasattr(v, 'real')) or hasattr(v, 'interp2D')   # noqa: E731
+    def is_profile(v):
+        if (hasattr(v, 'projected') and hasattr(v, 'real')) or hasattr(v, 'interp2D'):
+            return True
+        try:
+            import pyccl as ccl
+            return isinstance(v, ccl.halos.profiles.HaloProfile)
+        except Exception:
+            return False
     for k in dir(obj):
         if k == key:
             return getattr(obj, key)
