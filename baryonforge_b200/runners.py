@@ -1032,9 +1032,9 @@ class PaintProfilesAnisGrid(PaintProfilesGrid):
 
     def process(self):
         import warnings
-        torch = _torch()
         gm = self.GriddedMap
         assert gm.is2D == True, "Can only paint tSZ on 2D maps. You have passed a 3D Map"   # noqa: E712  (:847)
+        torch = _torch()
         dev = self._device()
         L = _lib.lib()
         cosmo = cosmology.runner_cosmology(self.cosmo, with_w0=False)             # :849-853
