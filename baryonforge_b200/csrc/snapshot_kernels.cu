@@ -113,60 +113,83 @@ k_snap_halos(TableView T, double L, int nc, const double *__restrict__ xs, const
         }
         // cells covering [c - rq, c + rq] per axis (periodic); never more than nc of them
         int lo[3], cnt[3];
+        bool wraps = false;       // does the ball (plus one cell of slack) reach across the box boundary?
         for (int d = 0; d < 3; ++d) {
             if (d >= NDIM) { lo[d] = 0; cnt[d] = 1; continue; }
             int a = (int)floor((s.c[d] - s.rq) / cell), b = (int)floor((s.c[d] + s.rq) / cell);
             int c = b - a + 1;
             if (c >= nc) { a = 0; c = nc; }
             lo[d] = a; cnt[d] = c;
+            wraps = wraps || !(s.c[d] - s.rq > cell) || !(s.c[d] + s.rq < L - cell);
         }
         const int last = NDIM - 1;                 // fastest-varying cell axis: runs along it are contiguous
         const int nouter = (NDIM == 3) ? cnt[0] * cnt[1] : cnt[0];
-        // the run along the last axis, split where it wraps around the box
-        int z0 = ((lo[last] % nc) + nc) % nc;
-        int len0 = min(cnt[last], nc - z0), len1 = cnt[last] - len0;
-        for (int o = warp; o < nouter * 2; o += NW) {
-            int seg = o & 1, oo = o >> 1;
-            int zlo = seg ? 0 : z0, zlen = seg ? len1 : len0;
-            if (zlen <= 0) continue;
-            int cx = (NDIM == 3) ? oo / cnt[1] : oo;
-            int cy = (NDIM == 3) ? oo - cx * cnt[1] : 0;
-            int gx = (((lo[0] + cx) % nc) + nc) % nc;
+        for (int oo = warp; oo < nouter; oo += NW) {
+            const int cx = (NDIM == 3) ? oo / cnt[1] : oo;
+            const int cy = (NDIM == 3) ? oo - cx * cnt[1] : 0;
+            // Column culling: the (cx[, cy]) column of cells is a rectangle in the leading axes; if it lies further than
+            // R_q from the halo the column is skipped, otherwise only the chord of the ball along the last axis is walked.
+            // (Unwrapped cell coordinates; a relative slack keeps the test conservative against round-off.)
+            int zl = lo[last], zc = cnt[last];
+            if (cnt[last] < nc) {
+                double dmin2 = 0.0;
+                for (int d = 0; d < last; ++d) {
+                    if (cnt[d] >= nc) continue;                      // the whole axis is covered: no constraint from it
+                    const double a0 = (double)(lo[d] + (d == 0 ? cx : cy)) * cell;
+                    const double gap = fmax(fmax(a0 - s.c[d], s.c[d] - (a0 + cell)) - 1e-9 * cell, 0.0);
+                    dmin2 = fma(gap, gap, dmin2);
+                }
+                const double rem = rq2 * (1.0 + 1e-12) - dmin2;
+                if (rem < 0.0) continue;
+                const double rz = sqrt(rem) + 1e-9 * cell;
+                const int za = max((int)floor((s.c[last] - rz) / cell), lo[last]);
+                const int zb = min((int)floor((s.c[last] + rz) / cell), lo[last] + cnt[last] - 1);
+                if (zb < za) continue;
+                zl = za; zc = zb - za + 1;
+            }
+            const int gx = (((lo[0] + cx) % nc) + nc) % nc;
             i64 cbase;
             if (NDIM == 3) {
-                int gy = (((lo[1] + cy) % nc) + nc) % nc;
+                const int gy = (((lo[1] + cy) % nc) + nc) % nc;
                 cbase = ((i64)gx * nc + gy) * nc;
             } else {
-                cbase = 0; zlo = seg ? 0 : z0;
-                // 2-D: the "last axis" is y; runs are over y for fixed x
-                cbase = (i64)gx * nc;
+                cbase = (i64)gx * nc;                  // 2-D: the "last axis" is y; runs are over y for fixed x
             }
-            i64 p0 = cell_start[cbase + zlo], p1 = cell_start[cbase + zlo + zlen];
-            for (i64 p = p0 + lane; p < p1; p += 32) {
-                double dx = min_image(xs[p] - s.c[0], L);      // SnapshotRunner.py:248-251 / :103-132
-                double dy = min_image(ys[p] - s.c[1], L);
-                double dz = (NDIM == 3) ? min_image(zs[p] - s.c[2], L) : 0.0;
-                double d2 = (NDIM == 3) ? dx * dx + dy * dy + dz * dz : dx * dx + dy * dy;
-                if (!(d2 <= rq2)) continue;                    // query_ball_point: d <= R_q, inclusive  (:232/:247)
-                ++done;
-                double val;
-                if (UNIFORM) {
-                    bool ok;
-                    val = row_at_r2(rl, d2, ok);
-                    if (!ok) val = CUDART_NAN;
-                } else {
-                    double xq = fast_log2(d2, l2tab) * 0.34657359027997264;   // ln d = 0.5 ln2 log2(d^2)
-                    if (T.flags & BFG_TABLE_RDELTA) xq -= s.lnRcom;
-                    val = row_lookup<false>(T, row, xq);
+            // the run along the last axis, split where it wraps around the box
+            const int z0 = ((zl % nc) + nc) % nc;
+            const int len0 = min(zc, nc - z0), len1 = zc - len0;
+            for (int seg = 0; seg < 2; ++seg) {
+                const int zlo = seg ? 0 : z0, zlen = seg ? len1 : len0;
+                if (zlen <= 0) continue;
+                const i64 p0 = cell_start[cbase + zlo], p1 = cell_start[cbase + zlo + zlen];
+                for (i64 p = p0 + lane; p < p1; p += 32) {
+                    double dx = xs[p] - s.c[0], dy = ys[p] - s.c[1], dz = (NDIM == 3) ? zs[p] - s.c[2] : 0.0;
+                    if (wraps) {                                   // SnapshotRunner.py:248-251 / :103-132 minimum image
+                        dx = min_image(dx, L); dy = min_image(dy, L);
+                        if (NDIM == 3) dz = min_image(dz, L);
+                    }
+                    const double d2 = (NDIM == 3) ? dx * dx + dy * dy + dz * dz : dx * dx + dy * dy;
+                    if (!(d2 <= rq2)) continue;                    // query_ball_point: d <= R_q, inclusive  (:232/:247)
+                    ++done;
+                    double val;
+                    if (UNIFORM) {
+                        bool ok;
+                        val = row_at_r2(rl, d2, ok);
+                        if (!ok) val = CUDART_NAN;
+                    } else {
+                        double xq = fast_log2(d2, l2tab) * 0.34657359027997264;   // ln d = 0.5 ln2 log2(d^2)
+                        if (T.flags & BFG_TABLE_RDELTA) xq -= s.lnRcom;
+                        val = row_lookup<false>(T, row, xq);
+                    }
+                    if (!valid) val = CUDART_NAN;
+                    val = (d2 < rcut2) ? val : 0.0;                // BaryonCorrection.py:410-411
+                    if (!isfinite(val)) val = 0.0;                 // SnapshotRunner.py:259
+                    if (val == 0.0 && d2 > 0.0) continue;          // adds exact zeros
+                    const double sc = val * rsqrt_pos(d2);         // d == 0 -> NaN, as in the reference's 0/0 (§10 #11)
+                    red_add(tot + p, sc * dx);                     // :260
+                    red_add(tot + n_part + p, sc * dy);
+                    if (NDIM == 3) red_add(tot + 2 * n_part + p, sc * dz);
                 }
-                if (!valid) val = CUDART_NAN;
-                val = (d2 < rcut2) ? val : 0.0;                // BaryonCorrection.py:410-411
-                if (!isfinite(val)) val = 0.0;                 // SnapshotRunner.py:259
-                if (val == 0.0 && d2 > 0.0) continue;          // adds exact zeros
-                const double sc = val * rsqrt_pos(d2);         // d == 0 -> NaN, as in the reference's 0/0 (§10 #11)
-                red_add(tot + p, sc * dx);                     // :260
-                red_add(tot + n_part + p, sc * dy);
-                if (NDIM == 3) red_add(tot + 2 * n_part + p, sc * dz);
             }
         }
     }
