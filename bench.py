@@ -169,6 +169,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    claim_stdout()
     import multiprocessing as mp
     cat, model, axes, vals = make_inputs(args)
     sc = cpu_scalars(cat, model, args.eps)
@@ -207,16 +208,35 @@ def run_reference(args):
                              "sample": sample},
             "e2e": {"value": value, "unit": "halo-pixel updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line: anything libraries write to fd 1 (NCCL prints its "NCCL version ..." banner
+    there) is sent to stderr, and emit() writes the line to the original stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def run_b200(args):
-    # stdout carries exactly ONE JSON line: NCCL's own banner ("NCCL version ...", printed when the box sets NCCL_DEBUG)
-    # goes to stderr instead
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    claim_stdout()
     import torch
     import torch.distributed as dist
     import baryonforge_b200 as b
@@ -420,7 +440,7 @@ def run_b200(args):
             "e2e": e2e, "particles": particles}
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, cat, model, axes, vals, args.cpu_sample)
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
