@@ -122,10 +122,19 @@ def _give_scratch(tensors):
             bucket.append(t)
 
 
+def _host_threads():
+    """Host threads of this process: BFG_HOST_THREADS, else min(16, cores / processes of this box (torchrun))."""
+    import os
+    if "BFG_HOST_THREADS" in os.environ:
+        return int(os.environ["BFG_HOST_THREADS"])
+    local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+    return max(1, min(16, (os.cpu_count() or 1) // local_world))
+
+
 def _parallel_chunks(fn, n, chunk=65536):
     """Run fn(slice) over [0, n) in chunks on a small thread pool (BFG_HOST_THREADS, default min(16, cores))."""
     import os
-    nthreads = int(os.environ.get("BFG_HOST_THREADS", min(16, os.cpu_count() or 1)))
+    nthreads = _host_threads()
     slices = [slice(i, min(i + chunk, n)) for i in range(0, n, chunk)]
     if nthreads <= 1 or len(slices) <= 1:
         for sl in slices:
@@ -342,18 +351,38 @@ class DefaultRunner(object):
             z_max = float(np.max(z_all))
             assert z_max <= 30, f"We assume max(z) = 30, but your catalog has max(z) = {z_max}"   # HealpixRunner.py:301
             pack, n_DA, n_g = self._spline_pack(paint, z_max)
-            stage = _take_scratch(6 * n)
+            # Sharded runs: every rank needs the whole catalogue on its device (it selects its own halos there), but the
+            # host staging is split -- rank r stages halos [r m, (r+1) m) and the columns are all-gathered over NVLink.
+            world, rank = 1, 0
+            import os
+            if self.pix_range is not None and os.environ.get("BFG_SHARD_STAGING", "1") == "1":
+                from .parallel import _dist
+                dist = _dist()
+                if dist is not None and dist.get_backend() == "nccl":
+                    world, rank = dist.get_world_size(), dist.get_rank()
+            m = -(-n // world)                       # halos staged per rank
+            lo_h, hi_h = min(rank * m, n), min((rank + 1) * m, n)
+            stage = _take_scratch(6 * m)
             self._scratch_inflight = getattr(self, '_scratch_inflight', None) or []
             self._scratch_inflight.append(stage)
-            cols = stage.numpy().reshape(6, n)
+            cols = stage.numpy().reshape(6, m)
 
             def fill(sl):   # numpy releases the GIL inside these ufuncs/copies
-                M, z = cat['M'][sl], cat['z'][sl]
-                cols[0, sl], cols[1, sl], cols[2, sl], cols[3, sl] = M, z, cat['ra'][sl], cat['dec'][sl]
+                src = slice(lo_h + sl.start, lo_h + sl.stop)
+                M, z = cat['M'][src], cat['z'][src]
+                cols[0, sl], cols[1, sl], cols[2, sl], cols[3, sl] = M, z, cat['ra'][src], cat['dec'][src]
                 np.log(1 / (1 / (1 + z)), out=cols[4, sl])                     # np.log(1/a_j)  BaryonCorrection.py:371
                 np.log(M, out=cols[5, sl])                                     # np.log(M_j)    BaryonCorrection.py:398
-            _parallel_chunks(fill, n)
-            d_cols = stage.to(dev, non_blocking=True)
+            _parallel_chunks(fill, hi_h - lo_h)
+            if world == 1:
+                d_cols = stage.to(dev, non_blocking=True)
+            else:
+                if hi_h - lo_h < m:
+                    cols[:, hi_h - lo_h:] = 1.0                               # padding of the last rank's block
+                d_part = stage.to(dev, non_blocking=True).reshape(6, m)
+                d_all = torch.empty((world, 6, m), dtype=torch.float64, device=dev)
+                dist.all_gather_into_tensor(d_all.reshape(-1), d_part.reshape(-1))
+                d_cols = d_all.permute(1, 0, 2).reshape(6, world * m)[:, :n].contiguous()   # [6][n], catalogue order
             d_pack = torch.from_numpy(pack).to(dev, non_blocking=True)
             d_aux = torch.empty((3, n), dtype=torch.float64, device=dev)
             base = d_pack.data_ptr()

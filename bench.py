@@ -377,7 +377,7 @@ def run_b200(args):
                "h2d_bytes_per_step": int(npix * 8 + world * 6 * n_rec * 8), "d2h_bytes_per_step": int(npix * 8),
                "bytes_note": "whole job: every rank uploads its map slice + the 6 catalogue columns and downloads its slice of the new map",
                "ms_per_step": 1e3 * float(tt[0]), "host_prep_ms": 1e3 * runner.last_timing.get("host_prep_s", 0.0),
-               "host_threads": int(os.environ.get("BFG_HOST_THREADS", min(16, os.cpu_count() or 1))),
+               "host_threads": b.runners._host_threads(),
                "iter_ms": iter_ms, "phases_ms": {k: round(1e3 * v, 2) for k, v in runner.last_timing.items()},
                "includes": "host staging of raw catalogue columns + numpy ln(1+z), ln M; H2D (pinned map + 6 columns); device scalar prep, sort, halo loop, re-binning, exchange (N>1); D2H of the new map"}
 
