@@ -11,45 +11,16 @@
 //       gx = x[j] + dx,  gy = x[i] + dy,  gz = x[k] + dz        with dx = bins[x_cen] - x_j, ...
 //     and component 0 of the offset is gx/r, component 1 is gy/r.
 #include <algorithm>
+#include <stdlib.h>
 #include <string.h>
 #include "bfg_common.cuh"
+#include "grid_common.cuh"
 
 using namespace bfg;
 
 namespace {
 
 constexpr int GRID_THREADS = 128;
-
-struct HaloBox {
-    double rq, lnz, lnM, rcut, lnRcom, d[3], paintcut;
-    int nsize, cen[3];
-};
-
-__device__ __forceinline__ HaloBox load_box(const double *__restrict__ H) {
-    HaloBox b;
-    b.rq = __ldg(H + BFG_HB_RQ);
-    b.nsize = (int)__ldg(H + BFG_HB_NSIZE);
-    b.cen[0] = (int)__ldg(H + BFG_HB_CX); b.cen[1] = (int)__ldg(H + BFG_HB_CY); b.cen[2] = (int)__ldg(H + BFG_HB_CZ);
-    b.lnz = __ldg(H + BFG_HB_LNZ); b.lnM = __ldg(H + BFG_HB_LNM);
-    b.rcut = __ldg(H + BFG_HB_RCUT); b.lnRcom = __ldg(H + BFG_HB_LNRCOM);
-    b.d[0] = __ldg(H + BFG_HB_DX); b.d[1] = __ldg(H + BFG_HB_DY); b.d[2] = __ldg(H + BFG_HB_DZ);
-    b.paintcut = __ldg(H + BFG_HB_PAINTCUT);
-    return b;
-}
-
-// np.linspace(-Ns/2, Ns/2, Ns)[i] * res, same operation order as numpy (arange*step + start, last = stop)
-__device__ __forceinline__ double cut_coord(int i, int ns, double res) {
-    double start = -0.5 * (double)ns, stop = 0.5 * (double)ns;
-    double step = (stop - start) / (double)(ns - 1);
-    double y = (i == ns - 1) ? stop : __dadd_rn(__dmul_rn((double)i, step), start);
-    return y * res;
-}
-
-__device__ __forceinline__ int wrap_idx(int c, int N) {   // pick_indices, Map2DRunner.py:400-429
-    if (c < 0) c += N;
-    if (c >= N) c -= N;
-    return c;
-}
 
 // ELL (2-D only): the last 4 columns of `extras` hold the halo's shear matrix Rmat (Map2DRunner.py:281-350, build_Rmat);
 // the radius handed to the table is |(gx, gy) @ Rmat| while the direction stays (gx, gy)/r   (:531-536, :769-774).
@@ -290,6 +261,16 @@ int launch_grid(const bfg_table *t, int ndim, i64 N, double res, double scale, i
         return BFG_OK;
     };
     const bool u = t->view.uniform_r != 0 && (MODE != MODE_ANIS || t2->view.uniform_r != 0);
+    if (MODE != MODE_ANIS && ndim == 3 && u) {
+        // 3-D grids: tile-centric gather (grid_tile_kernels.cu) -- each cell is written once instead of once per halo.
+        // BFG_GRID_TILES=0 forces the halo-centric scatter kernel (kept for geometries the tiling does not cover).
+        const char *env = getenv("BFG_GRID_TILES");
+        if (!(env && env[0] == '0')) {
+            int rc = launch_grid_tiles(PAINT, t, N, res, scale, n_halo, d_halos, d_extras, n_extra, d_out, plane_lo, plane_hi,
+                                       d_nupdates, st);
+            if (rc != BFG_ERR_UNSUPPORTED) return rc;
+        }
+    }
     if (MODE == MODE_ANIS) {   // 2-D only
         if (use_ell) return u ? go(k_grid_halos<MODE_ANIS, true, 2, true>) : go(k_grid_halos<MODE_ANIS, false, 2, true>);
         return u ? go(k_grid_halos<MODE_ANIS, true, 2, false>) : go(k_grid_halos<MODE_ANIS, false, 2, false>);

@@ -354,3 +354,66 @@ def test_parallelize_mirrors():
     assert_close(joined, outs[0], "SplitJoinParallel", rtol=1e-9, atol_scale=1e-12)
     with pytest.raises(AssertionError):
         b.SplitJoinParallel(bary, njobs=2)      # Parallelize.py:206-209
+
+
+def test_grid3d_tile_gather_matches_scatter_and_oracle(monkeypatch):
+    """3-D grids whose geometry fits the tiling (N % 16 == 0) run the tile-centric gather kernels (grid_tile_kernels.cu):
+    same offsets / painted map as the halo-centric scatter kernels (BFG_GRID_TILES=0) and as the oracle port, same update
+    count, independent of the slab split; covers periodic wrap, a halo outside the table (NaN -> cleaned) and the cut."""
+    import torch
+    import baryonforge_b200 as b
+    from baryonforge_b200 import synth
+    from oracle import runners_port as rp
+    N, Lbox, n = 64, 100.0, 150
+    pos, M = synth.box_halos(n, Lbox, seed=91)
+    M[0] = 3e11                                      # outside the table: NaN offsets inside its cut
+    pos[:, 1] = 0.01 * Lbox / N                      # cutouts that wrap around the box on every axis
+    pos[:, 2] = Lbox * (1 - 1e-3)
+    M[3] = 10 ** 15.4                                # a cutout of N/2 cells
+    bins = (np.arange(N) + 0.5) * Lbox / N
+    gaxes = synth.table_axes(nz=6, nM=10, nr=300, z_min=0.0, z_max=1.0, z_linear=True, r_min=1e-2, r_max=2e2)
+    dvals = synth.displacement_values(gaxes) * 25.0
+    pvals = synth.profile_values(gaxes)
+    gmap = np.random.default_rng(92).uniform(0, 10, (N, N, N))
+    cat = b.HaloNDCatalog(x=pos[0], y=pos[1], z=pos[2], M=M, redshift=0.3, cosmo=synth.COSMO)
+    gm = b.GriddedMap(map=gmap, redshift=0.3, bins=bins, cosmo=synth.COSMO)
+    dmodel = b.DisplacementModel(gaxes, dvals, 4, synth.COSMO)
+    pmodel = b.ProfileModel(gaxes, pvals * 3.0, pvals)
+    a = 1 / 1.3
+
+    run = b.BaryonifyGrid(cat, gm, 6, dmodel, verbose=False)
+    off_t, n_t = run.offsets_on_device()
+    sc = run.last_scalars
+    monkeypatch.setenv("BFG_GRID_TILES", "0")
+    off_s, n_s = b.BaryonifyGrid(cat, gm, 6, dmodel, verbose=False).offsets_on_device()
+    monkeypatch.delenv("BFG_GRID_TILES")
+    assert int(n_t.cpu()[0]) == int(n_s.cpu()[0])
+    assert_close(off_t.cpu().numpy(), off_s.cpu().numpy(), "tile vs scatter offsets", rtol=1e-9, atol_scale=1e-13)
+    hc = dict(M=cat.cat['M'].astype('<f4'), x=cat.cat['x'].astype('<f4'), y=cat.cat['y'].astype('<f4'),
+              z=cat.cat['z'].astype('<f4'))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        off_w, n_w = rp.grid_offsets((N, N, N), bins, hc, a, sc["R_phys"], sc["R_model_com"], 6,
+                                     rp.DisplacementTable(gaxes, dvals, 4), warn=False)
+        map_w = rp.grid_regrid(gmap, off_w)
+    assert int(n_t.cpu()[0]) == n_w
+    assert_close(off_t.cpu().numpy().T, off_w, "tile offsets vs oracle port")
+    assert_close(run.process(), map_w, "BaryonifyGrid (tiles) vs oracle port")
+    # slab split (plane ranges aligned to the tile height)
+    lo, _ = b.BaryonifyGrid(cat, gm, 6, dmodel, verbose=False, plane_range=(0, 24)).offsets_on_device()
+    hi, _ = b.BaryonifyGrid(cat, gm, 6, dmodel, verbose=False, plane_range=(24, N)).offsets_on_device()
+    both = torch.cat([lo.reshape(3, 24, N * N), hi.reshape(3, N - 24, N * N)], dim=1).reshape(3, -1)
+    assert_close(both.cpu().numpy(), off_t.cpu().numpy(), "tile slab split", rtol=1e-9, atol_scale=1e-13)
+    # painting (model.real table)
+    prun = b.PaintProfilesGrid(cat, gm, 5, pmodel, verbose=False)
+    got_p = prun.process()
+    monkeypatch.setenv("BFG_GRID_TILES", "0")
+    got_ps = b.PaintProfilesGrid(cat, gm, 5, pmodel, verbose=False).process()
+    monkeypatch.delenv("BFG_GRID_TILES")
+    assert_close(got_p, got_ps, "tile vs scatter paint", rtol=1e-9, atol_scale=1e-13)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want_p, n_wp = rp.paint_grid((N, N, N), bins, hc, a, prun.last_scalars["R_phys"] / a, 5,
+                                     rp.ProfileTable(gaxes, pvals * 3.0, pvals))
+    assert prun.last_stats["n_updates"] == n_wp
+    assert_close(got_p, want_p, "PaintProfilesGrid (tiles) vs oracle port")
