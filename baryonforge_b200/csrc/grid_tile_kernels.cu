@@ -166,9 +166,15 @@ k_tile_gather(TableView T, TileGeom g, double res, double scale, const double *_
     const i64 nloc = (i64)(g.plane_hi - g.plane_lo) * plane;
     const double inv_res = 1.0 / res;
     constexpr int NCOMP = PAINT ? 1 : 3;
-    const unsigned l2_s = (unsigned)__cvta_generic_to_shared(l2tab);
-    const double uA = 0.34657359027997264 * T.inv_dr, uMax = (double)(NR - 1);
-    const int nrm2 = NR - 2;
+    // kernel-lifetime constants, laundered through a shuffle so that ptxas keeps them in registers instead of re-deriving
+    // them from the parameter bank for every cell (see launder() in bfg_common.cuh)
+    RowLookup rl;
+    rl.uA = 0.34657359027997264 * T.inv_dr; rl.uB = 0.0; rl.uMax = (double)(NR - 1); rl.nrm2 = NR - 2;
+    rl.row_s = 0; rl.l2_s = (unsigned)__cvta_generic_to_shared(l2tab);
+    launder(rl);
+    const unsigned l2_s = rl.l2_s;
+    const double uA = rl.uA, uMax = rl.uMax;
+    const int nrm2 = rl.nrm2;
     const bool rdelta = (T.flags & BFG_TABLE_RDELTA) != 0;
 
     for (;;) {
@@ -188,6 +194,12 @@ k_tile_gather(TableView T, TileGeom g, double res, double scale, const double *_
         const i64 p_end = tile_start[tile + 1];
         for (i64 p = tile_start[tile]; p < p_end; ++p) {
             const i64 h = pair_halo[p];
+            // the halo's blended row (uniform across the CTA); laundered like the constants above, else its 64-bit address
+            // arithmetic is redone for every cell
+            __syncwarp();
+            i64 roff = h * NR;
+            roff = ((i64)__shfl_sync(0xffffffffu, (int)(roff >> 32), 0) << 32) | (unsigned)__shfl_sync(0xffffffffu, (int)roff, 0);
+            const double *__restrict__ rowp = rows + roff;
             const double *H = halos + h * BFG_HALO_STRIDE;
             const int ns = (int)__ldg(H + BFG_HB_NSIZE), cw = ns / 2;
             const int ia = cut_index(A, cut_start((int)__ldg(H + BFG_HB_CY), cw, N), N);
@@ -203,7 +215,6 @@ k_tile_gather(TableView T, TileGeom g, double res, double scale, const double *_
             const int s0 = cut_start((int)__ldg(H + BFG_HB_CX), cw, N);
             const double dy = __ldg(H + BFG_HB_DY);
             const double uB = ((rdelta ? -__ldg(H + BFG_HB_LNRCOM) : 0.0) - T.r0) * T.inv_dr;
-            const double *__restrict__ rowp = rows + h * NR;
             const bool valid = rows_valid[h] != 0;
 #pragma unroll
             for (int c = 0; c < TI; ++c) {
