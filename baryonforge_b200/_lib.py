@@ -46,6 +46,9 @@ _SIGNATURES = {
                               c_ptr, c_ptr], C.c_int),
     "bfg_anis_background": ([c_i64, c_ptr, c_dbl, c_ptr, c_dbl, c_dbl, c_ptr, c_ptr], C.c_int),
     "bfg_shell_regrid": ([C.c_int, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_ptr], C.c_int),
+    "bfg_shell_regrid_range": ([C.c_int, c_ptr, c_ptr, c_i64, c_ptr, c_i64, c_i64, c_ptr], C.c_int),
+    "bfg_offsets_max_norm2": ([c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr], C.c_int),
+    "bfg_halo_band_bounds": ([c_i64, c_ptr, c_dbl, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr], C.c_int),
     "bfg_shell_records": ([c_i64, c_ptr, C.c_int, c_dbl, c_dbl, c_dbl, C.c_int, c_ptr, c_ptr, C.c_int, c_ptr, c_ptr, c_ptr,
                            c_ptr, c_ptr, c_ptr], C.c_int),
     "bfg_shell_regrid_p2p": ([C.c_int, c_ptr, c_ptr, c_i64, c_i64, C.c_int, C.c_int, C.POINTER(c_i64), C.POINTER(c_ptr),

@@ -447,6 +447,64 @@ k_shell_regrid(Hpx h, const double *__restrict__ map_in, const double *__restric
     }
 }
 
+// Re-binning of a SOURCE pixel range of a full-size offsets array (component stride given explicitly): the pipelined
+// end-to-end path re-bins the rings whose offsets are final while the halo loop works further south.
+__global__ void __launch_bounds__(256)
+k_shell_regrid_range(Hpx h, const double *__restrict__ map_in, const double *__restrict__ off, i64 comp_stride,
+                     double *__restrict__ map_out, i64 src_lo, i64 src_hi) {
+    for (i64 p = src_lo + (i64)blockIdx.x * blockDim.x + threadIdx.x; p < src_hi; p += (i64)gridDim.x * blockDim.x) {
+        const double m = map_in[p];
+        if (m == 0.0) continue;                                  // HealpixRunner.py:359
+        double x, y, z;
+        pix2vec(h, p, x, y, z);
+        x += off[p]; y += off[comp_stride + p]; z += off[2 * comp_stride + p];   // :357 (not re-normalised)
+        const double dn = sqrt(x * x + y * y + z * z);           // hp.vec2ang(lonlat=True)  :358
+        const double theta = acos(z / dn);
+        double phi = atan2(y, x);
+        if (phi < 0) phi += BFG_TWOPI;
+        const double lon = phi * (180.0 / BFG_PI), lat = 90.0 - theta * (180.0 / BFG_PI);
+        const double th2 = BFG_HALFPI - lat * (BFG_PI / 180.0), ph2 = lon * (BFG_PI / 180.0);   // get_interp_weights  :361
+        i64 pix[4]; double w[4];
+        get_interpol(h, th2, ph2, pix, w);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) red_add(map_out + pix[k], w[k] * m);   // :17-71
+    }
+}
+
+// max_p |offset_p|^2 over [lo, hi) of a component-major offsets array (bounds how far the re-binning can move mass)
+__global__ void __launch_bounds__(256)
+k_max_norm3(const double *__restrict__ off, i64 comp_stride, i64 lo, i64 hi, unsigned long long *out_bits) {
+    double m = 0.0;
+    for (i64 p = lo + (i64)blockIdx.x * blockDim.x + threadIdx.x; p < hi; p += (i64)gridDim.x * blockDim.x) {
+        const double a = off[p], b = off[comp_stride + p], c = off[2 * comp_stride + p];
+        const double n2 = a * a + b * b + c * c;
+        m = fmax(m, (n2 == n2) ? n2 : CUDART_INF);               // a NaN offset counts as unbounded
+    }
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out_bits, (unsigned long long)__double_as_longlong(m));   // m >= 0: bit order = value order
+}
+
+// Sky-sorted halo records: first index whose colatitude band (floor(theta / band)) reaches each band edge, and the
+// largest disc radius -- what the host needs to cut the halo loop into latitude chunks.
+__global__ void k_band_bounds(i64 n, const double *__restrict__ halos, double band, int n_edges,
+                              const i64 *__restrict__ edge_band, i64 *__restrict__ bounds, unsigned long long *rho_bits) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n_edges) {
+        const i64 eb = edge_band[t];
+        i64 lo = 0, hi = n;                                       // first i with band(i) >= eb
+        while (lo < hi) {
+            const i64 mid = (lo + hi) >> 1;
+            const i64 bm = (i64)fmin(fmax(halos[mid * BFG_HALO_STRIDE + BFG_HS_THETA] / band, 0.0), 1048575.0);
+            if (bm >= eb) hi = mid; else lo = mid + 1;
+        }
+        bounds[t] = lo;
+    }
+    double m = 0.0;
+    for (i64 i = t; i < n; i += (i64)gridDim.x * blockDim.x) m = fmax(m, halos[i * BFG_HALO_STRIDE + BFG_HS_RADIUS]);
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.0) atomicMax(rho_bits, (unsigned long long)__double_as_longlong(m));
+}
+
 __global__ void k_disc_counts(Hpx h, i64 n_halo, const double *__restrict__ halos, i64 *__restrict__ npix) {
     const int lane = threadIdx.x & 31;
     i64 wid = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -621,6 +679,41 @@ extern "C" int bfg_shell_regrid(int nside, const double *d_map_in, const double 
     if (pix_lo == pix_hi) return BFG_OK;
     k_shell_regrid<<<grid_for(pix_hi - pix_lo, 256), 256, 0, (cudaStream_t)stream>>>(h, d_map_in, d_offsets, d_map_out,
                                                                                     pix_lo, pix_hi);
+    BFG_CUDA_OK(cudaGetLastError());
+    return BFG_OK;
+}
+
+extern "C" int bfg_shell_regrid_range(int nside, const double *d_map_in, const double *d_offsets, int64_t comp_stride,
+                                      double *d_map_out, int64_t src_lo, int64_t src_hi, void *stream) {
+    BFG_REQUIRE(d_map_in && d_offsets && d_map_out, "null argument");
+    if (int rc = check_nside(nside)) return rc;
+    Hpx h(nside);
+    BFG_REQUIRE(src_lo >= 0 && src_hi <= h.npix && src_lo <= src_hi && comp_stride >= src_hi, "bad pixel range");
+    if (src_lo == src_hi) return BFG_OK;
+    k_shell_regrid_range<<<grid_for(src_hi - src_lo, 256), 256, 0, (cudaStream_t)stream>>>(h, d_map_in, d_offsets, comp_stride,
+                                                                                          d_map_out, src_lo, src_hi);
+    BFG_CUDA_OK(cudaGetLastError());
+    return BFG_OK;
+}
+
+extern "C" int bfg_offsets_max_norm2(const double *d_offsets, int64_t comp_stride, int64_t lo, int64_t hi, double *d_out,
+                                     void *stream) {
+    BFG_REQUIRE(d_offsets && d_out && lo >= 0 && lo <= hi && hi <= comp_stride, "bad argument");
+    BFG_CUDA_OK(cudaMemsetAsync(d_out, 0, sizeof(double), (cudaStream_t)stream));
+    if (lo == hi) return BFG_OK;
+    k_max_norm3<<<grid_for(hi - lo, 256, 148 * 8), 256, 0, (cudaStream_t)stream>>>(d_offsets, comp_stride, lo, hi,
+                                                                                  (unsigned long long *)d_out);
+    BFG_CUDA_OK(cudaGetLastError());
+    return BFG_OK;
+}
+
+extern "C" int bfg_halo_band_bounds(int64_t n_halo, const double *d_sorted_halos, double band, int n_edges,
+                                    const int64_t *d_edge_band, int64_t *d_bounds, double *d_rho_max, void *stream) {
+    BFG_REQUIRE(d_sorted_halos && d_edge_band && d_bounds && d_rho_max && band > 0 && n_edges >= 1 && n_edges <= 4096,
+                "bad argument");
+    BFG_CUDA_OK(cudaMemsetAsync(d_rho_max, 0, sizeof(double), (cudaStream_t)stream));
+    k_band_bounds<<<32, 256, 0, (cudaStream_t)stream>>>(n_halo, d_sorted_halos, band, n_edges, (const i64 *)d_edge_band,
+                                                        (i64 *)d_bounds, (unsigned long long *)d_rho_max);
     BFG_CUDA_OK(cudaGetLastError());
     return BFG_OK;
 }

@@ -59,6 +59,33 @@ def _ring_z(nside, ring):
     return z
 
 
+def first_pixel_at_colatitude(nside, theta):
+    """First RING pixel of the first ring whose colatitude is >= theta (npix when theta lies south of the last ring)."""
+    npix = 12 * nside * nside
+    if theta <= 0:
+        return 0
+    if theta >= np.pi:
+        return npix
+    z = np.cos(theta)
+    lo, hi = 1, 4 * nside          # smallest ring r in [1, 4 nside - 1] with z_ring(r) <= z  (z decreases with r)
+    while lo < hi:
+        mid = (lo + hi) // 2
+        if mid <= 4 * nside - 1 and float(_ring_z(nside, mid)) <= z:
+            hi = mid
+        else:
+            lo = mid + 1
+    r = lo
+    if r > 4 * nside - 1:
+        return npix
+    ncap = 2 * nside * (nside - 1)
+    if r < nside:
+        return 2 * r * (r - 1)
+    if r < 3 * nside:
+        return ncap + (r - nside) * 4 * nside
+    q = 4 * nside - r
+    return npix - 2 * q * (q + 1)
+
+
 def halos_touching_pixel_range(nside, theta, radius, lo, hi, margin_rings=2):
     """
     Boolean mask of the halos whose disc (colatitude theta, angular radius) can contain a pixel of [lo, hi).

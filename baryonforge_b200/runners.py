@@ -508,12 +508,148 @@ class BaryonifyShell(DefaultRunner):
         d_n = d_nb.sum().reshape(1)
         return d_off, d_n
 
+    PIPELINE_MIN_HALOS = 200000     # below this the halo loop is too short to hide the download behind
+    PIPELINE_CHUNKS = 12
+    PIPELINE_MARGIN_RAD = 0.02      # how far (chord on the unit sphere) the re-binning may move mass; verified per call
+
+    def _process_pipelined(self):
+        """
+        Single-GPU end-to-end path for large catalogues: the sky-sorted halo loop is cut into latitude chunks of equal
+        area; as soon as a chunk is done the rings north of (chunk edge - largest disc radius) have their final offsets, so
+        they are re-binned and the finished part of the NEW map is downloaded on a side stream while the halo loop works
+        on the next chunk.  Only the last chunk's re-binning + download is exposed.  The assumption that the re-binning
+        moves mass by less than PIPELINE_MARGIN_RAD is checked against max|offset| at the end; if it fails (absurdly
+        large displacements) the whole map is downloaded again.  Returns None when the path does not apply.
+        """
+        torch = _torch()
+        from .parallel import first_pixel_at_colatitude
+        orig_map = self.LightconeShell.map
+        NSIDE = self.LightconeShell.NSIDE
+        npix = orig_map.size
+        cat = self.HaloLightConeCatalog.cat
+        n = cat.size
+        dev = self._device()
+        L = _lib.lib()
+        import os
+        K = int(os.environ.get("BFG_PIPELINE_CHUNKS", self.PIPELINE_CHUNKS))
+        keys = list(vars(self.model).get('p_keys', []))
+        _check_keys(self.model, keys)
+        with torch.cuda.device(dev):
+            table = self._tables.get((id(self.model), id(self.model.interp_d) if hasattr(self.model, 'interp_d') else 0),
+                                     lambda: displacement_table_of(self.model, dev.index))
+            if getattr(self, '_scratch_inflight', None):
+                torch.cuda.current_stream().synchronize()
+                _give_scratch(self._scratch_inflight)
+            self._scratch_inflight = []
+            st = _lib.current_stream()
+            main = torch.cuda.current_stream()
+            side = _side_stream(dev)
+            d_rec = self.device_records(False, dev)
+            ext = _extras(cat, keys)
+            d_ext = None if ext is None else _to_device(ext, dev)
+            d_rec, d_ext = _sort_records(d_rec, d_ext, 0, SKY_BAND_RAD)
+            # latitude chunks of equal area, expressed as band indices of the sort key
+            edges = [int(np.floor(np.arccos(1 - 2.0 * k / K) / SKY_BAND_RAD)) for k in range(K)] + [1 << 40]
+            d_edges = torch.tensor(edges, dtype=torch.int64, device=dev)
+            d_bounds = torch.empty(K + 1, dtype=torch.int64, device=dev)
+            d_rho = torch.zeros(1, dtype=torch.float64, device=dev)
+            _lib.check(L.bfg_halo_band_bounds(n, _lib.ptr(d_rec), SKY_BAND_RAD, K + 1, _lib.ptr(d_edges), _lib.ptr(d_bounds),
+                                              _lib.ptr(d_rho), st))
+            # the map goes up in K pieces on the side stream, underneath the halo loop; a re-binning step waits only for the
+            # pieces it reads (a single 1.6 GB copy would stall the first re-binning, and with it the halo loop, for ~15 ms)
+            h_map = torch.from_numpy(np.ascontiguousarray(orig_map, dtype=np.float64).reshape(-1))
+            piece = -(-npix // K)
+            ev_h2d = []
+            with torch.cuda.stream(side):
+                d_map = torch.empty(npix, dtype=torch.float64, device=dev)
+                for j in range(K):
+                    a0, a1 = j * piece, min((j + 1) * piece, npix)
+                    d_map[a0:a1].copy_(h_map[a0:a1], non_blocking=True)
+                    ev_h2d.append(side.record_event())
+            d_off = torch.zeros((3, npix), dtype=torch.float64, device=dev)
+            d_new = torch.zeros(npix, dtype=torch.float64, device=dev)
+            d_nb = torch.zeros(K, dtype=torch.int64, device=dev)
+            d_max = torch.zeros(1, dtype=torch.float64, device=dev)
+            bounds = d_bounds.cpu().tolist()        # one small synchronisation: chunk boundaries in the sorted catalogue
+            rho_max = float(d_rho.cpu()[0])
+            pix_rad = np.sqrt(4 * np.pi / npix)
+            out, out_np = _pinned_result(npix)
+            n_extra = table.n_extra
+            pieces_waited = 0
+            d_map.record_stream(main)
+            p_prev = q_prev = 0
+
+            def regrid_to(p_k):
+                nonlocal pieces_waited, p_prev
+                if p_k <= p_prev:
+                    return False
+                need = min(K, -(-p_k // piece))     # map pieces covering [0, p_k)
+                while pieces_waited < need:
+                    main.wait_event(ev_h2d[pieces_waited])
+                    pieces_waited += 1
+                _lib.check(L.bfg_shell_regrid_range(NSIDE, _lib.ptr(d_map), _lib.ptr(d_off), npix, _lib.ptr(d_new),
+                                                    p_prev, p_k, st))
+                p_prev = p_k
+                return True
+
+            def download_to(q_k):
+                nonlocal q_prev
+                if q_k <= q_prev:
+                    return
+                side.wait_event(main.record_event())
+                with torch.cuda.stream(side):
+                    out[q_prev:q_k].copy_(d_new[q_prev:q_k], non_blocking=True)
+                q_prev = q_k
+
+            for k in range(K):
+                b0, b1 = bounds[k], bounds[k + 1]
+                if b1 > b0:
+                    _lib.check(L.bfg_shell_offsets(table.handle, NSIDE, b1 - b0, d_rec.data_ptr() + 8 * _lib.HALO_STRIDE * b0,
+                                                   None if d_ext is None else d_ext.data_ptr() + 8 * n_extra * b0, n_extra,
+                                                   _lib.ptr(d_off), 0, npix, d_nb.data_ptr() + 8 * k, st))
+                if k + 1 == K:
+                    break
+                # every halo not yet processed has theta >= edge band * band width; its disc reaches rho_max further north
+                th_done = edges[k + 1] * SKY_BAND_RAD - rho_max - 3 * pix_rad
+                if th_done > 0 and regrid_to(first_pixel_at_colatitude(NSIDE, th_done)):
+                    th_copy = th_done - self.PIPELINE_MARGIN_RAD - 3 * pix_rad
+                    if th_copy > 0:
+                        download_to(first_pixel_at_colatitude(NSIDE, th_copy))
+            regrid_to(npix)
+            d_sums = torch.zeros(2, dtype=torch.float64, device=dev)
+            _lib.check(L.bfg_sum_f64(_lib.ptr(d_new), npix, _lib.ptr(d_sums), st))
+            _lib.check(L.bfg_sum_f64(_lib.ptr(d_map), npix, d_sums.data_ptr() + 8, st))   # regrid_to(npix) waited for every piece
+            _lib.check(L.bfg_offsets_max_norm2(_lib.ptr(d_off), npix, 0, npix, _lib.ptr(d_max), st))
+            download_to(npix)
+            d_new.record_stream(side)
+            sums = d_sums.cpu()
+            n_up = int(d_nb.sum().cpu())
+            max_norm = float(np.sqrt(float(d_max.cpu()[0])))
+            side.synchronize()
+            if not (max_norm < self.PIPELINE_MARGIN_RAD):
+                # the re-binning moved mass further than assumed: parts of the map were downloaded too early
+                out.copy_(d_new, non_blocking=True)
+                main.synchronize()
+        _give_scratch(getattr(self, '_scratch_inflight', []))
+        self._scratch_inflight = []
+        new_sum, old_sum = float(sums[0]), float(sums[1])
+        self.last_stats = dict(n_updates=n_up, new_sum=new_sum, old_sum=old_sum, pipelined=True, max_offset=max_norm)
+        self.last_timing = dict(host_prep_s=0.0)
+        assert np.isclose(new_sum, old_sum), \
+            "ERROR in pixel regridding, sum(new_map) [%0.14e] != sum(oldmap) [%0.14e]" % (new_sum, old_sum)   # :368-370
+        return out_np
+
     def process(self):
         torch = _torch()
         orig_map = self.LightconeShell.map
         NSIDE = self.LightconeShell.NSIDE
         if _all_close_to_zero(orig_map):             # :293-294 returns the input object
             return orig_map
+        import os
+        if (self.pix_range is None and self.sort_halos and os.environ.get("BFG_PIPELINE", "1") == "1"
+                and os.environ.get("BFG_PROFILE_E2E") != "1"
+                and self.HaloLightConeCatalog.cat.size >= self.PIPELINE_MIN_HALOS):
+            return self._process_pipelined()
         dev = self._device()
         L = _lib.lib()
         npix = orig_map.size

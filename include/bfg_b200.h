@@ -155,6 +155,18 @@ int bfg_anis_background(int64_t n, const double *d_mtot, double mtot_add, const 
 int bfg_shell_regrid(int nside, const double *d_map_in, const double *d_offsets, double *d_map_out, int64_t pix_lo,
                      int64_t pix_hi, void *stream);
 
+/* bfg_shell_regrid for a SOURCE pixel range [src_lo, src_hi) of FULL-size arrays: d_map_in (npix), d_offsets [3][comp_stride]
+ * (comp_stride >= src_hi), d_map_out (npix, zeroed once by the caller).  The pipelined BaryonifyShell.process re-bins and
+ * downloads the rings whose offsets are already final while the halo loop is still working on more southern halos. */
+int bfg_shell_regrid_range(int nside, const double *d_map_in, const double *d_offsets, int64_t comp_stride,
+                           double *d_map_out, int64_t src_lo, int64_t src_hi, void *stream);
+/* *d_out = max_p |offset_p|^2 over p in [lo, hi) (NaN counts as +inf): bounds how far the re-binning moves mass. */
+int bfg_offsets_max_norm2(const double *d_offsets, int64_t comp_stride, int64_t lo, int64_t hi, double *d_out, void *stream);
+/* For sky-sorted records (bfg_halo_sort, band width `band`): d_bounds[e] = first record whose colatitude band
+ * floor(theta / band) >= d_edge_band[e]; *d_rho_max = largest disc radius.  Cuts the halo loop into latitude chunks. */
+int bfg_halo_band_bounds(int64_t n_halo, const double *d_sorted_halos, double band, int n_edges, const int64_t *d_edge_band,
+                         int64_t *d_bounds, double *d_rho_max, void *stream);
+
 /* Multi-GPU form of bfg_shell_regrid (one process per GPU, ring-range sharding): the re-binning fused with its exchange
  * step.  h_slices[r] points at rank r's owned slice [h_bounds[r], h_bounds[r+1]) of the NEW map -- local memory for
  * r == self, CUDA-IPC peer mappings otherwise (bfg_shared_alloc / bfg_ipc_export / bfg_ipc_import) -- and every deposit

@@ -417,3 +417,41 @@ def test_grid3d_tile_gather_matches_scatter_and_oracle(monkeypatch):
                                      rp.ProfileTable(gaxes, pvals * 3.0, pvals))
     assert prun.last_stats["n_updates"] == n_wp
     assert_close(got_p, want_p, "PaintProfilesGrid (tiles) vs oracle port")
+
+
+def test_pipelined_process_equals_plain_process(monkeypatch):
+    """The latitude-chunked end-to-end path of BaryonifyShell.process (halo loop, re-binning and download of finished rings
+    overlapped) returns the same map as the plain path and as the oracle port -- including its fallback when the re-binning
+    moves mass further than the assumed margin."""
+    import baryonforge_b200 as b
+    from oracle import runners_port as rp
+    nside, n = 128, 3000
+    cat, shell, model, axes, vals = _fresh_shell_case(nside, n, 55, 20, 20)
+    monkeypatch.setenv("BFG_PIPELINE", "0")
+    plain = b.BaryonifyShell(cat, shell, 20, model, verbose=False)
+    want = plain.process()
+    assert not plain.last_stats.get("pipelined", False)
+    monkeypatch.setenv("BFG_PIPELINE", "1")
+    run = b.BaryonifyShell(cat, shell, 20, model, verbose=False)
+    run.PIPELINE_MIN_HALOS = 0
+    got = run.process()
+    assert run.last_stats["pipelined"] and run.last_stats["n_updates"] == plain.last_stats["n_updates"]
+    assert 0 < run.last_stats["max_offset"] < run.PIPELINE_MARGIN_RAD
+    assert_close(got, want, "pipelined vs plain", rtol=1e-9, atol_scale=1e-12)
+    sc = run.last_scalars
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        map_w = rp.baryonify_shell(nside, shell.map, cat.cat, sc["R_run"], sc["D_A"], sc["R_model_com"], 20,
+                                   rp.DisplacementTable(axes, vals, 20), warn=False)
+    assert_close(got, map_w, "pipelined vs oracle port")
+    # margin violated on purpose -> the whole map is downloaded again at the end
+    fb = b.BaryonifyShell(cat, shell, 20, model, verbose=False)
+    fb.PIPELINE_MIN_HALOS = 0
+    fb.PIPELINE_MARGIN_RAD = 1e-12
+    assert_close(fb.process(), want, "pipelined fallback", rtol=1e-9, atol_scale=1e-12)
+    # few chunks / many chunks
+    for K in (2, 19):
+        r2 = b.BaryonifyShell(cat, shell, 20, model, verbose=False)
+        r2.PIPELINE_MIN_HALOS = 0
+        r2.PIPELINE_CHUNKS = K
+        assert_close(r2.process(), want, f"pipelined K={K}", rtol=1e-9, atol_scale=1e-12)
