@@ -544,7 +544,10 @@ class BaryonifyShell(DefaultRunner):
             st = _lib.current_stream()
             main = torch.cuda.current_stream()
             side = _side_stream(dev)
+            import time
+            t0 = time.perf_counter()
             d_rec = self.device_records(False, dev)
+            host_prep_s = time.perf_counter() - t0
             ext = _extras(cat, keys)
             d_ext = None if ext is None else _to_device(ext, dev)
             d_rec, d_ext = _sort_records(d_rec, d_ext, 0, SKY_BAND_RAD)
@@ -634,7 +637,7 @@ class BaryonifyShell(DefaultRunner):
         self._scratch_inflight = []
         new_sum, old_sum = float(sums[0]), float(sums[1])
         self.last_stats = dict(n_updates=n_up, new_sum=new_sum, old_sum=old_sum, pipelined=True, max_offset=max_norm)
-        self.last_timing = dict(host_prep_s=0.0)
+        self.last_timing = dict(host_prep_s=host_prep_s, chunks=float(K))
         assert np.isclose(new_sum, old_sum), \
             "ERROR in pixel regridding, sum(new_map) [%0.14e] != sum(oldmap) [%0.14e]" % (new_sum, old_sum)   # :368-370
         return out_np
