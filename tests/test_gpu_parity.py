@@ -455,3 +455,50 @@ def test_pipelined_process_equals_plain_process(monkeypatch):
         r2.PIPELINE_MIN_HALOS = 0
         r2.PIPELINE_CHUNKS = K
         assert_close(r2.process(), want, f"pipelined K={K}", rtol=1e-9, atol_scale=1e-12)
+
+
+def test_full_size_properties_nside4096(monkeypatch):
+    """BASELINE's map size (NSIDE = 4096, 2.0e8 pixels) with 3e5 halos -- large enough that process() takes the pipelined
+    path on its own.  Size-independent properties (SURVEY.md §8d 'parity at scale'): mass conservation (the reference's own
+    assert), pipelined == plain path, update count == sum of device disc sizes, linearity in the input map, and a zero
+    table leaves the map unchanged."""
+    import torch
+    import baryonforge_b200 as b
+    from baryonforge_b200 import healpix as dh, synth
+    nside, n = 4096, 300000
+    ra, dec, M, z = synth.sky_halos(n, seed=77)
+    axes = synth.table_axes()
+    vals = synth.displacement_values(axes)
+    npix = 12 * nside * nside
+    hmap = synth.shell_map(nside, seed=78)
+    cat = b.HaloLightConeCatalog(ra=ra, dec=dec, M=M, z=z, cosmo=synth.COSMO)
+    shell = b.LightconeShell(map=hmap, cosmo=synth.COSMO)
+    model = b.DisplacementModel(axes, vals, 20, synth.COSMO)
+    run = b.BaryonifyShell(cat, shell, 20, model, verbose=False)
+    got = run.process()
+    assert run.last_stats["pipelined"]
+    assert np.isclose(run.last_stats["new_sum"], run.last_stats["old_sum"], rtol=1e-12)
+    n_up = run.last_stats["n_updates"]
+    # update count == sum_j |query_disc_j| (discs this large never take the < 4-pixel fallback)
+    rec = run.device_records(False)
+    counts = torch.empty(n, dtype=torch.int64, device=rec.device)
+    from baryonforge_b200 import _lib
+    _lib.check(_lib.lib().bfg_healpix_disc_counts(nside, n, rec.data_ptr(), counts.data_ptr(), _lib.current_stream()))
+    assert int(counts.sum().item()) == n_up and int(counts.min().item()) >= 4
+    monkeypatch.setenv("BFG_PIPELINE", "0")
+    plain_run = b.BaryonifyShell(cat, shell, 20, model, verbose=False)
+    plain = plain_run.process()
+    monkeypatch.delenv("BFG_PIPELINE")
+    assert plain_run.last_stats["n_updates"] == n_up
+    assert_close(got, plain, "pipelined vs plain at NSIDE=4096", rtol=1e-9, atol_scale=1e-12)
+    del plain
+    # linearity in the map: the offsets do not depend on it
+    shell3 = b.LightconeShell(map=3.0 * hmap, cosmo=synth.COSMO)
+    got3 = b.BaryonifyShell(cat, shell3, 20, model, verbose=False).process()
+    assert_close(got3, 3.0 * got, "linearity", rtol=1e-9, atol_scale=1e-12)
+    del got3
+    zero = b.DisplacementModel(axes, np.zeros_like(vals), 20, synth.COSMO)
+    ident = b.BaryonifyShell(cat, shell, 20, zero, verbose=False).process()
+    # not bit-exact in the reference either: the re-binning goes radians -> degrees -> radians (HealpixRunner.py:358,361),
+    # which at 0.86-arcmin pixels leaves ~1e-9 of a pixel's mass on its neighbours
+    assert_close(ident, hmap, "zero table = identity", rtol=1e-6, atol_scale=1e-8)
