@@ -149,7 +149,7 @@ struct __align__(16) RingSeg {
     double pz, sD;         // z * D, sin(theta) * D
     double phase0, inv2nr; // azimuth of pixel ip_lo in half-turns, 2 / nr
     double c0, s0;         // cos / sin of phase0 (equatorial rings)
-    double rotC, rotS;     // cos / sin of the azimuth step of one loop iteration (32 pixels; FAST_GW in the fast path)
+    double rotC, rotS;     // cos / sin of the azimuth step of one loop iteration (32 pixels; the lane-group width in the fast path)
     double dz, dz2;        // fast path: z - vz of the halo and its square (unit-sphere chord, see ring_pixels_fast)
 };
 
@@ -218,22 +218,24 @@ __device__ __forceinline__ FastHalo make_fast(const TableView &T, const HaloSph 
     return f;
 }
 
-// Lanes per ring in the fast path: a warp walks 32 / FAST_GW rings at once, FAST_GW consecutive pixels of each per
-// iteration.  Disc chords are short (34 pixels on average for a mass-function-like catalogue, ~105 for the flat one), so
+// Lanes per ring in the fast path: a warp walks 32 / GW rings at once, GW consecutive pixels of each per iteration.  Disc chords are short (34 pixels on average for a mass-function-like catalogue, ~105 for the flat one), so
 // narrow groups keep the lanes busy (34 pixels: 53 % of the lane slots with 32-wide groups, 85 % with 8-wide ones) and
 // the per-ring set-up is paid once per FOUR rings.  The REDs of a group still cover whole 32-byte sectors.
-constexpr int FAST_GW = 8;
+// 8 lanes per ring for small discs, 16 for large ones (measured: flat catalogue 110.3 / 105.8 / 102.5 ms with 32 / 8 / 16
+// lanes, mass-function-like catalogue 25.2 / 20.6 / 22.0 ms); chosen per halo from the disc's mean chord.
+constexpr int GW_SMALL = 8, GW_LARGE = 16;
+constexpr double GW_CHORD_SPLIT = 80.0;       // mean chord [pixels] above which GW_LARGE is used
 
-// One contiguous span of a ring (no wrap): lane handles pixels p0, p0 + FAST_GW, ... < pend;  (cs, sn) = azimuth of *p0.
+// One contiguous span of a ring (no wrap): lane handles pixels p0, p0 + GW, ... < pend;  (cs, sn) = azimuth of *p0.
 // p0 / pend point into component 0 of the offsets; components 1, 2 live nloc8 and 2 nloc8 bytes further.
 // CHECK: the ring straddles the owned pixel range [own_lo, own_hi) (ring-range sharding) -- same arithmetic, so results
 // do not depend on how the map is sharded.
-template <bool CHECK>
+template <bool CHECK, int GW>
 __device__ __forceinline__ void span_pixels_fast(const FastHalo &f, const RingSeg &g, double cs, double sn,
                                                  double *__restrict__ p0, const double *__restrict__ pend, i64 nloc8,
                                                  const double *own_lo = nullptr, const double *own_hi = nullptr) {
     const double z = g.z, sth = g.sth, dz = g.dz, dz2 = g.dz2, rotC = g.rotC, rotS = g.rotS;
-    for (; p0 < pend; p0 += FAST_GW) {
+    for (; p0 < pend; p0 += GW) {
         const double x = sth * cs, y = sth * sn;
         const double dx = x - f.vx, dy = y - f.vy;
         const double r2 = fma(dx, dx, fma(dy, dy, dz2));             // |vec - vec_j|^2   HealpixRunner.py:338-341
@@ -251,10 +253,67 @@ __device__ __forceinline__ void span_pixels_fast(const FastHalo &f, const RingSe
             red_add((double *)((char *)p0 + nloc8), fma(ny, ninv, -y));
             red_add((double *)((char *)p0 + 2 * nloc8), fma(nz, ninv, -z));
         }
-        const double c2 = cs * rotC - sn * rotS;                     // advance the azimuth by FAST_GW pixels
+        const double c2 = cs * rotC - sn * rotS;                     // advance the azimuth by GW pixels
         sn = fma(sn, rotC, cs * rotS);
         cs = c2;
     }
+}
+
+// Fast ring walk of one staged chunk: warp w takes ring groups w, w + 4, ...; inside a group of 32 / GW rings each ring
+// gets GW lanes.  Returns the number of (halo, pixel) updates owned by this lane.
+template <int GW>
+__device__ __forceinline__ i64 walk_rings_fast(const FastHalo &fh, const RingSeg *__restrict__ segs, int nseg, bool valid,
+                                               bool sharded, double eqC, double eqS, double *__restrict__ out, i64 nloc,
+                                               i64 nloc8) {
+    constexpr int NG = 32 / GW;
+    const int lane = threadIdx.x & 31;
+    const int li = lane & (GW - 1), gi = lane / GW;
+    i64 done = 0;
+    for (int rb0 = (threadIdx.x >> 5) * NG; rb0 < nseg; rb0 += (SHELL_THREADS / 32) * NG) {
+        const int r = rb0 + gi;
+        if (r >= nseg) continue;
+        const RingSeg &g = segs[r];
+        if (!g.active) continue;
+        const int cnt = g.cnt;
+        // updates of this ring owned by this lane (the pixel loop itself carries no counter)
+        if (!(g.flags & 1)) {
+            done += (cnt > li) ? ((cnt - li + GW - 1) / GW) : 0;
+        } else {
+            int ip = g.ip_lo + li;
+            if (ip >= g.nr) ip -= g.nr;
+            for (int i = li; i < cnt; i += GW) {
+                done += ((unsigned long long)(g.lbase + ip) < (unsigned long long)nloc) ? 1 : 0;
+                ip += GW;
+                if (ip >= g.nr) ip -= g.nr;
+            }
+        }
+        if (!valid) continue;   // halo outside the table in (z, M, extras): every read-out is NaN -> adds nothing
+        double cs, sn;
+        if (g.flags & 2) {      // equatorial: rotate the staged (c0, s0) by this lane's cached step
+            cs = g.c0 * eqC - g.s0 * eqS;
+            sn = fma(g.s0, eqC, g.c0 * eqS);
+        } else {
+            sincospi(fma((double)li, g.inv2nr, g.phase0), &sn, &cs);
+        }
+        // span A: [ip_lo, min(ip_lo + cnt, nr)); span B (disc straddles phi = 0): [0, ip_lo + cnt - nr)
+        const int endA = min(g.ip_lo + cnt, g.nr);
+        const int endB = g.ip_lo + cnt - g.nr;
+        double *rbp = out + g.lbase;
+        if (!sharded) {
+            span_pixels_fast<false, GW>(fh, g, cs, sn, rbp + g.ip_lo + li, rbp + endA, nloc8);
+            if (endB > 0) {
+                sincospi(((double)li + ((g.flags & 4) ? 0.5 : 0.0)) * g.inv2nr, &sn, &cs);
+                span_pixels_fast<false, GW>(fh, g, cs, sn, rbp + li, rbp + endB, nloc8);
+            }
+        } else {                // ring-range sharding: pixels outside the owned range are masked per lane
+            span_pixels_fast<true, GW>(fh, g, cs, sn, rbp + g.ip_lo + li, rbp + endA, nloc8, out, out + nloc);
+            if (endB > 0) {
+                sincospi(((double)li + ((g.flags & 4) ? 0.5 : 0.0)) * g.inv2nr, &sn, &cs);
+                span_pixels_fast<true, GW>(fh, g, cs, sn, rbp + li, rbp + endB, nloc8, out, out + nloc);
+            }
+        }
+    }
+    return done;
 }
 
 template <int MODE, bool UNIFORM>
@@ -263,7 +322,7 @@ k_shell_halos(TableView T, Hpx h, i64 n_halo, const double *__restrict__ halos, 
               int n_extra, double *__restrict__ out, i64 pix_lo, i64 pix_hi, unsigned long long *nupd,
               const double2 *__restrict__ g_l2tab, AnisArgs A, unsigned long long *queue) {
     constexpr bool PAINT = (MODE != MODE_BARYONIFY);
-    constexpr bool FAST = (MODE == MODE_BARYONIFY) && UNIFORM;   // span_pixels_fast: FAST_GW lanes per ring
+    constexpr bool FAST = (MODE == MODE_BARYONIFY) && UNIFORM;   // span_pixels_fast: 8 or 16 lanes per ring
     extern __shared__ double row[];
     __shared__ i64 s_j;
     const double *row2 = row + ((MODE == MODE_ANIS) ? T.n[2] : 0);   // anis: the tracer row follows the paint row
@@ -277,7 +336,7 @@ k_shell_halos(TableView T, Hpx h, i64 n_halo, const double *__restrict__ halos, 
     asm volatile("" : "+l"(nloc8));   // keep the component stride in a register pair (else recomputed per pixel)
     // azimuth of `lane` pixels on an equatorial ring (every equatorial ring has 4 nside pixels): computed once
     double eqC, eqS;
-    sincospi((double)(FAST ? (lane & (FAST_GW - 1)) : lane) * (2.0 / (double)h.nl4), &eqS, &eqC);
+    sincospi((double)lane * (2.0 / (double)h.nl4), &eqS, &eqC);   // (fast path: re-derived per halo for its lane group width)
     i64 done = 0;
     const bool sharded = pix_lo > 0 || pix_hi < h.npix;
 
@@ -304,7 +363,12 @@ k_shell_halos(TableView T, Hpx h, i64 n_halo, const double *__restrict__ halos, 
             u2 = make_upd(A.T2, s);
         }
         FastHalo fh;
-        if (MODE == MODE_BARYONIFY && UNIFORM) fh = make_fast(T, s, u, row, l2tab);
+        // lane-group width of the fast path from the disc's mean chord (pi/4 of its diameter) in pixels
+        const bool gw_small = (0.7853981633974483 * 2.0 * s.radius) * sqrt((double)h.npix * 0.07957747154594767) < GW_CHORD_SPLIT;
+        if (FAST) {
+            fh = make_fast(T, s, u, row, l2tab);
+            sincospi((double)(lane & ((gw_small ? GW_SMALL : GW_LARGE) - 1)) * (2.0 / (double)h.nl4), &eqS, &eqC);
+        }
         // `if pixind.size < 4` (HealpixRunner.py:333) can only trigger for discs of a few pixels (<= ~12 rings)
         const bool tiny = !PAINT && (s.radius * s.radius * (double)h.npix * 0.25 < 64.0);
 
@@ -360,7 +424,7 @@ k_shell_halos(TableView T, Hpx h, i64 n_halo, const double *__restrict__ halos, 
                         g.inv2nr = 2.0 / (double)nr;
                         g.phase0 = ((double)ip_lo + (sh ? 0.5 : 0.0)) * g.inv2nr;
                         sincospi(g.phase0, &g.s0, &g.c0);
-                        sincospi((FAST ? (double)FAST_GW : 32.0) * g.inv2nr, &g.rotS, &g.rotC);
+                        sincospi((FAST ? (gw_small ? (double)GW_SMALL : (double)GW_LARGE) : 32.0) * g.inv2nr, &g.rotS, &g.rotC);
                     }
                 }
                 segs[threadIdx.x] = g;
@@ -368,54 +432,10 @@ k_shell_halos(TableView T, Hpx h, i64 n_halo, const double *__restrict__ halos, 
             __syncthreads();  // segments + row ready
             const int nseg = (int)min((i64)RING_CHUNK, d.rb - base + 1);
 
-            // ---- fast path: each warp walks 32 / FAST_GW rings at once, FAST_GW lanes per ring --------------------
+            // ---- fast path: each warp walks 32 / GW rings at once, GW lanes per ring ------------------------------------
             if (FAST) {
-                constexpr int NG = 32 / FAST_GW;
-                const int li = lane & (FAST_GW - 1), gi = lane / FAST_GW;
-                for (int rb0 = (threadIdx.x >> 5) * NG; rb0 < nseg; rb0 += (SHELL_THREADS / 32) * NG) {
-                    const int r = rb0 + gi;
-                    if (r >= nseg) continue;
-                    const RingSeg &g = segs[r];
-                    if (!g.active) continue;
-                    const int cnt = g.cnt;
-                    // updates of this ring owned by this lane (the pixel loop itself carries no counter)
-                    if (!(g.flags & 1)) {
-                        done += (cnt > li) ? ((cnt - li + FAST_GW - 1) / FAST_GW) : 0;
-                    } else {
-                        int ip = g.ip_lo + li;
-                        if (ip >= g.nr) ip -= g.nr;
-                        for (int i = li; i < cnt; i += FAST_GW) {
-                            done += ((unsigned long long)(g.lbase + ip) < (unsigned long long)nloc) ? 1 : 0;
-                            ip += FAST_GW;
-                            if (ip >= g.nr) ip -= g.nr;
-                        }
-                    }
-                    if (!valid) continue;   // halo outside the table in (z, M, extras): every read-out is NaN -> adds nothing
-                    double cs, sn;
-                    if (g.flags & 2) {      // equatorial: rotate the staged (c0, s0) by this lane's cached step
-                        cs = g.c0 * eqC - g.s0 * eqS;
-                        sn = fma(g.s0, eqC, g.c0 * eqS);
-                    } else {
-                        sincospi(fma((double)li, g.inv2nr, g.phase0), &sn, &cs);
-                    }
-                    // span A: [ip_lo, min(ip_lo + cnt, nr)); span B (disc straddles phi = 0): [0, ip_lo + cnt - nr)
-                    const int endA = min(g.ip_lo + cnt, g.nr);
-                    const int endB = g.ip_lo + cnt - g.nr;
-                    double *rbp = out + g.lbase;
-                    if (!sharded) {
-                        span_pixels_fast<false>(fh, g, cs, sn, rbp + g.ip_lo + li, rbp + endA, nloc8);
-                        if (endB > 0) {
-                            sincospi(((double)li + ((g.flags & 4) ? 0.5 : 0.0)) * g.inv2nr, &sn, &cs);
-                            span_pixels_fast<false>(fh, g, cs, sn, rbp + li, rbp + endB, nloc8);
-                        }
-                    } else {                // ring-range sharding: pixels outside the owned range are masked per lane
-                        span_pixels_fast<true>(fh, g, cs, sn, rbp + g.ip_lo + li, rbp + endA, nloc8, out, out + nloc);
-                        if (endB > 0) {
-                            sincospi(((double)li + ((g.flags & 4) ? 0.5 : 0.0)) * g.inv2nr, &sn, &cs);
-                            span_pixels_fast<true>(fh, g, cs, sn, rbp + li, rbp + endB, nloc8, out, out + nloc);
-                        }
-                    }
-                }
+                if (gw_small) done += walk_rings_fast<GW_SMALL>(fh, segs, nseg, valid, sharded, eqC, eqS, out, nloc, nloc8);
+                else done += walk_rings_fast<GW_LARGE>(fh, segs, nseg, valid, sharded, eqC, eqS, out, nloc, nloc8);
             }
             // ---- generic path: warps take rings round-robin; lanes walk consecutive pixels ------------------------
             // static round-robin: neighbouring rings have neighbouring lengths, so the 4 warps stay balanced without a
