@@ -197,17 +197,18 @@ __device__ __forceinline__ void ring_pixels(const TableView &T, const double *__
 struct FastHalo {
     double vx, vy;        // halo unit vector (vz enters through RingSeg.dz)
     double rcut2;         // (model eps * R_com * a / D)^2  on the unit sphere
-    double aD;            // a / D
+    double aD;            // a / D   (paint: the record's SCALE, pixarea * D^2 or 1)
     RowLookup t;          // cell coordinate u = log2(|d|^2) * uA + uB   (uB includes ln D and ln(1/a) [- ln R_com])
 };
 
+template <bool PAINT>
 __device__ __forceinline__ FastHalo make_fast(const TableView &T, const HaloSph &s, const HaloUpd &u, const double *row,
                                               const double2 *l2tab) {
     FastHalo f;
     f.vx = s.vx; f.vy = s.vy;
     const double rc = s.rcut * s.a / s.D;
     f.rcut2 = rc * rc;
-    f.aD = s.a / s.D;
+    f.aD = PAINT ? s.scale : s.a / s.D;
     f.t.uA = u.uA;
     f.t.uB = fma(2.0 * log2(s.D), u.uA, u.uB);      // log2 r_sep^2 = log2 |d|^2 + 2 log2 D
     f.t.uMax = u.uMax;
@@ -259,9 +260,32 @@ __device__ __forceinline__ void span_pixels_fast(const FastHalo &f, const RingSe
     }
 }
 
+// PaintProfilesShell counterpart of span_pixels_fast (HealpixRunner.py:464-481): map[p] += exp(table(ln(r_sep / a))) * SCALE,
+// non-finite read-outs (outside the table, log of a zero or negative profile) contribute nothing.
+template <bool CHECK, int GW>
+__device__ __forceinline__ void span_pixels_paint(const FastHalo &f, const RingSeg &g, double cs, double sn,
+                                                  double *__restrict__ p0, const double *__restrict__ pend,
+                                                  const double *own_lo = nullptr, const double *own_hi = nullptr) {
+    const double sth = g.sth, dz2 = g.dz2, rotC = g.rotC, rotS = g.rotS;
+    for (; p0 < pend; p0 += GW) {
+        const double dx = fma(sth, cs, -f.vx), dy = fma(sth, sn, -f.vy);
+        const double r2 = fma(dx, dx, fma(dy, dy, dz2));             // |vec - vec_j|^2   HealpixRunner.py:466-469
+        bool ok;
+        double val = exp(row_at_r2(f.t, r2, ok));                    // Tabulate.py:319
+        val *= f.aD;                                                 // :478 (SCALE)
+        // :473 non-finite -> 0; exact zeros add nothing (one integer test on the exponent field covers NaN, inf and 0)
+        ok = ok && ((((unsigned)__double2hiint(val) & 0x7fffffffu) - 1u) < 0x7fefffffu);
+        if (CHECK) ok = ok && (p0 >= own_lo) && (p0 < own_hi);
+        if (ok) red_add(p0, val);                                    // :481
+        const double c2 = cs * rotC - sn * rotS;                     // advance the azimuth by GW pixels
+        sn = fma(sn, rotC, cs * rotS);
+        cs = c2;
+    }
+}
+
 // Fast ring walk of one staged chunk: warp w takes ring groups w, w + 4, ...; inside a group of 32 / GW rings each ring
 // gets GW lanes.  Returns the number of (halo, pixel) updates owned by this lane.
-template <int GW>
+template <int GW, bool PAINT>
 __device__ __forceinline__ i64 walk_rings_fast(const FastHalo &fh, const RingSeg *__restrict__ segs, int nseg, bool valid,
                                                bool sharded, double eqC, double eqS, double *__restrict__ out, i64 nloc,
                                                i64 nloc8) {
@@ -299,7 +323,21 @@ __device__ __forceinline__ i64 walk_rings_fast(const FastHalo &fh, const RingSeg
         const int endA = min(g.ip_lo + cnt, g.nr);
         const int endB = g.ip_lo + cnt - g.nr;
         double *rbp = out + g.lbase;
-        if (!sharded) {
+        if (PAINT) {
+            if (!sharded) {
+                span_pixels_paint<false, GW>(fh, g, cs, sn, rbp + g.ip_lo + li, rbp + endA);
+                if (endB > 0) {
+                    sincospi(((double)li + ((g.flags & 4) ? 0.5 : 0.0)) * g.inv2nr, &sn, &cs);
+                    span_pixels_paint<false, GW>(fh, g, cs, sn, rbp + li, rbp + endB);
+                }
+            } else {
+                span_pixels_paint<true, GW>(fh, g, cs, sn, rbp + g.ip_lo + li, rbp + endA, out, out + nloc);
+                if (endB > 0) {
+                    sincospi(((double)li + ((g.flags & 4) ? 0.5 : 0.0)) * g.inv2nr, &sn, &cs);
+                    span_pixels_paint<true, GW>(fh, g, cs, sn, rbp + li, rbp + endB, out, out + nloc);
+                }
+            }
+        } else if (!sharded) {
             span_pixels_fast<false, GW>(fh, g, cs, sn, rbp + g.ip_lo + li, rbp + endA, nloc8);
             if (endB > 0) {
                 sincospi(((double)li + ((g.flags & 4) ? 0.5 : 0.0)) * g.inv2nr, &sn, &cs);
@@ -322,7 +360,7 @@ k_shell_halos(TableView T, Hpx h, i64 n_halo, const double *__restrict__ halos, 
               int n_extra, double *__restrict__ out, i64 pix_lo, i64 pix_hi, unsigned long long *nupd,
               const double2 *__restrict__ g_l2tab, AnisArgs A, unsigned long long *queue) {
     constexpr bool PAINT = (MODE != MODE_BARYONIFY);
-    constexpr bool FAST = (MODE == MODE_BARYONIFY) && UNIFORM;   // span_pixels_fast: 8 or 16 lanes per ring
+    constexpr bool FAST = (MODE != MODE_ANIS) && UNIFORM;        // span_pixels_fast / _paint: 8 or 16 lanes per ring
     extern __shared__ double row[];
     __shared__ i64 s_j;
     const double *row2 = row + ((MODE == MODE_ANIS) ? T.n[2] : 0);   // anis: the tracer row follows the paint row
@@ -366,7 +404,7 @@ k_shell_halos(TableView T, Hpx h, i64 n_halo, const double *__restrict__ halos, 
         // lane-group width of the fast path from the disc's mean chord (pi/4 of its diameter) in pixels
         const bool gw_small = (0.7853981633974483 * 2.0 * s.radius) * sqrt((double)h.npix * 0.07957747154594767) < GW_CHORD_SPLIT;
         if (FAST) {
-            fh = make_fast(T, s, u, row, l2tab);
+            fh = make_fast<PAINT>(T, s, u, row, l2tab);
             sincospi((double)(lane & ((gw_small ? GW_SMALL : GW_LARGE) - 1)) * (2.0 / (double)h.nl4), &eqS, &eqC);
         }
         // `if pixind.size < 4` (HealpixRunner.py:333) can only trigger for discs of a few pixels (<= ~12 rings)
@@ -434,8 +472,8 @@ k_shell_halos(TableView T, Hpx h, i64 n_halo, const double *__restrict__ halos, 
 
             // ---- fast path: each warp walks 32 / GW rings at once, GW lanes per ring ------------------------------------
             if (FAST) {
-                if (gw_small) done += walk_rings_fast<GW_SMALL>(fh, segs, nseg, valid, sharded, eqC, eqS, out, nloc, nloc8);
-                else done += walk_rings_fast<GW_LARGE>(fh, segs, nseg, valid, sharded, eqC, eqS, out, nloc, nloc8);
+                if (gw_small) done += walk_rings_fast<GW_SMALL, PAINT>(fh, segs, nseg, valid, sharded, eqC, eqS, out, nloc, nloc8);
+                else done += walk_rings_fast<GW_LARGE, PAINT>(fh, segs, nseg, valid, sharded, eqC, eqS, out, nloc, nloc8);
             }
             // ---- generic path: warps take rings round-robin; lanes walk consecutive pixels ------------------------
             // static round-robin: neighbouring rings have neighbouring lengths, so the 4 warps stay balanced without a
