@@ -194,6 +194,10 @@ int bfg_copy_to_host_async(void *h_dst, const void *d_src, int64_t bytes, void *
 /* ---- periodic grids (2-D / 3-D) ------------------------------------------------------------------- */
 /* Halo loop of BaryonifyGrid.process (Map2DRunner.py:482-586).  d_offsets is [ndim][N^ndim] in units of cells,
  * restricted to axis-0 planes [plane_lo, plane_hi) (slab); NaNs propagate as in the reference.
+ * 3-D grids whose size is a multiple of 16 (and plane_lo of 8) with a uniform ln r axis run the tile-centric gather
+ * (csrc/grid_tile_kernels.cu: every cell written once); that path sizes its halo-per-tile list on the host, i.e. the call
+ * synchronises `stream` once and uses stream-ordered scratch (n_halo x NR doubles for the blended rows).  BFG_GRID_TILES=0
+ * in the environment forces the halo-centric scatter kernels.  Same for bfg_grid_paint.
  * use_ell (2-D only, Map2DRunner.py:281-350,531-536): d_extras rows carry, after the table's p_keys values, the 4 entries
  * (row-major) of the halo's shear matrix build_Rmat(A_ell, q_ell); n_extra counts them. */
 int bfg_grid_offsets(const bfg_table *t, int ndim, int64_t N, double res, int64_t n_halo, const double *d_halos,

@@ -172,3 +172,23 @@ def test_get_parameter_and_runner_pickling():
     grid_run = pickle.loads(pickle.dumps(b.PaintProfilesAnisGrid(nd, gm3, 5, inner, inner, inner, 1.0, 0.1, verbose=False)))
     with pytest.raises(AssertionError, match="2D maps"):      # Map2DRunner.py:847, raised before any GPU work
         grid_run.process()
+
+
+def test_first_pixel_at_colatitude_is_a_ring_start():
+    """Host helper of the pipelined BaryonifyShell.process: first pixel of the first ring at or south of a colatitude."""
+    rng = np.random.default_rng(6)
+    for nside in (1, 2, 16, 128):
+        npix = 12 * nside * nside
+        theta, _ = hpo.pix2ang(nside, np.arange(npix))
+        ring = parallel.ring_of_pixel(nside, np.arange(npix))
+        starts = np.flatnonzero(np.diff(ring, prepend=0) > 0)          # first pixel of every ring
+        assert parallel.first_pixel_at_colatitude(nside, 0.0) == 0
+        assert parallel.first_pixel_at_colatitude(nside, np.pi) == npix
+        for t in rng.uniform(1e-3, np.pi - 1e-3, 300):
+            p = parallel.first_pixel_at_colatitude(nside, t)
+            assert p == npix or p in starts
+            # every pixel before p lies strictly north of t, the ring starting at p does not
+            if p > 0:
+                assert theta[p - 1] < t + 1e-12
+            if p < npix:
+                assert theta[p] >= t - 1e-12
