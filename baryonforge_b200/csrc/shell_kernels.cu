@@ -1,13 +1,14 @@
 // shell_kernels.cu -- HEALPix-shell runners on sm_100a.
 //
-//   k_shell_halos<PAINT>  : the per-halo loop of BaryonifyShell.process  (BaryonForge/Runners/HealpixRunner.py:315-355)
-//                           and PaintProfilesShell.process              (BaryonForge/Runners/HealpixRunner.py:449-481)
-//   k_shell_regrid        : the re-binning step                         (BaryonForge/Runners/HealpixRunner.py:357-365, :17-71)
+//   k_shell_halos<MODE>   : the per-halo loop of BaryonifyShell.process        (BaryonForge/Runners/HealpixRunner.py:315-355),
+//                           PaintProfilesShell.process                        (BaryonForge/Runners/HealpixRunner.py:449-481)
+//                           and PaintProfilesAnisShell.process                (BaryonForge/Runners/HealpixRunner.py:589-631)
+//   k_shell_regrid[_range|_p2p] : the re-binning step                         (BaryonForge/Runners/HealpixRunner.py:357-365, :17-71)
 //
-// One CTA per halo: the CTA blends the halo's 2^(ndim-1) table rows into one radial row in shared memory, derives
-// the disc's ring range on the device (query_disc, no host round trip), and its warps walk (halo, ring) segments
-// with lanes over consecutive pixels of the ring, so the fp64 REDs of a warp hit consecutive addresses of the
-// component-major offsets array.
+// Persistent CTAs (148 SMs x 8) pull halos from a global queue.  Per halo the CTA blends the 2^(ndim-1) table rows into one
+// radial row in shared memory, derives the disc's ring range on the device (query_disc, no host round trip), stages the
+// per-ring constants, and its warps walk the rings -- 8 or 16 lanes per ring over consecutive pixels, so the fp64 REDs of a
+// lane group hit consecutive addresses of the component-major offsets array.
 #include <algorithm>
 #include <string.h>
 #include "bfg_common.cuh"
@@ -150,7 +151,7 @@ struct __align__(16) RingSeg {
     double phase0, inv2nr; // azimuth of pixel ip_lo in half-turns, 2 / nr
     double c0, s0;         // cos / sin of phase0 (equatorial rings)
     double rotC, rotS;     // cos / sin of the azimuth step of one loop iteration (32 pixels; the lane-group width in the fast path)
-    double dz, dz2;        // fast path: z - vz of the halo and its square (unit-sphere chord, see ring_pixels_fast)
+    double dz, dz2;        // fast path: z - vz of the halo and its square (unit-sphere chord, see span_pixels_fast)
 };
 
 template <int MODE, bool UNIFORM, bool CHECK>
@@ -502,9 +503,7 @@ k_shell_halos(TableView T, Hpx h, i64 n_halo, const double *__restrict__ halos, 
                 } else {
                     sincospi(fma((double)lane, g.inv2nr, g.phase0), &sn, &cs);
                 }
-                if (FAST) {
-                    // (handled above)
-                } else if (g.flags & 1) {
+                if (g.flags & 1) {
                     ring_pixels<MODE, UNIFORM, true>(T, row, u, g, cs, sn, lane, out, nloc, l2tab, A, row2, u2);
                 } else {
                     ring_pixels<MODE, UNIFORM, false>(T, row, u, g, cs, sn, lane, out, nloc, l2tab, A, row2, u2);
