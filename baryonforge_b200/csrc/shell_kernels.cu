@@ -216,8 +216,7 @@ __device__ __forceinline__ FastHalo make_fast(const TableView &T, const HaloSph 
     f.t.nrm2 = T.n[2] - 2;
     f.t.row_s = (unsigned)__cvta_generic_to_shared(row);
     f.t.l2_s = (unsigned)__cvta_generic_to_shared(l2tab);
-    launder(f.t);
-    return f;
+    return f;   // handed to the other warps through shared memory (HaloCtx), which also keeps ptxas from re-deriving it
 }
 
 // Lanes per ring in the fast path: a warp walks 32 / GW rings at once, GW consecutive pixels of each per iteration.  Disc chords are short (34 pixels on average for a mass-function-like catalogue, ~105 for the flat one), so
@@ -283,6 +282,16 @@ __device__ __forceinline__ void span_pixels_paint(const FastHalo &f, const RingS
         cs = c2;
     }
 }
+
+// Per-halo constants, computed ONCE per halo by warp 0 and read by the other warps from shared memory (they used to be
+// re-derived by all four warps: ~700 instructions each -- 5 cosines, 3 square roots, 2 divisions, a log2 -- which is a
+// fifth of all instructions for a catalogue of small discs).
+struct HaloCtx {
+    DiscRings d;
+    HaloUpd u;
+    FastHalo fh;
+    int gw_small, touches;
+};
 
 // Fast ring walk of one staged chunk: warp w takes ring groups w, w + 4, ...; inside a group of 32 / GW rings each ring
 // gets GW lanes.  Returns the number of (halo, pixel) updates owned by this lane.
@@ -373,27 +382,57 @@ k_shell_halos(TableView T, Hpx h, i64 n_halo, const double *__restrict__ halos, 
     const i64 nloc = pix_hi - pix_lo;
     i64 nloc8 = nloc * 8;
     asm volatile("" : "+l"(nloc8));   // keep the component stride in a register pair (else recomputed per pixel)
-    // azimuth of `lane` pixels on an equatorial ring (every equatorial ring has 4 nside pixels): computed once
+    // azimuth of `lane` pixels on an equatorial ring (every equatorial ring has 4 nside pixels): computed once; the fast
+    // path needs the offsets 0 .. GW-1 of its lane group instead, tabulated once for both group widths
     double eqC, eqS;
-    sincospi((double)lane * (2.0 / (double)h.nl4), &eqS, &eqC);   // (fast path: re-derived per halo for its lane group width)
+    sincospi((double)lane * (2.0 / (double)h.nl4), &eqS, &eqC);
+    __shared__ double2 s_eq[GW_SMALL + GW_LARGE];
+    __shared__ HaloCtx s_ctx;
+    if (FAST && threadIdx.x < GW_SMALL + GW_LARGE) {
+        const int k = (threadIdx.x < GW_SMALL) ? threadIdx.x : threadIdx.x - GW_SMALL;
+        double sk, ck;
+        sincospi((double)k * (2.0 / (double)h.nl4), &sk, &ck);
+        s_eq[threadIdx.x] = make_double2(ck, sk);
+    }
     i64 done = 0;
     const bool sharded = pix_lo > 0 || pix_hi < h.npix;
 
     // Persistent CTAs (8 per SM) pull halos from a global queue: consecutive halos of the sky-sorted batch go to whichever
     // CTA is free, so the halos in flight stay neighbours on the sky (L2 locality) and the tail is balanced.
     for (;;) {
-        __syncthreads();  // previous halo's row / segments / s_j no longer in use
-        if (threadIdx.x == 0) s_j = (i64)atomicAdd(queue, 1ULL);
+        __syncthreads();  // previous halo's row / segments / context no longer in use
+        if (threadIdx.x < 32) {   // warp 0: next halo from the queue + its per-halo constants
+            i64 jn = 0;
+            if (lane == 0) jn = (i64)atomicAdd(queue, 1ULL);
+            jn = ((i64)__shfl_sync(0xffffffffu, (int)(jn >> 32), 0) << 32) | (unsigned)__shfl_sync(0xffffffffu, (int)jn, 0);
+            if (jn < n_halo) {
+                const HaloSph s0 = load_halo(halos + jn * BFG_HALO_STRIDE);
+                if (s0.skip != 0.0) {
+                    jn = n_halo;   // bfg_halo_sort_owned puts the halos of other ranks last and marks them: stop here
+                } else {
+                    const DiscRings d0 = disc_rings(h, s0.theta, s0.phi, s0.radius);
+                    const HaloUpd u0 = make_upd(T, s0);
+                    // lane-group width of the fast path from the disc's mean chord (pi/4 of its diameter) in pixels
+                    const int gws = (0.7853981633974483 * 2.0 * s0.radius) * sqrt((double)h.npix * 0.07957747154594767)
+                                    < GW_CHORD_SPLIT;
+                    const int tch = !sharded || disc_touches_range(h, d0, pix_lo, pix_hi);
+                    if (lane == 0) {
+                        s_ctx.d = d0; s_ctx.u = u0; s_ctx.gw_small = gws; s_ctx.touches = tch;
+                        if (FAST) s_ctx.fh = make_fast<PAINT>(T, s0, u0, row, l2tab);
+                    }
+                }
+            }
+            if (lane == 0) s_j = jn;
+        }
         __syncthreads();
         const i64 j = s_j;
         if (j >= n_halo) break;
+        if (!s_ctx.touches) continue;   // uniform across the block (ring-range sharding: the disc misses the owned range)
         const HaloSph s = load_halo(halos + j * BFG_HALO_STRIDE);
-        if (s.skip != 0.0) break;   // bfg_halo_sort_owned puts the halos of other ranks last and marks them
-        const DiscRings d = disc_rings(h, s.theta, s.phi, s.radius);
-        if (sharded && !disc_touches_range(h, d, pix_lo, pix_hi)) continue;   // uniform across the block
+        const DiscRings d = s_ctx.d;
         bool valid;
         blend_row(T, s.lnz, s.lnM, extras ? extras + j * n_extra : nullptr, row, valid);
-        const HaloUpd u = make_upd(T, s);
+        const HaloUpd u = s_ctx.u;
         HaloUpd u2 = u;
         if (MODE == MODE_ANIS) {
             bool valid2;
@@ -402,11 +441,11 @@ k_shell_halos(TableView T, Hpx h, i64 n_halo, const double *__restrict__ halos, 
             u2 = make_upd(A.T2, s);
         }
         FastHalo fh;
-        // lane-group width of the fast path from the disc's mean chord (pi/4 of its diameter) in pixels
-        const bool gw_small = (0.7853981633974483 * 2.0 * s.radius) * sqrt((double)h.npix * 0.07957747154594767) < GW_CHORD_SPLIT;
+        const bool gw_small = s_ctx.gw_small != 0;
         if (FAST) {
-            fh = make_fast<PAINT>(T, s, u, row, l2tab);
-            sincospi((double)(lane & ((gw_small ? GW_SMALL : GW_LARGE) - 1)) * (2.0 / (double)h.nl4), &eqS, &eqC);
+            fh = s_ctx.fh;
+            const double2 e = gw_small ? s_eq[lane & (GW_SMALL - 1)] : s_eq[GW_SMALL + (lane & (GW_LARGE - 1))];
+            eqC = e.x; eqS = e.y;
         }
         // `if pixind.size < 4` (HealpixRunner.py:333) can only trigger for discs of a few pixels (<= ~12 rings)
         const bool tiny = !PAINT && (s.radius * s.radius * (double)h.npix * 0.25 < 64.0);
