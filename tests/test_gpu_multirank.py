@@ -53,6 +53,17 @@ def _worker(rank, world, port, q):
     out2 = b.PaintProfilesShell(cat, shell, 20, pmodel, verbose=False, device=rank, pix_range=pr).process()
     out3 = b.BaryonifyGrid(gcat, gm, 6, gmodel, verbose=False, device=rank,
                            plane_range=parallel.plane_ranges(N, world)[rank]).process()
+    # anisotropic shell painter, sharded: the total-mass pass, its global sum and the gather all cross the ranks
+    from helpers import load as _load
+    ga = _load("shell_anis_n32_background")
+    aaxes = (ga["ax0"], ga["ax1"], ga["ax2"])
+    acat = b.HaloLightConeCatalog(ra=ga["ra"], dec=ga["dec"], M=ga["M"], z=ga["z"], cosmo=b.synth.COSMO)
+    ashell = b.LightconeShell(map=ga["map"], cosmo=b.synth.COSMO, redshift=float(ga["z_shell"]))
+    out4 = b.PaintProfilesAnisShell(
+        acat, ashell, ga["eps_run"], b.ProfileModel(aaxes, None, ga["raw2D"]), b.ProfileModel(aaxes, None, ga["tracer2D"]),
+        b.ProfileModel(aaxes, None, ga["mtot2D"], proj_cutoff=float(ga["proj_cutoff"])), float(ga["background_val"]),
+        float(ga["global_tracer_fraction"]), include_pixel_size=bool(ga["pixsize"]), verbose=False, device=rank,
+        pix_range=parallel.pixel_ranges(int(ga["nside"]), world)[rank]).process()
     # snapshot: x-slabs of particles, every rank displaces its own, NGP grids are summed
     from helpers import load
     g = load("snap_3d")
@@ -66,7 +77,7 @@ def _worker(rank, world, port, q):
     ngp = parallel.deposit_ngp_all([moved["x"], moved["y"], moved["z"]], moved["M"], float(g["L"]), 16, device=rank)
     err = float(np.max(np.abs(moved["x"] - g["out_x"][sel]))) if sel.size else 0.0
     if rank == 0:
-        q.put((out1, out2, out3, ngp, err))
+        q.put((out1, out2, out3, ngp, err, out4))
     else:
         q.put(("err", err))
     torch.distributed.barrier()
@@ -92,7 +103,7 @@ def test_sharded_runs_match_single_gpu():
         p.start()
     items = [q.get(timeout=300) for _ in procs]
     main = [it for it in items if not isinstance(it[0], str)][0]
-    got1, got2, got3, ngp, err0 = main
+    got1, got2, got3, ngp, err0, got4 = main
     errs = [err0] + [it[1] for it in items if isinstance(it[0], str)]
     for p in procs:
         p.join(timeout=120)
@@ -101,5 +112,6 @@ def test_sharded_runs_match_single_gpu():
     assert_close(got2, want2, "sharded PaintProfilesShell", rtol=1e-9, atol_scale=1e-12)
     assert_close(got3, want3, "sharded BaryonifyGrid", rtol=1e-9, atol_scale=1e-12)
     from helpers import load
+    assert_close(got4, load("shell_anis_n32_background")["out"], "sharded PaintProfilesAnisShell vs the reference fixture")
     assert max(errs) < 1e-9                                     # each slab reproduces the reference's displaced positions
     assert np.array_equal(ngp, load("snap_3d")["ngp"])          # summed NGP grid == the reference's make_map
