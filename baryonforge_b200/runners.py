@@ -986,39 +986,51 @@ class DefaultRunnerGrid(object):
         res = self.GriddedMap.res
         ndim = 2 if self.GriddedMap.is2D else 3
         cosmo = cosmology.runner_cosmology(self.cosmo, with_w0=False)             # :462-465 (no w0)
-        M32 = cat['M'].astype('<f4')                                              # io.py:204-205
-        M = M32.astype(np.float64)
         a = 1 / (1 + self.HaloNDCatalog.redshift)                                 # :490
         rec = np.zeros((_lib.HALO_STRIDE, n), dtype=np.float64).T
         if n == 0:
             return rec, None
-        R_phys = cosmology.radius_of_mass(cosmo, M, a, self.mass_def)             # :491
-        if paint:
-            R_com = R_phys / a                                                    # :734
-            Nf = 2 * self.epsilon_max * R_com / res                               # :740
-            rec[:, _lib.HB_PAINTCUT] = R_com * self.epsilon_max                   # :815
-            rec[:, _lib.HB_RQ] = R_com * self.epsilon_max
-            rec[:, _lib.HB_RCUT] = np.inf
-        else:
-            R_q = np.clip(self.epsilon_max * R_phys / a, 0, np.max(bins) / 2)     # :492-493
-            Nf = 2 * R_q / res                                                    # :500
-            rec[:, _lib.HB_RQ] = R_q
-            mcosmo = _model_cosmo(self.model, cosmo)
-            R_mod = cosmology.radius_of_mass(mcosmo, M, a, getattr(self.model, 'mass_def', None)) / a   # BaryonCorrection.py:399
-            rec[:, _lib.HB_RCUT] = self.model.epsilon_max * R_mod
-            rec[:, _lib.HB_LNRCOM] = np.log(R_mod)
-        self.last_scalars = dict(R_phys=R_phys, R_model_com=None if paint else R_mod)
-        Nsize = ((Nf // 2).astype(np.int64)) * 2                                  # :501
-        Nsize = np.clip(Nsize, 2, bins.size // 2)                                 # :503
-        rec[:, _lib.HB_NSIZE] = Nsize
-        rec[:, _lib.HB_LNZ] = np.log(1 / a)
-        rec[:, _lib.HB_LNM] = np.log(M32).astype(np.float64)                      # float32 log, §10 #8
-        for k, name in enumerate(['x', 'y', 'z'][:ndim]):
-            x = cat[name].astype('<f4').astype(np.float64)
-            cen = _nearest_bin(bins, x)
-            rec[:, _lib.HB_X + k] = x
-            rec[:, _lib.HB_CX + k] = cen
-            rec[:, _lib.HB_DX + k] = bins[cen] - x                                # :519-520
+        R_phys_all = np.empty(n)
+        R_mod_all = None if paint else np.empty(n)
+        mcosmo = None if paint else _model_cosmo(self.model, cosmo)
+        bmax = np.max(bins)
+        eps_model = None if paint else self.model.epsilon_max
+        mdef_model = None if paint else getattr(self.model, 'mass_def', None)
+        names = ['x', 'y', 'z'][:ndim]
+
+        def fill(sl):   # chunks run on the host thread pool (numpy releases the GIL in these kernels)
+            r = rec[sl]
+            M32 = cat['M'][sl].astype('<f4')                                      # io.py:204-205
+            M = M32.astype(np.float64)
+            R_phys = cosmology.radius_of_mass(cosmo, M, a, self.mass_def)         # :491
+            R_phys_all[sl] = R_phys
+            if paint:
+                R_com = R_phys / a                                                # :734
+                Nf = 2 * self.epsilon_max * R_com / res                           # :740
+                r[:, _lib.HB_PAINTCUT] = R_com * self.epsilon_max                 # :815
+                r[:, _lib.HB_RQ] = R_com * self.epsilon_max
+                r[:, _lib.HB_RCUT] = np.inf
+            else:
+                R_q = np.clip(self.epsilon_max * R_phys / a, 0, bmax / 2)         # :492-493
+                Nf = 2 * R_q / res                                                # :500
+                r[:, _lib.HB_RQ] = R_q
+                R_mod = cosmology.radius_of_mass(mcosmo, M, a, mdef_model) / a    # BaryonCorrection.py:399
+                R_mod_all[sl] = R_mod
+                r[:, _lib.HB_RCUT] = eps_model * R_mod
+                r[:, _lib.HB_LNRCOM] = np.log(R_mod)
+            Nsize = ((Nf // 2).astype(np.int64)) * 2                              # :501
+            Nsize = np.clip(Nsize, 2, bins.size // 2)                             # :503
+            r[:, _lib.HB_NSIZE] = Nsize
+            r[:, _lib.HB_LNZ] = np.log(1 / a)
+            r[:, _lib.HB_LNM] = np.log(M32).astype(np.float64)                    # float32 log, §10 #8
+            for k, name in enumerate(names):
+                x = cat[name][sl].astype('<f4').astype(np.float64)
+                cen = _nearest_bin(bins, x)
+                r[:, _lib.HB_X + k] = x
+                r[:, _lib.HB_CX + k] = cen
+                r[:, _lib.HB_DX + k] = bins[cen] - x                              # :519-520
+        _parallel_chunks(fill, n, chunk=32768)
+        self.last_scalars = dict(R_phys=R_phys_all, R_model_com=R_mod_all)
         if ndim == 2:
             dx, dy = rec[:, _lib.HB_DX], rec[:, _lib.HB_DY]
             assert np.all((dx <= res) & (dy <= res)), "Halo offsets are larger than res"   # :522
