@@ -19,9 +19,11 @@ namespace {
 
 constexpr int SHELL_THREADS = 128;
 #ifndef BFG_SHELL_MIN_CTAS
-#define BFG_SHELL_MIN_CTAS 8
+#define BFG_SHELL_MIN_CTAS 7
 #endif
-constexpr int SHELL_MIN_CTAS = BFG_SHELL_MIN_CTAS;   // 8 -> 64 registers/thread, 32 warps/SM: measured best (profiles/README.md, occupancy sweep)
+// resident CTAs per SM = size of the persistent grid per SM.  7 -> 72 registers/thread, 28 warps/SM: measured best for the v8
+// kernel (flat catalogue 99.7 / 98.6 / 100.0 ms with 8 / 7 / 6; profiles/README.md has the sweeps of the earlier kernels)
+constexpr int SHELL_MIN_CTAS = BFG_SHELL_MIN_CTAS;
 constexpr int RING_CHUNK = SHELL_THREADS;   // ring segments staged in shared memory per pass (one per thread)
 
 struct HaloSph {
