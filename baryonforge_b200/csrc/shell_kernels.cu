@@ -5,7 +5,7 @@
 //                           and PaintProfilesAnisShell.process                (BaryonForge/Runners/HealpixRunner.py:589-631)
 //   k_shell_regrid[_range|_p2p] : the re-binning step                         (BaryonForge/Runners/HealpixRunner.py:357-365, :17-71)
 //
-// Persistent CTAs (148 SMs x 8) pull halos from a global queue.  Per halo the CTA blends the 2^(ndim-1) table rows into one
+// Persistent CTAs (148 SMs x 7) pull halos from a global queue.  Per halo the CTA blends the 2^(ndim-1) table rows into one
 // radial row in shared memory, derives the disc's ring range on the device (query_disc, no host round trip), stages the
 // per-ring constants, and its warps walk the rings -- 8 or 16 lanes per ring over consecutive pixels, so the fp64 REDs of a
 // lane group hit consecutive addresses of the component-major offsets array.
@@ -399,7 +399,7 @@ k_shell_halos(TableView T, Hpx h, i64 n_halo, const double *__restrict__ halos, 
     i64 done = 0;
     const bool sharded = pix_lo > 0 || pix_hi < h.npix;
 
-    // Persistent CTAs (8 per SM) pull halos from a global queue: consecutive halos of the sky-sorted batch go to whichever
+    // Persistent CTAs (SHELL_MIN_CTAS per SM) pull halos from a global queue: consecutive halos of the sky-sorted batch go to whichever
     // CTA is free, so the halos in flight stay neighbours on the sky (L2 locality) and the tail is balanced.
     for (;;) {
         __syncthreads();  // previous halo's row / segments / context no longer in use
