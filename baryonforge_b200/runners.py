@@ -1103,8 +1103,14 @@ class BaryonifyGrid(DefaultRunnerGrid):
         dev = self._device()
         L = _lib.lib()
         with torch.cuda.device(dev):
-            d_map = _to_device(orig_map[lo:hi], dev, dtype=np.float64)
+            # halo loop first (asynchronous); the map is only needed by the re-binning, so its upload runs on a side stream
+            # underneath the halo loop (a pageable source blocks the host, not the GPU)
             d_off, d_n = self.offsets_on_device()
+            side = _side_stream(dev)
+            with torch.cuda.stream(side):
+                d_map = _to_device(orig_map[lo:hi], dev, dtype=np.float64)
+            torch.cuda.current_stream().wait_stream(side)
+            d_map.record_stream(torch.cuda.current_stream())
             d_new = torch.zeros(orig_map.size, dtype=torch.float64, device=dev)
             st = _lib.current_stream()
             _lib.check(L.bfg_grid_regrid(ndim, N, _lib.ptr(d_map), _lib.ptr(d_off), _lib.ptr(d_new), lo, hi, st))
