@@ -404,6 +404,14 @@ def test_grid3d_tile_gather_matches_scatter_and_oracle(monkeypatch):
     hi, _ = b.BaryonifyGrid(cat, gm, 6, dmodel, verbose=False, plane_range=(24, N)).offsets_on_device()
     both = torch.cat([lo.reshape(3, 24, N * N), hi.reshape(3, N - 24, N * N)], dim=1).reshape(3, -1)
     assert_close(both.cpu().numpy(), off_t.cpu().numpy(), "tile slab split", rtol=1e-9, atol_scale=1e-13)
+    # uneven 3-way split: rank 0's slab ends inside a tile (masked planes), the other slabs do not start on a tile boundary
+    # and fall back to the scatter kernels -- the pieces still add up to the full result
+    parts = []
+    for plo, phi_ in ((0, 21), (21, 42), (42, N)):
+        o, _ = b.BaryonifyGrid(cat, gm, 6, dmodel, verbose=False, plane_range=(plo, phi_)).offsets_on_device()
+        parts.append(o.reshape(3, phi_ - plo, N * N))
+    assert_close(torch.cat(parts, dim=1).reshape(3, -1).cpu().numpy(), off_t.cpu().numpy(), "uneven slab split",
+                 rtol=1e-9, atol_scale=1e-13)
     # painting (model.real table)
     prun = b.PaintProfilesGrid(cat, gm, 5, pmodel, verbose=False)
     got_p = prun.process()
