@@ -510,3 +510,45 @@ def test_full_size_properties_nside4096(monkeypatch):
     # not bit-exact in the reference either: the re-binning goes radians -> degrees -> radians (HealpixRunner.py:358,361),
     # which at 0.86-arcmin pixels leaves ~1e-9 of a pixel's mass on its neighbours
     assert_close(ident, hmap, "zero table = identity", rtol=1e-6, atol_scale=1e-8)
+
+
+def test_grid_param_tables_p_keys_vs_oracle_port():
+    """4-D tables with a per-halo extra column on grids: 3-D (tile-centric gather) and 2-D (scatter kernel) BaryonifyGrid and
+    3-D PaintProfilesGrid against the oracle port (BaryonCorrection.py:211-212,307-322 / Tabulate.py:553-590)."""
+    import baryonforge_b200 as b
+    from baryonforge_b200 import synth
+    from oracle import runners_port as rp
+    rng = np.random.default_rng(5)
+    gaxes = synth.table_axes(nz=6, nM=9, nr=200, z_min=0.0, z_max=1.0, z_linear=True, r_min=1e-2, r_max=2e2)
+    cax = np.linspace(3.0, 11.0, 5)
+    d4 = synth.displacement_values(gaxes)[..., None] * 25.0 * (0.5 + 0.1 * cax)[None, None, None, :]
+    p4 = synth.profile_values(gaxes)[..., None] * (0.5 + 0.1 * cax)[None, None, None, :]
+    a = 1 / 1.3
+    for ndim, N, Lbox, n in ((3, 32, 60.0, 40), (2, 64, 120.0, 60)):
+        pos, M = synth.box_halos(n, Lbox, seed=60 + ndim, ndim=ndim)
+        cd = rng.uniform(3.0, 11.0, n)
+        cd[:3] = [2.0, 11.0, 3.0]                     # one outside the extra axis (NaN -> cleaned), two on its edges
+        bins = (np.arange(N) + 0.5) * Lbox / N
+        gmap = rng.uniform(0, 10, (N,) * ndim)
+        cat = b.HaloNDCatalog(x=pos[0], y=pos[1], z=pos[2] if ndim == 3 else None, M=M, redshift=0.3, cosmo=synth.COSMO,
+                              cdelta=cd)
+        gm = b.GriddedMap(map=gmap, redshift=0.3, bins=bins, cosmo=synth.COSMO)
+        hc = {k: cat.cat[k].astype('<f4') for k in ('M', 'x', 'y', 'z')}
+        ex = dict(cdelta=cat.cat['cdelta'].astype('<f4'))
+        run = b.BaryonifyGrid(cat, gm, 5, b.DisplacementModel(gaxes + (cax,), d4, 4, synth.COSMO, p_keys=['cdelta']),
+                              verbose=False)
+        got = run.process()
+        sc = run.last_scalars
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            want = rp.baryonify_grid(gmap, bins, hc, a, sc["R_phys"], sc["R_model_com"], 5,
+                                     rp.DisplacementTable(gaxes + (cax,), d4, 4, p_keys=['cdelta']), extras=ex, warn=False)
+        assert_close(got, want, f"{ndim}-D BaryonifyGrid with p_keys")
+        if ndim == 3:
+            prun = b.PaintProfilesGrid(cat, gm, 4, b.ProfileModel(gaxes + (cax,), p4 * 3, p4, p_keys=['cdelta']), verbose=False)
+            gotp = prun.process()
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                wantp, _ = rp.paint_grid((N,) * 3, bins, hc, a, prun.last_scalars["R_phys"] / a, 4,
+                                         rp.ProfileTable(gaxes + (cax,), p4 * 3, p4, p_keys=['cdelta']), extras=ex)
+            assert_close(gotp, wantp, "3-D PaintProfilesGrid with p_keys")
