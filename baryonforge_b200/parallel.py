@@ -272,13 +272,30 @@ class SharedHostMaps(object):
             os.ftruncate(fd, nbytes)
             info = [os.getpid(), fd]
         dist.broadcast_object_list(info, src=0)
-        if self.rank != 0:
-            fd = os.open(f"/proc/{info[0]}/fd/{info[1]}", os.O_RDWR)
-        mm = mmap.mmap(fd, nbytes)          # MAP_SHARED; mmap keeps its own duplicate of the descriptor
-        dist.barrier()                      # everybody has opened rank 0's descriptor
-        os.close(fd)
-        addr = C.addressof(C.c_char.from_buffer(mm))
-        _lib.check(_lib.lib().bfg_host_register(addr, nbytes))
+        import torch
+        mm, addr, ok = None, 0, 1
+        try:
+            if self.rank != 0:
+                fd = os.open(f"/proc/{info[0]}/fd/{info[1]}", os.O_RDWR)   # same PID namespace (one box, torchrun)
+            mm = mmap.mmap(fd, nbytes)      # MAP_SHARED; mmap keeps its own duplicate of the descriptor
+            addr = C.addressof(C.c_char.from_buffer(mm))
+            _lib.check(_lib.lib().bfg_host_register(addr, nbytes))
+        except Exception:
+            ok = 0
+        # every rank must agree before anybody relies on the segment (this also fences rank 0's descriptor)
+        flag = torch.tensor([ok], dtype=torch.int32, device=torch.device('cuda', self.device))
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if fd >= 0:
+            os.close(fd)
+        if int(flag.cpu()[0]) == 0:
+            if ok:
+                _lib.lib().bfg_host_unregister(addr)
+            if mm is not None:
+                try:
+                    mm.close()
+                except Exception:
+                    pass
+            raise OSError("shared host map could not be mapped by every rank")
         self.segs.append(dict(mm=mm, addr=addr, free=True))
         return len(self.segs) - 1
 

@@ -691,9 +691,14 @@ class BaryonifyShell(DefaultRunner):
                 dist.all_reduce(token)               # ... and every rank's deposits have landed before the gather
                 host = self._shared_host(npix, peers)
                 if host is not None:
+                    try:
+                        seg, addr = host.acquire()
+                    except OSError:             # collective failure (agreed by all ranks): use the per-rank download
+                        self._host_maps = (self._host_maps[0], None)
+                        host = None
+                if host is not None:
                     # every rank copies ITS slice into one page-locked host map all ranks have mapped: no device
                     # all-gather, npix*8 bytes over PCIe in total (not per rank), all links in parallel
-                    seg, addr = host.acquire()
                     _lib.check(L.bfg_copy_to_host_async(addr + 8 * lo, own.data_ptr(), 8 * (hi - lo), st))
                     d_sums = torch.zeros(2, dtype=torch.float64, device=dev)
                     _lib.check(L.bfg_sum_f64(own.data_ptr(), hi - lo, _lib.ptr(d_sums), st))
