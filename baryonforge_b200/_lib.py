@@ -39,6 +39,7 @@ _SIGNATURES = {
     "bfg_healpix_query_disc": ([C.c_int, c_ptr, c_ptr, c_i64, c_ptr, c_ptr], C.c_int),
     "bfg_healpix_pix2vec": ([C.c_int, c_i64, c_i64, c_ptr, c_ptr], C.c_int),
     "bfg_healpix_interp_weights": ([C.c_int, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr], C.c_int),
+    "bfg_healpix_reorder": ([C.c_int, C.c_int, c_i64, c_ptr, c_ptr, c_ptr], C.c_int),
     "bfg_healpix_ang2pix": ([C.c_int, c_i64, c_ptr, c_ptr, c_ptr, c_ptr], C.c_int),
     "bfg_shell_offsets": ([c_ptr, C.c_int, c_i64, c_ptr, c_ptr, C.c_int, c_ptr, c_i64, c_i64, c_ptr, c_ptr], C.c_int),
     "bfg_shell_paint": ([c_ptr, C.c_int, c_i64, c_ptr, c_ptr, C.c_int, c_ptr, c_i64, c_i64, c_ptr, c_ptr], C.c_int),

@@ -446,6 +446,75 @@ __device__ __forceinline__ i64 ang2pix_ring(const Hpx &h, double theta, double p
     return (z > 0) ? 2 * ir * (ir - 1) + ip : h.npix - 2 * ir * (ir + 1) + ip;
 }
 
+// RING <-> NEST (T_Healpix_Base ring2xyf / xyf2ring / xyf2nest / nest2xyf; nside a power of two).  The runners work on
+// RING maps like the reference (utils/io.py:302); NEST exists for callers that hold nested maps or shard by base face.
+__device__ __forceinline__ i64 spread_bits(i64 v) {      // bit k -> bit 2k (v < 2^31)
+    v = (v | (v << 16)) & 0x0000ffff0000ffffLL;
+    v = (v | (v << 8)) & 0x00ff00ff00ff00ffLL;
+    v = (v | (v << 4)) & 0x0f0f0f0f0f0f0f0fLL;
+    v = (v | (v << 2)) & 0x3333333333333333LL;
+    v = (v | (v << 1)) & 0x5555555555555555LL;
+    return v;
+}
+__device__ __forceinline__ i64 compress_bits(i64 v) {    // bit 2k -> bit k
+    v &= 0x5555555555555555LL;
+    v = (v | (v >> 1)) & 0x3333333333333333LL;
+    v = (v | (v >> 2)) & 0x0f0f0f0f0f0f0f0fLL;
+    v = (v | (v >> 4)) & 0x00ff00ff00ff00ffLL;
+    v = (v | (v >> 8)) & 0x0000ffff0000ffffLL;
+    v = (v | (v >> 16)) & 0x00000000ffffffffLL;
+    return v;
+}
+
+__device__ __forceinline__ i64 ring2nest(const Hpx &h, i64 pix) {
+    const int jrll[12] = {2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4}, jpll[12] = {1, 3, 5, 7, 0, 2, 4, 6, 1, 3, 5, 7};
+    const i64 n = h.nside, nl2 = 2 * n;
+    i64 iring, iphi, kshift, nr;
+    int face;
+    if (pix < h.ncap) {
+        iring = (1 + isqrt_i64(1 + 2 * pix)) >> 1;
+        iphi = pix + 1 - 2 * iring * (iring - 1);
+        kshift = 0; nr = iring;
+        face = (int)((iphi - 1) / nr);
+    } else if (pix < h.npix - h.ncap) {
+        const i64 ip = pix - h.ncap, tmp = ip / h.nl4;
+        iring = tmp + n;
+        iphi = ip - tmp * h.nl4 + 1;
+        kshift = (iring + n) & 1; nr = n;
+        const i64 ire = tmp + 1, irm = nl2 + 1 - tmp;
+        const i64 ifm = (iphi - ire / 2 + n - 1) / n, ifp = (iphi - irm / 2 + n - 1) / n;
+        face = (int)((ifp == ifm) ? (ifp | 4) : ((ifp < ifm) ? ifp : (ifm + 8)));
+    } else {
+        const i64 ip = h.npix - pix;
+        iring = (1 + isqrt_i64(2 * ip - 1)) >> 1;
+        iphi = 4 * iring + 1 - (ip - 2 * iring * (iring - 1));
+        kshift = 0; nr = iring;
+        iring = 2 * nl2 - iring;
+        face = (int)(8 + (iphi - 1) / nr);
+    }
+    const i64 irt = iring - jrll[face] * n + 1;
+    i64 ipt = 2 * iphi - jpll[face] * nr - kshift - 1;
+    if (ipt >= nl2) ipt -= 8 * n;
+    const i64 ix = (ipt - irt) >> 1, iy = (-ipt - irt) >> 1;
+    return (i64)face * n * n + spread_bits(ix) + (spread_bits(iy) << 1);
+}
+
+__device__ __forceinline__ i64 nest2ring(const Hpx &h, i64 pix) {
+    const int jrll[12] = {2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4}, jpll[12] = {1, 3, 5, 7, 0, 2, 4, 6, 1, 3, 5, 7};
+    const i64 n = h.nside, npface = n * n;
+    const int face = (int)(pix / npface);
+    const i64 p = pix - (i64)face * npface;
+    const i64 ix = compress_bits(p), iy = compress_bits(p >> 1);
+    const i64 jr = jrll[face] * n - ix - iy - 1;
+    i64 nr, n_before, kshift;
+    if (jr < n) { nr = jr; n_before = 2 * nr * (nr - 1); kshift = 0; }
+    else if (jr > 3 * n) { nr = h.nl4 - jr; n_before = h.npix - 2 * (nr + 1) * nr; kshift = 0; }
+    else { nr = n; n_before = h.ncap + (jr - n) * h.nl4; kshift = (jr - n) & 1; }
+    i64 jp = (jpll[face] * nr + ix - iy + 1 + kshift) / 2;
+    if (jp > h.nl4) jp -= h.nl4; else if (jp < 1) jp += h.nl4;
+    return n_before + jp - 1;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Table-driven log2 for the pixel loops (the CUDA libm log() costs ~60 instructions; this one ~18).
 //   x = 2^e * m, m in [1,2);  idx = top 7 mantissa bits;  rc = 1/c_idx (c_idx = bucket centre), f = m*rc - 1,

@@ -702,6 +702,13 @@ __global__ void k_ang2pix(Hpx h, i64 n, const double *__restrict__ th, const dou
         pix[i] = ang2pix_ring(h, th[i], ph[i]);
 }
 
+__global__ void k_reorder_index(Hpx h, i64 n, const i64 *__restrict__ in, i64 *__restrict__ out, int to_nest) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        const i64 p = in[i];
+        out[i] = (p < 0 || p >= h.npix) ? -1 : (to_nest ? ring2nest(h, p) : nest2ring(h, p));
+    }
+}
+
 int check_nside(int nside) {
     if (nside < 1 || nside > (1 << 24)) { set_error("nside out of range"); return BFG_ERR_INVALID; }
     return BFG_OK;
@@ -901,6 +908,18 @@ extern "C" int bfg_healpix_ang2pix(int nside, int64_t n, const double *d_theta, 
     if (int rc = check_nside(nside)) return rc;
     if (n == 0) return BFG_OK;
     k_ang2pix<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(Hpx(nside), n, d_theta, d_phi, (i64 *)d_pix);
+    BFG_CUDA_OK(cudaGetLastError());
+    return BFG_OK;
+}
+
+extern "C" int bfg_healpix_reorder(int nside, int to_nest, int64_t n, const int64_t *d_pix_in, int64_t *d_pix_out,
+                                   void *stream) {
+    BFG_REQUIRE(d_pix_in && d_pix_out, "null argument");
+    if (int rc = check_nside(nside)) return rc;
+    BFG_REQUIRE((nside & (nside - 1)) == 0, "the NESTED scheme needs nside to be a power of two");
+    if (n == 0) return BFG_OK;
+    k_reorder_index<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(Hpx(nside), n, (const i64 *)d_pix_in, (i64 *)d_pix_out,
+                                                                        to_nest);
     BFG_CUDA_OK(cudaGetLastError());
     return BFG_OK;
 }

@@ -31,12 +31,26 @@ def interp_weights(nside, theta, phi):
     return pix.cpu().numpy(), w.cpu().numpy()
 
 
-def ang2pix(nside, theta, phi):
+def ang2pix(nside, theta, phi, nest=False):
     torch = _torch()
     t, p = _to_device(theta, _dev(), np.float64), _to_device(phi, _dev(), np.float64)
     pix = torch.empty(t.numel(), dtype=torch.int64, device=_dev())
     _lib.check(_lib.lib().bfg_healpix_ang2pix(nside, t.numel(), _lib.ptr(t), _lib.ptr(p), _lib.ptr(pix), _lib.current_stream()))
+    if nest:
+        out = torch.empty_like(pix)
+        _lib.check(_lib.lib().bfg_healpix_reorder(nside, 1, pix.numel(), _lib.ptr(pix), _lib.ptr(out), _lib.current_stream()))
+        pix = out
     return pix.cpu().numpy()
+
+
+def reorder(nside, pix, to_nest):
+    """RING -> NEST (to_nest=True) or NEST -> RING pixel indices on the device."""
+    torch = _torch()
+    d_in = _to_device(np.asarray(pix, dtype=np.int64), _dev())
+    d_out = torch.empty_like(d_in)
+    _lib.check(_lib.lib().bfg_healpix_reorder(nside, 1 if to_nest else 0, d_in.numel(), _lib.ptr(d_in), _lib.ptr(d_out),
+                                              _lib.current_stream()))
+    return d_out.cpu().numpy()
 
 
 def halo_record(theta, phi, radius):

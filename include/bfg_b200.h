@@ -107,6 +107,10 @@ int bfg_healpix_pix2vec(int nside, int64_t pix_lo, int64_t pix_hi, double *d_xyz
 /* get_interp_weights(theta, phi): d_pix [4][n], d_w [4][n]. */
 int bfg_healpix_interp_weights(int nside, int64_t n, const double *d_theta, const double *d_phi, int64_t *d_pix,
                                double *d_w, void *stream);
+/* Pixel indices RING -> NEST (to_nest != 0) or NEST -> RING (nside a power of two); out-of-range ids map to -1.
+ * ang2pix in the NESTED scheme = bfg_healpix_ang2pix followed by this.  The runners themselves work on RING maps, like the
+ * reference (utils/io.py:302). */
+int bfg_healpix_reorder(int nside, int to_nest, int64_t n, const int64_t *d_pix_in, int64_t *d_pix_out, void *stream);
 /* ang2pix (RING), used for shard assignment. */
 int bfg_healpix_ang2pix(int nside, int64_t n, const double *d_theta, const double *d_phi, int64_t *d_pix, void *stream);
 

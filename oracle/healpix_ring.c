@@ -352,3 +352,79 @@ void hpo_regrid_scatter(double *hmap, i64 n, const double *parent_vals, const i6
     for (i64 i = 0; i < n; ++i)
         for (int j = 0; j < 4; ++j) hmap[child_pix[i * 4 + j]] += child_w[i * 4 + j] * parent_vals[i];
 }
+
+/* ---- RING <-> NEST (T_Healpix_Base::ring2xyf / xyf2ring / xyf2nest / nest2xyf; nside must be a power of two).
+ * The reference itself only uses RING maps (utils/io.py:302); these exist because BASELINE.json's north_star names
+ * "ang2pix ring/nest", and are pinned by the hierarchy property of the NESTED scheme (tests/test_oracle_healpix.py). */
+static const int JRLL[12] = {2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4};
+static const int JPLL[12] = {1, 3, 5, 7, 0, 2, 4, 6, 1, 3, 5, 7};
+
+static i64 spread(i64 v) {           /* bit k of v -> bit 2k */
+    i64 r = 0;
+    for (int k = 0; k < 31; ++k) r |= ((v >> k) & 1) << (2 * k);
+    return r;
+}
+static i64 compress(i64 v) {         /* bit 2k of v -> bit k */
+    i64 r = 0;
+    for (int k = 0; k < 31; ++k) r |= ((v >> (2 * k)) & 1) << k;
+    return r;
+}
+
+static void ring2xyf(hbase b, i64 pix, i64 *ix, i64 *iy, int *face) {
+    i64 n = b.nside, nl2 = 2 * n, iring, iphi, kshift, nr;
+    if (pix < b.ncap) {
+        iring = (1 + isqrt64(1 + 2 * pix)) >> 1;
+        iphi = pix + 1 - 2 * iring * (iring - 1);
+        kshift = 0; nr = iring;
+        *face = (int)((iphi - 1) / nr);
+    } else if (pix < b.npix - b.ncap) {
+        i64 ip = pix - b.ncap, tmp = ip / (4 * n);
+        iring = tmp + n;
+        iphi = ip - tmp * 4 * n + 1;
+        kshift = (iring + n) & 1; nr = n;
+        i64 ire = tmp + 1, irm = nl2 + 1 - tmp;
+        i64 ifm = (iphi - ire / 2 + n - 1) / n, ifp = (iphi - irm / 2 + n - 1) / n;
+        *face = (int)((ifp == ifm) ? (ifp | 4) : ((ifp < ifm) ? ifp : (ifm + 8)));
+    } else {
+        i64 ip = b.npix - pix;
+        iring = (1 + isqrt64(2 * ip - 1)) >> 1;
+        iphi = 4 * iring + 1 - (ip - 2 * iring * (iring - 1));
+        kshift = 0; nr = iring;
+        iring = 2 * nl2 - iring;
+        *face = (int)(8 + (iphi - 1) / nr);
+    }
+    i64 irt = iring - JRLL[*face] * n + 1;
+    i64 ipt = 2 * iphi - JPLL[*face] * nr - kshift - 1;
+    if (ipt >= nl2) ipt -= 8 * n;
+    *ix = (ipt - irt) >> 1;
+    *iy = (-ipt - irt) >> 1;
+}
+
+static i64 xyf2ring(hbase b, i64 ix, i64 iy, int face) {
+    i64 n = b.nside, nl4 = 4 * n, jr = JRLL[face] * n - ix - iy - 1, nr, n_before, kshift;
+    if (jr < n) { nr = jr; n_before = 2 * nr * (nr - 1); kshift = 0; }
+    else if (jr > 3 * n) { nr = nl4 - jr; n_before = b.npix - 2 * (nr + 1) * nr; kshift = 0; }
+    else { nr = n; n_before = b.ncap + (jr - n) * nl4; kshift = (jr - n) & 1; }
+    i64 jp = (JPLL[face] * nr + ix - iy + 1 + kshift) / 2;
+    if (jp > nl4) jp -= nl4; else if (jp < 1) jp += nl4;
+    return n_before + jp - 1;
+}
+
+void hpo_ring2nest(i64 nside, i64 n, const i64 *ring, i64 *nest) {
+    hbase b = mk(nside);
+    for (i64 i = 0; i < n; ++i) {
+        i64 ix, iy; int f;
+        ring2xyf(b, ring[i], &ix, &iy, &f);
+        nest[i] = (i64)f * nside * nside + spread(ix) + (spread(iy) << 1);
+    }
+}
+
+void hpo_nest2ring(i64 nside, i64 n, const i64 *nest, i64 *ring) {
+    hbase b = mk(nside);
+    i64 npface = nside * nside;
+    for (i64 i = 0; i < n; ++i) {
+        int f = (int)(nest[i] / npface);
+        i64 p = nest[i] % npface;
+        ring[i] = xyf2ring(b, compress(p), compress(p >> 1), f);
+    }
+}

@@ -44,6 +44,8 @@ def lib():
         L.hpo_ring2z.restype = dbl
         L.hpo_ring_info.argtypes = [i64, i64, C.POINTER(i64), C.POINTER(i64), C.POINTER(C.c_int)]
         L.hpo_regrid_scatter.argtypes = [pdbl, i64, pdbl, pi64, pdbl]
+        L.hpo_ring2nest.argtypes = [i64, i64, pi64, pi64]
+        L.hpo_nest2ring.argtypes = [i64, i64, pi64, pi64]
         _LIB = L
     return _LIB
 
@@ -105,3 +107,17 @@ def regrid_scatter(hmap, parent_vals, child_pix, child_w):
     lib().hpo_regrid_scatter(hmap, parent_vals.size, np.ascontiguousarray(parent_vals),
                              np.ascontiguousarray(child_pix, dtype=np.int64), np.ascontiguousarray(child_w))
     return hmap
+
+
+def ring2nest(nside, ipix):
+    ipix = np.ascontiguousarray(np.atleast_1d(ipix), dtype=np.int64)
+    out = np.empty(ipix.size, dtype=np.int64)
+    lib().hpo_ring2nest(int(nside), ipix.size, ipix.ravel(), out)
+    return out.reshape(ipix.shape)
+
+
+def nest2ring(nside, ipix):
+    ipix = np.ascontiguousarray(np.atleast_1d(ipix), dtype=np.int64)
+    out = np.empty(ipix.size, dtype=np.int64)
+    lib().hpo_nest2ring(int(nside), ipix.size, ipix.ravel(), out)
+    return out.reshape(ipix.shape)

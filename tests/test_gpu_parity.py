@@ -76,6 +76,20 @@ def test_healpix_device_geometry_matches_oracle():
         assert np.allclose(gw.sum(axis=0), 1.0, atol=1e-12)
 
 
+def test_ring_nest_device_matches_oracle():
+    from baryonforge_b200 import healpix as dh
+    from oracle import hpo
+    rng = np.random.default_rng(12)
+    for nside in (1, 2, 64, 4096):
+        npix = 12 * nside * nside
+        r = np.arange(npix) if nside <= 64 else rng.integers(0, npix, 200000)
+        n = dh.reorder(nside, r, True)
+        assert np.array_equal(n, hpo.ring2nest(nside, r))
+        assert np.array_equal(dh.reorder(nside, n, False), r)
+        th = np.arccos(rng.uniform(-1, 1, 2000)); ph = rng.uniform(0, 2 * np.pi, 2000)
+        assert np.array_equal(dh.ang2pix(nside, th, ph, nest=True), hpo.ring2nest(nside, hpo.ang2pix(nside, th, ph)))
+
+
 def test_query_disc_index_sets_bit_exact():
     from baryonforge_b200 import healpix as dh
     from oracle import hpo

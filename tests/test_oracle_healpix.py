@@ -66,3 +66,20 @@ def test_query_disc_equals_brute_force():
             want = np.where(ang < rad)[0]
             d = np.setxor1d(got, want)
             assert d.size == 0 or np.max(np.abs(ang[d] - rad)) < 1e-9   # only round-off ties may differ
+
+
+def test_ring_nest_conversion_hierarchy():
+    """RING <-> NEST of the oracle: a bijection, the healpy docstring table for nside = 2, and the defining property of the
+    NESTED scheme -- pixel q at nside lies inside pixel q >> 2 at nside / 2 -- checked through the RING functions above."""
+    want2 = [3, 7, 11, 15, 2, 1, 6, 5, 10, 9, 14, 13, 19, 0, 23, 4, 27, 8, 31, 12, 17, 22, 21, 26, 25, 30, 29, 18, 16, 35, 20,
+             39, 24, 43, 28, 47, 34, 33, 38, 37, 42, 41, 46, 45, 32, 36, 40, 44]
+    assert hpo.ring2nest(2, np.arange(48)).tolist() == want2
+    for nside in (1, 2, 4, 16, 128):
+        npix = 12 * nside * nside
+        r = np.arange(npix)
+        n = hpo.ring2nest(nside, r)
+        assert np.array_equal(np.sort(n), r) and np.array_equal(hpo.nest2ring(nside, n), r)
+        if nside > 1:
+            th, ph = hpo.pix2ang(nside, r)
+            parent = hpo.ring2nest(nside // 2, hpo.ang2pix(nside // 2, th, ph))
+            assert np.array_equal(parent, n >> 2)
