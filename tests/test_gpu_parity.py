@@ -566,3 +566,37 @@ def test_grid_param_tables_p_keys_vs_oracle_port():
                 wantp, _ = rp.paint_grid((N,) * 3, bins, hc, a, prun.last_scalars["R_phys"] / a, 4,
                                          rp.ProfileTable(gaxes + (cax,), p4 * 3, p4, p_keys=['cdelta']), extras=ex)
             assert_close(gotp, wantp, "3-D PaintProfilesGrid with p_keys")
+
+
+def test_snapshot_particle_on_halo_centre_becomes_nan():
+    """a particle sitting exactly on a (float32-rounded) halo centre has x_hat = 0/0; the reference
+    zeroes the non-finite displacement but not the direction, so the particle comes back with NaN coordinates
+    (SnapshotRunner.py:252-260).  The CUDA path reproduces that, and everything else matches the oracle port."""
+    import baryonforge_b200 as b
+    from baryonforge_b200 import synth
+    from oracle import runners_port as rp
+    Lbox, n, n_part = 60.0, 30, 4000
+    pos, M = synth.box_halos(n, Lbox, seed=81)
+    pos32 = pos.astype('f4').astype('f8')
+    rng = np.random.default_rng(82)
+    p = rng.uniform(0, Lbox, (3, n_part))
+    p[:, 0] = pos32[:, 5]                          # exactly on halo 5
+    p[:, 1] = pos32[:, 9]
+    gaxes = synth.table_axes(nz=6, nM=10, nr=300, z_min=0.0, z_max=1.0, z_linear=True, r_min=1e-2, r_max=2e2)
+    dvals = synth.displacement_values(gaxes) * 25.0
+    cat = b.HaloNDCatalog(x=pos[0], y=pos[1], z=pos[2], M=M, redshift=0.3, cosmo=synth.COSMO)
+    ps = b.ParticleSnapshot(x=p[0], y=p[1], z=p[2], M=np.ones(n_part), L=Lbox, redshift=0.3, cosmo=synth.COSMO)
+    run = b.BaryonifySnapshot(cat, ps, 4, b.DisplacementModel(gaxes, dvals, 5, synth.COSMO), verbose=False)
+    out = run.process()
+    sc = run.last_scalars
+    hc = {k: cat.cat[k].astype('<f4') for k in ('M', 'x', 'y', 'z')}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want, n_pairs, _ = rp.baryonify_snapshot([p[0], p[1], p[2]], Lbox, hc, 1 / 1.3, sc["R_phys"], sc["R_model_com"], 4,
+                                                 rp.DisplacementTable(gaxes, dvals, 5), warn=False)
+    assert run.last_stats["n_pairs"] == n_pairs
+    for k, name in enumerate(("x", "y", "z")):
+        assert np.isnan(want[k][0]) and np.isnan(want[k][1])            # the reference's own behaviour
+        assert np.array_equal(np.isnan(out[name]), np.isnan(want[k]))
+        ok = ~np.isnan(want[k])
+        assert np.max(np.abs(out[name][ok] - want[k][ok])) < 1e-9
