@@ -34,8 +34,8 @@ sys.path.insert(0, ROOT)
 
 ALG_BYTES_PER_UPDATE = 48.0        # 3 x f64 read-modify-write of pix_offsets
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_shell_halos launch of the default workload (N = 1), from the
-# `ncu --set full` capture summarised in profiles/r1_shell_halos_v7_ncu_summary.txt (13.04 GB read + 53.86 GB write)
-NCU_TRAFFIC_DEFAULT_WORKLOAD = 66.900302e9
+# `ncu --set full` capture summarised in profiles/r1_shell_halos_v8_ncu_summary.txt (9.56 GB read + 24.40 GB write)
+NCU_TRAFFIC_DEFAULT_WORKLOAD = 33.957503e9
 
 
 def parse():
@@ -434,9 +434,9 @@ def run_b200(args):
                          "alg_bytes_per_launch": ALG_BYTES_PER_UPDATE * (n_up_local if world == 1 else n_up / world),
                          "kernel_ms": ms_kernel,
                          "note": "algorithmic bytes = the reference dataflow's 3 f64 read-modify-writes per update; with "
-                                 "sky-ordered halos ~92 % of those REDs are absorbed by the 126 MB L2 (ncu traffic 66.9 GB vs "
+                                 "sky-ordered halos ~96 % of those REDs are absorbed by the 126 MB L2 (ncu traffic 34.0 GB vs "
                                  "852 GB algorithmic), so frac can exceed 1 and the kernel's real limiter is the FP64 pipe "
-                                 "(51.6 % active, 45 FP64 instructions per update) + issue slots (64.7 %); see profiles/README.md"},
+                                 "(52.0 % active, 45 FP64 instructions per update) + issue slots (65.8 %); see profiles/README.md"},
             "e2e": e2e, "particles": particles}
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, cat, model, axes, vals, args.cpu_sample)
