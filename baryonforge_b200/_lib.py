@@ -62,6 +62,8 @@ _SIGNATURES = {
     "bfg_host_register": ([c_ptr, c_i64], C.c_int),
     "bfg_host_unregister": ([c_ptr], C.c_int),
     "bfg_copy_to_host_async": ([c_ptr, c_ptr, c_i64, c_ptr], C.c_int),
+    "bfg_box_records": ([c_i64, c_ptr, C.c_int, C.c_int, C.c_int, c_dbl, c_dbl, c_dbl, c_dbl, c_dbl, c_dbl, c_dbl, c_dbl,
+                         c_i64, c_ptr, c_ptr, c_ptr, c_ptr], C.c_int),
     "bfg_grid_offsets": ([c_ptr, C.c_int, c_i64, c_dbl, c_i64, c_ptr, c_ptr, C.c_int, C.c_int, c_ptr, c_i64, c_i64, c_ptr,
                           c_ptr], C.c_int),
     "bfg_grid_paint": ([c_ptr, C.c_int, c_i64, c_dbl, c_dbl, c_i64, c_ptr, c_ptr, C.c_int, C.c_int, c_ptr, c_i64, c_i64,

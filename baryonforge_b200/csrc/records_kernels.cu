@@ -121,3 +121,104 @@ extern "C" int bfg_shell_records(int64_t n_halo, const double *d_cols, int paint
     BFG_CUDA_OK(cudaGetLastError());
     return BFG_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ box runners
+// Per-halo scalars of the grid / snapshot runners on the device (Map2DRunner.py:484-520, :727-760; SnapshotRunner.py:219-228;
+// BaryonCorrection.py:398-399,410).  All halos of a HaloNDCatalog share one redshift, so the cosmology enters through
+// two scalars: g_run, g_mod with R_delta(M, a) = cbrt(M) * g (physical Mpc).  ln M comes from the host because the reference
+// evaluates it in float32.
+namespace {
+
+struct BoxParams {
+    int ndim, paint, grid;          // grid = 1: BaryonifyGrid / PaintProfilesGrid records, 0: BaryonifySnapshot records
+    double a, lnz, g_run, g_mod, eps_run, eps_mod, res, rq_clip;
+    int N;
+    const double *bins;             // [N] cell centres (grid runners)
+};
+
+// np.argmin(np.abs(bins - x)): first minimum among the cells around round((x - bins[0]) / res)  (Map2DRunner.py:512-513)
+__device__ __forceinline__ int nearest_bin(const double *__restrict__ bins, int N, double res, double x) {
+    double cf = floor((x - bins[0]) / res + 0.5);
+    cf = fmin(fmax(cf, 0.0), (double)(N - 1));
+    const int c = (int)cf;
+    int best = min(max(c - 1, 0), N - 1);
+    double dbest = fabs(bins[best] - x);
+    for (int o = 0; o <= 1; ++o) {          // ascending index order + strict '<' == argmin's first-minimum rule
+        const int cand = min(max(c + o, 0), N - 1);
+        const double d = fabs(bins[cand] - x);
+        if (d < dbest) { best = cand; dbest = d; }
+    }
+    return best;
+}
+
+__global__ void __launch_bounds__(256)
+k_box_records(i64 n, const double *__restrict__ cols, BoxParams P, double *__restrict__ halos, double *__restrict__ aux) {
+    for (i64 j = (i64)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (i64)gridDim.x * blockDim.x) {
+        const double M = cols[j], lnM = cols[4 * n + j];
+        double *H = halos + j * BFG_HALO_STRIDE;
+        const double cm = cbrt(M);
+        const double R_phys = cm * P.g_run;                                   // get_radius(cosmo, M_j, a_j)  :491 / :734 / :226
+        double R_mod = CUDART_NAN;
+        double Nf;
+        if (P.paint) {
+            const double R_com = R_phys / P.a;                                // :734
+            Nf = 2.0 * P.eps_run * R_com / P.res;                             // :740
+            H[BFG_HB_PAINTCUT] = R_com * P.eps_run;                           // :815
+            H[BFG_HB_RQ] = R_com * P.eps_run;
+            H[BFG_HB_RCUT] = CUDART_INF;
+            H[BFG_HB_LNRCOM] = 0.0;
+        } else {
+            const double R_q = fmin(fmax(P.eps_run * R_phys / P.a, 0.0), P.rq_clip);   // :492-493 / SnapshotRunner.py:227-228
+            Nf = 2.0 * R_q / P.res;                                           // :500
+            H[BFG_HB_RQ] = R_q;
+            R_mod = cm * P.g_mod / P.a;                                       // BaryonCorrection.py:399
+            H[BFG_HB_RCUT] = P.eps_mod * R_mod;                               // :410
+            H[BFG_HB_LNRCOM] = log(R_mod);                                    // :408
+            H[BFG_HB_PAINTCUT] = 0.0;
+        }
+        H[BFG_HB_LNZ] = P.lnz;
+        H[BFG_HB_LNM] = lnM;
+        for (int k = 0; k < 3; ++k) {
+            if (k < P.ndim) {
+                const double x = cols[(1 + k) * n + j];
+                H[BFG_HB_X + k] = x;
+                if (P.grid) {
+                    const int cen = nearest_bin(P.bins, P.N, P.res, x);
+                    H[BFG_HB_CX + k] = (double)cen;
+                    H[BFG_HB_DX + k] = P.bins[cen] - x;                       // :519-520
+                } else {
+                    H[BFG_HB_CX + k] = 0.0; H[BFG_HB_DX + k] = 0.0;
+                }
+            } else {
+                H[BFG_HB_X + k] = 0.0; H[BFG_HB_CX + k] = 0.0; H[BFG_HB_DX + k] = 0.0;
+            }
+        }
+        if (P.grid) {
+            double ns = floor(Nf / 2.0) * 2.0;                                // int(Nsize // 2) * 2   :501
+            ns = fmin(fmax(ns, 2.0), (double)(P.N / 2));                      // np.clip(Nsize, 2, bins.size // 2)  :503
+            H[BFG_HB_NSIZE] = ns;
+        } else {
+            H[BFG_HB_NSIZE] = 0.0;
+        }
+        if (aux) { aux[j] = R_phys; aux[n + j] = R_mod; }
+    }
+}
+
+}  // namespace
+
+extern "C" int bfg_box_records(int64_t n_halo, const double *d_cols, int ndim, int grid, int paint, double a, double lnz,
+                               double g_run, double g_mod, double eps_run, double eps_mod, double res, double rq_clip,
+                               int64_t N, const double *d_bins, double *d_halos, double *d_aux, void *stream) {
+    BFG_REQUIRE(n_halo >= 0 && (ndim == 2 || ndim == 3), "bad argument");
+    if (n_halo == 0) return BFG_OK;
+    BFG_REQUIRE(d_cols && d_halos, "null argument");
+    BFG_REQUIRE(!grid || (d_bins && N >= 2 && N <= 32768 && res > 0), "grid records need the cell centres");
+    BoxParams P;
+    P.ndim = ndim; P.paint = paint ? 1 : 0; P.grid = grid ? 1 : 0;
+    P.a = a; P.lnz = lnz; P.g_run = g_run; P.g_mod = g_mod; P.eps_run = eps_run; P.eps_mod = eps_mod;
+    P.res = grid ? res : 1.0; P.rq_clip = rq_clip; P.N = (int)N; P.bins = d_bins;
+    int blocks = (int)std::max<i64>(1, std::min<i64>((n_halo + 255) / 256, 148 * 8));
+    k_box_records<<<blocks, 256, 0, (cudaStream_t)stream>>>(n_halo, d_cols, P, d_halos, d_aux);
+    BFG_CUDA_OK(cudaGetLastError());
+    return BFG_OK;
+}

@@ -937,6 +937,49 @@ def _nearest_bin(bins, x):
     return best
 
 
+def _box_device_records(runner, cat, redshift, ndim, paint, grid, rq_clip, dev, bins=None, res=1.0):
+    """
+    Box (grid / snapshot) halo records built on the device (bfg_box_records): the host stages the float32-rounded
+    M, x, y, z and numpy's float32 ln M; returns (records [n, 16] on the device, aux [2, n]: R_phys, R_model_com).
+    """
+    torch = _torch()
+    n = cat.size
+    d_rec = torch.empty((n, _lib.HALO_STRIDE), dtype=torch.float64, device=dev)
+    d_aux = torch.empty((2, n), dtype=torch.float64, device=dev)
+    if n == 0:
+        return d_rec, d_aux
+    cosmo = cosmology.runner_cosmology(runner.cosmo, with_w0=False)               # Map2DRunner.py:462-465 (no w0)
+    a = 1 / (1 + redshift)
+    one = np.ones(1)
+    g_run = float(cosmology.radius_of_mass(cosmo, one, a, runner.mass_def)[0])
+    g_mod = 0.0
+    if not paint:
+        g_mod = float(cosmology.radius_of_mass(_model_cosmo(runner.model, cosmo), one, a,
+                                               getattr(runner.model, 'mass_def', None))[0])
+    stage = _take_scratch(5 * n)
+    cols = stage.numpy().reshape(5, n)
+    names = ['x', 'y', 'z'][:ndim]
+
+    def fill(sl):
+        M32 = cat['M'][sl].astype('<f4')                                          # io.py:204-205
+        cols[0, sl] = M32
+        cols[4, sl] = np.log(M32)                                                 # float32 log, SURVEY §10 #8
+        for k, name in enumerate(names):
+            cols[1 + k, sl] = cat[name][sl].astype('<f4')
+        for k in range(ndim, 3):
+            cols[1 + k, sl] = 0.0
+    _parallel_chunks(fill, n)
+    d_cols = stage.to(dev, non_blocking=True)
+    d_bins = None if bins is None else _to_device(bins, dev, dtype=np.float64)
+    _lib.check(_lib.lib().bfg_box_records(
+        n, d_cols.data_ptr(), ndim, 1 if grid else 0, 1 if paint else 0, float(a), float(np.log(1 / a)), g_run, g_mod,
+        float(runner.epsilon_max), 0.0 if paint else float(runner.model.epsilon_max), float(res), float(rq_clip),
+        0 if bins is None else int(bins.size), _lib.ptr(d_bins), d_rec.data_ptr(), d_aux.data_ptr(), _lib.current_stream()))
+    torch.cuda.current_stream().synchronize()     # the pinned staging buffer goes straight back to the pool
+    _give_scratch([stage])
+    return d_rec, d_aux
+
+
 class DefaultRunnerGrid(object):
     """Constructor contract of BaryonForge/Runners/Map2DRunner.py:255-278 (+ keyword-only GPU knobs)."""
 
@@ -978,6 +1021,44 @@ class DefaultRunnerGrid(object):
         if keep.all():
             return rec, extras
         return np.ascontiguousarray(rec[keep]), (None if extras is None else np.ascontiguousarray(extras[keep]))
+
+    def _records_on_device(self, paint, dev):
+        """
+        (records, extras, n) on the device, box-cell ordered.  Unsharded runs build the records ON THE DEVICE
+        (bfg_box_records); slab-sharded runs keep the host path, whose records also drive the per-rank halo filter.
+        """
+        import os
+        gm = self.GriddedMap
+        ndim, N = (2 if gm.is2D else 3), gm.Npix
+        lo, hi = self._planes(N)
+        if self.plane_range is not None or os.environ.get("BFG_DEVICE_RECORDS", "1") != "1":
+            rec, extras = self.halo_records(paint)
+            rec, extras = self._owned_halos(rec, extras, N, lo, hi)
+            d_rec = _upload_records(rec, dev)
+        else:
+            if self.use_ellipticity and not gm.is2D:
+                if paint:
+                    raise ValueError("use_ellipticity is not implemented for 3D maps")               # Map2DRunner.py:801
+                raise NotImplementedError("Currently not able to ellipticities with 3D maps.")       # Map2DRunner.py:571
+            cat = self.HaloNDCatalog.cat
+            bins = np.asarray(gm.bins, dtype=np.float64)
+            d_rec, d_aux = _box_device_records(self, cat, self.HaloNDCatalog.redshift, ndim, paint, True,
+                                               np.max(bins) / 2, dev, bins=bins, res=gm.res)
+            aux = d_aux.cpu().numpy()
+            self.last_scalars = dict(R_phys=aux[0], R_model_com=None if paint else aux[1])
+            if ndim == 2 and cat.size:
+                dxy = d_rec[:, _lib.HB_DX:_lib.HB_DX + 2]
+                assert bool((dxy <= gm.res).all().item()), "Halo offsets are larger than res"        # :522
+            keys = list(vars(self.model).get('p_keys', []))
+            _check_keys(self.model, keys)
+            extras = _extras(cat, keys)
+            if self.use_ellipticity:
+                Rmat = self.shear_matrices()
+                extras = Rmat if extras is None else np.ascontiguousarray(np.hstack([extras, Rmat]))
+        d_ext = None if extras is None else _to_device(extras, dev)
+        n = d_rec.shape[0]
+        d_rec, d_ext = _sort_records(d_rec, d_ext, 1, float(gm.L), 16, ndim)
+        return d_rec, d_ext, n
 
     def halo_records(self, paint):
         """Per-halo scalars of Map2DRunner.py:484-520 / :727-760 (+ BaryonCorrection.py:371,398-399,410), vectorised."""
@@ -1084,17 +1165,13 @@ class BaryonifyGrid(DefaultRunnerGrid):
         with torch.cuda.device(dev):
             table = self._tables.get((id(self.model), id(getattr(self.model, 'interp_d', None))),
                                      lambda: displacement_table_of(self.model, dev.index))
-        rec, extras = self.halo_records(paint=False)
-        rec, extras = self._owned_halos(rec, extras, N, lo, hi)
         with torch.cuda.device(dev):
-            d_rec = _upload_records(rec, dev)
-            d_ext = None if extras is None else _to_device(extras, dev)
-            d_rec, d_ext = _sort_records(d_rec, d_ext, 1, float(gm.L), 16, ndim)
+            d_rec, d_ext, n_rec = self._records_on_device(False, dev)
             nloc = (hi - lo) * N ** (ndim - 1)
             d_off = torch.zeros((ndim, nloc), dtype=torch.float64, device=dev)
             d_n = torch.zeros(1, dtype=torch.int64, device=dev)
             n_cols = 0 if d_ext is None else d_ext.shape[1]
-            _lib.check(L.bfg_grid_offsets(table.handle, ndim, N, float(gm.res), rec.shape[0], _lib.ptr(d_rec),
+            _lib.check(L.bfg_grid_offsets(table.handle, ndim, N, float(gm.res), n_rec, _lib.ptr(d_rec),
                                           _lib.ptr(d_ext), n_cols, 1 if self.use_ellipticity else 0, _lib.ptr(d_off), lo, hi,
                                           _lib.ptr(d_n), _lib.current_stream()))
         return d_off, d_n
@@ -1147,15 +1224,7 @@ class PaintProfilesGrid(DefaultRunnerGrid):
 
     def _device_records(self, dev):
         """Halo records (+ extras) of the owned planes on the device, box-cell ordered."""
-        gm = self.GriddedMap
-        ndim, N = (2 if gm.is2D else 3), gm.Npix
-        lo, hi = self._planes(N)
-        rec, extras = self.halo_records(paint=True)
-        rec, extras = self._owned_halos(rec, extras, N, lo, hi)
-        d_rec = _upload_records(rec, dev)
-        d_ext = None if extras is None else _to_device(extras, dev)
-        d_rec, d_ext = _sort_records(d_rec, d_ext, 1, float(gm.L), 16, ndim)
-        return d_rec, d_ext, rec.shape[0]
+        return self._records_on_device(True, dev)
 
     def paint_on_device(self):
         """The halo loop only: returns (painted owned planes on the device, flat; update-count tensor)."""
@@ -1360,11 +1429,27 @@ class BaryonifySnapshot(DefaultRunnerSnapshot):
         Lbox = float(ps.L)
         dev = self._device()
         L = _lib.lib()
-        rec, extras = self.halo_records()
-        ncell = self._pick_ncell(rec[:, _lib.HB_RQ], n_part, ndim, Lbox)
+        import os
         with torch.cuda.device(dev):
             table = self._tables.get((id(self.model), id(getattr(self.model, 'interp_d', None))),
                                      lambda: displacement_table_of(self.model, dev.index))
+            if os.environ.get("BFG_DEVICE_RECORDS", "1") == "1":      # per-halo scalars on the device (bfg_box_records)
+                cat = self.HaloNDCatalog.cat
+                d_rec0, d_aux = _box_device_records(self, cat, self.HaloNDCatalog.redshift, ndim, False, False, Lbox / 2, dev)
+                aux = d_aux.cpu().numpy()
+                self.last_scalars = dict(R_phys=aux[0], R_model_com=aux[1])
+                keys = list(vars(self.model).get('p_keys', []))
+                _check_keys(self.model, keys)
+                extras = _extras(cat, keys)
+                rq = d_rec0[:, _lib.HB_RQ].cpu().numpy() if cat.size else np.zeros(0)
+                n_rec = cat.size
+            else:
+                rec, extras = self.halo_records()
+                rq = rec[:, _lib.HB_RQ]
+                d_rec0 = _upload_records(rec, dev)
+                n_rec = rec.shape[0]
+        ncell = self._pick_ncell(rq, n_part, ndim, Lbox)
+        with torch.cuda.device(dev):
             st = _lib.current_stream()
             names = ['x', 'y', 'z'][:ndim]
             d_p = [_to_device(ps.cat[k], dev, dtype=np.float64) for k in names] + ([None] if ndim == 2 else [])
@@ -1374,13 +1459,12 @@ class BaryonifySnapshot(DefaultRunnerSnapshot):
             _lib.check(L.bfg_snap_build_cells(ndim, n_part, _lib.ptr(d_p[0]), _lib.ptr(d_p[1]), _lib.ptr(d_p[2]), Lbox,
                                               ncell, _lib.ptr(d_start), _lib.ptr(d_order), _lib.ptr(d_s[0]),
                                               _lib.ptr(d_s[1]), _lib.ptr(d_s[2]), st))
-            d_rec = _upload_records(rec, dev)
             d_ext = None if extras is None else _to_device(extras, dev)
-            d_rec, d_ext = _sort_records(d_rec, d_ext, 1, Lbox, 16, ndim)
+            d_rec, d_ext = _sort_records(d_rec0, d_ext, 1, Lbox, 16, ndim)
             d_tot = torch.zeros((ndim, n_part), dtype=torch.float64, device=dev)
             d_n = torch.zeros(1, dtype=torch.int64, device=dev)
             _lib.check(L.bfg_snap_offsets(table.handle, ndim, n_part, _lib.ptr(d_s[0]), _lib.ptr(d_s[1]), _lib.ptr(d_s[2]),
-                                          Lbox, ncell, _lib.ptr(d_start), rec.shape[0], _lib.ptr(d_rec), _lib.ptr(d_ext),
+                                          Lbox, ncell, _lib.ptr(d_start), n_rec, _lib.ptr(d_rec), _lib.ptr(d_ext),
                                           table.n_extra, _lib.ptr(d_tot), _lib.ptr(d_n), st))
             # displaced positions overwrite the (no longer needed) unsorted device copies
             _lib.check(L.bfg_snap_apply(ndim, n_part, _lib.ptr(d_s[0]), _lib.ptr(d_s[1]), _lib.ptr(d_s[2]), _lib.ptr(d_tot),

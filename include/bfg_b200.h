@@ -196,6 +196,19 @@ int bfg_host_unregister(void *h_ptr);
 int bfg_copy_to_host_async(void *h_dst, const void *d_src, int64_t bytes, void *stream);
 
 /* ---- periodic grids (2-D / 3-D) ------------------------------------------------------------------- */
+/* Per-halo scalars of the grid (grid = 1) / snapshot (grid = 0) runners on the device (Map2DRunner.py:484-520, :727-760;
+ * SnapshotRunner.py:219-228; BaryonCorrection.py:398-399,410): fills n_halo box records.
+ *   d_cols   [5][n_halo] float64: M, x, y, z (the float32-rounded catalogue values, utils/io.py:204-205) and np.log(M) as the
+ *            reference evaluates it, in float32
+ *   a, lnz   scale factor of the catalogue's single redshift and np.log(1/a)
+ *   g_run, g_mod   R_delta(M, a) = cbrt(M) * g for the runner's / the model's cosmology and mass definition (physical Mpc)
+ *   rq_clip  np.max(bins)/2 (grids, Map2DRunner.py:493) or L/2 (snapshots, SnapshotRunner.py:228)
+ *   d_bins   [N] cell centres (grids): centre cells = argmin|bins - x|, offsets bins[cen] - x, even cutout size clipped to
+ *            [2, N/2]
+ *   d_aux    optional [2][n_halo]: R_phys, R_com of the model (NaN for paint) -- for parity tests. */
+int bfg_box_records(int64_t n_halo, const double *d_cols, int ndim, int grid, int paint, double a, double lnz, double g_run,
+                    double g_mod, double eps_run, double eps_mod, double res, double rq_clip, int64_t N, const double *d_bins,
+                    double *d_halos, double *d_aux, void *stream);
 /* Halo loop of BaryonifyGrid.process (Map2DRunner.py:482-586).  d_offsets is [ndim][N^ndim] in units of cells,
  * restricted to axis-0 planes [plane_lo, plane_hi) (slab); NaNs propagate as in the reference.
  * 3-D grids whose size is a multiple of 16 (and plane_lo of 8) with a uniform ln r axis run the tile-centric gather

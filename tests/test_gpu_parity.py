@@ -600,3 +600,53 @@ def test_snapshot_particle_on_halo_centre_becomes_nan():
         assert np.array_equal(np.isnan(out[name]), np.isnan(want[k]))
         ok = ~np.isnan(want[k])
         assert np.max(np.abs(out[name][ok] - want[k][ok])) < 1e-9
+
+
+def test_box_device_records_match_host_formulas():
+    """bfg_box_records (device-side per-halo scalars of the grid / snapshot runners) vs the numpy restatement of
+    Map2DRunner.py:484-520 / SnapshotRunner.py:219-228 in halo_records(): centre cells, cutout sizes, float32 ln M and
+    positions bit-identical, radii to 1e-13 (cbrt vs pow)."""
+    import torch
+    import baryonforge_b200 as b
+    from baryonforge_b200 import _lib, synth
+    from baryonforge_b200.runners import _box_device_records
+    dev = torch.device('cuda', torch.cuda.current_device())
+    gaxes = synth.table_axes(nz=6, nM=10, nr=300, z_min=0.0, z_max=1.0, z_linear=True, r_min=1e-2, r_max=2e2)
+    dm = b.DisplacementModel(gaxes, synth.displacement_values(gaxes), 4, dict(synth.COSMO, Omega_m=0.33))
+    pm = b.ProfileModel(gaxes, synth.profile_values(gaxes) * 3, synth.profile_values(gaxes))
+    exact = (_lib.HB_X, _lib.HB_Y, _lib.HB_Z, _lib.HB_NSIZE, _lib.HB_CX, _lib.HB_CY, _lib.HB_CZ, _lib.HB_LNZ, _lib.HB_LNM,
+             _lib.HB_DX, _lib.HB_DY, _lib.HB_DZ)
+    close = (_lib.HB_RQ, _lib.HB_RCUT, _lib.HB_LNRCOM, _lib.HB_PAINTCUT)
+    for ndim, N, Lbox in ((3, 64, 200.0), (2, 128, 200.0)):
+        n = 20000
+        pos, M = synth.box_halos(n, Lbox, seed=4, ndim=ndim)
+        pos[:, 0] = 0.0; pos[:, 1] = Lbox * (1 - 1e-7)         # box edges: centre cells 0 and N - 1
+        M[2], M[3] = 1e8, 1e17                                 # cutout sizes clipped to 2 and to N / 2
+        bins = (np.arange(N) + 0.5) * Lbox / N
+        pos[0, 4] = bins[10] + 0.5 * (bins[1] - bins[0])       # (as close as float32 allows to) a tie between two cells
+        cat = b.HaloNDCatalog(x=pos[0], y=pos[1], z=pos[2] if ndim == 3 else None, M=M, redshift=0.3, cosmo=synth.COSMO)
+        gm = b.GriddedMap(map=np.zeros((N,) * ndim), redshift=0.3, bins=bins, cosmo=synth.COSMO)
+        for paint, model, cls in ((False, dm, b.BaryonifyGrid), (True, pm, b.PaintProfilesGrid)):
+            run = cls(cat, gm, 6, model, verbose=False)
+            want, _ = run.halo_records(paint=paint)
+            sc_w = run.last_scalars
+            d_rec, d_aux = _box_device_records(run, cat.cat, 0.3, ndim, paint, True, np.max(bins) / 2, dev, bins=bins,
+                                               res=gm.res)
+            got, aux = d_rec.cpu().numpy(), d_aux.cpu().numpy()
+            for f in exact:
+                assert np.array_equal(got[:, f], want[:, f]), (ndim, paint, f)
+            for f in close:
+                assert np.allclose(got[:, f], want[:, f], rtol=1e-13, atol=1e-14, equal_nan=True), (ndim, paint, f)   # ln R ~ 0
+            assert np.allclose(aux[0], sc_w["R_phys"], rtol=1e-13)
+            if not paint:
+                assert np.allclose(aux[1], sc_w["R_model_com"], rtol=1e-13)
+        ps = b.ParticleSnapshot(x=np.zeros(1), y=np.zeros(1), z=np.zeros(1) if ndim == 3 else None, M=1.0, L=Lbox,
+                                redshift=0.3, cosmo=synth.COSMO)
+        srun = b.BaryonifySnapshot(cat, ps, 5, dm, verbose=False)
+        want, _ = srun.halo_records()
+        d_rec, _ = _box_device_records(srun, cat.cat, 0.3, ndim, False, False, Lbox / 2, dev)
+        got = d_rec.cpu().numpy()
+        for f in (_lib.HB_X, _lib.HB_Y, _lib.HB_Z, _lib.HB_LNZ, _lib.HB_LNM):
+            assert np.array_equal(got[:, f], want[:, f]), ("snap", ndim, f)
+        for f in (_lib.HB_RQ, _lib.HB_RCUT, _lib.HB_LNRCOM):
+            assert np.allclose(got[:, f], want[:, f], rtol=1e-13, atol=1e-14), ("snap", ndim, f)
