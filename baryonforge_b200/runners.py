@@ -1422,6 +1422,19 @@ class BaryonifySnapshot(DefaultRunnerSnapshot):
     """BaryonForge/Runners/SnapshotRunner.py:161-274."""
 
     def process(self):
+        ps = self.ParticleSnapshot
+        d_p = self.process_on_device()
+        new_cat = ps.cat.copy()                                                   # :263
+        for k, name in enumerate(['x', 'y', 'z'][:(2 if ps.is2D else 3)]):
+            new_cat[name] = d_p[k].cpu().numpy()
+        return new_cat
+
+    def process_on_device(self):
+        """
+        The work of process() without the final download: returns the displaced, wrapped coordinates as float64 device
+        tensors [x, y(, z)] in the caller's particle order, so that what follows in the reference's workflow (NGP deposit,
+        P(k): deposit_ngp / spectra.ShellPowerSpectrum) can run without the particles leaving HBM.
+        """
         torch = _torch()
         ps = self.ParticleSnapshot
         ndim = 2 if ps.is2D else 3
@@ -1469,12 +1482,9 @@ class BaryonifySnapshot(DefaultRunnerSnapshot):
             # displaced positions overwrite the (no longer needed) unsorted device copies
             _lib.check(L.bfg_snap_apply(ndim, n_part, _lib.ptr(d_s[0]), _lib.ptr(d_s[1]), _lib.ptr(d_s[2]), _lib.ptr(d_tot),
                                         _lib.ptr(d_order), Lbox, _lib.ptr(d_p[0]), _lib.ptr(d_p[1]), _lib.ptr(d_p[2]), st))
-            new_cat = ps.cat.copy()                                               # :263
-            for k, name in enumerate(names):
-                new_cat[name] = d_p[k].cpu().numpy()
             n_pairs = int(d_n.cpu()[0])
         self.last_stats = dict(n_pairs=n_pairs, ncell=ncell)
-        return new_cat
+        return d_p[:ndim]
 
 
 def deposit_ngp(coords, mass, L, N_grid, device=None):

@@ -260,6 +260,30 @@ int bfg_snap_apply(int ndim, int64_t n_part, const double *d_xs, const double *d
 int bfg_snap_deposit_ngp(int ndim, int64_t n_part, const double *d_x, const double *d_y, const double *d_z,
                          const double *d_mass, double L, int64_t n_grid, double *d_grid, void *stream);
 
+/* ---- P(k) of a particle set: the measurement that follows BaryonifySnapshot.process() in the reference's workflow ------
+ * The reference has no library function for this step; it is the cell code of examples/10_Reproduce_Schneider_deltaPk.ipynb
+ * (cells 1, 12, 15), cited as nb10:cell.  Keeping it on the device means displaced particles never leave HBM. */
+/* `numba_histogram3d(Part % L_fold, bins = n_grid, min_vals = 0, max_vals = L_fold)` (nb10:1, nb10:15; L_fold = L / factor):
+ * d_grid [n_grid^3] float64 (zeroed by the caller) += 1 at cell int((x mod L_fold) / (L_fold / n_grid)) per axis, C order.
+ * Non-finite coordinates are skipped and counted in *d_ndropped (optional); a folded coordinate that rounds up to L_fold
+ * (undefined behaviour in the notebook's numba loop) goes to the last cell. */
+int bfg_snap_deposit_folded(int64_t n_part, const double *d_x, const double *d_y, const double *d_z, double L_fold,
+                            int64_t n_grid, double *d_grid, int64_t *d_ndropped, void *stream);
+/* Shell sums of |F|^2 over the half spectrum d_spec = rfftn(grid): complex128 [N][N][N/2+1] (interleaved re, im).
+ *   |k|(a, b, c) = sqrt(klin[a]^2 + klin[c]^2 + klin[b]^2)   (the notebook's axis order, nb10:12)
+ *   shell        = floor((|k| - k0) / dk), kept when 0 <= shell < Nk        (k0 = kbins[0], dk = kbins[1] - kbins[0])
+ *   d_pk_sum[s] = sum |F|^2, d_k_sum[s] = sum |k|, d_count[s] = number of modes of the FULL N^3 spectrum in shell s
+ * (modes whose mirror image is outside the half spectrum count twice), i.e. np.bincount(kinds[kmsk], weights = ...) of
+ * nb10:12,15 before the division by k_c.  d_klin [N] = np.fft.fftfreq(N, ...) from the host.  Outputs are zeroed here.
+ * d_spec may be NULL: only d_k_sum and d_count are produced (the notebook's k_c, k_cen). */
+int bfg_power_bin_spectrum(int64_t N, const double *d_spec, const double *d_klin, double k0, double dk, int64_t Nk,
+                           double *d_pk_sum, double *d_k_sum, int64_t *d_count, void *stream);
+/* np.fft.fftn(grid) (nb10:15) as a cuFFT D2Z transform into stream-ordered scratch (N^2 (N/2+1) complex128), followed by
+ * bfg_power_bin_spectrum.  d_grid [N^3] float64 is left untouched.  cuFFT is loaded at first use (dlopen; BFG_CUFFT_LIB
+ * overrides the library name); BFG_ERR_UNSUPPORTED if it cannot be found.  The D2Z plan is cached per (device, N). */
+int bfg_grid_power_spectrum(int64_t N, const double *d_grid, const double *d_klin, double k0, double dk, int64_t Nk,
+                            double *d_pk_sum, double *d_k_sum, int64_t *d_count, void *stream);
+
 /* ---- locality ordering ----------------------------------------------------------------------------- */
 /* Re-orders halo records (and their extras rows) so that neighbours on the sky / in the box are adjacent: north_star (b)
  * "halo batches sorted by sky or box cell for locality".  The reference walks the catalogue in the given order

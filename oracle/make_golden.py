@@ -346,6 +346,52 @@ def main():
     snap_case("snap_3d", 3, 30000, 100.0, 60, 41, 4, 5, 0.3)
     snap_case("snap_2d", 2, 20000, 100.0, 60, 42, 4, 5, 0.3)
 
+    # ---------------- P(k) of a particle set: the notebook cells that follow BaryonifySnapshot.process()
+    pk_case("pk_nb10_n48", 48, 30, 60000, 205.0 / 0.6711, 7)
+    pk_case("pk_nb10_n64", 64, 45, 150000, 100.0, 8)
+
+
+def notebook_cells(name):
+    import json
+    nb = json.load(open(os.path.join(REF, "examples", name)))
+    return ["".join(c["source"]) for c in nb["cells"]]
+
+
+def pk_case(name, Ngrd, Nk, n_part, Lbox, seed):
+    """
+    Executes the reference's own P(k) code -- cells 1, 12 and the `for factor in [1, 8]` body of cell 15 of
+    examples/10_Reproduce_Schneider_deltaPk.ipynb, read from the notebook file -- on a seeded particle set.  Only the two
+    size constants of cell 12 (Ngrd = 256, Nk = 180) are replaced.
+    """
+    cells = notebook_cells("10_Reproduce_Schneider_deltaPk.ipynb")
+    c1, c12, c15 = cells[1], cells[12], cells[15]
+    assert "def numba_histogram3d" in c1 and "kinds  = np.floor" in c12 and "for factor in [1, 8]:" in c15
+    c12 = c12.replace("Ngrd   = 256", "Ngrd   = %d" % Ngrd).replace("Nk     = 180", "Nk     = %d" % Nk)
+    assert "Ngrd   = %d" % Ngrd in c12 and "Nk     = %d" % Nk in c12
+    lines = c15.split("\n")
+    i0 = next(i for i, l in enumerate(lines) if l.strip() == "for factor in [1, 8]:")
+    i1 = next(i for i in range(i0, len(lines)) if lines[i].strip().startswith("PkB  = np.bincount"))
+    body = [l[4:] for l in lines[i0:i1 + 1]] + ["    RES[factor] = PkB"]
+    body = [l.replace("; del FFTB; gc.collect()", "").replace("; del MapB; gc.collect()", "") for l in body]
+
+    class _Snap(object):
+        pass
+    p = synth.pk_particles(n_part, Lbox, seed)
+    Snap = _Snap()
+    Snap.L = Lbox
+    Snap.cat = dict(x=p[:, 0], y=p[:, 1], z=p[:, 2])
+    from numba import njit
+    ns = dict(np=np, njit=njit, Snap=Snap, RES={})
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        exec(c1, ns)
+        exec(c12, ns)
+        ns["Part_B"] = ns["Part_D"]
+        exec("\n".join(body), ns)
+    save(name, kind="pk", Ngrd=Ngrd, Nk=Nk, n_part=n_part, L=Lbox, seed=seed, kbins=ns["kbins"], klin=ns["klin"],
+         k_c=ns["k_c"], k_cen=ns["k_cen"], pk_f1=ns["RES"][1], pk_f8=ns["RES"][8],
+         kinds_sum=np.int64(ns["kinds"][ns["kmsk"]].sum()))
+
 
 if __name__ == "__main__":
     main()

@@ -57,3 +57,25 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt, f
+
+
+def test_cufft_resolves_at_first_use_and_pk_has_no_cpu_fallback():
+    """bfg_grid_power_spectrum loads cuFFT with dlopen (no load-time dependency of libbfg_b200.so): without a GPU the call
+    must get past the loader (status BFG_ERR_CUDA = -2 from the runtime, not BFG_ERR_UNSUPPORTED = -3), and the Python
+    front end must raise instead of computing anything on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import numpy as np
+    import baryonforge_b200 as b
+    L = b._lib.lib()
+    a, c = np.zeros(8), np.zeros(8, dtype=np.int64)
+    rc = L.bfg_grid_power_spectrum(2, a.ctypes.data, a.ctypes.data, 1.0, 1.0, 4, a.ctypes.data, a.ctypes.data, c.ctypes.data,
+                                   None)
+    assert rc == -2, (rc, L.bfg_last_error())
+    sp = b.ShellPowerSpectrum(16, 8, 100.0)
+    assert sp.kbins.size == 9 and sp.klin.size == 16
+    with pytest.raises(b._lib.BFGError):
+        sp.measure(np.zeros((4, 3)))
+    with pytest.raises(b._lib.BFGError):
+        sp.k_c
