@@ -7,7 +7,7 @@ behaviour), so user scripts that build these objects for the reference runners w
 Differences, all invisible to the runners:
   * GriddedMap.grid / .inds (io.py:463-470: d full-size float64 meshgrids + an int64 index cube, 34 GB at
     1024^3) are built lazily on first access -- the GPU path never touches them.
-  * LightconeShell(path=...) needs healpy for FITS I/O (outside the hot path) and raises without it.
+  * LightconeShell(path=...) reads the FITS file with healpy when it is installed, else with fits.read_map.
 """
 import warnings
 
@@ -100,9 +100,10 @@ class LightconeShell(_Container):
         elif isinstance(path, str):
             try:
                 import healpy as hp
-            except ImportError as e:
-                raise ImportError("LightconeShell(path=...) reads FITS through healpy, which is not installed") from e
-            self.map = hp.read_map(path)
+                self.map = hp.read_map(path)                              # io.py:347
+            except ImportError:
+                from .fits import read_map                                # same file layout, no healpy needed
+                self.map = read_map(path)
         elif isinstance(map, np.ndarray):
             self.map = map
         nside = int(round(np.sqrt(self.map.size / 12.0)))
