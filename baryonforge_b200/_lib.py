@@ -76,6 +76,8 @@ _SIGNATURES = {
                           c_ptr, c_ptr, c_ptr], C.c_int),
     "bfg_snap_apply": ([C.c_int, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr], C.c_int),
     "bfg_snap_deposit_ngp": ([C.c_int, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_dbl, c_i64, c_ptr, c_ptr], C.c_int),
+    "bfg_snap_apply_deposit": ([C.c_int, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_dbl, c_dbl, c_i64, c_ptr, c_ptr],
+                               C.c_int),
     "bfg_snap_deposit_folded": ([c_i64, c_ptr, c_ptr, c_ptr, c_dbl, c_i64, c_ptr, c_ptr, c_ptr], C.c_int),
     "bfg_power_bin_spectrum": ([c_i64, c_ptr, c_ptr, c_dbl, c_dbl, c_i64, c_ptr, c_ptr, c_ptr, c_ptr], C.c_int),
     "bfg_grid_power_spectrum": ([c_i64, c_ptr, c_ptr, c_dbl, c_dbl, c_i64, c_ptr, c_ptr, c_ptr, c_ptr], C.c_int),

@@ -247,6 +247,26 @@ __global__ void k_deposit_ngp(i64 n, const double *__restrict__ x, const double 
     }
 }
 
+// k_snap_apply + k_deposit_ngp in one pass over the CELL-ORDERED particles, for callers that only need the deposited grid
+// (BaryonifySnapshot.process() followed by ParticleSnapshot.make_map, utils/io.py:629-677): the displaced positions are
+// never scattered back to the caller's order (the un-permute is a random 32-byte write per particle), and lanes that walk
+// the particles of one cell-list cell deposit into a handful of neighbouring grid cells.
+template <int NDIM>
+__global__ void k_snap_apply_deposit(i64 n, const double *__restrict__ xs, const double *__restrict__ ys,
+                                     const double *__restrict__ zs, const double *__restrict__ tot,
+                                     const i64 *__restrict__ order, const double *__restrict__ mass, double mass_const,
+                                     double L, i64 N, double *__restrict__ grid) {
+    const double step = L / (double)N;
+    for (i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (i64)gridDim.x * blockDim.x) {
+        const i64 bx = ngp_bin(wrap_once(xs[p] + tot[p], L), L, N, step);
+        const i64 by = ngp_bin(wrap_once(ys[p] + tot[n + p], L), L, N, step);
+        const i64 bz = (NDIM == 3) ? ngp_bin(wrap_once(zs[p] + tot[2 * n + p], L), L, N, step) : 0;
+        if (bx < 0 || by < 0 || bz < 0) continue;
+        const i64 c = (NDIM == 3) ? (bx * N + by) * N + bz : bx * N + by;
+        red_add(grid + c, mass ? mass[order[p]] : mass_const);
+    }
+}
+
 int blocks_for(i64 n, int threads) { return (int)std::max<i64>(1, std::min<i64>((n + threads - 1) / threads, 148 * 32)); }
 
 }  // namespace
@@ -356,6 +376,25 @@ extern "C" int bfg_snap_deposit_ngp(int ndim, int64_t n_part, const double *d_x,
     cudaStream_t st = (cudaStream_t)stream;
     if (ndim == 3) k_deposit_ngp<3><<<blocks_for(n_part, 256), 256, 0, st>>>(n_part, d_x, d_y, d_z, d_mass, L, n_grid, d_grid);
     else k_deposit_ngp<2><<<blocks_for(n_part, 256), 256, 0, st>>>(n_part, d_x, d_y, d_z, d_mass, L, n_grid, d_grid);
+    BFG_CUDA_OK(cudaGetLastError());
+    return BFG_OK;
+}
+
+extern "C" int bfg_snap_apply_deposit(int ndim, int64_t n_part, const double *d_xs, const double *d_ys, const double *d_zs,
+                                      const double *d_tot, const int64_t *d_order, const double *d_mass, double mass_const,
+                                      double L, int64_t n_grid, double *d_grid, void *stream) {
+    BFG_REQUIRE(ndim == 2 || ndim == 3, "ndim must be 2 or 3");
+    BFG_REQUIRE(n_grid >= 1 && L > 0, "bad grid");
+    if (n_part == 0) return BFG_OK;
+    BFG_REQUIRE(d_xs && d_ys && (ndim == 2 || d_zs) && d_tot && d_grid, "null argument");
+    BFG_REQUIRE(!d_mass || d_order, "per-particle masses are in the caller's order: d_order is needed");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ndim == 3)
+        k_snap_apply_deposit<3><<<blocks_for(n_part, 256), 256, 0, st>>>(n_part, d_xs, d_ys, d_zs, d_tot, (const i64 *)d_order,
+                                                                         d_mass, mass_const, L, n_grid, d_grid);
+    else
+        k_snap_apply_deposit<2><<<blocks_for(n_part, 256), 256, 0, st>>>(n_part, d_xs, d_ys, d_zs, d_tot, (const i64 *)d_order,
+                                                                         d_mass, mass_const, L, n_grid, d_grid);
     BFG_CUDA_OK(cudaGetLastError());
     return BFG_OK;
 }

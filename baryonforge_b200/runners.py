@@ -1429,11 +1429,11 @@ class BaryonifySnapshot(DefaultRunnerSnapshot):
             new_cat[name] = d_p[k].cpu().numpy()
         return new_cat
 
-    def process_on_device(self):
+    def _displace_sorted(self):
         """
-        The work of process() without the final download: returns the displaced, wrapped coordinates as float64 device
-        tensors [x, y(, z)] in the caller's particle order, so that what follows in the reference's workflow (NGP deposit,
-        P(k): deposit_ngp / spectra.ShellPowerSpectrum) can run without the particles leaving HBM.
+        Cell list + halo loop (SnapshotRunner.py:217-260) on the device.  Returns a dict with the CELL-ORDERED particle
+        coordinates `d_s`, their accumulated offsets `d_tot` [ndim][n_part], `d_order` (sorted slot -> caller's index), the
+        caller-ordered device copies `d_p` (free to be overwritten) and the geometry.
         """
         torch = _torch()
         ps = self.ParticleSnapshot
@@ -1479,12 +1479,57 @@ class BaryonifySnapshot(DefaultRunnerSnapshot):
             _lib.check(L.bfg_snap_offsets(table.handle, ndim, n_part, _lib.ptr(d_s[0]), _lib.ptr(d_s[1]), _lib.ptr(d_s[2]),
                                           Lbox, ncell, _lib.ptr(d_start), n_rec, _lib.ptr(d_rec), _lib.ptr(d_ext),
                                           table.n_extra, _lib.ptr(d_tot), _lib.ptr(d_n), st))
+        return dict(dev=dev, ndim=ndim, n_part=n_part, L=Lbox, d_p=d_p, d_s=d_s, d_tot=d_tot, d_order=d_order, d_n=d_n,
+                    ncell=ncell)
+
+    def _finish_stats(self, S):
+        self.last_stats = dict(n_pairs=int(S['d_n'].cpu()[0]), ncell=S['ncell'])
+
+    def process_on_device(self):
+        """
+        The work of process() without the final download: returns the displaced, wrapped coordinates as float64 device
+        tensors [x, y(, z)] in the caller's particle order, so that what follows in the reference's workflow (NGP deposit,
+        P(k): deposit_ngp / spectra.ShellPowerSpectrum) can run without the particles leaving HBM.
+        """
+        torch = _torch()
+        S = self._displace_sorted()
+        d_p, d_s = S['d_p'], S['d_s']
+        with torch.cuda.device(S['dev']):
             # displaced positions overwrite the (no longer needed) unsorted device copies
-            _lib.check(L.bfg_snap_apply(ndim, n_part, _lib.ptr(d_s[0]), _lib.ptr(d_s[1]), _lib.ptr(d_s[2]), _lib.ptr(d_tot),
-                                        _lib.ptr(d_order), Lbox, _lib.ptr(d_p[0]), _lib.ptr(d_p[1]), _lib.ptr(d_p[2]), st))
-            n_pairs = int(d_n.cpu()[0])
-        self.last_stats = dict(n_pairs=n_pairs, ncell=ncell)
-        return d_p[:ndim]
+            _lib.check(_lib.lib().bfg_snap_apply(S['ndim'], S['n_part'], _lib.ptr(d_s[0]), _lib.ptr(d_s[1]), _lib.ptr(d_s[2]),
+                                                 _lib.ptr(S['d_tot']), _lib.ptr(S['d_order']), S['L'], _lib.ptr(d_p[0]),
+                                                 _lib.ptr(d_p[1]), _lib.ptr(d_p[2]), _lib.current_stream()))
+            self._finish_stats(S)
+        return d_p[:S['ndim']]
+
+    def process_to_map_on_device(self, N_grid):
+        """
+        `ParticleSnapshot(<process() output>).make_map(N_grid)` (SnapshotRunner.py:263-273 + utils/io.py:629-677) in one pass
+        over the cell-ordered particles: the displaced positions are deposited (NGP, mass-weighted) straight from the cell
+        list's order, without the scatter back to the caller's order.  Returns a float64 device tensor (N_grid,)*ndim.
+        """
+        torch = _torch()
+        ps = self.ParticleSnapshot
+        M = ps.cat['M']
+        assert np.isnan(M).sum() == 0, "If you want to make a map, provide a value for the particle mass"   # io.py:659
+        S = self._displace_sorted()
+        d_s, ndim = S['d_s'], S['ndim']
+        with torch.cuda.device(S['dev']):
+            equal = M.size == 0 or bool(np.all(M == M[0]))
+            d_m = None if equal else _to_device(M, S['dev'], dtype=np.float64)
+            d_grid = torch.zeros((int(N_grid),) * ndim, dtype=torch.float64, device=S['dev'])
+            _lib.check(_lib.lib().bfg_snap_apply_deposit(ndim, S['n_part'], _lib.ptr(d_s[0]), _lib.ptr(d_s[1]), _lib.ptr(d_s[2]),
+                                                         _lib.ptr(S['d_tot']), _lib.ptr(S['d_order']), _lib.ptr(d_m),
+                                                         float(M[0]) if (equal and M.size) else 0.0, S['L'], int(N_grid),
+                                                         d_grid.data_ptr(), _lib.current_stream()))
+            self._finish_stats(S)
+        return d_grid
+
+    def process_to_map(self, N_grid):
+        """process() followed by make_map(N_grid) of the displaced particles, as a numpy array (see process_to_map_on_device)."""
+        return self.process_to_map_on_device(N_grid).cpu().numpy()
+
+
 
 
 def deposit_ngp(coords, mass, L, N_grid, device=None):

@@ -260,6 +260,14 @@ int bfg_snap_apply(int ndim, int64_t n_part, const double *d_xs, const double *d
 int bfg_snap_deposit_ngp(int ndim, int64_t n_part, const double *d_x, const double *d_y, const double *d_z,
                          const double *d_mass, double L, int64_t n_grid, double *d_grid, void *stream);
 
+/* bfg_snap_apply + bfg_snap_deposit_ngp in one pass over the CELL-ORDERED particles, for callers that only need the grid
+ * (BaryonifySnapshot.process() followed by ParticleSnapshot.make_map, SnapshotRunner.py:263-273 + utils/io.py:629-677): the
+ * displaced positions are not scattered back to the caller's order.  d_mass [n_part] is in the CALLER's order (gathered
+ * through d_order) or NULL for equal-mass particles (mass_const).  d_grid zeroed by the caller. */
+int bfg_snap_apply_deposit(int ndim, int64_t n_part, const double *d_xs, const double *d_ys, const double *d_zs,
+                           const double *d_tot, const int64_t *d_order, const double *d_mass, double mass_const, double L,
+                           int64_t n_grid, double *d_grid, void *stream);
+
 /* ---- P(k) of a particle set: the measurement that follows BaryonifySnapshot.process() in the reference's workflow ------
  * The reference has no library function for this step; it is the cell code of examples/10_Reproduce_Schneider_deltaPk.ipynb
  * (cells 1, 12, 15), cited as nb10:cell.  Keeping it on the device means displaced particles never leave HBM. */

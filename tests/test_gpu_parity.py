@@ -53,6 +53,42 @@ def test_ngp_deposit_matches_histogramdd(name):
     assert np.array_equal(b.runners.deposit_ngp([x, y], np.ones_like(x), L, 4), want)
 
 
+@pytest.mark.parametrize("name", golden_names("snap"))
+def test_snapshot_process_to_map_matches_process_then_make_map(name):
+    """BaryonifySnapshot.process_to_map (displacement + NGP deposit fused over the cell-ordered particles, no un-permute)
+    == the reference's process() followed by ParticleSnapshot.make_map, for equal and for per-particle masses."""
+    import baryonforge_b200 as b
+    from baryonforge_b200 import synth
+    g = load(name)
+    ndim, L = int(g["ndim"]), float(g["L"])
+    cosmo = synth.COSMO
+    mc = dict(Omega_m=0.27 + 0.05, Omega_b=0.05, h=0.68, sigma8=0.82, n_s=0.97, w0=-1.0)
+    cat = b.HaloNDCatalog(x=g["x"], y=g["y"], z=g["z"] if ndim == 3 else None, M=g["M"], redshift=g["redshift"], cosmo=cosmo)
+    model = b.DisplacementModel((g["ax0"], g["ax1"], g["ax2"]), g["values"], g["eps_mod"], mc)
+    ps = b.ParticleSnapshot(x=g["px"], y=g["py"], z=g["pz"] if ndim == 3 else None, M=g["pM"], L=L, redshift=g["redshift"],
+                            cosmo=cosmo)
+    run = b.BaryonifySnapshot(cat, ps, g["eps_run"], model, verbose=False)
+    got = run.process_to_map(16)
+    assert got.shape == (16,) * ndim
+    # equal masses: integer multiples of one particle mass; a particle within 1e-12 of a cell edge may change cell
+    assert np.abs(got - g["ngp"]).sum() <= 2 * g["pM"][0] and np.isclose(got.sum(), g["ngp"].sum(), rtol=1e-14)
+    out = run.process()
+    px = [out["x"], out["y"]] + ([out["z"]] if ndim == 3 else [])
+    assert np.array_equal(got, b.runners.deposit_ngp(px, g["pM"], L, 16))       # same positions, same cells
+    assert run.last_stats["n_pairs"] > 0
+    # per-particle masses (gathered through the sort permutation)
+    Mp = np.random.default_rng(5).uniform(0.5, 2.0, g["pM"].size) * 1e10
+    ps2 = b.ParticleSnapshot(x=g["px"], y=g["py"], z=g["pz"] if ndim == 3 else None, M=Mp, L=L, redshift=g["redshift"],
+                             cosmo=cosmo)
+    run2 = b.BaryonifySnapshot(cat, ps2, g["eps_run"], model, verbose=False)
+    got2 = run2.process_to_map(16)
+    assert_close(got2, b.runners.deposit_ngp(px, Mp, L, 16), name + " per-particle masses", rtol=1e-12)
+    ps3 = b.ParticleSnapshot(x=g["px"], y=g["py"], z=g["pz"] if ndim == 3 else None, M=None, L=L, redshift=g["redshift"],
+                             cosmo=cosmo)
+    with pytest.raises(AssertionError):                                       # utils/io.py:659
+        b.BaryonifySnapshot(cat, ps3, g["eps_run"], model, verbose=False).process_to_map(16)
+
+
 def test_healpix_device_geometry_matches_oracle():
     from baryonforge_b200 import healpix as dh
     from oracle import hpo
