@@ -17,7 +17,8 @@
  *    N^d grids (GriddedMap.map, utils/io.py:382-494).  Pixel / cell / particle ids are int64.
  *  - Halo records are rows of BFG_HALO_STRIDE float64 (128 B, one cache line) -- the per-halo scalars the
  *    reference computes at the top of each loop iteration (Runners/HealpixRunner.py:317-329,
- *    Runners/Map2DRunner.py:484-503, Runners/SnapshotRunner.py:219-228), vectorised once on the host.
+ *    Runners/Map2DRunner.py:484-503, Runners/SnapshotRunner.py:219-228), built once per process() on the device
+ *    (bfg_shell_records / bfg_box_records) or, for slab-sharded grids, vectorised on the host.
  */
 #ifndef BFG_B200_H
 #define BFG_B200_H
