@@ -236,6 +236,19 @@ class DefaultRunner(object):
         torch = _torch()
         return torch.device('cuda', torch.cuda.current_device() if self.device is None else int(self.device))
 
+    # ---- small public helpers of the reference's DefaultRunner (host-side numpy; not used by the device path)
+    def build_Rmat(self, A, ref):
+        """2 x 2 rotation by the angle between A and ref; both are normalised IN PLACE, like HealpixRunner.py:179-208."""
+        A /= np.linalg.norm(A)
+        ref /= np.linalg.norm(ref)
+        ang = np.arccos(np.dot(A, ref))
+        c, s_ = np.cos(ang), np.sin(ang)
+        return np.array([[c, -s_], [s_, c]])
+
+    def coord_array(self, *args):
+        """(N, M) coordinate rows from M same-shaped arrays (HealpixRunner.py:211-233)."""
+        return np.stack([np.ravel(a) for a in args], axis=1)
+
     def _record_plan(self, paint):
         """
         The per-halo scalars of HealpixRunner.py:317-329 (+ BaryonCorrection.py:371,398-399,410), vectorised, as a plan:
@@ -1128,6 +1141,35 @@ class DefaultRunnerGrid(object):
             extras = Rmat if extras is None else np.ascontiguousarray(np.hstack([extras, Rmat]))
         return rec, extras
 
+    # ---- small public helpers of the reference's DefaultRunnerGrid (host-side numpy; the device path uses
+    #      shear_matrices() and the cutout index math of csrc/grid_kernels.cu instead)
+    def build_Rmat(self, A, q):
+        """Shear matrix of one halo from its orientation A (normalised IN PLACE) and axis ratio q (Map2DRunner.py:281-350)."""
+        A /= np.linalg.norm(A)
+        if len(A) == 1:
+            raise ValueError("Can't rotate a 1-dimensional vector")
+        if len(A) == 3:
+            raise NotImplementedError("This method has not yet been verified. Use 2D ellipticity method instead")
+        beta = np.arccos(np.dot(A, np.array([1., 0.])))
+        eta = -np.log(q)
+        if eta > 1e-4:
+            eta2g = np.tanh(0.5 * eta) / eta
+        else:
+            etasq = eta * eta
+            eta2g = 0.5 + etasq * ((-1 / 24) + etasq * (1 / 240))
+        g = eta2g * eta * np.exp(2j * beta)
+        return np.array([[1 + g.real, g.imag], [g.imag, 1 - g.real]]) / np.sqrt(1 - np.abs(g) ** 2)
+
+    def coord_array(self, *args):
+        """(N, M) coordinate rows from M same-shaped arrays (Map2DRunner.py:353-375)."""
+        return np.stack([np.ravel(a) for a in args], axis=1)
+
+    def pick_indices(self, center, width, Npix):
+        """Periodic cutout indices center - width .. center + width - 1 (Map2DRunner.py:400-429; one wrap, like the reference)."""
+        inds = np.arange(center - width, center + width)
+        inds = np.where(inds < 0, inds + Npix, inds)
+        return np.where(inds >= Npix, inds - Npix, inds)
+
     def shear_matrices(self):
         """
         build_Rmat(A_ell, q_ell) of every halo (Map2DRunner.py:281-350,495-498,533), row-major [n, 4], with the reference's
@@ -1407,6 +1449,21 @@ class DefaultRunnerSnapshot(object):
         keys = list(vars(self.model).get('p_keys', []))
         _check_keys(self.model, keys)
         return rec, _extras(cat, keys)
+
+    # ---- small public helpers of the reference's DefaultRunnerSnapshot (host-side numpy; k_snap_halos does the same
+    #      minimum-image arithmetic on the device)
+    def enforce_periodicity(self, dx):
+        """Minimum image of a coordinate difference, one wrap (SnapshotRunner.py:135-158)."""
+        L = self.ParticleSnapshot.L
+        dx = np.where(dx > L / 2, dx - L, dx)
+        return np.where(dx < -L / 2, dx + L, dx)
+
+    def compute_distance(self, *args):
+        """Periodic Euclidean distance from per-axis differences (SnapshotRunner.py:103-132)."""
+        d = 0
+        for dx in args:
+            d = d + self.enforce_periodicity(dx) ** 2
+        return np.sqrt(d)
 
     def _pick_ncell(self, rq, n_part, ndim, Lbox):
         if self.ncell is not None:

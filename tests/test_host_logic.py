@@ -192,3 +192,35 @@ def test_first_pixel_at_colatitude_is_a_ring_start():
                 assert theta[p - 1] < t + 1e-12
             if p < npix:
                 assert theta[p] >= t - 1e-12
+
+
+def test_public_helper_methods_of_the_runner_base_classes():
+    """build_Rmat / coord_array / pick_indices / enforce_periodicity / compute_distance keep the reference's behaviour
+    (HealpixRunner.py:179-233, Map2DRunner.py:281-375,400-429, SnapshotRunner.py:103-158), checked on known answers."""
+    import baryonforge_b200 as b
+    sh = object.__new__(b.runners.DefaultRunner)
+    A, ref = np.array([0.0, 2.0]), np.array([3.0, 0.0])
+    R = sh.build_Rmat(A, ref)
+    assert np.allclose(A, [0, 1]) and np.allclose(ref, [1, 0])                 # normalised in place
+    assert np.allclose(R, [[0, -1], [1, 0]])
+    xy = sh.coord_array(np.arange(6).reshape(2, 3), 10 * np.arange(6).reshape(2, 3))
+    assert xy.shape == (6, 2) and np.array_equal(xy[4], [4, 40])
+    gr = object.__new__(b.runners.DefaultRunnerGrid)
+    assert np.allclose(gr.build_Rmat(np.array([1.0, 0.0]), 1.0), np.eye(2))    # round halo: identity
+    S = gr.build_Rmat(np.array([2.0, 0.0]), 0.5)                               # galsim Shear(q = 0.5, beta = 0)
+    g = np.tanh(0.5 * np.log(2.0))
+    assert np.allclose(S, np.array([[1 + g, 0], [0, 1 - g]]) / np.sqrt(1 - g * g)) and np.isclose(np.linalg.det(S), 1.0)
+    with pytest.raises(NotImplementedError):
+        gr.build_Rmat(np.array([1.0, 0.0, 0.0]), 0.5)
+    with pytest.raises(ValueError):
+        gr.build_Rmat(np.array([1.0]), 0.5)
+    assert np.array_equal(gr.pick_indices(1, 3, 10), [8, 9, 0, 1, 2, 3])
+    assert np.array_equal(gr.pick_indices(9, 2, 10), [7, 8, 9, 0])
+    assert np.array_equal(gr.coord_array(np.ones((2, 2)), np.zeros((2, 2))), np.array([[1, 0]] * 4))
+    sn = object.__new__(b.runners.DefaultRunnerSnapshot)
+
+    class _PS(object):
+        L = 10.0
+    sn.ParticleSnapshot = _PS()
+    assert np.array_equal(sn.enforce_periodicity(np.array([6.0, -6.0, 5.0, -5.0, 1.0])), [-4.0, 4.0, 5.0, -5.0, 1.0])
+    assert np.allclose(sn.compute_distance(np.array([9.0]), np.array([-8.0]), np.array([0.5])), np.sqrt(1 + 4 + 0.25))
