@@ -12,6 +12,7 @@
 // halo touches is ONE contiguous range of the sorted arrays: lanes read consecutive particles (coalesced 8-byte
 // loads) and their REDs land on consecutive addresses of the cell-ordered offset array.
 #include <algorithm>
+#include <cstdlib>
 #include <cub/device/device_scan.cuh>
 #include "bfg_common.cuh"
 
@@ -52,6 +53,35 @@ __global__ void k_cell_fill(i64 n, const double *__restrict__ x, const double *_
         double4 r;
         r.x = x[i]; r.y = y[i]; r.z = (NDIM == 3) ? z[i] : 0.0; r.w = __longlong_as_double(i);
         rec[slot] = r;
+    }
+}
+
+// Two-pass variant of the scatter (BFG_CELL_SORT=2, staged for measurement): with ~10^7 cells a single-pass scatter keeps
+// ~10^7 partially written 128-byte lines open, far more than the L2 holds, so DRAM sees isolated 32-byte sector writes.
+// Pass A scatters the records into <= 65536 coarse buckets (runs of `group` consecutive cells, bucket start =
+// cell_start[bucket * group]): few enough write heads for the L2 to merge the four records of a line before it is evicted.
+// Pass B reads the bucket-ordered records coalesced and places them in their cells; everything in flight then lands in a
+// window of a few MB.
+__global__ void k_cell_coarse(i64 n, const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ z,
+                              const int *__restrict__ cell_id, const i64 *__restrict__ cell_start, int group, i64 ncells,
+                              unsigned long long *__restrict__ cursor_a, double4 *__restrict__ tmp) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        const i64 b = cell_id[i] / group;
+        const i64 slot = cell_start[min(b * group, ncells)] + (i64)atomicAdd(cursor_a + b, 1ULL);
+        double4 r;
+        r.x = x[i]; r.y = y[i]; r.z = z ? z[i] : 0.0; r.w = __longlong_as_double(i);
+        tmp[slot] = r;
+    }
+}
+
+template <int NDIM>
+__global__ void k_cell_fine(i64 n, const double4 *__restrict__ tmp, double L, int nc, const i64 *__restrict__ cell_start,
+                            unsigned long long *__restrict__ cursor, double4 *__restrict__ rec) {
+    for (i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (i64)gridDim.x * blockDim.x) {
+        const double4 r = tmp[p];
+        int c = cell_of(r.x, L, nc) * nc + cell_of(r.y, L, nc);                 // the cell k_cell_count assigned
+        if (NDIM == 3) c = c * nc + cell_of(r.z, L, nc);
+        rec[cell_start[c] + (i64)atomicAdd(cursor + c, 1ULL)] = r;
     }
 }
 
@@ -300,14 +330,30 @@ extern "C" int bfg_snap_build_cells(int ndim, int64_t n_part, const double *d_x,
     if (n_part > 0) {
         double4 *rec = nullptr;   // 32-byte particle records (stream-ordered scratch)
         BFG_CUDA_OK(cudaMallocAsync(&rec, sizeof(double4) * n_part, st));
-        if (ndim == 3) {
+        const char *mode = getenv("BFG_CELL_SORT");
+        const bool two_pass = mode && mode[0] == '2' && ncells > 65536;
+        double4 *tmp = nullptr;
+        unsigned long long *cursor_a = nullptr;
+        if (two_pass) {
+            const int group = (int)std::max<i64>(ncell, (ncells + 65535) / 65536);
+            const i64 n_buckets = (ncells + group - 1) / group;
+            BFG_CUDA_OK(cudaMallocAsync(&tmp, sizeof(double4) * n_part, st));
+            BFG_CUDA_OK(cudaMallocAsync(&cursor_a, sizeof(unsigned long long) * n_buckets, st));
+            BFG_CUDA_OK(cudaMemsetAsync(cursor_a, 0, sizeof(unsigned long long) * n_buckets, st));
+            k_cell_coarse<<<blocks_for(n_part, 256), 256, 0, st>>>(n_part, d_x, d_y, ndim == 3 ? d_z : nullptr, cell_id,
+                                                                   (const i64 *)d_cell_start, group, ncells, cursor_a, tmp);
+            if (ndim == 3) k_cell_fine<3><<<blocks_for(n_part, 256), 256, 0, st>>>(n_part, tmp, L, ncell, (const i64 *)d_cell_start, counts, rec);
+            else k_cell_fine<2><<<blocks_for(n_part, 256), 256, 0, st>>>(n_part, tmp, L, ncell, (const i64 *)d_cell_start, counts, rec);
+        } else if (ndim == 3) {
             k_cell_fill<3><<<blocks_for(n_part, 256), 256, 0, st>>>(n_part, d_x, d_y, d_z, cell_id, (const i64 *)d_cell_start, counts, rec);
-            k_unpack_records<3><<<blocks_for(n_part, 256), 256, 0, st>>>(n_part, rec, (i64 *)d_order, d_xs, d_ys, d_zs);
         } else {
             k_cell_fill<2><<<blocks_for(n_part, 256), 256, 0, st>>>(n_part, d_x, d_y, d_z, cell_id, (const i64 *)d_cell_start, counts, rec);
-            k_unpack_records<2><<<blocks_for(n_part, 256), 256, 0, st>>>(n_part, rec, (i64 *)d_order, d_xs, d_ys, d_zs);
         }
+        if (ndim == 3) k_unpack_records<3><<<blocks_for(n_part, 256), 256, 0, st>>>(n_part, rec, (i64 *)d_order, d_xs, d_ys, d_zs);
+        else k_unpack_records<2><<<blocks_for(n_part, 256), 256, 0, st>>>(n_part, rec, (i64 *)d_order, d_xs, d_ys, d_zs);
         BFG_CUDA_OK(cudaGetLastError());
+        if (tmp) BFG_CUDA_OK(cudaFreeAsync(tmp, st));
+        if (cursor_a) BFG_CUDA_OK(cudaFreeAsync(cursor_a, st));
         BFG_CUDA_OK(cudaFreeAsync(rec, st));
     }
     BFG_CUDA_OK(cudaFreeAsync(scan_tmp, st));
