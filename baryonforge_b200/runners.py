@@ -179,6 +179,25 @@ def _model_cosmo(model, fallback):
 SKY_BAND_RAD = 0.04     # colatitude band width of the sky ordering (~160 pixels at NSIDE=4096)
 
 
+class _Ident(object):
+    """Cache-key element that compares by object IDENTITY and keeps the object alive: a bare id() can be handed to a new
+    object once the old one is collected (`Runner.model = NewModel` in a loop, examples/10_...ipynb cell 15), which would
+    make a stale device table look current."""
+    __slots__ = ('obj',)
+
+    def __init__(self, obj):
+        self.obj = obj
+
+    def __eq__(self, other):
+        return isinstance(other, _Ident) and other.obj is self.obj
+
+    def __ne__(self, other):
+        return not self.__eq__(other)
+
+    def __hash__(self):
+        return id(self.obj)
+
+
 class _TableCache(object):
     """Tables go to the device once per (model, table) and are re-used by later process() calls."""
 
@@ -508,7 +527,7 @@ class BaryonifyShell(DefaultRunner):
         npix = 12 * NSIDE * NSIDE
         lo, hi = self._range(npix)
         with torch.cuda.device(dev):   # table first: a model without one fails here, as in the reference
-            table = self._tables.get((id(self.model), id(self.model.interp_d) if hasattr(self.model, 'interp_d') else 0),
+            table = self._tables.get((_Ident(self.model), _Ident(self.model.interp_d) if hasattr(self.model, 'interp_d') else 0),
                                      lambda: displacement_table_of(self.model, dev.index))
         with torch.cuda.device(dev):
             d_off = torch.zeros((3, hi - lo), dtype=torch.float64, device=dev)
@@ -548,7 +567,7 @@ class BaryonifyShell(DefaultRunner):
         keys = list(vars(self.model).get('p_keys', []))
         _check_keys(self.model, keys)
         with torch.cuda.device(dev):
-            table = self._tables.get((id(self.model), id(self.model.interp_d) if hasattr(self.model, 'interp_d') else 0),
+            table = self._tables.get((_Ident(self.model), _Ident(self.model.interp_d) if hasattr(self.model, 'interp_d') else 0),
                                      lambda: displacement_table_of(self.model, dev.index))
             if getattr(self, '_scratch_inflight', None):
                 torch.cuda.current_stream().synchronize()
@@ -784,7 +803,7 @@ class PaintProfilesShell(DefaultRunner):
         npix = self.LightconeShell.map.size
         lo, hi = self._range(npix)
         with torch.cuda.device(dev):
-            table = self._tables.get((id(self.model), id(getattr(self.model, 'interp2D', None))),
+            table = self._tables.get((_Ident(self.model), _Ident(getattr(self.model, 'interp2D', None))),
                                      lambda: profile_table_of(self.model, '2D', dev.index))
         with torch.cuda.device(dev):
             d_new = torch.zeros(hi - lo, dtype=torch.float64, device=dev)
@@ -806,7 +825,7 @@ class PaintProfilesShell(DefaultRunner):
         npix = self.LightconeShell.map.size
         lo, hi = self._range(npix)
         with torch.cuda.device(dev):
-            table = self._tables.get((id(self.model), id(getattr(self.model, 'interp2D', None))),
+            table = self._tables.get((_Ident(self.model), _Ident(getattr(self.model, 'interp2D', None))),
                                      lambda: profile_table_of(self.model, '2D', dev.index))
         with torch.cuda.device(dev):
             d_new = torch.zeros(hi - lo, dtype=torch.float64, device=dev)
@@ -899,9 +918,9 @@ class PaintProfilesAnisShell(DefaultRunner):
             warnings.warn("Inputted halos contribute more mass than is available for this mean matter density."
                           "Your Mtot_model profiles are either too extended or you are using the wrong cosmology.")
         with torch.cuda.device(dev):
-            t_paint = self._tables.get((id(self.model), id(getattr(self.model, 'interp2D', None))),
+            t_paint = self._tables.get((_Ident(self.model), _Ident(getattr(self.model, 'interp2D', None))),
                                        lambda: profile_table_of(self.model, '2D', dev.index))
-            t_tracer = self._tables2.get((id(self.Tracer_model), id(getattr(self.Tracer_model, 'interp2D', None))),
+            t_tracer = self._tables2.get((_Ident(self.Tracer_model), _Ident(getattr(self.Tracer_model, 'interp2D', None))),
                                          lambda: profile_table_of(self.Tracer_model, '2D', dev.index))
             d_orig = _to_device(orig_map[lo:hi], dev, dtype=np.float64)
             d_new = torch.zeros(hi - lo, dtype=torch.float64, device=dev)
@@ -1205,7 +1224,7 @@ class BaryonifyGrid(DefaultRunnerGrid):
         ndim, N = (2 if gm.is2D else 3), gm.Npix
         lo, hi = self._planes(N)
         with torch.cuda.device(dev):
-            table = self._tables.get((id(self.model), id(getattr(self.model, 'interp_d', None))),
+            table = self._tables.get((_Ident(self.model), _Ident(getattr(self.model, 'interp_d', None))),
                                      lambda: displacement_table_of(self.model, dev.index))
         with torch.cuda.device(dev):
             d_rec, d_ext, n_rec = self._records_on_device(False, dev)
@@ -1280,7 +1299,7 @@ class PaintProfilesGrid(DefaultRunnerGrid):
         dV = float(np.power(gm.res, ndim)) if self.include_pixel_size else 1.0    # :723,825
         with torch.cuda.device(dev):
             d_rec, d_ext, n = self._device_records(dev)
-            table = self._tables.get((id(self.model), which, id(getattr(self.model, 'interp' + which, None))),
+            table = self._tables.get((_Ident(self.model), which, _Ident(getattr(self.model, 'interp' + which, None))),
                                      lambda: profile_table_of(self.model, which, dev.index))
             nloc = (hi - lo) * N ** (ndim - 1)
             d_new = torch.zeros(nloc, dtype=torch.float64, device=dev)
@@ -1369,9 +1388,9 @@ class PaintProfilesAnisGrid(PaintProfilesGrid):
                           "Your Mtot_model profiles are either too extended or you are using the wrong cosmology.")
         final = float(np.power(res, 2)) if self.include_pixel_size else 1.0       # :1012-1015
         with torch.cuda.device(dev):
-            t_paint = self._tables.get((id(self.model), '2D', id(getattr(self.model, 'interp2D', None))),
+            t_paint = self._tables.get((_Ident(self.model), '2D', _Ident(getattr(self.model, 'interp2D', None))),
                                        lambda: profile_table_of(self.model, '2D', dev.index))
-            t_tracer = self._tables2.get((id(self.Tracer_model), id(getattr(self.Tracer_model, 'interp2D', None))),
+            t_tracer = self._tables2.get((_Ident(self.Tracer_model), _Ident(getattr(self.Tracer_model, 'interp2D', None))),
                                          lambda: profile_table_of(self.Tracer_model, '2D', dev.index))
             d_rec, d_ext, n = self._device_records(dev)
             d_orig = _to_device(orig_map[lo:hi], dev, dtype=np.float64)
@@ -1501,7 +1520,7 @@ class BaryonifySnapshot(DefaultRunnerSnapshot):
         L = _lib.lib()
         import os
         with torch.cuda.device(dev):
-            table = self._tables.get((id(self.model), id(getattr(self.model, 'interp_d', None))),
+            table = self._tables.get((_Ident(self.model), _Ident(getattr(self.model, 'interp_d', None))),
                                      lambda: displacement_table_of(self.model, dev.index))
             if os.environ.get("BFG_DEVICE_RECORDS", "1") == "1":      # per-halo scalars on the device (bfg_box_records)
                 cat = self.HaloNDCatalog.cat

@@ -224,3 +224,42 @@ def test_public_helper_methods_of_the_runner_base_classes():
     sn.ParticleSnapshot = _PS()
     assert np.array_equal(sn.enforce_periodicity(np.array([6.0, -6.0, 5.0, -5.0, 1.0])), [-4.0, 4.0, 5.0, -5.0, 1.0])
     assert np.allclose(sn.compute_distance(np.array([9.0]), np.array([-8.0]), np.array([0.5])), np.sqrt(1 + 4 + 0.25))
+
+
+def test_table_cache_is_keyed_by_identity_not_by_a_recyclable_id():
+    """`Runner.model = NewModel` in a loop (examples/10_...ipynb cell 15): a new model must never be served the previous
+    model's device table, even when CPython gives it the address of the collected one."""
+    from baryonforge_b200.runners import _Ident, _TableCache
+
+    class FakeTable(object):
+        def __init__(self, tag):
+            self.tag, self.closed = tag, False
+
+        def close(self):
+            self.closed = True
+
+    class Model(object):
+        def __init__(self, tag):
+            self.interp_d = [tag]
+
+    cache = _TableCache()
+    made = []
+
+    def table_for(m):
+        def make():
+            made.append(FakeTable(m.interp_d[0]))
+            return made[-1]
+        return cache.get((_Ident(m), _Ident(m.interp_d)), make)
+
+    m = Model(0)
+    t0 = table_for(m)
+    assert table_for(m) is t0 and len(made) == 1                      # same model, same table object: re-used
+    for k in range(1, 50):                                            # fresh models, the old ones become garbage
+        m = Model(k)
+        t = table_for(m)
+        assert t.tag == k, "stale table served for a new model"
+        assert made[-2].closed and not t.closed
+    m.interp_d = [99]                                                 # setup_interpolator() re-run on the same model
+    assert table_for(m).tag == 99
+    assert _Ident(m) == _Ident(m) and _Ident(m) != _Ident(Model(1)) and (_Ident(m), '2D') != (_Ident(m), '3D')
+    assert _Ident(None) == _Ident(None) and _Ident(m) != 0
