@@ -11,6 +11,12 @@ with numpy (cosmology.py), packed into 128-byte halo records.  Everything per (h
 CUDA.  PyTorch is used only for device memory, streams and (parallel.py) torch.distributed.
 There is no CPU fallback: without a GPU / the shared library, process() raises.
 """
+import os
+import time
+import warnings
+import weakref
+from concurrent.futures import ThreadPoolExecutor
+
 import numpy as np
 
 from . import _lib, cosmology
@@ -93,7 +99,6 @@ def _pinned_result(numel):
     array handed to the caller (and every view of it) is garbage-collected, so steady-state calls never pay the ~0.5 s/GB
     page-locking of a fresh allocation; a caller that keeps N results alive simply owns N buffers.
     """
-    import weakref
     torch = _torch()
     free = _PINNED_FREE.setdefault(numel, [])
     t = free.pop() if free else torch.empty(numel, dtype=torch.float64, pin_memory=True)
@@ -124,7 +129,6 @@ def _give_scratch(tensors):
 
 def _host_threads():
     """Host threads of this process: BFG_HOST_THREADS, else min(16, cores / processes of this box (torchrun))."""
-    import os
     if "BFG_HOST_THREADS" in os.environ:
         return int(os.environ["BFG_HOST_THREADS"])
     local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
@@ -133,14 +137,12 @@ def _host_threads():
 
 def _parallel_chunks(fn, n, chunk=65536):
     """Run fn(slice) over [0, n) in chunks on a small thread pool (BFG_HOST_THREADS, default min(16, cores))."""
-    import os
     nthreads = _host_threads()
     slices = [slice(i, min(i + chunk, n)) for i in range(0, n, chunk)]
     if nthreads <= 1 or len(slices) <= 1:
         for sl in slices:
             fn(sl)
         return
-    from concurrent.futures import ThreadPoolExecutor
     with ThreadPoolExecutor(max_workers=nthreads) as ex:
         list(ex.map(fn, slices))
 
@@ -386,7 +388,6 @@ class DefaultRunner(object):
             # Sharded runs: every rank needs the whole catalogue on its device (it selects its own halos there), but the
             # host staging is split -- rank r stages halos [r m, (r+1) m) and the columns are all-gathered over NVLink.
             world, rank = 1, 0
-            import os
             if self.pix_range is not None and os.environ.get("BFG_SHARD_STAGING", "1") == "1":
                 from .parallel import _dist
                 dist = _dist()
@@ -436,7 +437,6 @@ class DefaultRunner(object):
         Stage raw columns -> device scalar prep -> sky sort -> `launch(d_rec, d_ext, n, 0)`.  Nothing here waits for the
         GPU; halos that cannot touch [lo, hi) are skipped inside the halo-loop kernel (ring-range sharding).
         """
-        import time
         torch = _torch()
         t0 = time.perf_counter()
         cat = self.HaloLightConeCatalog.cat
@@ -482,7 +482,6 @@ class BaryonifyShell(DefaultRunner):
     def _peer_slices(self, npix, dev):
         """Peer-mapped owned slices for the fused regrid + exchange (needs an initialised NCCL group whose ranks use the
         ranges of parallel.pixel_ranges); None -> fall back to full-size partial maps + all-reduce."""
-        import os
         import torch.distributed as dist
         if os.environ.get("BFG_EXCHANGE", "p2p") != "p2p":
             return None
@@ -505,7 +504,6 @@ class BaryonifyShell(DefaultRunner):
 
     def _shared_host(self, npix, peers):
         """Shared page-locked host maps for the result (parallel.SharedHostMaps); None -> per-rank full-map D2H."""
-        import os
         if os.environ.get("BFG_HOST_GATHER", "shared") != "shared":
             return None
         key = (npix, peers.world, peers.rank)
@@ -562,7 +560,6 @@ class BaryonifyShell(DefaultRunner):
         n = cat.size
         dev = self._device()
         L = _lib.lib()
-        import os
         K = int(os.environ.get("BFG_PIPELINE_CHUNKS", self.PIPELINE_CHUNKS))
         keys = list(vars(self.model).get('p_keys', []))
         _check_keys(self.model, keys)
@@ -576,7 +573,6 @@ class BaryonifyShell(DefaultRunner):
             st = _lib.current_stream()
             main = torch.cuda.current_stream()
             side = _side_stream(dev)
-            import time
             t0 = time.perf_counter()
             d_rec = self.device_records(False, dev)
             host_prep_s = time.perf_counter() - t0
@@ -680,7 +676,6 @@ class BaryonifyShell(DefaultRunner):
         NSIDE = self.LightconeShell.NSIDE
         if _all_close_to_zero(orig_map):             # :293-294 returns the input object
             return orig_map
-        import os
         if (self.pix_range is None and self.sort_halos and os.environ.get("BFG_PIPELINE", "1") == "1"
                 and os.environ.get("BFG_PROFILE_E2E") != "1"
                 and self.HaloLightConeCatalog.cat.size >= self.PIPELINE_MIN_HALOS):
@@ -689,7 +684,6 @@ class BaryonifyShell(DefaultRunner):
         L = _lib.lib()
         npix = orig_map.size
         lo, hi = self._range(npix)
-        import os, time
         prof = os.environ.get("BFG_PROFILE_E2E") == "1"
         t_start = time.perf_counter()
         with torch.cuda.device(dev):
@@ -878,7 +872,6 @@ class PaintProfilesAnisShell(DefaultRunner):
         return d
 
     def process(self):
-        import warnings
         torch = _torch()
         dev = self._device()
         L = _lib.lib()
@@ -1059,7 +1052,6 @@ class DefaultRunnerGrid(object):
         (records, extras, n) on the device, box-cell ordered.  Unsharded runs build the records ON THE DEVICE
         (bfg_box_records); slab-sharded runs keep the host path, whose records also drive the per-rank halo filter.
         """
-        import os
         gm = self.GriddedMap
         ndim, N = (2 if gm.is2D else 3), gm.Npix
         lo, hi = self._planes(N)
@@ -1352,7 +1344,6 @@ class PaintProfilesAnisGrid(PaintProfilesGrid):
         return d
 
     def process(self):
-        import warnings
         gm = self.GriddedMap
         assert gm.is2D == True, "Can only paint tSZ on 2D maps. You have passed a 3D Map"   # noqa: E712  (:847)
         torch = _torch()
@@ -1518,7 +1509,6 @@ class BaryonifySnapshot(DefaultRunnerSnapshot):
         Lbox = float(ps.L)
         dev = self._device()
         L = _lib.lib()
-        import os
         with torch.cuda.device(dev):
             table = self._tables.get((_Ident(self.model), _Ident(getattr(self.model, 'interp_d', None))),
                                      lambda: displacement_table_of(self.model, dev.index))
