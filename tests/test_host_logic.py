@@ -263,3 +263,48 @@ def test_table_cache_is_keyed_by_identity_not_by_a_recyclable_id():
     assert table_for(m).tag == 99
     assert _Ident(m) == _Ident(m) and _Ident(m) != _Ident(Model(1)) and (_Ident(m), '2D') != (_Ident(m), '3D')
     assert _Ident(None) == _Ident(None) and _Ident(m) != 0
+
+
+def test_parallel_driver_mirrors_keep_the_reference_contract_without_a_gpu():
+    """SimpleParallel / SplitJoinParallel (utils/Parallelize.py:8-113, 116-320) with a duck-typed painting runner: output
+    order, njobs semantics, the seeded reshuffle + ceil(N / njobs) chunks, include_pixel_size not forwarded,
+    Baryonify* runners refused (:206-209)."""
+    import baryonforge_b200 as b
+    from baryonforge_b200 import synth
+
+    class CountingPainter(object):
+        """process() = histogram of halo masses over 8 'pixels' -- additive over halos like a painting runner."""
+        def __init__(self, HaloLightConeCatalog, LightconeShell, epsilon_max, model, use_ellipticity=False, mass_def=None,
+                     include_pixel_size=False, verbose=True):
+            self.HaloLightConeCatalog, self.LightconeShell = HaloLightConeCatalog, LightconeShell
+            self.cosmo = HaloLightConeCatalog.cosmology
+            self.epsilon_max, self.model, self.use_ellipticity, self.mass_def = epsilon_max, model, use_ellipticity, mass_def
+            self.include_pixel_size, self.verbose = include_pixel_size, verbose
+
+        def process(self):
+            cat = self.HaloLightConeCatalog.cat
+            return np.bincount((cat['ra'] // 45).astype(int), weights=cat['M'], minlength=8) + self.LightconeShell.map[:8]
+
+    ra, dec, M, z = synth.sky_halos(103, seed=9)
+    cat = b.HaloLightConeCatalog(ra=ra, dec=dec, M=M, z=z, cosmo=synth.COSMO)
+    shell = b.LightconeShell(map=np.zeros(12 * 4 * 4), cosmo=synth.COSMO)
+    whole = CountingPainter(cat, shell, 5, None, include_pixel_size=True)
+    sj = b.SplitJoinParallel(whole, njobs=4)
+    assert sj.njobs == 4 and len(sj.Runner_list) == 4
+    sizes = [len(r.HaloLightConeCatalog.cat) for r in sj.Runner_list]
+    assert sizes == [26, 26, 26, 25]                                             # ceil(103 / 4) per split
+    perm = np.random.default_rng(42).choice(103, size=103, replace=False)         # Parallelize.py:255
+    assert np.array_equal(sj.Runner_list[0].HaloLightConeCatalog.cat['M'], M[perm[:26]])
+    assert all(r.include_pixel_size is False and r.verbose is False for r in sj.Runner_list)   # :271 drops it
+    assert all(np.all(r.LightconeShell.map == 0) for r in sj.Runner_list)
+    np.testing.assert_allclose(sj.process(), whole.process(), rtol=1e-12)
+    # njobs = -1: the reference forks cpu_count() workers (Parallelize.py:210); on the GPU one pass does the same sum
+    assert b.SplitJoinParallel(whole).njobs == 1
+    a, c = CountingPainter(cat[:10], shell, 5, None), CountingPainter(cat[10:30], shell, 5, None)
+    outs = b.SimpleParallel([a, c, a]).process()
+    assert len(outs) == 3 and np.array_equal(outs[0], a.process()) and np.array_equal(outs[1], c.process())
+    assert b.SimpleParallel([a, c, a], njobs=2).njobs == 2 and b.SimpleParallel([a, c]).njobs == 2
+    axes = synth.table_axes()
+    model = b.DisplacementModel(axes, synth.displacement_values(axes), 20, synth.COSMO)
+    with pytest.raises(AssertionError):
+        b.SplitJoinParallel(b.BaryonifyShell(cat, shell, 20, model, verbose=False), njobs=2)
