@@ -79,6 +79,7 @@ _SIGNATURES = {
     "bfg_snap_apply_deposit": ([C.c_int, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_dbl, c_dbl, c_i64, c_ptr, c_ptr],
                                C.c_int),
     "bfg_snap_deposit_folded": ([c_i64, c_ptr, c_ptr, c_ptr, c_dbl, c_i64, c_ptr, c_ptr, c_ptr], C.c_int),
+    "bfg_snap_apply_deposit_folded": ([c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_dbl, c_dbl, c_i64, c_ptr, c_ptr, c_ptr], C.c_int),
     "bfg_power_bin_spectrum": ([c_i64, c_ptr, c_ptr, c_dbl, c_dbl, c_i64, c_ptr, c_ptr, c_ptr, c_ptr], C.c_int),
     "bfg_grid_power_spectrum": ([c_i64, c_ptr, c_ptr, c_dbl, c_dbl, c_i64, c_ptr, c_ptr, c_ptr, c_ptr], C.c_int),
     "bfg_halo_sort": ([C.c_int, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, c_dbl, c_dbl, C.c_int, c_ptr], C.c_int),

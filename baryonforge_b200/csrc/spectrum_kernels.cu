@@ -59,6 +59,36 @@ k_deposit_folded(i64 n, const double *__restrict__ x, const double *__restrict__
     }
 }
 
+// k_deposit_folded straight from the CELL-ORDERED particles of bfg_snap_build_cells + their accumulated offsets (what
+// k_snap_apply_deposit does for the NGP grid): position = wrap_once(xs + tot) exactly as bfg_snap_apply computes it
+// (SnapshotRunner.py:263-273), then the folded cell.  Lanes walk the particles of one cell-list cell, so their REDs fall
+// into neighbouring grid cells instead of random DRAM sectors.  Staged for measurement.
+__global__ void __launch_bounds__(256)
+k_apply_deposit_folded(i64 n, const double *__restrict__ xs, const double *__restrict__ ys, const double *__restrict__ zs,
+                       const double *__restrict__ tot, double L, double Lfold, i64 N, double *__restrict__ grid,
+                       unsigned long long *__restrict__ n_dropped) {
+    const double width = __ddiv_rn(Lfold - 0.0, (double)N);
+    i64 dropped = 0;
+    for (i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (i64)gridDim.x * blockDim.x) {
+        double q[3] = {xs[p] + tot[p], ys[p] + tot[n + p], zs[p] + tot[2 * n + p]};
+        i64 c[3];
+        bool ok = true;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            if (q[k] > L) q[k] -= L;                         // the single wrap of SnapshotRunner.py:272-273
+            if (q[k] < 0) q[k] += L;
+            c[k] = folded_cell(q[k], Lfold, width, N);
+            ok = ok && (c[k] >= 0);
+        }
+        if (!ok) { ++dropped; continue; }
+        red_add(grid + (c[0] * N + c[1]) * N + c[2], 1.0);
+    }
+    if (n_dropped) {
+        dropped = warp_sum_i64(dropped);
+        if ((threadIdx.x & 31) == 0 && dropped) atomicAdd(n_dropped, (unsigned long long)dropped);
+    }
+}
+
 // One warp per (a, b) row of the half spectrum, lanes along c (coalesced 16-byte loads).  Along a row |k| never decreases,
 // so equal shell indices sit in adjacent lanes: a segmented shuffle reduction leaves one shared-memory atomic per
 // (row chunk, shell) instead of one per mode; per-CTA shell sums then go out with one RED per non-empty shell.
@@ -220,6 +250,21 @@ extern "C" int bfg_snap_deposit_folded(int64_t n_part, const double *d_x, const 
     BFG_REQUIRE(d_x && d_y && d_z && d_grid, "null argument");
     const int blocks = (int)std::max<i64>(1, std::min<i64>((n_part + 255) / 256, 148 * 32));
     k_deposit_folded<<<blocks, 256, 0, st>>>(n_part, d_x, d_y, d_z, L_fold, n_grid, d_grid, (unsigned long long *)d_ndropped);
+    BFG_CUDA_OK(cudaGetLastError());
+    return BFG_OK;
+}
+
+extern "C" int bfg_snap_apply_deposit_folded(int64_t n_part, const double *d_xs, const double *d_ys, const double *d_zs,
+                                             const double *d_tot, double L, double L_fold, int64_t n_grid, double *d_grid,
+                                             int64_t *d_ndropped, void *stream) {
+    BFG_REQUIRE(n_part >= 0 && n_grid >= 1 && n_grid <= 4096 && L_fold > 0 && L > 0, "bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d_ndropped) BFG_CUDA_OK(cudaMemsetAsync(d_ndropped, 0, sizeof(int64_t), st));
+    if (n_part == 0) return BFG_OK;
+    BFG_REQUIRE(d_xs && d_ys && d_zs && d_tot && d_grid, "null argument");
+    const int blocks = (int)std::max<i64>(1, std::min<i64>((n_part + 255) / 256, 148 * 32));
+    k_apply_deposit_folded<<<blocks, 256, 0, st>>>(n_part, d_xs, d_ys, d_zs, d_tot, L, L_fold, n_grid, d_grid,
+                                                   (unsigned long long *)d_ndropped);
     BFG_CUDA_OK(cudaGetLastError());
     return BFG_OK;
 }

@@ -123,6 +123,31 @@ class ShellPowerSpectrum(object):
             self.last_dropped = int(d_drop.cpu()[0])
         return d_grid
 
+    def measure_runner(self, runner, factors=(1,)):
+        """
+        `Runner.process()` followed by one `measure()` per folding factor (the body of the parameter loop of nb10:15), with the
+        deposits taken straight from the cell-ordered particles of the runner's cell list (bfg_snap_apply_deposit_folded): the
+        displaced particles are never scattered back to the caller's order.  Returns [P(k) for factor in factors].
+        STAGED: written after the GPU budget of round 1 was spent; tests/test_gpu_spectrum.py covers it only with
+        BFG_TEST_EXPERIMENTAL=1.  `measure(runner.process_on_device(), factor)` is the measured path.
+        """
+        torch = _torch()
+        S = runner._displace_sorted()
+        if S['ndim'] != 3:
+            raise ValueError("P(k) is measured on 3-D particle sets (x, y, z)")
+        d_s, out = S['d_s'], []
+        with torch.cuda.device(S['dev']):
+            d_drop = torch.zeros(1, dtype=torch.int64, device=S['dev'])
+            for factor in factors:
+                d_grid = torch.zeros((self.Ngrd,) * 3, dtype=torch.float64, device=S['dev'])
+                _lib.check(_lib.lib().bfg_snap_apply_deposit_folded(
+                    S['n_part'], d_s[0].data_ptr(), d_s[1].data_ptr(), d_s[2].data_ptr(), S['d_tot'].data_ptr(), S['L'],
+                    self.Lbox / factor, self.Ngrd, d_grid.data_ptr(), d_drop.data_ptr(), _lib.current_stream()))
+                out.append(self.measure_grid(d_grid))
+            self.last_dropped = int(d_drop.cpu()[0])
+            runner._finish_stats(S)
+        return out
+
     def measure_grid(self, grid):
         """nb10:15 from the FFT on: np.bincount(kinds[kmsk], weights = |fftn(grid)|^2) / k_c for an (Ngrd,)*3 grid (numpy array
         or float64 CUDA tensor)."""

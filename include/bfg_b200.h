@@ -278,6 +278,13 @@ int bfg_snap_apply_deposit(int ndim, int64_t n_part, const double *d_xs, const d
  * (undefined behaviour in the notebook's numba loop) goes to the last cell. */
 int bfg_snap_deposit_folded(int64_t n_part, const double *d_x, const double *d_y, const double *d_z, double L_fold,
                             int64_t n_grid, double *d_grid, int64_t *d_ndropped, void *stream);
+/* bfg_snap_deposit_folded over the CELL-ORDERED particles of bfg_snap_build_cells and their accumulated offsets d_tot
+ * [3][n_part] (3-D): position = wrap_once(xs + tot) as bfg_snap_apply computes it (SnapshotRunner.py:263-273), then the
+ * folded cell -- the displaced particles are never scattered back to the caller's order.  Same grid as
+ * bfg_snap_apply + bfg_snap_deposit_folded.  Staged: not measured in round 1. */
+int bfg_snap_apply_deposit_folded(int64_t n_part, const double *d_xs, const double *d_ys, const double *d_zs,
+                                  const double *d_tot, double L, double L_fold, int64_t n_grid, double *d_grid,
+                                  int64_t *d_ndropped, void *stream);
 /* Shell sums of |F|^2 over the half spectrum d_spec = rfftn(grid): complex128 [N][N][N/2+1] (interleaved re, im).
  *   |k|(a, b, c) = sqrt(klin[a]^2 + klin[c]^2 + klin[b]^2)   (the notebook's axis order, nb10:12)
  *   shell        = floor((|k| - k0) / dk), kept when 0 <= shell < Nk        (k0 = kbins[0], dk = kbins[1] - kbins[0])
