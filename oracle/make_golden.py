@@ -163,6 +163,26 @@ def main():
     shell_bary("shell_bary_n32_signed", 32, 150, 12, 10, 20, map_lo=-10.0)
     shell_bary("shell_bary_n32_rdelta", 32, 150, 13, 20, 8, rdelta=True)
 
+    def shell_bary_config1(name, nside=256, n=10000, seed=42, eps_run=20, eps_mod=20, stride=8):
+        """BASELINE.json configs[0] at full size -- BaryonifyShell NSIDE=256, 10^4 halos of the reference's own test
+        distribution (tests/test_healpix.py:29-32), table 10x10x500, epsilon_max=20 -- run by the reference's code.  Inputs
+        are regenerated from the seeds; the fixture keeps the per-halo pyccl scalars and every `stride`-th output pixel."""
+        ra, dec, M, z = synth.sky_halos(n, seed=seed)
+        hmap = synth.shell_map(nside, seed=seed + 1)
+        vals = synth.displacement_values(axes)
+        model = ref_displacement_model(axes, vals, eps_mod, '2D', False)
+        cat = HaloLightConeCatalog(ra=ra, dec=dec, M=M, z=z, cosmo=cosmo)
+        shell = LightconeShell(map=hmap, cosmo=cosmo)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            new_map = BaryonifyShell(cat, shell, eps_run, model, verbose=False).process()
+        R_run, D_A, R_mod = per_halo_scalars_shell(ccl, cosmo, model, cat.cat['M'], cat.cat['z'])
+        save(name, kind="shell_bary_config1", nside=nside, n=n, seed=seed, eps_run=eps_run, eps_mod=eps_mod, stride=stride,
+             R_run=R_run, D_A=D_A, R_mod=R_mod, out_sub=new_map[::stride], out_sum=new_map.sum(), map_sum=hmap.sum(),
+             n_changed=np.int64(np.count_nonzero(new_map != hmap)))
+
+    shell_bary_config1("shell_bary_config1")
+
     def shell_paint(name, nside, n, seed, eps_run, pixsize):
         ra, dec, M, z = shell_catalog(n, seed)
         model = ref_profile_model(axes, pvals * 3.0, pvals)
