@@ -196,6 +196,22 @@ def main():
              ax0=axes[0], ax1=axes[1], ax2=axes[2], raw2D=pvals, raw3D=pvals * 3.0, eps_run=eps_run, pixsize=pixsize,
              R_run=R_run, D_A=D_A, out=new_map)
 
+    def shell_paint_config2_map(name, nside=1024, n=10000, seed=42, eps_run=20, stride=128):
+        """BASELINE.json configs[1] (PaintProfilesShell, NSIDE=1024) at the full map size with 10^4 of its halos -- what the
+        reference's code can paint in seconds.  Inputs regenerate from the seeds; every `stride`-th output pixel is kept."""
+        ra, dec, M, z = synth.sky_halos(n, seed=seed)
+        model = ref_profile_model(axes, pvals * 3.0, pvals)
+        cat = HaloLightConeCatalog(ra=ra, dec=dec, M=M, z=z, cosmo=cosmo)
+        shell = LightconeShell(map=np.zeros(12 * nside * nside), cosmo=cosmo)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            new_map = PaintProfilesShell(cat, shell, eps_run, model, include_pixel_size=False, verbose=False).process()
+        R_run, D_A, _ = per_halo_scalars_shell(ccl, cosmo, None, cat.cat['M'], cat.cat['z'])
+        save(name, kind="shell_paint_config2", nside=nside, n=n, seed=seed, eps_run=eps_run, stride=stride, R_run=R_run, D_A=D_A,
+             out_sub=new_map[::stride], out_sum=new_map.sum(), n_painted=np.int64(np.count_nonzero(new_map)))
+
+    shell_paint_config2_map("shell_paint_config2_map")
+
     shell_paint("shell_paint_n64", 64, 400, 21, 20, False)
     shell_paint("shell_paint_n32_pixsize", 32, 150, 22, 10, True)
 
