@@ -74,6 +74,9 @@ def test_ring_nest_conversion_hierarchy():
     want2 = [3, 7, 11, 15, 2, 1, 6, 5, 10, 9, 14, 13, 19, 0, 23, 4, 27, 8, 31, 12, 17, 22, 21, 26, 25, 30, 29, 18, 16, 35, 20,
              39, 24, 43, 28, 47, 34, 33, 38, 37, 42, 41, 46, 45, 32, 36, 40, 44]
     assert hpo.ring2nest(2, np.arange(48)).tolist() == want2
+    # healpy docstrings: hp.ring2nest(16, 1504) -> 1130, hp.nest2ring(16, 1130) -> 1504, hp.nest2ring(2, np.arange(10))
+    assert hpo.ring2nest(16, np.array([1504]))[0] == 1130 and hpo.nest2ring(16, np.array([1130]))[0] == 1504
+    assert hpo.nest2ring(2, np.arange(10)).tolist() == [13, 5, 4, 0, 15, 7, 6, 1, 17, 9]
     for nside in (1, 2, 4, 16, 128):
         npix = 12 * nside * nside
         r = np.arange(npix)
