@@ -178,6 +178,51 @@ def _model_cosmo(model, fallback):
     return c
 
 
+def _table_range_messages(model, z, M):
+    """
+    The out-of-table warnings of BaryonificationClass._readout (BaryonCorrection.py:378-389) for a whole catalogue: the
+    reference evaluates them for every halo inside the loop; here once per process() from the catalogue's extremes (SURVEY.md
+    section 10 #13).  Returns the message list (same wording); never raises -- a diagnostic must not break process().
+    """
+    try:
+        zr, Mr = getattr(model, 'raw_input_z_range', None), getattr(model, 'raw_input_M_range', None)
+        if zr is None or Mr is None:
+            grid = getattr(getattr(model, 'interp_d', None), 'grid', None)
+            if grid is None:
+                return []
+            zr, Mr = grid[0], grid[1]
+        z = np.atleast_1d(np.asarray(z, dtype=np.float64))
+        M = np.atleast_1d(np.asarray(M, dtype=np.float64))
+        if z.size == 0 or M.size == 0:
+            return []
+        z_tab, M_tab = np.exp(np.asarray(zr, dtype=np.float64)) - 1, np.exp(np.asarray(Mr, dtype=np.float64))
+        out = []
+        if (np.min(z) < np.min(z_tab)) | (np.max(z) > np.max(z_tab)):
+            out.append(f"Requested redshift range [{np.min(z)}, {np.max(z)}] outside table's range "
+                       f"[{np.min(z_tab)}, {np.max(z_tab)}]")
+        if (np.min(M) < np.min(M_tab)) | (np.max(M) > np.max(M_tab)):
+            out.append(f"Requested log_Mass range [{np.log10(np.min(M))}, {np.log10(np.max(M))}] outside "
+                       f"table's range [{np.log10(np.min(M_tab))}, {np.log10(np.max(M_tab))}]")
+        return out
+    except Exception:
+        return []
+
+
+def _warn_table_range(model, z, M, runner=None, owner=None):
+    """Emit the messages; with `runner`, only once per (model, catalogue `owner`) so that repeated process() calls on the same
+    inputs do not rescan a 10^6-halo catalogue (a few ms of host time on the end-to-end path)."""
+    if runner is not None:
+        key = (id(model), id(owner), np.size(M))
+        if getattr(runner, '_range_checked', None) == key:
+            return
+        try:
+            runner._range_checked = key
+        except Exception:
+            pass
+    for text in _table_range_messages(model, z, M):
+        warnings.warn(text, UserWarning, stacklevel=3)
+
+
 SKY_BAND_RAD = 0.04     # colatitude band width of the sky ordering (~160 pixels at NSIDE=4096)
 
 
@@ -676,6 +721,8 @@ class BaryonifyShell(DefaultRunner):
         NSIDE = self.LightconeShell.NSIDE
         if _all_close_to_zero(orig_map):             # :293-294 returns the input object
             return orig_map
+        _warn_table_range(self.model, self.HaloLightConeCatalog.cat['z'], self.HaloLightConeCatalog.cat['M'], self,
+                          self.HaloLightConeCatalog.cat)
         if (self.pix_range is None and self.sort_halos and os.environ.get("BFG_PIPELINE", "1") == "1"
                 and os.environ.get("BFG_PROFILE_E2E") != "1"
                 and self.HaloLightConeCatalog.cat.size >= self.PIPELINE_MIN_HALOS):
@@ -1237,6 +1284,7 @@ class BaryonifyGrid(DefaultRunnerGrid):
         lo, hi = self._planes(N)
         dev = self._device()
         L = _lib.lib()
+        _warn_table_range(self.model, self.HaloNDCatalog.redshift, self.HaloNDCatalog.cat['M'], self, self.HaloNDCatalog.cat)
         with torch.cuda.device(dev):
             # halo loop first (asynchronous); the map is only needed by the re-binning, so its upload runs on a side stream
             # underneath the halo loop (a pageable source blocks the host, not the GPU)
@@ -1509,6 +1557,7 @@ class BaryonifySnapshot(DefaultRunnerSnapshot):
         Lbox = float(ps.L)
         dev = self._device()
         L = _lib.lib()
+        _warn_table_range(self.model, self.HaloNDCatalog.redshift, self.HaloNDCatalog.cat['M'], self, self.HaloNDCatalog.cat)
         with torch.cuda.device(dev):
             table = self._tables.get((_Ident(self.model), _Ident(getattr(self.model, 'interp_d', None))),
                                      lambda: displacement_table_of(self.model, dev.index))

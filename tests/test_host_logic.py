@@ -308,3 +308,29 @@ def test_parallel_driver_mirrors_keep_the_reference_contract_without_a_gpu():
     model = b.DisplacementModel(axes, synth.displacement_values(axes), 20, synth.COSMO)
     with pytest.raises(AssertionError):
         b.SplitJoinParallel(b.BaryonifyShell(cat, shell, 20, model, verbose=False), njobs=2)
+
+
+def test_out_of_table_warnings_once_per_catalogue():
+    """BaryonCorrection.py:378-389 words the out-of-range warnings per halo; the GPU runners emit them once per process()
+    from the catalogue's extremes (SURVEY.md section 10 #13) -- same wording, and a broken model never breaks process()."""
+    import warnings
+    import baryonforge_b200 as b
+    from baryonforge_b200 import synth
+    from baryonforge_b200.runners import _table_range_messages, _warn_table_range
+    axes = synth.table_axes(z_min=0.01, z_max=1.0, M_min=1e12, M_max=10 ** 15.5)
+    model = b.DisplacementModel(axes, synth.displacement_values(axes), 20, synth.COSMO)
+    inside = _table_range_messages(model, np.array([0.1, 0.5]), np.array([1e13, 1e15]))
+    assert inside == []
+    msgs = _table_range_messages(model, np.array([0.1, 1.2]), np.array([3e11, 1e15]))
+    assert len(msgs) == 2
+    assert msgs[0].startswith("Requested redshift range [0.1, 1.2] outside table's range [")
+    assert msgs[1].startswith("Requested log_Mass range [") and "outside table's range [" in msgs[1]
+    assert _table_range_messages(model, 0.3, np.array([1e13], dtype='>f4')) == []          # box catalogues: scalar z, f32 M
+    assert _table_range_messages(model, np.zeros(0), np.zeros(0)) == []
+    assert _table_range_messages(object(), np.array([5.0]), np.array([1.0])) == []         # no table: nothing to say
+    assert _table_range_messages(model, np.array(['x']), np.array([1.0])) == []            # garbage in: swallowed
+    with pytest.warns(UserWarning, match="Requested redshift range"):
+        _warn_table_range(model, np.array([2.0]), np.array([1e13]))
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        _warn_table_range(model, np.array([0.2]), np.array([1e13]))                        # in range: silent
