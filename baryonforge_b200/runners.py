@@ -395,9 +395,9 @@ class DefaultRunner(object):
         (BaryonCorrection.py:399).  Cached on (cosmology, z_max, mass definitions).
         """
         mcos = None if paint else getattr(self.model, 'cosmo', None)
-        key = (paint, float(z_max), tuple(sorted(self.cosmo.items())), id(self.mass_def), id(mcos),
+        key = (paint, float(z_max), tuple(sorted(self.cosmo.items())), _Ident(self.mass_def), _Ident(mcos),
                tuple(sorted(mcos.items())) if isinstance(mcos, dict) else None,
-               None if paint else id(getattr(self.model, 'mass_def', None)))
+               None if paint else _Ident(getattr(self.model, 'mass_def', None)))
         if getattr(self, '_spl_cache', None) is not None and self._spl_cache[0] == key:
             return self._spl_cache[1]
         cosmo = cosmology.runner_cosmology(self.cosmo, with_w0=True)          # :280-284
