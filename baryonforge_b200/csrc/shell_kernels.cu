@@ -262,6 +262,56 @@ __device__ __forceinline__ void span_pixels_fast(const FastHalo &f, const RingSe
     }
 }
 
+#ifdef BFG_SHELL_UNROLL2
+// STAGED VARIANT (compile with -DBFG_SHELL_UNROLL2, tools/build_variant.sh; not measured in round 1):
+// the v8 loop is latency-limited, not throughput-limited (issue slots 65.8 % busy, FP64 pipe 52 %, 'wait' the largest stall at
+// 3.15 per issue with one dependent chain per warp and 7 warps per scheduler).  Here every lane carries TWO independent pixel
+// chains -- its pixels p and p + GW -- per iteration, each advanced by a double azimuth step, so the scheduler has twice the
+// instruction-level parallelism per warp.  Same per-pixel arithmetic; the double-step rotation constants differ from two single
+// steps by round-off only.
+template <bool CHECK>
+__device__ __forceinline__ void pixel_update_fast(const FastHalo &f, double z, double sth, double dz, double dz2, double cs,
+                                                  double sn, double *__restrict__ p0, i64 nloc8, const double *own_lo,
+                                                  const double *own_hi) {
+    const double x = sth * cs, y = sth * sn;
+    const double dx = x - f.vx, dy = y - f.vy;
+    const double r2 = fma(dx, dx, fma(dy, dy, dz2));
+    bool ok;
+    const double val = row_at_r2(f.t, r2, ok);
+    const double sc = (val * f.aD) * rsqrt_pos(r2);
+    ok = ok && (r2 < f.rcut2) && ((((unsigned)__double2hiint(sc) & 0x7fffffffu) - 1u) < 0x7fefffffu);
+    if (CHECK) ok = ok && (p0 >= own_lo) && (p0 < own_hi);
+    const double nx = fma(sc, dx, x), ny = fma(sc, dy, y), nz = fma(sc, dz, z);
+    const double ninv = rsqrt_pos(fma(nx, nx, fma(ny, ny, nz * nz)));
+    if (ok) {
+        red_add(p0, fma(nx, ninv, -x));
+        red_add((double *)((char *)p0 + nloc8), fma(ny, ninv, -y));
+        red_add((double *)((char *)p0 + 2 * nloc8), fma(nz, ninv, -z));
+    }
+}
+
+template <bool CHECK, int GW>
+__device__ __forceinline__ void span_pixels_fast2(const FastHalo &f, const RingSeg &g, double cs, double sn,
+                                                  double *__restrict__ p0, const double *__restrict__ pend, i64 nloc8,
+                                                  const double *own_lo = nullptr, const double *own_hi = nullptr) {
+    const double z = g.z, sth = g.sth, dz = g.dz, dz2 = g.dz2, rotC = g.rotC, rotS = g.rotS;
+    const double rot2C = fma(rotC, rotC, -rotS * rotS), rot2S = 2.0 * rotC * rotS;      // two azimuth steps at once
+    double cs1 = cs * rotC - sn * rotS, sn1 = fma(sn, rotC, cs * rotS);                  // the lane's second chain: p0 + GW
+    for (; p0 + GW < pend; p0 += 2 * GW) {
+        pixel_update_fast<CHECK>(f, z, sth, dz, dz2, cs, sn, p0, nloc8, own_lo, own_hi);
+        pixel_update_fast<CHECK>(f, z, sth, dz, dz2, cs1, sn1, p0 + GW, nloc8, own_lo, own_hi);
+        const double c2 = cs * rot2C - sn * rot2S, c3 = cs1 * rot2C - sn1 * rot2S;
+        sn = fma(sn, rot2C, cs * rot2S);
+        sn1 = fma(sn1, rot2C, cs1 * rot2S);
+        cs = c2; cs1 = c3;
+    }
+    if (p0 < pend) pixel_update_fast<CHECK>(f, z, sth, dz, dz2, cs, sn, p0, nloc8, own_lo, own_hi);
+}
+#define BFG_SPAN_FAST span_pixels_fast2
+#else
+#define BFG_SPAN_FAST span_pixels_fast
+#endif
+
 // PaintProfilesShell counterpart of span_pixels_fast (HealpixRunner.py:464-481): map[p] += exp(table(ln(r_sep / a))) * SCALE,
 // non-finite read-outs (outside the table, log of a zero or negative profile) contribute nothing.
 template <bool CHECK, int GW>
@@ -350,16 +400,16 @@ __device__ __forceinline__ i64 walk_rings_fast(const FastHalo &fh, const RingSeg
                 }
             }
         } else if (!sharded) {
-            span_pixels_fast<false, GW>(fh, g, cs, sn, rbp + g.ip_lo + li, rbp + endA, nloc8);
+            BFG_SPAN_FAST<false, GW>(fh, g, cs, sn, rbp + g.ip_lo + li, rbp + endA, nloc8);
             if (endB > 0) {
                 sincospi(((double)li + ((g.flags & 4) ? 0.5 : 0.0)) * g.inv2nr, &sn, &cs);
-                span_pixels_fast<false, GW>(fh, g, cs, sn, rbp + li, rbp + endB, nloc8);
+                BFG_SPAN_FAST<false, GW>(fh, g, cs, sn, rbp + li, rbp + endB, nloc8);
             }
         } else {                // ring-range sharding: pixels outside the owned range are masked per lane
-            span_pixels_fast<true, GW>(fh, g, cs, sn, rbp + g.ip_lo + li, rbp + endA, nloc8, out, out + nloc);
+            BFG_SPAN_FAST<true, GW>(fh, g, cs, sn, rbp + g.ip_lo + li, rbp + endA, nloc8, out, out + nloc);
             if (endB > 0) {
                 sincospi(((double)li + ((g.flags & 4) ? 0.5 : 0.0)) * g.inv2nr, &sn, &cs);
-                span_pixels_fast<true, GW>(fh, g, cs, sn, rbp + li, rbp + endB, nloc8, out, out + nloc);
+                BFG_SPAN_FAST<true, GW>(fh, g, cs, sn, rbp + li, rbp + endB, nloc8, out, out + nloc);
             }
         }
     }
