@@ -11,6 +11,6 @@ from .runners import *       # noqa: F401,F403
 from .tables import DeviceTable, DisplacementModel, ProfileModel   # noqa: F401
 from .parallel import SimpleParallel, SplitJoinParallel             # noqa: F401
 from .spectra import ShellPowerSpectrum                             # noqa: F401
-from . import _lib, cosmology, io, parallel, runners, spectra, synth, tables   # noqa: F401
+from . import _lib, cosmology, harmonics, io, parallel, runners, spectra, synth, tables   # noqa: F401
 
 __version__ = "0.1.0"

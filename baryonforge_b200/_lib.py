@@ -82,6 +82,11 @@ _SIGNATURES = {
     "bfg_snap_apply_deposit_folded": ([c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_dbl, c_dbl, c_i64, c_ptr, c_ptr, c_ptr], C.c_int),
     "bfg_power_bin_spectrum": ([c_i64, c_ptr, c_ptr, c_dbl, c_dbl, c_i64, c_ptr, c_ptr, c_ptr, c_ptr], C.c_int),
     "bfg_grid_power_spectrum": ([c_i64, c_ptr, c_ptr, c_dbl, c_dbl, c_i64, c_ptr, c_ptr, c_ptr, c_ptr], C.c_int),
+    "bfg_sht_workspace_elems": ([C.c_int, C.c_int], c_i64),
+    "bfg_sht_map2alm_pass": ([C.c_int, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr], C.c_int),
+    "bfg_sht_alm2map": ([C.c_int, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr], C.c_int),
+    "bfg_sht_alm2cl": ([C.c_int, c_ptr, c_ptr, c_ptr], C.c_int),
+    "bfg_test_sht_lambda_host": ([C.c_int, C.c_int, c_dbl, c_dbl, c_dbl, c_ptr], C.c_int),
     "bfg_halo_sort": ([C.c_int, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, c_dbl, c_dbl, C.c_int, c_ptr], C.c_int),
     "bfg_halo_sort_owned": ([C.c_int, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, c_dbl, c_ptr], C.c_int),
     "bfg_test_fast_log2": ([c_i64, c_ptr, c_ptr, c_ptr], C.c_int),

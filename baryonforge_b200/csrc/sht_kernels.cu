@@ -1,0 +1,330 @@
+// sht_kernels.cu -- spherical-harmonic transforms on the HEALPix RING grid for the C_l measurement that follows BaryonifyShell in
+// the reference's workflow: `hp.anafast(map)` (examples/04_Baryonify_Density_Shell.ipynb cell 18).
+//
+// STAGED: written after the GPU budget of round 1 was spent -- compiled, never run.  The algorithm is the one of
+// oracle/anafast_rings.py (checked on the CPU against the dense definition oracle/anafast_port.py); its tests are gated behind
+// BFG_TEST_EXPERIMENTAL=1.  First version: correctness before speed --
+//   k_sht_ring_analysis  : F_m(r) = sum_j f(r, j) exp(-i m phi_j) for every ring r and 0 <= m <= lmax, as a direct sum with exact
+//                          seeds for the twiddle recurrence (m phi_j / pi is a rational number with denominator 4 n_r / 4);
+//   k_sht_leg_analysis   : a_lm += w sum_r lambda_lm(cos theta_r) F_m(r), one warp per (m, 32 ring pairs), north/south rings
+//                          paired through lambda_lm(-x) = (-1)^(l+m) lambda_lm(x), a power-of-two exponent per lane keeps
+//                          sin^m(theta) from underflowing, warp-shuffle sum then one RED per (l, warp);
+//   k_sht_leg_synthesis  : b_m(r) = sum_l a_lm lambda_lm(cos theta_r), same recursion, accumulators in registers;
+//   k_sht_ring_synthesis : f(r, j) = b_0 + 2 Re sum_{m>0} b_m exp(i m phi_j);
+//   k_sht_alm2cl         : C_l = (|a_l0|^2 + 2 sum_{m>0} |a_lm|^2) / (2l + 1).
+// A ring transform costs n_r (lmax + 1) complex multiply-adds per ring (2.5e12 at NSIDE = 4096); replacing it by batched
+// cuFFT for the 2 NSIDE + 1 equatorial rings is the obvious next step once this version is parity-green.
+#include <algorithm>
+#include "bfg_common.cuh"
+
+using namespace bfg;
+
+namespace {
+
+constexpr int SHT_SCALE_BITS = 256;
+
+// ---- ring geometry -------------------------------------------------------------------------------------------------------
+struct RingGeo {
+    i64 start, n;      // first pixel, pixel count
+    int den;           // phi_j / pi = (2 j + odd) / den
+    int odd;
+    double z, sin2;    // cos(theta), sin^2(theta)
+};
+
+__device__ __forceinline__ RingGeo ring_geo(const Hpx &h, i64 ring) {
+    RingGeo g;
+    bool shifted;
+    ring_info(h, ring, g.start, g.n, shifted);
+    double sth;
+    ring_z_sth(h, ring, g.z, sth);
+    g.sin2 = sth * sth;
+    // caps: phi_j = (j + 1/2) pi / (2 i) = (2j + 1) pi / (4 i);  belt: phi_j = (j + s/2) pi / (2 nside) = (2j + s) pi / (4 nside)
+    g.den = (int)g.n;              // n = 4 i in the caps, 4 nside in the belt
+    g.odd = shifted ? 1 : 0;
+    return g;
+}
+
+// exp(+i m phi_j) with an exact argument reduction: m (2j + odd) / den is taken modulo 2 in integers
+__device__ __forceinline__ void twiddle(i64 m, i64 j, const RingGeo &g, double &c, double &s) {
+    const i64 num = (m * (2 * j + g.odd)) % (2 * (i64)g.den);
+    sincospi((double)num / (double)g.den, &s, &c);
+}
+
+constexpr int RING_THREADS = 256;
+constexpr int RESEED = 64;          // twiddle recurrence steps between exact seeds
+
+// F[m][ring-1] = sum_j f_j exp(-i m phi_j).  One CTA per ring; the ring sits in shared memory; thread t takes m = t, t + T, ...
+__global__ void __launch_bounds__(RING_THREADS)
+k_sht_ring_analysis(Hpx h, int lmax, const double *__restrict__ map, double2 *__restrict__ F, i64 ring_stride) {
+    extern __shared__ double s_ring[];
+    const i64 ring = (i64)blockIdx.x + 1;
+    const RingGeo g = ring_geo(h, ring);
+    for (i64 j = threadIdx.x; j < g.n; j += blockDim.x) s_ring[j] = map[g.start + j];
+    __syncthreads();
+    for (int m = threadIdx.x; m <= lmax; m += blockDim.x) {
+        // step of the recurrence: exp(-i m dphi), dphi = 2 pi / n  ->  -2 m / n in units of pi
+        double rc, rs;
+        {
+            const i64 num = (2 * (i64)m) % (2 * g.n);
+            sincospi(-(double)num / (double)g.n, &rs, &rc);
+        }
+        double accr = 0.0, acci = 0.0;
+        for (i64 j0 = 0; j0 < g.n; j0 += RESEED) {
+            double c, s;
+            twiddle(m, j0, g, c, s);
+            s = -s;                                              // exp(-i m phi_j0)
+            const i64 j1 = min(j0 + RESEED, g.n);
+            for (i64 j = j0; j < j1; ++j) {
+                const double f = s_ring[j];
+                accr = fma(f, c, accr);
+                acci = fma(f, s, acci);
+                const double c2 = c * rc - s * rs;
+                s = fma(s, rc, c * rs);
+                c = c2;
+            }
+        }
+        F[(i64)m * ring_stride + (ring - 1)] = make_double2(accr, acci);
+    }
+}
+
+// f_j = b_0 + 2 Re sum_{m>0} b_m exp(i m phi_j).  One CTA per ring; b_m staged through shared memory in chunks.
+constexpr int B_CHUNK = 1024;
+
+__global__ void __launch_bounds__(RING_THREADS)
+k_sht_ring_synthesis(Hpx h, int lmax, const double2 *__restrict__ B, i64 ring_stride, double *__restrict__ map) {
+    __shared__ double2 s_b[B_CHUNK];
+    const i64 ring = (i64)blockIdx.x + 1;
+    const RingGeo g = ring_geo(h, ring);
+    const i64 n_pass = (g.n + blockDim.x - 1) / blockDim.x;
+    for (i64 pass = 0; pass < n_pass; ++pass) {
+        const i64 j = pass * blockDim.x + threadIdx.x;
+        const bool live = j < g.n;
+        double acc = 0.0;
+        // exp(i phi_j): one azimuth step in m
+        double pc = 1.0, ps = 0.0;
+        if (live) twiddle(1, j, g, pc, ps);
+        for (int m0 = 0; m0 <= lmax; m0 += B_CHUNK) {
+            const int m1 = min(m0 + B_CHUNK, lmax + 1);
+            __syncthreads();
+            for (int m = m0 + threadIdx.x; m < m1; m += blockDim.x) s_b[m - m0] = B[(i64)m * ring_stride + (ring - 1)];
+            __syncthreads();
+            if (!live) continue;
+            for (int ms = m0; ms < m1; ms += RESEED) {
+                double c, s;
+                twiddle(ms, j, g, c, s);                         // exp(i ms phi_j), exact seed
+                const int me = min(ms + RESEED, m1);
+                for (int m = ms; m < me; ++m) {
+                    const double2 b = s_b[m - m0];
+                    const double w = (m == 0) ? 1.0 : 2.0;
+                    acc = fma(w, fma(b.x, c, -b.y * s), acc);    // Re(b exp(i m phi))
+                    const double c2 = c * pc - s * ps;
+                    s = fma(s, pc, c * ps);
+                    c = c2;
+                }
+            }
+        }
+        if (live) map[g.start + j] = acc;
+    }
+}
+
+// ---- Legendre recursion --------------------------------------------------------------------------------------------------
+// lambda_mm and the recursion coefficients follow oracle/anafast_rings.py.  State per lane: (prev, cur) mantissas sharing one
+// power-of-two exponent `expo` (a multiple of SHT_SCALE_BITS, <= 0); true value = mantissa * 2^expo.
+struct LegState {
+    double prev, cur, sf;    // sf = 2^expo (0 when that underflows: the contribution is negligible)
+    int expo;
+};
+
+__host__ __device__ __forceinline__ double pow2_or_zero(int e) { return (e < -1000) ? 0.0 : ldexp(1.0, e); }
+
+__host__ __device__ __forceinline__ LegState leg_start(int m, double ln_mm, double sin2) {
+    LegState st;
+    st.prev = 0.0;
+    if (m > 0 && !(sin2 > 0.0)) {            // exactly on a pole: lambda_lm = 0 for every m > 0
+        st.cur = 0.0; st.expo = 0; st.sf = 1.0;
+        return st;
+    }
+    const double ln = (m == 0) ? ln_mm : fma(0.5 * (double)m, log(sin2), ln_mm);
+    const double log2v = ln * 1.4426950408889634074;
+    double e = floor(log2v / (double)SHT_SCALE_BITS) * (double)SHT_SCALE_BITS;
+    if (e > 0.0) e = 0.0;
+    if (e < -1.0e9) e = -1.0e9;
+    st.expo = (int)e;
+    st.cur = exp2(log2v - e) * ((m & 1) ? -1.0 : 1.0);
+    st.sf = pow2_or_zero(st.expo);
+    return st;
+}
+
+// advance l - 1 -> l (l > m): a_l (x cur - c_{l-1} prev), rescale when the mantissa outgrows 2^SHT_SCALE_BITS
+__host__ __device__ __forceinline__ void leg_step(LegState &st, int l, int m, double x, double &c_prev) {
+    const double l2 = (double)l * (double)l, m2 = (double)m * (double)m;
+    const double a = sqrt((4.0 * l2 - 1.0) / (l2 - m2));
+    const double nxt = a * (x * st.cur - c_prev * st.prev);
+    st.prev = st.cur;
+    st.cur = nxt;
+    if (fabs(st.cur) > 1.157920892373162e77) {          // 2^256
+        st.cur *= 8.636168555094445e-78;                // 2^-256
+        st.prev *= 8.636168555094445e-78;
+        st.expo += SHT_SCALE_BITS;
+        st.sf = pow2_or_zero(st.expo);
+    }
+    c_prev = sqrt((l2 - m2) / (4.0 * l2 - 1.0));
+}
+
+// pair p of rings: north ring p + 1 with its mirror 4 nside - (p + 1); p = 2 nside - 1 is the equator alone
+__device__ __forceinline__ void pair_rings(const Hpx &h, i64 p, i64 &rn, i64 &rs) {
+    rn = p + 1;
+    rs = (rn == 2 * h.nside) ? -1 : 4 * h.nside - rn;
+}
+
+__global__ void __launch_bounds__(256)
+k_sht_leg_analysis(Hpx h, int lmax, const double *__restrict__ ln_mm, const double2 *__restrict__ F, i64 ring_stride,
+                   double weight, double *__restrict__ alm) {
+    const int lane = threadIdx.x & 31;
+    const i64 warp = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const i64 n_pairs = 2 * h.nside, chunks = (n_pairs + 31) / 32;
+    const i64 m64 = warp / chunks;
+    if (m64 > lmax) return;                                       // whole warp leaves together
+    const int m = (int)m64;
+    const i64 p = (warp - m64 * chunks) * 32 + lane;
+    const bool live = p < n_pairs;
+    double Pr = 0.0, Pi = 0.0, Qr = 0.0, Qi = 0.0, x = 0.0;
+    LegState st; st.prev = 0.0; st.cur = 0.0; st.sf = 0.0; st.expo = 0;
+    if (live) {
+        i64 rn, rs;
+        pair_rings(h, p, rn, rs);
+        double sth;
+        ring_z_sth(h, rn, x, sth);
+        const double2 fn = F[(i64)m * ring_stride + (rn - 1)];
+        const double2 fs = (rs > 0) ? F[(i64)m * ring_stride + (rs - 1)] : make_double2(0.0, 0.0);
+        Pr = fn.x + fs.x; Pi = fn.y + fs.y;                       // multiplies lambda when l + m is even
+        Qr = fn.x - fs.x; Qi = fn.y - fs.y;                       // ... odd
+        st = leg_start(m, ln_mm[m], sth * sth);
+    }
+    const i64 base = (i64)m * (2 * (i64)lmax + 1 - m) / 2;        // healpy packing: idx(l, m) = base + l
+    double c_prev = 0.0;
+    for (int l = m; l <= lmax; ++l) {
+        if (l > m) leg_step(st, l, m, x, c_prev);
+        const double lam = st.cur * st.sf * weight;
+        const bool even = ((l + m) & 1) == 0;
+        double vr = lam * (even ? Pr : Qr), vi = lam * (even ? Pi : Qi);
+        vr = warp_sum(vr);
+        vi = warp_sum(vi);
+        if (lane == 0 && (vr != 0.0 || vi != 0.0)) {
+            red_add(alm + 2 * (base + l), vr);
+            red_add(alm + 2 * (base + l) + 1, vi);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_sht_leg_synthesis(Hpx h, int lmax, const double *__restrict__ ln_mm, const double2 *__restrict__ alm, double2 *__restrict__ B,
+                    i64 ring_stride) {
+    const int lane = threadIdx.x & 31;
+    const i64 warp = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const i64 n_pairs = 2 * h.nside, chunks = (n_pairs + 31) / 32;
+    const i64 m64 = warp / chunks;
+    if (m64 > lmax) return;
+    const int m = (int)m64;
+    const i64 p = (warp - m64 * chunks) * 32 + lane;
+    if (p >= n_pairs) return;                                     // no warp-wide operation below
+    i64 rn, rs;
+    pair_rings(h, p, rn, rs);
+    double x, sth;
+    ring_z_sth(h, rn, x, sth);
+    LegState st = leg_start(m, ln_mm[m], sth * sth);
+    const i64 base = (i64)m * (2 * (i64)lmax + 1 - m) / 2;
+    double er = 0.0, ei = 0.0, orr = 0.0, oi = 0.0, c_prev = 0.0;
+    for (int l = m; l <= lmax; ++l) {
+        if (l > m) leg_step(st, l, m, x, c_prev);
+        const double lam = st.cur * st.sf;
+        const double2 a = __ldg(alm + base + l);
+        if (((l + m) & 1) == 0) { er = fma(a.x, lam, er); ei = fma(a.y, lam, ei); }
+        else { orr = fma(a.x, lam, orr); oi = fma(a.y, lam, oi); }
+    }
+    B[(i64)m * ring_stride + (rn - 1)] = make_double2(er + orr, ei + oi);
+    if (rs > 0) B[(i64)m * ring_stride + (rs - 1)] = make_double2(er - orr, ei - oi);   // lambda_lm(-x) = (-1)^(l+m) lambda_lm(x)
+}
+
+__global__ void k_sht_alm2cl(int lmax, const double2 *__restrict__ alm, double *__restrict__ cl) {
+    for (int l = blockIdx.x * blockDim.x + threadIdx.x; l <= lmax; l += gridDim.x * blockDim.x) {
+        double acc = 0.0;
+        for (int m = 0; m <= l; ++m) {
+            const double2 a = alm[(i64)m * (2 * (i64)lmax + 1 - m) / 2 + l];
+            acc += ((m == 0) ? 1.0 : 2.0) * fma(a.x, a.x, a.y * a.y);
+        }
+        cl[l] = acc / (double)(2 * l + 1);
+    }
+}
+
+int check_sht_args(int nside, int lmax) {
+    BFG_REQUIRE(nside >= 1 && nside <= 8192, "nside out of range");
+    BFG_REQUIRE(lmax >= 0 && lmax <= 4 * nside, "lmax out of range (0 <= lmax <= 4 nside)");
+    return BFG_OK;
+}
+
+}  // namespace
+
+extern "C" int64_t bfg_sht_workspace_elems(int nside, int lmax) {
+    // complex128 elements of the [lmax + 1][4 nside - 1] ring-coefficient array F_m(r) / b_m(r)
+    if (nside < 1 || lmax < 0) return 0;
+    return (int64_t)(lmax + 1) * (4 * (int64_t)nside - 1);
+}
+
+extern "C" int bfg_sht_map2alm_pass(int nside, int lmax, const double *d_map, const double *d_ln_mm, double *d_work,
+                                    double *d_alm, void *stream) {
+    if (int rc = check_sht_args(nside, lmax)) return rc;
+    BFG_REQUIRE(d_map && d_ln_mm && d_work && d_alm, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const Hpx h(nside);
+    const i64 n_rings = 4 * (i64)nside - 1;
+    const size_t smem = sizeof(double) * 4 * (size_t)nside;
+    BFG_REQUIRE(smem <= 200 * 1024, "ring too long for shared memory (nside <= 6400)");
+    BFG_CUDA_OK(cudaFuncSetAttribute(k_sht_ring_analysis, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_sht_ring_analysis<<<(unsigned)n_rings, RING_THREADS, smem, st>>>(h, lmax, d_map, (double2 *)d_work, n_rings);
+    BFG_CUDA_OK(cudaGetLastError());
+    const i64 chunks = (2 * (i64)nside + 31) / 32, warps = (i64)(lmax + 1) * chunks;
+    const i64 blocks = (warps + 7) / 8;
+    BFG_REQUIRE(blocks <= 0x7fffffff, "transform too large for one launch");
+    k_sht_leg_analysis<<<(unsigned)blocks, 256, 0, st>>>(h, lmax, d_ln_mm, (const double2 *)d_work, n_rings,
+                                                          4.0 * BFG_PI / (double)h.npix, d_alm);
+    BFG_CUDA_OK(cudaGetLastError());
+    return BFG_OK;
+}
+
+extern "C" int bfg_sht_alm2map(int nside, int lmax, const double *d_alm, const double *d_ln_mm, double *d_work, double *d_map,
+                               void *stream) {
+    if (int rc = check_sht_args(nside, lmax)) return rc;
+    BFG_REQUIRE(d_map && d_ln_mm && d_work && d_alm, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const Hpx h(nside);
+    const i64 n_rings = 4 * (i64)nside - 1;
+    const i64 chunks = (2 * (i64)nside + 31) / 32, warps = (i64)(lmax + 1) * chunks;
+    const i64 blocks = (warps + 7) / 8;
+    BFG_REQUIRE(blocks <= 0x7fffffff, "transform too large for one launch");
+    k_sht_leg_synthesis<<<(unsigned)blocks, 256, 0, st>>>(h, lmax, d_ln_mm, (const double2 *)d_alm, (double2 *)d_work, n_rings);
+    BFG_CUDA_OK(cudaGetLastError());
+    k_sht_ring_synthesis<<<(unsigned)n_rings, RING_THREADS, 0, st>>>(h, lmax, (const double2 *)d_work, n_rings, d_map);
+    BFG_CUDA_OK(cudaGetLastError());
+    return BFG_OK;
+}
+
+extern "C" int bfg_sht_alm2cl(int lmax, const double *d_alm, double *d_cl, void *stream) {
+    BFG_REQUIRE(lmax >= 0 && d_alm && d_cl, "bad argument");
+    k_sht_alm2cl<<<(lmax + 256) / 256, 256, 0, (cudaStream_t)stream>>>(lmax, (const double2 *)d_alm, d_cl);
+    BFG_CUDA_OK(cudaGetLastError());
+    return BFG_OK;
+}
+
+// Unit-test entry, HOST side: the scaled recursion exactly as the kernels run it (same source, compiled for the host), so that
+// its underflow handling can be checked without a GPU.  h_out[l - m] = lambda_lm(x) for l = m .. lmax.
+extern "C" int bfg_test_sht_lambda_host(int m, int lmax, double ln_mm, double x, double sin2, double *h_out) {
+    BFG_REQUIRE(m >= 0 && lmax >= m && h_out, "bad argument");
+    LegState st = leg_start(m, ln_mm, sin2);
+    double c_prev = 0.0;
+    for (int l = m; l <= lmax; ++l) {
+        if (l > m) leg_step(st, l, m, x, c_prev);
+        h_out[l - m] = st.cur * st.sf;
+    }
+    return BFG_OK;
+}

@@ -300,6 +300,25 @@ int bfg_power_bin_spectrum(int64_t N, const double *d_spec, const double *d_klin
 int bfg_grid_power_spectrum(int64_t N, const double *d_grid, const double *d_klin, double k0, double dk, int64_t Nk,
                             double *d_pk_sum, double *d_k_sum, int64_t *d_count, void *stream);
 
+/* ---- C_l of a shell: the measurement that follows BaryonifyShell.process() in the reference's workflow ------------------
+ * `hp.anafast(map)` (examples/04_Baryonify_Density_Shell.ipynb cell 18) = healpix_cxx map2alm_iter (lmax = 3 nside - 1, three
+ * Jacobi iterations, unit ring weights) + alm2cl.  STAGED: compiled, not yet run on a GPU; the algorithm
+ * is oracle/anafast_rings.py.  a_lm are complex128 in healpy's packing idx(l, m) = m (2 lmax + 1 - m) / 2 + l, m >= 0.
+ *   d_ln_mm [lmax + 1]  ln of sqrt((2m+1)/(4 pi) prod_{k<=m} (2k-1)/(2k)), from the host
+ *   d_work              complex128 [lmax + 1][4 nside - 1] ring coefficients, bfg_sht_workspace_elems() elements */
+int64_t bfg_sht_workspace_elems(int nside, int lmax);
+/* One quadrature pass ADDED to d_alm: a_lm += 4 pi / npix * sum_r lambda_lm(cos theta_r) F_m(r)  (map2alm, add = true). */
+int bfg_sht_map2alm_pass(int nside, int lmax, const double *d_map, const double *d_ln_mm, double *d_work, double *d_alm,
+                         void *stream);
+/* d_map = sum_l a_l0 Y_l0 + 2 Re sum_{m>0} a_lm Y_lm  (alm2map; overwrites d_map). */
+int bfg_sht_alm2map(int nside, int lmax, const double *d_alm, const double *d_ln_mm, double *d_work, double *d_map,
+                    void *stream);
+/* d_cl[l] = (|a_l0|^2 + 2 sum_{m=1..l} |a_lm|^2) / (2 l + 1), l = 0 .. lmax  (hp.alm2cl). */
+int bfg_sht_alm2cl(int lmax, const double *d_alm, double *d_cl, void *stream);
+/* Unit-test entry on the HOST (no GPU needed): the scaled Legendre recursion exactly as the kernels run it;
+ * h_out[l - m] = lambda_lm(x), l = m .. lmax, for sin^2(theta) = sin2. */
+int bfg_test_sht_lambda_host(int m, int lmax, double ln_mm, double x, double sin2, double *h_out);
+
 /* ---- locality ordering ----------------------------------------------------------------------------- */
 /* Re-orders halo records (and their extras rows) so that neighbours on the sky / in the box are adjacent: north_star (b)
  * "halo batches sorted by sky or box cell for locality".  The reference walks the catalogue in the given order
