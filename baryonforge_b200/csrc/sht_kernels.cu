@@ -24,106 +24,117 @@ namespace {
 constexpr int SHT_SCALE_BITS = 256;
 
 // ---- ring geometry -------------------------------------------------------------------------------------------------------
-struct RingGeo {
-    i64 start, n;      // first pixel, pixel count
-    int den;           // phi_j / pi = (2 j + odd) / den
-    int odd;
-    double z, sin2;    // cos(theta), sin^2(theta)
+// The per-ring sums are written as __host__ __device__ functions so that the phase conventions can be checked on the CPU
+// (bfg_test_sht_ring_host) against the oracle; the kernels only distribute them over threads.
+struct RingPhase {
+    i64 n;             // pixels in the ring; phi_j / pi = (2 j + odd) / n
+    int odd;           // caps: phi_j = (2j + 1) pi / (4 i), n = 4 i;  belt: phi_j = (2j + s) pi / (4 nside), n = 4 nside
 };
 
-__device__ __forceinline__ RingGeo ring_geo(const Hpx &h, i64 ring) {
-    RingGeo g;
-    bool shifted;
-    ring_info(h, ring, g.start, g.n, shifted);
-    double sth;
-    ring_z_sth(h, ring, g.z, sth);
-    g.sin2 = sth * sth;
-    // caps: phi_j = (j + 1/2) pi / (2 i) = (2j + 1) pi / (4 i);  belt: phi_j = (j + s/2) pi / (2 nside) = (2j + s) pi / (4 nside)
-    g.den = (int)g.n;              // n = 4 i in the caps, 4 nside in the belt
-    g.odd = shifted ? 1 : 0;
-    return g;
+__host__ __device__ __forceinline__ void sincospi_hd(double x, double *s, double *c) {
+#ifdef __CUDA_ARCH__
+    sincospi(x, s, c);
+#else
+    *s = sin(BFG_PI * x);
+    *c = cos(BFG_PI * x);
+#endif
 }
 
-// exp(+i m phi_j) with an exact argument reduction: m (2j + odd) / den is taken modulo 2 in integers
-__device__ __forceinline__ void twiddle(i64 m, i64 j, const RingGeo &g, double &c, double &s) {
-    const i64 num = (m * (2 * j + g.odd)) % (2 * (i64)g.den);
-    sincospi((double)num / (double)g.den, &s, &c);
+// exp(+i m phi_j) with an exact argument reduction: m (2j + odd) / n is taken modulo 2 in integers
+__host__ __device__ __forceinline__ void twiddle(i64 m, i64 j, const RingPhase &g, double &c, double &s) {
+    const i64 num = (m * (2 * j + g.odd)) % (2 * g.n);
+    sincospi_hd((double)num / (double)g.n, &s, &c);
 }
 
 constexpr int RING_THREADS = 256;
 constexpr int RESEED = 64;          // twiddle recurrence steps between exact seeds
+constexpr int B_CHUNK = 1024;       // b_m staged through shared memory in chunks of this many m
+
+// F_m = sum_j f_j exp(-i m phi_j) of one ring
+__host__ __device__ __forceinline__ double2 ring_dft_m(int m, const RingPhase &g, const double *ring) {
+    double rc, rs;                                               // one step in j: exp(-i m 2 pi / n)
+    {
+        const i64 num = (2 * (i64)m) % (2 * g.n);
+        sincospi_hd(-(double)num / (double)g.n, &rs, &rc);
+    }
+    double accr = 0.0, acci = 0.0;
+    for (i64 j0 = 0; j0 < g.n; j0 += RESEED) {
+        double c, s;
+        twiddle(m, j0, g, c, s);
+        s = -s;                                                  // exp(-i m phi_j0)
+        const i64 j1 = (j0 + RESEED < g.n) ? j0 + RESEED : g.n;
+        for (i64 j = j0; j < j1; ++j) {
+            const double f = ring[j];
+            accr = fma(f, c, accr);
+            acci = fma(f, s, acci);
+            const double c2 = c * rc - s * rs;
+            s = fma(s, rc, c * rs);
+            c = c2;
+        }
+    }
+    double2 out; out.x = accr; out.y = acci;
+    return out;
+}
+
+// acc += sum_{m0 <= m < m1} c_m Re(b_m exp(i m phi_j)), c_0 = 1, c_{m>0} = 2; b is indexed by m - m0; (pc, ps) = exp(i phi_j)
+__host__ __device__ __forceinline__ void ring_synth_chunk(i64 j, const RingPhase &g, int m0, int m1, const double2 *b, double pc,
+                                                          double ps, double &acc) {
+    for (int ms = m0; ms < m1; ms += RESEED) {
+        double c, s;
+        twiddle(ms, j, g, c, s);                                 // exp(i ms phi_j), exact seed
+        const int me = (ms + RESEED < m1) ? ms + RESEED : m1;
+        for (int m = ms; m < me; ++m) {
+            const double2 bm = b[m - m0];
+            const double w = (m == 0) ? 1.0 : 2.0;
+            acc = fma(w, fma(bm.x, c, -bm.y * s), acc);
+            const double c2 = c * pc - s * ps;
+            s = fma(s, pc, c * ps);
+            c = c2;
+        }
+    }
+}
+
+__device__ __forceinline__ RingPhase ring_phase(const Hpx &h, i64 ring, i64 &start) {
+    RingPhase g;
+    bool shifted;
+    ring_info(h, ring, start, g.n, shifted);
+    g.odd = shifted ? 1 : 0;
+    return g;
+}
 
 // F[m][ring-1] = sum_j f_j exp(-i m phi_j).  One CTA per ring; the ring sits in shared memory; thread t takes m = t, t + T, ...
 __global__ void __launch_bounds__(RING_THREADS)
 k_sht_ring_analysis(Hpx h, int lmax, const double *__restrict__ map, double2 *__restrict__ F, i64 ring_stride) {
     extern __shared__ double s_ring[];
     const i64 ring = (i64)blockIdx.x + 1;
-    const RingGeo g = ring_geo(h, ring);
-    for (i64 j = threadIdx.x; j < g.n; j += blockDim.x) s_ring[j] = map[g.start + j];
+    i64 start;
+    const RingPhase g = ring_phase(h, ring, start);
+    for (i64 j = threadIdx.x; j < g.n; j += blockDim.x) s_ring[j] = map[start + j];
     __syncthreads();
-    for (int m = threadIdx.x; m <= lmax; m += blockDim.x) {
-        // step of the recurrence: exp(-i m dphi), dphi = 2 pi / n  ->  -2 m / n in units of pi
-        double rc, rs;
-        {
-            const i64 num = (2 * (i64)m) % (2 * g.n);
-            sincospi(-(double)num / (double)g.n, &rs, &rc);
-        }
-        double accr = 0.0, acci = 0.0;
-        for (i64 j0 = 0; j0 < g.n; j0 += RESEED) {
-            double c, s;
-            twiddle(m, j0, g, c, s);
-            s = -s;                                              // exp(-i m phi_j0)
-            const i64 j1 = min(j0 + RESEED, g.n);
-            for (i64 j = j0; j < j1; ++j) {
-                const double f = s_ring[j];
-                accr = fma(f, c, accr);
-                acci = fma(f, s, acci);
-                const double c2 = c * rc - s * rs;
-                s = fma(s, rc, c * rs);
-                c = c2;
-            }
-        }
-        F[(i64)m * ring_stride + (ring - 1)] = make_double2(accr, acci);
-    }
+    for (int m = threadIdx.x; m <= lmax; m += blockDim.x) F[(i64)m * ring_stride + (ring - 1)] = ring_dft_m(m, g, s_ring);
 }
 
-// f_j = b_0 + 2 Re sum_{m>0} b_m exp(i m phi_j).  One CTA per ring; b_m staged through shared memory in chunks.
-constexpr int B_CHUNK = 1024;
-
+// f_j = b_0 + 2 Re sum_{m>0} b_m exp(i m phi_j).  One CTA per ring; thread t takes pixels j = t, t + T, ...
 __global__ void __launch_bounds__(RING_THREADS)
 k_sht_ring_synthesis(Hpx h, int lmax, const double2 *__restrict__ B, i64 ring_stride, double *__restrict__ map) {
     __shared__ double2 s_b[B_CHUNK];
     const i64 ring = (i64)blockIdx.x + 1;
-    const RingGeo g = ring_geo(h, ring);
+    i64 start;
+    const RingPhase g = ring_phase(h, ring, start);
     const i64 n_pass = (g.n + blockDim.x - 1) / blockDim.x;
     for (i64 pass = 0; pass < n_pass; ++pass) {
         const i64 j = pass * blockDim.x + threadIdx.x;
         const bool live = j < g.n;
-        double acc = 0.0;
-        // exp(i phi_j): one azimuth step in m
-        double pc = 1.0, ps = 0.0;
-        if (live) twiddle(1, j, g, pc, ps);
+        double acc = 0.0, pc = 1.0, ps = 0.0;
+        if (live) twiddle(1, j, g, pc, ps);                      // exp(i phi_j): one step in m
         for (int m0 = 0; m0 <= lmax; m0 += B_CHUNK) {
             const int m1 = min(m0 + B_CHUNK, lmax + 1);
             __syncthreads();
             for (int m = m0 + threadIdx.x; m < m1; m += blockDim.x) s_b[m - m0] = B[(i64)m * ring_stride + (ring - 1)];
             __syncthreads();
-            if (!live) continue;
-            for (int ms = m0; ms < m1; ms += RESEED) {
-                double c, s;
-                twiddle(ms, j, g, c, s);                         // exp(i ms phi_j), exact seed
-                const int me = min(ms + RESEED, m1);
-                for (int m = ms; m < me; ++m) {
-                    const double2 b = s_b[m - m0];
-                    const double w = (m == 0) ? 1.0 : 2.0;
-                    acc = fma(w, fma(b.x, c, -b.y * s), acc);    // Re(b exp(i m phi))
-                    const double c2 = c * pc - s * ps;
-                    s = fma(s, pc, c * ps);
-                    c = c2;
-                }
-            }
+            if (live) ring_synth_chunk(j, g, m0, m1, s_b, pc, ps, acc);
         }
-        if (live) map[g.start + j] = acc;
+        if (live) map[start + j] = acc;
     }
 }
 
@@ -325,6 +336,31 @@ extern "C" int bfg_test_sht_lambda_host(int m, int lmax, double ln_mm, double x,
     for (int l = m; l <= lmax; ++l) {
         if (l > m) leg_step(st, l, m, x, c_prev);
         h_out[l - m] = st.cur * st.sf;
+    }
+    return BFG_OK;
+}
+
+// Unit-test entry, HOST side: the per-ring sums exactly as the kernels run them (same functions, compiled for the host), to
+// pin the phase conventions without a GPU.  One ring of n pixels with phi_j = (2 j + odd) pi / n:
+//   h_F   [lmax + 1][2]  <- sum_j h_ring[j] exp(-i m phi_j)                       (k_sht_ring_analysis)
+//   h_out [n]            <- sum_m c_m Re(h_b[m] exp(i m phi_j)), c_0 = 1, c_m = 2  (k_sht_ring_synthesis, chunked the same way)
+extern "C" int bfg_test_sht_ring_host(int64_t n, int odd, int lmax, const double *h_ring, double *h_F, const double *h_b,
+                                      double *h_out) {
+    BFG_REQUIRE(n >= 1 && lmax >= 0 && (odd == 0 || odd == 1) && h_ring && h_F && h_b && h_out, "bad argument");
+    RingPhase g; g.n = n; g.odd = odd;
+    for (int m = 0; m <= lmax; ++m) {
+        const double2 f = ring_dft_m(m, g, h_ring);
+        h_F[2 * m] = f.x; h_F[2 * m + 1] = f.y;
+    }
+    const double2 *b = (const double2 *)h_b;
+    for (i64 j = 0; j < n; ++j) {
+        double acc = 0.0, pc, ps;
+        twiddle(1, j, g, pc, ps);
+        for (int m0 = 0; m0 <= lmax; m0 += B_CHUNK) {
+            const int m1 = (m0 + B_CHUNK < lmax + 1) ? m0 + B_CHUNK : lmax + 1;
+            ring_synth_chunk(j, g, m0, m1, b + m0, pc, ps, acc);
+        }
+        h_out[j] = acc;
     }
     return BFG_OK;
 }

@@ -318,6 +318,10 @@ int bfg_sht_alm2cl(int lmax, const double *d_alm, double *d_cl, void *stream);
 /* Unit-test entry on the HOST (no GPU needed): the scaled Legendre recursion exactly as the kernels run it;
  * h_out[l - m] = lambda_lm(x), l = m .. lmax, for sin^2(theta) = sin2. */
 int bfg_test_sht_lambda_host(int m, int lmax, double ln_mm, double x, double sin2, double *h_out);
+/* Unit-test entry on the HOST: the per-ring sums of the two ring kernels (same functions, compiled for the host) for one ring
+ * of n pixels at phi_j = (2 j + odd) pi / n:  h_F [lmax + 1][2] = sum_j h_ring[j] exp(-i m phi_j);
+ * h_out [n] = sum_m c_m Re(h_b[m] exp(i m phi_j)) with c_0 = 1, c_{m>0} = 2 and h_b [lmax + 1][2]. */
+int bfg_test_sht_ring_host(int64_t n, int odd, int lmax, const double *h_ring, double *h_F, const double *h_b, double *h_out);
 
 /* ---- locality ordering ----------------------------------------------------------------------------- */
 /* Re-orders halo records (and their extras rows) so that neighbours on the sky / in the box are adjacent: north_star (b)

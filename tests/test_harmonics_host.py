@@ -41,3 +41,36 @@ def test_shell_harmonics_front_end_without_a_gpu():
         sh.anafast(np.zeros(768))
     with pytest.raises(ValueError):
         b.harmonics.anafast(np.zeros(100))
+
+
+@pytest.mark.parametrize("nside,ring", [(4, 1), (4, 3), (4, 4), (4, 5), (4, 8), (4, 13), (4, 15), (64, 1), (64, 40), (64, 64),
+                                        (64, 127), (64, 128), (64, 200), (512, 300), (512, 1024)])
+def test_device_ring_sums_compiled_for_the_host_follow_the_oracle_phase_conventions(nside, ring):
+    """k_sht_ring_analysis / k_sht_ring_synthesis bodies on the host: cap rings (half-pixel phase), belt rings of both parities,
+    the equator, south-cap rings, rings longer than the recurrence's re-seed interval and than one shared-memory chunk."""
+    from baryonforge_b200 import _lib
+    from oracle import hpo
+    from oracle.anafast_rings import RingSHT
+    L = _lib.lib()
+    r = RingSHT(nside)
+    i = ring - 1
+    n, start, lmax = int(r.n_ring[i]), int(r.start[i]), r.lmax
+    theta, phi = hpo.pix2ang(nside, start + np.arange(n))
+    odd = int(round(phi[0] / np.pi * n))                          # phi_0 / pi = odd / n
+    assert odd in (0, 1) and np.allclose(phi, (2 * np.arange(n) + odd) * np.pi / n, rtol=0, atol=1e-12)
+    rng = np.random.default_rng(ring)
+    f = rng.normal(size=n)
+    b = rng.normal(size=(lmax + 1, 2))
+    b[0, 1] = 0.0
+    F = np.zeros((lmax + 1, 2))
+    out = np.zeros(n)
+    assert L.bfg_test_sht_ring_host(n, odd, lmax, f.ctypes.data, F.ctypes.data, b.ctypes.data, out.ctypes.data) == 0
+    m = np.arange(lmax + 1)
+    # analysis: the oracle's F_m(r) = exp(-i m phi_0) FFT[m mod n]
+    want_F = np.fft.fft(f)[m % n] * np.exp(-1j * m * phi[0])
+    got_F = F[:, 0] + 1j * F[:, 1]
+    assert np.max(np.abs(got_F - want_F)) < 1e-11 * np.sqrt(n)
+    # synthesis: f_j = sum_m c_m Re(b_m exp(i m phi_j))
+    bm = (b[:, 0] + 1j * b[:, 1]) * np.where(m == 0, 1.0, 2.0)
+    want = (np.exp(1j * np.outer(phi, m)) @ bm).real
+    assert np.max(np.abs(out - want)) < 1e-11 * np.sqrt(lmax + 1.0) * 4
