@@ -87,6 +87,7 @@ _SIGNATURES = {
     "bfg_sht_alm2map": ([C.c_int, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr], C.c_int),
     "bfg_sht_alm2cl": ([C.c_int, c_ptr, c_ptr, c_ptr], C.c_int),
     "bfg_test_sht_ring_host": ([c_i64, C.c_int, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr], C.c_int),
+    "bfg_test_sht_legendre_host": ([C.c_int, C.c_int, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr], C.c_int),
     "bfg_test_sht_lambda_host": ([C.c_int, C.c_int, c_dbl, c_dbl, c_dbl, c_ptr], C.c_int),
     "bfg_halo_sort": ([C.c_int, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, c_dbl, c_dbl, C.c_int, c_ptr], C.c_int),
     "bfg_halo_sort_owned": ([C.c_int, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, c_dbl, c_ptr], C.c_int),

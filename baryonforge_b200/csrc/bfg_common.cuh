@@ -230,7 +230,7 @@ __device__ __forceinline__ void ring_info(const Hpx &h, i64 ring, i64 &start, i6
 }
 
 // colatitude-related quantities of a ring: z and sin(theta) with the polar-cap accurate form
-__device__ __forceinline__ void ring_z_sth(const Hpx &h, i64 ring, double &z, double &sth) {
+__host__ __device__ __forceinline__ void ring_z_sth(const Hpx &h, i64 ring, double &z, double &sth) {
     if (ring < h.nside) {
         double tmp = (double)(ring * ring) * h.fact2;
         z = 1.0 - tmp;

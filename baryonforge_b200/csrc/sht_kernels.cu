@@ -182,10 +182,62 @@ __host__ __device__ __forceinline__ void leg_step(LegState &st, int l, int m, do
     c_prev = sqrt((l2 - m2) / (4.0 * l2 - 1.0));
 }
 
-// pair p of rings: north ring p + 1 with its mirror 4 nside - (p + 1); p = 2 nside - 1 is the equator alone
-__device__ __forceinline__ void pair_rings(const Hpx &h, i64 p, i64 &rn, i64 &rs) {
+// pair p of rings: north ring p + 1 with its mirror 4 nside - (p + 1); p = 2 nside - 1 is the equator alone (rs = -1)
+__host__ __device__ __forceinline__ void pair_rings(const Hpx &h, i64 p, i64 &rn, i64 &rs) {
     rn = p + 1;
     rs = (rn == 2 * h.nside) ? -1 : 4 * h.nside - rn;
+}
+
+// What one lane of the Legendre kernels holds for its ring pair.  Written as __host__ __device__ so that pairing, parity and
+// packing can be checked on the CPU (bfg_test_sht_legendre_host); the kernels add the thread mapping and the warp sum.
+struct PairLane {
+    double x;                  // cos(theta) of the northern ring
+    double Pr, Pi, Qr, Qi;     // F_north +- F_south: multiply lambda_lm when l + m is even / odd
+    LegState st;
+    i64 rn, rs;
+};
+
+__host__ __device__ __forceinline__ PairLane pair_lane(const Hpx &h, i64 p, int m, double ln_mm_m, const double2 *F_m /* [ring-1] */) {
+    PairLane q;
+    pair_rings(h, p, q.rn, q.rs);
+    double sth;
+    ring_z_sth(h, q.rn, q.x, sth);
+    q.Pr = q.Pi = q.Qr = q.Qi = 0.0;
+    if (F_m) {
+        const double2 fn = F_m[q.rn - 1];
+        double2 fs; fs.x = 0.0; fs.y = 0.0;
+        if (q.rs > 0) fs = F_m[q.rs - 1];
+        q.Pr = fn.x + fs.x; q.Pi = fn.y + fs.y;
+        q.Qr = fn.x - fs.x; q.Qi = fn.y - fs.y;
+    }
+    q.st = leg_start(m, ln_mm_m, sth * sth);
+    return q;
+}
+
+// healpy packing of the m >= 0 coefficients: idx(l, m) = alm_base(m) + l
+__host__ __device__ __forceinline__ i64 alm_base(int lmax, int m) { return (i64)m * (2 * (i64)lmax + 1 - m) / 2; }
+
+// this pair's contribution to a_lm (before the sum over pairs): weight * lambda_lm(x) * (P or Q)
+__host__ __device__ __forceinline__ void pair_contribution(const PairLane &q, int l, int m, double weight, double &vr, double &vi) {
+    const double lam = q.st.cur * q.st.sf * weight;
+    const bool even = ((l + m) & 1) == 0;
+    vr = lam * (even ? q.Pr : q.Qr);
+    vi = lam * (even ? q.Pi : q.Qi);
+}
+
+// b_m of the pair's two rings from a_lm (l = m .. lmax): lambda_lm(-x) = (-1)^(l+m) lambda_lm(x)
+__host__ __device__ __forceinline__ void pair_synthesis(PairLane &q, int m, int lmax, const double2 *alm_m /* indexed by l */,
+                                                        double2 &bn, double2 &bs) {
+    double er = 0.0, ei = 0.0, orr = 0.0, oi = 0.0, c_prev = 0.0;
+    for (int l = m; l <= lmax; ++l) {
+        if (l > m) leg_step(q.st, l, m, q.x, c_prev);
+        const double lam = q.st.cur * q.st.sf;
+        const double2 a = alm_m[l];
+        if (((l + m) & 1) == 0) { er = fma(a.x, lam, er); ei = fma(a.y, lam, ei); }
+        else { orr = fma(a.x, lam, orr); oi = fma(a.y, lam, oi); }
+    }
+    bn.x = er + orr; bn.y = ei + oi;
+    bs.x = er - orr; bs.y = ei - oi;
 }
 
 __global__ void __launch_bounds__(256)
@@ -198,27 +250,20 @@ k_sht_leg_analysis(Hpx h, int lmax, const double *__restrict__ ln_mm, const doub
     if (m64 > lmax) return;                                       // whole warp leaves together
     const int m = (int)m64;
     const i64 p = (warp - m64 * chunks) * 32 + lane;
-    const bool live = p < n_pairs;
-    double Pr = 0.0, Pi = 0.0, Qr = 0.0, Qi = 0.0, x = 0.0;
-    LegState st; st.prev = 0.0; st.cur = 0.0; st.sf = 0.0; st.expo = 0;
-    if (live) {
-        i64 rn, rs;
-        pair_rings(h, p, rn, rs);
-        double sth;
-        ring_z_sth(h, rn, x, sth);
-        const double2 fn = F[(i64)m * ring_stride + (rn - 1)];
-        const double2 fs = (rs > 0) ? F[(i64)m * ring_stride + (rs - 1)] : make_double2(0.0, 0.0);
-        Pr = fn.x + fs.x; Pi = fn.y + fs.y;                       // multiplies lambda when l + m is even
-        Qr = fn.x - fs.x; Qi = fn.y - fs.y;                       // ... odd
-        st = leg_start(m, ln_mm[m], sth * sth);
+    PairLane q;
+    if (p < n_pairs) {
+        q = pair_lane(h, p, m, ln_mm[m], F + (i64)m * ring_stride);
+    } else {                                                      // idle lane: contributes zeros to the warp sums
+        q.x = 0.0; q.Pr = q.Pi = q.Qr = q.Qi = 0.0;
+        q.st.prev = 0.0; q.st.cur = 0.0; q.st.sf = 0.0; q.st.expo = 0;
+        q.rn = 1; q.rs = -1;
     }
-    const i64 base = (i64)m * (2 * (i64)lmax + 1 - m) / 2;        // healpy packing: idx(l, m) = base + l
+    const i64 base = alm_base(lmax, m);
     double c_prev = 0.0;
     for (int l = m; l <= lmax; ++l) {
-        if (l > m) leg_step(st, l, m, x, c_prev);
-        const double lam = st.cur * st.sf * weight;
-        const bool even = ((l + m) & 1) == 0;
-        double vr = lam * (even ? Pr : Qr), vi = lam * (even ? Pi : Qi);
+        if (l > m) leg_step(q.st, l, m, q.x, c_prev);
+        double vr, vi;
+        pair_contribution(q, l, m, weight, vr, vi);
         vr = warp_sum(vr);
         vi = warp_sum(vi);
         if (lane == 0 && (vr != 0.0 || vi != 0.0)) {
@@ -231,30 +276,18 @@ k_sht_leg_analysis(Hpx h, int lmax, const double *__restrict__ ln_mm, const doub
 __global__ void __launch_bounds__(256)
 k_sht_leg_synthesis(Hpx h, int lmax, const double *__restrict__ ln_mm, const double2 *__restrict__ alm, double2 *__restrict__ B,
                     i64 ring_stride) {
-    const int lane = threadIdx.x & 31;
     const i64 warp = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const i64 n_pairs = 2 * h.nside, chunks = (n_pairs + 31) / 32;
     const i64 m64 = warp / chunks;
     if (m64 > lmax) return;
     const int m = (int)m64;
-    const i64 p = (warp - m64 * chunks) * 32 + lane;
+    const i64 p = (warp - m64 * chunks) * 32 + (threadIdx.x & 31);
     if (p >= n_pairs) return;                                     // no warp-wide operation below
-    i64 rn, rs;
-    pair_rings(h, p, rn, rs);
-    double x, sth;
-    ring_z_sth(h, rn, x, sth);
-    LegState st = leg_start(m, ln_mm[m], sth * sth);
-    const i64 base = (i64)m * (2 * (i64)lmax + 1 - m) / 2;
-    double er = 0.0, ei = 0.0, orr = 0.0, oi = 0.0, c_prev = 0.0;
-    for (int l = m; l <= lmax; ++l) {
-        if (l > m) leg_step(st, l, m, x, c_prev);
-        const double lam = st.cur * st.sf;
-        const double2 a = __ldg(alm + base + l);
-        if (((l + m) & 1) == 0) { er = fma(a.x, lam, er); ei = fma(a.y, lam, ei); }
-        else { orr = fma(a.x, lam, orr); oi = fma(a.y, lam, oi); }
-    }
-    B[(i64)m * ring_stride + (rn - 1)] = make_double2(er + orr, ei + oi);
-    if (rs > 0) B[(i64)m * ring_stride + (rs - 1)] = make_double2(er - orr, ei - oi);   // lambda_lm(-x) = (-1)^(l+m) lambda_lm(x)
+    PairLane q = pair_lane(h, p, m, ln_mm[m], nullptr);
+    double2 bn, bs;
+    pair_synthesis(q, m, lmax, alm + alm_base(lmax, m), bn, bs);
+    B[(i64)m * ring_stride + (q.rn - 1)] = bn;
+    if (q.rs > 0) B[(i64)m * ring_stride + (q.rs - 1)] = bs;
 }
 
 __global__ void k_sht_alm2cl(int lmax, const double2 *__restrict__ alm, double *__restrict__ cl) {
@@ -361,6 +394,35 @@ extern "C" int bfg_test_sht_ring_host(int64_t n, int odd, int lmax, const double
             ring_synth_chunk(j, g, m0, m1, b + m0, pc, ps, acc);
         }
         h_out[j] = acc;
+    }
+    return BFG_OK;
+}
+
+// Unit-test entry, HOST side: the Legendre stage of one m over ALL ring pairs with the lane functions of the two kernels --
+// pairing of north/south rings, parity, healpy packing -- so that only the thread mapping and the warp sum remain for the GPU.
+//   h_F_m   [4 nside - 1][2]  F_m(r) of every ring            ->  h_alm_m [lmax + 1][2] (entries l >= m) = w sum_pairs ...
+//   h_alm_in [lmax + 1][2]    a_lm for this m, indexed by l   ->  h_B_m [4 nside - 1][2] = b_m(r)
+extern "C" int bfg_test_sht_legendre_host(int nside, int lmax, int m, const double *h_ln_mm, const double *h_F_m, double *h_alm_m,
+                                          const double *h_alm_in, double *h_B_m) {
+    if (int rc = check_sht_args(nside, lmax)) return rc;
+    BFG_REQUIRE(m >= 0 && m <= lmax && h_ln_mm && h_F_m && h_alm_m && h_alm_in && h_B_m, "bad argument");
+    const Hpx h(nside);
+    const double weight = 4.0 * BFG_PI / (double)h.npix;
+    for (int l = 0; l <= lmax; ++l) { h_alm_m[2 * l] = 0.0; h_alm_m[2 * l + 1] = 0.0; }
+    for (i64 p = 0; p < 2 * (i64)nside; ++p) {
+        PairLane q = pair_lane(h, p, m, h_ln_mm[m], (const double2 *)h_F_m);
+        double c_prev = 0.0;
+        for (int l = m; l <= lmax; ++l) {
+            if (l > m) leg_step(q.st, l, m, q.x, c_prev);
+            double vr, vi;
+            pair_contribution(q, l, m, weight, vr, vi);
+            h_alm_m[2 * l] += vr; h_alm_m[2 * l + 1] += vi;
+        }
+        PairLane q2 = pair_lane(h, p, m, h_ln_mm[m], nullptr);
+        double2 bn, bs;
+        pair_synthesis(q2, m, lmax, (const double2 *)h_alm_in, bn, bs);
+        h_B_m[2 * (q2.rn - 1)] = bn.x; h_B_m[2 * (q2.rn - 1) + 1] = bn.y;
+        if (q2.rs > 0) { h_B_m[2 * (q2.rs - 1)] = bs.x; h_B_m[2 * (q2.rs - 1) + 1] = bs.y; }
     }
     return BFG_OK;
 }

@@ -322,6 +322,11 @@ int bfg_test_sht_lambda_host(int m, int lmax, double ln_mm, double x, double sin
  * of n pixels at phi_j = (2 j + odd) pi / n:  h_F [lmax + 1][2] = sum_j h_ring[j] exp(-i m phi_j);
  * h_out [n] = sum_m c_m Re(h_b[m] exp(i m phi_j)) with c_0 = 1, c_{m>0} = 2 and h_b [lmax + 1][2]. */
 int bfg_test_sht_ring_host(int64_t n, int odd, int lmax, const double *h_ring, double *h_F, const double *h_b, double *h_out);
+/* Unit-test entry on the HOST: the Legendre stage of ONE m over all ring pairs with the lane functions of the two Legendre kernels
+ * (north/south pairing, parity, packing).  h_F_m [4 nside - 1][2] -> h_alm_m [lmax + 1][2] (entries l >= m; the quadrature
+ * weight 4 pi / npix included);  h_alm_in [lmax + 1][2] (indexed by l) -> h_B_m [4 nside - 1][2]. */
+int bfg_test_sht_legendre_host(int nside, int lmax, int m, const double *h_ln_mm, const double *h_F_m, double *h_alm_m,
+                               const double *h_alm_in, double *h_B_m);
 
 /* ---- locality ordering ----------------------------------------------------------------------------- */
 /* Re-orders halo records (and their extras rows) so that neighbours on the sky / in the box are adjacent: north_star (b)

@@ -74,3 +74,38 @@ def test_device_ring_sums_compiled_for_the_host_follow_the_oracle_phase_conventi
     bm = (b[:, 0] + 1j * b[:, 1]) * np.where(m == 0, 1.0, 2.0)
     want = (np.exp(1j * np.outer(phi, m)) @ bm).real
     assert np.max(np.abs(out - want)) < 1e-11 * np.sqrt(lmax + 1.0) * 4
+
+
+@pytest.mark.parametrize("nside,ms", [(4, (0, 1, 2, 5, 11)), (16, (0, 3, 20, 47)), (64, (0, 1, 100, 191))])
+def test_device_legendre_stage_compiled_for_the_host_equals_the_oracle(nside, ms):
+    """The lane functions of k_sht_leg_analysis / k_sht_leg_synthesis over all ring pairs of one m: north/south pairing through
+    lambda_lm(-x) = (-1)^(l+m) lambda_lm(x), the equator on its own, healpy's packing, the 4 pi / npix weight."""
+    from baryonforge_b200 import _lib
+    from oracle.anafast_port import alm_index
+    from oracle.anafast_rings import RingSHT
+    L = _lib.lib()
+    r = RingSHT(nside)
+    lmax, nr = r.lmax, r.n_ring.size
+    rng = np.random.default_rng(nside)
+    f = rng.normal(size=r.npix)
+    Fm = r.ring_ffts(f)                                                   # [ring, m]
+    alm_want = r.analysis(f)
+    ln_mm = np.ascontiguousarray(r._ln_mm)
+    for m in ms:
+        F_m = np.ascontiguousarray(np.stack([Fm[:, m].real, Fm[:, m].imag], axis=1))
+        a_in = rng.normal(size=(lmax + 1, 2))
+        a_in[:m] = 0.0
+        a_out, B = np.zeros((lmax + 1, 2)), np.full((nr, 2), np.nan)
+        rc = L.bfg_test_sht_legendre_host(nside, lmax, m, ln_mm.ctypes.data, F_m.ctypes.data, a_out.ctypes.data, a_in.ctypes.data,
+                                          B.ctypes.data)
+        assert rc == 0
+        ls = np.arange(m, lmax + 1)
+        want = alm_want[alm_index(lmax, ls, m)]
+        got = a_out[m:, 0] + 1j * a_out[m:, 1]
+        assert np.max(np.abs(got - want)) < 1e-12 * np.max(np.abs(alm_want)), m
+        b_want = np.zeros(nr, dtype=np.complex128)
+        for l, lam in r._lambdas(m):
+            b_want += (a_in[l, 0] + 1j * a_in[l, 1]) * lam
+        b_got = B[:, 0] + 1j * B[:, 1]
+        assert np.all(np.isfinite(b_got))                                  # every ring of the map was written
+        assert np.max(np.abs(b_got - b_want)) < 1e-11 * np.max(np.abs(b_want)), m
