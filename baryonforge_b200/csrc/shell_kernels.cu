@@ -262,6 +262,28 @@ __device__ __forceinline__ void span_pixels_fast(const FastHalo &f, const RingSe
     }
 }
 
+// Loop control of the staged two-chain variant below (span_pixels_fast2), kept outside the #ifdef and __host__ __device__ so that
+// bfg_test_span2_host can check on the CPU that every pixel of a lane is visited exactly once with the right azimuth.
+// The lane's pixels are p0, p0 + GW, ... < pend; (cs, sn) is the azimuth of *p0, (rotC, rotS) a step of GW pixels.  The
+// recurrence runs on (x, y) = sin(theta) (cos phi, sin phi) itself -- a rotation is linear, so the two products sth * cs,
+// sth * sn of the v8 loop are paid once per span -- and advances two independent chains by a double step per iteration.
+template <int GW, typename UPD>
+__host__ __device__ __forceinline__ void span2_walk(double cs, double sn, double sth, double rotC, double rotS, double *p0,
+                                                    const double *pend, UPD upd) {
+    const double rot2C = fma(rotC, rotC, -rotS * rotS), rot2S = 2.0 * rotC * rotS;      // two azimuth steps at once
+    double x0 = sth * cs, y0 = sth * sn;
+    double x1 = x0 * rotC - y0 * rotS, y1 = fma(y0, rotC, x0 * rotS);                    // the lane's second chain: p0 + GW
+    for (; p0 + GW < pend; p0 += 2 * GW) {
+        upd(x0, y0, p0);
+        upd(x1, y1, p0 + GW);
+        const double a0 = x0 * rot2C - y0 * rot2S, a1 = x1 * rot2C - y1 * rot2S;
+        y0 = fma(y0, rot2C, x0 * rot2S);
+        y1 = fma(y1, rot2C, x1 * rot2S);
+        x0 = a0; x1 = a1;
+    }
+    if (p0 < pend) upd(x0, y0, p0);
+}
+
 #ifdef BFG_SHELL_UNROLL2
 // STAGED VARIANT (compile with -DBFG_SHELL_UNROLL2, tools/build_variant.sh; not measured in round 1):
 // the v8 loop is latency-limited, not throughput-limited (issue slots 65.8 % busy, FP64 pipe 52 %, 'wait' the largest stall at
@@ -293,21 +315,10 @@ template <bool CHECK, int GW>
 __device__ __forceinline__ void span_pixels_fast2(const FastHalo &f, const RingSeg &g, double cs, double sn,
                                                   double *__restrict__ p0, const double *__restrict__ pend, i64 nloc8,
                                                   const double *own_lo = nullptr, const double *own_hi = nullptr) {
-    const double z = g.z, sth = g.sth, dz = g.dz, dz2 = g.dz2, rotC = g.rotC, rotS = g.rotS;
-    const double rot2C = fma(rotC, rotC, -rotS * rotS), rot2S = 2.0 * rotC * rotS;      // two azimuth steps at once
-    // the recurrence runs on (x, y) = sin(theta) (cos phi, sin phi) itself -- a rotation is linear, so the two products
-    // sth * cs, sth * sn of the v8 loop are paid once per span instead of once per pixel
-    double x0 = sth * cs, y0 = sth * sn;
-    double x1 = x0 * rotC - y0 * rotS, y1 = fma(y0, rotC, x0 * rotS);                    // the lane's second chain: p0 + GW
-    for (; p0 + GW < pend; p0 += 2 * GW) {
-        pixel_update_fast<CHECK>(f, z, dz, dz2, x0, y0, p0, nloc8, own_lo, own_hi);
-        pixel_update_fast<CHECK>(f, z, dz, dz2, x1, y1, p0 + GW, nloc8, own_lo, own_hi);
-        const double a0 = x0 * rot2C - y0 * rot2S, a1 = x1 * rot2C - y1 * rot2S;
-        y0 = fma(y0, rot2C, x0 * rot2S);
-        y1 = fma(y1, rot2C, x1 * rot2S);
-        x0 = a0; x1 = a1;
-    }
-    if (p0 < pend) pixel_update_fast<CHECK>(f, z, dz, dz2, x0, y0, p0, nloc8, own_lo, own_hi);
+    const double z = g.z, dz = g.dz, dz2 = g.dz2;
+    span2_walk<GW>(cs, sn, g.sth, g.rotC, g.rotS, p0, pend, [&](double x, double y, double *p) {
+        pixel_update_fast<CHECK>(f, z, dz, dz2, x, y, p, nloc8, own_lo, own_hi);
+    });
 }
 #define BFG_SPAN_FAST span_pixels_fast2
 #else
@@ -1127,5 +1138,37 @@ extern "C" int bfg_shell_regrid_p2p(int nside, const double *d_map_in, const dou
     k_shell_regrid_p2p<<<grid_for(pix_hi - pix_lo, 256), 256, 0, (cudaStream_t)stream>>>(
         h, d_map_in, d_offsets, own, pix_lo, pix_hi, (unsigned long long *)d_remote_count);
     BFG_CUDA_OK(cudaGetLastError());
+    return BFG_OK;
+}
+
+namespace {
+struct VisitRecorder {
+    double *base; int32_t *visits; double *xy;
+    __host__ __device__ void operator()(double x, double y, double *p) const {
+        const int64_t off = p - base;
+        visits[off] += 1;
+        xy[2 * off] = x; xy[2 * off + 1] = y;
+    }
+};
+}  // namespace
+
+// Unit-test entry, HOST side, for the loop control of the staged two-chain pixel loop (span2_walk): one lane of a `gw`-lane
+// group walks a span of n_span pixels starting at its own pixel `li`; for every visit it records the pixel offset and the
+// (x, y) handed to the update.  h_visits [n_span]: number of visits per pixel; h_xy [n_span][2]: the (x, y) of the last visit.
+extern "C" int bfg_test_span2_host(int gw, int li, int64_t n_span, double phi_first, double dphi_pixel, double sth,
+                                   int32_t *h_visits, double *h_xy) {
+    BFG_REQUIRE((gw == 8 || gw == 16) && li >= 0 && li < gw && n_span >= 0 && h_visits && h_xy, "bad argument");
+    for (int64_t i = 0; i < n_span; ++i) { h_visits[i] = 0; h_xy[2 * i] = 0.0; h_xy[2 * i + 1] = 0.0; }
+    if (li >= n_span) return BFG_OK;
+    double *base = h_xy;                               // any array works as the pointer space: offsets are what matters
+    const double cs = cos(phi_first + li * dphi_pixel), sn = sin(phi_first + li * dphi_pixel);
+    const double rotC = cos(gw * dphi_pixel), rotS = sin(gw * dphi_pixel);
+    const VisitRecorder upd{base, h_visits, h_xy};
+    // the pointer arithmetic of the kernel: p0 = span start + li, pend = span end, stride gw (here scaled by 1 double per pixel;
+    // the visit records use a side array, so the walk itself never writes through p)
+    double *p0 = base + li;
+    const double *pend = base + n_span;
+    if (gw == 8) span2_walk<8>(cs, sn, sth, rotC, rotS, p0, pend, upd);
+    else span2_walk<16>(cs, sn, sth, rotC, rotS, p0, pend, upd);
     return BFG_OK;
 }
