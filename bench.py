@@ -52,6 +52,9 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-sort", action="store_true", help="skip the device-side sky ordering of halos (L2 locality)")
     ap.add_argument("--mass-function", action="store_true", help="steeper dn/dlogM ~ M^-0.9 catalogue variant")
+    ap.add_argument("--owned-result", action="store_true",
+                    help="N > 1: leave the new map distributed (every rank keeps the slice it owns, as the end-to-end path does) "
+                         "instead of all-gathering 1.6 GB onto every rank inside the device-resident step; staged, unmeasured")
     ap.add_argument("--no-particles", action="store_true",
                     help="skip the secondary metric (BaryonifySnapshot particles displaced/s, weak scaling)")
     ap.add_argument("--particles-per-gpu", type=int, default=250000000)
@@ -307,8 +310,11 @@ def run_b200(args):
             _lib.check(L.bfg_shell_regrid_p2p(nside, d_map.data_ptr(), d_off.data_ptr(), lo, hi, world, rank, peers.h_bounds,
                                               peers.h_slices, None, st))
             dist.all_reduce(token)
-            full = parallel.gather_owned_ranges(own, npix)
-            _lib.check(L.bfg_sum_f64(full.data_ptr(), npix, d_sums.data_ptr(), st))
+            if args.owned_result:
+                _lib.check(L.bfg_sum_f64(own.data_ptr(), hi - lo, d_sums.data_ptr(), st))
+            else:
+                full = parallel.gather_owned_ranges(own, npix)
+                _lib.check(L.bfg_sum_f64(full.data_ptr(), npix, d_sums.data_ptr(), st))
         else:
             _lib.check(L.bfg_shell_regrid(nside, d_map.data_ptr(), d_off.data_ptr(), d_new.data_ptr(), lo, hi, st))
             if world > 1:
@@ -429,7 +435,9 @@ def run_b200(args):
                        "l2_policy": "working set (4.8 GB offsets + 3.2 GB maps per step) >> 126 MB L2; no flush needed",
                        "sharding": "none" if world == 1 else (
                            f"RING pixel ranges x{world}, overlap halos replicated, " + (
-                               "re-binning fused with the exchange (fp64 REDs into the owner's slice over NVLink peer memory) + NCCL all-gather of slices"
+                               "re-binning fused with the exchange (fp64 REDs into the owner's slice over NVLink peer memory) + " + (
+                                   "new map left distributed over the owners (--owned-result)" if args.owned_result
+                                   else "NCCL all-gather of slices")
                                if peers is not None else "NCCL all-reduce of partial maps"))},
             "clocks": clocks, "gpu_launches": n_launch,
             "roofline": {"bound": "hbm", "kernel": "k_shell_halos<baryonify> (fused disc/separation/table/accumulate)",
