@@ -290,7 +290,7 @@ class DefaultRunner(object):
     def __getstate__(self):
         d = dict(self.__dict__)
         d['_tables'] = None
-        for k in ('_scratch_inflight', '_peers', '_d_aux', '_spl_cache', '_host_maps'):
+        for k in ('_scratch_inflight', '_peers', '_d_aux', '_spl_cache', '_host_maps', '_cells'):
             d.pop(k, None)
         return d
 
@@ -1462,7 +1462,7 @@ class DefaultRunnerSnapshot(object):
     by a device cell list built inside process(); KDTree_kwargs is accepted and ignored."""
 
     def __init__(self, HaloNDCatalog, ParticleSnapshot, epsilon_max, model, mass_def=None, verbose=True,
-                 KDTree_kwargs={}, *, device=None, ncell=None):
+                 KDTree_kwargs={}, *, device=None, ncell=None, keep_cells=False):
         self.HaloNDCatalog = HaloNDCatalog
         self.ParticleSnapshot = ParticleSnapshot
         self.epsilon_max = epsilon_max
@@ -1473,6 +1473,11 @@ class DefaultRunnerSnapshot(object):
         self.KDTree_kwargs = KDTree_kwargs
         self.device = device
         self.ncell = ncell
+        # keep_cells: keep the device cell list (cell-sorted particle copies, 32 B per particle of HBM) between process() calls
+        # on the same ParticleSnapshot, the way the reference builds its KD-tree once in __init__ (SnapshotRunner.py:95-100)
+        # and re-uses it when only `Runner.model` changes (examples/10_...ipynb cell 15).  STAGED: default off until measured.
+        self.keep_cells = keep_cells
+        self._cells = None
         self.last_stats = {}
         self._tables = _TableCache()
 
@@ -1580,13 +1585,22 @@ class BaryonifySnapshot(DefaultRunnerSnapshot):
         with torch.cuda.device(dev):
             st = _lib.current_stream()
             names = ['x', 'y', 'z'][:ndim]
-            d_p = [_to_device(ps.cat[k], dev, dtype=np.float64) for k in names] + ([None] if ndim == 2 else [])
-            d_s = [torch.empty(n_part, dtype=torch.float64, device=dev) for _ in names] + ([None] if ndim == 2 else [])
-            d_start = torch.empty(ncell ** ndim + 1, dtype=torch.int64, device=dev)
-            d_order = torch.empty(n_part, dtype=torch.int64, device=dev)
-            _lib.check(L.bfg_snap_build_cells(ndim, n_part, _lib.ptr(d_p[0]), _lib.ptr(d_p[1]), _lib.ptr(d_p[2]), Lbox,
-                                              ncell, _lib.ptr(d_start), _lib.ptr(d_order), _lib.ptr(d_s[0]),
-                                              _lib.ptr(d_s[1]), _lib.ptr(d_s[2]), st))
+            cells_key = (_Ident(ps.cat), ncell, ndim, str(dev))
+            kept = getattr(self, '_cells', None) if getattr(self, 'keep_cells', False) else None
+            if kept is not None and kept[0] == cells_key:
+                # the cell list of this ParticleSnapshot is still on the device: no upload, no counting sort; fresh output buffers
+                _, d_s, d_start, d_order = kept
+                d_p = [torch.empty(n_part, dtype=torch.float64, device=dev) for _ in names] + ([None] if ndim == 2 else [])
+            else:
+                d_p = [_to_device(ps.cat[k], dev, dtype=np.float64) for k in names] + ([None] if ndim == 2 else [])
+                d_s = [torch.empty(n_part, dtype=torch.float64, device=dev) for _ in names] + ([None] if ndim == 2 else [])
+                d_start = torch.empty(ncell ** ndim + 1, dtype=torch.int64, device=dev)
+                d_order = torch.empty(n_part, dtype=torch.int64, device=dev)
+                _lib.check(L.bfg_snap_build_cells(ndim, n_part, _lib.ptr(d_p[0]), _lib.ptr(d_p[1]), _lib.ptr(d_p[2]), Lbox,
+                                                  ncell, _lib.ptr(d_start), _lib.ptr(d_order), _lib.ptr(d_s[0]),
+                                                  _lib.ptr(d_s[1]), _lib.ptr(d_s[2]), st))
+                if getattr(self, 'keep_cells', False):
+                    self._cells = (cells_key, d_s, d_start, d_order)
             d_ext = None if extras is None else _to_device(extras, dev)
             d_rec, d_ext = _sort_records(d_rec0, d_ext, 1, Lbox, 16, ndim)
             d_tot = torch.zeros((ndim, n_part), dtype=torch.float64, device=dev)

@@ -103,6 +103,36 @@ def test_two_pass_cell_sort_gives_the_same_snapshot(name, monkeypatch):
         assert_close(a, b, name, rtol=1e-12, atol_scale=1e-13)        # summation order of the halo loop's REDs only
 
 
+@pytest.mark.skipif(__import__("os").environ.get("BFG_TEST_EXPERIMENTAL") != "1",
+                    reason="keep_cells is staged for measurement (DESIGN.md section 8); set BFG_TEST_EXPERIMENTAL=1")
+def test_kept_cell_list_gives_the_same_snapshots_for_successive_models():
+    """keep_cells=True: the cell list survives between process() calls while `Runner.model` changes (the reference builds its
+    KD-tree once in __init__ and the notebooks swap models); results equal fresh runners', and earlier results are not clobbered."""
+    import baryonforge_b200 as b
+    from baryonforge_b200 import synth
+    g = load("snap_3d")
+    cosmo = synth.COSMO
+    mc = dict(Omega_m=0.27 + 0.05, Omega_b=0.05, h=0.68, sigma8=0.82, n_s=0.97, w0=-1.0)
+    axes = (g["ax0"], g["ax1"], g["ax2"])
+    cat = b.HaloNDCatalog(x=g["x"], y=g["y"], z=g["z"], M=g["M"], redshift=g["redshift"], cosmo=cosmo)
+    ps = b.ParticleSnapshot(x=g["px"], y=g["py"], z=g["pz"], M=g["pM"], L=float(g["L"]), redshift=g["redshift"], cosmo=cosmo)
+    models = [b.DisplacementModel(axes, g["values"] * f, g["eps_mod"], mc) for f in (1.0, 0.5, -0.7)]
+    kept = b.BaryonifySnapshot(cat, ps, g["eps_run"], models[0], verbose=False, keep_cells=True)
+    outs, dev_outs = [], []
+    for m in models:
+        kept.model = m
+        dev_outs.append(kept.process_on_device())
+        outs.append(kept.process())
+        assert kept._cells is not None
+    for m, out, d_out in zip(models, outs, dev_outs):
+        want = b.BaryonifySnapshot(cat, ps, g["eps_run"], m, verbose=False).process()
+        for k, name in enumerate("xyz"):
+            assert_close(out[name], want[name], "kept cells " + name, rtol=1e-12, atol_scale=1e-13)
+            assert_close(d_out[k].cpu().numpy(), want[name], "earlier device result " + name, rtol=1e-12, atol_scale=1e-13)
+    assert np.array_equal(kept.process_to_map(16), b.BaryonifySnapshot(cat, ps, g["eps_run"], models[-1],
+                                                                       verbose=False).process_to_map(16))
+
+
 def test_healpix_device_geometry_matches_oracle():
     from baryonforge_b200 import healpix as dh
     from oracle import hpo

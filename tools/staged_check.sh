@@ -7,7 +7,7 @@ set -u
 cd "$(dirname "$0")/.."
 OUT=gpurun_out; mkdir -p $OUT
 echo "=== gated parity tests (two-pass cell list, P(k) from the cell list, C_l kernels)"
-BFG_TEST_EXPERIMENTAL=1 python -m pytest tests -m gpu -q -k "two_pass or cell_ordered or harmonics" 2>&1 | tail -15
+BFG_TEST_EXPERIMENTAL=1 python -m pytest tests -m gpu -q -k "two_pass or cell_ordered or harmonics or kept_cell" 2>&1 | tail -15
 echo "=== cell-list build: default vs BFG_CELL_SORT=2"
 python tools/bench_configs.py --which c4 2>/dev/null | tee $OUT/staged_c4_default.json | cut -c1-400
 BFG_CELL_SORT=2 python tools/bench_configs.py --which c4 2>/dev/null | tee $OUT/staged_c4_twopass.json | cut -c1-400
