@@ -50,7 +50,19 @@ def _worker(rank, world, port, q):
     part = np.zeros(npix); part[lo:hi] = hmap[lo:hi]
     red, src_sum = parallel.reduce_partial_map(torch.from_numpy(part), torch.from_numpy(hmap[lo:hi].copy()))
     ok_reduce = np.allclose(red.numpy(), hmap) and np.isclose(float(src_sum), hmap.sum())
-    q.put((rank, bool(ok_gather), bool(ok_reduce), int(keep.sum())))
+    # SimpleParallel under torch.distributed: the runner list is split round-robin over the ranks, every rank gets all outputs
+    class _Job(object):
+        def __init__(self, i):
+            self.i, self.ran_on = i, None
+
+        def process(self):
+            self.ran_on = dist.get_rank()
+            return np.full(7, float(self.i)) + np.arange(7)
+    jobs = [_Job(i) for i in range(5)]
+    outs = parallel.SimpleParallel(jobs).process()
+    ok_simple = (len(outs) == 5 and all(np.array_equal(o, np.full(7, float(i)) + np.arange(7)) for i, o in enumerate(outs))
+                 and [j.ran_on for j in jobs] == [rank if i % world == rank else None for i in range(5)])
+    q.put((rank, bool(ok_gather), bool(ok_reduce and ok_simple), int(keep.sum())))
     dist.destroy_process_group()
 
 
