@@ -92,7 +92,7 @@ struct HaloCell {
 // All corners are always multiplied in, like scipy's _evaluate_linear, so 0 * (-inf) = NaN survives.
 // Called by every thread of the block; caller __syncthreads() afterwards.
 __device__ __forceinline__ void blend_row(const TableView &T, double lnz, double lnM, const double *__restrict__ extras,
-                                          double *__restrict__ row, bool &valid) {
+                                          double *__restrict__ row, bool &valid, const double post = 1.0) {
     const int nd = T.ndim;
     int idx[BFG_MAX_TABLE_DIM];
     double tt[BFG_MAX_TABLE_DIM];
@@ -122,7 +122,7 @@ __device__ __forceinline__ void blend_row(const TableView &T, double lnz, double
             acc = acc + __ldg(v01 + o) * w01;
             acc = acc + __ldg(v10 + o) * w10;
             acc = acc + __ldg(v11 + o) * w11;
-            row[k] = acc;
+            row[k] = acc * post;
         }
         return;
     }
@@ -141,7 +141,7 @@ __device__ __forceinline__ void blend_row(const TableView &T, double lnz, double
             }
             acc = acc + __ldg(T.v + off) * w;
         }
-        row[k] = acc;
+        row[k] = acc * post;
     }
 }
 

@@ -202,11 +202,104 @@ struct FastHalo {
     double rcut2;         // (model eps * R_com * a / D)^2  on the unit sphere
     double aD;            // a / D   (paint: the record's SCALE, pixarea * D^2 or 1)
     RowLookup t;          // cell coordinate u = log2(|d|^2) * uA + uB   (uB includes ln D and ln(1/a) [- ln R_com])
+    unsigned et_s;        // v9 loop: shared-window address of the per-halo exponent table E[i] = uB + uA (i + V9_EMIN)
 };
+
+// ------------------------------------------------------------------------------------------------------------------
+// v9 pixel loop (round 2).  ncu of v8: FP64 pipe 52 % active, XU pipe 19 % (2 MUFU.RSQ64H + F2I.F64 + I2F.F64 per update),
+// 'wait' the largest stall -- the loop is one long dependent FP64 chain, so fewer FP64 instructions shorten both the pipe
+// time and the latency.  47 -> 37 FP64-pipe instructions per update, 1 XU instruction instead of 4, by
+//   * rotating (x, y) = sin(theta) (cos phi, sin phi) itself (a rotation is linear: no sth * cs, sth * sn per pixel);
+//   * log2(1+f) to degree 3 (|f| <= 2^-8: abs. error 8e-11 in log2 r^2, 3e-11 in ln r -- six orders below the 1e-6 bar);
+//   * the exponent's share of the cell coordinate, uB + uA e, from a 64-entry per-halo table in shared memory
+//     (r^2 in [2^-61, 8) on the unit sphere; anything else takes the arithmetic path);
+//   * floor(u) with one round-down add of 2^52 + 2^51 (DADD.RM) -- the cell index is the low word of the sum, its double is
+//     the sum minus the constant: no F2I / I2F;
+//   * the table row pre-multiplied by a / D at blend time;
+//   * 1/sqrt(r^2) = MUFU seed + one Newton step (rel. error 1e-13);
+//   * the re-normalisation nw_vec - vec = normalise(vec + sc d) - vec expanded in eps = |vec + sc d|^2 - 1.  Both vectors
+//     are unit vectors, so vec . d = |d|^2 / 2 and eps = sc r^2 (1 + sc) needs no dot product; with
+//     dl = 1/sqrt(1 + eps) - 1 = eps (-1/2 + 3/8 eps - 5/16 eps^2) the result is sc (1 + dl) d + dl vec.  dl vec is
+//     <~ 1 % of the result, so the truncation (0.27 eps^4) is < 1e-8 of it for |eps| < 2^-6; larger eps (a displacement
+//     comparable to the halo's distance) takes the exact rsqrt path.  No cancellation, unlike fma(nx, ninv, -x).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int V9_EMIN = -61, V9_NE = 64;
+
+struct V9Cell { double val; bool ok; };
+
+// blended-row value at squared chord r2 (lean version of row_at_r2; same interval rule and edge handling)
+__device__ __forceinline__ double row_at_r2_v9(const FastHalo &f, double r2, bool &ok) {
+    const int hi = __double2hiint(r2);
+    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(r2));
+    const double2 t = lds_f64x2(f.t.l2_s + (((unsigned)hi >> 9) & 0x7f0u));
+    const double fr = fma(m, t.x, -1.0);
+    double p = fma(fr, c_l2p[2], c_l2p[3]);
+    p = fma(fr, p, c_l2p[4]);
+    const double lf = fma(fr, p, t.y);                                   // log2 of the mantissa
+    const unsigned ei = ((unsigned)hi >> 20) - (unsigned)(1023 + V9_EMIN);
+    double E;
+    if (__builtin_expect(ei < (unsigned)V9_NE, 1)) E = lds_f64(f.et_s + (ei << 3));
+    else E = fma(__hiloint2double(0x43300000, (hi >> 20) ^ 0x80000000) - 4503601774855167.0, f.t.uA, f.t.uB);
+    const double uu = fma(lf, f.t.uA, E);
+    double kk = __dadd_rd(uu, 6755399441055744.0);                       // 2^52 + 2^51 + floor(uu)
+    ok = true;
+    if (__builtin_expect(!((__double2hiint(kk) == 0x43380000) & ((unsigned)__double2loint(kk) <= (unsigned)f.t.nrm2)), 0)) {
+        ok = (uu == f.t.uMax);                                           // outside the table, or exactly on its last node
+        kk = __hiloint2double(0x43380000, f.t.nrm2);
+    }
+    const double tt = uu - (kk - 6755399441055744.0);
+    const unsigned ra = f.t.row_s + ((unsigned)__double2loint(kk) << 3);
+    const double v0 = lds_f64(ra);
+    return fma(tt, lds_f64(ra + 8) - v0, v0);
+}
+
+// 1/sqrt(x), positive normal x: MUFU seed (2^-22) + one Newton step -> relative error < 1e-13
+__device__ __forceinline__ double rsqrt_newton(double x) {
+    double y0;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+    const double e = fma(-x, y0 * y0, 1.0);
+    return fma(y0 * e, 0.5, y0);
+}
+
+// one (halo, pixel) update of the v9 loop; the row holds displacement * a / D
+template <bool CHECK>
+__device__ __forceinline__ void pixel_update_v9(const FastHalo &f, double z, double dz, double dz2, double x, double y,
+                                                double *__restrict__ p0, i64 nloc8, const double *own_lo,
+                                                const double *own_hi) {
+    const double dx = x - f.vx, dy = y - f.vy;
+    const double r2 = fma(dx, dx, fma(dy, dy, dz2));                 // |vec - vec_j|^2   HealpixRunner.py:338-341
+    bool ok;
+    const double val = row_at_r2_v9(f, r2, ok);                      // :345 via ln(r_sep / a) [- ln R_com]
+    const double sc = val * rsqrt_newton(r2);                        // offset / r_sep   :345-346
+    // BaryonCorrection.py:410-411 zero beyond the model's cut; HealpixRunner.py:347 non-finite -> 0; exact zeros add nothing
+    ok = ok && (r2 < f.rcut2) && ((((unsigned)__double2hiint(sc) & 0x7fffffffu) - 1u) < 0x7fefffffu);
+    if (CHECK) ok = ok && (p0 >= own_lo) && (p0 < own_hi);
+    const double t1 = sc * r2;
+    const double eps = fma(t1, sc, t1);                              // |vec + sc d|^2 - 1
+    if (ok) {
+        double ox, oy, oz;
+        if (__builtin_expect(((unsigned)__double2hiint(eps) & 0x7fffffffu) < 0x3f900000u, 1)) {   // |eps| < 2^-6
+            const double dl = eps * fma(eps, fma(eps, -0.3125, 0.375), -0.5);
+            const double q = fma(sc, dl, sc);
+            ox = fma(q, dx, dl * x); oy = fma(q, dy, dl * y); oz = fma(q, dz, dl * z);   // :350-355
+        } else {
+            const double nx = fma(sc, dx, x), ny = fma(sc, dy, y), nz = fma(sc, dz, z);
+            const double ninv = rsqrt_pos(fma(nx, nx, fma(ny, ny, nz * nz)));
+            ox = fma(nx, ninv, -x); oy = fma(ny, ninv, -y); oz = fma(nz, ninv, -z);
+        }
+#ifdef BFG_SHELL_NO_RED   // diagnostic build: the arithmetic without its scatter-add (where does the time go?)
+        asm volatile("" :: "d"(ox), "d"(oy), "d"(oz), "l"(p0));
+#else
+        red_add(p0, ox);
+        red_add((double *)((char *)p0 + nloc8), oy);
+        red_add((double *)((char *)p0 + 2 * nloc8), oz);
+#endif
+    }
+}
 
 template <bool PAINT>
 __device__ __forceinline__ FastHalo make_fast(const TableView &T, const HaloSph &s, const HaloUpd &u, const double *row,
-                                              const double2 *l2tab) {
+                                              const double2 *l2tab, const double *etab) {
     FastHalo f;
     f.vx = s.vx; f.vy = s.vy;
     const double rc = s.rcut * s.a / s.D;
@@ -218,6 +311,7 @@ __device__ __forceinline__ FastHalo make_fast(const TableView &T, const HaloSph 
     f.t.nrm2 = T.n[2] - 2;
     f.t.row_s = (unsigned)__cvta_generic_to_shared(row);
     f.t.l2_s = (unsigned)__cvta_generic_to_shared(l2tab);
+    f.et_s = (unsigned)__cvta_generic_to_shared(etab);
     return f;   // handed to the other warps through shared memory (HaloCtx), which also keeps ptxas from re-deriving it
 }
 
@@ -284,45 +378,38 @@ __host__ __device__ __forceinline__ void span2_walk(double cs, double sn, double
     if (p0 < pend) upd(x0, y0, p0);
 }
 
-#ifdef BFG_SHELL_UNROLL2
-// STAGED VARIANT (compile with -DBFG_SHELL_UNROLL2, tools/build_variant.sh; not measured in round 1):
-// the v8 loop is latency-limited, not throughput-limited (issue slots 65.8 % busy, FP64 pipe 52 %, 'wait' the largest stall at
-// 3.15 per issue with one dependent chain per warp and 7 warps per scheduler).  Here every lane carries TWO independent pixel
-// chains -- its pixels p and p + GW -- per iteration, each advanced by a double azimuth step, so the scheduler has twice the
-// instruction-level parallelism per warp; and the azimuth recurrence rotates (x, y) directly (43 instead of 45 FP64
-// instructions per update).  Same per-pixel arithmetic otherwise; results differ from v8 by round-off only.
-template <bool CHECK>
-__device__ __forceinline__ void pixel_update_fast(const FastHalo &f, double z, double dz, double dz2, double x, double y,
-                                                  double *__restrict__ p0, i64 nloc8, const double *own_lo,
-                                                  const double *own_hi) {
-    const double dx = x - f.vx, dy = y - f.vy;
-    const double r2 = fma(dx, dx, fma(dy, dy, dz2));
-    bool ok;
-    const double val = row_at_r2(f.t, r2, ok);
-    const double sc = (val * f.aD) * rsqrt_pos(r2);
-    ok = ok && (r2 < f.rcut2) && ((((unsigned)__double2hiint(sc) & 0x7fffffffu) - 1u) < 0x7fefffffu);
-    if (CHECK) ok = ok && (p0 >= own_lo) && (p0 < own_hi);
-    const double nx = fma(sc, dx, x), ny = fma(sc, dy, y), nz = fma(sc, dz, z);
-    const double ninv = rsqrt_pos(fma(nx, nx, fma(ny, ny, nz * nz)));
-    if (ok) {
-        red_add(p0, fma(nx, ninv, -x));
-        red_add((double *)((char *)p0 + nloc8), fma(ny, ninv, -y));
-        red_add((double *)((char *)p0 + 2 * nloc8), fma(nz, ninv, -z));
-    }
-}
-
+// Pixels per lane and iteration of the v9 loop: 1 = one dependent chain per lane; 2 = two independent chains (the lane's
+// pixels p and p + GW, each advanced by a double azimuth step -- span2_walk), which doubles the instruction-level
+// parallelism a warp offers its scheduler at the price of ~20 more live registers.
+#ifndef BFG_SHELL_CHAINS
+#define BFG_SHELL_CHAINS 1
+#endif
 template <bool CHECK, int GW>
-__device__ __forceinline__ void span_pixels_fast2(const FastHalo &f, const RingSeg &g, double cs, double sn,
-                                                  double *__restrict__ p0, const double *__restrict__ pend, i64 nloc8,
-                                                  const double *own_lo = nullptr, const double *own_hi = nullptr) {
+__device__ __forceinline__ void span_pixels_v9(const FastHalo &f, const RingSeg &g, double cs, double sn,
+                                               double *__restrict__ p0, const double *__restrict__ pend, i64 nloc8,
+                                               const double *own_lo = nullptr, const double *own_hi = nullptr) {
     const double z = g.z, dz = g.dz, dz2 = g.dz2;
+#if BFG_SHELL_CHAINS == 2
     span2_walk<GW>(cs, sn, g.sth, g.rotC, g.rotS, p0, pend, [&](double x, double y, double *p) {
-        pixel_update_fast<CHECK>(f, z, dz, dz2, x, y, p, nloc8, own_lo, own_hi);
+        pixel_update_v9<CHECK>(f, z, dz, dz2, x, y, p, nloc8, own_lo, own_hi);
     });
-}
-#define BFG_SPAN_FAST span_pixels_fast2
 #else
+    const double rotC = g.rotC, rotS = g.rotS;
+    double x = g.sth * cs, y = g.sth * sn;
+    for (; p0 < pend; p0 += GW) {
+        pixel_update_v9<CHECK>(f, z, dz, dz2, x, y, p0, nloc8, own_lo, own_hi);
+        const double x2 = x * rotC - y * rotS;                       // advance the azimuth by GW pixels
+        y = fma(y, rotC, x * rotS);
+        x = x2;
+    }
+#endif
+}
+#ifdef BFG_SHELL_V8
 #define BFG_SPAN_FAST span_pixels_fast
+constexpr bool SHELL_V9 = false;
+#else
+#define BFG_SPAN_FAST span_pixels_v9
+constexpr bool SHELL_V9 = true;
 #endif
 
 // PaintProfilesShell counterpart of span_pixels_fast (HealpixRunner.py:464-481): map[p] += exp(table(ln(r_sep / a))) * SCALE,
@@ -453,6 +540,7 @@ k_shell_halos(TableView T, Hpx h, i64 n_halo, const double *__restrict__ halos, 
     sincospi((double)lane * (2.0 / (double)h.nl4), &eqS, &eqC);
     __shared__ double2 s_eq[GW_SMALL + GW_LARGE];
     __shared__ HaloCtx s_ctx;
+    __shared__ double s_etab[V9_NE];   // v9 loop: uB + uA * exponent, per halo
     if (FAST && threadIdx.x < GW_SMALL + GW_LARGE) {
         const int k = (threadIdx.x < GW_SMALL) ? threadIdx.x : threadIdx.x - GW_SMALL;
         double sk, ck;
@@ -481,10 +569,15 @@ k_shell_halos(TableView T, Hpx h, i64 n_halo, const double *__restrict__ halos, 
                     const int gws = (0.7853981633974483 * 2.0 * s0.radius) * sqrt((double)h.npix * 0.07957747154594767)
                                     < GW_CHORD_SPLIT;
                     const int tch = !sharded || disc_touches_range(h, d0, pix_lo, pix_hi);
-                    if (lane == 0) {
-                        s_ctx.d = d0; s_ctx.u = u0; s_ctx.gw_small = gws; s_ctx.touches = tch;
-                        if (FAST) s_ctx.fh = make_fast<PAINT>(T, s0, u0, row, l2tab);
+                    if (FAST) {
+                        const FastHalo f0 = make_fast<PAINT>(T, s0, u0, row, l2tab, s_etab);
+                        if (lane == 0) s_ctx.fh = f0;
+                        if (SHELL_V9 && !PAINT) {
+#pragma unroll
+                            for (int i = lane; i < V9_NE; i += 32) s_etab[i] = fma((double)(i + V9_EMIN), f0.t.uA, f0.t.uB);
+                        }
                     }
+                    if (lane == 0) { s_ctx.d = d0; s_ctx.u = u0; s_ctx.gw_small = gws; s_ctx.touches = tch; }
                 }
             }
             if (lane == 0) s_j = jn;
@@ -496,8 +589,11 @@ k_shell_halos(TableView T, Hpx h, i64 n_halo, const double *__restrict__ halos, 
         const HaloSph s = load_halo(halos + j * BFG_HALO_STRIDE);
         const DiscRings d = s_ctx.d;
         bool valid;
-        blend_row(T, s.lnz, s.lnM, extras ? extras + j * n_extra : nullptr, row, valid);
-        const HaloUpd u = s_ctx.u;
+        // v9 baryonify loop: the row holds displacement * a / D (the unit-sphere offset per unit chord is row / |d|)
+        constexpr bool PRESCALED = FAST && !PAINT && SHELL_V9;
+        blend_row(T, s.lnz, s.lnM, extras ? extras + j * n_extra : nullptr, row, valid, PRESCALED ? s.a / s.D : 1.0);
+        HaloUpd u = s_ctx.u;
+        if (PRESCALED) u.a = u.D;       // generic update on a prescaled row: sc = (row * D) / r_sep   (the < 4-pixel fallback)
         HaloUpd u2 = u;
         if (MODE == MODE_ANIS) {
             bool valid2;

@@ -10,7 +10,7 @@ CS=${COMPUTE_SANITIZER:-/usr/local/cuda/bin/compute-sanitizer}
 SMALL='map_runners_match_reference_fixture or snapshot_matches_reference_fixture or process_to_map or pk_matches_notebook_fixture or folded_deposit_edge_cases'
 for tool in memcheck racecheck initcheck; do
     echo "=== compute-sanitizer --tool $tool"
-    timeout 600 "$CS" --tool "$tool" --target-processes all --error-exitcode 9 \
+    timeout ${SANITIZE_TIMEOUT:-600} "$CS" --tool "$tool" --target-processes all --error-exitcode 9 \
         python -m pytest tests/test_gpu_parity.py tests/test_gpu_spectrum.py -m gpu -q -x -k "$SMALL" 2>&1 \
         | grep -E "ERROR SUMMARY|passed|failed|error|Error|=====" | tail -20
     echo "exit code of the $tool pass: ${PIPESTATUS[0]}"

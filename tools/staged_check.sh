@@ -24,4 +24,4 @@ done
 echo "=== C_l step timing"
 timeout 300 python tools/bench_anafast.py 2>$OUT/staged_anafast.err | tee $OUT/staged_anafast.json | cut -c1-600
 echo "=== compute-sanitizer"
-timeout 600 bash tools/sanitize.sh 2>&1 | tail -12
+SANITIZE_TIMEOUT=240 timeout 800 bash tools/sanitize.sh 2>&1 | tail -12
