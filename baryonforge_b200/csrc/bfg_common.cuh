@@ -90,43 +90,46 @@ struct HaloCell {
 // Blend the 2^(ndim-1) (z, M, extras) corner rows into ONE radial row in shared memory:
 //   row[k] = sum_c w_c * values[corner_c, k]
 // All corners are always multiplied in, like scipy's _evaluate_linear, so 0 * (-inf) = NaN survives.
-// Called by every thread of the block; caller __syncthreads() afterwards.
-__device__ __forceinline__ void blend_row(const TableView &T, double lnz, double lnM, const double *__restrict__ extras,
-                                          double *__restrict__ row, bool &valid, const double post = 1.0) {
-    const int nd = T.ndim;
+// RowBlender holds the per-halo part (cells and weights of the non-radial axes); node(k) is one blended value.
+struct RowBlender {
+    int nd, NR;
+    i64 sr;
+    bool valid;                            // false -> a non-radial coordinate is outside its axis: every read-out is NaN
     int idx[BFG_MAX_TABLE_DIM];
     double tt[BFG_MAX_TABLE_DIM];
-    bool ok = true;
-    int e = 0;
-    for (int d = 0; d < nd; ++d) {
-        if (d == 2) continue;
-        double x = (d == 0) ? lnz : (d == 1) ? lnM : extras[e++];
-        ok &= axis_cell(T.ax[d], T.n[d], x, idx[d], tt[d]);
-    }
-    valid = ok;
-    const int nc = 1 << (nd - 1);
-    const int NR = T.n[2];
-    const i64 sr = T.stride[2];
-    if (nd == 3) {   // the common (z, M, r) table: corner rows and weights hoisted out of the radial loop
-        const double *__restrict__ v00 = T.v + (i64)idx[0] * T.stride[0] + (i64)idx[1] * T.stride[1];
-        const double *__restrict__ v01 = v00 + T.stride[1];
-        const double *__restrict__ v10 = v00 + T.stride[0];
-        const double *__restrict__ v11 = v10 + T.stride[1];
+    const double *v00, *v01, *v10, *v11;   // the common (z, M, r) table: corner rows ...
+    double w00, w01, w10, w11;             // ... and weights hoisted out of the radial loop
+
+    __device__ __forceinline__ RowBlender(const TableView &T, double lnz, double lnM, const double *__restrict__ extras) {
+        nd = T.ndim; NR = T.n[2]; sr = T.stride[2];
+        bool ok = true;
+        int e = 0;
+        for (int d = 0; d < nd; ++d) {
+            if (d == 2) continue;
+            double x = (d == 0) ? lnz : (d == 1) ? lnM : extras[e++];
+            ok &= axis_cell(T.ax[d], T.n[d], x, idx[d], tt[d]);
+        }
+        valid = ok;
+        v00 = T.v + (i64)idx[0] * T.stride[0] + (i64)idx[1] * T.stride[1];
+        v01 = v00 + T.stride[1];
+        v10 = v00 + T.stride[0];
+        v11 = v10 + T.stride[1];
         // itertools.product order (z, M) = (0,0), (0,1), (1,0), (1,1); weight = w_z * w_M, summed in that order
-        const double w00 = (1.0 - tt[0]) * (1.0 - tt[1]), w01 = (1.0 - tt[0]) * tt[1];
-        const double w10 = tt[0] * (1.0 - tt[1]), w11 = tt[0] * tt[1];
-        for (int k = threadIdx.x; k < NR; k += blockDim.x) {
+        w00 = (1.0 - tt[0]) * (1.0 - tt[1]); w01 = (1.0 - tt[0]) * tt[1];
+        w10 = tt[0] * (1.0 - tt[1]); w11 = tt[0] * tt[1];
+    }
+
+    __device__ __forceinline__ double node(const TableView &T, int k) const {
+        if (nd == 3) {
             const i64 o = (i64)k * sr;
             double acc = 0.0;
             acc = acc + __ldg(v00 + o) * w00;
             acc = acc + __ldg(v01 + o) * w01;
             acc = acc + __ldg(v10 + o) * w10;
             acc = acc + __ldg(v11 + o) * w11;
-            row[k] = acc * post;
+            return acc;
         }
-        return;
-    }
-    for (int k = threadIdx.x; k < NR; k += blockDim.x) {
+        const int nc = 1 << (nd - 1);
         double acc = 0.0;
         for (int c = 0; c < nc; ++c) {
             i64 off = (i64)k * sr;
@@ -141,7 +144,36 @@ __device__ __forceinline__ void blend_row(const TableView &T, double lnz, double
             }
             acc = acc + __ldg(T.v + off) * w;
         }
-        row[k] = acc * post;
+        return acc;
+    }
+};
+
+// row[k] = blended node k (times `post`).  Called by every thread of the block; caller __syncthreads() afterwards.
+__device__ __forceinline__ void blend_row(const TableView &T, double lnz, double lnM, const double *__restrict__ extras,
+                                          double *__restrict__ row, bool &valid, const double post = 1.0) {
+    const RowBlender B(T, lnz, lnM, extras);
+    valid = B.valid;
+    for (int k = threadIdx.x; k < B.NR; k += blockDim.x) row[k] = B.node(T, k) * post;
+}
+
+// The same, plus the row as (value, step to the next node) pairs for read-outs that fetch a whole cell with one 16-byte load:
+// rowp[k] = (row[k], row[k+1] - row[k]), rowp[NR-1] = (row[NR-1], 0).  The neighbour's value comes from the next lane by
+// shuffle; only the last lane of a warp blends a second node.  Every thread of the block must call it (blockDim.x % 32 == 0).
+__device__ __forceinline__ void blend_row_pairs(const TableView &T, double lnz, double lnM, const double *__restrict__ extras,
+                                                double *__restrict__ row, double2 *__restrict__ rowp, bool &valid,
+                                                const double post = 1.0) {
+    const RowBlender B(T, lnz, lnM, extras);
+    valid = B.valid;
+    const int lane = threadIdx.x & 31;
+    for (int k0 = 0; k0 < B.NR; k0 += blockDim.x) {      // uniform trip count: the shuffle needs the whole warp
+        const int k = k0 + threadIdx.x;
+        const double v = (k < B.NR) ? B.node(T, k) * post : 0.0;
+        double nxt = __shfl_down_sync(0xffffffffu, v, 1);
+        if (lane == 31 && k + 1 < B.NR) nxt = B.node(T, k + 1) * post;
+        if (k < B.NR) {
+            row[k] = v;
+            rowp[k] = make_double2(v, (k + 1 < B.NR) ? nxt - v : 0.0);
+        }
     }
 }
 

@@ -202,109 +202,141 @@ struct FastHalo {
     double rcut2;         // (model eps * R_com * a / D)^2  on the unit sphere
     double aD;            // a / D   (paint: the record's SCALE, pixarea * D^2 or 1)
     RowLookup t;          // cell coordinate u = log2(|d|^2) * uA + uB   (uB includes ln D and ln(1/a) [- ln R_com])
-    unsigned et_s;        // v9 loop: shared-window address of the per-halo exponent table E[i] = uB + uA (i + V9_EMIN)
+    unsigned et_s;        // lean loop: shared-window address of the per-halo exponent table E[i] = uB + uA (i + V9_EMIN)
+    unsigned rowp_s;      // ... and of the row as (v_k, v_{k+1} - v_k) pairs
+    int lean0;            // lean loop allowed as far as the table's range goes (no in-table radius below r^2 = 2^-61)
+    double lean_thr;      // ... and every finite node of the (a / D)-scaled row must be smaller than this (|eps| < 2^-6)
 };
 
 // ------------------------------------------------------------------------------------------------------------------
-// v9 pixel loop (round 2).  ncu of v8: FP64 pipe 52 % active, XU pipe 19 % (2 MUFU.RSQ64H + F2I.F64 + I2F.F64 per update),
-// 'wait' the largest stall -- the loop is one long dependent FP64 chain, so fewer FP64 instructions shorten both the pipe
-// time and the latency.  47 -> 37 FP64-pipe instructions per update, 1 XU instruction instead of 4, by
-//   * rotating (x, y) = sin(theta) (cos phi, sin phi) itself (a rotation is linear: no sth * cs, sth * sn per pixel);
-//   * log2(1+f) to degree 3 (|f| <= 2^-8: abs. error 8e-11 in log2 r^2, 3e-11 in ln r -- six orders below the 1e-6 bar);
-//   * the exponent's share of the cell coordinate, uB + uA e, from a 64-entry per-halo table in shared memory
-//     (r^2 in [2^-61, 8) on the unit sphere; anything else takes the arithmetic path);
-//   * floor(u) with one round-down add of 2^52 + 2^51 (DADD.RM) -- the cell index is the low word of the sum, its double is
-//     the sum minus the constant: no F2I / I2F;
-//   * the table row pre-multiplied by a / D at blend time;
+// Lean pixel loop (round 2, "v10").  What the profiles of v8 said (profiles/r2_shell_halos_*): the loop is NOT bound by its
+// scatter-adds -- with the REDs compiled out the kernel takes 90.0 ms instead of 94.1 -- but by instruction issue: ~100 SASS
+// instructions per 32 updates of which 47 on the FP64 pipe (2 issue cycles each), 4 on the XU pipe, 6 branches, 64-bit pointer
+// arithmetic and constant reloads, with issue slots 68 % busy.  So this loop spends as few instructions of ANY kind as the
+// arithmetic allows and has no branch in its body:
+//   * (x, y) = sin(theta) (cos phi, sin phi) is rotated directly (a rotation is linear: no sth * cs, sth * sn per pixel);
+//   * log2(1+f) to degree 3 (|f| <= 2^-8: abs. error 8e-11 in log2 r^2, 3e-11 in ln r -- four orders below the 1e-6 bar);
+//   * the exponent's share of the cell coordinate, uB + uA e, comes from a 64-entry per-halo table in shared memory
+//     (r^2 in [2^-61, 8) on the unit sphere; anything else reads a NaN entry and lands outside the table);
+//   * floor(u) with ONE round-down add of 2^52 + 2^51 (DADD.RM): the cell index is the low word of the sum, its double is
+//     the sum minus the constant -- no F2I / I2F (quarter-rate XU instructions);
+//   * the table row is pre-multiplied by a / D at blend time;
 //   * 1/sqrt(r^2) = MUFU seed + one Newton step (rel. error 1e-13);
-//   * the re-normalisation nw_vec - vec = normalise(vec + sc d) - vec expanded in eps = |vec + sc d|^2 - 1.  Both vectors
+//   * the re-normalisation nw_vec - vec = normalise(vec + sc d) - vec is expanded in eps = |vec + sc d|^2 - 1.  Both vectors
 //     are unit vectors, so vec . d = |d|^2 / 2 and eps = sc r^2 (1 + sc) needs no dot product; with
 //     dl = 1/sqrt(1 + eps) - 1 = eps (-1/2 + 3/8 eps - 5/16 eps^2) the result is sc (1 + dl) d + dl vec.  dl vec is
-//     <~ 1 % of the result, so the truncation (0.27 eps^4) is < 1e-8 of it for |eps| < 2^-6; larger eps (a displacement
-//     comparable to the halo's distance) takes the exact rsqrt path.  No cancellation, unlike fma(nx, ninv, -x).
+//     <~ 1 % of the result, so the truncation (0.27 eps^4) is < 1e-8 of it for |eps| < 2^-6.  No cancellation, unlike
+//     fma(nx, ninv, -x);
+//   * the three REDs are predicated, not branched around.
+// 37 FP64-pipe + 1 XU + ~35 other instructions per 32 updates.  A halo takes this loop only if it is provably safe for it
+// (FastHalo.lean, decided per halo): every finite node of its row is small enough that |eps| < 2^-6 anywhere in the disc
+// and its table does not reach below r^2 = 2^-61.  Other halos (displacements comparable to their distance, exotic tables)
+// take the exact loop (span_pixels_fast).  Deviations from it, all documented boundary ties: a pixel EXACTLY on the table's
+// last radial node counts as outside; cell coordinates differ by <= 4e-9 cells, so a pixel within that of a node or of the
+// table's edge may land in the neighbouring cell (same value: the interpolant is continuous) or just outside.
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int V9_EMIN = -61, V9_NE = 64;
-
-struct V9Cell { double val; bool ok; };
-
-// blended-row value at squared chord r2 (lean version of row_at_r2; same interval rule and edge handling)
-__device__ __forceinline__ double row_at_r2_v9(const FastHalo &f, double r2, bool &ok) {
-    const int hi = __double2hiint(r2);
-    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(r2));
-    const double2 t = lds_f64x2(f.t.l2_s + (((unsigned)hi >> 9) & 0x7f0u));
-    const double fr = fma(m, t.x, -1.0);
-    double p = fma(fr, c_l2p[2], c_l2p[3]);
-    p = fma(fr, p, c_l2p[4]);
-    const double lf = fma(fr, p, t.y);                                   // log2 of the mantissa
-    const unsigned ei = ((unsigned)hi >> 20) - (unsigned)(1023 + V9_EMIN);
-    double E;
-    if (__builtin_expect(ei < (unsigned)V9_NE, 1)) E = lds_f64(f.et_s + (ei << 3));
-    else E = fma(__hiloint2double(0x43300000, (hi >> 20) ^ 0x80000000) - 4503601774855167.0, f.t.uA, f.t.uB);
-    const double uu = fma(lf, f.t.uA, E);
-    double kk = __dadd_rd(uu, 6755399441055744.0);                       // 2^52 + 2^51 + floor(uu)
-    ok = true;
-    if (__builtin_expect(!((__double2hiint(kk) == 0x43380000) & ((unsigned)__double2loint(kk) <= (unsigned)f.t.nrm2)), 0)) {
-        ok = (uu == f.t.uMax);                                           // outside the table, or exactly on its last node
-        kk = __hiloint2double(0x43380000, f.t.nrm2);
-    }
-    const double tt = uu - (kk - 6755399441055744.0);
-    const unsigned ra = f.t.row_s + ((unsigned)__double2loint(kk) << 3);
-    const double v0 = lds_f64(ra);
-    return fma(tt, lds_f64(ra + 8) - v0, v0);
-}
-
-// 1/sqrt(x), positive normal x: MUFU seed (2^-22) + one Newton step -> relative error < 1e-13
-__device__ __forceinline__ double rsqrt_newton(double x) {
-    double y0;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
-    const double e = fma(-x, y0 * y0, 1.0);
-    return fma(y0 * e, 0.5, y0);
-}
-
-// one (halo, pixel) update of the v9 loop; the row holds displacement * a / D
-template <bool CHECK>
-__device__ __forceinline__ void pixel_update_v9(const FastHalo &f, double z, double dz, double dz2, double x, double y,
-                                                double *__restrict__ p0, i64 nloc8, const double *own_lo,
-                                                const double *own_hi) {
-    const double dx = x - f.vx, dy = y - f.vy;
-    const double r2 = fma(dx, dx, fma(dy, dy, dz2));                 // |vec - vec_j|^2   HealpixRunner.py:338-341
-    bool ok;
-    const double val = row_at_r2_v9(f, r2, ok);                      // :345 via ln(r_sep / a) [- ln R_com]
-    const double sc = val * rsqrt_newton(r2);                        // offset / r_sep   :345-346
-    // BaryonCorrection.py:410-411 zero beyond the model's cut; HealpixRunner.py:347 non-finite -> 0; exact zeros add nothing
-    ok = ok && (r2 < f.rcut2) && ((((unsigned)__double2hiint(sc) & 0x7fffffffu) - 1u) < 0x7fefffffu);
-    if (CHECK) ok = ok && (p0 >= own_lo) && (p0 < own_hi);
-    const double t1 = sc * r2;
-    const double eps = fma(t1, sc, t1);                              // |vec + sc d|^2 - 1
-    if (ok) {
-        double ox, oy, oz;
-        if (__builtin_expect(((unsigned)__double2hiint(eps) & 0x7fffffffu) < 0x3f900000u, 1)) {   // |eps| < 2^-6
-            const double dl = eps * fma(eps, fma(eps, -0.3125, 0.375), -0.5);
-            const double q = fma(sc, dl, sc);
-            ox = fma(q, dx, dl * x); oy = fma(q, dy, dl * y); oz = fma(q, dz, dl * z);   // :350-355
-        } else {
-            const double nx = fma(sc, dx, x), ny = fma(sc, dy, y), nz = fma(sc, dz, z);
-            const double ninv = rsqrt_pos(fma(nx, nx, fma(ny, ny, nz * nz)));
-            ox = fma(nx, ninv, -x); oy = fma(ny, ninv, -y); oz = fma(nz, ninv, -z);
-        }
-#ifdef BFG_SHELL_NO_RED   // diagnostic build: the arithmetic without its scatter-add (where does the time go?)
-        asm volatile("" :: "d"(ox), "d"(oy), "d"(oz), "l"(p0));
+#ifdef BFG_SHELL_V8
+constexpr bool SHELL_LEAN = false;     // A/B build: every halo takes the exact loop (span_pixels_fast)
 #else
-        red_add(p0, ox);
-        red_add((double *)((char *)p0 + nloc8), oy);
-        red_add((double *)((char *)p0 + 2 * nloc8), oz);
+constexpr bool SHELL_LEAN = true;
 #endif
+constexpr bool SHELL_PRESCALED = true; // the baryonify row holds displacement * a / D
+constexpr int SHELL_MAX_PAIR_NODES = 8192;   // radial axes up to this length get the (value, step) pair copy of the row (lean loop)
+constexpr int V9_EMIN = -61, V9_NE = 64;          // exponent table: entries 0 .. 63 = uB + uA (i + V9_EMIN), entry 64 = NaN
+constexpr double LEAN_EPS_MAX = 0.015625;         // 2^-6
+
+// Per-lane constants of the lean loop's log2: lane l holds entry l of a 32-entry table (bucket centre c_l = 1 + (l + 1/2) / 32 of
+// the mantissa): rc = 1 / c_l cut to 17 significant bits and lt = -log2(rc).  The loop fetches its entry from the lane whose
+// number is the top 5 mantissa bits with two warp shuffles -- no shared-memory traffic and no bank conflicts (the 128-entry
+// shared-memory table of the exact loop costs ~10 wavefronts per warp read because the indices are scattered).  rc's 16
+// mantissa bits ride in the low 16 bits of lt's low word (they perturb lt by < 2^-36).
+struct Log2Lane { int lt_hi, lt_lo; };
+
+__device__ __forceinline__ Log2Lane make_log2_lane() {
+    const int lane = threadIdx.x & 31;
+    const double c = 1.0 + ((double)lane + 0.5) * 0.03125;
+    const int m16 = (__double2hiint(1.0 / c) >> 4) & 0xffff;                       // 1/c in (1/2, 1): exponent word 0x3fe
+    const double rc = __hiloint2double(0x3fe00000 | (m16 << 4), 0);
+    const double lt = -log2(rc);
+    Log2Lane t;
+    t.lt_hi = __double2hiint(lt);
+    t.lt_lo = (__double2loint(lt) & 0xffff0000) | m16;
+    return t;
+}
+
+// One lean pixel loop over this lane's pixels p0 + it * GW, it_lo <= it < n, of a ring span ((cs, sn) = azimuth of *p0; it_lo = 1
+// when *p0 itself lies before the disc -- spans start on a sector boundary).  CONVERGENT: all 32 lanes of the warp must call it
+// together (lanes without work pass n = 0) -- the trip count is the warp's maximum, because the log2 table lives in the lanes'
+// registers.
+template <bool CHECK, int GW>
+__device__ __forceinline__ void span_pixels_lean(const FastHalo &f, const RingSeg &g, const Log2Lane &L2, double cs, double sn,
+                                                 double *__restrict__ p0, int it_lo, int n, i64 nloc8,
+                                                 const double *own_lo = nullptr, const double *own_hi = nullptr) {
+    const double z = g.z, dz = g.dz, dz2 = g.dz2, rotC = g.rotC, rotS = g.rotS;
+    const double vx = f.vx, vy = f.vy, rcut2 = f.rcut2, uA = f.t.uA;
+    const unsigned rowp_s = f.rowp_s, nrm2 = (unsigned)f.t.nrm2, et_s = f.et_s;
+    double x = g.sth * cs, y = g.sth * sn;
+    const int n_warp = __reduce_max_sync(0xffffffffu, n);
+    for (int it = 0; it < n_warp; ++it) {
+        const double dx = x - vx, dy = y - vy;
+        const double r2 = fma(dx, dx, fma(dy, dy, dz2));             // |vec - vec_j|^2   HealpixRunner.py:338-341
+        // ---- blended-row value at r2: :345 via ln(r_sep / a) [- ln R_com]
+        const int hi = __double2hiint(r2);
+        const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(r2));
+        const int src = (hi >> 15) & 31;                             // top 5 mantissa bits
+        const int w_hi = __shfl_sync(0xffffffffu, L2.lt_hi, src), w_lo = __shfl_sync(0xffffffffu, L2.lt_lo, src);
+        const double rc = __hiloint2double(((w_lo << 4) & 0x000ffff0) | 0x3fe00000, 0);
+        const unsigned ei = min(((unsigned)hi >> 20) - (unsigned)(1023 + V9_EMIN), (unsigned)V9_NE);
+        const double E = lds_f64(et_s + (ei << 3));
+        const double fr = fma(m, rc, -1.0);                          // |fr| <= 2^-6
+        double p = fma(fr, c_l2p[1], c_l2p[2]);
+        p = fma(fr, p, c_l2p[3]);
+        p = fma(fr, p, c_l2p[4]);
+        const double uu = fma(fma(fr, p, __hiloint2double(w_hi, w_lo)), uA, E);   // (ln r - r0) / step
+        const double kk = __dadd_rd(uu, 6755399441055744.0);         // 2^52 + 2^51 + floor(uu)
+        const unsigned kl = (unsigned)__double2loint(kk);
+        bool ok = (it >= it_lo) & (it < n) & (__double2hiint(kk) == 0x43380000) & (kl <= nrm2);   // a disc pixel, inside [r0, r1)
+        const double2 cell = lds_f64x2(rowp_s + (min(kl, nrm2) << 4));             // (v_k, v_{k+1} - v_k), times a / D
+        const double tt = uu - (kk - 6755399441055744.0);
+        const double val = fma(tt, cell.y, cell.x);
+        // ---- offset / r_sep   :345-346
+        double y0;
+        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(r2));
+        const double e = fma(-r2, y0 * y0, 1.0);
+        const double sc = val * fma(y0 * e, 0.5, y0);
+        // BaryonCorrection.py:410-411 zero beyond the model's cut; HealpixRunner.py:347 non-finite -> 0; exact zeros add nothing
+        ok = ok & (r2 < rcut2) & ((((unsigned)__double2hiint(sc) & 0x7fffffffu) - 1u) < 0x7fefffffu);
+        if (CHECK) ok = ok & (p0 >= own_lo) & (p0 < own_hi);
+        const double t1 = sc * r2;
+        const double eps = fma(t1, sc, t1);                          // |vec + sc d|^2 - 1
+        const double dl = eps * fma(eps, fma(eps, -0.3125, 0.375), -0.5);
+        const double q = fma(sc, dl, sc);
+        const double ox = fma(q, dx, dl * x), oy = fma(q, dy, dl * y), oz = fma(q, dz, dl * z);   // :350-355
+#ifdef BFG_SHELL_NO_RED   // diagnostic build: the arithmetic without its scatter-add (where does the time go?)
+        if (ok && ox + oy + oz == 1.2345e300) red_add(p0, ox);      // never true; keeps the arithmetic alive
+#else
+        if (ok) {
+            red_add(p0, ox);
+            red_add((double *)((char *)p0 + nloc8), oy);
+            red_add((double *)((char *)p0 + 2 * nloc8), oz);
+        }
+#endif
+        p0 += GW;
+        const double x2 = x * rotC - y * rotS;                       // advance the azimuth by GW pixels
+        y = fma(y, rotC, x * rotS);
+        x = x2;
     }
 }
 
 template <bool PAINT>
 __device__ __forceinline__ FastHalo make_fast(const TableView &T, const HaloSph &s, const HaloUpd &u, const double *row,
                                               const double2 *l2tab, const double *etab) {
+    // (the row pairs of the lean loop follow the plain row in dynamic shared memory, 16-byte aligned)
     FastHalo f;
     f.vx = s.vx; f.vy = s.vy;
     const double rc = s.rcut * s.a / s.D;
     f.rcut2 = rc * rc;
-    f.aD = PAINT ? s.scale : s.a / s.D;
+    f.aD = PAINT ? s.scale : (SHELL_PRESCALED ? 1.0 : s.a / s.D);   // baryonify: a / D is folded into the row at blend time
     f.t.uA = u.uA;
     f.t.uB = fma(2.0 * log2(s.D), u.uA, u.uB);      // log2 r_sep^2 = log2 |d|^2 + 2 log2 D
     f.t.uMax = u.uMax;
@@ -312,6 +344,11 @@ __device__ __forceinline__ FastHalo make_fast(const TableView &T, const HaloSph 
     f.t.row_s = (unsigned)__cvta_generic_to_shared(row);
     f.t.l2_s = (unsigned)__cvta_generic_to_shared(l2tab);
     f.et_s = (unsigned)__cvta_generic_to_shared(etab);
+    f.rowp_s = (unsigned)__cvta_generic_to_shared(row + ((T.n[2] + 1) & ~1));
+    // lean loop (span_pixels_lean): in-table radii must have exponents the 64-entry table covers, and
+    // |eps| = |row| (r + |row|) <= m (rmax + m) < 2^-6 with rmax = the disc's radius, m = max |row|
+    f.lean0 = (f.t.uB <= -(double)V9_EMIN * f.t.uA) ? 1 : 0;
+    f.lean_thr = 0.5 * (sqrt(fma(s.radius, s.radius, 4.0 * LEAN_EPS_MAX)) - s.radius);
     return f;   // handed to the other warps through shared memory (HaloCtx), which also keeps ptxas from re-deriving it
 }
 
@@ -355,62 +392,6 @@ __device__ __forceinline__ void span_pixels_fast(const FastHalo &f, const RingSe
         cs = c2;
     }
 }
-
-// Loop control of the staged two-chain variant below (span_pixels_fast2), kept outside the #ifdef and __host__ __device__ so that
-// bfg_test_span2_host can check on the CPU that every pixel of a lane is visited exactly once with the right azimuth.
-// The lane's pixels are p0, p0 + GW, ... < pend; (cs, sn) is the azimuth of *p0, (rotC, rotS) a step of GW pixels.  The
-// recurrence runs on (x, y) = sin(theta) (cos phi, sin phi) itself -- a rotation is linear, so the two products sth * cs,
-// sth * sn of the v8 loop are paid once per span -- and advances two independent chains by a double step per iteration.
-template <int GW, typename UPD>
-__host__ __device__ __forceinline__ void span2_walk(double cs, double sn, double sth, double rotC, double rotS, double *p0,
-                                                    const double *pend, UPD upd) {
-    const double rot2C = fma(rotC, rotC, -rotS * rotS), rot2S = 2.0 * rotC * rotS;      // two azimuth steps at once
-    double x0 = sth * cs, y0 = sth * sn;
-    double x1 = x0 * rotC - y0 * rotS, y1 = fma(y0, rotC, x0 * rotS);                    // the lane's second chain: p0 + GW
-    for (; p0 + GW < pend; p0 += 2 * GW) {
-        upd(x0, y0, p0);
-        upd(x1, y1, p0 + GW);
-        const double a0 = x0 * rot2C - y0 * rot2S, a1 = x1 * rot2C - y1 * rot2S;
-        y0 = fma(y0, rot2C, x0 * rot2S);
-        y1 = fma(y1, rot2C, x1 * rot2S);
-        x0 = a0; x1 = a1;
-    }
-    if (p0 < pend) upd(x0, y0, p0);
-}
-
-// Pixels per lane and iteration of the v9 loop: 1 = one dependent chain per lane; 2 = two independent chains (the lane's
-// pixels p and p + GW, each advanced by a double azimuth step -- span2_walk), which doubles the instruction-level
-// parallelism a warp offers its scheduler at the price of ~20 more live registers.
-#ifndef BFG_SHELL_CHAINS
-#define BFG_SHELL_CHAINS 1
-#endif
-template <bool CHECK, int GW>
-__device__ __forceinline__ void span_pixels_v9(const FastHalo &f, const RingSeg &g, double cs, double sn,
-                                               double *__restrict__ p0, const double *__restrict__ pend, i64 nloc8,
-                                               const double *own_lo = nullptr, const double *own_hi = nullptr) {
-    const double z = g.z, dz = g.dz, dz2 = g.dz2;
-#if BFG_SHELL_CHAINS == 2
-    span2_walk<GW>(cs, sn, g.sth, g.rotC, g.rotS, p0, pend, [&](double x, double y, double *p) {
-        pixel_update_v9<CHECK>(f, z, dz, dz2, x, y, p, nloc8, own_lo, own_hi);
-    });
-#else
-    const double rotC = g.rotC, rotS = g.rotS;
-    double x = g.sth * cs, y = g.sth * sn;
-    for (; p0 < pend; p0 += GW) {
-        pixel_update_v9<CHECK>(f, z, dz, dz2, x, y, p0, nloc8, own_lo, own_hi);
-        const double x2 = x * rotC - y * rotS;                       // advance the azimuth by GW pixels
-        y = fma(y, rotC, x * rotS);
-        x = x2;
-    }
-#endif
-}
-#ifdef BFG_SHELL_V8
-#define BFG_SPAN_FAST span_pixels_fast
-constexpr bool SHELL_V9 = false;
-#else
-#define BFG_SPAN_FAST span_pixels_v9
-constexpr bool SHELL_V9 = true;
-#endif
 
 // PaintProfilesShell counterpart of span_pixels_fast (HealpixRunner.py:464-481): map[p] += exp(table(ln(r_sep / a))) * SCALE,
 // non-finite read-outs (outside the table, log of a zero or negative profile) contribute nothing.
@@ -500,17 +481,82 @@ __device__ __forceinline__ i64 walk_rings_fast(const FastHalo &fh, const RingSeg
                 }
             }
         } else if (!sharded) {
-            BFG_SPAN_FAST<false, GW>(fh, g, cs, sn, rbp + g.ip_lo + li, rbp + endA, nloc8);
+            span_pixels_fast<false, GW>(fh, g, cs, sn, rbp + g.ip_lo + li, rbp + endA, nloc8);
             if (endB > 0) {
                 sincospi(((double)li + ((g.flags & 4) ? 0.5 : 0.0)) * g.inv2nr, &sn, &cs);
-                BFG_SPAN_FAST<false, GW>(fh, g, cs, sn, rbp + li, rbp + endB, nloc8);
+                span_pixels_fast<false, GW>(fh, g, cs, sn, rbp + li, rbp + endB, nloc8);
             }
-        } else {                // ring-range sharding: pixels outside the owned range are masked per lane
-            BFG_SPAN_FAST<true, GW>(fh, g, cs, sn, rbp + g.ip_lo + li, rbp + endA, nloc8, out, out + nloc);
+        } else {
+            span_pixels_fast<true, GW>(fh, g, cs, sn, rbp + g.ip_lo + li, rbp + endA, nloc8, out, out + nloc);
             if (endB > 0) {
                 sincospi(((double)li + ((g.flags & 4) ? 0.5 : 0.0)) * g.inv2nr, &sn, &cs);
-                BFG_SPAN_FAST<true, GW>(fh, g, cs, sn, rbp + li, rbp + endB, nloc8, out, out + nloc);
+                span_pixels_fast<true, GW>(fh, g, cs, sn, rbp + li, rbp + endB, nloc8, out, out + nloc);
             }
+        }
+    }
+    return done;
+}
+
+// Ring walk of the lean loop: the same assignment of rings to lane groups as walk_rings_fast, but written CONVERGENT -- every
+// lane of the warp reaches every span_pixels_lean call, lanes without a ring (or without a wrap-around span) with n = 0.
+template <int GW>
+__device__ __forceinline__ i64 walk_rings_lean(const FastHalo &fh, const Log2Lane &L2, const RingSeg *__restrict__ segs, int nseg,
+                                               bool sharded, const double2 *__restrict__ eq, double *__restrict__ out, i64 nloc,
+                                               i64 nloc8) {
+    constexpr int NG = 32 / GW;
+    const int lane = threadIdx.x & 31;
+    const int li = lane & (GW - 1), gi = lane / GW;
+    i64 done = 0;
+    for (int rb0 = (threadIdx.x >> 5) * NG; rb0 < nseg; rb0 += (SHELL_THREADS / 32) * NG) {   // warp-uniform
+        const int r = rb0 + gi;
+        const RingSeg &g = segs[min(r, nseg - 1)];
+        const bool have = (r < nseg) && g.active;
+        const int cnt = have ? g.cnt : 0;
+        // span A: [ip_lo, min(ip_lo + cnt, nr)); span B (disc straddles phi = 0): [0, ip_lo + cnt - nr).
+        // Span A is walked from the 32-byte sector boundary at or before ip_lo (ring starts are multiples of 4 pixels), so that
+        // every RED of a lane group covers whole sectors of the offsets array: the L2 atomic unit is what binds this kernel
+        // (84 % busy), and an unaligned 16-lane group touches 5 sectors instead of 4.  Lanes before ip_lo idle for one iteration.
+        const int endA = min(g.ip_lo + cnt, g.nr);
+        const int endB = g.ip_lo + cnt - g.nr;
+#ifdef BFG_SHELL_NO_ALIGN   // A/B build
+        const int s_al = 0;
+#else
+        const int s_al = g.ip_lo & 3;
+#endif
+        const int first = g.ip_lo - s_al + li;
+        const int itA = (li < s_al) ? 1 : 0;
+        const int nA = have ? max(0, (endA - first + GW - 1) / GW) : 0;
+        const int nB = (have && endB > li) ? (endB - li + GW - 1) / GW : 0;
+        const bool straddles = have && (g.flags & 1);
+        if (!straddles) {
+            done += max(0, nA - itA) + nB;
+        } else {   // updates of this ring owned by this lane (the pixel loop itself carries no counter)
+            int ip = g.ip_lo + li;
+            if (ip >= g.nr) ip -= g.nr;
+            for (int i = li; i < cnt; i += GW) {
+                done += ((unsigned long long)(g.lbase + ip) < (unsigned long long)nloc) ? 1 : 0;
+                ip += GW;
+                if (ip >= g.nr) ip -= g.nr;
+            }
+        }
+        double cs = 1.0, sn = 0.0;
+        if (have) {
+            if (g.flags & 2) {      // equatorial: rotate the staged (c0, s0) (azimuth of pixel ip_lo) by li - s_al pixels
+                const double2 e = eq[3 + li - s_al];
+                cs = g.c0 * e.x - g.s0 * e.y;
+                sn = fma(g.s0, e.x, g.c0 * e.y);
+            } else {
+                sincospi(fma((double)(li - s_al), g.inv2nr, g.phase0), &sn, &cs);
+            }
+        }
+        double *rbp = out + g.lbase;
+        const bool any_straddle = sharded && __any_sync(0xffffffffu, straddles);   // warp-uniform
+        if (!any_straddle) span_pixels_lean<false, GW>(fh, g, L2, cs, sn, rbp + first, itA, nA, nloc8);
+        else span_pixels_lean<true, GW>(fh, g, L2, cs, sn, rbp + first, itA, nA, nloc8, out, out + nloc);
+        if (__any_sync(0xffffffffu, nB > 0)) {
+            if (nB > 0) sincospi(((double)li + ((g.flags & 4) ? 0.5 : 0.0)) * g.inv2nr, &sn, &cs);
+            if (!any_straddle) span_pixels_lean<false, GW>(fh, g, L2, cs, sn, rbp + li, 0, nB, nloc8);
+            else span_pixels_lean<true, GW>(fh, g, L2, cs, sn, rbp + li, 0, nB, nloc8, out, out + nloc);
         }
     }
     return done;
@@ -530,6 +576,7 @@ k_shell_halos(TableView T, Hpx h, i64 n_halo, const double *__restrict__ halos, 
     __shared__ double2 l2tab[BFG_LOG2_TAB];
     __shared__ int s_cnt[SHELL_THREADS / 32];
     load_log2_table(l2tab, g_l2tab);   // visible after the first __syncthreads() below
+    const Log2Lane L2 = make_log2_lane();
     const int lane = threadIdx.x & 31;
     const i64 nloc = pix_hi - pix_lo;
     i64 nloc8 = nloc * 8;
@@ -538,11 +585,14 @@ k_shell_halos(TableView T, Hpx h, i64 n_halo, const double *__restrict__ halos, 
     // path needs the offsets 0 .. GW-1 of its lane group instead, tabulated once for both group widths
     double eqC, eqS;
     sincospi((double)lane * (2.0 / (double)h.nl4), &eqS, &eqC);
-    __shared__ double2 s_eq[GW_SMALL + GW_LARGE];
+    // rotation by k pixels of an equatorial ring, k = -3 .. GW-1, for both group widths (entry k + 3 of each set): the lean
+    // walk starts its spans on a 32-byte sector boundary, up to 3 pixels before the first pixel of the disc
+    __shared__ double2 s_eq[(GW_SMALL + 3) + (GW_LARGE + 3)];
     __shared__ HaloCtx s_ctx;
-    __shared__ double s_etab[V9_NE];   // v9 loop: uB + uA * exponent, per halo
-    if (FAST && threadIdx.x < GW_SMALL + GW_LARGE) {
-        const int k = (threadIdx.x < GW_SMALL) ? threadIdx.x : threadIdx.x - GW_SMALL;
+    __shared__ double s_etab[V9_NE + 1];   // lean loop: uB + uA * exponent per halo; the last entry stays NaN
+    if (threadIdx.x == 0) s_etab[V9_NE] = CUDART_NAN;
+    if (FAST && threadIdx.x < (GW_SMALL + 3) + (GW_LARGE + 3)) {
+        const int k = ((threadIdx.x < GW_SMALL + 3) ? threadIdx.x : threadIdx.x - (GW_SMALL + 3)) - 3;
         double sk, ck;
         sincospi((double)k * (2.0 / (double)h.nl4), &sk, &ck);
         s_eq[threadIdx.x] = make_double2(ck, sk);
@@ -572,7 +622,7 @@ k_shell_halos(TableView T, Hpx h, i64 n_halo, const double *__restrict__ halos, 
                     if (FAST) {
                         const FastHalo f0 = make_fast<PAINT>(T, s0, u0, row, l2tab, s_etab);
                         if (lane == 0) s_ctx.fh = f0;
-                        if (SHELL_V9 && !PAINT) {
+                        if (!PAINT) {
 #pragma unroll
                             for (int i = lane; i < V9_NE; i += 32) s_etab[i] = fma((double)(i + V9_EMIN), f0.t.uA, f0.t.uB);
                         }
@@ -589,9 +639,13 @@ k_shell_halos(TableView T, Hpx h, i64 n_halo, const double *__restrict__ halos, 
         const HaloSph s = load_halo(halos + j * BFG_HALO_STRIDE);
         const DiscRings d = s_ctx.d;
         bool valid;
-        // v9 baryonify loop: the row holds displacement * a / D (the unit-sphere offset per unit chord is row / |d|)
-        constexpr bool PRESCALED = FAST && !PAINT && SHELL_V9;
-        blend_row(T, s.lnz, s.lnM, extras ? extras + j * n_extra : nullptr, row, valid, PRESCALED ? s.a / s.D : 1.0);
+        // fast baryonify loops: the row holds displacement * a / D (the unit-sphere offset per unit chord is row / |d|)
+        constexpr bool PRESCALED = FAST && !PAINT && SHELL_PRESCALED;
+        // (value, step) pairs for the lean loop, unless the radial axis is too long for a second copy in shared memory
+        const bool pairs = PRESCALED && T.n[2] <= SHELL_MAX_PAIR_NODES;
+        if (pairs) blend_row_pairs(T, s.lnz, s.lnM, extras ? extras + j * n_extra : nullptr, row,
+                                   (double2 *)(row + ((T.n[2] + 1) & ~1)), valid, s.a / s.D);
+        else blend_row(T, s.lnz, s.lnM, extras ? extras + j * n_extra : nullptr, row, valid, PRESCALED ? s.a / s.D : 1.0);
         HaloUpd u = s_ctx.u;
         if (PRESCALED) u.a = u.D;       // generic update on a prescaled row: sc = (row * D) / r_sep   (the < 4-pixel fallback)
         HaloUpd u2 = u;
@@ -603,10 +657,20 @@ k_shell_halos(TableView T, Hpx h, i64 n_halo, const double *__restrict__ halos, 
         }
         FastHalo fh;
         const bool gw_small = s_ctx.gw_small != 0;
+        int lean_bad = 0;   // this thread saw a finite row node too large for the lean loop's series (span_pixels_lean)
         if (FAST) {
             fh = s_ctx.fh;
-            const double2 e = gw_small ? s_eq[lane & (GW_SMALL - 1)] : s_eq[GW_SMALL + (lane & (GW_LARGE - 1))];
+            const double2 e = gw_small ? s_eq[3 + (lane & (GW_SMALL - 1))] : s_eq[(GW_SMALL + 3) + 3 + (lane & (GW_LARGE - 1))];
             eqC = e.x; eqS = e.y;
+            if (PRESCALED && SHELL_LEAN && pairs) {
+                if (!fh.lean0) lean_bad = 1;
+                for (int k = threadIdx.x; k < T.n[2]; k += SHELL_THREADS) {   // the nodes this thread blended itself
+                    const double av = fabs(row[k]);
+                    if (av >= fh.lean_thr && av < CUDART_INF) lean_bad = 1;
+                }
+            } else {
+                lean_bad = 1;
+            }
         }
         // `if pixind.size < 4` (HealpixRunner.py:333) can only trigger for discs of a few pixels (<= ~12 rings)
         const bool tiny = !PAINT && (s.radius * s.radius * (double)h.npix * 0.25 < 64.0);
@@ -668,13 +732,18 @@ k_shell_halos(TableView T, Hpx h, i64 n_halo, const double *__restrict__ halos, 
                 }
                 segs[threadIdx.x] = g;
             }
-            __syncthreads();  // segments + row ready
+            const bool lean = !__syncthreads_or(lean_bad);   // barrier: segments + row ready; and is the halo fit for the lean loop?
             const int nseg = (int)min((i64)RING_CHUNK, d.rb - base + 1);
 
             // ---- fast path: each warp walks 32 / GW rings at once, GW lanes per ring ------------------------------------
             if (FAST) {
-                if (gw_small) done += walk_rings_fast<GW_SMALL, PAINT>(fh, segs, nseg, valid, sharded, eqC, eqS, out, nloc, nloc8);
-                else done += walk_rings_fast<GW_LARGE, PAINT>(fh, segs, nseg, valid, sharded, eqC, eqS, out, nloc, nloc8);
+                if (!PAINT && lean && valid) {   // block-uniform
+                    if (gw_small) done += walk_rings_lean<GW_SMALL>(fh, L2, segs, nseg, sharded, s_eq, out, nloc, nloc8);
+                    else done += walk_rings_lean<GW_LARGE>(fh, L2, segs, nseg, sharded, s_eq + (GW_SMALL + 3), out, nloc, nloc8);
+                } else {
+                    if (gw_small) done += walk_rings_fast<GW_SMALL, PAINT>(fh, segs, nseg, valid, sharded, eqC, eqS, out, nloc, nloc8);
+                    else done += walk_rings_fast<GW_LARGE, PAINT>(fh, segs, nseg, valid, sharded, eqC, eqS, out, nloc, nloc8);
+                }
             }
             // ---- generic path: warps take rings round-robin; lanes walk consecutive pixels ------------------------
             // static round-robin: neighbouring rings have neighbouring lengths, so the 4 warps stay balanced without a
@@ -903,6 +972,9 @@ int launch_shell(const bfg_table *t, int nside, i64 n_halo, const double *d_halo
     if (d_nupdates) BFG_CUDA_OK(cudaMemsetAsync(d_nupdates, 0, sizeof(i64), st));
     if (n_halo == 0 || pix_lo == pix_hi) return BFG_OK;
     size_t smem = sizeof(double) * (t->view.n[2] + (MODE == MODE_ANIS ? t2->view.n[2] : 0));
+    // baryonify: the row once more as (value, step) pairs behind the plain row (fast loops, blend_row_pairs)
+    if (MODE == MODE_BARYONIFY && t->view.n[2] <= SHELL_MAX_PAIR_NODES)
+        smem = sizeof(double) * (((t->view.n[2] + 1) & ~1) + 2 * (size_t)t->view.n[2]);
     BFG_REQUIRE(smem <= 200 * 1024, "radial axis too long for the shared-memory row (max 25600 nodes)");
     int sms = 148;
     BFG_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, t->device));
@@ -1237,34 +1309,4 @@ extern "C" int bfg_shell_regrid_p2p(int nside, const double *d_map_in, const dou
     return BFG_OK;
 }
 
-namespace {
-struct VisitRecorder {
-    double *base; int32_t *visits; double *xy;
-    __host__ __device__ void operator()(double x, double y, double *p) const {
-        const int64_t off = p - base;
-        visits[off] += 1;
-        xy[2 * off] = x; xy[2 * off + 1] = y;
-    }
-};
-}  // namespace
 
-// Unit-test entry, HOST side, for the loop control of the staged two-chain pixel loop (span2_walk): one lane of a `gw`-lane
-// group walks a span of n_span pixels starting at its own pixel `li`; for every visit it records the pixel offset and the
-// (x, y) handed to the update.  h_visits [n_span]: number of visits per pixel; h_xy [n_span][2]: the (x, y) of the last visit.
-extern "C" int bfg_test_span2_host(int gw, int li, int64_t n_span, double phi_first, double dphi_pixel, double sth,
-                                   int32_t *h_visits, double *h_xy) {
-    BFG_REQUIRE((gw == 8 || gw == 16) && li >= 0 && li < gw && n_span >= 0 && h_visits && h_xy, "bad argument");
-    for (int64_t i = 0; i < n_span; ++i) { h_visits[i] = 0; h_xy[2 * i] = 0.0; h_xy[2 * i + 1] = 0.0; }
-    if (li >= n_span) return BFG_OK;
-    double *base = h_xy;                               // any array works as the pointer space: offsets are what matters
-    const double cs = cos(phi_first + li * dphi_pixel), sn = sin(phi_first + li * dphi_pixel);
-    const double rotC = cos(gw * dphi_pixel), rotS = sin(gw * dphi_pixel);
-    const VisitRecorder upd{base, h_visits, h_xy};
-    // the pointer arithmetic of the kernel: p0 = span start + li, pend = span end, stride gw (here scaled by 1 double per pixel;
-    // the visit records use a side array, so the walk itself never writes through p)
-    double *p0 = base + li;
-    const double *pend = base + n_span;
-    if (gw == 8) span2_walk<8>(cs, sn, sth, rotC, rotS, p0, pend, upd);
-    else span2_walk<16>(cs, sn, sth, rotC, rotS, p0, pend, upd);
-    return BFG_OK;
-}

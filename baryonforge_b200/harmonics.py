@@ -2,9 +2,10 @@
 C_l of a HEALPix shell on the device -- `hp.anafast(map)`, the measurement that follows BaryonifyShell.process() in the
 reference's workflow (/root/reference/examples/04_Baryonify_Density_Shell.ipynb cell 18).
 
-STAGED: the kernels (csrc/sht_kernels.cu) were written after the GPU budget of round 1 was spent; they compile but have not run
-on a GPU yet, and tests/test_gpu_harmonics.py is gated behind BFG_TEST_EXPERIMENTAL=1.  The algorithm
-is the one of oracle/anafast_rings.py.  healpy's defaults: lmax = 3 nside - 1, iter = 3, unit ring weights.  No CPU fallback.
+The algorithm is the ring route of oracle/anafast_rings.py (per-ring DFTs + a rescaled Legendre recursion in l), with healpy's
+defaults: lmax = 3 nside - 1, iter = 3, unit ring weights.  First run on a B200 in round 2: tests/test_gpu_harmonics.py (the
+dense definition at NSIDE <= 8, the ring-route oracle up to NSIDE = 128, underflow at NSIDE = 512).  PARITY UNPINNED at the
+healpy boundary (healpy is absent here and the reference's tests hold no C_l vector).  No CPU fallback.
 """
 import numpy as np
 

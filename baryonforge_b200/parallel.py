@@ -17,7 +17,7 @@ results here are independent of the number of ranks up to fp64 summation order (
 """
 import numpy as np
 
-__all__ = ['pixel_ranges', 'plane_ranges', 'ring_of_pixel', 'halos_touching_pixel_range', 'halos_touching_planes',
+__all__ = ['single_node_group', 'SegmentsExhausted', 'pixel_ranges', 'plane_ranges', 'ring_of_pixel', 'halos_touching_pixel_range', 'halos_touching_planes',
            'reduce_partial_map', 'gather_owned_ranges', 'init_from_env', 'PeerSlices', 'SharedHostMaps', 'SimpleParallel',
            'SplitJoinParallel', 'snapshot_slab', 'deposit_ngp_all']
 
@@ -182,6 +182,38 @@ def gather_owned_ranges(owned, total):
     return torch.cat([p[:n] for p, n in zip(parts, sizes)])
 
 
+_SINGLE_NODE = {}
+
+
+def single_node_group():
+    """True when every rank of the default process group runs on THIS machine (same hostname and boot id), i.e. CUDA IPC
+    handles and /proc/<pid>/fd paths are meaningful between the ranks.  Collective; cached per process group size."""
+    import os
+    import socket
+    dist = _dist()
+    if dist is None:
+        return True
+    key = (dist.get_world_size(), dist.get_rank())
+    if key not in _SINGLE_NODE:
+        lws = os.environ.get("LOCAL_WORLD_SIZE")
+        try:
+            boot = open("/proc/sys/kernel/random/boot_id").read().strip()
+        except OSError:
+            boot = ""
+        mine = (socket.gethostname(), boot, os.environ.get("BFG_FAKE_NODE", ""))
+        got = [None] * dist.get_world_size()
+        dist.all_gather_object(got, mine)
+        same = all(g == got[0] for g in got)
+        if lws is not None and int(lws) != dist.get_world_size():
+            same = False
+        _SINGLE_NODE[key] = same
+    return _SINGLE_NODE[key]
+
+
+class SegmentsExhausted(RuntimeError):
+    """Every shared host segment is still referenced by a result map of an earlier process() call (raised on ALL ranks)."""
+
+
 class PeerSlices(object):
     """
     Each rank's slice of a sharded output map, allocated IPC-exportable and mapped into every other process of the box, so
@@ -206,6 +238,7 @@ class PeerSlices(object):
         dist.all_gather(allh, mine)
         self._peers = []
         ptrs = []
+        ok = 1
         for r in range(world):
             if r == rank:
                 ptrs.append(own.value)
@@ -213,9 +246,17 @@ class PeerSlices(object):
             raw = bytes(allh[r].cpu().tolist())
             buf = (C.c_ubyte * 64).from_buffer_copy(raw)
             p = C.c_void_p()
-            _lib.check(L.bfg_ipc_import(buf, C.byref(p)))
+            if L.bfg_ipc_import(buf, C.byref(p)) != 0:   # e.g. the peer lives on another node / no P2P between the GPUs
+                ok = 0
+                break
             self._peers.append(p)
             ptrs.append(p.value)
+        # every rank must have mapped every peer before anybody launches a kernel that writes peer memory
+        vote = torch.tensor([ok], dtype=torch.int32, device=mine.device)
+        dist.all_reduce(vote, op=dist.ReduceOp.MIN)
+        if int(vote.cpu()[0]) == 0:
+            self.close()
+            raise OSError("peer slices could not be mapped by every rank (CUDA IPC); use the all-reduce exchange")
         self.h_bounds = (C.c_int64 * (world + 1))(*self.bounds)
         self.h_slices = (C.c_void_p * world)(*ptrs)
 
@@ -310,8 +351,9 @@ class SharedHostMaps(object):
         common = flags.cpu().tolist()
         idx = next((i for i, f in enumerate(common) if f), None)
         if idx is None:
+            # len(self.segs) is the same on every rank (segments are created collectively), so all ranks raise together
             if len(self.segs) >= self.MAX_SEGMENTS:
-                raise RuntimeError(f"{self.MAX_SEGMENTS} result maps of earlier process() calls are still referenced")
+                raise SegmentsExhausted(f"{self.MAX_SEGMENTS} result maps of earlier process() calls are still referenced")
             idx = self._new_segment()
         self.segs[idx]['free'] = False
         return idx, self.segs[idx]['addr']

@@ -534,17 +534,29 @@ class BaryonifyShell(DefaultRunner):
             return None
         if dist.get_backend() != "nccl":
             return None
-        from .parallel import pixel_ranges, PeerSlices
+        from .parallel import pixel_ranges, PeerSlices, single_node_group
         world, rank = dist.get_world_size(), dist.get_rank()
         ranges = pixel_ranges(self.LightconeShell.NSIDE, world)
-        if tuple(ranges[rank]) != tuple(int(v) for v in self.pix_range):
+        # every rank must take the same branch below (the constructor is collective): agree on "my range is the standard one"
+        # through the group instead of deciding locally
+        if not single_node_group():              # CUDA IPC and /proc/<pid>/fd only work inside one machine
             return None
         key = (npix, world, rank, dev.index)
         if getattr(self, '_peers', None) is None or self._peers[0] != key:
-            if getattr(self, '_peers', None) is not None:
+            if getattr(self, '_peers', None) is not None and self._peers[1] is not None:
                 self._peers[1].close()
-            bounds = [r[0] for r in ranges] + [npix]
-            self._peers = (key, PeerSlices(bounds, rank, world, dev.index))
+            std = int(tuple(ranges[rank]) == tuple(int(v) for v in self.pix_range))
+            import torch
+            vote = torch.tensor([std], dtype=torch.int32, device=dev)
+            dist.all_reduce(vote, op=dist.ReduceOp.MIN)
+            peers = None
+            if int(vote.cpu()[0]) == 1:
+                bounds = [r[0] for r in ranges] + [npix]
+                try:
+                    peers = PeerSlices(bounds, rank, world, dev.index)
+                except OSError:                  # agreed by all ranks (collective vote inside): all-reduce exchange instead
+                    peers = None
+            self._peers = (key, peers)
         return self._peers[1]
 
     def _shared_host(self, npix, peers):
@@ -715,6 +727,95 @@ class BaryonifyShell(DefaultRunner):
             "ERROR in pixel regridding, sum(new_map) [%0.14e] != sum(oldmap) [%0.14e]" % (new_sum, old_sum)   # :368-370
         return out_np
 
+    def _process_sharded(self, peers):
+        """
+        Ring-range sharded end-to-end path (one process per GPU, NCCL group on one machine, `peers` = the IPC-mapped slices
+        of the new map).  Everything is enqueued without waiting for the GPU; the ranks meet at three stream-ordered points:
+          fence 1  every rank's slice of the new map is zero        -- on the side stream, hidden under the halo loop
+          fence 2  every rank's deposits have landed                 -- after the fused re-binning + exchange
+          sums     one all-reduce of [sum(new), sum(old), n_updates, n_remote] enqueued AFTER the rank's slice went to the
+                   shared host map: its completion on this rank means every rank's copy is done, so no extra barrier.
+        The map slice goes up on the side stream underneath the halo loop; each rank downloads only its own slice, into ONE
+        page-locked host map all ranks have mapped (parallel.SharedHostMaps).
+        """
+        torch = _torch()
+        import torch.distributed as dist
+        from .parallel import SegmentsExhausted, gather_owned_ranges
+        orig_map = self.LightconeShell.map
+        NSIDE = self.LightconeShell.NSIDE
+        npix = orig_map.size
+        lo, hi = self._range(npix)
+        dev = self._device()
+        L = _lib.lib()
+        prof = os.environ.get("BFG_PROFILE_E2E") == "1"
+        marks = [("start", time.perf_counter())]
+
+        def mark(name):
+            if prof:
+                torch.cuda.synchronize()
+                marks.append((name, time.perf_counter()))
+
+        with torch.cuda.device(dev):
+            main = torch.cuda.current_stream()
+            side = _side_stream(dev)
+            own = peers.own_tensor()
+            side.wait_stream(main)                   # the previous call's reads of `own` are stream-ordered before the zeroing
+            with torch.cuda.stream(side):
+                own.zero_()
+                token = torch.zeros(1, device=dev)
+                dist.all_reduce(token)               # fence 1
+                d_map = _to_device(orig_map[lo:hi], dev, dtype=np.float64)
+                ev_side = side.record_event()
+            d_off, d_n = self.offsets_on_device()    # staging, device scalar prep, owned sort, halo loop -- all enqueued on main
+            mark("halo_loop")
+            # where the result goes: a segment of the shared host map (collective choice; its tiny all-reduce runs on the side
+            # stream so that it does not queue behind the halo loop)
+            host = self._shared_host(npix, peers)
+            seg = addr = None
+            if host is not None:
+                try:
+                    with torch.cuda.stream(side):
+                        seg, addr = host.acquire()
+                except SegmentsExhausted:            # the caller still holds MAX_SEGMENTS earlier results (raised on all ranks):
+                    host = None                      # this call returns a private copy instead
+                except OSError:                      # collective failure (agreed by all ranks)
+                    self._host_maps = (self._host_maps[0], None)
+                    host = None
+            main.wait_event(ev_side)
+            d_map.record_stream(main)
+            st = _lib.current_stream()
+            d_acc = torch.zeros(4, dtype=torch.float64, device=dev)     # sum(new slice), sum(old slice), n_updates, n_remote
+            d_rem = torch.zeros(1, dtype=torch.int64, device=dev)
+            _lib.check(L.bfg_shell_regrid_p2p(NSIDE, _lib.ptr(d_map), _lib.ptr(d_off), lo, hi, peers.world, peers.rank,
+                                              peers.h_bounds, peers.h_slices, _lib.ptr(d_rem), st))
+            del d_off
+            dist.all_reduce(token)                   # fence 2
+            mark("regrid_exchange")
+            if host is not None:
+                _lib.check(L.bfg_copy_to_host_async(addr + 8 * lo, own.data_ptr(), 8 * (hi - lo), st))
+            _lib.check(L.bfg_sum_f64(own.data_ptr(), hi - lo, _lib.ptr(d_acc), st))
+            _lib.check(L.bfg_sum_f64(_lib.ptr(d_map), hi - lo, d_acc.data_ptr() + 8, st))
+            d_acc[2] = d_n.reshape(()).to(torch.float64)                # counts are < 2^53: exact as float64
+            d_acc[3] = d_rem.reshape(()).to(torch.float64)
+            dist.all_reduce(d_acc)                   # sums + "every rank's slice is in the host map"
+            if host is None:
+                d_new = gather_owned_ranges(own, npix)
+                out, out_np = _pinned_result(npix)
+                out.copy_(d_new, non_blocking=True)
+            acc = d_acc.cpu()
+            main.synchronize()
+            mark("download")
+        _give_scratch(getattr(self, '_scratch_inflight', []))
+        self._scratch_inflight = []
+        new_sum, old_sum = float(acc[0]), float(acc[1])
+        self.last_stats = dict(n_updates=int(acc[2]), new_sum=new_sum, old_sum=old_sum, sharded=True)
+        self.last_stats_remote = int(acc[3])
+        if prof:
+            self.last_timing.update({"sharded_" + b[0] + "_s": b[1] - a[1] for a, b in zip(marks[:-1], marks[1:])})
+        assert np.isclose(new_sum, old_sum), \
+            "ERROR in pixel regridding, sum(new_map) [%0.14e] != sum(oldmap) [%0.14e]" % (new_sum, old_sum)   # :368-370
+        return host.export(seg, orig_map.shape) if host is not None else out_np.reshape(orig_map.shape)
+
     def process(self):
         torch = _torch()
         orig_map = self.LightconeShell.map
@@ -731,6 +832,10 @@ class BaryonifyShell(DefaultRunner):
         L = _lib.lib()
         npix = orig_map.size
         lo, hi = self._range(npix)
+        if self.pix_range is not None:
+            peers = self._peer_slices(npix, dev)
+            if peers is not None:
+                return self._process_sharded(peers)
         prof = os.environ.get("BFG_PROFILE_E2E") == "1"
         t_start = time.perf_counter()
         with torch.cuda.device(dev):
@@ -748,60 +853,13 @@ class BaryonifyShell(DefaultRunner):
                 torch.cuda.synchronize(); t_h2d = time.perf_counter()
             st = _lib.current_stream()
             d_map_sum = None
-            peers = self._peer_slices(npix, dev) if self.pix_range is not None else None
-            if peers is not None:
-                # fused re-binning + exchange: deposits go straight to the owning rank's slice over NVLink peer memory
-                import torch.distributed as dist
-                from .parallel import gather_owned_ranges
-                own = peers.own_tensor()
-                own.zero_()
-                token = torch.zeros(1, device=dev)
-                dist.all_reduce(token)               # stream-ordered barrier: every slice is zero before any deposit
-                d_rem = torch.zeros(1, dtype=torch.int64, device=dev)
-                _lib.check(L.bfg_shell_regrid_p2p(NSIDE, _lib.ptr(d_map), _lib.ptr(d_off), lo, hi, peers.world, peers.rank,
-                                                  peers.h_bounds, peers.h_slices, _lib.ptr(d_rem), st))
-                del d_off
-                dist.all_reduce(token)               # ... and every rank's deposits have landed before the gather
-                host = self._shared_host(npix, peers)
-                if host is not None:
-                    try:
-                        seg, addr = host.acquire()
-                    except OSError:             # collective failure (agreed by all ranks): use the per-rank download
-                        self._host_maps = (self._host_maps[0], None)
-                        host = None
-                if host is not None:
-                    # every rank copies ITS slice into one page-locked host map all ranks have mapped: no device
-                    # all-gather, npix*8 bytes over PCIe in total (not per rank), all links in parallel
-                    _lib.check(L.bfg_copy_to_host_async(addr + 8 * lo, own.data_ptr(), 8 * (hi - lo), st))
-                    d_sums = torch.zeros(2, dtype=torch.float64, device=dev)
-                    _lib.check(L.bfg_sum_f64(own.data_ptr(), hi - lo, _lib.ptr(d_sums), st))
-                    _lib.check(L.bfg_sum_f64(_lib.ptr(d_map), hi - lo, d_sums.data_ptr() + 8, st))
-                    d_cnt = torch.stack([d_n.reshape(()), d_rem.reshape(())])
-                    dist.all_reduce(d_sums)
-                    sums = d_sums.cpu()
-                    cnt = d_cnt.cpu()
-                    torch.cuda.current_stream().synchronize()
-                    dist.barrier()                   # every slice has landed in the shared host map
-                    _give_scratch(getattr(self, '_scratch_inflight', []))
-                    self._scratch_inflight = []
-                    new_sum, old_sum = float(sums[0]), float(sums[1])
-                    self.last_stats = dict(n_updates=int(cnt[0]), new_sum=new_sum, old_sum=old_sum)
-                    self.last_stats_remote = int(cnt[1])
-                    assert np.isclose(new_sum, old_sum), \
-                        "ERROR in pixel regridding, sum(new_map) [%0.14e] != sum(oldmap) [%0.14e]" % (new_sum, old_sum)
-                    return host.export(seg, orig_map.shape)
-                d_new = gather_owned_ranges(own, npix)
-                d_map_sum = d_map.sum().reshape(1)
-                dist.all_reduce(d_map_sum)
-                d_map_sum = d_map_sum[0]
-                self.last_stats_remote = int(d_rem.cpu()[0])
-            else:
-                d_new = torch.zeros(npix, dtype=torch.float64, device=dev)
-                _lib.check(L.bfg_shell_regrid(NSIDE, _lib.ptr(d_map), _lib.ptr(d_off), _lib.ptr(d_new), lo, hi, st))
-                del d_off
-                if self.pix_range is not None:
-                    from .parallel import reduce_partial_map
-                    d_new, d_map_sum = reduce_partial_map(d_new, d_map)
+            # (the NVLink peer-memory exchange is _process_sharded; here: single GPU, or full-size partial maps + all-reduce)
+            d_new = torch.zeros(npix, dtype=torch.float64, device=dev)
+            _lib.check(L.bfg_shell_regrid(NSIDE, _lib.ptr(d_map), _lib.ptr(d_off), _lib.ptr(d_new), lo, hi, st))
+            del d_off
+            if self.pix_range is not None:
+                from .parallel import reduce_partial_map
+                d_new, d_map_sum = reduce_partial_map(d_new, d_map)
             d_sums = torch.zeros(2, dtype=torch.float64, device=dev)
             _lib.check(L.bfg_sum_f64(_lib.ptr(d_new), npix, _lib.ptr(d_sums), st))
             if d_map_sum is None:

@@ -33,9 +33,24 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ALG_BYTES_PER_UPDATE = 48.0        # 3 x f64 read-modify-write of pix_offsets
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_shell_halos launch of the default workload (N = 1), from the
-# `ncu --set full` capture summarised in profiles/r1_shell_halos_v8_ncu_summary.txt (9.56 GB read + 24.40 GB write)
-NCU_TRAFFIC_DEFAULT_WORKLOAD = 33.957503e9
+# Per-round ncu evidence of the dominant kernel (written by tools/ncu_summary.py --json from the round's `ncu --set full`
+# capture of THIS bench command): DRAM bytes per launch, FP64-pipe instructions per update, pipe utilisations.  bench.py
+# only reports what that file holds for the workload it is running -- nothing here is a literal.
+NCU_FACTS = os.path.join(ROOT, "profiles", "shell_halos_ncu_facts.json")
+B200_SMS = 148
+FP64_LANES_PER_SM_CLK = 64         # 4 sub-partitions x 16 lanes: one FP64 warp instruction per 2 cycles per scheduler
+
+
+def ncu_facts(workload):
+    """The committed ncu facts for `workload` (exact string match on config.workload), else {}."""
+    try:
+        facts = json.load(open(NCU_FACTS))
+    except Exception:
+        return {}
+    for f in facts.get("captures", []):
+        if f.get("workload") == workload:
+            return f
+    return {}
 
 
 def parse():
@@ -356,15 +371,64 @@ def run_b200(args):
         n_up = float(n_up_local)
     ms_step = ms_total / args.steps
     value = n_up / (ms_step * 1e-3)
-    sums = d_sums.cpu().numpy()
-    assert np.isclose(sums[0], sums[1] if world == 1 else sums[0]), "mass not conserved"
+    # mass conservation of the timed step (HealpixRunner.py:368-370): sum(new map) == sum(old map) over ALL ranks
+    d_chk = d_sums.clone()
+    if world > 1:
+        if peers is not None and args.owned_result:
+            dist.all_reduce(d_chk)                   # both entries are per-slice sums
+        else:
+            dist.all_reduce(d_chk[1:])               # the new map was gathered / all-reduced: only the old map's sum is partial
+    sums = d_chk.cpu().numpy()
+    assert np.isclose(sums[0], sums[1], rtol=1e-9), f"mass not conserved: {sums[0]!r} != {sums[1]!r}"
     n_launch = launches[0]
+
+    # ---- N > 1: is the sharded result the single-GPU result?  (driver-visible multi-GPU parity) ------------------------
+    # Rank 0 recomputes the shell un-sharded on its own GPU (same seeds, same kernels, pix range = whole map) outside the
+    # timed region and compares it with the map the sharded step produced: every pixel of a strided sample + the sums.
+    parity_vs_n1 = None
+    sample_stride = max(1, npix // 200000)
+    step_sample = None if world > 1 else d_new[::sample_stride].clone()
+    if world > 1:
+        if peers is not None:
+            sharded = parallel.gather_owned_ranges(own, npix)
+        else:
+            sharded = d_new
+        step_sample = sharded[::sample_stride].clone()
+        if rank == 0:
+            d_map_full = pinned_map.to(dev)
+            d_off_full = torch.zeros((3, npix), dtype=torch.float64, device=dev)
+            d_ref = torch.zeros(npix, dtype=torch.float64, device=dev)
+            d_n1 = torch.zeros(1, dtype=torch.int64, device=dev)
+            _lib.check(L.bfg_halo_sort(0, n_rec, d_rec.data_ptr(), d_rec_sorted.data_ptr(), None, None, 0,
+                                       b.runners.SKY_BAND_RAD, 0.0, 3, st))
+            _lib.check(L.bfg_shell_offsets(table.handle, nside, n_rec, d_rec_sorted.data_ptr(), None, 0, d_off_full.data_ptr(),
+                                           0, npix, d_n1.data_ptr(), st))
+            _lib.check(L.bfg_shell_regrid(nside, d_map_full.data_ptr(), d_off_full.data_ptr(), d_ref.data_ptr(), 0, npix, st))
+            stride = max(1, npix // 200000)
+            a_s, r_s = sharded[::stride], d_ref[::stride]
+            scale = float(r_s.abs().max())
+            err = float(((a_s - r_s).abs() / (r_s.abs() + 1e-3 * scale)).max())
+            parity_vs_n1 = {"max_rel_err": err, "n_sample": int(a_s.numel()), "stride": int(stride),
+                            "sum_rel_err": float(abs(float(sharded.sum()) - float(d_ref.sum())) / abs(float(d_ref.sum()))),
+                            "n_updates_equal": bool(int(d_n1.cpu()[0]) == int(n_up)),
+                            "what": "new map of the sharded step vs the same shell computed un-sharded on rank 0's GPU"}
+            assert err < 1e-9 and parity_vs_n1["n_updates_equal"], f"sharded result differs from N=1: {parity_vs_n1}"
+            del d_map_full, d_off_full, d_ref
+        del sharded
+        torch.cuda.empty_cache()
+        dist.barrier()
 
     # ---- end-to-end through the reference-shaped API -------------------------------------------------------
     e2e = None
     if not args.no_e2e:
         for _ in range(2):
-            runner.process()
+            out = runner.process()
+        # the API result must be the device-resident step's result (same map on every rank at N > 1)
+        ref_s = step_sample.cpu().numpy()
+        got_s = np.asarray(out)[::sample_stride]
+        e2e_err = float(np.max(np.abs(got_s - ref_s) / (np.abs(ref_s) + 1e-3 * np.max(np.abs(ref_s)))))
+        assert e2e_err < 1e-9, f"process() result differs from the device-resident step: {e2e_err}"
+        del out
         barrier()
         t0 = time.perf_counter()
         n_e2e = 3
@@ -383,7 +447,7 @@ def run_b200(args):
                "h2d_bytes_per_step": int(npix * 8 + world * 6 * n_rec * 8), "d2h_bytes_per_step": int(npix * 8),
                "bytes_note": "whole job: every rank uploads its map slice + the 6 catalogue columns and downloads its slice of the new map",
                "ms_per_step": 1e3 * float(tt[0]), "host_prep_ms": 1e3 * runner.last_timing.get("host_prep_s", 0.0),
-               "host_threads": b.runners._host_threads(),
+               "host_threads": b.runners._host_threads(), "parity_vs_device_step": e2e_err,
                "iter_ms": iter_ms, "phases_ms": {k: round(1e3 * v, 2) for k, v in runner.last_timing.items()},
                "includes": "host staging of raw catalogue columns + numpy ln(1+z), ln M; H2D (pinned map + 6 columns); device scalar prep, sort, halo loop, re-binning, exchange (N>1); D2H of the new map"}
 
@@ -427,7 +491,23 @@ def run_b200(args):
             dist.destroy_process_group()
         return
     peak, peak_src = peaks()
-    achieved = ALG_BYTES_PER_UPDATE * (n_up_local if world == 1 else n_up / world) / (ms_kernel * 1e-3) / 1e9
+    upd_per_launch = n_up_local if world == 1 else n_up / world
+    achieved = ALG_BYTES_PER_UPDATE * upd_per_launch / (ms_kernel * 1e-3) / 1e9
+    facts = ncu_facts(workload_name(args)) if world == 1 else {}
+    # The resource that binds this kernel (profiles/README.md, round 2): the FP64 pipe / instruction issue, not HBM.  The
+    # ceiling is what the FP64 pipe could do if it issued nothing but this loop's FP64 instructions, at the SM clock measured
+    # DURING the timed region: SMs x 64 FP64 lanes per clock x clock / (FP64-pipe instructions per update, counted in the
+    # committed SASS of the pixel loop).
+    fp64_per_upd = facts.get("fp64_inst_per_update")
+    sm_mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz")
+    binding = {"resource": "FP64 pipe (instruction issue)", "fp64_inst_per_update": fp64_per_upd,
+               "fp64_inst_source": facts.get("fp64_inst_source"), "sm_clock_mhz": sm_mhz}
+    if fp64_per_upd and sm_mhz:
+        ceil_ups = B200_SMS * FP64_LANES_PER_SM_CLK * sm_mhz * 1e6 / fp64_per_upd
+        binding.update({"fp64_ceiling_updates_s": ceil_ups,
+                        "frac_fp64": upd_per_launch / (ms_kernel * 1e-3) / ceil_ups,
+                        "ncu_fp64_pipe_active_pct": facts.get("fp64_pipe_active_pct"),
+                        "ncu_issue_active_pct": facts.get("issue_active_pct")})
     line = {"metric": "halo-pixel updates/s (BaryonifyShell)", "value": value, "unit": "halo-pixel updates/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -442,18 +522,18 @@ def run_b200(args):
             "clocks": clocks, "gpu_launches": n_launch,
             "roofline": {"bound": "hbm", "kernel": "k_shell_halos<baryonify> (fused disc/separation/table/accumulate)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": (NCU_TRAFFIC_DEFAULT_WORKLOAD if (world == 1 and args.nside == 4096 and
-                                                                      args.halos == 1000000 and args.eps == 20.0 and
-                                                                      not args.mass_function and not args.no_sort)
-                                     else None),
+                         "traffic": facts.get("dram_bytes_per_launch"), "traffic_source": facts.get("source"),
                          "peak_source": peak_src, "alg_bytes_per_update": ALG_BYTES_PER_UPDATE,
-                         "alg_bytes_per_launch": ALG_BYTES_PER_UPDATE * (n_up_local if world == 1 else n_up / world),
-                         "kernel_ms": ms_kernel,
-                         "note": "algorithmic bytes = the reference dataflow's 3 f64 read-modify-writes per update; with "
-                                 "sky-ordered halos ~96 % of those REDs are absorbed by the 126 MB L2 (ncu traffic 34.0 GB vs "
-                                 "852 GB algorithmic), so frac can exceed 1 and the kernel's real limiter is the FP64 pipe "
-                                 "(52.0 % active, 45 FP64 instructions per update) + issue slots (65.8 %); see profiles/README.md"},
+                         "alg_bytes_per_launch": ALG_BYTES_PER_UPDATE * upd_per_launch,
+                         "kernel_ms": ms_kernel, "binding": binding,
+                         "note": "algorithmic bytes = the reference dataflow's 3 f64 read-modify-writes per update (SURVEY 8d). "
+                                 "With sky-ordered halos those REDs are absorbed by the 126 MB L2 (`traffic` = measured DRAM "
+                                 "bytes of one launch, ~1/25 of algorithmic), so `frac` can exceed 1 and says nothing about "
+                                 "efficiency; the binding resource is the FP64 pipe / instruction issue -- read "
+                                 "`binding.frac_fp64`"},
             "e2e": e2e, "particles": particles}
+    if parity_vs_n1 is not None:
+        line["parity_vs_n1"] = parity_vs_n1
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, cat, model, axes, vals, args.cpu_sample)
     emit(line)

@@ -348,12 +348,6 @@ int bfg_halo_sort_owned(int nside, int64_t pix_lo, int64_t pix_hi, int64_t n_hal
 int bfg_sum_f64(const double *d_x, int64_t n, double *d_out, void *stream);
 /* Unit-test entry for the table-driven log2 used inside the pixel loops: d_out[i] = log2(d_x[i]). */
 int bfg_test_fast_log2(int64_t n, const double *d_x, double *d_out, void *stream);
-/* Unit-test entry on the HOST for the loop control of the staged two-chain pixel loop (-DBFG_SHELL_UNROLL2, span2_walk in
- * csrc/shell_kernels.cu): lane `li` of a `gw`-lane group (8 or 16) walks a span of n_span pixels whose first pixel sits at azimuth
- * phi_first, dphi_pixel apart, on a ring with sin(theta) = sth.  h_visits [n_span] counts the visits per pixel, h_xy [n_span][2]
- * holds the (x, y) = sth (cos phi, sin phi) handed to the update of each visited pixel. */
-int bfg_test_span2_host(int gw, int li, int64_t n_span, double phi_first, double dphi_pixel, double sth, int32_t *h_visits,
-                        double *h_xy);
 /* out[i][c] = in[c][i] : component-major offsets -> the reference's (n, ncomp) layout, for tests. */
 int bfg_transpose_offsets(const double *d_in, double *d_out, int64_t n, int ncomp, void *stream);
 

@@ -1,16 +1,15 @@
 """
 -m gpu parity tests of the C_l step (`hp.anafast(map)`, examples/04_Baryonify_Density_Shell.ipynb cell 18) against the oracle
-(oracle/anafast_port.py = the definition, oracle/anafast_rings.py = the ring route).  GATED: the kernels were written after the
-GPU budget of round 1 was spent and have not run yet -- set BFG_TEST_EXPERIMENTAL=1.
-"""
-import os
+(oracle/anafast_port.py = the definition, oracle/anafast_rings.py = the ring route).
 
+PARITY UNPINNED at the healpy boundary: healpy is absent from this image and the reference's tests hold no C_l vector, so the
+oracle restates `anafast`'s published algorithm (healpix_cxx map2alm_iter: lmax = 3 nside - 1, iter = 3, unit ring weights)
+and is held by analytic identities (tests/test_oracle_anafast.py: pure-Y_lm maps, Parseval, the dense definition).
+"""
 import numpy as np
 import pytest
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("BFG_TEST_EXPERIMENTAL") != "1",
-                                 reason="csrc/sht_kernels.cu is staged for its first GPU run; set BFG_TEST_EXPERIMENTAL=1")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("nside", [1, 2, 4, 8])
@@ -44,20 +43,22 @@ def test_anafast_matches_the_ring_route_oracle(nside, lmax):
 
 
 def test_high_m_near_the_poles_nside_512():
-    """lmax = 1535: lambda_mm underflows fp64 by thousands of orders near the poles; synthesis -> analysis of a band-limited
-    field must still come back (quadrature accuracy) and conserve power."""
+    """lmax = 1535, m up to 512: lambda_mm = sin^m(theta) underflows fp64 by more than a thousand orders of magnitude on the
+    polar rings; synthesis -> analysis of a field band-limited to l <= nside (where HEALPix's unit-weight quadrature with
+    iter = 3 is good to ~1e-4: oracle/anafast_rings.py gives 7e-5 / 1.4e-4 for the same construction at nside = 64) must come
+    back, without leaking into the coefficients that were zero."""
     import baryonforge_b200 as b
     nside = 512
     sh = b.harmonics.ShellHarmonics(nside)
     rng = np.random.default_rng(0)
     alm = np.zeros(sh.n_alm, dtype=np.complex128)
-    lmax_in = 1200
-    for m in (0, 1, 400, 900, 1200):
+    lmax_in = nside
+    for m in (0, 1, 200, 400, 512):
         for l in range(max(m, 2), lmax_in + 1, 37):
             alm[m * (2 * sh.lmax + 1 - m) // 2 + l] = rng.normal() + (0 if m == 0 else 1j * rng.normal())
     f = sh.alm2map(alm)
     assert np.all(np.isfinite(f))
-    back = sh.map2alm(f, iter=1)
+    back = sh.map2alm(f, iter=3)
     nz = alm != 0
     assert np.max(np.abs(back[nz] - alm[nz])) < 2e-3 * np.max(np.abs(alm))
     assert np.max(np.abs(back[~nz])) < 2e-3 * np.max(np.abs(alm))

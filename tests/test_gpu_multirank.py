@@ -50,6 +50,12 @@ def _worker(rank, world, port, q):
     nside, cat, shell, dmodel, pmodel, N, gcat, gm, gmodel = _inputs()
     pr = parallel.pixel_ranges(nside, world)[rank]
     out1 = b.BaryonifyShell(cat, shell, 20, dmodel, verbose=False, device=rank, pix_range=pr).process()
+    # the lightcone pattern `maps.append(runner.process())`: more results alive than SharedHostMaps has segments -- the calls
+    # beyond MAX_SEGMENTS fall back (collectively) to a private copy instead of raising
+    srun = b.BaryonifyShell(cat, shell, 20, dmodel, verbose=False, device=rank, pix_range=pr)
+    held = [srun.process() for _ in range(parallel.SharedHostMaps.MAX_SEGMENTS + 2)]
+    held_err = max(float(np.max(np.abs(h - out1))) for h in held)
+    del held
     out2 = b.PaintProfilesShell(cat, shell, 20, pmodel, verbose=False, device=rank, pix_range=pr).process()
     out3 = b.BaryonifyGrid(gcat, gm, 6, gmodel, verbose=False, device=rank,
                            plane_range=parallel.plane_ranges(N, world)[rank]).process()
@@ -76,6 +82,7 @@ def _worker(rank, world, port, q):
     moved = b.BaryonifySnapshot(hc, sub, g["eps_run"], smodel, verbose=False, device=rank).process()
     ngp = parallel.deposit_ngp_all([moved["x"], moved["y"], moved["z"]], moved["M"], float(g["L"]), 16, device=rank)
     err = float(np.max(np.abs(moved["x"] - g["out_x"][sel]))) if sel.size else 0.0
+    err = max(err, held_err * 1e3)          # held results equal the first one to summation order (|map| ~ 10 -> 1e-12)
     if rank == 0:
         q.put((out1, out2, out3, ngp, err, out4))
     else:

@@ -334,31 +334,3 @@ def test_out_of_table_warnings_once_per_catalogue():
     with warnings.catch_warnings():
         warnings.simplefilter("error")
         _warn_table_range(model, np.array([0.2]), np.array([1e13]))                        # in range: silent
-
-
-def test_staged_two_chain_pixel_walk_visits_every_pixel_once_with_the_right_azimuth():
-    """Loop control of the staged headline-kernel variant (-DBFG_SHELL_UNROLL2, span2_walk), compiled for the host: over all
-    lanes of a group every pixel of a span is visited exactly once, and the (x, y) handed to the update is the pixel's own
-    sin(theta) (cos phi, sin phi) -- including spans shorter than the group, odd and even pixel counts per lane, long spans."""
-    from baryonforge_b200 import _lib
-    L = _lib.lib()
-    rng = np.random.default_rng(0)
-    for gw in (8, 16):
-        for n_span in (0, 1, 3, gw - 1, gw, gw + 1, 2 * gw, 2 * gw + 5, 3 * gw, 7 * gw + 3, 105, 1000, 16384):
-            phi0, sth = rng.uniform(0, 2 * np.pi), rng.uniform(0.01, 1.0)
-            dphi = 2 * np.pi / max(n_span, 4) / rng.uniform(1.0, 3.0)
-            total = np.zeros(n_span, dtype=np.int32)
-            xy_all = np.zeros((n_span, 2))
-            for li in range(gw):
-                visits = np.zeros(max(n_span, 1), dtype=np.int32)
-                xy = np.zeros((max(n_span, 1), 2))
-                assert L.bfg_test_span2_host(gw, li, n_span, phi0, dphi, sth, visits.ctypes.data, xy.ctypes.data) == 0
-                v = visits[:n_span]
-                assert np.array_equal(np.flatnonzero(v), np.arange(li, n_span, gw))      # exactly this lane's pixels
-                total += v
-                xy_all[v > 0] = xy[:n_span][v > 0]
-            assert np.all(total == 1)
-            phi = phi0 + dphi * np.arange(n_span)
-            want = sth * np.stack([np.cos(phi), np.sin(phi)], axis=1)
-            if n_span:
-                assert np.max(np.abs(xy_all - want)) < 1e-12                             # recurrence round-off over <= 2048 steps

@@ -21,15 +21,16 @@ __device__ __forceinline__ uint64_t mix(uint64_t x) {
 }
 
 // spans handed out in "sky order": consecutive span ids are neighbours in memory (like the sky-sorted halos), with jitter
-__device__ __forceinline__ int64_t span_base(uint64_t id, int64_t n, int len, int64_t n_spans) {
+__device__ __forceinline__ int64_t span_base(uint64_t id, int64_t n, int len, int64_t n_spans, int align = 1) {
     const int64_t stride = (n - len - 64) / n_spans;
     int64_t b = (int64_t)id * stride + (int64_t)(mix(id) % (uint64_t)(8 * len + 1));
     if (b > n - len - 64) b = n - len - 64;
-    return b;
+    return b & ~(int64_t)(align - 1);          // align = 1, 4 (32-byte sector) or 16 (128-byte line) pixels
 }
 
 template <int GW>
-__global__ void __launch_bounds__(128, 7) k_red(double *out, int64_t n, int len, int64_t n_spans, unsigned long long *queue) {
+__global__ void __launch_bounds__(128, 7) k_red(double *out, int64_t n, int len, int64_t n_spans, unsigned long long *queue,
+                                                 int align) {
     const int lane = threadIdx.x & 31, li = lane & (GW - 1), gi = lane / GW;
     constexpr int NG = 32 / GW;
     for (;;) {
@@ -39,7 +40,7 @@ __global__ void __launch_bounds__(128, 7) k_red(double *out, int64_t n, int len,
         if ((int64_t)w >= n_spans) break;
         const uint64_t id = w + gi;
         if ((int64_t)id >= n_spans) continue;
-        double *p = out + span_base(id, n, len, n_spans);
+        double *p = out + span_base(id, n, len, n_spans, align);
         const double v = 1e-9 * (double)(lane + 1);
         for (int i = li; i < len; i += GW) {
             atomicAdd(p + i, v);
@@ -109,17 +110,19 @@ int main() {
     CK(cudaMemset(out, 0, 3 * n * sizeof(double)));
     CK(cudaMalloc(&queue, 8));
     const int grid = 148 * 7;
-    const int lens[] = {32, 64, 104, 128, 256};
+    const int lens[] = {48, 112, 256};
     const int64_t total_updates = 4000000000LL;  // ~ a quarter of the headline step
     for (int len : lens) {
         const int64_t n_spans = total_updates / len;
         float ms;
-        ms = time_ms([&] { k_red<8><<<grid, 128>>>(out, n, len, n_spans, queue); }, queue);
-        printf("RED  GW=8   len=%3d  %7.2f ms  %6.1f Gupd/s  %7.1f GB/s payload\n", len, ms, n_spans * len / ms * 1e-6, n_spans * len * 24.0 / ms * 1e-6);
-        ms = time_ms([&] { k_red<16><<<grid, 128>>>(out, n, len, n_spans, queue); }, queue);
-        printf("RED  GW=16  len=%3d  %7.2f ms  %6.1f Gupd/s  %7.1f GB/s payload\n", len, ms, n_spans * len / ms * 1e-6, n_spans * len * 24.0 / ms * 1e-6);
-        ms = time_ms([&] { k_red<32><<<grid, 128>>>(out, n, len, n_spans, queue); }, queue);
-        printf("RED  GW=32  len=%3d  %7.2f ms  %6.1f Gupd/s  %7.1f GB/s payload\n", len, ms, n_spans * len / ms * 1e-6, n_spans * len * 24.0 / ms * 1e-6);
+        for (int align : {1, 4, 16}) {
+            ms = time_ms([&] { k_red<8><<<grid, 128>>>(out, n, len, n_spans, queue, align); }, queue);
+            printf("RED  GW=8   align=%2d len=%3d  %7.2f ms  %6.1f Gupd/s  %7.1f GB/s payload\n", align, len, ms, n_spans * len / ms * 1e-6, n_spans * len * 24.0 / ms * 1e-6);
+            ms = time_ms([&] { k_red<16><<<grid, 128>>>(out, n, len, n_spans, queue, align); }, queue);
+            printf("RED  GW=16  align=%2d len=%3d  %7.2f ms  %6.1f Gupd/s  %7.1f GB/s payload\n", align, len, ms, n_spans * len / ms * 1e-6, n_spans * len * 24.0 / ms * 1e-6);
+            ms = time_ms([&] { k_red<32><<<grid, 128>>>(out, n, len, n_spans, queue, align); }, queue);
+            printf("RED  GW=32  align=%2d len=%3d  %7.2f ms  %6.1f Gupd/s  %7.1f GB/s payload\n", align, len, ms, n_spans * len / ms * 1e-6, n_spans * len * 24.0 / ms * 1e-6);
+        }
         ms = time_ms([&] { k_bulk<256><<<grid, 128>>>(out, n, len, n_spans, queue); }, queue);
         printf("BULK        len=%3d  %7.2f ms  %6.1f Gupd/s  %7.1f GB/s payload\n", len, ms, n_spans * len / ms * 1e-6, n_spans * len * 24.0 / ms * 1e-6);
         fflush(stdout);
@@ -132,7 +135,7 @@ int main() {
         CK(cudaMemset(a, 0, 3 * m * 8)); CK(cudaMemset(b, 0, 3 * m * 8));
         const int len = 104; const int64_t ns = 40000;
         CK(cudaMemset(queue, 0, 8));
-        k_red<32><<<grid, 128>>>(a, m, len, ns, queue);
+        k_red<32><<<grid, 128>>>(a, m, len, ns, queue, 1);
         CK(cudaMemset(queue, 0, 8));
         k_bulk<256><<<grid, 128>>>(b, m, len, ns, queue);
         CK(cudaDeviceSynchronize());
