@@ -56,7 +56,7 @@ __global__ void k_cell_fill(i64 n, const double *__restrict__ x, const double *_
     }
 }
 
-// Two-pass variant of the scatter (BFG_CELL_SORT=2, staged for measurement): with ~10^7 cells a single-pass scatter keeps
+// Two-pass scatter (the default above 65536 cells; measured 26.2 vs 29.6 ms for 2.5e8 particles): with ~10^7 cells a single-pass scatter keeps
 // ~10^7 partially written 128-byte lines open, far more than the L2 holds, so DRAM sees isolated 32-byte sector writes.
 // Pass A scatters the records into <= 65536 coarse buckets (runs of `group` consecutive cells, bucket start =
 // cell_start[bucket * group]): few enough write heads for the L2 to merge the four records of a line before it is evicted.
@@ -330,8 +330,8 @@ extern "C" int bfg_snap_build_cells(int ndim, int64_t n_part, const double *d_x,
     if (n_part > 0) {
         double4 *rec = nullptr;   // 32-byte particle records (stream-ordered scratch)
         BFG_CUDA_OK(cudaMallocAsync(&rec, sizeof(double4) * n_part, st));
-        const char *mode = getenv("BFG_CELL_SORT");
-        const bool two_pass = mode && mode[0] == '2' && ncells > 65536;
+        const char *mode = getenv("BFG_CELL_SORT");      // 1 = single-pass scatter (A/B); default: two passes above 65536 cells
+        const bool two_pass = !(mode && mode[0] == '1') && ncells > 65536;
         double4 *tmp = nullptr;
         unsigned long long *cursor_a = nullptr;
         if (two_pass) {

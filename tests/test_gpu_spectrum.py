@@ -131,8 +131,6 @@ def test_snapshot_on_device_then_pk_matches_host_path():
         assert_close(sp.measure(d_p, factor), want, f"snap_3d P(k) on device, factor {factor}", rtol=1e-3)
 
 
-@pytest.mark.skipif(__import__("os").environ.get("BFG_TEST_EXPERIMENTAL") != "1",
-                    reason="measure_runner is staged for measurement (DESIGN.md section 8); set BFG_TEST_EXPERIMENTAL=1")
 def test_pk_from_the_cell_ordered_particles_equals_the_caller_ordered_path():
     import baryonforge_b200 as b
     from baryonforge_b200 import synth

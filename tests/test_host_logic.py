@@ -242,6 +242,8 @@ def test_table_cache_is_keyed_by_identity_not_by_a_recyclable_id():
         def __init__(self, tag):
             self.interp_d = [tag]
 
+    from baryonforge_b200 import runners
+    del runners._SHARED_TABLES[:]
     cache = _TableCache()
     made = []
 
@@ -258,7 +260,9 @@ def test_table_cache_is_keyed_by_identity_not_by_a_recyclable_id():
         m = Model(k)
         t = table_for(m)
         assert t.tag == k, "stale table served for a new model"
-        assert made[-2].closed and not t.closed
+        assert not t.closed and not made[-2].closed                   # the last 8 tables stay resident (shared by all runners) ...
+        assert len(made) < 9 or made[-9].closed                       # ... older ones are released
+    assert _TableCache().get((_Ident(m), _Ident(m.interp_d)), lambda: None) is t   # another runner's cache object: same table
     m.interp_d = [99]                                                 # setup_interpolator() re-run on the same model
     assert table_for(m).tag == 99
     assert _Ident(m) == _Ident(m) and _Ident(m) != _Ident(Model(1)) and (_Ident(m), '2D') != (_Ident(m), '3D')
