@@ -54,6 +54,8 @@ _SIGNATURES = {
                            c_ptr, c_ptr, c_ptr], C.c_int),
     "bfg_shell_regrid_p2p": ([C.c_int, c_ptr, c_ptr, c_i64, c_i64, C.c_int, C.c_int, C.POINTER(c_i64), C.POINTER(c_ptr),
                               c_ptr, c_ptr], C.c_int),
+    "bfg_shell_regrid_p2p_range": ([C.c_int, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, C.c_int, C.c_int, C.POINTER(c_i64),
+                                    C.POINTER(c_ptr), c_ptr, c_ptr], C.c_int),
     "bfg_shared_alloc": ([C.POINTER(c_ptr), c_i64, C.c_int], C.c_int),
     "bfg_shared_free": ([c_ptr], C.c_int),
     "bfg_ipc_export": ([c_ptr, c_ptr], C.c_int),

@@ -81,10 +81,10 @@ def _sort_records(d_rec, d_ext, mode, p0, p1=0.0, ndim=3, owned=None):
 _SIDE_STREAMS = {}
 
 
-def _side_stream(dev):
-    """One copy stream per device (H2D of the map underneath the halo loop)."""
+def _side_stream(dev, which=0):
+    """Copy streams per device: 0 = uploads (H2D of the map underneath the halo loop), 1 = downloads of finished map parts."""
     torch = _torch()
-    key = dev.index
+    key = (dev.index, which)
     if key not in _SIDE_STREAMS:
         _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
     return _SIDE_STREAMS[key]
@@ -804,6 +804,23 @@ class BaryonifyShell(DefaultRunner):
                 torch.cuda.synchronize()
                 marks.append((name, time.perf_counter()))
 
+        # large catalogues: the chunked variant that overlaps upload, halo loop and download (same decision on every rank:
+        # it depends on the catalogue size and the environment only)
+        if (not prof and self.sort_halos and os.environ.get("BFG_PIPELINE", "1") == "1"
+                and self.HaloLightConeCatalog.cat.size >= self.PIPELINE_MIN_HALOS):
+            host = self._shared_host(npix, peers)
+            if host is not None:
+                seg = None
+                try:
+                    with torch.cuda.device(dev):
+                        seg, addr = host.acquire()
+                except SegmentsExhausted:            # raised on all ranks: the plain path below returns a private copy
+                    pass
+                except OSError:                      # collective failure (agreed by all ranks)
+                    _HOST_MAPS[(npix, peers.world, peers.rank, peers.device)] = None
+                if seg is not None:
+                    return self._process_sharded_pipelined(peers, host, seg, addr)
+
         with torch.cuda.device(dev):
             main = torch.cuda.current_stream()
             side = _side_stream(dev)
@@ -813,9 +830,10 @@ class BaryonifyShell(DefaultRunner):
                 own.zero_()
                 token = torch.zeros(1, device=dev)
                 dist.all_reduce(token)               # fence 1
+            d_off, d_n = self.offsets_on_device()    # staging, device scalar prep, owned sort, halo loop -- all enqueued on main
+            with torch.cuda.stream(side):            # after the catalogue's small copies: the copy engine serves its queue in order
                 d_map = _to_device(orig_map[lo:hi], dev, dtype=np.float64)
                 ev_side = side.record_event()
-            d_off, d_n = self.offsets_on_device()    # staging, device scalar prep, owned sort, halo loop -- all enqueued on main
             mark("halo_loop")
             # where the result goes: a segment of the shared host map (collective choice; its tiny all-reduce runs on the side
             # stream so that it does not queue behind the halo loop)
@@ -864,6 +882,170 @@ class BaryonifyShell(DefaultRunner):
         assert np.isclose(new_sum, old_sum), \
             "ERROR in pixel regridding, sum(new_map) [%0.14e] != sum(oldmap) [%0.14e]" % (new_sum, old_sum)   # :368-370
         return host.export(seg, orig_map.shape) if host is not None else out_np.reshape(orig_map.shape)
+
+    SHARD_CHUNKS = 4            # latitude chunks per rank of the pipelined sharded path
+
+    def _process_sharded_pipelined(self, peers, host, seg, addr):
+        """
+        _process_sharded with the rank's work cut into latitude chunks, so that the three things that take time at N = 8 --
+        the map slice going up, the halo loop, the new slice coming down -- overlap instead of following each other (on the
+        measured box the host link moves ~90 GB/s per direction for all GPUs together: 1.6 GB up and 1.6 GB down are 18 ms
+        each, the halo loop 12 ms).  The owned, sky-sorted halos are processed chunk by chunk; after chunk k every ring north
+        of (next chunk's first band - largest disc radius) has its final offsets, so those source rings are re-binned
+        (bfg_shell_regrid_p2p_range, deposits go to this rank's slice or to a neighbour's over NVLink) and the part of this
+        rank's slice that can no longer change -- a margin further north, and not the strip next to the northern neighbour,
+        which keeps receiving that neighbour's deposits until fence 2 -- is copied to the shared host map on a second copy
+        stream while the next chunk computes.  The margin assumption (no pixel is moved by PIPELINE_MARGIN_RAD or more) is
+        verified from max|offset| over ALL ranks; if it fails every rank downloads its whole slice again.
+        """
+        torch = _torch()
+        import torch.distributed as dist
+        from .parallel import first_pixel_at_colatitude, ring_of_pixel, _ring_z
+        orig_map = self.LightconeShell.map
+        NSIDE = self.LightconeShell.NSIDE
+        npix = orig_map.size
+        lo, hi = self._range(npix)
+        nloc = hi - lo
+        dev = self._device()
+        L = _lib.lib()
+        cat = self.HaloLightConeCatalog.cat
+        n = cat.size
+        K = max(1, int(os.environ.get("BFG_SHARD_CHUNKS", self.SHARD_CHUNKS)))
+        keys = list(vars(self.model).get('p_keys', []))
+        _check_keys(self.model, keys)
+        pix_rad = np.sqrt(4 * np.pi / npix)
+
+        def colat_of_pixel(p):
+            if p <= 0:
+                return 0.0
+            if p >= npix:
+                return np.pi
+            return float(np.arccos(np.clip(_ring_z(NSIDE, ring_of_pixel(NSIDE, np.array([p]))[0]), -1, 1)))
+
+        with torch.cuda.device(dev):
+            table = self._tables.get((_Ident(self.model), _Ident(self.model.interp_d) if hasattr(self.model, 'interp_d') else 0),
+                                     lambda: displacement_table_of(self.model, dev.index))
+            if getattr(self, '_scratch_inflight', None):
+                torch.cuda.current_stream().synchronize()
+                _give_scratch(self._scratch_inflight)
+            self._scratch_inflight = []
+            main = torch.cuda.current_stream()
+            up, down = _side_stream(dev, 0), _side_stream(dev, 1)
+            st = _lib.current_stream()
+            own = peers.own_tensor()
+            up.wait_stream(main)                     # the previous call's reads of `own` precede the zeroing
+            h_map = torch.from_numpy(np.ascontiguousarray(orig_map, dtype=np.float64).reshape(-1))
+            piece = -(-nloc // K)
+            ev_h2d = []
+            with torch.cuda.stream(up):
+                own.zero_()
+                token = torch.zeros(1, device=dev)
+                dist.all_reduce(token)               # fence 1: every rank's slice is zero before any deposit
+            t0 = time.perf_counter()
+            d_rec = self.device_records(False, dev)  # the (small) catalogue copies go first: the copy engine serves its queue in
+            ext = _extras(cat, keys)                 # order, and behind the map upload they would hold the halo loop back
+            d_ext = None if ext is None else _to_device(ext, dev)
+            d_rec, d_ext = _sort_records(d_rec, d_ext, 0, SKY_BAND_RAD, owned=(NSIDE, lo, hi))
+            with torch.cuda.stream(up):
+                d_map = torch.empty(nloc, dtype=torch.float64, device=dev)
+                for j in range(K):
+                    a0, a1 = j * piece, min((j + 1) * piece, nloc)
+                    if a1 > a0:
+                        d_map[a0:a1].copy_(h_map[lo + a0:lo + a1], non_blocking=True)
+                    ev_h2d.append(up.record_event())
+            # chunk k = owned halos whose colatitude band lies in [edges[k], edges[k+1]); the last edge (2^20) = "all owned"
+            th_cut = [colat_of_pixel(lo + (nloc * k) // K) for k in range(1, K)]
+            edges = [0] + [int(np.floor(t / SKY_BAND_RAD)) for t in th_cut] + [1 << 20]
+            d_edges = torch.tensor(edges, dtype=torch.int64, device=dev)
+            d_bounds = torch.empty(K + 1, dtype=torch.int64, device=dev)
+            d_rho = torch.zeros(1, dtype=torch.float64, device=dev)
+            _lib.check(L.bfg_halo_band_bounds(n, _lib.ptr(d_rec), SKY_BAND_RAD, K + 1, _lib.ptr(d_edges), _lib.ptr(d_bounds),
+                                              _lib.ptr(d_rho), st))
+            d_off = torch.zeros((3, nloc), dtype=torch.float64, device=dev)
+            d_nb = torch.zeros(K, dtype=torch.int64, device=dev)
+            d_rem = torch.zeros(1, dtype=torch.int64, device=dev)
+            d_max = torch.zeros(1, dtype=torch.float64, device=dev)
+            d_acc = torch.zeros(5, dtype=torch.float64, device=dev)     # sum(new), sum(old), n_updates, n_remote, margin violated
+            bounds = d_bounds.cpu().tolist()         # the one early synchronisation: chunk boundaries in the sorted catalogue
+            rho_max = float(d_rho.cpu()[0])
+            host_prep_s = time.perf_counter() - t0
+            bounds[0] = 0
+            n_extra = table.n_extra
+            d_map.record_stream(main)
+            # the strip next to the northern neighbour keeps receiving its deposits until fence 2
+            q_top = lo if peers.rank == 0 else min(hi, max(lo, first_pixel_at_colatitude(
+                NSIDE, colat_of_pixel(lo) + self.PIPELINE_MARGIN_RAD + 3 * pix_rad)))
+            p_prev, q_prev, pieces_waited = lo, q_top, 0
+
+            def regrid_to(p_k):
+                nonlocal p_prev, pieces_waited
+                if p_k <= p_prev:
+                    return False
+                need = min(K, -(-(p_k - lo) // piece))     # map pieces covering [lo, p_k); the first one also orders fence 1
+                while pieces_waited < need:
+                    main.wait_event(ev_h2d[pieces_waited])
+                    pieces_waited += 1
+                _lib.check(L.bfg_shell_regrid_p2p_range(NSIDE, _lib.ptr(d_map), _lib.ptr(d_off), lo, hi, p_prev, p_k,
+                                                        peers.world, peers.rank, peers.h_bounds, peers.h_slices,
+                                                        _lib.ptr(d_rem), st))
+                p_prev = p_k
+                return True
+
+            def download(a, b, stream):
+                if b > a:
+                    _lib.check(L.bfg_copy_to_host_async(addr + 8 * a, own.data_ptr() + 8 * (a - lo), 8 * (b - a),
+                                                        stream.cuda_stream))
+
+            for k in range(K):
+                b0, b1 = bounds[k], bounds[k + 1]
+                if b1 > b0:
+                    _lib.check(L.bfg_shell_offsets(table.handle, NSIDE, b1 - b0, d_rec.data_ptr() + 8 * _lib.HALO_STRIDE * b0,
+                                                   None if d_ext is None else d_ext.data_ptr() + 8 * n_extra * b0, n_extra,
+                                                   _lib.ptr(d_off), lo, hi, d_nb.data_ptr() + 8 * k, st))
+                if k + 1 == K:
+                    break
+                # every owned halo not yet processed has theta >= edge band * band width; its disc reaches rho_max further north
+                th_done = edges[k + 1] * SKY_BAND_RAD - rho_max - 3 * pix_rad
+                p_k = min(hi, max(lo, first_pixel_at_colatitude(NSIDE, th_done))) if th_done > 0 else lo
+                if regrid_to(p_k):
+                    th_copy = th_done - self.PIPELINE_MARGIN_RAD - 3 * pix_rad
+                    q_k = min(hi, max(lo, first_pixel_at_colatitude(NSIDE, th_copy))) if th_copy > 0 else lo
+                    if q_k > q_prev:
+                        down.wait_event(main.record_event())
+                        download(q_prev, q_k, down)
+                        q_prev = q_k
+            regrid_to(hi)
+            if pieces_waited == 0:                   # nothing re-binned yet (empty range): still order fence 1 before fence 2
+                main.wait_event(ev_h2d[0])
+            dist.all_reduce(token)                   # fence 2: every rank's deposits have landed
+            down.wait_event(main.record_event())
+            download(lo, q_top, down)                # the northern strip and everything not yet copied
+            download(max(q_prev, q_top), hi, down)
+            _lib.check(L.bfg_sum_f64(own.data_ptr(), nloc, _lib.ptr(d_acc), st))
+            _lib.check(L.bfg_sum_f64(_lib.ptr(d_map), nloc, d_acc.data_ptr() + 8, st))
+            _lib.check(L.bfg_offsets_max_norm2(_lib.ptr(d_off), nloc, 0, nloc, _lib.ptr(d_max), st))
+            d_acc[2] = d_nb.sum().to(torch.float64)                     # counts are < 2^53: exact as float64
+            d_acc[3] = d_rem.reshape(()).to(torch.float64)
+            d_acc[4] = (~(d_max.reshape(()) < self.PIPELINE_MARGIN_RAD ** 2)).to(torch.float64)
+            main.wait_stream(down)
+            dist.all_reduce(d_acc)                   # sums + "every rank's slice is in the host map" + "any margin violated?"
+            acc = d_acc.cpu()
+            if float(acc[4]) > 0:
+                # somewhere the re-binning moved mass further than assumed: parts were copied too early -- on every rank again
+                download(lo, hi, main)
+                dist.all_reduce(token)
+                token.cpu()
+            main.synchronize()
+        _give_scratch(getattr(self, '_scratch_inflight', []))
+        self._scratch_inflight = []
+        new_sum, old_sum = float(acc[0]), float(acc[1])
+        self.last_stats = dict(n_updates=int(acc[2]), new_sum=new_sum, old_sum=old_sum, sharded=True, pipelined=True,
+                               margin_violated=bool(float(acc[4]) > 0))
+        self.last_stats_remote = int(acc[3])
+        self.last_timing = dict(host_prep_s=host_prep_s, chunks=float(K))
+        assert np.isclose(new_sum, old_sum), \
+            "ERROR in pixel regridding, sum(new_map) [%0.14e] != sum(oldmap) [%0.14e]" % (new_sum, old_sum)   # :368-370
+        return host.export(seg, orig_map.shape)
 
     def process(self):
         torch = _torch()

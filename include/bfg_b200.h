@@ -167,8 +167,10 @@ int bfg_shell_regrid_range(int nside, const double *d_map_in, const double *d_of
                            double *d_map_out, int64_t src_lo, int64_t src_hi, void *stream);
 /* *d_out = max_p |offset_p|^2 over p in [lo, hi) (NaN counts as +inf): bounds how far the re-binning moves mass. */
 int bfg_offsets_max_norm2(const double *d_offsets, int64_t comp_stride, int64_t lo, int64_t hi, double *d_out, void *stream);
-/* For sky-sorted records (bfg_halo_sort, band width `band`): d_bounds[e] = first record whose colatitude band
- * floor(theta / band) >= d_edge_band[e]; *d_rho_max = largest disc radius.  Cuts the halo loop into latitude chunks. */
+/* For sky-sorted records (bfg_halo_sort / bfg_halo_sort_owned, band width `band`): d_bounds[e] = first record whose colatitude
+ * band floor(theta / band) >= d_edge_band[e]; *d_rho_max = largest disc radius.  Cuts the halo loop into latitude chunks.
+ * Records marked BFG_HS_SKIP (other ranks' halos, sorted last) count as band 2^20, so an edge of 2^20 yields the number of
+ * owned halos; they do not enter *d_rho_max. */
 int bfg_halo_band_bounds(int64_t n_halo, const double *d_sorted_halos, double band, int n_edges, const int64_t *d_edge_band,
                          int64_t *d_bounds, double *d_rho_max, void *stream);
 
@@ -181,6 +183,12 @@ int bfg_halo_band_bounds(int64_t n_halo, const double *d_sorted_halos, double ba
 int bfg_shell_regrid_p2p(int nside, const double *d_map_in, const double *d_offsets, int64_t pix_lo, int64_t pix_hi,
                          int world, int self, const int64_t *h_bounds, double *const *h_slices,
                          int64_t *d_remote_count, void *stream);
+/* The same for the source pixels [src_lo, src_hi) of the owned range only (d_remote_count is accumulated, not reset): the
+ * pipelined sharded end-to-end path re-bins the rings whose offsets are final while the halo loop works further south
+ * (the ring-range counterpart of bfg_shell_regrid_range; HealpixRunner.py:357-365). */
+int bfg_shell_regrid_p2p_range(int nside, const double *d_map_in, const double *d_offsets, int64_t pix_lo, int64_t pix_hi,
+                               int64_t src_lo, int64_t src_hi, int world, int self, const int64_t *h_bounds,
+                               double *const *h_slices, int64_t *d_remote_count, void *stream);
 
 /* ---- peer memory between the processes of one box (CUDA IPC) --------------------------------------------------------- */
 int bfg_shared_alloc(void **d_ptr, int64_t bytes, int device);            /* cudaMalloc'd, exportable */

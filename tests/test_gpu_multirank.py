@@ -56,6 +56,14 @@ def _worker(rank, world, port, q):
     held = [srun.process() for _ in range(parallel.SharedHostMaps.MAX_SEGMENTS + 2)]
     held_err = max(float(np.max(np.abs(h - out1))) for h in held)
     del held
+    # the chunked sharded path (upload / halo loop / download overlapped; normally only for >= 2e5 halos) gives the same map
+    b.BaryonifyShell.PIPELINE_MIN_HALOS = 1000
+    piped = b.BaryonifyShell(cat, shell, 20, dmodel, verbose=False, device=rank, pix_range=pr)
+    out1p = piped.process()
+    assert piped.last_stats.get("pipelined") and not piped.last_stats["margin_violated"]
+    held_err = max(held_err, float(np.max(np.abs(out1p - out1))))
+    b.BaryonifyShell.PIPELINE_MIN_HALOS = 200000
+    del out1p
     out2 = b.PaintProfilesShell(cat, shell, 20, pmodel, verbose=False, device=rank, pix_range=pr).process()
     out3 = b.BaryonifyGrid(gcat, gm, 6, gmodel, verbose=False, device=rank,
                            plane_range=parallel.plane_ranges(N, world)[rank]).process()
