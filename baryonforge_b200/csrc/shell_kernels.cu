@@ -209,26 +209,32 @@ struct FastHalo {
 };
 
 // ------------------------------------------------------------------------------------------------------------------
-// Lean pixel loop (round 2, "v10").  What the profiles of v8 said (profiles/r2_shell_halos_*): the loop is NOT bound by its
-// scatter-adds -- with the REDs compiled out the kernel takes 90.0 ms instead of 94.1 -- but by instruction issue: ~100 SASS
-// instructions per 32 updates of which 47 on the FP64 pipe (2 issue cycles each), 4 on the XU pipe, 6 branches, 64-bit pointer
-// arithmetic and constant reloads, with issue slots 68 % busy.  So this loop spends as few instructions of ANY kind as the
-// arithmetic allows and has no branch in its body:
+// Lean pixel loop (round 2, "v11").  What round 2's experiments said about the v8 loop (profiles/README.md "Round 2"):
+// with its REDs compiled out the kernel takes 84-90 ms instead of 94, i.e. the arithmetic alone is as slow as the whole
+// kernel, while WITH the REDs the L2 atomic unit is 82-84 % busy (lts__d_atomic_input_cycles_active) -- two ceilings of equal
+// height, each hiding the other.  The arithmetic side: ~100 SASS instructions per 32 updates, 47 of them on the FP64 pipe
+// (2 issue cycles each), 4 on the XU pipe, 6 branches, ~21 shared-memory wavefronts (half of them bank-conflict replays of
+// the 128-entry log2 table), issue slots 66 % busy.  This loop trims all of those:
 //   * (x, y) = sin(theta) (cos phi, sin phi) is rotated directly (a rotation is linear: no sth * cs, sth * sn per pixel);
-//   * log2(1+f) to degree 3 (|f| <= 2^-8: abs. error 8e-11 in log2 r^2, 3e-11 in ln r -- four orders below the 1e-6 bar);
+//   * log2 of the mantissa from a 32-entry table held in the lanes' registers (two warp shuffles, no shared-memory bank
+//     conflicts) + a degree-4 series (|f| <= 2^-6: abs. error 2.7e-10 in log2 r^2, 1e-10 in ln r -- four orders below
+//     the 1e-6 bar);
 //   * the exponent's share of the cell coordinate, uB + uA e, comes from a 64-entry per-halo table in shared memory
 //     (r^2 in [2^-61, 8) on the unit sphere; anything else reads a NaN entry and lands outside the table);
 //   * floor(u) with ONE round-down add of 2^52 + 2^51 (DADD.RM): the cell index is the low word of the sum, its double is
 //     the sum minus the constant -- no F2I / I2F (quarter-rate XU instructions);
-//   * the table row is pre-multiplied by a / D at blend time;
+//   * the table row is pre-multiplied by a / D at blend time and stored as (value, step to the next node) pairs: one
+//     16-byte read per update;
 //   * 1/sqrt(r^2) = MUFU seed + one Newton step (rel. error 1e-13);
 //   * the re-normalisation nw_vec - vec = normalise(vec + sc d) - vec is expanded in eps = |vec + sc d|^2 - 1.  Both vectors
 //     are unit vectors, so vec . d = |d|^2 / 2 and eps = sc r^2 (1 + sc) needs no dot product; with
 //     dl = 1/sqrt(1 + eps) - 1 = eps (-1/2 + 3/8 eps - 5/16 eps^2) the result is sc (1 + dl) d + dl vec.  dl vec is
 //     <~ 1 % of the result, so the truncation (0.27 eps^4) is < 1e-8 of it for |eps| < 2^-6.  No cancellation, unlike
 //     fma(nx, ninv, -x);
-//   * the three REDs are predicated, not branched around.
-// 37 FP64-pipe + 1 XU + ~35 other instructions per 32 updates.  A halo takes this loop only if it is provably safe for it
+//   * spans start on a 32-byte sector boundary, so a lane group's RED covers whole sectors (the L2 atomic unit is 82 % busy);
+//   * no branch in the body except the one around the three REDs.
+// 36 FP64-pipe + 1 XU + ~50 other instructions per 32 updates (profiles/r2_shell_halos_v11_loop.sass), 9 shared-memory
+// wavefronts.  A halo takes this loop only if its disc is large (16 lanes per ring) and it is provably safe for it
 // (FastHalo.lean, decided per halo): every finite node of its row is small enough that |eps| < 2^-6 anywhere in the disc
 // and its table does not reach below r^2 = 2^-61.  Other halos (displacements comparable to their distance, exotic tables)
 // take the exact loop (span_pixels_fast).  Deviations from it, all documented boundary ties: a pixel EXACTLY on the table's
