@@ -552,14 +552,19 @@ def run_b200(args):
     upd_per_launch = n_up_local if world == 1 else n_up / world
     achieved = ALG_BYTES_PER_UPDATE * upd_per_launch / (ms_kernel * 1e-3) / 1e9
     facts = ncu_facts(workload_name(args)) if world == 1 else {}
-    # The resource that binds this kernel (profiles/README.md, round 2): the FP64 pipe / instruction issue, not HBM.  The
-    # ceiling is what the FP64 pipe could do if it issued nothing but this loop's FP64 instructions, at the SM clock measured
-    # DURING the timed region: SMs x 64 FP64 lanes per clock x clock / (FP64-pipe instructions per update, counted in the
-    # committed SASS of the pixel loop).
+    # The resources that bind this kernel (profiles/README.md, round 2) are not HBM: (1) the L2's fp64 atomic unit -- ncu
+    # lts__d_atomic_input_cycles_active of the committed capture -- and (2) the arithmetic itself: with the REDs compiled out the
+    # kernel is only ~10 % faster.  For (2) the ceiling is what the FP64 pipe could do if it issued nothing but this loop's FP64
+    # instructions, at the SM clock measured DURING the timed region: SMs x 64 FP64 lanes per clock x clock / (FP64-pipe
+    # instructions per update, counted in the committed SASS of the pixel loop).
     fp64_per_upd = facts.get("fp64_inst_per_update")
     sm_mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz")
-    binding = {"resource": "FP64 pipe (instruction issue)", "fp64_inst_per_update": fp64_per_upd,
-               "fp64_inst_source": facts.get("fp64_inst_source"), "sm_clock_mhz": sm_mhz}
+    binding = {"resource": "L2 fp64 atomic unit, co-limited by the arithmetic (FP64 pipe + instruction issue)",
+               "l2_atomic_unit_busy_frac": (facts.get("l2_atomic_input_active_pct") or 0) / 100.0 or None,
+               "l2_red_sectors_per_launch": facts.get("l2_red_sectors"),
+               "kernel_ms_without_reds": facts.get("kernel_ms_without_reds"),
+               "fp64_inst_per_update": fp64_per_upd, "fp64_inst_source": facts.get("fp64_inst_source"),
+               "sm_clock_mhz": sm_mhz, "ncu_source": facts.get("source")}
     if fp64_per_upd and sm_mhz:
         ceil_ups = B200_SMS * FP64_LANES_PER_SM_CLK * sm_mhz * 1e6 / fp64_per_upd
         binding.update({"fp64_ceiling_updates_s": ceil_ups,
@@ -587,8 +592,8 @@ def run_b200(args):
                          "note": "algorithmic bytes = the reference dataflow's 3 f64 read-modify-writes per update (SURVEY 8d). "
                                  "With sky-ordered halos those REDs are absorbed by the 126 MB L2 (`traffic` = measured DRAM "
                                  "bytes of one launch, ~1/25 of algorithmic), so `frac` can exceed 1 and says nothing about "
-                                 "efficiency; the binding resource is the FP64 pipe / instruction issue -- read "
-                                 "`binding.frac_fp64`"},
+                                 "efficiency; read `binding`: the L2 atomic unit is `l2_atomic_unit_busy_frac` busy, and the "
+                                 "arithmetic alone (`kernel_ms_without_reds`) is almost as slow as the whole kernel"},
             "e2e": e2e, "particles": particles}
     if parity_vs_n1 is not None:
         line["parity_vs_n1"] = parity_vs_n1
