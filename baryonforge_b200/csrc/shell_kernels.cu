@@ -437,12 +437,13 @@ struct HaloCtx {
 template <int GW, bool PAINT>
 __device__ __forceinline__ i64 walk_rings_fast(const FastHalo &fh, const RingSeg *__restrict__ segs, int nseg, bool valid,
                                                bool sharded, double eqC, double eqS, double *__restrict__ out, i64 nloc,
-                                               i64 nloc8) {
+                                               i64 nloc8, int wi = (int)(threadIdx.x >> 5), int nw = SHELL_THREADS / 32) {
+    // warp wi of the nw warps that share `segs` takes ring groups wi, wi + nw, ...  (nw = 1: the warp-per-halo kernel)
     constexpr int NG = 32 / GW;
     const int lane = threadIdx.x & 31;
     const int li = lane & (GW - 1), gi = lane / GW;
     i64 done = 0;
-    for (int rb0 = (threadIdx.x >> 5) * NG; rb0 < nseg; rb0 += (SHELL_THREADS / 32) * NG) {
+    for (int rb0 = wi * NG; rb0 < nseg; rb0 += nw * NG) {
         const int r = rb0 + gi;
         if (r >= nseg) continue;
         const RingSeg &g = segs[r];
@@ -572,7 +573,8 @@ template <int MODE, bool UNIFORM>
 __global__ void __launch_bounds__(SHELL_THREADS, SHELL_MIN_CTAS)
 k_shell_halos(TableView T, Hpx h, i64 n_halo, const double *__restrict__ halos, const double *__restrict__ extras,
               int n_extra, double *__restrict__ out, i64 pix_lo, i64 pix_hi, unsigned long long *nupd,
-              const double2 *__restrict__ g_l2tab, AnisArgs A, unsigned long long *queue) {
+              const double2 *__restrict__ g_l2tab, AnisArgs A, unsigned long long *queue, int min_rings) {
+    // min_rings: discs of at most this many rings belong to k_shell_halos_warp (0: this kernel takes every halo)
     constexpr bool PAINT = (MODE != MODE_BARYONIFY);
     constexpr bool FAST = (MODE != MODE_ANIS) && UNIFORM;        // span_pixels_fast / _paint: 8 or 16 lanes per ring
     extern __shared__ double row[];
@@ -624,7 +626,7 @@ k_shell_halos(TableView T, Hpx h, i64 n_halo, const double *__restrict__ halos, 
                     // lane-group width of the fast path from the disc's mean chord (pi/4 of its diameter) in pixels
                     const int gws = (0.7853981633974483 * 2.0 * s0.radius) * sqrt((double)h.npix * 0.07957747154594767)
                                     < GW_CHORD_SPLIT;
-                    const int tch = !sharded || disc_touches_range(h, d0, pix_lo, pix_hi);
+                    const int tch = (d0.rb - d0.ra + 1 > (i64)min_rings) && (!sharded || disc_touches_range(h, d0, pix_lo, pix_hi));
                     if (FAST) {
                         const FastHalo f0 = make_fast<PAINT>(T, s0, u0, row, l2tab, s_etab);
                         if (lane == 0) s_ctx.fh = f0;
@@ -787,6 +789,132 @@ k_shell_halos(TableView T, Hpx h, i64 n_halo, const double *__restrict__ halos, 
                 }
             }
             __syncthreads();  // before the next chunk overwrites the segments
+        }
+    }
+    if (nupd) {
+        done = warp_sum_i64(done);
+        if (lane == 0 && done) atomicAdd(nupd, (unsigned long long)done);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Small discs: ONE WARP PER HALO.  A disc of the mass-function-like catalogue has ~1500 pixels on ~40 rings: in the CTA-per-halo
+// kernel above that is 11 updates per thread behind three block barriers, a per-halo set-up done by one warp while three wait,
+// and a ring-staging pass that uses a third of the threads -- the fixed cost per halo, not the pixel loop, sets the pace
+// (4.7e10 updates/s against 1.7e11 for large discs).  Here every warp pulls its own halos from the queue, blends its own row,
+// stages its rings 32 at a time and walks them with the same lane groups and the same exact pixel loop -- no block barrier
+// anywhere, four independent halos in flight per CTA.  Discs of more than WARP_MAX_RINGS rings are left to k_shell_halos
+// (launched with min_rings = WARP_MAX_RINGS), which skips the ones taken here; both add into the same array.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int WARP_MAX_RINGS = 64;
+constexpr int WARP_KERNEL_CTAS = 6;
+
+template <int MODE>
+__global__ void __launch_bounds__(SHELL_THREADS, WARP_KERNEL_CTAS)
+k_shell_halos_warp(TableView T, Hpx h, i64 n_halo, const double *__restrict__ halos, const double *__restrict__ extras,
+                   int n_extra, double *__restrict__ out, i64 pix_lo, i64 pix_hi, unsigned long long *nupd,
+                   const double2 *__restrict__ g_l2tab, unsigned long long *queue, int row_stride) {
+    constexpr bool PAINT = (MODE != MODE_BARYONIFY);
+    constexpr bool UNIFORM = true;
+    extern __shared__ double rows[];                       // [warps][row_stride]
+    __shared__ RingSeg segs_all[SHELL_THREADS / 32][32];
+    __shared__ double2 l2tab[BFG_LOG2_TAB];
+    __shared__ double2 s_eq[GW_SMALL];
+    load_log2_table(l2tab, g_l2tab);
+    if (threadIdx.x < GW_SMALL) {
+        double sk, ck;
+        sincospi((double)threadIdx.x * (2.0 / (double)h.nl4), &sk, &ck);
+        s_eq[threadIdx.x] = make_double2(ck, sk);
+    }
+    __syncthreads();                                       // the only block barrier: tables ready
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    double *row = rows + (size_t)wid * row_stride;
+    RingSeg *segs = segs_all[wid];
+    const i64 nloc = pix_hi - pix_lo;
+    i64 nloc8 = nloc * 8;
+    asm volatile("" : "+l"(nloc8));
+    const bool sharded = pix_lo > 0 || pix_hi < h.npix;
+    const double2 e = s_eq[lane & (GW_SMALL - 1)];
+    const double eqC = e.x, eqS = e.y;
+    const AnisArgs A = {};
+    i64 done = 0;
+    for (;;) {
+        i64 j = 0;
+        if (lane == 0) j = (i64)atomicAdd(queue, 1ULL);
+        j = ((i64)__shfl_sync(0xffffffffu, (int)(j >> 32), 0) << 32) | (unsigned)__shfl_sync(0xffffffffu, (int)j, 0);
+        if (j >= n_halo) break;
+        const HaloSph s = load_halo(halos + j * BFG_HALO_STRIDE);
+        if (s.skip != 0.0) break;                          // bfg_halo_sort_owned: the halos of other ranks come last
+        const DiscRings d = disc_rings(h, s.theta, s.phi, s.radius);
+        if (d.rb - d.ra + 1 > (i64)WARP_MAX_RINGS) continue;                     // a large disc: k_shell_halos takes it
+        if (sharded && !disc_touches_range(h, d, pix_lo, pix_hi)) continue;
+        HaloUpd u = make_upd(T, s);
+        const FastHalo fh = make_fast<PAINT>(T, s, u, row, l2tab, nullptr);
+        // blend this warp's row (a / D folded in for the displacement table, like the CTA kernel's fast loops)
+        const RowBlender B(T, s.lnz, s.lnM, extras ? extras + j * n_extra : nullptr);
+        const bool valid = B.valid;
+        const double post = (!PAINT && SHELL_PRESCALED) ? s.a / s.D : 1.0;
+        __syncwarp();                                      // the previous halo's row is no longer read
+        for (int k = lane; k < B.NR; k += 32) row[k] = B.node(T, k) * post;
+        if (!PAINT && SHELL_PRESCALED) u.a = u.D;          // generic update on a prescaled row (the < 4-pixel fallback)
+        __syncwarp();
+        // `if pixind.size < 4` (HealpixRunner.py:333): count the disc when it could be that small
+        const bool tiny = !PAINT && (s.radius * s.radius * (double)h.npix * 0.25 < 64.0);
+        if (tiny) {
+            i64 c = 0;
+            for (i64 iz = d.ra + lane; iz <= d.rb; iz += 32) {
+                i64 start, nr, ip_lo, cnt; bool sh;
+                disc_ring_span(h, d, iz, start, nr, sh, ip_lo, cnt);
+                c += cnt;
+            }
+            c = warp_sum_i64(c);
+            if (c < 4) {
+                if (lane < 4) {
+                    i64 pix[4]; double w[4];
+                    get_interpol(h, s.theta_ll, s.phi_ll, pix, w);   // HealpixRunner.py:334
+                    const i64 p = pix[lane];
+                    if (p >= pix_lo && p < pix_hi) {
+                        ++done;
+                        if (valid) {
+                            double x, y, z;
+                            pix2vec(h, p, x, y, z);
+                            double *q = out + (p - pix_lo);
+                            shell_update<MODE, UNIFORM>(T, row, u, x, y, z, x * u.D, y * u.D, z * u.D, q, q + nloc,
+                                                        q + 2 * nloc, l2tab, A, row, u);
+                        }
+                    }
+                }
+                continue;
+            }
+        }
+        for (i64 base = d.ra; base <= d.rb; base += 32) {
+            {   // stage up to 32 ring segments: one ring per lane
+                const i64 iz = base + lane;
+                RingSeg g;
+                g.cnt = 0; g.active = 0;
+                if (iz <= d.rb) {
+                    i64 start, nr, ip_lo, cnt; bool sh;
+                    disc_ring_span(h, d, iz, start, nr, sh, ip_lo, cnt);
+                    if (cnt > 0 && start < pix_hi && start + nr > pix_lo) {
+                        g.active = 1;
+                        g.lbase = start - pix_lo;
+                        g.nr = (int)nr; g.ip_lo = (int)ip_lo; g.cnt = (int)cnt;
+                        g.flags = ((start < pix_lo || start + nr > pix_hi) ? 1 : 0) | ((nr == h.nl4) ? 2 : 0) | (sh ? 4 : 0);
+                        ring_z_sth(h, iz, g.z, g.sth);
+                        g.pz = g.z * u.D; g.sD = g.sth * u.D;
+                        g.dz = g.z - s.vz; g.dz2 = g.dz * g.dz;
+                        g.inv2nr = 2.0 / (double)nr;
+                        g.phase0 = ((double)ip_lo + (sh ? 0.5 : 0.0)) * g.inv2nr;
+                        if (g.flags & 2) sincospi(g.phase0, &g.s0, &g.c0);       // only equatorial rings rotate a staged start
+                        sincospi((double)GW_SMALL * g.inv2nr, &g.rotS, &g.rotC);
+                    }
+                }
+                segs[lane] = g;
+            }
+            __syncwarp();
+            const int nseg = (int)min((i64)32, d.rb - base + 1);
+            done += walk_rings_fast<GW_SMALL, PAINT>(fh, segs, nseg, valid, sharded, eqC, eqS, out, nloc, nloc8, 0, 1);
+            __syncwarp();
         }
     }
     if (nupd) {
@@ -997,15 +1125,38 @@ int launch_shell(const bfg_table *t, int nside, i64 n_halo, const double *d_halo
     unsigned long long *queue = nullptr;   // halo queue head (stream-ordered scratch)
     BFG_CUDA_OK(cudaMallocAsync(&queue, sizeof(unsigned long long), st));
     BFG_CUDA_OK(cudaMemsetAsync(queue, 0, sizeof(unsigned long long), st));
+    const bool uni = t->view.uniform_r && (MODE != MODE_ANIS || t2->view.uniform_r);
+    // small discs first, one warp per halo (k_shell_halos_warp); the CTA-per-halo kernel then skips them
+    int min_rings = 0;
+    // Measured (B200, same box): PaintProfilesShell NSIDE=1024 1.72 -> 1.59 ms; BaryonifyShell on the dn/dlogM ~ M^-0.9 catalogue
+    // 22.1 -> 20.0 ms, but on the flat 10^U(12,15.5) catalogue 97.2 -> 100.3 ms (two persistent kernels in a row, and the second
+    // still pops the halos the first took).  So: on by default for painting, opt-in (BFG_SHELL_WARP_KERNEL=1) for BaryonifyShell;
+    // BFG_SHELL_WARP_KERNEL=0 switches it off everywhere.
+    const char *wenv = getenv("BFG_SHELL_WARP_KERNEL");
+    const bool want_warp = wenv ? (wenv[0] != '0') : (MODE == MODE_PAINT);
+    const size_t wsmem = sizeof(double) * (SHELL_THREADS / 32) * (size_t)((t->view.n[2] + 1) & ~1);
+    if (uni && MODE != MODE_ANIS && want_warp && wsmem <= 64 * 1024) {
+        unsigned long long *queue_w = nullptr;
+        BFG_CUDA_OK(cudaMallocAsync(&queue_w, sizeof(unsigned long long), st));
+        BFG_CUDA_OK(cudaMemsetAsync(queue_w, 0, sizeof(unsigned long long), st));
+        auto kw = k_shell_halos_warp<MODE == MODE_ANIS ? MODE_PAINT : MODE>;
+        BFG_CUDA_OK(cudaFuncSetAttribute(kw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
+        const int wblocks = (int)std::min<i64>((n_halo + SHELL_THREADS / 32 - 1) / (SHELL_THREADS / 32), (i64)sms * WARP_KERNEL_CTAS);
+        kw<<<wblocks, SHELL_THREADS, wsmem, st>>>(t->view, h, n_halo, d_halos, d_extras, n_extra, d_out, pix_lo, pix_hi,
+                                                  (unsigned long long *)d_nupdates, g_l2tab, queue_w,
+                                                  (int)((t->view.n[2] + 1) & ~1));
+        BFG_CUDA_OK(cudaGetLastError());
+        BFG_CUDA_OK(cudaFreeAsync(queue_w, st));
+        min_rings = WARP_MAX_RINGS;
+    }
     auto go = [&](auto kern) -> int {
         BFG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<blocks, SHELL_THREADS, smem, st>>>(t->view, h, n_halo, d_halos, d_extras, n_extra, d_out, pix_lo, pix_hi,
-                                                  (unsigned long long *)d_nupdates, g_l2tab, A, queue);
+                                                  (unsigned long long *)d_nupdates, g_l2tab, A, queue, min_rings);
         BFG_CUDA_OK(cudaGetLastError());
         BFG_CUDA_OK(cudaFreeAsync(queue, st));
         return BFG_OK;
     };
-    const bool uni = t->view.uniform_r && (MODE != MODE_ANIS || t2->view.uniform_r);
     return uni ? go(k_shell_halos<MODE, true>) : go(k_shell_halos<MODE, false>);
 }
 

@@ -565,7 +565,9 @@ def run_b200(args):
                "kernel_ms_without_reds": facts.get("kernel_ms_without_reds"),
                "fp64_inst_per_update": fp64_per_upd, "fp64_inst_source": facts.get("fp64_inst_source"),
                "sm_clock_mhz": sm_mhz, "ncu_source": facts.get("source")}
-    if fp64_per_upd and sm_mhz:
+    if world > 1:
+        binding = {"note": "per-kernel ncu facts are captured at N = 1 (profiles/shell_halos_ncu_facts.json); see that line"}
+    if world == 1 and fp64_per_upd and sm_mhz:
         ceil_ups = B200_SMS * FP64_LANES_PER_SM_CLK * sm_mhz * 1e6 / fp64_per_upd
         binding.update({"fp64_ceiling_updates_s": ceil_ups,
                         "frac_fp64": upd_per_launch / (ms_kernel * 1e-3) / ceil_ups,

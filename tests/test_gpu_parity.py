@@ -22,6 +22,16 @@ def test_map_runners_match_reference_fixture(name):
     assert_close(got, g["out"], name)
 
 
+@pytest.mark.parametrize("name", golden_names("shell_bary"))
+def test_warp_per_halo_kernel_matches_reference_fixture(name, monkeypatch):
+    """k_shell_halos_warp (one warp per small disc; the default for painting, opt-in for BaryonifyShell) against the same fixtures."""
+    monkeypatch.setenv("BFG_SHELL_WARP_KERNEL", "1")
+    g = load(name)
+    assert_close(product_run(g), g["out"], name + " (warp-per-halo kernel)")
+    monkeypatch.setenv("BFG_SHELL_WARP_KERNEL", "0")
+    assert_close(product_run(g), g["out"], name + " (CTA-per-halo kernel only)")
+
+
 @pytest.mark.parametrize("name", golden_names("snap"))
 def test_snapshot_matches_reference_fixture(name):
     g = load(name)
