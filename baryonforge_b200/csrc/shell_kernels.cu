@@ -626,7 +626,9 @@ k_shell_halos(TableView T, Hpx h, i64 n_halo, const double *__restrict__ halos, 
                     // lane-group width of the fast path from the disc's mean chord (pi/4 of its diameter) in pixels
                     const int gws = (0.7853981633974483 * 2.0 * s0.radius) * sqrt((double)h.npix * 0.07957747154594767)
                                     < GW_CHORD_SPLIT;
-                    const int tch = (d0.rb - d0.ra + 1 > (i64)min_rings) && (!sharded || disc_touches_range(h, d0, pix_lo, pix_hi));
+                    // (a disc without any ring -- rb < ra -- still owes the < 4-pixel fallback: only min_rings > 0 may skip it)
+                    const int tch = (min_rings == 0 || d0.rb - d0.ra + 1 > (i64)min_rings) &&
+                                    (!sharded || disc_touches_range(h, d0, pix_lo, pix_hi));
                     if (FAST) {
                         const FastHalo f0 = make_fast<PAINT>(T, s0, u0, row, l2tab, s_etab);
                         if (lane == 0) s_ctx.fh = f0;

@@ -150,6 +150,85 @@ def _parallel_chunks(fn, n, chunk=65536):
         list(ex.map(fn, slices))
 
 
+_FIELD_CHUNK = 1 << 22      # elements per staging chunk (32 MB of float64)
+
+
+def _fields_to_device(cat, names, dev):
+    """
+    Columns of a structured catalogue (strided 8-byte fields) -> contiguous float64 device tensors.  The reference keeps particles
+    as ONE structured array (utils/io.py:588), so every column is a strided view: np.ascontiguousarray + a pageable copy moves
+    2 GB per column at ~1 GB/s.  Here host threads gather chunks of the field into a ring of page-locked buffers while the
+    previous chunks are in flight to the device (asynchronous copies on the current stream).
+    """
+    torch = _torch()
+    n = cat.shape[0]
+    outs = [torch.empty(n, dtype=torch.float64, device=dev) for _ in names]
+    if n == 0:
+        return outs
+    nbuf = 4
+    bufs = [_take_scratch(_FIELD_CHUNK) for _ in range(nbuf)]
+    evs = [None] * nbuf
+    stream = torch.cuda.current_stream()
+    nth = max(1, _host_threads())
+    with ThreadPoolExecutor(max_workers=nth) as ex:
+        k = 0
+        for col, name in enumerate(names):
+            src = cat[name]
+            for a in range(0, n, _FIELD_CHUNK):
+                b = min(n, a + _FIELD_CHUNK)
+                slot = k % nbuf
+                if evs[slot] is not None:
+                    evs[slot].synchronize()                  # the copy that last used this buffer has left the host
+                dst = bufs[slot].numpy()[:b - a]
+                step = -(-(b - a) // nth)
+                list(ex.map(lambda i: np.copyto(dst[i:i + step], src[a + i:a + i + step], casting='unsafe'),
+                            range(0, b - a, step)))
+                outs[col][a:b].copy_(bufs[slot][:b - a], non_blocking=True)
+                evs[slot] = stream.record_event()
+                k += 1
+    for e in evs:
+        if e is not None:
+            e.synchronize()
+    _give_scratch(bufs)
+    return outs
+
+
+def _device_to_fields(d_cols, out_cat, names):
+    """The way back: contiguous device tensors -> the strided fields of a structured array, chunked through page-locked buffers
+    with the host-side scatter of chunk k running while chunk k + 1 comes down."""
+    torch = _torch()
+    n = out_cat.shape[0]
+    if n == 0:
+        return
+    nbuf = 4
+    bufs = [_take_scratch(_FIELD_CHUNK) for _ in range(nbuf)]
+    stream = torch.cuda.current_stream()
+    nth = max(1, _host_threads())
+    jobs = []       # (slot, event, column name, a, b) in flight
+    with ThreadPoolExecutor(max_workers=nth) as ex:
+        def drain(job):
+            slot, ev, name, a, b = job
+            ev.synchronize()
+            src = bufs[slot].numpy()[:b - a]
+            dst = out_cat[name]
+            step = -(-(b - a) // nth)
+            list(ex.map(lambda i: np.copyto(dst[a + i:a + i + step], src[i:i + step]), range(0, b - a, step)))
+        k = 0
+        for col, name in enumerate(names):
+            for a in range(0, n, _FIELD_CHUNK):
+                b = min(n, a + _FIELD_CHUNK)
+                if len(jobs) == nbuf:
+                    drain(jobs.pop(0))
+                slot = k % nbuf
+                bufs[slot][:b - a].copy_(d_cols[col][a:b], non_blocking=True)
+                jobs.append((slot, stream.record_event(), name, a, b))
+                k += 1
+        while jobs:
+            drain(jobs.pop(0))
+    _give_scratch(bufs)
+
+
+
 def _all_close_to_zero(a):
     """np.allclose(a, 0) (HealpixRunner.py:293) without scanning a 1.6 GB map when its first entries already say no."""
     head = a.reshape(-1)[:4096]
@@ -1833,9 +1912,14 @@ class BaryonifySnapshot(DefaultRunnerSnapshot):
     def process(self):
         ps = self.ParticleSnapshot
         d_p = self.process_on_device()
-        new_cat = ps.cat.copy()                                                   # :263
-        for k, name in enumerate(['x', 'y', 'z'][:(2 if ps.is2D else 3)]):
-            new_cat[name] = d_p[k].cpu().numpy()
+        names = ['x', 'y', 'z'][:(2 if ps.is2D else 3)]
+        new_cat = np.empty_like(ps.cat)                                           # :263 (a copy with x, y, z replaced below)
+        for name in ps.cat.dtype.names:
+            if name not in names:
+                src, dst = ps.cat[name], new_cat[name]
+                _parallel_chunks(lambda sl: np.copyto(dst[sl], src[sl]), len(src), chunk=1 << 22)
+        with _torch().cuda.device(self._device()):
+            _device_to_fields(d_p, new_cat, names)
         return new_cat
 
     def _displace_sorted(self):
@@ -1881,7 +1965,7 @@ class BaryonifySnapshot(DefaultRunnerSnapshot):
                 _, d_s, d_start, d_order = kept
                 d_p = [torch.empty(n_part, dtype=torch.float64, device=dev) for _ in names] + ([None] if ndim == 2 else [])
             else:
-                d_p = [_to_device(ps.cat[k], dev, dtype=np.float64) for k in names] + ([None] if ndim == 2 else [])
+                d_p = _fields_to_device(ps.cat, names, dev) + ([None] if ndim == 2 else [])
                 d_s = [torch.empty(n_part, dtype=torch.float64, device=dev) for _ in names] + ([None] if ndim == 2 else [])
                 d_start = torch.empty(ncell ** ndim + 1, dtype=torch.int64, device=dev)
                 d_order = torch.empty(n_part, dtype=torch.int64, device=dev)

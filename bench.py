@@ -291,6 +291,96 @@ def emit(line):
         os.write(_REAL_STDOUT, data)
 
 
+def particles_e2e(args, world, rank, local, dev, c4, host_in, barrier):
+    """particles displaced/s through BaryonifySnapshot.process() / process_to_map() with HOST inputs and outputs: this rank's
+    slab of the box as a ParticleSnapshot (structured array), the overlap halos as a HaloNDCatalog."""
+    import torch
+    import torch.distributed as dist
+    import baryonforge_b200 as b
+    from baryonforge_b200 import synth
+    n = int(args.particles_per_gpu)
+    try:
+        avail = [int(l.split()[1]) for l in open("/proc/meminfo") if l.startswith("MemAvailable")][0] / 2 ** 20
+    except Exception:
+        avail = 64.0
+    need = world * n * 8 * 12 / 2 ** 30          # per rank: x, y, z (24 B) + input catalogue (32 B) + output (32 B) + slack
+    if need > 0.6 * avail:
+        return {"skipped": f"host RAM: {need:.0f} GB needed for {world} x {n} particles, {avail:.0f} GB available"}
+    Lbox = float(c4["L"])
+    rng = np.random.default_rng(1000 + rank)
+    x = host_in["x_lo"] + rng.random(n) * (host_in["x_hi"] - host_in["x_lo"])
+    y, z = rng.random(n) * Lbox, rng.random(n) * Lbox
+    ps = b.ParticleSnapshot(x=x, y=y, z=z, M=1.0, L=Lbox, redshift=0.3, cosmo=synth.COSMO)
+    del x, y, z
+    gaxes = host_in["gaxes"]
+    model = b.DisplacementModel(gaxes, synth.displacement_values(gaxes), 5.0, synth.COSMO)
+    cat = b.HaloNDCatalog(x=host_in["halo_x"], y=host_in["halo_y"], z=host_in["halo_z"], M=host_in["halo_M"], redshift=0.3,
+                          cosmo=synth.COSMO)
+    run = b.BaryonifySnapshot(cat, ps, 5.0, model, verbose=False, device=local)
+    out = run.process()                           # warm-up (pinned staging buffers, table)
+    del out
+    barrier()
+    t0 = time.perf_counter()
+    out = run.process()
+    dt_cat = time.perf_counter() - t0
+    moved = float(np.abs(out["x"][:1000000] - ps.cat["x"][:1000000]).max())
+    del out
+    barrier()
+    t0 = time.perf_counter()
+    grid = run.process_to_map(512)
+    dt_map = time.perf_counter() - t0
+    ok = bool(abs(float(grid.sum()) - n) < 0.5)
+    del grid
+    t = torch.tensor([dt_cat, dt_map], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return {"value": world * n / float(t[0]), "unit": "particles/s", "seconds_per_pass": float(t[0]),
+            "h2d_bytes_per_step": int(world * n * 24), "d2h_bytes_per_step": int(world * n * 24),
+            "api": "BaryonifySnapshot.process(): host structured array in, structured array of displaced particles out",
+            "to_map": {"value": world * n / float(t[1]), "seconds_per_pass": float(t[1]),
+                       "api": "BaryonifySnapshot.process_to_map(512): host particles in, host NGP grid out (per rank; N > 1: the "
+                              "partial grids still have to be summed, parallel.deposit_ngp_all)",
+                       "deposited_mass_equals_particle_count": ok},
+            "pairs": int(run.last_stats.get("n_pairs", 0)), "max_displacement_checked": moved}
+
+
+def particles_cpu_baseline(gaxes, n_cpu=2000000):
+    """The reference's BaryonifySnapshot on the host (oracle/runners_port.baryonify_snapshot: scipy KDTree + the Python halo
+    loop) on a sub-box of the same particle and halo density: 2e6 particles in (100 Mpc)^3 with 3000 halos."""
+    import warnings
+    import baryonforge_b200 as b
+    from baryonforge_b200 import synth
+    from oracle import runners_port as rp
+    from scipy.spatial import KDTree
+    dens = 2e9 / 1000.0 ** 3
+    Lc = (n_cpu / dens) ** (1 / 3.)
+    n_halo = int(round(3e6 * (Lc / 1000.0) ** 3))
+    pos, M = synth.box_halos(n_halo, Lc, seed=42)
+    p = np.random.default_rng(5).uniform(0, Lc, (3, n_cpu))
+    cat = b.HaloNDCatalog(x=pos[0], y=pos[1], z=pos[2], M=M, redshift=0.3, cosmo=synth.COSMO)
+    ps = b.ParticleSnapshot(x=p[0], y=p[1], z=p[2], M=1.0, L=Lc, redshift=0.3, cosmo=synth.COSMO)
+    model = b.DisplacementModel(gaxes, synth.displacement_values(gaxes), 5.0, synth.COSMO)
+    run = b.BaryonifySnapshot(cat, ps, 5.0, model, verbose=False)
+    run.halo_records()
+    sc = run.last_scalars
+    hc = {k: cat.cat[k].astype('<f4') for k in ("M", "x", "y", "z")}
+    t0 = time.perf_counter()
+    tree = KDTree(p.T, boxsize=Lc, leafsize=1000)                 # examples/10: KDTree_kwargs = {'leafsize': 1e3}
+    t_tree = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        _, n_pairs, _ = rp.baryonify_snapshot(list(p), Lc, hc, 1 / 1.3, sc["R_phys"], sc["R_model_com"], 5.0,
+                                              rp.DisplacementTable(gaxes, synth.displacement_values(gaxes), 5.0), tree=tree,
+                                              warn=False)
+    t_loop = time.perf_counter() - t0
+    return {"value": n_cpu / t_loop, "unit": "particles/s", "cores": 1, "kind": "port",
+            "sample": f"{n_cpu} particles in a ({Lc:.0f} Mpc)^3 periodic box (the workload's particle and halo density), {n_halo} halos, "
+                      f"halo loop {t_loop:.1f} s ({n_pairs} pairs); KD-tree build {t_tree:.1f} s stated separately "
+                      "(the reference builds it once per snapshot, SnapshotRunner.py:95-100)",
+            "kdtree_build_s": t_tree}
+
+
 def run_b200(args):
     claim_stdout()
     import torch
@@ -505,6 +595,7 @@ def run_b200(args):
                                              slab=None if world == 1 else (rank, world))
         reduce_ms = 0.0
         d_grid = c4.pop("grid_handle")
+        host_in = c4.pop("host_inputs")
         if world > 1:
             barrier()
             ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -535,6 +626,17 @@ def run_b200(args):
                      "phases_ms_rank0": dict({k: c4[k] for k in ("build_cells_ms", "halo_loop_ms", "apply_deposit_ms")},
                                              ngp_allreduce_ms=reduce_ms),
                      "pairs_per_s_rank0": c4["pairs_per_s"], "halo_loop_alg_frac_rank0": c4["halo_loop_frac"]}
+        # ---- end to end through the reference-shaped API: host ParticleSnapshot (one structured array, utils/io.py:588) ->
+        # BaryonifySnapshot.process() -> structured array of displaced particles on the host; and process_to_map -> host grid
+        try:
+            particles["e2e"] = particles_e2e(args, world, rank, local, dev, c4, host_in, barrier)
+        except Exception as exc:
+            particles["e2e"] = {"error": str(exc)[:300]}
+        if rank == 0 and not args.no_cpu_baseline:
+            try:
+                particles["cpu_baseline"] = particles_cpu_baseline(host_in["gaxes"])
+            except Exception as exc:
+                particles["cpu_baseline"] = {"error": str(exc)[:300]}
         if np.isfinite(float(tp[1])):
             # BaryonifySnapshot.process_to_map: the same cell list and halo loop, then the NGP deposit straight from the
             # cell-ordered particles (no scatter back to the caller's order) -- for callers that only need the grid

@@ -123,6 +123,8 @@ def snapshot_pipeline(n_part, snap_eps=5.0, device=0, reps=2, peak=6650.0, slab=
     tot_ms = ms_b + ms_h + ms_a
     out = dict(n_part=n_part, L=Lbox, halos=n_halo, halos_in_box=n_halo_box, ncell=ncell, eps=snap_eps, pairs=npairs,
                slab=None if slab is None else [x_lo, x_hi], grid_handle=d_grid,
+               host_inputs=dict(halo_x=rec[:, _lib.HB_X].copy(), halo_y=rec[:, _lib.HB_Y].copy(), halo_z=rec[:, _lib.HB_Z].copy(),
+                                halo_M=np.exp(rec[:, _lib.HB_LNM]), x_lo=x_lo, x_hi=x_hi, gaxes=gaxes),
                build_cells_ms=ms_b, halo_loop_ms=ms_h, apply_deposit_ms=ms_a,
                particles_per_s=n_part / tot_ms * 1e3, pairs_per_s=npairs / ms_h * 1e3,
                halo_loop_alg_GBs=72 * npairs / ms_h / 1e6, halo_loop_frac=72 * npairs / ms_h / 1e6 / peak,
@@ -228,6 +230,7 @@ def main():
     if "c4" in args.which:
         out["c4_snapshot"] = snapshot_pipeline(args.npart, args.snap_eps, 0, 2, peak)
         out["c4_snapshot"].pop("grid_handle", None)
+        out["c4_snapshot"].pop("host_inputs", None)
 
     print(json.dumps(out))
 
