@@ -4,7 +4,7 @@ HEALPix FITS maps on disk -- the data format on the input side of the shell runn
 The reference reads a shell with `hp.read_map(path)` (BaryonForge/utils/io.py:346-347); healpy is a third-party dependency
 that is not always installed next to a GPU box, so `read_map` / `write_map` here restate what that call does for the files
 healpy itself writes: the first binary-table extension holds the map as big-endian columns (TFORMn = '1024E', 'D', ...),
-pixel order from the ORDERING card, full sky (INDXSCHM = IMPLICIT).  Like hp.read_map's defaults: field 0, RING order
+pixel order from the ORDERING card, full sky (INDXSCHM = IMPLICIT) or partial sky (EXPLICIT, a PIXEL column).  Like hp.read_map's defaults: field 0, RING order
 out (a NESTED file is re-ordered), native-endian array of the column's own type.  Host-side I/O only: nothing here is on
 the per-halo hot path.
 """
@@ -102,12 +102,16 @@ def nest2ring(nside, ipnest):
     return n_before + jp - 1
 
 
+UNSEEN = -1.6375e30     # healpy's marker of a pixel without data
+
+
 def read_map(path, field=0, nest=False, hdu=1):
     """
     hp.read_map(path) for full-sky maps (BaryonForge/utils/io.py:347): column `field` of binary-table extension `hdu`,
     flattened row by row, in RING order (nest=False, healpy's default; nest=True returns NESTED order; a file in the other
     order is re-ordered), as a native-endian numpy array of the column's type.  Scaled columns (TSCALn / TZEROn) are
-    applied; partial-sky files (INDXSCHM = EXPLICIT) are not supported.
+    applied.  Partial-sky files (INDXSCHM = EXPLICIT: a PIXEL column followed by the data columns, as hp.write_map(...,
+    partial=True) writes them) come back as a full-sky array with UNSEEN (-1.6375e30) in the pixels the file does not list.
     """
     with open(path, 'rb') as f:
         h = _read_header(f)
@@ -121,11 +125,13 @@ def read_map(path, field=0, nest=False, hdu=1):
             f.seek(start + ((size + _BLOCK - 1) // _BLOCK) * _BLOCK)
         if str(h.get('XTENSION', '')).strip() != 'BINTABLE':
             raise ValueError("HDU %d of %s is not a binary table" % (hdu, path))
-        if str(h.get('INDXSCHM', 'IMPLICIT')).strip().upper() == 'EXPLICIT':
-            raise NotImplementedError("partial-sky HEALPix files (INDXSCHM = EXPLICIT) are not supported")
+        explicit = str(h.get('INDXSCHM', 'IMPLICIT')).strip().upper() == 'EXPLICIT'
         nrow, rowbytes, nfield = int(h['NAXIS2']), int(h['NAXIS1']), int(h['TFIELDS'])
-        if not 0 <= field < nfield:
-            raise IndexError("field %d out of range (file has %d)" % (field, nfield))
+        if explicit:            # partial-sky file: column 1 holds the pixel numbers, `field` counts the data columns after it
+            field = field + 1
+        if not (1 if explicit else 0) <= field < nfield:
+            raise IndexError("field %d out of range (file has %d data columns)" % (field - (1 if explicit else 0),
+                                                                                    nfield - (1 if explicit else 0)))
         fields = []
         for i in range(1, nfield + 1):
             tform = str(h['TFORM%d' % i]).strip()
@@ -149,6 +155,7 @@ def read_map(path, field=0, nest=False, hdu=1):
             if rows.size != nrow:
                 raise ValueError("truncated FITS table")
             col = rows['f%d' % (field + 1)].reshape(-1)
+            pix = rows['f1'].reshape(-1).astype(np.int64) if explicit else None
     if nfield == 1 and col.dtype.byteorder == '>':
         out = col.byteswap(inplace=True).view(col.dtype.newbyteorder('='))     # our own buffer: swap in place (6x faster than astype)
     else:
@@ -156,6 +163,14 @@ def read_map(path, field=0, nest=False, hdu=1):
     scale, zero = h.get('TSCAL%d' % (field + 1), 1), h.get('TZERO%d' % (field + 1), 0)
     if scale != 1 or zero != 0:
         out = out * scale + zero
+    if explicit:
+        # hp.read_map on a partial-sky file: a full-sky array of UNSEEN with the listed pixels filled in
+        nside = int(h['NSIDE'])
+        if pix.size != out.size or (pix.size and (pix.min() < 0 or pix.max() >= 12 * nside * nside)):
+            raise ValueError("PIXEL column does not match the data column / NSIDE")
+        full = np.full(12 * nside * nside, UNSEEN, dtype=out.dtype if out.dtype.kind == 'f' else np.float64)
+        full[pix] = out
+        out = full
     nside = int(h.get('NSIDE', int(round(np.sqrt(out.size / 12.0)))))
     if 12 * nside * nside != out.size:
         raise ValueError("Wrong pixel number (it is not 12*nside**2)")
@@ -194,9 +209,10 @@ def _pad(b, fill):
     return b + fill * ((-len(b)) % _BLOCK)
 
 
-def write_map(path, m, nest=False, dtype=None, column_name='TEMPERATURE', overwrite=False):
+def write_map(path, m, nest=False, dtype=None, column_name='TEMPERATURE', overwrite=False, partial=False):
     """hp.write_map(path, m) for one full-sky map: a primary HDU and one BINTABLE with 1024-pixel rows (one pixel per row
-    below nside = 32), big-endian, ORDERING / NSIDE / INDXSCHM cards as healpy writes them."""
+    below nside = 32), big-endian, ORDERING / NSIDE / INDXSCHM cards as healpy writes them.  partial=True writes the
+    partial-sky form instead: only the pixels that are not UNSEEN, one per row, behind a PIXEL column (INDXSCHM = EXPLICIT)."""
     import os
     m = np.asarray(m)
     if dtype is not None:
@@ -204,6 +220,30 @@ def write_map(path, m, nest=False, dtype=None, column_name='TEMPERATURE', overwr
     nside = int(round(np.sqrt(m.size / 12.0)))
     if m.ndim != 1 or 12 * nside * nside != m.size:
         raise ValueError("Wrong pixel number (it is not 12*nside**2)")
+    if partial:
+        if m.dtype.str[1:] not in ('f4', 'f8'):
+            raise TypeError("partial-sky maps are floating point (UNSEEN marks the missing pixels)")
+        if os.path.exists(path) and not overwrite:
+            raise OSError("File %s already exists (overwrite=False)" % path)
+        pix = np.flatnonzero(m != m.dtype.type(UNSEEN)).astype('>i8')
+        rows = np.empty(pix.size, dtype=[('p', '>i8'), ('v', m.dtype.newbyteorder('>'))])
+        rows['p'], rows['v'] = pix, m[pix]
+        code = {'f4': 'E', 'f8': 'D'}[m.dtype.str[1:]]
+        prim = [_card('SIMPLE', True, 'conforms to FITS standard'), _card('BITPIX', 8), _card('NAXIS', 0), _card('EXTEND', True),
+                '%-80s' % 'END']
+        ext = [_card('XTENSION', 'BINTABLE', 'binary table extension'), _card('BITPIX', 8), _card('NAXIS', 2),
+               _card('NAXIS1', rows.dtype.itemsize), _card('NAXIS2', pix.size), _card('PCOUNT', 0), _card('GCOUNT', 1),
+               _card('TFIELDS', 2), _card('TTYPE1', 'PIXEL'), _card('TFORM1', '1K'), _card('TTYPE2', column_name),
+               _card('TFORM2', '1' + code), _card('PIXTYPE', 'HEALPIX', 'HEALPIX pixelisation'),
+               _card('ORDERING', 'NESTED' if nest else 'RING', 'Pixel ordering scheme, either RING or NESTED'),
+               _card('NSIDE', nside, 'Resolution parameter of HEALPIX'),
+               _card('INDXSCHM', 'EXPLICIT', 'Indexing: IMPLICIT or EXPLICIT'), _card('OBJECT', 'PARTIAL'), _card('GRAIN', 1),
+               '%-80s' % 'END']
+        with open(path, 'wb') as f:
+            f.write(_pad(''.join(prim).encode('ascii'), b' '))
+            f.write(_pad(''.join(ext).encode('ascii'), b' '))
+            f.write(_pad(rows.tobytes(), b'\0'))
+        return
     code = {'f4': 'E', 'f8': 'D', 'i2': 'I', 'i4': 'J', 'i8': 'K', 'u1': 'B'}.get(m.dtype.str[1:])
     if code is None:
         raise TypeError("unsupported map dtype %s" % m.dtype)

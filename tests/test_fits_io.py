@@ -89,3 +89,29 @@ def test_lightcone_shell_reads_a_path(tmp_path):
     fits.write_map(path, m)
     shell = b.LightconeShell(path=path, cosmo=synth.COSMO, redshift=0.3)
     assert shell.NSIDE == 16 and np.array_equal(shell.map, m) and shell.data is shell.map
+
+
+def test_partial_sky_files_round_trip_like_healpy(tmp_path):
+    """INDXSCHM = EXPLICIT (hp.write_map(..., partial=True)): a PIXEL column + the data column, one listed pixel per row;
+    hp.read_map returns the full sky with UNSEEN in the pixels the file does not list -- in RING or NESTED order."""
+    from baryonforge_b200 import fits
+    nside = 16
+    npix = 12 * nside * nside
+    rng = np.random.default_rng(3)
+    m = np.full(npix, fits.UNSEEN)
+    seen = np.sort(rng.choice(npix, 500, replace=False))
+    m[seen] = rng.uniform(-5, 5, seen.size)
+    for dt in (np.float64, np.float32):
+        p = str(tmp_path / f"partial_{np.dtype(dt).name}.fits")
+        fits.write_map(p, m, dtype=dt, partial=True)
+        got = fits.read_map(p)
+        assert got.shape == (npix,) and got.dtype == np.dtype(dt)
+        assert np.array_equal(got, m.astype(dt))
+        assert np.array_equal(np.flatnonzero(got != np.dtype(dt).type(fits.UNSEEN)), seen)
+        # the same pixels, asked for in NESTED order
+        ring_of_nest = fits.nest2ring(nside, np.arange(npix))
+        assert np.array_equal(fits.read_map(p, nest=True), m.astype(dt)[ring_of_nest])
+    with pytest.raises(IndexError):
+        fits.read_map(p, field=1)                              # one data column only
+    shell_map = fits.read_map(p)
+    assert np.count_nonzero(shell_map == np.float32(fits.UNSEEN)) == npix - seen.size

@@ -20,6 +20,10 @@ def test_map_runners_match_reference_fixture(name):
     g = load(name)
     got = product_run(g)
     assert_close(got, g["out"], name)
+    if "paint" in str(g["kind"]) or "anis" in str(g["kind"]):
+        # painted maps span many orders of magnitude and have no cancellation: the absolute floor of the default tolerance
+        # (1e-9 of the map's maximum) would hide errors in their faint pixels, so these are also held to a floor of 1e-13
+        assert_close(got, g["out"], name + " (faint pixels)", atol_scale=1e-13)
 
 
 @pytest.mark.parametrize("name", golden_names("shell_bary"))
