@@ -62,7 +62,19 @@ def _worker(rank, world, port, q):
     outs = parallel.SimpleParallel(jobs).process()
     ok_simple = (len(outs) == 5 and all(np.array_equal(o, np.full(7, float(i)) + np.arange(7)) for i, o in enumerate(outs))
                  and [j.ran_on for j in jobs] == [rank if i % world == rank else None for i in range(5)])
-    q.put((rank, bool(ok_gather), bool(ok_reduce and ok_simple), int(keep.sum())))
+    # "do all ranks share one machine?" -- the gate of the CUDA-IPC / shared-host-map path: yes here; no as soon as one rank
+    # reports another node (BFG_FAKE_NODE stands in for a second host); no when torchrun says the node holds fewer ranks
+    ok_node = parallel.single_node_group() is True
+    parallel._SINGLE_NODE.clear()
+    os.environ["BFG_FAKE_NODE"] = "node%d" % rank
+    ok_node = ok_node and parallel.single_node_group() is False
+    parallel._SINGLE_NODE.clear()
+    os.environ["BFG_FAKE_NODE"] = ""
+    os.environ["LOCAL_WORLD_SIZE"] = "1"
+    ok_node = ok_node and parallel.single_node_group() is False
+    del os.environ["LOCAL_WORLD_SIZE"]
+    parallel._SINGLE_NODE.clear()
+    q.put((rank, bool(ok_gather), bool(ok_reduce and ok_simple and ok_node), int(keep.sum())))
     dist.destroy_process_group()
 
 
