@@ -74,6 +74,10 @@ _SIGNATURES = {
                              c_i64, c_i64, c_ptr, c_ptr], C.c_int),
     "bfg_grid_regrid": ([C.c_int, c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_ptr], C.c_int),
     "bfg_snap_build_cells": ([C.c_int, c_i64, c_ptr, c_ptr, c_ptr, c_dbl, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr], C.c_int),
+    "bfg_snap_build_cells_strided": ([C.c_int, c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_dbl, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr,
+                                      c_ptr, c_ptr], C.c_int),
+    "bfg_snap_apply_records": ([C.c_int, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_dbl, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int,
+                                c_ptr], C.c_int),
     "bfg_snap_offsets": ([c_ptr, C.c_int, c_i64, c_ptr, c_ptr, c_ptr, c_dbl, C.c_int, c_ptr, c_i64, c_ptr, c_ptr, C.c_int,
                           c_ptr, c_ptr, c_ptr], C.c_int),
     "bfg_snap_apply": ([C.c_int, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr], C.c_int),

@@ -30,6 +30,18 @@ int retain_async_pool();
         }                                                                                  \
     } while (0)
 
+// Stream-ordered scratch that is handed back on EVERY return path of an entry point (BFG_CUDA_OK / BFG_REQUIRE return early).
+struct StreamScratch {
+    void *p = nullptr;
+    cudaStream_t st;
+    explicit StreamScratch(cudaStream_t s) : st(s) {}
+    StreamScratch(const StreamScratch &) = delete;
+    StreamScratch &operator=(const StreamScratch &) = delete;
+    ~StreamScratch() { if (p) cudaFreeAsync(p, st); }
+    cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes ? bytes : 1, st); }
+    template <class T> T *as() const { return (T *)p; }
+};
+
 #define BFG_REQUIRE(cond, msg)                                    \
     do {                                                          \
         if (!(cond)) {                                            \

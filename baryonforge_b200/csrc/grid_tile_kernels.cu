@@ -268,14 +268,14 @@ int launch_grid_tiles(bool paint, const bfg_table *t, i64 N, double res, double 
     g.ntiles = (i64)g.ntI * g.ntA * g.ntB;
     if (g.ntiles >= ((i64)1 << 31)) return BFG_ERR_UNSUPPORTED;
     if (int rc = retain_async_pool()) return rc;
-    unsigned int *counts = nullptr, *pair_halo = nullptr;
-    i64 *tile_start = nullptr;
-    unsigned long long *queue = nullptr;
-    void *scan_tmp = nullptr;
+    StreamScratch s_counts(st), s_start(st), s_queue(st), s_scan(st), s_pairs(st), s_rows(st), s_valid(st);   // freed on every return
     size_t scan_bytes = 0;
-    BFG_CUDA_OK(cudaMallocAsync(&counts, sizeof(unsigned int) * (g.ntiles + 1), st));
-    BFG_CUDA_OK(cudaMallocAsync(&tile_start, sizeof(i64) * (g.ntiles + 1) * 2, st));
-    BFG_CUDA_OK(cudaMallocAsync(&queue, sizeof(unsigned long long), st));
+    BFG_CUDA_OK(s_counts.alloc(sizeof(unsigned int) * (g.ntiles + 1)));
+    BFG_CUDA_OK(s_start.alloc(sizeof(i64) * (g.ntiles + 1) * 2));
+    BFG_CUDA_OK(s_queue.alloc(sizeof(unsigned long long)));
+    unsigned int *counts = s_counts.as<unsigned int>();
+    i64 *tile_start = s_start.as<i64>();
+    unsigned long long *queue = s_queue.as<unsigned long long>();
     BFG_CUDA_OK(cudaMemsetAsync(counts, 0, sizeof(unsigned int) * (g.ntiles + 1), st));
     BFG_CUDA_OK(cudaMemsetAsync(queue, 0, sizeof(unsigned long long), st));
     i64 *counts64 = tile_start + (g.ntiles + 1);
@@ -285,22 +285,23 @@ int launch_grid_tiles(bool paint, const bfg_table *t, i64 N, double res, double 
     k_widen_counts<<<tblocks, 256, 0, st>>>(g.ntiles, counts, counts64);
     BFG_CUDA_OK(cudaGetLastError());
     BFG_CUDA_OK(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, counts64, tile_start, g.ntiles + 1, st));
-    BFG_CUDA_OK(cudaMallocAsync(&scan_tmp, scan_bytes, st));
-    BFG_CUDA_OK(cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, counts64, tile_start, g.ntiles + 1, st));
+    BFG_CUDA_OK(s_scan.alloc(scan_bytes));
+    BFG_CUDA_OK(cub::DeviceScan::ExclusiveSum(s_scan.p, scan_bytes, counts64, tile_start, g.ntiles + 1, st));
     i64 n_pairs = 0;   // the pair list is sized on the host: one 8-byte read-back per call
     BFG_CUDA_OK(cudaMemcpyAsync(&n_pairs, tile_start + g.ntiles, sizeof(i64), cudaMemcpyDeviceToHost, st));
     BFG_CUDA_OK(cudaStreamSynchronize(st));
-    BFG_CUDA_OK(cudaMallocAsync(&pair_halo, sizeof(unsigned int) * std::max<i64>(n_pairs, 1), st));
+    BFG_CUDA_OK(s_pairs.alloc(sizeof(unsigned int) * std::max<i64>(n_pairs, 1)));
+    unsigned int *pair_halo = s_pairs.as<unsigned int>();
     BFG_CUDA_OK(cudaMemsetAsync(counts, 0, sizeof(unsigned int) * (g.ntiles + 1), st));
     k_tile_fill<<<hblocks, 256, 0, st>>>(g, n_halo, d_halos, tile_start, counts, pair_halo);
     BFG_CUDA_OK(cudaGetLastError());
     const double2 *g_l2tab = nullptr;
     if (int rc = get_log2_table(&g_l2tab)) return rc;
     // blended rows of all halos (n_halo x NR doubles; 4 GB for 10^6 halos x 500 nodes)
-    double *rows = nullptr;
-    unsigned char *rows_valid = nullptr;
-    BFG_CUDA_OK(cudaMallocAsync(&rows, sizeof(double) * n_halo * t->view.n[2], st));
-    BFG_CUDA_OK(cudaMallocAsync(&rows_valid, (size_t)n_halo, st));
+    BFG_CUDA_OK(s_rows.alloc(sizeof(double) * n_halo * t->view.n[2]));
+    BFG_CUDA_OK(s_valid.alloc((size_t)n_halo));
+    double *rows = s_rows.as<double>();
+    unsigned char *rows_valid = s_valid.as<unsigned char>();
     k_blend_rows<<<(int)std::min<i64>(n_halo, 148 * 32), 128, 0, st>>>(t->view, n_halo, d_halos, d_extras, n_extra, rows,
                                                                      rows_valid);
     BFG_CUDA_OK(cudaGetLastError());
@@ -314,13 +315,6 @@ int launch_grid_tiles(bool paint, const bfg_table *t, i64 N, double res, double 
         k_tile_gather<false><<<blocks, TILE_THREADS, 0, st>>>(t->view, g, res, scale, d_halos, rows, rows_valid, d_out,
                                                              tile_start, pair_halo, queue, g_l2tab);
     BFG_CUDA_OK(cudaGetLastError());
-    BFG_CUDA_OK(cudaFreeAsync(rows_valid, st));
-    BFG_CUDA_OK(cudaFreeAsync(rows, st));
-    BFG_CUDA_OK(cudaFreeAsync(pair_halo, st));
-    BFG_CUDA_OK(cudaFreeAsync(scan_tmp, st));
-    BFG_CUDA_OK(cudaFreeAsync(queue, st));
-    BFG_CUDA_OK(cudaFreeAsync(tile_start, st));
-    BFG_CUDA_OK(cudaFreeAsync(counts, st));
     return BFG_OK;
 }
 

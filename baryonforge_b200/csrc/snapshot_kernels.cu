@@ -27,13 +27,15 @@ __device__ __forceinline__ int cell_of(double x, double L, int nc) {
     return min(max(c, 0), nc - 1);
 }
 
+// The caller's particles are read through an element stride: 1 for separate coordinate arrays, 4 for the reference's own
+// layout -- ONE structured array of 32-byte records (M, x, y, z), utils/io.py:588 -- uploaded as raw bytes.
 template <int NDIM>
 __global__ void k_cell_count(i64 n, const double *__restrict__ x, const double *__restrict__ y,
-                             const double *__restrict__ z, double L, int nc, int *__restrict__ cell_id,
+                             const double *__restrict__ z, i64 stride, double L, int nc, int *__restrict__ cell_id,
                              unsigned long long *__restrict__ counts) {
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
-        int c = cell_of(x[i], L, nc) * nc + cell_of(y[i], L, nc);
-        if (NDIM == 3) c = c * nc + cell_of(z[i], L, nc);
+        int c = cell_of(x[i * stride], L, nc) * nc + cell_of(y[i * stride], L, nc);
+        if (NDIM == 3) c = c * nc + cell_of(z[i * stride], L, nc);
         cell_id[i] = c;
         atomicAdd(counts + c, 1ULL);
     }
@@ -44,14 +46,14 @@ __global__ void k_cell_count(i64 n, const double *__restrict__ x, const double *
 // a fifth of the HBM rate).  k_unpack_records turns the records back into the SoA arrays with coalesced traffic.
 template <int NDIM>
 __global__ void k_cell_fill(i64 n, const double *__restrict__ x, const double *__restrict__ y,
-                            const double *__restrict__ z, const int *__restrict__ cell_id,
+                            const double *__restrict__ z, i64 stride, const int *__restrict__ cell_id,
                             const i64 *__restrict__ cell_start, unsigned long long *__restrict__ cursor,
                             double4 *__restrict__ rec) {
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
         int c = cell_id[i];
         i64 slot = cell_start[c] + (i64)atomicAdd(cursor + c, 1ULL);
         double4 r;
-        r.x = x[i]; r.y = y[i]; r.z = (NDIM == 3) ? z[i] : 0.0; r.w = __longlong_as_double(i);
+        r.x = x[i * stride]; r.y = y[i * stride]; r.z = (NDIM == 3) ? z[i * stride] : 0.0; r.w = __longlong_as_double(i);
         rec[slot] = r;
     }
 }
@@ -63,13 +65,13 @@ __global__ void k_cell_fill(i64 n, const double *__restrict__ x, const double *_
 // Pass B reads the bucket-ordered records coalesced and places them in their cells; everything in flight then lands in a
 // window of a few MB.
 __global__ void k_cell_coarse(i64 n, const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ z,
-                              const int *__restrict__ cell_id, const i64 *__restrict__ cell_start, int group, i64 ncells,
+                              i64 stride, const int *__restrict__ cell_id, const i64 *__restrict__ cell_start, int group, i64 ncells,
                               unsigned long long *__restrict__ cursor_a, double4 *__restrict__ tmp) {
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
         const i64 b = cell_id[i] / group;
         const i64 slot = cell_start[min(b * group, ncells)] + (i64)atomicAdd(cursor_a + b, 1ULL);
         double4 r;
-        r.x = x[i]; r.y = y[i]; r.z = z ? z[i] : 0.0; r.w = __longlong_as_double(i);
+        r.x = x[i * stride]; r.y = y[i * stride]; r.z = z ? z[i * stride] : 0.0; r.w = __longlong_as_double(i);
         tmp[slot] = r;
     }
 }
@@ -251,6 +253,28 @@ __global__ void k_snap_apply(i64 n, const double *__restrict__ xs, const double 
     }
 }
 
+__device__ __forceinline__ void put_field(double4 &r, int f, double v) {
+    r.x = (f == 0) ? v : r.x; r.y = (f == 1) ? v : r.y; r.z = (f == 2) ? v : r.z; r.w = (f == 3) ? v : r.w;
+}
+
+// k_snap_apply for callers that hold the particles as 32-byte records (the reference's structured array: M, x, y, z in any
+// field order): `new_cat = copy of cat with x, y(, z) replaced` (SnapshotRunner.py:263-273) as ONE full-sector read and ONE
+// full-sector write per particle, in place or into a second record array -- no column arrays, no unpack pass.
+template <int NDIM>
+__global__ void k_snap_apply_records(i64 n, const double *__restrict__ xs, const double *__restrict__ ys,
+                                     const double *__restrict__ zs, const double *__restrict__ tot,
+                                     const i64 *__restrict__ order, double L, const double4 *rec_in, double4 *rec_out,
+                                     int fx, int fy, int fz) {
+    for (i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (i64)gridDim.x * blockDim.x) {
+        const i64 j = order[p];
+        double4 r = rec_in[j];
+        put_field(r, fx, wrap_once(xs[p] + tot[p], L));
+        put_field(r, fy, wrap_once(ys[p] + tot[n + p], L));
+        if (NDIM == 3) put_field(r, fz, wrap_once(zs[p] + tot[2 * n + p], L));
+        rec_out[j] = r;
+    }
+}
+
 // np.histogramdd bin of x on edges = np.linspace(0, L, N+1): searchsorted(side='right') - 1, x == L -> last bin
 __device__ __forceinline__ i64 ngp_bin(double x, double L, i64 N, double step) {
     if (!(x >= 0.0) || !(x <= L)) return -1;
@@ -304,61 +328,62 @@ int blocks_for(i64 n, int threads) { return (int)std::max<i64>(1, std::min<i64>(
 extern "C" int bfg_snap_build_cells(int ndim, int64_t n_part, const double *d_x, const double *d_y, const double *d_z,
                                     double L, int ncell, int64_t *d_cell_start, int64_t *d_order, double *d_xs,
                                     double *d_ys, double *d_zs, void *stream) {
+    return bfg_snap_build_cells_strided(ndim, n_part, d_x, d_y, d_z, 1, L, ncell, d_cell_start, d_order, d_xs, d_ys, d_zs, stream);
+}
+
+extern "C" int bfg_snap_build_cells_strided(int ndim, int64_t n_part, const double *d_x, const double *d_y, const double *d_z,
+                                            int64_t stride, double L, int ncell, int64_t *d_cell_start, int64_t *d_order,
+                                            double *d_xs, double *d_ys, double *d_zs, void *stream) {
     BFG_REQUIRE(ndim == 2 || ndim == 3, "ndim must be 2 or 3");
+    BFG_REQUIRE(stride >= 1, "stride must be >= 1");
     BFG_REQUIRE(d_x && d_y && (ndim == 2 || d_z) && d_cell_start && d_order && d_xs && d_ys && (ndim == 2 || d_zs), "null argument");
     BFG_REQUIRE(ncell >= 1 && (ndim == 2 ? ncell <= 32768 : ncell <= 1024), "ncell out of range");
     BFG_REQUIRE(L > 0, "L must be positive");
     if (int rc = retain_async_pool()) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const i64 ncells = (ndim == 3) ? (i64)ncell * ncell * ncell : (i64)ncell * ncell;
-    int *cell_id = nullptr;
-    unsigned long long *counts = nullptr;
-    void *scan_tmp = nullptr;
+    StreamScratch s_cell(st), s_counts(st), s_scan(st), s_rec(st), s_tmp(st), s_cursor(st);   // released on every return path
     size_t scan_bytes = 0;
-    BFG_CUDA_OK(cudaMallocAsync(&cell_id, sizeof(int) * std::max<i64>(n_part, 1), st));
-    BFG_CUDA_OK(cudaMallocAsync(&counts, sizeof(unsigned long long) * (ncells + 1), st));
+    BFG_CUDA_OK(s_cell.alloc(sizeof(int) * std::max<i64>(n_part, 1)));
+    BFG_CUDA_OK(s_counts.alloc(sizeof(unsigned long long) * (ncells + 1)));
+    int *cell_id = s_cell.as<int>();
+    unsigned long long *counts = s_counts.as<unsigned long long>();
     BFG_CUDA_OK(cudaMemsetAsync(counts, 0, sizeof(unsigned long long) * (ncells + 1), st));
     if (n_part > 0) {
-        if (ndim == 3) k_cell_count<3><<<blocks_for(n_part, 256), 256, 0, st>>>(n_part, d_x, d_y, d_z, L, ncell, cell_id, counts);
-        else k_cell_count<2><<<blocks_for(n_part, 256), 256, 0, st>>>(n_part, d_x, d_y, d_z, L, ncell, cell_id, counts);
+        if (ndim == 3) k_cell_count<3><<<blocks_for(n_part, 256), 256, 0, st>>>(n_part, d_x, d_y, d_z, stride, L, ncell, cell_id, counts);
+        else k_cell_count<2><<<blocks_for(n_part, 256), 256, 0, st>>>(n_part, d_x, d_y, d_z, stride, L, ncell, cell_id, counts);
         BFG_CUDA_OK(cudaGetLastError());
     }
     BFG_CUDA_OK(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (const i64 *)counts, (i64 *)d_cell_start, ncells + 1, st));
-    BFG_CUDA_OK(cudaMallocAsync(&scan_tmp, scan_bytes, st));
-    BFG_CUDA_OK(cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, (const i64 *)counts, (i64 *)d_cell_start, ncells + 1, st));
+    BFG_CUDA_OK(s_scan.alloc(scan_bytes));
+    BFG_CUDA_OK(cub::DeviceScan::ExclusiveSum(s_scan.p, scan_bytes, (const i64 *)counts, (i64 *)d_cell_start, ncells + 1, st));
     BFG_CUDA_OK(cudaMemsetAsync(counts, 0, sizeof(unsigned long long) * (ncells + 1), st));
     if (n_part > 0) {
-        double4 *rec = nullptr;   // 32-byte particle records (stream-ordered scratch)
-        BFG_CUDA_OK(cudaMallocAsync(&rec, sizeof(double4) * n_part, st));
+        BFG_CUDA_OK(s_rec.alloc(sizeof(double4) * n_part));   // 32-byte particle records
+        double4 *rec = s_rec.as<double4>();
         const char *mode = getenv("BFG_CELL_SORT");      // 1 = single-pass scatter (A/B); default: two passes above 65536 cells
         const bool two_pass = !(mode && mode[0] == '1') && ncells > 65536;
-        double4 *tmp = nullptr;
-        unsigned long long *cursor_a = nullptr;
         if (two_pass) {
             const int group = (int)std::max<i64>(ncell, (ncells + 65535) / 65536);
             const i64 n_buckets = (ncells + group - 1) / group;
-            BFG_CUDA_OK(cudaMallocAsync(&tmp, sizeof(double4) * n_part, st));
-            BFG_CUDA_OK(cudaMallocAsync(&cursor_a, sizeof(unsigned long long) * n_buckets, st));
+            BFG_CUDA_OK(s_tmp.alloc(sizeof(double4) * n_part));
+            BFG_CUDA_OK(s_cursor.alloc(sizeof(unsigned long long) * n_buckets));
+            double4 *tmp = s_tmp.as<double4>();
+            unsigned long long *cursor_a = s_cursor.as<unsigned long long>();
             BFG_CUDA_OK(cudaMemsetAsync(cursor_a, 0, sizeof(unsigned long long) * n_buckets, st));
-            k_cell_coarse<<<blocks_for(n_part, 256), 256, 0, st>>>(n_part, d_x, d_y, ndim == 3 ? d_z : nullptr, cell_id,
+            k_cell_coarse<<<blocks_for(n_part, 256), 256, 0, st>>>(n_part, d_x, d_y, ndim == 3 ? d_z : nullptr, stride, cell_id,
                                                                    (const i64 *)d_cell_start, group, ncells, cursor_a, tmp);
             if (ndim == 3) k_cell_fine<3><<<blocks_for(n_part, 256), 256, 0, st>>>(n_part, tmp, L, ncell, (const i64 *)d_cell_start, counts, rec);
             else k_cell_fine<2><<<blocks_for(n_part, 256), 256, 0, st>>>(n_part, tmp, L, ncell, (const i64 *)d_cell_start, counts, rec);
         } else if (ndim == 3) {
-            k_cell_fill<3><<<blocks_for(n_part, 256), 256, 0, st>>>(n_part, d_x, d_y, d_z, cell_id, (const i64 *)d_cell_start, counts, rec);
+            k_cell_fill<3><<<blocks_for(n_part, 256), 256, 0, st>>>(n_part, d_x, d_y, d_z, stride, cell_id, (const i64 *)d_cell_start, counts, rec);
         } else {
-            k_cell_fill<2><<<blocks_for(n_part, 256), 256, 0, st>>>(n_part, d_x, d_y, d_z, cell_id, (const i64 *)d_cell_start, counts, rec);
+            k_cell_fill<2><<<blocks_for(n_part, 256), 256, 0, st>>>(n_part, d_x, d_y, d_z, stride, cell_id, (const i64 *)d_cell_start, counts, rec);
         }
         if (ndim == 3) k_unpack_records<3><<<blocks_for(n_part, 256), 256, 0, st>>>(n_part, rec, (i64 *)d_order, d_xs, d_ys, d_zs);
         else k_unpack_records<2><<<blocks_for(n_part, 256), 256, 0, st>>>(n_part, rec, (i64 *)d_order, d_xs, d_ys, d_zs);
         BFG_CUDA_OK(cudaGetLastError());
-        if (tmp) BFG_CUDA_OK(cudaFreeAsync(tmp, st));
-        if (cursor_a) BFG_CUDA_OK(cudaFreeAsync(cursor_a, st));
-        BFG_CUDA_OK(cudaFreeAsync(rec, st));
     }
-    BFG_CUDA_OK(cudaFreeAsync(scan_tmp, st));
-    BFG_CUDA_OK(cudaFreeAsync(counts, st));
-    BFG_CUDA_OK(cudaFreeAsync(cell_id, st));
     return BFG_OK;
 }
 
@@ -399,8 +424,9 @@ extern "C" int bfg_snap_apply(int ndim, int64_t n_part, const double *d_xs, cons
     if (n_part == 0) return BFG_OK;
     cudaStream_t st = (cudaStream_t)stream;
     if (int rc = retain_async_pool()) return rc;
-    double4 *rec = nullptr;
-    BFG_CUDA_OK(cudaMallocAsync(&rec, sizeof(double4) * n_part, st));
+    StreamScratch s_rec(st);
+    BFG_CUDA_OK(s_rec.alloc(sizeof(double4) * n_part));
+    double4 *rec = s_rec.as<double4>();
     if (ndim == 3) {
         k_snap_apply<3><<<blocks_for(n_part, 256), 256, 0, st>>>(n_part, d_xs, d_ys, d_zs, d_tot, (const i64 *)d_order, L, rec);
         k_unpack_records<3><<<blocks_for(n_part, 256), 256, 0, st>>>(n_part, rec, nullptr, d_x_out, d_y_out, d_z_out);
@@ -409,7 +435,26 @@ extern "C" int bfg_snap_apply(int ndim, int64_t n_part, const double *d_xs, cons
         k_unpack_records<2><<<blocks_for(n_part, 256), 256, 0, st>>>(n_part, rec, nullptr, d_x_out, d_y_out, d_z_out);
     }
     BFG_CUDA_OK(cudaGetLastError());
-    BFG_CUDA_OK(cudaFreeAsync(rec, st));
+    return BFG_OK;
+}
+
+extern "C" int bfg_snap_apply_records(int ndim, int64_t n_part, const double *d_xs, const double *d_ys, const double *d_zs,
+                                      const double *d_tot, const int64_t *d_order, double L, const double *d_rec_in,
+                                      double *d_rec_out, int fx, int fy, int fz, void *stream) {
+    BFG_REQUIRE(ndim == 2 || ndim == 3, "ndim must be 2 or 3");
+    BFG_REQUIRE(d_xs && d_ys && d_tot && d_order && d_rec_in && d_rec_out && (ndim == 2 || d_zs), "null argument");
+    BFG_REQUIRE((((uintptr_t)d_rec_in | (uintptr_t)d_rec_out) & 31) == 0, "records must be 32-byte aligned");
+    BFG_REQUIRE(fx >= 0 && fx < 4 && fy >= 0 && fy < 4 && fx != fy, "bad field slots");
+    BFG_REQUIRE(ndim == 2 || (fz >= 0 && fz < 4 && fz != fx && fz != fy), "bad field slots");
+    if (n_part == 0) return BFG_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ndim == 3)
+        k_snap_apply_records<3><<<blocks_for(n_part, 256), 256, 0, st>>>(n_part, d_xs, d_ys, d_zs, d_tot, (const i64 *)d_order, L,
+                                                                         (const double4 *)d_rec_in, (double4 *)d_rec_out, fx, fy, fz);
+    else
+        k_snap_apply_records<2><<<blocks_for(n_part, 256), 256, 0, st>>>(n_part, d_xs, d_ys, d_zs, d_tot, (const i64 *)d_order, L,
+                                                                         (const double4 *)d_rec_in, (double4 *)d_rec_out, fx, fy, fz);
+    BFG_CUDA_OK(cudaGetLastError());
     return BFG_OK;
 }
 

@@ -193,7 +193,9 @@ struct PlanSlot { int device = -1; int N = 0; cufftHandle plan = 0; };
 std::mutex g_plan_mutex;
 PlanSlot g_plans[16];
 
-int get_plan(int N, cufftHandle *out) {
+// Caller holds g_plan_mutex from here until the plan's Exec has been issued: a plan is bound to one stream at a time, and a
+// full cache evicts slot 0, which no other thread can be using while the lock is held.
+int get_plan_locked(int N, cufftHandle *out) {
     const CufftApi &api = cufft_api();
     if (!api.ok) {
         set_error("bfg_grid_power_spectrum: cuFFT (libcufft.so.11) could not be loaded; set BFG_CUFFT_LIB");
@@ -201,7 +203,6 @@ int get_plan(int N, cufftHandle *out) {
     }
     int dev = 0;
     BFG_CUDA_OK(cudaGetDevice(&dev));
-    std::lock_guard<std::mutex> lock(g_plan_mutex);
     PlanSlot *free_slot = nullptr;
     for (PlanSlot &s : g_plans) {
         if (s.N == N && s.device == dev) { *out = s.plan; return BFG_OK; }
@@ -282,15 +283,17 @@ extern "C" int bfg_grid_power_spectrum(int64_t N, const double *d_grid, const do
     BFG_REQUIRE(N >= 2 && N <= 4096 && Nk >= 1 && Nk <= 8192 && dk > 0, "bad argument");
     BFG_REQUIRE(d_grid && d_klin && d_pk_sum && d_k_sum && d_count, "null argument");
     cudaStream_t st = (cudaStream_t)stream;
-    cufftHandle plan = 0;
-    if (int rc = get_plan((int)N, &plan)) return rc;
     if (int rc = retain_async_pool()) return rc;
     const CufftApi &api = cufft_api();
-    double2 *spec = nullptr;
-    BFG_CUDA_OK(cudaMallocAsync(&spec, sizeof(double2) * (size_t)N * N * (N / 2 + 1), st));
+    StreamScratch s_spec(st);
     int rc = BFG_OK;
+    double2 *spec = nullptr;
     {
-        std::lock_guard<std::mutex> lock(g_plan_mutex);      // a plan is bound to one stream at a time
+        std::lock_guard<std::mutex> lock(g_plan_mutex);
+        cufftHandle plan = 0;
+        if (int prc = get_plan_locked((int)N, &plan)) return prc;
+        BFG_CUDA_OK(s_spec.alloc(sizeof(double2) * (size_t)N * N * (N / 2 + 1)));
+        spec = s_spec.as<double2>();
         cufftResult r = api.SetStream(plan, st);
         if (r == CUFFT_SUCCESS) r = api.ExecD2Z(plan, const_cast<double *>(d_grid), (cufftDoubleComplex *)spec);
         if (r != CUFFT_SUCCESS) {
@@ -299,10 +302,5 @@ extern "C" int bfg_grid_power_spectrum(int64_t N, const double *d_grid, const do
         }
     }
     if (rc == BFG_OK) rc = launch_power_bins((int)N, spec, d_klin, k0, dk, (int)Nk, d_pk_sum, d_k_sum, d_count, st);
-    cudaError_t e = cudaFreeAsync(spec, st);
-    if (rc == BFG_OK && e != cudaSuccess) {
-        set_error("bfg_grid_power_spectrum: cudaFreeAsync -> %s", cudaGetErrorString(e));
-        rc = BFG_ERR_CUDA;
-    }
     return rc;
 }

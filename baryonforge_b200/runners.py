@@ -193,6 +193,103 @@ def _fields_to_device(cat, names, dev):
     return outs
 
 
+_RAW_CHUNK = 1 << 24        # doubles per staging chunk of a raw record copy (128 MB)
+_RAW_RESULT_MAX_BYTES = int(float(os.environ.get("BFG_PINNED_RESULT_MAX_GB", "24")) * 2 ** 30)
+
+
+def _record_layout(cat, names):
+    """
+    Slot (in doubles) of every field when `cat` is what the reference's ParticleSnapshot holds (utils/io.py:588): ONE
+    C-contiguous structured array of 32-byte records made of four native float64 fields, `names` among them.  Such a catalogue
+    crosses the host link as raw bytes -- contiguous copies at memory speed -- and the device reads the coordinates out of the
+    records with a stride; anything else returns None and takes the per-field path (_fields_to_device).
+    """
+    dt = cat.dtype
+    if dt.names is None or dt.itemsize != 32 or len(dt.names) != 4 or cat.ndim != 1 or not cat.flags.c_contiguous:
+        return None
+    slots = {}
+    for nm in dt.names:
+        fdt, off = dt.fields[nm][:2]
+        if fdt != np.dtype('<f8') or off % 8:
+            return None
+        slots[nm] = off // 8
+    if sorted(slots.values()) != [0, 1, 2, 3] or any(nm not in slots for nm in names):
+        return None
+    return slots
+
+
+def _raw_to_device(flat, dev):
+    """Contiguous float64 host array (pageable) -> device tensor: host threads copy chunk k + 1 into a ring of page-locked
+    buffers (plain memcpy, the GIL is released) while chunk k is on its way over the link."""
+    torch = _torch()
+    n = flat.shape[0]
+    out = torch.empty(n, dtype=torch.float64, device=dev)
+    if n == 0:
+        return out
+    chunk = max(1, min(_RAW_CHUNK, n))
+    nbuf = 3
+    bufs = [_take_scratch(chunk) for _ in range(nbuf)]
+    evs = [None] * nbuf
+    stream = torch.cuda.current_stream()
+    nth = max(1, _host_threads())
+    with ThreadPoolExecutor(max_workers=nth) as ex:
+        for k, a in enumerate(range(0, n, chunk)):
+            b = min(n, a + chunk)
+            slot = k % nbuf
+            if evs[slot] is not None:
+                evs[slot].synchronize()                          # the copy that last used this buffer has left the host
+            dst = bufs[slot].numpy()[:b - a]
+            step = -(-(b - a) // nth)
+            list(ex.map(lambda i: np.copyto(dst[i:i + step], flat[a + i:a + i + step]), range(0, b - a, step)))
+            out[a:b].copy_(bufs[slot][:b - a], non_blocking=True)
+            evs[slot] = stream.record_event()
+    for e in evs:
+        if e is not None:
+            e.synchronize()
+    _give_scratch(bufs)
+    return out
+
+
+def _device_to_raw(d_flat):
+    """
+    Device tensor -> float64 host array.  Up to BFG_PINNED_RESULT_MAX_GB (24) the result IS a recycled page-locked buffer
+    (_pinned_result: one DMA, no host copy; the buffer returns to the pool when the caller drops the array); beyond that it
+    is ordinary memory filled through the page-locked ring by host threads while the next chunk comes down.
+    """
+    torch = _torch()
+    n = d_flat.numel()
+    if n * 8 <= _RAW_RESULT_MAX_BYTES:
+        t, arr = _pinned_result(n)
+        t.copy_(d_flat, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return arr
+    out = np.empty(n, dtype=np.float64)
+    chunk = max(1, min(_RAW_CHUNK, n))
+    nbuf = 3
+    bufs = [_take_scratch(chunk) for _ in range(nbuf)]
+    stream = torch.cuda.current_stream()
+    nth = max(1, _host_threads())
+    jobs = []
+    with ThreadPoolExecutor(max_workers=nth) as ex:
+        def drain(job):
+            slot, ev, a, b = job
+            ev.synchronize()
+            src = bufs[slot].numpy()[:b - a]
+            step = -(-(b - a) // nth)
+            list(ex.map(lambda i: np.copyto(out[a + i:a + i + step], src[i:i + step]), range(0, b - a, step)))
+        for k, a in enumerate(range(0, n, chunk)):
+            b = min(n, a + chunk)
+            if len(jobs) == nbuf:
+                drain(jobs.pop(0))
+            slot = k % nbuf
+            bufs[slot][:b - a].copy_(d_flat[a:b], non_blocking=True)
+            jobs.append((slot, stream.record_event(), a, b))
+        while jobs:
+            drain(jobs.pop(0))
+    _give_scratch(bufs)
+    return out
+
+
 def _device_to_fields(d_cols, out_cat, names):
     """The way back: contiguous device tensors -> the strided fields of a structured array, chunked through page-locked buffers
     with the host-side scatter of chunk k running while chunk k + 1 comes down."""
@@ -1911,8 +2008,20 @@ class BaryonifySnapshot(DefaultRunnerSnapshot):
 
     def process(self):
         ps = self.ParticleSnapshot
-        d_p = self.process_on_device()
         names = ['x', 'y', 'z'][:(2 if ps.is2D else 3)]
+        S = self._displace_sorted()
+        if S.get('d_raw') is not None:
+            # the catalogue is on the device as raw 32-byte records: replace x, y(, z) inside the records (one sector read, one
+            # sector write per particle) and bring the records back as they are -- no per-field traffic on either side
+            d_raw, slots, d_s = S['d_raw'], S['slots'], S['d_s']
+            with _torch().cuda.device(S['dev']):
+                _lib.check(_lib.lib().bfg_snap_apply_records(S['ndim'], S['n_part'], _lib.ptr(d_s[0]), _lib.ptr(d_s[1]),
+                                                             _lib.ptr(d_s[2]), _lib.ptr(S['d_tot']), _lib.ptr(S['d_order']),
+                                                             S['L'], _lib.ptr(d_raw), _lib.ptr(d_raw), slots['x'], slots['y'],
+                                                             slots.get('z', 0), _lib.current_stream()))
+                self._finish_stats(S)
+                return _device_to_raw(d_raw).view(ps.cat.dtype)
+        d_p = self._apply_to_columns(S)
         new_cat = np.empty_like(ps.cat)                                           # :263 (a copy with x, y, z replaced below)
         for name in ps.cat.dtype.names:
             if name not in names:
@@ -1958,6 +2067,7 @@ class BaryonifySnapshot(DefaultRunnerSnapshot):
         with torch.cuda.device(dev):
             st = _lib.current_stream()
             names = ['x', 'y', 'z'][:ndim]
+            d_raw = slots = None
             cells_key = (_Ident(ps.cat), ncell, ndim, str(dev))
             kept = getattr(self, '_cells', None) if getattr(self, 'keep_cells', False) else None
             if kept is not None and kept[0] == cells_key:
@@ -1965,13 +2075,21 @@ class BaryonifySnapshot(DefaultRunnerSnapshot):
                 _, d_s, d_start, d_order = kept
                 d_p = [torch.empty(n_part, dtype=torch.float64, device=dev) for _ in names] + ([None] if ndim == 2 else [])
             else:
-                d_p = _fields_to_device(ps.cat, names, dev) + ([None] if ndim == 2 else [])
+                slots = None if getattr(self, 'keep_cells', False) or os.environ.get("BFG_SNAP_RAW", "1") != "1" \
+                    else _record_layout(ps.cat, names)
                 d_s = [torch.empty(n_part, dtype=torch.float64, device=dev) for _ in names] + ([None] if ndim == 2 else [])
                 d_start = torch.empty(ncell ** ndim + 1, dtype=torch.int64, device=dev)
                 d_order = torch.empty(n_part, dtype=torch.int64, device=dev)
-                _lib.check(L.bfg_snap_build_cells(ndim, n_part, _lib.ptr(d_p[0]), _lib.ptr(d_p[1]), _lib.ptr(d_p[2]), Lbox,
-                                                  ncell, _lib.ptr(d_start), _lib.ptr(d_order), _lib.ptr(d_s[0]),
-                                                  _lib.ptr(d_s[1]), _lib.ptr(d_s[2]), st))
+                if slots is not None:
+                    d_raw = _raw_to_device(ps.cat.view(np.float64), dev)
+                    d_p, base = None, d_raw.data_ptr()
+                    src, stride = [base + 8 * slots[nm] for nm in names] + [None], 4
+                else:
+                    d_p = _fields_to_device(ps.cat, names, dev) + ([None] if ndim == 2 else [])
+                    src, stride = [_lib.ptr(t) for t in d_p], 1
+                _lib.check(L.bfg_snap_build_cells_strided(ndim, n_part, src[0], src[1], src[2], stride, Lbox, ncell,
+                                                          _lib.ptr(d_start), _lib.ptr(d_order), _lib.ptr(d_s[0]),
+                                                          _lib.ptr(d_s[1]), _lib.ptr(d_s[2]), st))
                 if getattr(self, 'keep_cells', False):
                     self._cells = (cells_key, d_s, d_start, d_order)
             d_ext = None if extras is None else _to_device(extras, dev)
@@ -1982,7 +2100,7 @@ class BaryonifySnapshot(DefaultRunnerSnapshot):
                                           Lbox, ncell, _lib.ptr(d_start), n_rec, _lib.ptr(d_rec), _lib.ptr(d_ext),
                                           table.n_extra, _lib.ptr(d_tot), _lib.ptr(d_n), st))
         return dict(dev=dev, ndim=ndim, n_part=n_part, L=Lbox, d_p=d_p, d_s=d_s, d_tot=d_tot, d_order=d_order, d_n=d_n,
-                    ncell=ncell)
+                    ncell=ncell, d_raw=d_raw, slots=slots)
 
     def _finish_stats(self, S):
         self.last_stats = dict(n_pairs=int(S['d_n'].cpu()[0]), ncell=S['ncell'])
@@ -1993,10 +2111,15 @@ class BaryonifySnapshot(DefaultRunnerSnapshot):
         tensors [x, y(, z)] in the caller's particle order, so that what follows in the reference's workflow (NGP deposit,
         P(k): deposit_ngp / spectra.ShellPowerSpectrum) can run without the particles leaving HBM.
         """
+        return self._apply_to_columns(self._displace_sorted())
+
+    def _apply_to_columns(self, S):
         torch = _torch()
-        S = self._displace_sorted()
         d_p, d_s = S['d_p'], S['d_s']
         with torch.cuda.device(S['dev']):
+            if d_p is None:   # the particles came up as raw records: fresh column outputs
+                d_p = [torch.empty(S['n_part'], dtype=torch.float64, device=S['dev']) for _ in range(S['ndim'])] + \
+                      ([None] if S['ndim'] == 2 else [])
             # displaced positions overwrite the (no longer needed) unsorted device copies
             _lib.check(_lib.lib().bfg_snap_apply(S['ndim'], S['n_part'], _lib.ptr(d_s[0]), _lib.ptr(d_s[1]), _lib.ptr(d_s[2]),
                                                  _lib.ptr(S['d_tot']), _lib.ptr(S['d_order']), S['L'], _lib.ptr(d_p[0]),
@@ -2013,12 +2136,22 @@ class BaryonifySnapshot(DefaultRunnerSnapshot):
         torch = _torch()
         ps = self.ParticleSnapshot
         M = ps.cat['M']
-        assert np.isnan(M).sum() == 0, "If you want to make a map, provide a value for the particle mass"   # io.py:659
+        msg = "If you want to make a map, provide a value for the particle mass"                           # io.py:659
         S = self._displace_sorted()
         d_s, ndim = S['d_s'], S['ndim']
         with torch.cuda.device(S['dev']):
-            equal = M.size == 0 or bool(np.all(M == M[0]))
-            d_m = None if equal else _to_device(M, S['dev'], dtype=np.float64)
+            if S.get('d_raw') is not None and 'M' in S['slots'] and M.size:
+                # the masses came up inside the raw records: the NaN and equal-mass scans run on the device copy instead of
+                # two strided passes over the host array
+                col = S['d_raw'].view(-1, 4)[:, S['slots']['M']]
+                flags = torch.stack([torch.isnan(col).any(), (col == col[0]).all()]).cpu()
+                assert not bool(flags[0]), msg
+                equal = bool(flags[1])
+                d_m = None if equal else col.contiguous()
+            else:
+                assert np.isnan(M).sum() == 0, msg
+                equal = M.size == 0 or bool(np.all(M == M[0]))
+                d_m = None if equal else _to_device(M, S['dev'], dtype=np.float64)
             d_grid = torch.zeros((int(N_grid),) * ndim, dtype=torch.float64, device=S['dev'])
             _lib.check(_lib.lib().bfg_snap_apply_deposit(ndim, S['n_part'], _lib.ptr(d_s[0]), _lib.ptr(d_s[1]), _lib.ptr(d_s[2]),
                                                          _lib.ptr(S['d_tot']), _lib.ptr(S['d_order']), _lib.ptr(d_m),

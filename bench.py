@@ -335,8 +335,9 @@ def particles_e2e(args, world, rank, local, dev, c4, host_in, barrier):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return {"value": world * n / float(t[0]), "unit": "particles/s", "seconds_per_pass": float(t[0]),
-            "h2d_bytes_per_step": int(world * n * 24), "d2h_bytes_per_step": int(world * n * 24),
-            "api": "BaryonifySnapshot.process(): host structured array in, structured array of displaced particles out",
+            "h2d_bytes_per_step": int(world * n * 32), "d2h_bytes_per_step": int(world * n * 32),
+            "api": "BaryonifySnapshot.process(): host structured array in (pageable, the reference's 32-byte M, x, y, z records, moved "
+                   "as raw bytes), structured array of displaced particles out",
             "to_map": {"value": world * n / float(t[1]), "seconds_per_pass": float(t[1]),
                        "api": "BaryonifySnapshot.process_to_map(512): host particles in, host NGP grid out (per rank; N > 1: the "
                               "partial grids still have to be summed, parallel.deposit_ngp_all)",

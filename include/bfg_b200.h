@@ -255,6 +255,12 @@ int bfg_grid_regrid(int ndim, int64_t N, const double *d_map_in, const double *d
 int bfg_snap_build_cells(int ndim, int64_t n_part, const double *d_x, const double *d_y, const double *d_z, double L,
                          int ncell, int64_t *d_cell_start, int64_t *d_order, double *d_xs, double *d_ys, double *d_zs,
                          void *stream);
+/* The same with an element stride on the caller's coordinates: stride 4 reads them out of the reference's own particle
+ * container, ONE structured array of 32-byte records (M, x, y, z; utils/io.py:588), uploaded as raw bytes (d_x = records +
+ * slot of 'x', ...).  stride 1 == bfg_snap_build_cells. */
+int bfg_snap_build_cells_strided(int ndim, int64_t n_part, const double *d_x, const double *d_y, const double *d_z,
+                                 int64_t stride, double L, int ncell, int64_t *d_cell_start, int64_t *d_order, double *d_xs,
+                                 double *d_ys, double *d_zs, void *stream);
 /* Halo loop of BaryonifySnapshot.process (SnapshotRunner.py:217-260) over the cell-ordered particles:
  * d_tot [ndim][n_part] (cell order, zeroed by the caller) += displacement * unit vector. */
 int bfg_snap_offsets(const bfg_table *t, int ndim, int64_t n_part, const double *d_xs, const double *d_ys,
@@ -265,6 +271,12 @@ int bfg_snap_offsets(const bfg_table *t, int ndim, int64_t n_part, const double 
 int bfg_snap_apply(int ndim, int64_t n_part, const double *d_xs, const double *d_ys, const double *d_zs,
                    const double *d_tot, const int64_t *d_order, double L, double *d_x_out, double *d_y_out,
                    double *d_z_out, void *stream);
+/* bfg_snap_apply for particles held as 32-byte records of 4 doubles (32-byte aligned): rec_out[order[p]] = rec_in[order[p]]
+ * with the doubles in slots fx, fy(, fz) replaced by the displaced, wrapped coordinates -- the reference's
+ * `new_cat = cat.copy(); new_cat['x'] = ...` (SnapshotRunner.py:263-273).  d_rec_out may be d_rec_in (in place). */
+int bfg_snap_apply_records(int ndim, int64_t n_part, const double *d_xs, const double *d_ys, const double *d_zs,
+                           const double *d_tot, const int64_t *d_order, double L, const double *d_rec_in,
+                           double *d_rec_out, int fx, int fy, int fz, void *stream);
 /* NGP mass deposit = ParticleSnapshot.make_map / np.histogramdd (utils/io.py:629-677); d_grid zeroed by caller. */
 int bfg_snap_deposit_ngp(int ndim, int64_t n_part, const double *d_x, const double *d_y, const double *d_z,
                          const double *d_mass, double L, int64_t n_grid, double *d_grid, void *stream);

@@ -741,3 +741,61 @@ def test_box_device_records_match_host_formulas():
             assert np.array_equal(got[:, f], want[:, f]), ("snap", ndim, f)
         for f in (_lib.HB_RQ, _lib.HB_RCUT, _lib.HB_LNRCOM):
             assert np.allclose(got[:, f], want[:, f], rtol=1e-13, atol=1e-14), ("snap", ndim, f)
+
+
+def test_snapshot_raw_record_path_matches_the_per_field_path(monkeypatch):
+    """BaryonifySnapshot.process() moves the reference's particle container (one structured array of 32-byte M, x, y, z
+    records, utils/io.py:588) over the host link as raw bytes and replaces x, y(, z) inside the records on the device
+    (bfg_snap_build_cells_strided + bfg_snap_apply_records).  Same answer as the per-field staging (BFG_SNAP_RAW=0), with the
+    other fields passed through untouched; several staging chunks; pinned and pageable results; other record layouts."""
+    import baryonforge_b200 as b
+    from baryonforge_b200 import runners, synth
+    n, Lbox = 300000, 60.0
+    rng = np.random.default_rng(77)
+    p = rng.uniform(0, Lbox, (3, n))
+    Mp = rng.uniform(0.5, 2.0, n)
+    pos, M = synth.box_halos(40, Lbox, seed=78)
+    gaxes = synth.table_axes(nz=10, nM=10, nr=500, z_min=0.0, z_max=1.0, z_linear=True, r_min=1e-3, r_max=3e2)
+    model = b.DisplacementModel(gaxes, synth.displacement_values(gaxes), 5.0, synth.COSMO)
+    monkeypatch.setattr(runners, "_RAW_CHUNK", 100003)                   # 12 ragged chunks through the 3-buffer ring
+    for ndim in (3, 2):
+        cat = b.HaloNDCatalog(x=pos[0], y=pos[1], z=pos[2] if ndim == 3 else None, M=M, redshift=0.3, cosmo=synth.COSMO)
+        ps = b.ParticleSnapshot(x=p[0], y=p[1], z=p[2] if ndim == 3 else None, M=Mp, L=Lbox, redshift=0.3, cosmo=synth.COSMO)
+        assert runners._record_layout(ps.cat, ['x', 'y']) == dict(M=0, x=1, y=2, z=3)
+        run = b.BaryonifySnapshot(cat, ps, 5.0, model, verbose=False)
+        monkeypatch.setenv("BFG_SNAP_RAW", "0")
+        want = run.process()
+        want_map = run.process_to_map(32)
+        monkeypatch.setenv("BFG_SNAP_RAW", "1")
+        got = run.process()
+        assert got.dtype == ps.cat.dtype and got.shape == ps.cat.shape
+        assert np.abs(want["x"] - ps.cat["x"]).max() > 1e-6              # something moved
+        for nm in ("x", "y", "z")[:ndim]:
+            assert_close(got[nm], want[nm], f"raw records, {ndim}-D, {nm}", rtol=1e-12, atol_scale=1e-13)
+        assert np.array_equal(got["M"], Mp) and (ndim == 3 or np.array_equal(got["z"], ps.cat["z"]))
+        assert_close(run.process_to_map(32), want_map, f"raw records, {ndim}-D, process_to_map", rtol=1e-12)
+        # a second result does not clobber the first (each is its own recycled page-locked buffer) ...
+        keep = got.copy()
+        run.model = b.DisplacementModel(gaxes, synth.displacement_values(gaxes) * -0.5, 5.0, synth.COSMO)
+        other = run.process()
+        assert np.array_equal(got, keep) and not np.array_equal(other["x"], got["x"])
+        # ... and results above BFG_PINNED_RESULT_MAX_GB come back through the staging ring into ordinary memory
+        monkeypatch.setattr(runners, "_RAW_RESULT_MAX_BYTES", 0)
+        again = run.process()
+        for nm in ps.cat.dtype.names:
+            assert_close(again[nm], other[nm], f"pageable result, {nm}", rtol=1e-12, atol_scale=1e-13)
+        monkeypatch.setattr(runners, "_RAW_RESULT_MAX_BYTES", 1 << 40)
+        # the same particles with the fields in another order take the raw path too; float32 masses do not (per-field path)
+        for dt in ([('x', 'f8'), ('z', 'f8'), ('M', 'f8'), ('y', 'f8')], [('M', 'f4'), ('x', 'f8'), ('y', 'f8'), ('z', 'f8')]):
+            alt = np.zeros(n, dt)
+            for nm in alt.dtype.names:
+                alt[nm] = ps.cat[nm]
+            ps_alt = b.ParticleSnapshot(x=p[0], y=p[1], z=p[2] if ndim == 3 else None, M=Mp, L=Lbox, redshift=0.3,
+                                        cosmo=synth.COSMO)
+            ps_alt.cat = alt
+            assert (runners._record_layout(alt, ['x', 'y']) is not None) == (dt[0][0] == 'x')
+            out = b.BaryonifySnapshot(cat, ps_alt, 5.0, run.model, verbose=False).process()
+            assert out.dtype == alt.dtype
+            for nm in ("x", "y", "z")[:ndim]:
+                assert_close(out[nm], other[nm], f"layout {dt[0][0]}..., {nm}", rtol=1e-12, atol_scale=1e-13)
+            assert np.array_equal(out["M"], alt["M"])
