@@ -1765,6 +1765,9 @@ class BaryonifyGrid(DefaultRunnerGrid):
             del d_off
             d_map_sum = None
             if self.plane_range is not None:
+                shared = self._slab_exchange(N, ndim, lo, hi, dev)
+                if shared is not None:
+                    return self._finish_sharded(shared, d_new, d_map, d_n, orig_map, N, ndim, lo, hi, dev)
                 from .parallel import reduce_partial_map
                 d_new, d_map_sum = reduce_partial_map(d_new, d_map)
             d_sums = torch.zeros(2, dtype=torch.float64, device=dev)
@@ -1783,6 +1786,79 @@ class BaryonifyGrid(DefaultRunnerGrid):
         assert np.isclose(new_sum, old_sum), \
             "ERROR in pixel regridding, sum(new_map) [%0.14e] != sum(oldmap) [%0.14e]" % (new_sum, old_sum)   # :616-619
         return out_np.reshape(orig_map.shape)
+
+
+    def _slab_exchange(self, N, ndim, lo, hi, dev):
+        """
+        The SharedHostMaps of the slab-sharded end-to-end path, or None for the plain all-reduce path.  Taken when the ranks
+        are the NCCL processes of ONE machine and the slabs are parallel.plane_ranges' equal, rank-ordered ones (same test on
+        every rank: it depends on the group and the grid size only, plus a vote on the plane ranges).
+        """
+        from . import parallel
+        dist = parallel._dist()
+        if dist is None or os.environ.get("BFG_EXCHANGE", "p2p") == "allreduce" or not hasattr(os, 'memfd_create'):
+            return None
+        world, rank = dist.get_world_size(), dist.get_rank()
+        if world < 2 or world > 8 or dist.get_backend() != 'nccl' or N % world or not parallel.single_node_group():
+            return None
+        torch = _torch()
+        mine = tuple(parallel.plane_ranges(N, world)[rank]) == (int(lo), int(hi))
+        vote = torch.tensor([1 if mine else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(vote, op=dist.ReduceOp.MIN)
+        if int(vote.cpu()[0]) == 0:
+            return None
+        numel = N ** ndim
+        key = (numel, world, rank, dev.index)
+        if key not in _HOST_MAPS:
+            el = N ** (ndim - 1)
+            _HOST_MAPS[key] = parallel.SharedHostMaps(numel, rank, world, dev.index, own_range=(lo * el, hi * el))
+        return _HOST_MAPS[key]
+
+    def _finish_sharded(self, host, d_new, d_map, d_n, orig_map, N, ndim, lo, hi, dev):
+        """
+        Slab-sharded tail of process(): the CIC deposit of a slab reaches into the neighbouring slabs, so the per-rank partial
+        maps are summed -- by ONE NCCL reduce-scatter that leaves every rank with its own slab of the new map (half the NVLink
+        traffic of the all-reduce) -- and each rank copies only its slab into a page-locked host map that all processes of the
+        box have mapped (parallel.SharedHostMaps): 1 / N of the full-map download per rank instead of N full copies through
+        the one host link.  The small all-reduce of [sum new, sum old, n_updates] is enqueued behind the copy, so its
+        completion also says that every rank's slab has arrived.
+        """
+        torch = _torch()
+        import torch.distributed as dist
+        from .parallel import SegmentsExhausted, reduce_partial_map
+        L = _lib.lib()
+        st = _lib.current_stream()
+        el = N ** (ndim - 1)
+        seg = addr = None
+        try:
+            seg, addr = host.acquire()
+        except SegmentsExhausted:                # raised on all ranks: the caller holds MAX_SEGMENTS earlier results
+            pass
+        except OSError:                          # collective failure (agreed by all ranks)
+            _HOST_MAPS[(N ** ndim, dist.get_world_size(), dist.get_rank(), dev.index)] = None
+        d_acc = torch.zeros(3, dtype=torch.float64, device=dev)
+        if seg is None:                          # private full copy on every rank (the all-reduce path)
+            d_new, d_map_sum = reduce_partial_map(d_new, d_map)
+            _lib.check(L.bfg_sum_f64(_lib.ptr(d_new), d_new.numel(), _lib.ptr(d_acc), st))
+            d_acc[0] /= dist.get_world_size()    # every rank holds the full sum; the all-reduce below adds them up again
+            d_acc[1] = d_map_sum / dist.get_world_size()
+            out, out_np = _pinned_result(orig_map.size)
+            out.copy_(d_new, non_blocking=True)
+        else:
+            own = torch.empty((hi - lo) * el, dtype=torch.float64, device=dev)
+            dist.reduce_scatter_tensor(own, d_new, op=dist.ReduceOp.SUM)
+            _lib.check(L.bfg_copy_to_host_async(addr + 8 * lo * el, own.data_ptr(), 8 * own.numel(), st))
+            _lib.check(L.bfg_sum_f64(own.data_ptr(), own.numel(), _lib.ptr(d_acc), st))
+            _lib.check(L.bfg_sum_f64(_lib.ptr(d_map), d_map.numel(), d_acc.data_ptr() + 8, st))
+        d_acc[2] = d_n.reshape(()).to(torch.float64)                 # counts are < 2^53: exact as float64
+        dist.all_reduce(d_acc)
+        acc = d_acc.cpu()
+        torch.cuda.current_stream().synchronize()
+        new_sum, old_sum = float(acc[0]), float(acc[1])
+        self.last_stats = dict(n_updates=int(acc[2]), new_sum=new_sum, old_sum=old_sum, sharded=True)
+        assert np.isclose(new_sum, old_sum), \
+            "ERROR in pixel regridding, sum(new_map) [%0.14e] != sum(oldmap) [%0.14e]" % (new_sum, old_sum)   # :616-619
+        return host.export(seg, orig_map.shape) if seg is not None else out_np.reshape(orig_map.shape)
 
 
 class PaintProfilesGrid(DefaultRunnerGrid):

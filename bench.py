@@ -76,7 +76,12 @@ def parse():
     ap.add_argument("--no-particles", action="store_true",
                     help="skip the secondary metric (BaryonifySnapshot particles displaced/s, weak scaling)")
     ap.add_argument("--particles-per-gpu", type=int, default=250000000)
-    ap.add_argument("--config", default="shell", choices=["shell", "lightcone", "paint"],
+    ap.add_argument("--grid-n", type=int, default=1024, help="grid leg / --config grid: cells per axis")
+    ap.add_argument("--grid-halos", type=int, default=1000000, help="grid leg / --config grid: halos in the box")
+    ap.add_argument("--leg-timeout", type=float, default=240.0, help="seconds after which a hanging extra leg is abandoned")
+    ap.add_argument("--no-extra-configs", action="store_true",
+                    help="skip the BASELINE configs[2] (BaryonifyGrid 1024^3) and configs[4] (20-shell lightcone) legs of the default line")
+    ap.add_argument("--config", default="shell", choices=["shell", "lightcone", "paint", "grid"],
                     help="shell = the headline line (one BaryonifyShell shell, BASELINE metric); lightcone = configs[4] (20 shells "
                          "on N GPUs); paint = configs[1] (PaintProfilesShell NSIDE=1024, 10^5 halos) -- bench_modes.py")
     ap.add_argument("--shells", type=int, default=20, help="--config lightcone: shells in the lightcone")
@@ -584,7 +589,7 @@ def run_b200(args):
     # weak scaling: every rank owns one x-slab share of the 2e9-particle box (configs[3]: 2.5e8 particles per GPU at N = 8)
     particles = None
     if not args.no_particles:
-        del d_off, d_new, d_map, d_rec_sorted
+        d_off.resize_(0); d_new.resize_(0); d_map.resize_(0); d_rec_sorted.resize_(0)     # give the HBM back (names stay bound)
         torch.cuda.empty_cache()
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import bench_configs
@@ -647,64 +652,107 @@ def run_b200(args):
 
     if world > 1:
         dist.barrier()
-    if rank != 0:
+
+    def make_line():
+        peak, peak_src = peaks()
+        upd_per_launch = n_up_local if world == 1 else n_up / world
+        achieved = ALG_BYTES_PER_UPDATE * upd_per_launch / (ms_kernel * 1e-3) / 1e9
+        facts = ncu_facts(workload_name(args)) if world == 1 else {}
+        # The resources that bind this kernel (profiles/README.md, round 2) are not HBM: (1) the L2's fp64 atomic unit -- ncu
+        # lts__d_atomic_input_cycles_active of the committed capture -- and (2) the arithmetic itself: with the REDs compiled out the
+        # kernel is only ~10 % faster.  For (2) the ceiling is what the FP64 pipe could do if it issued nothing but this loop's FP64
+        # instructions, at the SM clock measured DURING the timed region: SMs x 64 FP64 lanes per clock x clock / (FP64-pipe
+        # instructions per update, counted in the committed SASS of the pixel loop).
+        fp64_per_upd = facts.get("fp64_inst_per_update")
+        sm_mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz")
+        binding = {"resource": "L2 fp64 atomic unit, co-limited by the arithmetic (FP64 pipe + instruction issue)",
+                   "l2_atomic_unit_busy_frac": (facts.get("l2_atomic_input_active_pct") or 0) / 100.0 or None,
+                   "l2_red_sectors_per_launch": facts.get("l2_red_sectors"),
+                   "kernel_ms_without_reds": facts.get("kernel_ms_without_reds"),
+                   "fp64_inst_per_update": fp64_per_upd, "fp64_inst_source": facts.get("fp64_inst_source"),
+                   "sm_clock_mhz": sm_mhz, "ncu_source": facts.get("source")}
         if world > 1:
-            dist.destroy_process_group()
-        return
-    peak, peak_src = peaks()
-    upd_per_launch = n_up_local if world == 1 else n_up / world
-    achieved = ALG_BYTES_PER_UPDATE * upd_per_launch / (ms_kernel * 1e-3) / 1e9
-    facts = ncu_facts(workload_name(args)) if world == 1 else {}
-    # The resources that bind this kernel (profiles/README.md, round 2) are not HBM: (1) the L2's fp64 atomic unit -- ncu
-    # lts__d_atomic_input_cycles_active of the committed capture -- and (2) the arithmetic itself: with the REDs compiled out the
-    # kernel is only ~10 % faster.  For (2) the ceiling is what the FP64 pipe could do if it issued nothing but this loop's FP64
-    # instructions, at the SM clock measured DURING the timed region: SMs x 64 FP64 lanes per clock x clock / (FP64-pipe
-    # instructions per update, counted in the committed SASS of the pixel loop).
-    fp64_per_upd = facts.get("fp64_inst_per_update")
-    sm_mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz")
-    binding = {"resource": "L2 fp64 atomic unit, co-limited by the arithmetic (FP64 pipe + instruction issue)",
-               "l2_atomic_unit_busy_frac": (facts.get("l2_atomic_input_active_pct") or 0) / 100.0 or None,
-               "l2_red_sectors_per_launch": facts.get("l2_red_sectors"),
-               "kernel_ms_without_reds": facts.get("kernel_ms_without_reds"),
-               "fp64_inst_per_update": fp64_per_upd, "fp64_inst_source": facts.get("fp64_inst_source"),
-               "sm_clock_mhz": sm_mhz, "ncu_source": facts.get("source")}
-    if world > 1:
-        binding = {"note": "per-kernel ncu facts are captured at N = 1 (profiles/shell_halos_ncu_facts.json); see that line"}
-    if world == 1 and fp64_per_upd and sm_mhz:
-        ceil_ups = B200_SMS * FP64_LANES_PER_SM_CLK * sm_mhz * 1e6 / fp64_per_upd
-        binding.update({"fp64_ceiling_updates_s": ceil_ups,
-                        "frac_fp64": upd_per_launch / (ms_kernel * 1e-3) / ceil_ups,
-                        "ncu_fp64_pipe_active_pct": facts.get("fp64_pipe_active_pct"),
-                        "ncu_issue_active_pct": facts.get("issue_active_pct")})
-    line = {"metric": "halo-pixel updates/s (BaryonifyShell)", "value": value, "unit": "halo-pixel updates/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args), "n_updates_per_step": int(n_up),
-                       "l2_policy": "working set (4.8 GB offsets + 3.2 GB maps per step) >> 126 MB L2; no flush needed",
-                       "sharding": "none" if world == 1 else (
-                           f"RING pixel ranges x{world}, overlap halos replicated, " + (
-                               "re-binning fused with the exchange (fp64 REDs into the owner's slice over NVLink peer memory) + " + (
-                                   "new map left distributed over the ranks that own its slices (as in the end-to-end path)" if (not args.gather_result)
-                                   else "NCCL all-gather of slices")
-                               if peers is not None else "NCCL all-reduce of partial maps"))},
-            "clocks": clocks, "gpu_launches": n_launch,
-            "roofline": {"bound": "hbm", "kernel": "k_shell_halos<baryonify> (fused disc/separation/table/accumulate)",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": facts.get("dram_bytes_per_launch"), "traffic_source": facts.get("source"),
-                         "peak_source": peak_src, "alg_bytes_per_update": ALG_BYTES_PER_UPDATE,
-                         "alg_bytes_per_launch": ALG_BYTES_PER_UPDATE * upd_per_launch,
-                         "kernel_ms": ms_kernel, "binding": binding,
-                         "note": "algorithmic bytes = the reference dataflow's 3 f64 read-modify-writes per update (SURVEY 8d). "
-                                 "With sky-ordered halos those REDs are absorbed by the 126 MB L2 (`traffic` = measured DRAM "
-                                 "bytes of one launch, ~1/25 of algorithmic), so `frac` can exceed 1 and says nothing about "
-                                 "efficiency; read `binding`: the L2 atomic unit is `l2_atomic_unit_busy_frac` busy, and the "
-                                 "arithmetic alone (`kernel_ms_without_reds`) is almost as slow as the whole kernel"},
-            "e2e": e2e, "particles": particles}
-    if parity_vs_n1 is not None:
-        line["parity_vs_n1"] = parity_vs_n1
-    if not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(args, cat, model, axes, vals, args.cpu_sample)
-    emit(line)
+            binding = {"note": "per-kernel ncu facts are captured at N = 1 (profiles/shell_halos_ncu_facts.json); see that line"}
+        if world == 1 and fp64_per_upd and sm_mhz:
+            ceil_ups = B200_SMS * FP64_LANES_PER_SM_CLK * sm_mhz * 1e6 / fp64_per_upd
+            binding.update({"fp64_ceiling_updates_s": ceil_ups,
+                            "frac_fp64": upd_per_launch / (ms_kernel * 1e-3) / ceil_ups,
+                            "ncu_fp64_pipe_active_pct": facts.get("fp64_pipe_active_pct"),
+                            "ncu_issue_active_pct": facts.get("issue_active_pct")})
+        line = {"metric": "halo-pixel updates/s (BaryonifyShell)", "value": value, "unit": "halo-pixel updates/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload_name(args), "n_updates_per_step": int(n_up),
+                           "l2_policy": "working set (4.8 GB offsets + 3.2 GB maps per step) >> 126 MB L2; no flush needed",
+                           "sharding": "none" if world == 1 else (
+                               f"RING pixel ranges x{world}, overlap halos replicated, " + (
+                                   "re-binning fused with the exchange (fp64 REDs into the owner's slice over NVLink peer memory) + " + (
+                                       "new map left distributed over the ranks that own its slices (as in the end-to-end path)" if (not args.gather_result)
+                                       else "NCCL all-gather of slices")
+                                   if peers is not None else "NCCL all-reduce of partial maps"))},
+                "clocks": clocks, "gpu_launches": n_launch,
+                "roofline": {"bound": "hbm", "kernel": "k_shell_halos<baryonify> (fused disc/separation/table/accumulate)",
+                             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": facts.get("dram_bytes_per_launch"), "traffic_source": facts.get("source"),
+                             "peak_source": peak_src, "alg_bytes_per_update": ALG_BYTES_PER_UPDATE,
+                             "alg_bytes_per_launch": ALG_BYTES_PER_UPDATE * upd_per_launch,
+                             "kernel_ms": ms_kernel, "binding": binding,
+                             "note": "algorithmic bytes = the reference dataflow's 3 f64 read-modify-writes per update (SURVEY 8d). "
+                                     "With sky-ordered halos those REDs are absorbed by the 126 MB L2 (`traffic` = measured DRAM "
+                                     "bytes of one launch, ~1/25 of algorithmic), so `frac` can exceed 1 and says nothing about "
+                                     "efficiency; read `binding`: the L2 atomic unit is `l2_atomic_unit_busy_frac` busy, and the "
+                                     "arithmetic alone (`kernel_ms_without_reds`) is almost as slow as the whole kernel"},
+                "e2e": e2e, "particles": particles}
+        if parity_vs_n1 is not None:
+            line["parity_vs_n1"] = parity_vs_n1
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args, cat, model, axes, vals, args.cpu_sample)
+        return line
+
+    line = make_line() if rank == 0 else None
+
+    # ---- BASELINE configs[2] and configs[4] at their stated sizes, as legs of this line (so that the driver's N = 1..8 runs
+    # measure them).  The headline line is complete at this point; a watchdog prints it and ends the process if a leg hangs
+    # (a collective some rank never reaches), and an exception inside a leg only marks that leg.
+    if not args.no_extra_configs:
+        import gc
+        import threading
+        import bench_modes
+        del d_off, d_new, d_map, d_rec_sorted
+        state = {"leg": None, "deadline": None}
+
+        def watchdog():
+            while state["deadline"] is not None:
+                time.sleep(1.0)
+                dl = state["deadline"]
+                if dl is not None and time.monotonic() > dl:
+                    if line is not None:
+                        line[state["leg"]] = {"error": f"leg exceeded {args.leg_timeout} s and was abandoned"}
+                        emit(line)
+                    os._exit(0)
+        for name, fn in (("grid", bench_modes.grid_leg), ("lightcone", bench_modes.lightcone_leg)):
+            gc.collect()
+            torch.cuda.empty_cache()
+            barrier()
+            state["leg"], state["deadline"] = name, time.monotonic() + args.leg_timeout
+            if name == "grid":
+                th = threading.Thread(target=watchdog, daemon=True)
+                th.start()
+            try:
+                kw = {"cpu_baseline": not args.no_cpu_baseline} if name == "grid" else {}
+                res = fn(args, sys.modules[__name__], rank, world, local, **kw)
+            except Exception as exc:       # a leg must never take the headline line down with it
+                res = {"error": f"{type(exc).__name__}: {str(exc)[:300]}"}
+            if line is not None:
+                line[name] = res
+        state["leg"], state["deadline"] = "extra_legs_exit_barrier", time.monotonic() + 120.0
+        if world > 1:
+            dist.barrier()
+        state["deadline"] = None
+    elif world > 1:
+        dist.barrier()
+    if rank == 0:
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -719,6 +767,9 @@ def main():
     elif args.config == "paint":
         import bench_modes
         bench_modes.run_paint(args, sys.modules[__name__])
+    elif args.config == "grid":
+        import bench_modes
+        bench_modes.run_grid(args, sys.modules[__name__])
     else:
         run_b200(args)
 

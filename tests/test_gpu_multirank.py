@@ -67,6 +67,15 @@ def _worker(rank, world, port, q):
     out2 = b.PaintProfilesShell(cat, shell, 20, pmodel, verbose=False, device=rank, pix_range=pr).process()
     out3 = b.BaryonifyGrid(gcat, gm, 6, gmodel, verbose=False, device=rank,
                            plane_range=parallel.plane_ranges(N, world)[rank]).process()
+    # the slab-sharded grid path (reduce-scatter + every rank's slab into the shared host map) against the all-reduce route
+    os.environ["BFG_EXCHANGE"] = "allreduce"
+    grun = b.BaryonifyGrid(gcat, gm, 6, gmodel, verbose=False, device=rank, plane_range=parallel.plane_ranges(N, world)[rank])
+    out3b = grun.process()
+    del os.environ["BFG_EXCHANGE"]
+    held_err = max(held_err, float(np.max(np.abs(out3b - out3))))
+    out3c = [grun.process() for _ in range(8)]        # more held results than SharedHostMaps has segments: private copies
+    held_err = max(held_err, max(float(np.max(np.abs(o - out3))) for o in out3c))
+    del out3b, out3c
     # anisotropic shell painter, sharded: the total-mass pass, its global sum and the gather all cross the ranks
     from helpers import load as _load
     ga = _load("shell_anis_n32_background")
