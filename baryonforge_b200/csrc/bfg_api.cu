@@ -4,6 +4,8 @@
 #include <vector>
 #include <cmath>
 #include <algorithm>
+#include <cstdlib>
+#include <mutex>
 #include "bfg_common.cuh"
 
 namespace bfg {
@@ -51,6 +53,52 @@ int get_log2_table(const double2 **d_tab) {
         tabs[dev] = d;
     }
     *d_tab = tabs[dev];
+    return BFG_OK;
+}
+namespace {
+// ring r (1 .. 4 nside - 1): colatitude by the literal ring formula of get_interpol (ring_theta_info), z and sin(theta) by the
+// polar-cap accurate forms (ring_z_sth)
+__global__ void k_ring_table(Hpx h, RingTabEntry *__restrict__ tab) {
+    const i64 n = 4 * h.nside;
+    for (i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (i64)gridDim.x * blockDim.x) {
+        RingTabEntry e = {0.0, 1.0, 0.0, 0.0};
+        if (r >= 1) {
+            i64 start, nr;
+            bool shifted;
+            ring_theta_info(h, r, start, nr, e.theta, shifted);
+            ring_z_sth(h, r, e.z, e.sth);
+        }
+        tab[r] = e;
+    }
+}
+}  // namespace
+
+int get_ring_table(long long nside, const RingTabEntry **d_tab, void *stream) {
+    struct Slot { int dev; long long nside; RingTabEntry *tab; };
+    static Slot slots[64];
+    static int n_slots = 0;
+    static std::mutex mu;
+    *d_tab = nullptr;
+    const char *lit = getenv("BFG_REGRID_LITERAL");
+    if ((lit && lit[0] == '1') || nside < 32) return BFG_OK;      // coarse maps: ring spacing beyond the small-angle series
+    int dev = 0;
+    BFG_CUDA_OK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    for (int i = 0; i < n_slots; ++i)
+        if (slots[i].dev == dev && slots[i].nside == nside) { *d_tab = slots[i].tab; return BFG_OK; }
+    if (n_slots == 64) return BFG_OK;                             // cache full: the literal path is always correct
+    RingTabEntry *tab = nullptr;
+    BFG_CUDA_OK(cudaMalloc(&tab, sizeof(RingTabEntry) * 4 * nside));
+    k_ring_table<<<(int)std::min<long long>((4 * nside + 255) / 256, 148 * 4), 256, 0, (cudaStream_t)stream>>>(Hpx(nside), tab);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);   // other streams may use the table next
+    if (e != cudaSuccess) {
+        cudaFree(tab);
+        set_error("get_ring_table: %s", cudaGetErrorString(e));
+        return BFG_ERR_CUDA;
+    }
+    slots[n_slots++] = Slot{dev, nside, tab};
+    *d_tab = tab;
     return BFG_OK;
 }
 }  // namespace bfg

@@ -20,6 +20,10 @@ void set_error(const char *fmt, ...);
 // Keep stream-ordered scratch (cudaMallocAsync) cached in the device's default pool instead of handing it back to
 // the OS at every synchronisation (the default release threshold is 0).  Idempotent per device.
 int retain_async_pool();
+struct RingTabEntry;
+// Per-(device, nside) table of ring colatitudes for regrid_target_fast; *d_tab = nullptr when BFG_REGRID_LITERAL=1 or the
+// map is too coarse for the small-angle forms (nside < 32).
+int get_ring_table(long long nside, const RingTabEntry **d_tab, void *stream);
 
 #define BFG_CUDA_OK(expr)                                                                  \
     do {                                                                                   \
@@ -458,6 +462,86 @@ __device__ __forceinline__ void get_interpol(const Hpx &h, double theta, double 
         w[0] *= 1.0 - wt; w[1] *= 1.0 - wt;
         w[2] *= wt; w[3] *= wt;
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Re-binning target of one displaced pixel without the acos / atan2 / sincos / cos / acos / acos chain of the literal
+// restatement (vec2ang -> degrees -> radians -> get_interp_weights, HealpixRunner.py:357-365).  The displaced direction is
+// close to the source pixel's, so the two angles the weights need come from exact small-angle forms:
+//   azimuth      phi'  = phi_src + atan(cross / dot),   cross = x oy - y ox  (no cancellation),  dot = x x' + y y'
+//   colatitude   theta' - theta_1 = asin(sin theta' cos theta_1 - cos theta' sin theta_1)   (ring 1 = the ring above theta')
+// with odd series for |t|, |s| <= 0.05 (truncation < 2e-16 relative).  theta_1, theta_2 and their cos / sin come from a
+// per-nside ring table built once with the literal ring formulas (ring_theta_info / ring_z_sth), so the denominator
+// theta_2 - theta_1 has the reference's bits.  Round-off differs from the literal chain at the 1e-16 level in the angles,
+// i.e. ~1e-12 in a weight (the literal chain itself carries ~1e-11 through phi / dphi); a displaced direction within
+// round-off of a ring boundary may pick the neighbouring ring pair, where the bilinear weights are continuous.
+// Returns false (caller takes the literal path) next to the poles, for large displacements and for coarse maps.
+struct RingTabEntry { double theta, z, sth, pad; };
+
+__device__ __forceinline__ bool regrid_target_fast(const Hpx &h, const RingTabEntry *__restrict__ rt, i64 p, double ox,
+                                                   double oy, double oz, i64 pix[4], double w[4]) {
+    i64 ring, ip, start, nr;
+    bool shifted;
+    pix2ring(h, p, ring, ip);
+    ring_info(h, ring, start, nr, shifted);
+    const double z = __ldg(&rt[ring].z), sth = __ldg(&rt[ring].sth);
+    // azimuth of the source pixel in units of pi (exact half-integers over 2 nr)
+    const double a_pi = (ring < h.nside || ring >= 3 * h.nside) ? ((double)ip + 0.5) * (2.0 / (double)nr)
+                                                                : ((double)ip + (shifted ? 0.5 : 0.0)) * (2.0 / (double)nr);
+    double sn, cs;
+    sincospi(a_pi, &sn, &cs);
+    const double x = sth * cs, y = sth * sn;
+    const double xn = x + ox, yn = y + oy, zn = z + oz;                       // HealpixRunner.py:357 (not re-normalised)
+    const double cross = x * oy - y * ox, dot = fma(x, ox, fma(y, oy, sth * sth));
+    if (!(dot > 0.0)) return false;
+    const double t = cross / dot;
+    if (!(fabs(t) <= 0.05)) return false;
+    const double t2 = t * t;
+    const double dphi_s = t * fma(t2, fma(t2, fma(t2, fma(t2, 1.0 / 9.0, -1.0 / 7.0), 0.2), -1.0 / 3.0), 1.0);
+    double phi = fma(a_pi, BFG_PI, dphi_s);
+    if (phi < 0.0) phi += BFG_TWOPI;
+    if (phi >= BFG_TWOPI) phi -= BFG_TWOPI;
+    const double rho2 = fma(xn, xn, yn * yn);
+    const double inv_dn = 1.0 / sqrt(fma(zn, zn, rho2));
+    const double zc = zn * inv_dn, rs = sqrt(rho2) * inv_dn;                  // cos, sin of the displaced colatitude
+    const i64 ir1 = ring_above(h, zc), ir2 = ir1 + 1;
+    if (ir1 < 1 || ir2 > 4 * h.nside - 1) return false;                       // polar caps' first / last ring: literal path
+    const double th1 = __ldg(&rt[ir1].theta), z1 = __ldg(&rt[ir1].z), s1r = __ldg(&rt[ir1].sth), th2 = __ldg(&rt[ir2].theta);
+    const double s = fma(rs, z1, -(zc * s1r));                                // sin(theta' - theta_1)
+    if (!(fabs(s) <= 0.05)) return false;
+    const double s2 = s * s;
+    const double dth = s * fma(s2, fma(s2, fma(s2, fma(s2, 35.0 / 1152.0, 15.0 / 336.0), 0.075), 1.0 / 6.0), 1.0);
+    const double wt = dth / (th2 - th1);
+    i64 sp, nr1;
+    bool sh;
+    double w1;
+    ring_info(h, ir1, sp, nr1, sh);
+    ring_pair(nr1, sh, sp, phi, pix[0], pix[1], w1);
+    w[0] = (1.0 - w1) * (1.0 - wt); w[1] = w1 * (1.0 - wt);
+    ring_info(h, ir2, sp, nr1, sh);
+    ring_pair(nr1, sh, sp, phi, pix[2], pix[3], w1);
+    w[2] = (1.0 - w1) * wt; w[3] = w1 * wt;
+    return true;
+}
+
+// The literal chain (kept as the checked fallback): vec2ang(lonlat=True) :358, get_interp_weights(lonlat=True) :361.
+__device__ __forceinline__ void regrid_target_literal(const Hpx &h, i64 p, double ox, double oy, double oz, i64 pix[4],
+                                                      double w[4]) {
+    double x, y, z;
+    pix2vec(h, p, x, y, z);
+    x += ox; y += oy; z += oz;                                                // :357 (not re-normalised)
+    const double dn = sqrt(x * x + y * y + z * z);
+    const double theta = acos(z / dn);
+    double phi = atan2(y, x);
+    if (phi < 0) phi += BFG_TWOPI;
+    const double lon = phi * (180.0 / BFG_PI), lat = 90.0 - theta * (180.0 / BFG_PI);
+    const double th2 = BFG_HALFPI - lat * (BFG_PI / 180.0), ph2 = lon * (BFG_PI / 180.0);
+    get_interpol(h, th2, ph2, pix, w);
+}
+
+__device__ __forceinline__ void regrid_target(const Hpx &h, const RingTabEntry *__restrict__ rt, i64 p, double ox, double oy,
+                                              double oz, i64 pix[4], double w[4]) {
+    if (rt == nullptr || !regrid_target_fast(h, rt, p, ox, oy, oz, pix, w)) regrid_target_literal(h, p, ox, oy, oz, pix, w);
 }
 
 __device__ __forceinline__ double fmodulo(double v1, double v2) {

@@ -927,25 +927,15 @@ k_shell_halos_warp(TableView T, Hpx h, i64 n_halo, const double *__restrict__ ha
 
 // Re-binning: one thread per source pixel.
 __global__ void __launch_bounds__(256)
-k_shell_regrid(Hpx h, const double *__restrict__ map_in, const double *__restrict__ off, double *__restrict__ map_out,
-               i64 pix_lo, i64 pix_hi) {
+k_shell_regrid(Hpx h, const RingTabEntry *__restrict__ rt, const double *__restrict__ map_in, const double *__restrict__ off,
+               double *__restrict__ map_out, i64 pix_lo, i64 pix_hi) {
     const i64 nloc = pix_hi - pix_lo;
     for (i64 lp = (i64)blockIdx.x * blockDim.x + threadIdx.x; lp < nloc; lp += (i64)gridDim.x * blockDim.x) {
         double m = map_in[lp];
         if (m == 0.0) continue;                                  // HealpixRunner.py:359
-        double x, y, z;
-        pix2vec(h, pix_lo + lp, x, y, z);
-        x += off[lp]; y += off[nloc + lp]; z += off[2 * nloc + lp];   // :357 (not re-normalised)
-        // hp.vec2ang(lonlat=True)  :358
-        double dn = sqrt(x * x + y * y + z * z);
-        double theta = acos(z / dn);
-        double phi = atan2(y, x);
-        if (phi < 0) phi += BFG_TWOPI;
-        double lon = phi * (180.0 / BFG_PI), lat = 90.0 - theta * (180.0 / BFG_PI);
-        // hp.get_interp_weights(lonlat=True)  :361
-        double th2 = BFG_HALFPI - lat * (BFG_PI / 180.0), ph2 = lon * (BFG_PI / 180.0);
         i64 pix[4]; double w[4];
-        get_interpol(h, th2, ph2, pix, w);
+        // :357-361  displaced direction -> 4 neighbours + bilinear weights (regrid_target: fast small-angle form or literal chain)
+        regrid_target(h, rt, pix_lo + lp, off[lp], off[nloc + lp], off[2 * nloc + lp], pix, w);
 #pragma unroll
         for (int k = 0; k < 4; ++k) red_add(map_out + pix[k], w[k] * m);   // :17-71
     }
@@ -954,22 +944,13 @@ k_shell_regrid(Hpx h, const double *__restrict__ map_in, const double *__restric
 // Re-binning of a SOURCE pixel range of a full-size offsets array (component stride given explicitly): the pipelined
 // end-to-end path re-bins the rings whose offsets are final while the halo loop works further south.
 __global__ void __launch_bounds__(256)
-k_shell_regrid_range(Hpx h, const double *__restrict__ map_in, const double *__restrict__ off, i64 comp_stride,
-                     double *__restrict__ map_out, i64 src_lo, i64 src_hi) {
+k_shell_regrid_range(Hpx h, const RingTabEntry *__restrict__ rt, const double *__restrict__ map_in, const double *__restrict__ off,
+                     i64 comp_stride, double *__restrict__ map_out, i64 src_lo, i64 src_hi) {
     for (i64 p = src_lo + (i64)blockIdx.x * blockDim.x + threadIdx.x; p < src_hi; p += (i64)gridDim.x * blockDim.x) {
         const double m = map_in[p];
         if (m == 0.0) continue;                                  // HealpixRunner.py:359
-        double x, y, z;
-        pix2vec(h, p, x, y, z);
-        x += off[p]; y += off[comp_stride + p]; z += off[2 * comp_stride + p];   // :357 (not re-normalised)
-        const double dn = sqrt(x * x + y * y + z * z);           // hp.vec2ang(lonlat=True)  :358
-        const double theta = acos(z / dn);
-        double phi = atan2(y, x);
-        if (phi < 0) phi += BFG_TWOPI;
-        const double lon = phi * (180.0 / BFG_PI), lat = 90.0 - theta * (180.0 / BFG_PI);
-        const double th2 = BFG_HALFPI - lat * (BFG_PI / 180.0), ph2 = lon * (BFG_PI / 180.0);   // get_interp_weights  :361
         i64 pix[4]; double w[4];
-        get_interpol(h, th2, ph2, pix, w);
+        regrid_target(h, rt, p, off[p], off[comp_stride + p], off[2 * comp_stride + p], pix, w);   // :357-361
 #pragma unroll
         for (int k = 0; k < 4; ++k) red_add(map_out + pix[k], w[k] * m);   // :17-71
     }
@@ -1218,7 +1199,9 @@ extern "C" int bfg_shell_regrid(int nside, const double *d_map_in, const double 
     Hpx h(nside);
     BFG_REQUIRE(pix_lo >= 0 && pix_hi <= h.npix && pix_lo <= pix_hi, "bad pixel range");
     if (pix_lo == pix_hi) return BFG_OK;
-    k_shell_regrid<<<grid_for(pix_hi - pix_lo, 256), 256, 0, (cudaStream_t)stream>>>(h, d_map_in, d_offsets, d_map_out,
+    const RingTabEntry *rt = nullptr;
+    if (int rc = get_ring_table(nside, &rt, stream)) return rc;
+    k_shell_regrid<<<grid_for(pix_hi - pix_lo, 256), 256, 0, (cudaStream_t)stream>>>(h, rt, d_map_in, d_offsets, d_map_out,
                                                                                     pix_lo, pix_hi);
     BFG_CUDA_OK(cudaGetLastError());
     return BFG_OK;
@@ -1231,7 +1214,9 @@ extern "C" int bfg_shell_regrid_range(int nside, const double *d_map_in, const d
     Hpx h(nside);
     BFG_REQUIRE(src_lo >= 0 && src_hi <= h.npix && src_lo <= src_hi && comp_stride >= src_hi, "bad pixel range");
     if (src_lo == src_hi) return BFG_OK;
-    k_shell_regrid_range<<<grid_for(src_hi - src_lo, 256), 256, 0, (cudaStream_t)stream>>>(h, d_map_in, d_offsets, comp_stride,
+    const RingTabEntry *rt = nullptr;
+    if (int rc = get_ring_table(nside, &rt, stream)) return rc;
+    k_shell_regrid_range<<<grid_for(src_hi - src_lo, 256), 256, 0, (cudaStream_t)stream>>>(h, rt, d_map_in, d_offsets, comp_stride,
                                                                                           d_map_out, src_lo, src_hi);
     BFG_CUDA_OK(cudaGetLastError());
     return BFG_OK;
@@ -1414,8 +1399,8 @@ struct OwnerTable {
 };
 
 __global__ void __launch_bounds__(256)
-k_shell_regrid_p2p(Hpx h, const double *__restrict__ map_in, const double *__restrict__ off, OwnerTable own, i64 pix_lo,
-                   i64 pix_hi, i64 src_lo, i64 src_hi, unsigned long long *remote_count) {
+k_shell_regrid_p2p(Hpx h, const RingTabEntry *__restrict__ rt, const double *__restrict__ map_in, const double *__restrict__ off,
+                   OwnerTable own, i64 pix_lo, i64 pix_hi, i64 src_lo, i64 src_hi, unsigned long long *remote_count) {
     const i64 nloc = pix_hi - pix_lo;
     const double inv_span = (double)own.world / (double)h.npix;
     unsigned long long nrem = 0;
@@ -1424,17 +1409,8 @@ k_shell_regrid_p2p(Hpx h, const double *__restrict__ map_in, const double *__res
          lp += (i64)gridDim.x * blockDim.x) {
         double m = map_in[lp];
         if (m == 0.0) continue;                                  // HealpixRunner.py:359
-        double x, y, z;
-        pix2vec(h, pix_lo + lp, x, y, z);
-        x += off[lp]; y += off[nloc + lp]; z += off[2 * nloc + lp];   // :357
-        double dn = sqrt(x * x + y * y + z * z);
-        double theta = acos(z / dn);
-        double phi = atan2(y, x);
-        if (phi < 0) phi += BFG_TWOPI;
-        double lon = phi * (180.0 / BFG_PI), lat = 90.0 - theta * (180.0 / BFG_PI);   // :358
-        double th2 = BFG_HALFPI - lat * (BFG_PI / 180.0), ph2 = lon * (BFG_PI / 180.0);
         i64 pix[4]; double w[4];
-        get_interpol(h, th2, ph2, pix, w);                       // :361
+        regrid_target(h, rt, pix_lo + lp, off[lp], off[nloc + lp], off[2 * nloc + lp], pix, w);   // :357-361
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const i64 p = pix[k];
@@ -1472,8 +1448,10 @@ static int regrid_p2p_impl(int nside, const double *d_map_in, const double *d_of
     for (int r = 0; r < 8; ++r) own.slice[r] = (r < world) ? h_slices[r] : nullptr;
     if (d_remote_count && zero_count) BFG_CUDA_OK(cudaMemsetAsync(d_remote_count, 0, sizeof(i64), (cudaStream_t)stream));
     if (src_lo == src_hi) return BFG_OK;
+    const RingTabEntry *rt = nullptr;
+    if (int rc = get_ring_table(nside, &rt, stream)) return rc;
     k_shell_regrid_p2p<<<grid_for(src_hi - src_lo, 256), 256, 0, (cudaStream_t)stream>>>(
-        h, d_map_in, d_offsets, own, pix_lo, pix_hi, src_lo, src_hi, (unsigned long long *)d_remote_count);
+        h, rt, d_map_in, d_offsets, own, pix_lo, pix_hi, src_lo, src_hi, (unsigned long long *)d_remote_count);
     BFG_CUDA_OK(cudaGetLastError());
     return BFG_OK;
 }

@@ -181,7 +181,7 @@ def _fields_to_device(cat, names, dev):
                     evs[slot].synchronize()                  # the copy that last used this buffer has left the host
                 dst = bufs[slot].numpy()[:b - a]
                 step = -(-(b - a) // nth)
-                list(ex.map(lambda i: np.copyto(dst[i:i + step], src[a + i:a + i + step], casting='unsafe'),
+                list(ex.map(lambda i: np.copyto(dst[i:i + step], src[a + i:min(a + i + step, b)], casting='unsafe'),
                             range(0, b - a, step)))
                 outs[col][a:b].copy_(bufs[slot][:b - a], non_blocking=True)
                 evs[slot] = stream.record_event()
@@ -240,7 +240,7 @@ def _raw_to_device(flat, dev):
                 evs[slot].synchronize()                          # the copy that last used this buffer has left the host
             dst = bufs[slot].numpy()[:b - a]
             step = -(-(b - a) // nth)
-            list(ex.map(lambda i: np.copyto(dst[i:i + step], flat[a + i:a + i + step]), range(0, b - a, step)))
+            list(ex.map(lambda i: np.copyto(dst[i:i + step], flat[a + i:min(a + i + step, b)]), range(0, b - a, step)))
             out[a:b].copy_(bufs[slot][:b - a], non_blocking=True)
             evs[slot] = stream.record_event()
     for e in evs:
@@ -276,7 +276,7 @@ def _device_to_raw(d_flat):
             ev.synchronize()
             src = bufs[slot].numpy()[:b - a]
             step = -(-(b - a) // nth)
-            list(ex.map(lambda i: np.copyto(out[a + i:a + i + step], src[i:i + step]), range(0, b - a, step)))
+            list(ex.map(lambda i: np.copyto(out[a + i:min(a + i + step, b)], src[i:i + step]), range(0, b - a, step)))
         for k, a in enumerate(range(0, n, chunk)):
             b = min(n, a + chunk)
             if len(jobs) == nbuf:
@@ -309,7 +309,7 @@ def _device_to_fields(d_cols, out_cat, names):
             src = bufs[slot].numpy()[:b - a]
             dst = out_cat[name]
             step = -(-(b - a) // nth)
-            list(ex.map(lambda i: np.copyto(dst[a + i:a + i + step], src[i:i + step]), range(0, b - a, step)))
+            list(ex.map(lambda i: np.copyto(dst[a + i:min(a + i + step, b)], src[i:i + step]), range(0, b - a, step)))
         k = 0
         for col, name in enumerate(names):
             for a in range(0, n, _FIELD_CHUNK):
@@ -2238,7 +2238,9 @@ class BaryonifySnapshot(DefaultRunnerSnapshot):
 
     def process_to_map(self, N_grid):
         """process() followed by make_map(N_grid) of the displaced particles, as a numpy array (see process_to_map_on_device)."""
-        return self.process_to_map_on_device(N_grid).cpu().numpy()
+        d_grid = self.process_to_map_on_device(N_grid)
+        with _torch().cuda.device(d_grid.device):
+            return _device_to_raw(d_grid.reshape(-1)).reshape(d_grid.shape)       # page-locked, recycled result buffer
 
 
 

@@ -426,7 +426,7 @@ def grid_leg(args, bench, rank, world, local, cpu_baseline=True, reps=2):
         torch.cuda.empty_cache()
         # ---- end to end: BaryonifyGrid.process() on the host map (this rank's planes page-locked) ----
         out = run.process()                               # warm-up: result buffers / shared host map
-        got_s = np.asarray(out)[lo:hi].reshape(-1)[::stride]
+        got_s = np.asarray(out)[lo:hi].reshape(-1)[::stride].copy()    # a view would keep the result's buffer alive
         e2e_err = float(np.max(np.abs(got_s - ref_s) / (np.abs(ref_s) + 1e-3 * np.max(np.abs(ref_s)))))
         del out
         ts = []

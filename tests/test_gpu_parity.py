@@ -799,3 +799,43 @@ def test_snapshot_raw_record_path_matches_the_per_field_path(monkeypatch):
             for nm in ("x", "y", "z")[:ndim]:
                 assert_close(out[nm], other[nm], f"layout {dt[0][0]}..., {nm}", rtol=1e-12, atol_scale=1e-13)
             assert np.array_equal(out["M"], alt["M"])
+
+
+@pytest.mark.parametrize("nside", [16, 64, 256])
+def test_shell_regrid_small_angle_path_matches_literal_chain_and_oracle(nside, monkeypatch):
+    """k_shell_regrid's default path (regrid_target_fast: small-angle azimuth / colatitude, ring table) against the literal
+    acos / atan2 / degrees chain on the device (BFG_REGRID_LITERAL=1) and against the oracle port's shell_regrid: pixel-sized,
+    sub-pixel and zero offsets, a few huge ones and the polar pixels (which fall back to the literal chain), sparse map.
+    Tolerance 1e-7 relative: next to the poles the LITERAL chain's arccos(z / |v|) carries ~1e-9 of round-off in a weight."""
+    import torch
+    from baryonforge_b200 import _lib
+    from oracle import runners_port as rp
+    npix = 12 * nside * nside
+    rng = np.random.default_rng(400 + nside)
+    pixsize = np.sqrt(4 * np.pi / npix)
+    off = rng.normal(0, 1.0, (3, npix)) * pixsize * rng.choice([0.0, 0.01, 0.3, 2.5], npix)[None, :]
+    big = rng.choice(npix, 50, replace=False)
+    off[:, big] = rng.normal(0, 0.3, (3, 50))                                 # far beyond the small-angle guards
+    m = rng.uniform(0, 10, npix) * (rng.random(npix) < 0.9)
+    d_map, d_off = torch.from_numpy(m).cuda(), torch.from_numpy(np.ascontiguousarray(off)).cuda()
+    outs = {}
+    for literal in ("1", "0"):
+        monkeypatch.setenv("BFG_REGRID_LITERAL", literal)
+        d_new = torch.zeros(npix, dtype=torch.float64, device="cuda")
+        _lib.check(_lib.lib().bfg_shell_regrid(nside, d_map.data_ptr(), d_off.data_ptr(), d_new.data_ptr(), 0, npix,
+                                               _lib.current_stream()))
+        outs[literal] = d_new.cpu().numpy()
+        # the range form used by the pipelined end-to-end path: two source ranges into the same output
+        d_new2 = torch.zeros(npix, dtype=torch.float64, device="cuda")
+        cut = (npix // 3) & ~3
+        for a, b in ((0, cut), (cut, npix)):
+            _lib.check(_lib.lib().bfg_shell_regrid_range(nside, d_map.data_ptr(), d_off.data_ptr(), npix, d_new2.data_ptr(), a, b,
+                                                         _lib.current_stream()))
+        assert_close(d_new2.cpu().numpy(), outs[literal], f"regrid_range, literal={literal}", rtol=1e-12, atol_scale=1e-14)
+    want = rp.shell_regrid(nside, m, np.ascontiguousarray(off.T))
+    assert_close(outs["1"], want, f"literal chain vs oracle, NSIDE={nside}", rtol=1e-7, atol_scale=1e-10)
+    assert_close(outs["0"], want, f"small-angle path vs oracle, NSIDE={nside}", rtol=1e-7, atol_scale=1e-10)
+    assert_close(outs["0"], outs["1"], f"small-angle path vs literal chain, NSIDE={nside}", rtol=1e-7, atol_scale=1e-10)
+    assert np.isclose(outs["0"].sum(), m.sum(), rtol=1e-12)                   # mass conservation (HealpixRunner.py:368-370)
+    # evidence that the two device paths are different code: identical bits only where the table is not used (NSIDE < 32)
+    assert np.array_equal(outs["0"], outs["1"]) == (nside < 32)
