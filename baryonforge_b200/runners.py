@@ -855,6 +855,11 @@ class BaryonifyShell(DefaultRunner):
             st = _lib.current_stream()
             main = torch.cuda.current_stream()
             side = _side_stream(dev)
+            # the accumulators are zeroed first, so that the GPU clears 6.4 GB while the host still stages the catalogue
+            d_off = torch.zeros((3, npix), dtype=torch.float64, device=dev)
+            d_new = torch.zeros(npix, dtype=torch.float64, device=dev)
+            d_nb = torch.zeros(K, dtype=torch.int64, device=dev)
+            d_max = torch.zeros(1, dtype=torch.float64, device=dev)
             t0 = time.perf_counter()
             d_rec = self.device_records(False, dev)
             host_prep_s = time.perf_counter() - t0
@@ -879,10 +884,6 @@ class BaryonifyShell(DefaultRunner):
                     a0, a1 = j * piece, min((j + 1) * piece, npix)
                     d_map[a0:a1].copy_(h_map[a0:a1], non_blocking=True)
                     ev_h2d.append(side.record_event())
-            d_off = torch.zeros((3, npix), dtype=torch.float64, device=dev)
-            d_new = torch.zeros(npix, dtype=torch.float64, device=dev)
-            d_nb = torch.zeros(K, dtype=torch.int64, device=dev)
-            d_max = torch.zeros(1, dtype=torch.float64, device=dev)
             bounds = d_bounds.cpu().tolist()        # one small synchronisation: chunk boundaries in the sorted catalogue
             rho_max = float(d_rho.cpu()[0])
             pix_rad = np.sqrt(4 * np.pi / npix)
@@ -928,13 +929,13 @@ class BaryonifyShell(DefaultRunner):
                     th_copy = th_done - self.PIPELINE_MARGIN_RAD - 3 * pix_rad
                     if th_copy > 0:
                         download_to(first_pixel_at_colatitude(NSIDE, th_copy))
-            regrid_to(npix)
             d_sums = torch.zeros(2, dtype=torch.float64, device=dev)
+            regrid_to(npix)
+            download_to(npix)                        # the last piece leaves first; the three reductions below run underneath it
+            d_new.record_stream(side)
             _lib.check(L.bfg_sum_f64(_lib.ptr(d_new), npix, _lib.ptr(d_sums), st))
             _lib.check(L.bfg_sum_f64(_lib.ptr(d_map), npix, d_sums.data_ptr() + 8, st))   # regrid_to(npix) waited for every piece
             _lib.check(L.bfg_offsets_max_norm2(_lib.ptr(d_off), npix, 0, npix, _lib.ptr(d_max), st))
-            download_to(npix)
-            d_new.record_stream(side)
             sums = d_sums.cpu()
             n_up = int(d_nb.sum().cpu())
             max_norm = float(np.sqrt(float(d_max.cpu()[0])))
@@ -1117,6 +1118,7 @@ class BaryonifyShell(DefaultRunner):
                 own.zero_()
                 token = torch.zeros(1, device=dev)
                 dist.all_reduce(token)               # fence 1: every rank's slice is zero before any deposit
+            d_off = torch.zeros((3, nloc), dtype=torch.float64, device=dev)    # cleared while the host stages the catalogue
             t0 = time.perf_counter()
             d_rec = self.device_records(False, dev)  # the (small) catalogue copies go first: the copy engine serves its queue in
             ext = _extras(cat, keys)                 # order, and behind the map upload they would hold the halo loop back
@@ -1137,7 +1139,6 @@ class BaryonifyShell(DefaultRunner):
             d_rho = torch.zeros(1, dtype=torch.float64, device=dev)
             _lib.check(L.bfg_halo_band_bounds(n, _lib.ptr(d_rec), SKY_BAND_RAD, K + 1, _lib.ptr(d_edges), _lib.ptr(d_bounds),
                                               _lib.ptr(d_rho), st))
-            d_off = torch.zeros((3, nloc), dtype=torch.float64, device=dev)
             d_nb = torch.zeros(K, dtype=torch.int64, device=dev)
             d_rem = torch.zeros(1, dtype=torch.int64, device=dev)
             d_max = torch.zeros(1, dtype=torch.float64, device=dev)
