@@ -318,7 +318,7 @@ def _host_map_with_pinned_slab(N, lo, hi, d_slab):
     return full, slab.ctypes.data
 
 
-def _grid_cpu_sample(N, Lbox, n_halo_total, eps, gaxes, vals, n_sample=40):
+def _grid_cpu_sample(N, Lbox, n_halo_total, eps, gaxes, vals, n_sample=120):
     """Oracle port of the BaryonifyGrid halo loop (oracle/runners_port.grid_offsets, Map2DRunner.py:474-586) on the first
     n_sample halos of the same catalogue on the full N^3 grid (the offsets array is lazily zeroed memory)."""
     import warnings
@@ -467,7 +467,7 @@ def grid_leg(args, bench, rank, world, local, cpu_baseline=True, reps=2):
         try:
             n_cpu, dt_cpu = _grid_cpu_sample(N, Lbox, n, eps, gaxes, vals)
             leg["cpu_baseline"] = {"value": n_cpu / dt_cpu, "unit": "halo-cell updates/s", "cores": 1, "kind": "port",
-                                   "sample": f"first 40 halos of the same catalogue on the full {N}^3 grid, halo loop only "
+                                   "sample": f"first 120 halos of the same catalogue on the full {N}^3 grid, halo loop only "
                                              f"(oracle/runners_port.grid_offsets), {dt_cpu:.1f} s, {n_cpu} updates"}
         except Exception as exc:
             leg["cpu_baseline"] = {"error": str(exc)[:300]}
