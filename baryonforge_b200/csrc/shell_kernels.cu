@@ -622,22 +622,27 @@ k_shell_halos(TableView T, Hpx h, i64 n_halo, const double *__restrict__ halos, 
                     jn = n_halo;   // bfg_halo_sort_owned puts the halos of other ranks last and marks them: stop here
                 } else {
                     const DiscRings d0 = disc_rings(h, s0.theta, s0.phi, s0.radius);
-                    const HaloUpd u0 = make_upd(T, s0);
-                    // lane-group width of the fast path from the disc's mean chord (pi/4 of its diameter) in pixels
-                    const int gws = (0.7853981633974483 * 2.0 * s0.radius) * sqrt((double)h.npix * 0.07957747154594767)
-                                    < GW_CHORD_SPLIT;
                     // (a disc without any ring -- rb < ra -- still owes the < 4-pixel fallback: only min_rings > 0 may skip it)
                     const int tch = (min_rings == 0 || d0.rb - d0.ra + 1 > (i64)min_rings) &&
                                     (!sharded || disc_touches_range(h, d0, pix_lo, pix_hi));
-                    if (FAST) {
-                        const FastHalo f0 = make_fast<PAINT>(T, s0, u0, row, l2tab, s_etab);
-                        if (lane == 0) s_ctx.fh = f0;
-                        if (!PAINT) {
+                    if (lane == 0) s_ctx.touches = tch;
+                    // a halo this kernel does not take (k_shell_halos_warp had it, or its disc misses the owned range) costs
+                    // no more than the ring range of its disc: the constants below are ~500 instructions
+                    if (tch) {
+                        const HaloUpd u0 = make_upd(T, s0);
+                        // lane-group width of the fast path from the disc's mean chord (pi/4 of its diameter) in pixels
+                        const int gws = (0.7853981633974483 * 2.0 * s0.radius) * sqrt((double)h.npix * 0.07957747154594767)
+                                        < GW_CHORD_SPLIT;
+                        if (FAST) {
+                            const FastHalo f0 = make_fast<PAINT>(T, s0, u0, row, l2tab, s_etab);
+                            if (lane == 0) s_ctx.fh = f0;
+                            if (!PAINT) {
 #pragma unroll
-                            for (int i = lane; i < V9_NE; i += 32) s_etab[i] = fma((double)(i + V9_EMIN), f0.t.uA, f0.t.uB);
+                                for (int i = lane; i < V9_NE; i += 32) s_etab[i] = fma((double)(i + V9_EMIN), f0.t.uA, f0.t.uB);
+                            }
                         }
+                        if (lane == 0) { s_ctx.d = d0; s_ctx.u = u0; s_ctx.gw_small = gws; }
                     }
-                    if (lane == 0) { s_ctx.d = d0; s_ctx.u = u0; s_ctx.gw_small = gws; s_ctx.touches = tch; }
                 }
             }
             if (lane == 0) s_j = jn;
@@ -815,7 +820,7 @@ template <int MODE>
 __global__ void __launch_bounds__(SHELL_THREADS, WARP_KERNEL_CTAS)
 k_shell_halos_warp(TableView T, Hpx h, i64 n_halo, const double *__restrict__ halos, const double *__restrict__ extras,
                    int n_extra, double *__restrict__ out, i64 pix_lo, i64 pix_hi, unsigned long long *nupd,
-                   const double2 *__restrict__ g_l2tab, unsigned long long *queue, int row_stride) {
+                   const double2 *__restrict__ g_l2tab, unsigned long long *queue, int row_stride, int max_rings) {
     constexpr bool PAINT = (MODE != MODE_BARYONIFY);
     constexpr bool UNIFORM = true;
     extern __shared__ double rows[];                       // [warps][row_stride]
@@ -848,7 +853,7 @@ k_shell_halos_warp(TableView T, Hpx h, i64 n_halo, const double *__restrict__ ha
         const HaloSph s = load_halo(halos + j * BFG_HALO_STRIDE);
         if (s.skip != 0.0) break;                          // bfg_halo_sort_owned: the halos of other ranks come last
         const DiscRings d = disc_rings(h, s.theta, s.phi, s.radius);
-        if (d.rb - d.ra + 1 > (i64)WARP_MAX_RINGS) continue;                     // a large disc: k_shell_halos takes it
+        if (d.rb - d.ra + 1 > (i64)max_rings) continue;                          // a large disc: k_shell_halos takes it
         if (sharded && !disc_touches_range(h, d, pix_lo, pix_hi)) continue;
         HaloUpd u = make_upd(T, s);
         const FastHalo fh = make_fast<PAINT>(T, s, u, row, l2tab, nullptr);
@@ -1115,6 +1120,8 @@ int launch_shell(const bfg_table *t, int nside, i64 n_halo, const double *d_halo
     // 22.1 -> 20.0 ms, but on the flat 10^U(12,15.5) catalogue 97.2 -> 100.3 ms (two persistent kernels in a row, and the second
     // still pops the halos the first took).  So: on by default for painting, opt-in (BFG_SHELL_WARP_KERNEL=1) for BaryonifyShell;
     // BFG_SHELL_WARP_KERNEL=0 switches it off everywhere.
+    const char *renv = getenv("BFG_SHELL_WARP_MAX_RINGS");   // discs of at most this many rings go to the warp kernel
+    const int warp_max_rings = renv ? std::max(1, std::min(4096, atoi(renv))) : WARP_MAX_RINGS;
     const char *wenv = getenv("BFG_SHELL_WARP_KERNEL");
     const bool want_warp = wenv ? (wenv[0] != '0') : (MODE == MODE_PAINT);
     const size_t wsmem = sizeof(double) * (SHELL_THREADS / 32) * (size_t)((t->view.n[2] + 1) & ~1);
@@ -1127,10 +1134,10 @@ int launch_shell(const bfg_table *t, int nside, i64 n_halo, const double *d_halo
         const int wblocks = (int)std::min<i64>((n_halo + SHELL_THREADS / 32 - 1) / (SHELL_THREADS / 32), (i64)sms * WARP_KERNEL_CTAS);
         kw<<<wblocks, SHELL_THREADS, wsmem, st>>>(t->view, h, n_halo, d_halos, d_extras, n_extra, d_out, pix_lo, pix_hi,
                                                   (unsigned long long *)d_nupdates, g_l2tab, queue_w,
-                                                  (int)((t->view.n[2] + 1) & ~1));
+                                                  (int)((t->view.n[2] + 1) & ~1), warp_max_rings);
         BFG_CUDA_OK(cudaGetLastError());
         BFG_CUDA_OK(cudaFreeAsync(queue_w, st));
-        min_rings = WARP_MAX_RINGS;
+        min_rings = warp_max_rings;
     }
     auto go = [&](auto kern) -> int {
         BFG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

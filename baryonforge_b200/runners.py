@@ -1574,13 +1574,15 @@ class DefaultRunnerGrid(object):
 
     def _records_on_device(self, paint, dev):
         """
-        (records, extras, n) on the device, box-cell ordered.  Unsharded runs build the records ON THE DEVICE
-        (bfg_box_records); slab-sharded runs keep the host path, whose records also drive the per-rank halo filter.
+        (records, extras, n) on the device, box-cell ordered, built ON THE DEVICE (bfg_box_records).  Slab-sharded runs hand
+        every rank the whole catalogue as well: the tile binning / the scatter kernels only take the part of a cutout that
+        lies in the owned planes, so a halo that does not reach the slab costs one record read (the host-side filter of
+        BFG_DEVICE_RECORDS=0 took ~0.15 s per call for 10^6 halos).
         """
         gm = self.GriddedMap
         ndim, N = (2 if gm.is2D else 3), gm.Npix
         lo, hi = self._planes(N)
-        if self.plane_range is not None or os.environ.get("BFG_DEVICE_RECORDS", "1") != "1":
+        if os.environ.get("BFG_DEVICE_RECORDS", "1") != "1":
             rec, extras = self.halo_records(paint)
             rec, extras = self._owned_halos(rec, extras, N, lo, hi)
             d_rec = _upload_records(rec, dev)
