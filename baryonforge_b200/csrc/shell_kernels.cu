@@ -573,8 +573,10 @@ template <int MODE, bool UNIFORM>
 __global__ void __launch_bounds__(SHELL_THREADS, SHELL_MIN_CTAS)
 k_shell_halos(TableView T, Hpx h, i64 n_halo, const double *__restrict__ halos, const double *__restrict__ extras,
               int n_extra, double *__restrict__ out, i64 pix_lo, i64 pix_hi, unsigned long long *nupd,
-              const double2 *__restrict__ g_l2tab, AnisArgs A, unsigned long long *queue, int min_rings) {
-    // min_rings: discs of at most this many rings belong to k_shell_halos_warp (0: this kernel takes every halo)
+              const double2 *__restrict__ g_l2tab, AnisArgs A, unsigned long long *queue, const int *__restrict__ d_min_rings) {
+    // min_rings: discs of at most this many rings belong to k_shell_halos_warp (0: this kernel takes every halo); decided on the
+    // device by k_warp_vote, so the launch sequence does not depend on the catalogue
+    const int min_rings = d_min_rings ? __ldg(d_min_rings) : 0;
     constexpr bool PAINT = (MODE != MODE_BARYONIFY);
     constexpr bool FAST = (MODE != MODE_ANIS) && UNIFORM;        // span_pixels_fast / _paint: 8 or 16 lanes per ring
     extern __shared__ double row[];
@@ -814,15 +816,40 @@ k_shell_halos(TableView T, Hpx h, i64 n_halo, const double *__restrict__ halos, 
 // (launched with min_rings = WARP_MAX_RINGS), which skips the ones taken here; both add into the same array.
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int WARP_MAX_RINGS = 64;
+
+// Which catalogues go through the warp kernel?  Measured (B200, NSIDE = 4096, 10^6 halos): it pays when nearly every disc is small
+// (dn/dlogM ~ M^-0.9: 22.2 -> 20.0 ms) and costs when the catalogue is mixed (flat in log M: 96.3 -> 99.6 ms; two persistent
+// kernels in a row, two tails), whatever the ring threshold.  So the decision is a vote over the batch, taken on the device:
+// vote[0] = max_rings when at least 80 % of the (owned) halos have discs of at most max_rings rings, else 0.
+__global__ void k_warp_vote_count(Hpx h, i64 n_halo, const double *__restrict__ halos, int max_rings, unsigned long long *cnt) {
+    unsigned long long small = 0, total = 0;
+    for (i64 j = (i64)blockIdx.x * blockDim.x + threadIdx.x; j < n_halo; j += (i64)gridDim.x * blockDim.x) {
+        const double *H = halos + j * BFG_HALO_STRIDE;
+        if (__ldg(H + BFG_HS_SKIP) != 0.0) continue;
+        const DiscRings d = disc_rings(h, __ldg(H + BFG_HS_THETA), __ldg(H + BFG_HS_PHI), __ldg(H + BFG_HS_RADIUS));
+        ++total;
+        small += (d.rb - d.ra + 1 <= (i64)max_rings) ? 1 : 0;
+    }
+    small = (unsigned long long)warp_sum_i64((i64)small);
+    total = (unsigned long long)warp_sum_i64((i64)total);
+    if ((threadIdx.x & 31) == 0 && total) { atomicAdd(cnt, small); atomicAdd(cnt + 1, total); }
+}
+
+__global__ void k_warp_vote_finish(const unsigned long long *cnt, int max_rings, int force, int *vote) {
+    vote[0] = (force > 0 || (force == 0 && cnt[0] * 10 >= cnt[1] * 8 && cnt[1] > 0)) ? max_rings : 0;
+}
 constexpr int WARP_KERNEL_CTAS = 6;
 
 template <int MODE>
 __global__ void __launch_bounds__(SHELL_THREADS, WARP_KERNEL_CTAS)
 k_shell_halos_warp(TableView T, Hpx h, i64 n_halo, const double *__restrict__ halos, const double *__restrict__ extras,
                    int n_extra, double *__restrict__ out, i64 pix_lo, i64 pix_hi, unsigned long long *nupd,
-                   const double2 *__restrict__ g_l2tab, unsigned long long *queue, int row_stride, int max_rings) {
+                   const double2 *__restrict__ g_l2tab, unsigned long long *queue, int row_stride,
+                   const int *__restrict__ d_max_rings) {
     constexpr bool PAINT = (MODE != MODE_BARYONIFY);
     constexpr bool UNIFORM = true;
+    const int max_rings = __ldg(d_max_rings);
+    if (max_rings <= 0) return;                            // k_warp_vote: this catalogue is left to k_shell_halos
     extern __shared__ double rows[];                       // [warps][row_stride]
     __shared__ RingSeg segs_all[SHELL_THREADS / 32][32];
     __shared__ double2 l2tab[BFG_LOG2_TAB];
@@ -1114,35 +1141,40 @@ int launch_shell(const bfg_table *t, int nside, i64 n_halo, const double *d_halo
     BFG_CUDA_OK(cudaMallocAsync(&queue, sizeof(unsigned long long), st));
     BFG_CUDA_OK(cudaMemsetAsync(queue, 0, sizeof(unsigned long long), st));
     const bool uni = t->view.uniform_r && (MODE != MODE_ANIS || t2->view.uniform_r);
-    // small discs first, one warp per halo (k_shell_halos_warp); the CTA-per-halo kernel then skips them
-    int min_rings = 0;
-    // Measured (B200, same box): PaintProfilesShell NSIDE=1024 1.72 -> 1.59 ms; BaryonifyShell on the dn/dlogM ~ M^-0.9 catalogue
-    // 22.1 -> 20.0 ms, but on the flat 10^U(12,15.5) catalogue 97.2 -> 100.3 ms (two persistent kernels in a row, and the second
-    // still pops the halos the first took).  So: on by default for painting, opt-in (BFG_SHELL_WARP_KERNEL=1) for BaryonifyShell;
-    // BFG_SHELL_WARP_KERNEL=0 switches it off everywhere.
-    const char *renv = getenv("BFG_SHELL_WARP_MAX_RINGS");   // discs of at most this many rings go to the warp kernel
+    // small discs first, one warp per halo (k_shell_halos_warp); the CTA-per-halo kernel then skips them.  PaintProfilesShell:
+    // always (NSIDE=1024: 1.72 -> 1.59 ms).  BaryonifyShell: when the batch votes for it (k_warp_vote_*), i.e. for catalogues of
+    // small discs.  BFG_SHELL_WARP_KERNEL=1 / 0 forces it on / off, BFG_SHELL_WARP_MAX_RINGS sets the ring threshold.
+    const char *renv = getenv("BFG_SHELL_WARP_MAX_RINGS");
     const int warp_max_rings = renv ? std::max(1, std::min(4096, atoi(renv))) : WARP_MAX_RINGS;
     const char *wenv = getenv("BFG_SHELL_WARP_KERNEL");
-    const bool want_warp = wenv ? (wenv[0] != '0') : (MODE == MODE_PAINT);
+    const int force = wenv ? (wenv[0] != '0' ? 1 : -1) : (MODE == MODE_PAINT ? 1 : 0);
     const size_t wsmem = sizeof(double) * (SHELL_THREADS / 32) * (size_t)((t->view.n[2] + 1) & ~1);
-    if (uni && MODE != MODE_ANIS && want_warp && wsmem <= 64 * 1024) {
-        unsigned long long *queue_w = nullptr;
-        BFG_CUDA_OK(cudaMallocAsync(&queue_w, sizeof(unsigned long long), st));
-        BFG_CUDA_OK(cudaMemsetAsync(queue_w, 0, sizeof(unsigned long long), st));
+    StreamScratch s_vote(st), s_queue_w(st);
+    const int *d_vote = nullptr;
+    if (uni && MODE != MODE_ANIS && force >= 0 && wsmem <= 64 * 1024) {
+        BFG_CUDA_OK(s_vote.alloc(32));
+        BFG_CUDA_OK(s_queue_w.alloc(sizeof(unsigned long long)));
+        BFG_CUDA_OK(cudaMemsetAsync(s_vote.p, 0, 32, st));
+        BFG_CUDA_OK(cudaMemsetAsync(s_queue_w.p, 0, sizeof(unsigned long long), st));
+        unsigned long long *cnt = s_vote.as<unsigned long long>();
+        int *vote = (int *)(cnt + 2);
+        if (force == 0)
+            k_warp_vote_count<<<(int)std::min<i64>((n_halo + 255) / 256, (i64)sms * 8), 256, 0, st>>>(h, n_halo, d_halos,
+                                                                                                   warp_max_rings, cnt);
+        k_warp_vote_finish<<<1, 1, 0, st>>>(cnt, warp_max_rings, force, vote);
         auto kw = k_shell_halos_warp<MODE == MODE_ANIS ? MODE_PAINT : MODE>;
         BFG_CUDA_OK(cudaFuncSetAttribute(kw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
         const int wblocks = (int)std::min<i64>((n_halo + SHELL_THREADS / 32 - 1) / (SHELL_THREADS / 32), (i64)sms * WARP_KERNEL_CTAS);
         kw<<<wblocks, SHELL_THREADS, wsmem, st>>>(t->view, h, n_halo, d_halos, d_extras, n_extra, d_out, pix_lo, pix_hi,
-                                                  (unsigned long long *)d_nupdates, g_l2tab, queue_w,
-                                                  (int)((t->view.n[2] + 1) & ~1), warp_max_rings);
+                                                  (unsigned long long *)d_nupdates, g_l2tab, s_queue_w.as<unsigned long long>(),
+                                                  (int)((t->view.n[2] + 1) & ~1), vote);
         BFG_CUDA_OK(cudaGetLastError());
-        BFG_CUDA_OK(cudaFreeAsync(queue_w, st));
-        min_rings = warp_max_rings;
+        d_vote = vote;
     }
     auto go = [&](auto kern) -> int {
         BFG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<blocks, SHELL_THREADS, smem, st>>>(t->view, h, n_halo, d_halos, d_extras, n_extra, d_out, pix_lo, pix_hi,
-                                                  (unsigned long long *)d_nupdates, g_l2tab, A, queue, min_rings);
+                                                  (unsigned long long *)d_nupdates, g_l2tab, A, queue, d_vote);
         BFG_CUDA_OK(cudaGetLastError());
         BFG_CUDA_OK(cudaFreeAsync(queue, st));
         return BFG_OK;
