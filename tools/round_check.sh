@@ -23,7 +23,7 @@ for f in ("$OUT/${TAG}_bench_n1.json", "$OUT/${TAG}_bench_ref.json"):
         print(f, "unreadable:", e)
 PY
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches.csv \
-    python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline --no-particles >$OUT/${TAG}_ncu_launches.log 2>&1
+    python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline --no-particles --no-extra-configs >$OUT/${TAG}_ncu_launches.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_shell_halos -s 1 -c 1 -o $OUT/${TAG}_shell_halos \
-    python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-particles >$OUT/${TAG}_ncu_full.log 2>&1
+    python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-particles --no-extra-configs >$OUT/${TAG}_ncu_full.log 2>&1
 ls -la $OUT | grep "${TAG}_"

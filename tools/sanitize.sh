@@ -7,7 +7,7 @@
 set -u
 cd "$(dirname "$0")/.."
 CS=${COMPUTE_SANITIZER:-/usr/local/cuda/bin/compute-sanitizer}
-SMALL='map_runners_match_reference_fixture or snapshot_matches_reference_fixture or process_to_map or pk_matches_notebook_fixture or folded_deposit_edge_cases'
+SMALL='map_runners_match_reference_fixture or snapshot_matches_reference_fixture or process_to_map or pk_matches_notebook_fixture or folded_deposit_edge_cases or raw_record or small_angle or warp_per_halo'
 for tool in memcheck racecheck initcheck; do
     echo "=== compute-sanitizer --tool $tool"
     timeout ${SANITIZE_TIMEOUT:-600} "$CS" --tool "$tool" --target-processes all --error-exitcode 9 \
