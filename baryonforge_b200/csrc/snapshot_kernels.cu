@@ -13,6 +13,7 @@
 // loads) and their REDs land on consecutive addresses of the cell-ordered offset array.
 #include <algorithm>
 #include <cstdlib>
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include "bfg_common.cuh"
 
@@ -84,6 +85,26 @@ __global__ void k_cell_fine(i64 n, const double4 *__restrict__ tmp, double L, in
         int c = cell_of(r.x, L, nc) * nc + cell_of(r.y, L, nc);                 // the cell k_cell_count assigned
         if (NDIM == 3) c = c * nc + cell_of(r.z, L, nc);
         rec[cell_start[c] + (i64)atomicAdd(cursor + c, 1ULL)] = r;
+    }
+}
+
+// Index sort (BFG_CELL_SORT=3): the particle INDICES are radix-sorted by cell (8 bytes per particle and pass instead of a
+// 32-byte record), then every sorted slot gathers its particle.  Random 32-byte READS run near the sector rate of the HBM,
+// random 32-byte WRITES into 10^7 open lines do not; with the caller's particles held as 32-byte records (stride 4) the gather
+// is one sector per particle.  The sort is stable, so the order inside a cell is the caller's (deterministic cell lists).
+__global__ void k_iota_u32(i64 n, unsigned int *__restrict__ idx) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) idx[i] = (unsigned int)i;
+}
+
+template <int NDIM>
+__global__ void k_cell_gather(i64 n, const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ z,
+                              i64 stride, const unsigned int *__restrict__ sorted_idx, i64 *__restrict__ order,
+                              double *__restrict__ xs, double *__restrict__ ys, double *__restrict__ zs) {
+    for (i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (i64)gridDim.x * blockDim.x) {
+        const i64 i = (i64)sorted_idx[p];
+        xs[p] = x[i * stride]; ys[p] = y[i * stride];
+        if (NDIM == 3) zs[p] = z[i * stride];
+        order[p] = i;
     }
 }
 
@@ -358,6 +379,29 @@ extern "C" int bfg_snap_build_cells_strided(int ndim, int64_t n_part, const doub
     BFG_CUDA_OK(s_scan.alloc(scan_bytes));
     BFG_CUDA_OK(cub::DeviceScan::ExclusiveSum(s_scan.p, scan_bytes, (const i64 *)counts, (i64 *)d_cell_start, ncells + 1, st));
     BFG_CUDA_OK(cudaMemsetAsync(counts, 0, sizeof(unsigned long long) * (ncells + 1), st));
+    const char *mode0 = getenv("BFG_CELL_SORT");
+    if (n_part > 0 && mode0 && mode0[0] == '3' && n_part < ((i64)1 << 31)) {
+        // index sort: (cell id, particle index) pairs through cub::DeviceRadixSort (library call, like bfg_halo_sort), then gather
+        StreamScratch s_key2(st), s_idx(st), s_idx2(st), s_sort(st);
+        BFG_CUDA_OK(s_key2.alloc(sizeof(unsigned int) * n_part));
+        BFG_CUDA_OK(s_idx.alloc(sizeof(unsigned int) * n_part));
+        BFG_CUDA_OK(s_idx2.alloc(sizeof(unsigned int) * n_part));
+        k_iota_u32<<<blocks_for(n_part, 256), 256, 0, st>>>(n_part, s_idx.as<unsigned int>());
+        int end_bit = 1;
+        while (end_bit < 32 && ((i64)1 << end_bit) < ncells) ++end_bit;
+        size_t sort_bytes = 0;
+        BFG_CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const unsigned int *)cell_id, s_key2.as<unsigned int>(),
+                                                    s_idx.as<unsigned int>(), s_idx2.as<unsigned int>(), (int)n_part, 0, end_bit, st));
+        BFG_CUDA_OK(s_sort.alloc(sort_bytes));
+        BFG_CUDA_OK(cub::DeviceRadixSort::SortPairs(s_sort.p, sort_bytes, (const unsigned int *)cell_id, s_key2.as<unsigned int>(),
+                                                    s_idx.as<unsigned int>(), s_idx2.as<unsigned int>(), (int)n_part, 0, end_bit, st));
+        if (ndim == 3) k_cell_gather<3><<<blocks_for(n_part, 256), 256, 0, st>>>(n_part, d_x, d_y, d_z, stride, s_idx2.as<unsigned int>(),
+                                                                               (i64 *)d_order, d_xs, d_ys, d_zs);
+        else k_cell_gather<2><<<blocks_for(n_part, 256), 256, 0, st>>>(n_part, d_x, d_y, d_z, stride, s_idx2.as<unsigned int>(),
+                                                                     (i64 *)d_order, d_xs, d_ys, d_zs);
+        BFG_CUDA_OK(cudaGetLastError());
+        return BFG_OK;
+    }
     if (n_part > 0) {
         BFG_CUDA_OK(s_rec.alloc(sizeof(double4) * n_part));   // 32-byte particle records
         double4 *rec = s_rec.as<double4>();

@@ -881,7 +881,12 @@ class BaryonifyShell(DefaultRunner):
             d_ext = None if ext is None else _to_device(ext, dev)
             d_rec, d_ext = _sort_records(d_rec, d_ext, 0, SKY_BAND_RAD)
             # latitude chunks of equal area, expressed as band indices of the sort key
-            edges = [int(np.floor(np.arccos(1 - 2.0 * k / K) / SKY_BAND_RAD)) for k in range(K)] + [1 << 40]
+            # BFG_PIPELINE_TAPER=1: the last three chunks shrink (6 %, 3 %, 1 % of the sky), so that what is left exposed after
+            # the last halo -- the re-binning and the download of the final chunk's rings -- is a 1 % piece, without more chunks
+            fr = [k / K for k in range(K)]
+            if os.environ.get("BFG_PIPELINE_TAPER", "0") == "1" and K >= 6:
+                fr = [0.90 * k / (K - 3) for k in range(K - 3)] + [0.90, 0.96, 0.99]
+            edges = [int(np.floor(np.arccos(1 - 2.0 * f) / SKY_BAND_RAD)) for f in fr] + [1 << 40]
             d_edges = torch.tensor(edges, dtype=torch.int64, device=dev)
             d_bounds = torch.empty(K + 1, dtype=torch.int64, device=dev)
             d_rho = torch.zeros(1, dtype=torch.float64, device=dev)

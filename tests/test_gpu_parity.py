@@ -110,10 +110,11 @@ def test_two_pass_cell_sort_gives_the_same_snapshot(name, monkeypatch):
     g = load(name)
     ncell = 41 if int(g["ndim"]) == 3 else 300                       # > 65536 cells, so the two-pass route is taken
     got = product_run(g, ncell=ncell)
-    monkeypatch.setenv("BFG_CELL_SORT", "1")
-    want = product_run(g, ncell=ncell)
-    for a, b in zip(got, want):
-        assert_close(a, b, name, rtol=1e-12, atol_scale=1e-13)        # summation order of the halo loop's REDs only
+    for mode in ("1", "3"):            # 1 = single-pass scatter, 3 = radix sort of (cell, index) pairs + gather
+        monkeypatch.setenv("BFG_CELL_SORT", mode)
+        want = product_run(g, ncell=ncell)
+        for a, b in zip(got, want):
+            assert_close(a, b, f"{name}, BFG_CELL_SORT={mode}", rtol=1e-12, atol_scale=1e-13)   # summation order of the REDs only
 
 
 def test_kept_cell_list_gives_the_same_snapshots_for_successive_models():
