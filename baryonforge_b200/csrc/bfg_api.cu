@@ -67,6 +67,11 @@ __global__ void k_ring_table(Hpx h, RingTabEntry *__restrict__ tab) {
             bool shifted;
             ring_theta_info(h, r, start, nr, e.theta, shifted);
             ring_z_sth(h, r, e.z, e.sth);
+            if (r + 1 < n) {
+                double th_next;
+                ring_theta_info(h, r + 1, start, nr, th_next, shifted);
+                e.inv_dth = 1.0 / (th_next - e.theta);
+            }
         }
         tab[r] = e;
     }

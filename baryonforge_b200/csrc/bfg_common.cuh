@@ -476,7 +476,21 @@ __device__ __forceinline__ void get_interpol(const Hpx &h, double theta, double 
 // i.e. ~1e-12 in a weight (the literal chain itself carries ~1e-11 through phi / dphi); a displaced direction within
 // round-off of a ring boundary may pick the neighbouring ring pair, where the bilinear weights are continuous.
 // Returns false (caller takes the literal path) next to the poles, for large displacements and for coarse maps.
-struct RingTabEntry { double theta, z, sth, pad; };
+struct RingTabEntry { double theta, z, sth, inv_dth; };   // inv_dth = 1 / (theta of the next ring - theta)
+
+// ring_pair with the reference's two divisions by dphi folded into ONE multiplication: tmp = phi nr / 2 pi - shift,
+// w1 = (phi - (i1 + shift) dphi) / dphi == tmp - i1 (identical in exact arithmetic; ~1e-12 apart in double, like everything
+// that goes through phi / dphi with up to 16384 pixels per ring)
+__device__ __forceinline__ void ring_pair_fast(i64 nr, bool shifted, i64 start, double phi, i64 &p0, i64 &p1, double &w1) {
+    const double tmp = fma(phi, (double)nr * BFG_INV_TWOPI, shifted ? -0.5 : 0.0);
+    const double fl = floor(tmp);
+    w1 = tmp - fl;
+    i64 i1 = (i64)fl, i2 = i1 + 1;
+    if (i1 < 0) i1 += nr;
+    if (i2 >= nr) i2 -= nr;
+    p0 = start + i1;
+    p1 = start + i2;
+}
 
 __device__ __forceinline__ bool regrid_target_fast(const Hpx &h, const RingTabEntry *__restrict__ rt, i64 p, double ox,
                                                    double oy, double oz, i64 pix[4], double w[4]) {
@@ -502,24 +516,24 @@ __device__ __forceinline__ bool regrid_target_fast(const Hpx &h, const RingTabEn
     if (phi < 0.0) phi += BFG_TWOPI;
     if (phi >= BFG_TWOPI) phi -= BFG_TWOPI;
     const double rho2 = fma(xn, xn, yn * yn);
-    const double inv_dn = 1.0 / sqrt(fma(zn, zn, rho2));
-    const double zc = zn * inv_dn, rs = sqrt(rho2) * inv_dn;                  // cos, sin of the displaced colatitude
+    const double inv_dn = rsqrt(fma(zn, zn, rho2));
+    const double zc = zn * inv_dn, rs = (rho2 * rsqrt(rho2)) * inv_dn;        // cos, sin of the displaced colatitude
     const i64 ir1 = ring_above(h, zc), ir2 = ir1 + 1;
     if (ir1 < 1 || ir2 > 4 * h.nside - 1) return false;                       // polar caps' first / last ring: literal path
-    const double th1 = __ldg(&rt[ir1].theta), z1 = __ldg(&rt[ir1].z), s1r = __ldg(&rt[ir1].sth), th2 = __ldg(&rt[ir2].theta);
+    const double z1 = __ldg(&rt[ir1].z), s1r = __ldg(&rt[ir1].sth), inv_dth = __ldg(&rt[ir1].inv_dth);
     const double s = fma(rs, z1, -(zc * s1r));                                // sin(theta' - theta_1)
     if (!(fabs(s) <= 0.05)) return false;
     const double s2 = s * s;
     const double dth = s * fma(s2, fma(s2, fma(s2, fma(s2, 35.0 / 1152.0, 15.0 / 336.0), 0.075), 1.0 / 6.0), 1.0);
-    const double wt = dth / (th2 - th1);
+    const double wt = dth * inv_dth;
     i64 sp, nr1;
     bool sh;
     double w1;
     ring_info(h, ir1, sp, nr1, sh);
-    ring_pair(nr1, sh, sp, phi, pix[0], pix[1], w1);
+    ring_pair_fast(nr1, sh, sp, phi, pix[0], pix[1], w1);
     w[0] = (1.0 - w1) * (1.0 - wt); w[1] = w1 * (1.0 - wt);
     ring_info(h, ir2, sp, nr1, sh);
-    ring_pair(nr1, sh, sp, phi, pix[2], pix[3], w1);
+    ring_pair_fast(nr1, sh, sp, phi, pix[2], pix[3], w1);
     w[2] = (1.0 - w1) * wt; w[3] = w1 * wt;
     return true;
 }

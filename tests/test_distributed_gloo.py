@@ -74,6 +74,17 @@ def _worker(rank, world, port, q):
     ok_node = ok_node and parallel.single_node_group() is False
     del os.environ["LOCAL_WORLD_SIZE"]
     parallel._SINGLE_NODE.clear()
+    # the slab-sharded grid path only takes the reduce-scatter + shared-host-map route inside an NCCL group on one machine:
+    # under gloo the gate says no before anything touches a device, and process() falls back to the all-reduce
+    import baryonforge_b200 as b
+    N = 16
+    pos, Mh = synth.box_halos(5, 100.0, seed=1)
+    gcat = b.HaloNDCatalog(x=pos[0], y=pos[1], z=pos[2], M=Mh, redshift=0.3, cosmo=synth.COSMO)
+    gm = b.GriddedMap(map=np.ones((N, N, N)), redshift=0.3, bins=(np.arange(N) + 0.5) * 100.0 / N, cosmo=synth.COSMO)
+    glo, ghi = parallel.plane_ranges(N, world)[rank]
+    grun = b.BaryonifyGrid(gcat, gm, 5, b.DisplacementModel(axes, synth.displacement_values(axes), 5, synth.COSMO),
+                           verbose=False, plane_range=(glo, ghi))
+    ok_node = ok_node and grun._slab_exchange(N, 3, glo, ghi, None) is None
     q.put((rank, bool(ok_gather), bool(ok_reduce and ok_simple and ok_node), int(keep.sum())))
     dist.destroy_process_group()
 

@@ -338,3 +338,27 @@ def test_out_of_table_warnings_once_per_catalogue():
     with warnings.catch_warnings():
         warnings.simplefilter("error")
         _warn_table_range(model, np.array([0.2]), np.array([1e13]))                        # in range: silent
+
+
+def test_record_layout_and_chunk_fractions(monkeypatch):
+    """Host logic of the round-2 end-to-end paths: which particle catalogues cross the link as raw 32-byte records, and where the
+    latitude chunks of the pipelined shell paths start."""
+    from baryonforge_b200 import runners
+    ref = np.zeros(10, [('M', 'f8'), ('x', 'f8'), ('y', 'f8'), ('z', 'f8')])          # utils/io.py:588
+    assert runners._record_layout(ref, ['x', 'y', 'z']) == dict(M=0, x=1, y=2, z=3)
+    assert runners._record_layout(np.zeros(4, [('z', 'f8'), ('y', 'f8'), ('x', 'f8'), ('M', 'f8')]), ['x', 'y']) == dict(z=0, y=1, x=2, M=3)
+    assert ref.view(np.float64).shape == (40,)                                       # the raw view the staging copies
+    for bad in (np.zeros(10, [('M', 'f4'), ('x', 'f8'), ('y', 'f8'), ('z', 'f8')]),   # float32 masses
+                np.zeros(10, [('M', '>f8'), ('x', 'f8'), ('y', 'f8'), ('z', 'f8')]),  # big-endian field
+                np.zeros(10, [('M', 'f8'), ('x', 'f8'), ('y', 'f8'), ('z', 'f8'), ('id', 'i8')]),
+                np.zeros(10, [('M', 'f8'), ('x', 'f8'), ('y', 'f8')]),
+                ref[::2], np.zeros((2, 5), ref.dtype), np.zeros(10)):
+        assert runners._record_layout(bad, ['x', 'y']) is None
+    assert runners._record_layout(np.zeros(3, [('M', 'f8'), ('x', 'f8'), ('y', 'f8'), ('w', 'f8')]), ['x', 'y', 'z']) is None
+    for K in (1, 4, 6, 8, 12, 24):
+        fr = runners._chunk_fractions(K)
+        assert len(fr) == K and fr[0] == 0.0 and all(b > a for a, b in zip(fr[:-1], fr[1:])) and fr[-1] < 1.0
+        if K >= 6:
+            assert fr[-3:] == [0.90, 0.96, 0.99]                                      # the exposed tail is a 1 % piece
+    monkeypatch.setenv("BFG_PIPELINE_TAPER", "0")
+    assert runners._chunk_fractions(8) == [k / 8 for k in range(8)]
