@@ -117,6 +117,7 @@ __global__ void k_fast_log2(i64 n, const double2 *__restrict__ g_tab, const doub
 }
 
 extern "C" int bfg_test_fast_log2(int64_t n, const double *d_x, double *d_out, void *stream) {
+    BFG_ENTRY();
     BFG_REQUIRE(d_x && d_out, "null argument");
     const double2 *g_tab = nullptr;
     if (int rc = get_log2_table(&g_tab)) return rc;
@@ -136,6 +137,7 @@ extern "C" int bfg_device_count(void) {
 }
 
 extern "C" int bfg_device_info(int device, int *sm_count, int64_t *mem_total, int64_t *mem_free) {
+    BFG_ENTRY();
     cudaDeviceProp p;
     BFG_CUDA_OK(cudaGetDeviceProperties(&p, device));
     if (sm_count) *sm_count = p.multiProcessorCount;
@@ -153,6 +155,7 @@ extern "C" int bfg_device_info(int device, int *sm_count, int64_t *mem_total, in
 // ------------------------------------------------------------------------------------------------ tables
 extern "C" int bfg_table_create(bfg_table **out, int ndim, const int64_t *shape, const double *const *h_axes,
                                 const double *h_values, int flags, int device) {
+    BFG_ENTRY();
     BFG_REQUIRE(out && shape && h_axes && h_values, "null argument");
     BFG_REQUIRE(ndim >= 3 && ndim <= BFG_MAX_TABLE_DIM, "ndim must be 3..6 (ln(1+z), ln M, ln r, extras...)");
     for (int d = 0; d < ndim; ++d) {
@@ -209,6 +212,7 @@ extern "C" int bfg_table_create(bfg_table **out, int ndim, const int64_t *shape,
 }
 
 extern "C" int bfg_table_destroy(bfg_table *t) {
+    BFG_ENTRY();
     if (!t) return BFG_OK;
     int cur = 0;
     cudaGetDevice(&cur);
@@ -222,6 +226,7 @@ extern "C" int bfg_table_destroy(bfg_table *t) {
 }
 
 extern "C" int bfg_table_info(const bfg_table *t, int *ndim, int64_t *shape, int *flags, int *device, int *uniform_r) {
+    BFG_ENTRY();
     BFG_REQUIRE(t, "null table");
     if (ndim) *ndim = t->view.ndim;
     if (shape) for (int d = 0; d < t->view.ndim; ++d) shape[d] = t->shape[d];
@@ -250,6 +255,7 @@ __global__ void k_table_readout(TableView T, double lnz, double lnM, ExtrasArg e
 
 extern "C" int bfg_table_readout(const bfg_table *t, double lnz, double lnM, const double *h_extras, int64_t n,
                                  const double *d_x, double *d_out, void *stream) {
+    BFG_ENTRY();
     BFG_REQUIRE(t && d_x && d_out, "null argument");
     ExtrasArg ex;
     memset(&ex, 0, sizeof(ex));
@@ -281,6 +287,7 @@ __global__ void k_sum_f64(const double *__restrict__ x, i64 n, double *out) {
 }
 
 extern "C" int bfg_sum_f64(const double *d_x, int64_t n, double *d_out, void *stream) {
+    BFG_ENTRY();
     BFG_REQUIRE(d_out && (d_x || n == 0), "null argument");
     BFG_CUDA_OK(cudaMemsetAsync(d_out, 0, sizeof(double), (cudaStream_t)stream));
     if (n > 0) {
@@ -297,6 +304,7 @@ __global__ void k_transpose_offsets(const double *__restrict__ in, double *__res
 }
 
 extern "C" int bfg_transpose_offsets(const double *d_in, double *d_out, int64_t n, int ncomp, void *stream) {
+    BFG_ENTRY();
     BFG_REQUIRE(d_in && d_out && ncomp >= 1 && ncomp <= 64, "bad argument");
     if (n == 0) return BFG_OK;
     int blocks = (int)std::min<i64>((n + 255) / 256, 148 * 16);
@@ -307,6 +315,7 @@ extern "C" int bfg_transpose_offsets(const double *d_in, double *d_out, int64_t 
 
 // ------------------------------------------------------------------------------------------------ peer memory (IPC)
 extern "C" int bfg_shared_alloc(void **d_ptr, int64_t bytes, int device) {
+    BFG_ENTRY();
     BFG_REQUIRE(d_ptr && bytes >= 0, "bad argument");
     int cur = 0;
     BFG_CUDA_OK(cudaGetDevice(&cur));
@@ -318,11 +327,13 @@ extern "C" int bfg_shared_alloc(void **d_ptr, int64_t bytes, int device) {
 }
 
 extern "C" int bfg_shared_free(void *d_ptr) {
+    BFG_ENTRY();
     if (d_ptr) BFG_CUDA_OK(cudaFree(d_ptr));
     return BFG_OK;
 }
 
 extern "C" int bfg_ipc_export(const void *d_ptr, unsigned char *handle64) {
+    BFG_ENTRY();
     BFG_REQUIRE(d_ptr && handle64, "null argument");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     cudaIpcMemHandle_t hdl;
@@ -332,6 +343,7 @@ extern "C" int bfg_ipc_export(const void *d_ptr, unsigned char *handle64) {
 }
 
 extern "C" int bfg_ipc_import(const unsigned char *handle64, void **d_peer_ptr) {
+    BFG_ENTRY();
     BFG_REQUIRE(handle64 && d_peer_ptr, "null argument");
     cudaIpcMemHandle_t hdl;
     memcpy(&hdl, handle64, 64);
@@ -340,6 +352,7 @@ extern "C" int bfg_ipc_import(const unsigned char *handle64, void **d_peer_ptr) 
 }
 
 extern "C" int bfg_ipc_close(void *d_peer_ptr) {
+    BFG_ENTRY();
     if (d_peer_ptr) BFG_CUDA_OK(cudaIpcCloseMemHandle(d_peer_ptr));
     return BFG_OK;
 }
@@ -348,17 +361,20 @@ extern "C" int bfg_ipc_close(void *d_peer_ptr) {
 // Page-locks a host range that several processes of the box have mapped (memfd / POSIX shared memory), so each rank
 // can copy its owned slice of a result map straight into ONE host map at full PCIe speed (parallel.SharedHostMaps).
 extern "C" int bfg_host_register(void *h_ptr, int64_t bytes) {
+    BFG_ENTRY();
     BFG_REQUIRE(h_ptr && bytes > 0, "bad argument");
     BFG_CUDA_OK(cudaHostRegister(h_ptr, (size_t)bytes, cudaHostRegisterPortable));
     return BFG_OK;
 }
 
 extern "C" int bfg_host_unregister(void *h_ptr) {
+    BFG_ENTRY();
     if (h_ptr) BFG_CUDA_OK(cudaHostUnregister(h_ptr));
     return BFG_OK;
 }
 
 extern "C" int bfg_copy_to_host_async(void *h_dst, const void *d_src, int64_t bytes, void *stream) {
+    BFG_ENTRY();
     BFG_REQUIRE(bytes >= 0 && (bytes == 0 || (h_dst && d_src)), "bad argument");
     if (bytes) BFG_CUDA_OK(cudaMemcpyAsync(h_dst, d_src, (size_t)bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     return BFG_OK;

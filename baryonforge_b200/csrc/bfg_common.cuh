@@ -46,6 +46,12 @@ struct StreamScratch {
     template <class T> T *as() const { return (T *)p; }
 };
 
+// First statement of every entry point: forget a NON-sticky error another library left behind in this thread.  NCCL probes
+// features at its first collective of a kind (8 ranks, first reduce-scatter: an internal call failed with
+// cudaErrorOperatingSystem, NCCL fell back -- and the next `cudaGetLastError()` after one of OUR launches reported it).
+// Sticky errors (a faulted context) are not cleared by this and still surface in the checks below.
+#define BFG_ENTRY() ((void)cudaGetLastError())
+
 #define BFG_REQUIRE(cond, msg)                                    \
     do {                                                          \
         if (!(cond)) {                                            \

@@ -286,6 +286,7 @@ int launch_grid(const bfg_table *t, int ndim, i64 N, double res, double scale, i
 extern "C" int bfg_grid_offsets(const bfg_table *t, int ndim, int64_t N, double res, int64_t n_halo,
                                 const double *d_halos, const double *d_extras, int n_extra, int use_ell,
                                 double *d_offsets, int64_t plane_lo, int64_t plane_hi, int64_t *d_nupdates, void *stream) {
+    BFG_ENTRY();
     return launch_grid<MODE_BARYONIFY>(t, ndim, N, res, 1.0, n_halo, d_halos, d_extras, n_extra, use_ell, d_offsets, plane_lo,
                               plane_hi, (i64 *)d_nupdates, (cudaStream_t)stream);
 }
@@ -293,6 +294,7 @@ extern "C" int bfg_grid_offsets(const bfg_table *t, int ndim, int64_t N, double 
 extern "C" int bfg_grid_paint(const bfg_table *t, int ndim, int64_t N, double res, double scale, int64_t n_halo,
                               const double *d_halos, const double *d_extras, int n_extra, int use_ell, double *d_map,
                               int64_t plane_lo, int64_t plane_hi, int64_t *d_nupdates, void *stream) {
+    BFG_ENTRY();
     return launch_grid<MODE_PAINT>(t, ndim, N, res, scale, n_halo, d_halos, d_extras, n_extra, use_ell, d_map, plane_lo,
                              plane_hi, (i64 *)d_nupdates, (cudaStream_t)stream);
 }
@@ -301,12 +303,14 @@ extern "C" int bfg_grid_paint_anis(const bfg_table *t_paint, const bfg_table *t_
                                    int64_t n_halo, const double *d_halos, const double *d_extras, int n_extra, int use_ell,
                                    const double *d_mtot, double mtot_add, const double *d_orig, double *d_map,
                                    int64_t plane_lo, int64_t plane_hi, int64_t *d_nupdates, void *stream) {
+    BFG_ENTRY();
     return launch_grid<MODE_ANIS>(t_paint, 2, N, res, 1.0, n_halo, d_halos, d_extras, n_extra, use_ell, d_map, plane_lo,
                                   plane_hi, (i64 *)d_nupdates, (cudaStream_t)stream, t_tracer, d_mtot, d_orig, mtot_add);
 }
 
 extern "C" int bfg_grid_regrid(int ndim, int64_t N, const double *d_map_in, const double *d_offsets, double *d_map_out,
                                int64_t plane_lo, int64_t plane_hi, void *stream) {
+    BFG_ENTRY();
     BFG_REQUIRE(d_map_in && d_offsets && d_map_out, "null argument");
     BFG_REQUIRE(ndim == 2 || ndim == 3, "ndim must be 2 or 3");
     BFG_REQUIRE(N >= 4 && N <= 32768, "N out of range (need 4 <= N <= 32768)");

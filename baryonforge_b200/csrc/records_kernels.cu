@@ -105,6 +105,7 @@ extern "C" int bfg_shell_records(int64_t n_halo, const double *d_cols, int paint
                                  double pixarea, int n_DA, const double *d_DA_x, const double *d_DA_c, int n_g,
                                  const double *d_g_x, const double *d_g_run_c, const double *d_g_mod_c, double *d_halos,
                                  double *d_aux, void *stream) {
+    BFG_ENTRY();
     BFG_REQUIRE(n_halo >= 0, "negative halo count");
     if (n_halo == 0) return BFG_OK;
     BFG_REQUIRE(d_cols && d_halos && d_DA_x && d_DA_c && d_g_x && d_g_run_c, "null argument");
@@ -209,6 +210,7 @@ k_box_records(i64 n, const double *__restrict__ cols, BoxParams P, double *__res
 extern "C" int bfg_box_records(int64_t n_halo, const double *d_cols, int ndim, int grid, int paint, double a, double lnz,
                                double g_run, double g_mod, double eps_run, double eps_mod, double res, double rq_clip,
                                int64_t N, const double *d_bins, double *d_halos, double *d_aux, void *stream) {
+    BFG_ENTRY();
     BFG_REQUIRE(n_halo >= 0 && (ndim == 2 || ndim == 3), "bad argument");
     if (n_halo == 0) return BFG_OK;
     BFG_REQUIRE(d_cols && d_halos, "null argument");

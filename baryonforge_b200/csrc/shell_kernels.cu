@@ -1187,6 +1187,7 @@ int launch_shell(const bfg_table *t, int nside, i64 n_halo, const double *d_halo
 extern "C" int bfg_shell_offsets(const bfg_table *t, int nside, int64_t n_halo, const double *d_halos,
                                  const double *d_extras, int n_extra, double *d_offsets, int64_t pix_lo, int64_t pix_hi,
                                  int64_t *d_nupdates, void *stream) {
+    BFG_ENTRY();
     return launch_shell<MODE_BARYONIFY>(t, nside, n_halo, d_halos, d_extras, n_extra, d_offsets, pix_lo, pix_hi,
                                (i64 *)d_nupdates, (cudaStream_t)stream);
 }
@@ -1194,6 +1195,7 @@ extern "C" int bfg_shell_offsets(const bfg_table *t, int nside, int64_t n_halo, 
 extern "C" int bfg_shell_paint(const bfg_table *t, int nside, int64_t n_halo, const double *d_halos,
                                const double *d_extras, int n_extra, double *d_map, int64_t pix_lo, int64_t pix_hi,
                                int64_t *d_nupdates, void *stream) {
+    BFG_ENTRY();
     return launch_shell<MODE_PAINT>(t, nside, n_halo, d_halos, d_extras, n_extra, d_map, pix_lo, pix_hi, (i64 *)d_nupdates,
                               (cudaStream_t)stream);
 }
@@ -1202,6 +1204,7 @@ extern "C" int bfg_shell_paint_anis(const bfg_table *t_paint, const bfg_table *t
                                     const double *d_halos, const double *d_extras, int n_extra, const double *d_mtot,
                                     double mtot_add, const double *d_orig, double *d_map, int64_t pix_lo,
                                     int64_t pix_hi, int64_t *d_nupdates, void *stream) {
+    BFG_ENTRY();
     return launch_shell<MODE_ANIS>(t_paint, nside, n_halo, d_halos, d_extras, n_extra, d_map, pix_lo, pix_hi,
                                    (i64 *)d_nupdates, (cudaStream_t)stream, t_tracer, d_mtot, d_orig, mtot_add);
 }
@@ -1223,6 +1226,7 @@ k_anis_background(i64 n, const double *__restrict__ mtot, double mtot_add, const
 
 extern "C" int bfg_anis_background(int64_t n, const double *d_mtot, double mtot_add, const double *d_orig, double coef,
                                    double final_scale, double *d_map, void *stream) {
+    BFG_ENTRY();
     BFG_REQUIRE(n >= 0 && (n == 0 || (d_mtot && d_orig && d_map)), "null argument");
     if (n == 0) return BFG_OK;
     k_anis_background<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(n, d_mtot, mtot_add, d_orig, coef, final_scale,
@@ -1233,6 +1237,7 @@ extern "C" int bfg_anis_background(int64_t n, const double *d_mtot, double mtot_
 
 extern "C" int bfg_shell_regrid(int nside, const double *d_map_in, const double *d_offsets, double *d_map_out,
                                 int64_t pix_lo, int64_t pix_hi, void *stream) {
+    BFG_ENTRY();
     BFG_REQUIRE(d_map_in && d_offsets && d_map_out, "null argument");
     if (int rc = check_nside(nside)) return rc;
     Hpx h(nside);
@@ -1248,6 +1253,7 @@ extern "C" int bfg_shell_regrid(int nside, const double *d_map_in, const double 
 
 extern "C" int bfg_shell_regrid_range(int nside, const double *d_map_in, const double *d_offsets, int64_t comp_stride,
                                       double *d_map_out, int64_t src_lo, int64_t src_hi, void *stream) {
+    BFG_ENTRY();
     BFG_REQUIRE(d_map_in && d_offsets && d_map_out, "null argument");
     if (int rc = check_nside(nside)) return rc;
     Hpx h(nside);
@@ -1263,6 +1269,7 @@ extern "C" int bfg_shell_regrid_range(int nside, const double *d_map_in, const d
 
 extern "C" int bfg_offsets_max_norm2(const double *d_offsets, int64_t comp_stride, int64_t lo, int64_t hi, double *d_out,
                                      void *stream) {
+    BFG_ENTRY();
     BFG_REQUIRE(d_offsets && d_out && lo >= 0 && lo <= hi && hi <= comp_stride, "bad argument");
     BFG_CUDA_OK(cudaMemsetAsync(d_out, 0, sizeof(double), (cudaStream_t)stream));
     if (lo == hi) return BFG_OK;
@@ -1274,6 +1281,7 @@ extern "C" int bfg_offsets_max_norm2(const double *d_offsets, int64_t comp_strid
 
 extern "C" int bfg_halo_band_bounds(int64_t n_halo, const double *d_sorted_halos, double band, int n_edges,
                                     const int64_t *d_edge_band, int64_t *d_bounds, double *d_rho_max, void *stream) {
+    BFG_ENTRY();
     BFG_REQUIRE(d_sorted_halos && d_edge_band && d_bounds && d_rho_max && band > 0 && n_edges >= 1 && n_edges <= 4096,
                 "bad argument");
     BFG_CUDA_OK(cudaMemsetAsync(d_rho_max, 0, sizeof(double), (cudaStream_t)stream));
@@ -1284,6 +1292,7 @@ extern "C" int bfg_halo_band_bounds(int64_t n_halo, const double *d_sorted_halos
 }
 
 extern "C" int bfg_healpix_disc_counts(int nside, int64_t n_halo, const double *d_halos, int64_t *d_npix, void *stream) {
+    BFG_ENTRY();
     BFG_REQUIRE(d_halos && d_npix, "null argument");
     if (int rc = check_nside(nside)) return rc;
     if (n_halo == 0) return BFG_OK;
@@ -1294,6 +1303,7 @@ extern "C" int bfg_healpix_disc_counts(int nside, int64_t n_halo, const double *
 
 extern "C" int bfg_healpix_query_disc(int nside, const double *d_halo, int64_t *d_pix, int64_t cap, int64_t *d_count,
                                       void *stream) {
+    BFG_ENTRY();
     BFG_REQUIRE(d_halo && d_count && (d_pix || cap == 0), "null argument");
     if (int rc = check_nside(nside)) return rc;
     k_query_disc<<<1, 32, 0, (cudaStream_t)stream>>>(Hpx(nside), d_halo, (i64 *)d_pix, cap, (i64 *)d_count);
@@ -1302,6 +1312,7 @@ extern "C" int bfg_healpix_query_disc(int nside, const double *d_halo, int64_t *
 }
 
 extern "C" int bfg_healpix_pix2vec(int nside, int64_t pix_lo, int64_t pix_hi, double *d_xyz, void *stream) {
+    BFG_ENTRY();
     BFG_REQUIRE(d_xyz, "null argument");
     if (int rc = check_nside(nside)) return rc;
     Hpx h(nside);
@@ -1314,6 +1325,7 @@ extern "C" int bfg_healpix_pix2vec(int nside, int64_t pix_lo, int64_t pix_hi, do
 
 extern "C" int bfg_healpix_interp_weights(int nside, int64_t n, const double *d_theta, const double *d_phi,
                                           int64_t *d_pix, double *d_w, void *stream) {
+    BFG_ENTRY();
     BFG_REQUIRE(d_theta && d_phi && d_pix && d_w, "null argument");
     if (int rc = check_nside(nside)) return rc;
     if (n == 0) return BFG_OK;
@@ -1324,6 +1336,7 @@ extern "C" int bfg_healpix_interp_weights(int nside, int64_t n, const double *d_
 
 extern "C" int bfg_healpix_ang2pix(int nside, int64_t n, const double *d_theta, const double *d_phi, int64_t *d_pix,
                                    void *stream) {
+    BFG_ENTRY();
     BFG_REQUIRE(d_theta && d_phi && d_pix, "null argument");
     if (int rc = check_nside(nside)) return rc;
     if (n == 0) return BFG_OK;
@@ -1334,6 +1347,7 @@ extern "C" int bfg_healpix_ang2pix(int nside, int64_t n, const double *d_theta, 
 
 extern "C" int bfg_healpix_reorder(int nside, int to_nest, int64_t n, const int64_t *d_pix_in, int64_t *d_pix_out,
                                    void *stream) {
+    BFG_ENTRY();
     BFG_REQUIRE(d_pix_in && d_pix_out, "null argument");
     if (int rc = check_nside(nside)) return rc;
     BFG_REQUIRE((nside & (nside - 1)) == 0, "the NESTED scheme needs nside to be a power of two");
@@ -1362,6 +1376,7 @@ struct DevBuf {
 extern "C" int bfg_shell_baryonify_host(const bfg_table *t, int nside, int64_t n_halo, const double *h_halos,
                                         const double *h_extras, int n_extra, const double *h_map_in, double *h_map_out,
                                         int64_t *h_nupdates, double *h_sums) {
+    BFG_ENTRY();
     BFG_REQUIRE(t && h_map_in && h_map_out && (h_halos || n_halo == 0), "null argument");
     if (int rc = check_nside(nside)) return rc;
     BFG_CUDA_OK(cudaSetDevice(t->device));
@@ -1400,6 +1415,7 @@ extern "C" int bfg_shell_baryonify_host(const bfg_table *t, int nside, int64_t n
 
 extern "C" int bfg_shell_paint_host(const bfg_table *t, int nside, int64_t n_halo, const double *h_halos,
                                     const double *h_extras, int n_extra, double *h_map_out, int64_t *h_nupdates) {
+    BFG_ENTRY();
     BFG_REQUIRE(t && h_map_out && (h_halos || n_halo == 0), "null argument");
     if (int rc = check_nside(nside)) return rc;
     BFG_CUDA_OK(cudaSetDevice(t->device));
@@ -1498,6 +1514,7 @@ static int regrid_p2p_impl(int nside, const double *d_map_in, const double *d_of
 extern "C" int bfg_shell_regrid_p2p(int nside, const double *d_map_in, const double *d_offsets, int64_t pix_lo,
                                     int64_t pix_hi, int world, int self, const int64_t *h_bounds,
                                     double *const *h_slices, int64_t *d_remote_count, void *stream) {
+    BFG_ENTRY();
     return regrid_p2p_impl(nside, d_map_in, d_offsets, pix_lo, pix_hi, pix_lo, pix_hi, world, self, h_bounds, h_slices,
                            d_remote_count, true, stream);
 }
@@ -1506,6 +1523,7 @@ extern "C" int bfg_shell_regrid_p2p_range(int nside, const double *d_map_in, con
                                           int64_t pix_hi, int64_t src_lo, int64_t src_hi, int world, int self,
                                           const int64_t *h_bounds, double *const *h_slices, int64_t *d_remote_count,
                                           void *stream) {
+    BFG_ENTRY();
     return regrid_p2p_impl(nside, d_map_in, d_offsets, pix_lo, pix_hi, src_lo, src_hi, world, self, h_bounds, h_slices,
                            d_remote_count, false, stream);
 }

@@ -317,6 +317,7 @@ extern "C" int64_t bfg_sht_workspace_elems(int nside, int lmax) {
 
 extern "C" int bfg_sht_map2alm_pass(int nside, int lmax, const double *d_map, const double *d_ln_mm, double *d_work,
                                     double *d_alm, void *stream) {
+    BFG_ENTRY();
     if (int rc = check_sht_args(nside, lmax)) return rc;
     BFG_REQUIRE(d_map && d_ln_mm && d_work && d_alm, "null argument");
     cudaStream_t st = (cudaStream_t)stream;
@@ -338,6 +339,7 @@ extern "C" int bfg_sht_map2alm_pass(int nside, int lmax, const double *d_map, co
 
 extern "C" int bfg_sht_alm2map(int nside, int lmax, const double *d_alm, const double *d_ln_mm, double *d_work, double *d_map,
                                void *stream) {
+    BFG_ENTRY();
     if (int rc = check_sht_args(nside, lmax)) return rc;
     BFG_REQUIRE(d_map && d_ln_mm && d_work && d_alm, "null argument");
     cudaStream_t st = (cudaStream_t)stream;
@@ -354,6 +356,7 @@ extern "C" int bfg_sht_alm2map(int nside, int lmax, const double *d_alm, const d
 }
 
 extern "C" int bfg_sht_alm2cl(int lmax, const double *d_alm, double *d_cl, void *stream) {
+    BFG_ENTRY();
     BFG_REQUIRE(lmax >= 0 && d_alm && d_cl, "bad argument");
     k_sht_alm2cl<<<(lmax + 256) / 256, 256, 0, (cudaStream_t)stream>>>(lmax, (const double2 *)d_alm, d_cl);
     BFG_CUDA_OK(cudaGetLastError());

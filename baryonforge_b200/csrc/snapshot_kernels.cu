@@ -349,12 +349,14 @@ int blocks_for(i64 n, int threads) { return (int)std::max<i64>(1, std::min<i64>(
 extern "C" int bfg_snap_build_cells(int ndim, int64_t n_part, const double *d_x, const double *d_y, const double *d_z,
                                     double L, int ncell, int64_t *d_cell_start, int64_t *d_order, double *d_xs,
                                     double *d_ys, double *d_zs, void *stream) {
+    BFG_ENTRY();
     return bfg_snap_build_cells_strided(ndim, n_part, d_x, d_y, d_z, 1, L, ncell, d_cell_start, d_order, d_xs, d_ys, d_zs, stream);
 }
 
 extern "C" int bfg_snap_build_cells_strided(int ndim, int64_t n_part, const double *d_x, const double *d_y, const double *d_z,
                                             int64_t stride, double L, int ncell, int64_t *d_cell_start, int64_t *d_order,
                                             double *d_xs, double *d_ys, double *d_zs, void *stream) {
+    BFG_ENTRY();
     BFG_REQUIRE(ndim == 2 || ndim == 3, "ndim must be 2 or 3");
     BFG_REQUIRE(stride >= 1, "stride must be >= 1");
     BFG_REQUIRE(d_x && d_y && (ndim == 2 || d_z) && d_cell_start && d_order && d_xs && d_ys && (ndim == 2 || d_zs), "null argument");
@@ -435,6 +437,7 @@ extern "C" int bfg_snap_offsets(const bfg_table *t, int ndim, int64_t n_part, co
                                 const double *d_zs, double L, int ncell, const int64_t *d_cell_start, int64_t n_halo,
                                 const double *d_halos, const double *d_extras, int n_extra, double *d_tot,
                                 int64_t *d_npairs, void *stream) {
+    BFG_ENTRY();
     BFG_REQUIRE(t && d_xs && d_ys && (ndim == 2 || d_zs) && d_cell_start && d_tot && (d_halos || n_halo == 0), "null argument");
     BFG_REQUIRE(ndim == 2 || ndim == 3, "ndim must be 2 or 3");
     BFG_REQUIRE(n_extra == t->view.ndim - 3, "n_extra must equal the table's extra axes");
@@ -463,6 +466,7 @@ extern "C" int bfg_snap_offsets(const bfg_table *t, int ndim, int64_t n_part, co
 extern "C" int bfg_snap_apply(int ndim, int64_t n_part, const double *d_xs, const double *d_ys, const double *d_zs,
                               const double *d_tot, const int64_t *d_order, double L, double *d_x_out, double *d_y_out,
                               double *d_z_out, void *stream) {
+    BFG_ENTRY();
     BFG_REQUIRE(ndim == 2 || ndim == 3, "ndim must be 2 or 3");
     BFG_REQUIRE(d_xs && d_ys && d_tot && d_order && d_x_out && d_y_out && (ndim == 2 || (d_zs && d_z_out)), "null argument");
     if (n_part == 0) return BFG_OK;
@@ -485,6 +489,7 @@ extern "C" int bfg_snap_apply(int ndim, int64_t n_part, const double *d_xs, cons
 extern "C" int bfg_snap_apply_records(int ndim, int64_t n_part, const double *d_xs, const double *d_ys, const double *d_zs,
                                       const double *d_tot, const int64_t *d_order, double L, const double *d_rec_in,
                                       double *d_rec_out, int fx, int fy, int fz, void *stream) {
+    BFG_ENTRY();
     BFG_REQUIRE(ndim == 2 || ndim == 3, "ndim must be 2 or 3");
     BFG_REQUIRE(d_xs && d_ys && d_tot && d_order && d_rec_in && d_rec_out && (ndim == 2 || d_zs), "null argument");
     BFG_REQUIRE((((uintptr_t)d_rec_in | (uintptr_t)d_rec_out) & 31) == 0, "records must be 32-byte aligned");
@@ -504,6 +509,7 @@ extern "C" int bfg_snap_apply_records(int ndim, int64_t n_part, const double *d_
 
 extern "C" int bfg_snap_deposit_ngp(int ndim, int64_t n_part, const double *d_x, const double *d_y, const double *d_z,
                                     const double *d_mass, double L, int64_t n_grid, double *d_grid, void *stream) {
+    BFG_ENTRY();
     BFG_REQUIRE(ndim == 2 || ndim == 3, "ndim must be 2 or 3");
     BFG_REQUIRE(d_x && d_y && (ndim == 2 || d_z) && d_mass && d_grid, "null argument");
     BFG_REQUIRE(n_grid >= 1 && L > 0, "bad grid");
@@ -518,6 +524,7 @@ extern "C" int bfg_snap_deposit_ngp(int ndim, int64_t n_part, const double *d_x,
 extern "C" int bfg_snap_apply_deposit(int ndim, int64_t n_part, const double *d_xs, const double *d_ys, const double *d_zs,
                                       const double *d_tot, const int64_t *d_order, const double *d_mass, double mass_const,
                                       double L, int64_t n_grid, double *d_grid, void *stream) {
+    BFG_ENTRY();
     BFG_REQUIRE(ndim == 2 || ndim == 3, "ndim must be 2 or 3");
     BFG_REQUIRE(n_grid >= 1 && L > 0, "bad grid");
     if (n_part == 0) return BFG_OK;

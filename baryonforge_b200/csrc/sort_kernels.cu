@@ -132,6 +132,7 @@ int halo_sort_impl(int mode, int64_t n_halo, const double *d_in, double *d_out, 
 
 extern "C" int bfg_halo_sort(int mode, int64_t n_halo, const double *d_in, double *d_out, const double *d_extras_in,
                              double *d_extras_out, int n_extra, double p0, double p1, int ndim, void *stream) {
+    BFG_ENTRY();
     BFG_REQUIRE(mode == 0 || mode == 1, "mode: 0 = sky bands, 1 = box cells");
     return halo_sort_impl(mode, n_halo, d_in, d_out, d_extras_in, d_extras_out, n_extra, p0, p1, ndim, 0, 0, 0, stream);
 }
@@ -139,6 +140,7 @@ extern "C" int bfg_halo_sort(int mode, int64_t n_halo, const double *d_in, doubl
 extern "C" int bfg_halo_sort_owned(int nside, int64_t pix_lo, int64_t pix_hi, int64_t n_halo, const double *d_in,
                                    double *d_out, const double *d_extras_in, double *d_extras_out, int n_extra,
                                    double band, void *stream) {
+    BFG_ENTRY();
     BFG_REQUIRE(pix_lo >= 0 && pix_lo <= pix_hi, "bad pixel range");
     return halo_sort_impl(2, n_halo, d_in, d_out, d_extras_in, d_extras_out, n_extra, band, 0.0, 3, nside, pix_lo, pix_hi,
                           stream);

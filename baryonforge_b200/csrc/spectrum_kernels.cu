@@ -244,6 +244,7 @@ int launch_power_bins(int N, const double2 *spec, const double *d_klin, double k
 
 extern "C" int bfg_snap_deposit_folded(int64_t n_part, const double *d_x, const double *d_y, const double *d_z, double L_fold,
                                        int64_t n_grid, double *d_grid, int64_t *d_ndropped, void *stream) {
+    BFG_ENTRY();
     BFG_REQUIRE(n_part >= 0 && n_grid >= 1 && n_grid <= 4096 && L_fold > 0, "bad argument");
     cudaStream_t st = (cudaStream_t)stream;
     if (d_ndropped) BFG_CUDA_OK(cudaMemsetAsync(d_ndropped, 0, sizeof(int64_t), st));
@@ -258,6 +259,7 @@ extern "C" int bfg_snap_deposit_folded(int64_t n_part, const double *d_x, const 
 extern "C" int bfg_snap_apply_deposit_folded(int64_t n_part, const double *d_xs, const double *d_ys, const double *d_zs,
                                              const double *d_tot, double L, double L_fold, int64_t n_grid, double *d_grid,
                                              int64_t *d_ndropped, void *stream) {
+    BFG_ENTRY();
     BFG_REQUIRE(n_part >= 0 && n_grid >= 1 && n_grid <= 4096 && L_fold > 0 && L > 0, "bad argument");
     cudaStream_t st = (cudaStream_t)stream;
     if (d_ndropped) BFG_CUDA_OK(cudaMemsetAsync(d_ndropped, 0, sizeof(int64_t), st));
@@ -272,6 +274,7 @@ extern "C" int bfg_snap_apply_deposit_folded(int64_t n_part, const double *d_xs,
 
 extern "C" int bfg_power_bin_spectrum(int64_t N, const double *d_spec, const double *d_klin, double k0, double dk, int64_t Nk,
                                       double *d_pk_sum, double *d_k_sum, int64_t *d_count, void *stream) {
+    BFG_ENTRY();
     BFG_REQUIRE(N >= 2 && N <= 4096 && Nk >= 1 && Nk <= 8192 && dk > 0, "bad argument");
     BFG_REQUIRE(d_klin && d_pk_sum && d_k_sum && d_count, "null argument");
     return launch_power_bins((int)N, (const double2 *)d_spec, d_klin, k0, dk, (int)Nk, d_pk_sum, d_k_sum, d_count,
@@ -280,6 +283,7 @@ extern "C" int bfg_power_bin_spectrum(int64_t N, const double *d_spec, const dou
 
 extern "C" int bfg_grid_power_spectrum(int64_t N, const double *d_grid, const double *d_klin, double k0, double dk, int64_t Nk,
                                        double *d_pk_sum, double *d_k_sum, int64_t *d_count, void *stream) {
+    BFG_ENTRY();
     BFG_REQUIRE(N >= 2 && N <= 4096 && Nk >= 1 && Nk <= 8192 && dk > 0, "bad argument");
     BFG_REQUIRE(d_grid && d_klin && d_pk_sum && d_k_sum && d_count, "null argument");
     cudaStream_t st = (cudaStream_t)stream;
