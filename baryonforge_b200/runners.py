@@ -117,6 +117,24 @@ def _pinned_result(numel):
 _PINNED_SCRATCH = {}   # numel -> list of idle pinned float64 staging tensors (halo-record batches)
 
 
+def release_host_buffers():
+    """
+    Give the IDLE page-locked buffers of this process back to the system: recycled result buffers (_pinned_result), staging
+    rings (_take_scratch) and what torch's pinned-memory allocator caches behind them.  Buffers a caller still holds (results of
+    earlier process() calls) and the shared host maps of sharded runs are not touched.  For long-lived processes that move on to
+    a workload of a different size (the pools are keyed by size: a 2.5e8-particle run leaves 8 GB result buffers behind).
+    """
+    _PINNED_FREE.clear()
+    _PINNED_SCRATCH.clear()
+    import gc
+    gc.collect()
+    try:
+        import torch
+        torch._C._host_emptyCache()
+    except Exception:      # older torch: the cached pinned blocks stay with its allocator
+        pass
+
+
 def _take_scratch(numel):
     torch = _torch()
     free = _PINNED_SCRATCH.setdefault(numel, [])

@@ -734,6 +734,7 @@ def run_b200(args):
         for name, fn in (("grid", bench_modes.grid_leg), ("lightcone", bench_modes.lightcone_leg)):
             gc.collect()
             torch.cuda.empty_cache()
+            b.runners.release_host_buffers()       # the previous leg's idle page-locked buffers (8 GB particle / grid results)
             barrier()
             state["leg"], state["deadline"] = name, time.monotonic() + args.leg_timeout
             if name == "grid":
