@@ -61,15 +61,20 @@ namespace {
 __global__ void k_ring_table(Hpx h, RingTabEntry *__restrict__ tab) {
     const i64 n = 4 * h.nside;
     for (i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (i64)gridDim.x * blockDim.x) {
-        RingTabEntry e = {0.0, 1.0, 0.0, 0.0};
+        RingTabEntry e = {0.0, 1.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
         if (r >= 1) {
-            i64 start, nr;
-            bool shifted;
+            i64 start, nr, s2, n2;
+            bool shifted, sh2;
             ring_theta_info(h, r, start, nr, e.theta, shifted);
             ring_z_sth(h, r, e.z, e.sth);
+            ring_info(h, r, start, nr, shifted);
+            e.two_over_nr = 2.0 / (double)nr;
+            e.nr_over_2pi = (double)nr * BFG_INV_TWOPI;
+            e.start = (double)start;
+            e.nr2s = (double)(2 * nr + (shifted ? 1 : 0));
             if (r + 1 < n) {
                 double th_next;
-                ring_theta_info(h, r + 1, start, nr, th_next, shifted);
+                ring_theta_info(h, r + 1, s2, n2, th_next, sh2);
                 e.inv_dth = 1.0 / (th_next - e.theta);
             }
         }

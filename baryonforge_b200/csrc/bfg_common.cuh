@@ -482,39 +482,73 @@ __device__ __forceinline__ void get_interpol(const Hpx &h, double theta, double 
 // i.e. ~1e-12 in a weight (the literal chain itself carries ~1e-11 through phi / dphi); a displaced direction within
 // round-off of a ring boundary may pick the neighbouring ring pair, where the bilinear weights are continuous.
 // Returns false (caller takes the literal path) next to the poles, for large displacements and for coarse maps.
-struct RingTabEntry { double theta, z, sth, inv_dth; };   // inv_dth = 1 / (theta of the next ring - theta)
+// One 64-byte entry per ring (two 32-byte loads): everything ring_info / ring_theta_info / ring_z_sth would derive, so the fast
+// path has no integer division, no ring-type branches and no trigonometry per ring.
+struct __align__(32) RingTabEntry {
+    double theta, z, sth, inv_dth;            // colatitude (literal ring formula), cos, sin, 1 / (theta of the next ring - theta)
+    double two_over_nr, nr_over_2pi, start, nr2s;   // 2 / nr, nr / 2 pi, first pixel, 2 nr + (1 if the ring is shifted by half a pixel)
+};
 
-// ring_pair with the reference's two divisions by dphi folded into ONE multiplication: tmp = phi nr / 2 pi - shift,
-// w1 = (phi - (i1 + shift) dphi) / dphi == tmp - i1 (identical in exact arithmetic; ~1e-12 apart in double, like everything
-// that goes through phi / dphi with up to 16384 pixels per ring)
-__device__ __forceinline__ void ring_pair_fast(i64 nr, bool shifted, i64 start, double phi, i64 &p0, i64 &p1, double &w1) {
-    const double tmp = fma(phi, (double)nr * BFG_INV_TWOPI, shifted ? -0.5 : 0.0);
+struct RingGeo { double two_over_nr, nr_over_2pi; i64 start, nr; bool shifted; };
+
+__device__ __forceinline__ double4 ldg_f64x4(const void *p) {     // 32 bytes through the read-only path (two 16-byte loads)
+    const double2 a = __ldg(reinterpret_cast<const double2 *>(p)), b = __ldg(reinterpret_cast<const double2 *>(p) + 1);
+    return make_double4(a.x, a.y, b.x, b.y);
+}
+
+__device__ __forceinline__ RingGeo ring_geo(const RingTabEntry *__restrict__ rt, i64 ring) {
+    const double4 b = ldg_f64x4(reinterpret_cast<const double4 *>(rt + ring) + 1);
+    RingGeo g;
+    g.two_over_nr = b.x; g.nr_over_2pi = b.y; g.start = (i64)b.z;
+    const i64 k = (i64)b.w;
+    g.nr = k >> 1; g.shifted = (k & 1) != 0;
+    return g;
+}
+
+// ring of a RING pixel without the 64-bit integer division of pix2ring's equatorial branch (~70 instructions): quotient by a
+// reciprocal multiplication (exact operands below 2^52) and one correction step
+__device__ __forceinline__ i64 pix2ring_only(const Hpx &h, i64 pix) {
+    if (pix < h.ncap) return (1 + isqrt_i64(1 + 2 * pix)) >> 1;
+    if (pix < h.npix - h.ncap) {
+        const i64 q = pix - h.ncap;
+        i64 t = (i64)((double)q * (1.0 / (double)h.nl4));
+        if (t * h.nl4 > q) --t;
+        else if ((t + 1) * h.nl4 <= q) ++t;
+        return t + h.nside;
+    }
+    const i64 q = h.npix - pix;
+    return 4 * h.nside - ((1 + isqrt_i64(2 * q - 1)) >> 1);
+}
+
+// in-ring neighbours of azimuth phi and the weight of the second one: the reference's two divisions by dphi folded into ONE
+// multiplication -- tmp = phi nr / 2 pi - shift, w1 = (phi - (i1 + shift) dphi) / dphi == tmp - i1 (identical in exact arithmetic;
+// ~1e-12 apart in double, like everything that goes through phi / dphi with up to 16384 pixels per ring)
+__device__ __forceinline__ void ring_pair_fast(const RingGeo &g, double phi, i64 &p0, i64 &p1, double &w1) {
+    const double tmp = fma(phi, g.nr_over_2pi, g.shifted ? -0.5 : 0.0);
     const double fl = floor(tmp);
     w1 = tmp - fl;
     i64 i1 = (i64)fl, i2 = i1 + 1;
-    if (i1 < 0) i1 += nr;
-    if (i2 >= nr) i2 -= nr;
-    p0 = start + i1;
-    p1 = start + i2;
+    if (i1 < 0) i1 += g.nr;
+    if (i2 >= g.nr) i2 -= g.nr;
+    p0 = g.start + i1;
+    p1 = g.start + i2;
 }
 
 __device__ __forceinline__ bool regrid_target_fast(const Hpx &h, const RingTabEntry *__restrict__ rt, i64 p, double ox,
                                                    double oy, double oz, i64 pix[4], double w[4]) {
-    i64 ring, ip, start, nr;
-    bool shifted;
-    pix2ring(h, p, ring, ip);
-    ring_info(h, ring, start, nr, shifted);
-    const double z = __ldg(&rt[ring].z), sth = __ldg(&rt[ring].sth);
+    const i64 ring = pix2ring_only(h, p);
+    const RingGeo gs = ring_geo(rt, ring);
+    const double4 as = ldg_f64x4(rt + ring);
+    const double z = as.y, sth = as.z;
     // azimuth of the source pixel in units of pi (exact half-integers over 2 nr)
-    const double a_pi = (ring < h.nside || ring >= 3 * h.nside) ? ((double)ip + 0.5) * (2.0 / (double)nr)
-                                                                : ((double)ip + (shifted ? 0.5 : 0.0)) * (2.0 / (double)nr);
+    const double a_pi = ((double)(p - gs.start) + (gs.shifted ? 0.5 : 0.0)) * gs.two_over_nr;
     double sn, cs;
     sincospi(a_pi, &sn, &cs);
     const double x = sth * cs, y = sth * sn;
     const double xn = x + ox, yn = y + oy, zn = z + oz;                       // HealpixRunner.py:357 (not re-normalised)
     const double cross = x * oy - y * ox, dot = fma(x, ox, fma(y, oy, sth * sth));
     if (!(dot > 0.0)) return false;
-    const double t = cross / dot;
+    const double t = cross * __drcp_rn(dot);
     if (!(fabs(t) <= 0.05)) return false;
     const double t2 = t * t;
     const double dphi_s = t * fma(t2, fma(t2, fma(t2, fma(t2, 1.0 / 9.0, -1.0 / 7.0), 0.2), -1.0 / 3.0), 1.0);
@@ -526,20 +560,16 @@ __device__ __forceinline__ bool regrid_target_fast(const Hpx &h, const RingTabEn
     const double zc = zn * inv_dn, rs = (rho2 * rsqrt(rho2)) * inv_dn;        // cos, sin of the displaced colatitude
     const i64 ir1 = ring_above(h, zc), ir2 = ir1 + 1;
     if (ir1 < 1 || ir2 > 4 * h.nside - 1) return false;                       // polar caps' first / last ring: literal path
-    const double z1 = __ldg(&rt[ir1].z), s1r = __ldg(&rt[ir1].sth), inv_dth = __ldg(&rt[ir1].inv_dth);
-    const double s = fma(rs, z1, -(zc * s1r));                                // sin(theta' - theta_1)
+    const double4 a1 = ldg_f64x4(rt + ir1);    // theta_1, cos, sin, 1 / (theta_2 - theta_1)
+    const double s = fma(rs, a1.y, -(zc * a1.z));                             // sin(theta' - theta_1)
     if (!(fabs(s) <= 0.05)) return false;
     const double s2 = s * s;
     const double dth = s * fma(s2, fma(s2, fma(s2, fma(s2, 35.0 / 1152.0, 15.0 / 336.0), 0.075), 1.0 / 6.0), 1.0);
-    const double wt = dth * inv_dth;
-    i64 sp, nr1;
-    bool sh;
+    const double wt = dth * a1.w;
     double w1;
-    ring_info(h, ir1, sp, nr1, sh);
-    ring_pair_fast(nr1, sh, sp, phi, pix[0], pix[1], w1);
+    ring_pair_fast(ring_geo(rt, ir1), phi, pix[0], pix[1], w1);
     w[0] = (1.0 - w1) * (1.0 - wt); w[1] = w1 * (1.0 - wt);
-    ring_info(h, ir2, sp, nr1, sh);
-    ring_pair_fast(nr1, sh, sp, phi, pix[2], pix[3], w1);
+    ring_pair_fast(ring_geo(rt, ir2), phi, pix[2], pix[3], w1);
     w[2] = (1.0 - w1) * wt; w[3] = w1 * wt;
     return true;
 }
