@@ -56,29 +56,12 @@ int get_log2_table(const double2 **d_tab) {
     return BFG_OK;
 }
 namespace {
-// ring r (1 .. 4 nside - 1): colatitude by the literal ring formula of get_interpol (ring_theta_info), z and sin(theta) by the
-// polar-cap accurate forms (ring_z_sth)
 __global__ void k_ring_table(Hpx h, RingTabEntry *__restrict__ tab) {
     const i64 n = 4 * h.nside;
     for (i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (i64)gridDim.x * blockDim.x) {
-        RingTabEntry e = {0.0, 1.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-        if (r >= 1) {
-            i64 start, nr, s2, n2;
-            bool shifted, sh2;
-            ring_theta_info(h, r, start, nr, e.theta, shifted);
-            ring_z_sth(h, r, e.z, e.sth);
-            ring_info(h, r, start, nr, shifted);
-            e.two_over_nr = 2.0 / (double)nr;
-            e.nr_over_2pi = (double)nr * BFG_INV_TWOPI;
-            e.start = (double)start;
-            e.nr2s = (double)(2 * nr + (shifted ? 1 : 0));
-            if (r + 1 < n) {
-                double th_next;
-                ring_theta_info(h, r + 1, s2, n2, th_next, sh2);
-                e.inv_dth = 1.0 / (th_next - e.theta);
-            }
-        }
-        tab[r] = e;
+        double e[8];
+        ring_table_entry(h, r, e);
+        tab[r] = RingTabEntry{e[0], e[1], e[2], e[3], e[4], e[5], e[6], e[7]};
     }
 }
 }  // namespace
@@ -112,6 +95,31 @@ int get_ring_table(long long nside, const RingTabEntry **d_tab, void *stream) {
     return BFG_OK;
 }
 }  // namespace bfg
+
+// test entry (pure host, no GPU): regrid_target_fast -- the source k_shell_regrid runs -- on the CPU, for the CPU parity suite.
+// h_off is [3][n] (component-major like the device offsets); h_out_pix / h_out_w are [n][4]; h_fast[i] = 0 where the function
+// declined (poles, large displacements) and the kernel would take the literal chain.
+extern "C" int bfg_test_regrid_target_host(int nside, int64_t n, const int64_t *h_pix, const double *h_off, int64_t *h_out_pix,
+                                           double *h_out_w, int *h_fast) {
+    BFG_REQUIRE(nside >= 1 && nside <= (1 << 24) && n >= 0, "bad argument");
+    BFG_REQUIRE(n == 0 || (h_pix && h_off && h_out_pix && h_out_w && h_fast), "null argument");
+    const Hpx h(nside);
+    std::vector<RingTabEntry> tab((size_t)(4 * h.nside + 1));
+    for (i64 r = 0; r < 4 * h.nside; ++r) {
+        double e[8];
+        ring_table_entry(h, r, e);
+        tab[(size_t)r] = RingTabEntry{e[0], e[1], e[2], e[3], e[4], e[5], e[6], e[7]};
+    }
+    for (int64_t i = 0; i < n; ++i) {
+        i64 pix[4] = {0, 0, 0, 0};
+        double w[4] = {0, 0, 0, 0};
+        BFG_REQUIRE(h_pix[i] >= 0 && h_pix[i] < h.npix, "pixel out of range");
+        const bool ok = regrid_target_fast(h, tab.data(), h_pix[i], h_off[i], h_off[n + i], h_off[2 * n + i], pix, w);
+        h_fast[i] = ok ? 1 : 0;
+        for (int k = 0; k < 4; ++k) { h_out_pix[4 * i + k] = ok ? pix[k] : -1; h_out_w[4 * i + k] = ok ? w[k] : 0.0; }
+    }
+    return BFG_OK;
+}
 
 // test entry: out[i] = fast_log2(x[i])
 __global__ void k_fast_log2(i64 n, const double2 *__restrict__ g_tab, const double *__restrict__ x, double *__restrict__ out) {

@@ -256,9 +256,9 @@ struct Hpx {
 #define BFG_INV_HALFPI 0.6366197723675813430755350534900574
 #define BFG_TWOTHIRD (2.0 / 3.0)
 
-__device__ __forceinline__ i64 isqrt_i64(i64 v) { return (i64)sqrt((double)v + 0.5); }  // exact for v < 2^50
+__host__ __device__ __forceinline__ i64 isqrt_i64(i64 v) { return (i64)sqrt((double)v + 0.5); }  // exact for v < 2^50
 
-__device__ __forceinline__ i64 ring_above(const Hpx &h, double z) {
+__host__ __device__ __forceinline__ i64 ring_above(const Hpx &h, double z) {
     double az = fabs(z);
     if (az <= BFG_TWOTHIRD) return (i64)((double)h.nside * (2.0 - 1.5 * z));
     i64 ir = (i64)((double)h.nside * sqrt(3.0 * (1.0 - az)));
@@ -273,7 +273,7 @@ __device__ __forceinline__ double ring2z(const Hpx &h, i64 ring) {
 }
 
 // first pixel, pixel count and half-pixel phase of a ring (1 <= ring <= 4 nside - 1)
-__device__ __forceinline__ void ring_info(const Hpx &h, i64 ring, i64 &start, i64 &nr, bool &shifted) {
+__host__ __device__ __forceinline__ void ring_info(const Hpx &h, i64 ring, i64 &start, i64 &nr, bool &shifted) {
     if (ring < h.nside) {
         shifted = true; nr = 4 * ring; start = 2 * ring * (ring - 1);
     } else if (ring < 3 * h.nside) {
@@ -405,7 +405,7 @@ __device__ __forceinline__ void disc_ring_span(const Hpx &h, const DiscRings &d,
 }
 
 // get_interpol: 4 neighbour pixels + bilinear weights of a direction (theta, phi)
-__device__ __forceinline__ void ring_theta_info(const Hpx &h, i64 ring, i64 &start, i64 &nr, double &theta, bool &shifted) {
+__host__ __device__ __forceinline__ void ring_theta_info(const Hpx &h, i64 ring, i64 &start, i64 &nr, double &theta, bool &shifted) {
     i64 nring = (ring > 2 * h.nside) ? 4 * h.nside - ring : ring;
     if (nring < h.nside) {
         double tmp = (double)(nring * nring) * h.fact2;
@@ -491,12 +491,49 @@ struct __align__(32) RingTabEntry {
 
 struct RingGeo { double two_over_nr, nr_over_2pi; i64 start, nr; bool shifted; };
 
-__device__ __forceinline__ double4 ldg_f64x4(const void *p) {     // 32 bytes through the read-only path (two 16-byte loads)
+// (the re-binning target below is __host__ __device__: bfg_test_regrid_target_host runs the SAME source on the CPU, where the CPU
+// suite holds it against the oracle; the two device-only intrinsics have host stand-ins here)
+__host__ __device__ __forceinline__ double4 ldg_f64x4(const void *p) {     // 32 bytes through the read-only path (two 16-byte loads)
+#ifdef __CUDA_ARCH__
     const double2 a = __ldg(reinterpret_cast<const double2 *>(p)), b = __ldg(reinterpret_cast<const double2 *>(p) + 1);
     return make_double4(a.x, a.y, b.x, b.y);
+#else
+    const double *q = reinterpret_cast<const double *>(p);
+    return make_double4(q[0], q[1], q[2], q[3]);
+#endif
 }
 
-__device__ __forceinline__ RingGeo ring_geo(const RingTabEntry *__restrict__ rt, i64 ring) {
+__host__ __device__ __forceinline__ double rcp_rn(double x) {
+#ifdef __CUDA_ARCH__
+    return __drcp_rn(x);
+#else
+    return 1.0 / x;
+#endif
+}
+
+// One entry of the per-nside ring table (k_ring_table on the device, bfg_test_regrid_target_host on the CPU)
+struct RingTabEntry;
+__host__ __device__ __forceinline__ void ring_table_entry(const Hpx &h, i64 r, double out[8]) {
+    for (int k = 0; k < 8; ++k) out[k] = 0.0;
+    out[1] = 1.0;
+    if (r < 1 || r >= 4 * h.nside) return;
+    i64 start, nr, s2, n2;
+    bool shifted, sh2;
+    ring_theta_info(h, r, start, nr, out[0], shifted);        // colatitude by the literal ring formula of get_interpol
+    ring_z_sth(h, r, out[1], out[2]);                         // z and sin(theta) by the polar-cap accurate forms
+    ring_info(h, r, start, nr, shifted);
+    out[4] = 2.0 / (double)nr;
+    out[5] = (double)nr * BFG_INV_TWOPI;
+    out[6] = (double)start;
+    out[7] = (double)(2 * nr + (shifted ? 1 : 0));
+    if (r + 1 < 4 * h.nside) {
+        double th_next;
+        ring_theta_info(h, r + 1, s2, n2, th_next, sh2);
+        out[3] = 1.0 / (th_next - out[0]);
+    }
+}
+
+__host__ __device__ __forceinline__ RingGeo ring_geo(const RingTabEntry *__restrict__ rt, i64 ring) {
     const double4 b = ldg_f64x4(reinterpret_cast<const double4 *>(rt + ring) + 1);
     RingGeo g;
     g.two_over_nr = b.x; g.nr_over_2pi = b.y; g.start = (i64)b.z;
@@ -507,7 +544,7 @@ __device__ __forceinline__ RingGeo ring_geo(const RingTabEntry *__restrict__ rt,
 
 // ring of a RING pixel without the 64-bit integer division of pix2ring's equatorial branch (~70 instructions): quotient by a
 // reciprocal multiplication (exact operands below 2^52) and one correction step
-__device__ __forceinline__ i64 pix2ring_only(const Hpx &h, i64 pix) {
+__host__ __device__ __forceinline__ i64 pix2ring_only(const Hpx &h, i64 pix) {
     if (pix < h.ncap) return (1 + isqrt_i64(1 + 2 * pix)) >> 1;
     if (pix < h.npix - h.ncap) {
         const i64 q = pix - h.ncap;
@@ -523,7 +560,7 @@ __device__ __forceinline__ i64 pix2ring_only(const Hpx &h, i64 pix) {
 // in-ring neighbours of azimuth phi and the weight of the second one: the reference's two divisions by dphi folded into ONE
 // multiplication -- tmp = phi nr / 2 pi - shift, w1 = (phi - (i1 + shift) dphi) / dphi == tmp - i1 (identical in exact arithmetic;
 // ~1e-12 apart in double, like everything that goes through phi / dphi with up to 16384 pixels per ring)
-__device__ __forceinline__ void ring_pair_fast(const RingGeo &g, double phi, i64 &p0, i64 &p1, double &w1) {
+__host__ __device__ __forceinline__ void ring_pair_fast(const RingGeo &g, double phi, i64 &p0, i64 &p1, double &w1) {
     const double tmp = fma(phi, g.nr_over_2pi, g.shifted ? -0.5 : 0.0);
     const double fl = floor(tmp);
     w1 = tmp - fl;
@@ -534,7 +571,7 @@ __device__ __forceinline__ void ring_pair_fast(const RingGeo &g, double phi, i64
     p1 = g.start + i2;
 }
 
-__device__ __forceinline__ bool regrid_target_fast(const Hpx &h, const RingTabEntry *__restrict__ rt, i64 p, double ox,
+__host__ __device__ __forceinline__ bool regrid_target_fast(const Hpx &h, const RingTabEntry *__restrict__ rt, i64 p, double ox,
                                                    double oy, double oz, i64 pix[4], double w[4]) {
     const i64 ring = pix2ring_only(h, p);
     const RingGeo gs = ring_geo(rt, ring);
@@ -548,7 +585,7 @@ __device__ __forceinline__ bool regrid_target_fast(const Hpx &h, const RingTabEn
     const double xn = x + ox, yn = y + oy, zn = z + oz;                       // HealpixRunner.py:357 (not re-normalised)
     const double cross = x * oy - y * ox, dot = fma(x, ox, fma(y, oy, sth * sth));
     if (!(dot > 0.0)) return false;
-    const double t = cross * __drcp_rn(dot);
+    const double t = cross * rcp_rn(dot);
     if (!(fabs(t) <= 0.05)) return false;
     const double t2 = t * t;
     const double dphi_s = t * fma(t2, fma(t2, fma(t2, fma(t2, 1.0 / 9.0, -1.0 / 7.0), 0.2), -1.0 / 3.0), 1.0);

@@ -366,6 +366,11 @@ int bfg_halo_sort_owned(int nside, int64_t pix_lo, int64_t pix_hi, int64_t n_hal
 /* ---- small utilities ------------------------------------------------------------------------------ */
 /* *d_out (one double) = sum of n doubles (mass-conservation assert, HealpixRunner.py:368-370). */
 int bfg_sum_f64(const double *d_x, int64_t n, double *d_out, void *stream);
+/* Test entry, pure host (no GPU): the re-binning target the shell re-binning kernels compute per displaced pixel
+ * (HealpixRunner.py:357-361: pix2vec + offset -> vec2ang -> get_interp_weights), i.e. the device source regrid_target_fast compiled
+ * for the CPU.  h_off [3][n]; outputs [n][4]; h_fast[i] = 0 where the function declines and the kernel takes the literal chain. */
+int bfg_test_regrid_target_host(int nside, int64_t n, const int64_t *h_pix, const double *h_off, int64_t *h_out_pix,
+                                double *h_out_w, int *h_fast);
 /* Unit-test entry for the table-driven log2 used inside the pixel loops: d_out[i] = log2(d_x[i]). */
 int bfg_test_fast_log2(int64_t n, const double *d_x, double *d_out, void *stream);
 /* out[i][c] = in[c][i] : component-major offsets -> the reference's (n, ncomp) layout, for tests. */
