@@ -121,6 +121,59 @@ extern "C" int bfg_test_regrid_target_host(int nside, int64_t n, const int64_t *
     return BFG_OK;
 }
 
+// test entries (pure host, no GPU): the HEALPix device functions of bfg_common.cuh -- the SAME source the kernels inline --
+// compiled for the CPU, so that the CPU suite can hold them against the oracle over many discs / directions / NSIDE values.
+// what = 0: query_disc (a[0] = theta, a[1] = phi, a[2] = radius; out_i [cap] pixels, out_i[cap] = count)
+//        1: pix2vec    (idx [n] pixels; out_d [n][3])
+//        2: get_interpol / hp.get_interp_weights (a = theta [n], b = phi [n]; out_i [n][4], out_d [n][4])
+//        3: ang2pix    (a = theta [n], b = phi [n]; out_i [n])
+//        4: ring2nest, 5: nest2ring (idx [n]; out_i [n])
+extern "C" int bfg_test_healpix_host(int what, int nside, int64_t n, const int64_t *h_idx, const double *h_a, const double *h_b,
+                                     int64_t cap, int64_t *h_out_i, double *h_out_d) {
+    BFG_REQUIRE(nside >= 1 && nside <= (1 << 24) && n >= 0, "bad argument");
+    const Hpx h(nside);
+    if (what == 0) {
+        BFG_REQUIRE(h_a && h_out_i && cap >= 0, "null argument");
+        const DiscRings d = disc_rings(h, h_a[0], h_a[1], h_a[2]);
+        i64 cnt_all = 0;
+        for (i64 iz = d.ra; iz <= d.rb; ++iz) {
+            i64 start, nr, ip_lo, cnt;
+            bool sh;
+            disc_ring_span(h, d, iz, start, nr, sh, ip_lo, cnt);
+            for (i64 i = 0; i < cnt; ++i) {
+                i64 ip = ip_lo + i;
+                if (ip >= nr) ip -= nr;
+                if (cnt_all < cap) h_out_i[cnt_all] = start + ip;
+                ++cnt_all;
+            }
+        }
+        h_out_i[cap] = cnt_all;
+        return BFG_OK;
+    }
+    for (int64_t i = 0; i < n; ++i) {
+        if (what == 1) {
+            BFG_REQUIRE(h_idx && h_out_d && h_idx[i] >= 0 && h_idx[i] < h.npix, "bad pixel");
+            pix2vec(h, h_idx[i], h_out_d[3 * i], h_out_d[3 * i + 1], h_out_d[3 * i + 2]);
+        } else if (what == 2) {
+            BFG_REQUIRE(h_a && h_b && h_out_i && h_out_d, "null argument");
+            i64 pix[4];
+            double w[4];
+            get_interpol(h, h_a[i], h_b[i], pix, w);
+            for (int k = 0; k < 4; ++k) { h_out_i[4 * i + k] = pix[k]; h_out_d[4 * i + k] = w[k]; }
+        } else if (what == 3) {
+            BFG_REQUIRE(h_a && h_b && h_out_i, "null argument");
+            h_out_i[i] = ang2pix_ring(h, h_a[i], h_b[i]);
+        } else if (what == 4 || what == 5) {
+            BFG_REQUIRE(h_idx && h_out_i && h_idx[i] >= 0 && h_idx[i] < h.npix, "bad pixel");
+            BFG_REQUIRE((nside & (nside - 1)) == 0, "NESTED needs a power-of-two nside");
+            h_out_i[i] = (what == 4) ? ring2nest(h, h_idx[i]) : nest2ring(h, h_idx[i]);
+        } else {
+            BFG_REQUIRE(false, "what must be 0..5");
+        }
+    }
+    return BFG_OK;
+}
+
 // test entry: out[i] = fast_log2(x[i])
 __global__ void k_fast_log2(i64 n, const double2 *__restrict__ g_tab, const double *__restrict__ x, double *__restrict__ out) {
     __shared__ double2 tab[BFG_LOG2_TAB];

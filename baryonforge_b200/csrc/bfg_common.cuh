@@ -265,7 +265,7 @@ __host__ __device__ __forceinline__ i64 ring_above(const Hpx &h, double z) {
     return (z > 0) ? ir : 4 * h.nside - ir - 1;
 }
 
-__device__ __forceinline__ double ring2z(const Hpx &h, i64 ring) {
+__host__ __device__ __forceinline__ double ring2z(const Hpx &h, i64 ring) {
     if (ring < h.nside) return 1.0 - (double)(ring * ring) * h.fact2;
     if (ring <= 3 * h.nside) return (double)(2 * h.nside - ring) * h.fact1;
     i64 q = 4 * h.nside - ring;
@@ -301,14 +301,14 @@ __host__ __device__ __forceinline__ void ring_z_sth(const Hpx &h, i64 ring, doub
 }
 
 // azimuth of pixel `ip` (0-based within its ring)
-__device__ __forceinline__ double ring_phi(const Hpx &h, i64 ring, i64 ip, bool shifted) {
+__host__ __device__ __forceinline__ double ring_phi(const Hpx &h, i64 ring, i64 ip, bool shifted) {
     if (ring < h.nside) return ((double)(ip + 1) - 0.5) * BFG_HALFPI / (double)ring;
     if (ring < 3 * h.nside) return ((double)(ip + 1) - (shifted ? 0.5 : 1.0)) * BFG_PI * 0.75 * h.fact1;
     return ((double)(ip + 1) - 0.5) * BFG_HALFPI / (double)(4 * h.nside - ring);
 }
 
 // ring number (1-based from the north pole) and in-ring index of a RING pixel
-__device__ __forceinline__ void pix2ring(const Hpx &h, i64 pix, i64 &ring, i64 &ip) {
+__host__ __device__ __forceinline__ void pix2ring(const Hpx &h, i64 pix, i64 &ring, i64 &ip) {
     if (pix < h.ncap) {
         ring = (1 + isqrt_i64(1 + 2 * pix)) >> 1;
         ip = pix - 2 * ring * (ring - 1);
@@ -325,7 +325,7 @@ __device__ __forceinline__ void pix2ring(const Hpx &h, i64 pix, i64 &ring, i64 &
     }
 }
 
-__device__ __forceinline__ void pix2vec(const Hpx &h, i64 pix, double &x, double &y, double &z) {
+__host__ __device__ __forceinline__ void pix2vec(const Hpx &h, i64 pix, double &x, double &y, double &z) {
     i64 ring, ip, start, nr;
     bool shifted;
     pix2ring(h, pix, ring, ip);
@@ -346,7 +346,7 @@ struct DiscRings {
     bool all_sky;
 };
 
-__device__ __forceinline__ DiscRings disc_rings(const Hpx &h, double theta, double phi, double radius) {
+__host__ __device__ __forceinline__ DiscRings disc_rings(const Hpx &h, double theta, double phi, double radius) {
     DiscRings d;
     d.phi0 = phi;
     d.all_sky = false;
@@ -381,7 +381,7 @@ __device__ __forceinline__ bool disc_touches_range(const Hpx &h, const DiscRings
 }
 
 // Pixels of ring `iz` inside the disc: in-ring indices (ip_lo + i) mod nr for i in [0, cnt).
-__device__ __forceinline__ void disc_ring_span(const Hpx &h, const DiscRings &d, i64 iz, i64 &start, i64 &nr,
+__host__ __device__ __forceinline__ void disc_ring_span(const Hpx &h, const DiscRings &d, i64 iz, i64 &start, i64 &nr,
                                                bool &shifted, i64 &ip_lo, i64 &cnt) {
     ring_info(h, iz, start, nr, shifted);
     if (iz < d.irmin || iz > d.irmax) { ip_lo = 0; cnt = nr; return; }
@@ -418,7 +418,7 @@ __host__ __device__ __forceinline__ void ring_theta_info(const Hpx &h, i64 ring,
     if (nring != ring) { theta = BFG_PI - theta; start = h.npix - start - nr; }
 }
 
-__device__ __forceinline__ void ring_pair(i64 nr, bool shifted, i64 start, double phi, i64 &p0, i64 &p1, double &w1) {
+__host__ __device__ __forceinline__ void ring_pair(i64 nr, bool shifted, i64 start, double phi, i64 &p0, i64 &p1, double &w1) {
     double dphi = BFG_TWOPI / (double)nr;
     double sh = shifted ? 0.5 : 0.0;
     double tmp = phi / dphi - sh;
@@ -431,7 +431,7 @@ __device__ __forceinline__ void ring_pair(i64 nr, bool shifted, i64 start, doubl
     p1 = start + i2;
 }
 
-__device__ __forceinline__ void get_interpol(const Hpx &h, double theta, double phi, i64 pix[4], double w[4]) {
+__host__ __device__ __forceinline__ void get_interpol(const Hpx &h, double theta, double phi, i64 pix[4], double w[4]) {
     double z = cos(theta);
     i64 ir1 = ring_above(h, z), ir2 = ir1 + 1;
     double th1 = 0, th2 = 0, w1;
@@ -631,13 +631,13 @@ __device__ __forceinline__ void regrid_target(const Hpx &h, const RingTabEntry *
     if (rt == nullptr || !regrid_target_fast(h, rt, p, ox, oy, oz, pix, w)) regrid_target_literal(h, p, ox, oy, oz, pix, w);
 }
 
-__device__ __forceinline__ double fmodulo(double v1, double v2) {
+__host__ __device__ __forceinline__ double fmodulo(double v1, double v2) {
     if (v1 >= 0) return (v1 < v2) ? v1 : fmod(v1, v2);
     double tmp = fmod(v1, v2) + v2;
     return (tmp == v2) ? 0.0 : tmp;
 }
 
-__device__ __forceinline__ i64 ang2pix_ring(const Hpx &h, double theta, double phi) {
+__host__ __device__ __forceinline__ i64 ang2pix_ring(const Hpx &h, double theta, double phi) {
     double z = cos(theta);
     bool have_sth = (theta < 0.01) || (theta > 3.14159 - 0.01);
     double sth = have_sth ? sin(theta) : 0.0;
@@ -663,7 +663,7 @@ __device__ __forceinline__ i64 ang2pix_ring(const Hpx &h, double theta, double p
 
 // RING <-> NEST (T_Healpix_Base ring2xyf / xyf2ring / xyf2nest / nest2xyf; nside a power of two).  The runners work on
 // RING maps like the reference (utils/io.py:302); NEST exists for callers that hold nested maps or shard by base face.
-__device__ __forceinline__ i64 spread_bits(i64 v) {      // bit k -> bit 2k (v < 2^31)
+__host__ __device__ __forceinline__ i64 spread_bits(i64 v) {      // bit k -> bit 2k (v < 2^31)
     v = (v | (v << 16)) & 0x0000ffff0000ffffLL;
     v = (v | (v << 8)) & 0x00ff00ff00ff00ffLL;
     v = (v | (v << 4)) & 0x0f0f0f0f0f0f0f0fLL;
@@ -671,7 +671,7 @@ __device__ __forceinline__ i64 spread_bits(i64 v) {      // bit k -> bit 2k (v <
     v = (v | (v << 1)) & 0x5555555555555555LL;
     return v;
 }
-__device__ __forceinline__ i64 compress_bits(i64 v) {    // bit 2k -> bit k
+__host__ __device__ __forceinline__ i64 compress_bits(i64 v) {    // bit 2k -> bit k
     v &= 0x5555555555555555LL;
     v = (v | (v >> 1)) & 0x3333333333333333LL;
     v = (v | (v >> 2)) & 0x0f0f0f0f0f0f0f0fLL;
@@ -681,7 +681,7 @@ __device__ __forceinline__ i64 compress_bits(i64 v) {    // bit 2k -> bit k
     return v;
 }
 
-__device__ __forceinline__ i64 ring2nest(const Hpx &h, i64 pix) {
+__host__ __device__ __forceinline__ i64 ring2nest(const Hpx &h, i64 pix) {
     const int jrll[12] = {2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4}, jpll[12] = {1, 3, 5, 7, 0, 2, 4, 6, 1, 3, 5, 7};
     const i64 n = h.nside, nl2 = 2 * n;
     i64 iring, iphi, kshift, nr;
@@ -714,7 +714,7 @@ __device__ __forceinline__ i64 ring2nest(const Hpx &h, i64 pix) {
     return (i64)face * n * n + spread_bits(ix) + (spread_bits(iy) << 1);
 }
 
-__device__ __forceinline__ i64 nest2ring(const Hpx &h, i64 pix) {
+__host__ __device__ __forceinline__ i64 nest2ring(const Hpx &h, i64 pix) {
     const int jrll[12] = {2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4}, jpll[12] = {1, 3, 5, 7, 0, 2, 4, 6, 1, 3, 5, 7};
     const i64 n = h.nside, npface = n * n;
     const int face = (int)(pix / npface);

@@ -371,6 +371,12 @@ int bfg_sum_f64(const double *d_x, int64_t n, double *d_out, void *stream);
  * for the CPU.  h_off [3][n]; outputs [n][4]; h_fast[i] = 0 where the function declines and the kernel takes the literal chain. */
 int bfg_test_regrid_target_host(int nside, int64_t n, const int64_t *h_pix, const double *h_off, int64_t *h_out_pix,
                                 double *h_out_w, int *h_fast);
+/* Test entry, pure host (no GPU): the HEALPix RING device functions (csrc/bfg_common.cuh: query_disc rings and spans, pix2vec,
+ * get_interpol, ang2pix, ring2nest / nest2ring -- healpy's C++ T_Healpix_Base algorithms) compiled for the CPU.
+ * what = 0 query_disc (h_a = {theta, phi, radius}; h_out_i [cap + 1], last = count), 1 pix2vec (h_idx; h_out_d [n][3]),
+ * 2 get_interpol (h_a = theta, h_b = phi; h_out_i, h_out_d [n][4]), 3 ang2pix (h_a, h_b; h_out_i), 4 ring2nest, 5 nest2ring. */
+int bfg_test_healpix_host(int what, int nside, int64_t n, const int64_t *h_idx, const double *h_a, const double *h_b, int64_t cap,
+                          int64_t *h_out_i, double *h_out_d);
 /* Unit-test entry for the table-driven log2 used inside the pixel loops: d_out[i] = log2(d_x[i]). */
 int bfg_test_fast_log2(int64_t n, const double *d_x, double *d_out, void *stream);
 /* out[i][c] = in[c][i] : component-major offsets -> the reference's (n, ncomp) layout, for tests. */
