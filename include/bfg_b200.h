@@ -371,6 +371,11 @@ int bfg_sum_f64(const double *d_x, int64_t n, double *d_out, void *stream);
  * for the CPU.  h_off [3][n]; outputs [n][4]; h_fast[i] = 0 where the function declines and the kernel takes the literal chain. */
 int bfg_test_regrid_target_host(int nside, int64_t n, const int64_t *h_pix, const double *h_off, int64_t *h_out_pix,
                                 double *h_out_w, int *h_fast);
+/* Test entry, pure host (no GPU): the per-halo scalar prep of bfg_shell_records (same source, same argument meaning) on HOST
+ * buffers. */
+int bfg_test_shell_records_host(int64_t n_halo, const double *h_cols, int paint, double eps_run, double eps_model, double pixarea,
+                                int n_DA, const double *h_DA_x, const double *h_DA_c, int n_g, const double *h_g_x,
+                                const double *h_g_run_c, const double *h_g_mod_c, double *h_halos, double *h_aux);
 /* Test entry, pure host (no GPU): the HEALPix RING device functions (csrc/bfg_common.cuh: query_disc rings and spans, pix2vec,
  * get_interpol, ang2pix, ring2nest / nest2ring -- healpy's C++ T_Healpix_Base algorithms) compiled for the CPU.
  * what = 0 query_disc (h_a = {theta, phi, radius}; h_out_i [cap + 1], last = count), 1 pix2vec (h_idx; h_out_d [n][3]),
