@@ -23,14 +23,19 @@ __device__ __forceinline__ HaloBox load_box(const double *__restrict__ H) {
 }
 
 // np.linspace(-Ns/2, Ns/2, Ns)[i] * res, same operation order as numpy (arange*step + start, last = stop)
-__device__ __forceinline__ double cut_coord(int i, int ns, double res) {
+// (__host__ __device__: bfg_test_index_helpers_host runs the same source on the CPU against np.linspace / pick_indices)
+__host__ __device__ __forceinline__ double cut_coord(int i, int ns, double res) {
     double start = -0.5 * (double)ns, stop = 0.5 * (double)ns;
     double step = (stop - start) / (double)(ns - 1);
+#ifdef __CUDA_ARCH__
     double y = (i == ns - 1) ? stop : __dadd_rn(__dmul_rn((double)i, step), start);
+#else
+    double y = (i == ns - 1) ? stop : ((double)i * step) + start;     // x86-64 baseline: no FMA contraction
+#endif
     return y * res;
 }
 
-__device__ __forceinline__ int wrap_idx(int c, int N) {   // pick_indices, Map2DRunner.py:400-429
+__host__ __device__ __forceinline__ int wrap_idx(int c, int N) {   // pick_indices, Map2DRunner.py:400-429
     if (c < 0) c += N;
     if (c >= N) c -= N;
     return c;

@@ -16,6 +16,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include "bfg_common.cuh"
+#include "grid_common.cuh"
 
 using namespace bfg;
 
@@ -23,7 +24,7 @@ namespace {
 
 constexpr int SNAP_THREADS = 128;
 
-__device__ __forceinline__ int cell_of(double x, double L, int nc) {
+__host__ __device__ __forceinline__ int cell_of(double x, double L, int nc) {
     int c = (int)floor(x / L * (double)nc);
     return min(max(c, 0), nc - 1);
 }
@@ -252,7 +253,7 @@ k_snap_halos(TableView T, double L, int nc, const double *__restrict__ xs, const
     }
 }
 
-__device__ __forceinline__ double wrap_once(double q, double L) {   // SnapshotRunner.py:272-273
+__host__ __device__ __forceinline__ double wrap_once(double q, double L) {   // SnapshotRunner.py:272-273
     if (q > L) q -= L;
     if (q < 0) q += L;
     return q;
@@ -297,7 +298,7 @@ __global__ void k_snap_apply_records(i64 n, const double *__restrict__ xs, const
 }
 
 // np.histogramdd bin of x on edges = np.linspace(0, L, N+1): searchsorted(side='right') - 1, x == L -> last bin
-__device__ __forceinline__ i64 ngp_bin(double x, double L, i64 N, double step) {
+__host__ __device__ __forceinline__ i64 ngp_bin(double x, double L, i64 N, double step) {
     if (!(x >= 0.0) || !(x <= L)) return -1;
     if (x == L) return N - 1;
     i64 i = (i64)(x / step);
@@ -538,5 +539,34 @@ extern "C" int bfg_snap_apply_deposit(int ndim, int64_t n_part, const double *d_
         k_snap_apply_deposit<2><<<blocks_for(n_part, 256), 256, 0, st>>>(n_part, d_xs, d_ys, d_zs, d_tot, (const i64 *)d_order,
                                                                          d_mass, mass_const, L, n_grid, d_grid);
     BFG_CUDA_OK(cudaGetLastError());
+    return BFG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------- host test entry
+// Pure host, no GPU: the index helpers the grid and particle kernels inline, on the CPU.
+//   what = 0  NGP cell of a coordinate (ngp_bin: np.histogramdd on np.linspace(0, L, N + 1) edges, utils/io.py:629-677): h_x [n] -> h_out_i [n]
+//   what = 1  wrap_once (SnapshotRunner.py:272-273): h_x [n] -> h_out_d [n]
+//   what = 2  cell-list cell of a coordinate (cell_of): h_x [n], N = cells per axis -> h_out_i [n]
+//   what = 3  cutout of a halo along one axis (Map2DRunner.py:400-429, :500-528): n = Nsize, L = res, centre = (int)h_x[0], N = cells per
+//             axis -> h_out_d [n] = np.linspace(-n/2, n/2, n) * res, h_out_i [n] = pick_indices(centre, n / 2, N)
+extern "C" int bfg_test_index_helpers_host(int what, int64_t n, const double *h_x, double L, int64_t N, int64_t *h_out_i,
+                                           double *h_out_d) {
+    BFG_REQUIRE(n >= 0 && N >= 1 && what >= 0 && what <= 3, "bad argument");
+    BFG_REQUIRE(n == 0 || h_x, "null argument");
+    if (what == 3) {
+        BFG_REQUIRE(n >= 2 && h_out_i && h_out_d && N <= 2147483647LL, "bad cutout");
+        const int ns = (int)n, cen = (int)h_x[0];
+        for (int i = 0; i < ns; ++i) {
+            h_out_d[i] = cut_coord(i, ns, L);
+            h_out_i[i] = wrap_idx(cen - ns / 2 + i, (int)N);
+        }
+        return BFG_OK;
+    }
+    const double step = L / (double)N;
+    for (int64_t i = 0; i < n; ++i) {
+        if (what == 0) h_out_i[i] = ngp_bin(h_x[i], L, N, step);
+        else if (what == 1) h_out_d[i] = wrap_once(h_x[i], L);
+        else h_out_i[i] = cell_of(h_x[i], L, (int)N);
+    }
     return BFG_OK;
 }

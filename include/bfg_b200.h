@@ -376,6 +376,10 @@ int bfg_test_regrid_target_host(int nside, int64_t n, const int64_t *h_pix, cons
 int bfg_test_shell_records_host(int64_t n_halo, const double *h_cols, int paint, double eps_run, double eps_model, double pixarea,
                                 int n_DA, const double *h_DA_x, const double *h_DA_c, int n_g, const double *h_g_x,
                                 const double *h_g_run_c, const double *h_g_mod_c, double *h_halos, double *h_aux);
+/* Test entry, pure host (no GPU): index helpers of the grid and particle kernels on the CPU.  what = 0 NGP cell (np.histogramdd edges,
+ * utils/io.py:629-677), 1 wrap_once (SnapshotRunner.py:272-273), 2 cell-list cell, 3 cutout coordinates + periodic indices of one axis
+ * (n = Nsize, L = res, h_x[0] = centre cell; Map2DRunner.py:400-429, :500-528). */
+int bfg_test_index_helpers_host(int what, int64_t n, const double *h_x, double L, int64_t N, int64_t *h_out_i, double *h_out_d);
 /* Test entry, pure host (no GPU): the HEALPix RING device functions (csrc/bfg_common.cuh: query_disc rings and spans, pix2vec,
  * get_interpol, ang2pix, ring2nest / nest2ring -- healpy's C++ T_Healpix_Base algorithms) compiled for the CPU.
  * what = 0 query_disc (h_a = {theta, phi, radius}; h_out_i [cap + 1], last = count), 1 pix2vec (h_idx; h_out_d [n][3]),

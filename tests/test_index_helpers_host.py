@@ -1,0 +1,71 @@
+"""
+CPU: the index helpers the grid and particle kernels inline (ngp_bin, wrap_once, cell_of in csrc/snapshot_kernels.cu; cut_coord,
+wrap_idx in csrc/grid_common.cuh), compiled for the HOST (bfg_test_index_helpers_host), against numpy and the oracle port:
+NGP cell assignments and cutout index sets bit-exact, cutout coordinates bit-identical to np.linspace.
+tools/sass_fingerprint.py shows no kernel changed when these functions became host-compilable.
+"""
+import numpy as np
+
+from oracle import runners_port as rp
+
+
+def helper(what, x, L, N, n=None):
+    from baryonforge_b200 import _lib
+    x = np.ascontiguousarray(np.atleast_1d(x), dtype=np.float64)
+    n = x.size if n is None else int(n)
+    out_i = np.zeros(max(n, 1), dtype=np.int64)
+    out_d = np.zeros(max(n, 1), dtype=np.float64)
+    _lib.check(_lib.lib().bfg_test_index_helpers_host(int(what), n, x.ctypes.data, float(L), int(N), out_i.ctypes.data,
+                                                      out_d.ctypes.data))
+    return out_i[:n], out_d[:n]
+
+
+def test_ngp_cell_is_histogramdd_bin_for_bin():
+    """ParticleSnapshot.make_map == np.histogramdd on np.linspace(0, L, N + 1) (utils/io.py:629-677): interior edges go up,
+    x == L goes to the last bin, anything outside is dropped (-1)."""
+    rng = np.random.default_rng(3)
+    for L, N in ((205.0, 512), (1000.0, 1024), (1.0, 7), (62.5, 3), (33.3, 1000)):
+        edges = np.linspace(0, L, N + 1)
+        x = np.concatenate([rng.uniform(0, L, 200000), edges, np.nextafter(edges, -np.inf), np.nextafter(edges, np.inf),
+                            [-1e-300, -1.0, L * (1 + 1e-15), 2 * L, np.nan, np.inf, -np.inf]])
+        got, _ = helper(0, x, L, N)
+        want = np.searchsorted(edges, x, side='right') - 1
+        want = np.where(x == L, N - 1, want)
+        want = np.where((x >= 0) & (x <= L), want, -1)
+        assert np.array_equal(got, want), (L, N, np.flatnonzero(got != want)[:5])
+        # and through np.histogramdd itself (1-D marginal of what make_map calls)
+        ok = got >= 0
+        h = np.histogramdd(x[ok][:, None], bins=(edges,))[0]
+        assert np.array_equal(h, np.bincount(got[ok], minlength=N))
+
+
+def test_wrap_once_and_cell_of():
+    rng = np.random.default_rng(4)
+    L = 205.0
+    x = np.concatenate([rng.uniform(-L, 2 * L, 100000), [0.0, L, -0.0, np.nextafter(L, np.inf), np.nextafter(0.0, -np.inf)]])
+    _, got = helper(1, x, L, 1)
+    want = x.copy()                                                       # SnapshotRunner.py:272-273: one wrap, > L then < 0
+    want = np.where(want > L, want - L, want)
+    want = np.where(want < 0, want + L, want)
+    assert np.array_equal(got, want)
+    xin = np.concatenate([rng.uniform(0, L, 100000), [0.0, L, np.nextafter(L, -np.inf)]])
+    for nc in (1, 41, 215, 1024):
+        got_c, _ = helper(2, xin, L, nc)
+        want_c = np.clip(np.floor(xin / L * nc).astype(np.int64), 0, nc - 1)
+        assert np.array_equal(got_c, want_c)
+
+
+def test_cutout_coordinates_and_indices_are_numpy_bit_for_bit():
+    """Map2DRunner.py:500-528: x = np.linspace(-Nsize/2, Nsize/2, Nsize) * res ; pick_indices(centre, Nsize // 2, Npix)."""
+    rng = np.random.default_rng(5)
+    for ns in list(range(2, 130, 2)) + [256, 510, 512]:
+        for res in (1.0, 0.9765625, 0.3, 1000.0 / 1024, float(rng.uniform(0.01, 5))):
+            N = max(2 * ns, 64)
+            cen = int(rng.integers(0, N))
+            idx, coord = helper(3, [float(cen)], res, N, n=ns)
+            assert np.array_equal(coord, np.linspace(-ns / 2, ns / 2, ns) * res), (ns, res)
+            assert np.array_equal(idx, rp._pick_indices(cen, ns // 2, N)), (ns, cen, N)
+    # centres at the box edge: the periodic wrap on both sides
+    for cen in (0, 1, 63):
+        idx, _ = helper(3, [float(cen)], 1.0, 64, n=32)
+        assert np.array_equal(idx, rp._pick_indices(cen, 16, 64)) and idx.min() >= 0 and idx.max() < 64
