@@ -5,6 +5,7 @@
 #include <cmath>
 #include <algorithm>
 #include <cstdlib>
+#include <limits>
 #include <mutex>
 #include "bfg_common.cuh"
 
@@ -219,6 +220,18 @@ extern "C" int bfg_device_info(int device, int *sm_count, int64_t *mem_total, in
 }
 
 // ------------------------------------------------------------------------------------------------ tables
+// radial axis: uniform in ln r (np.geomspace -> np.log) unlocks the closed-form cell index
+static void describe_radial_axis(const double *ar, int64_t nr, TableView &view) {
+    double step = (ar[nr - 1] - ar[0]) / (double)(nr - 1);
+    bool uni = true;
+    for (int64_t i = 0; i < nr; ++i)
+        if (std::fabs(ar[i] - (ar[0] + step * (double)i)) > 1e-12 * std::fabs(step)) { uni = false; break; }
+    view.uniform_r = uni ? 1 : 0;
+    view.r0 = ar[0];
+    view.r1 = ar[nr - 1];
+    view.inv_dr = 1.0 / step;
+}
+
 extern "C" int bfg_table_create(bfg_table **out, int ndim, const int64_t *shape, const double *const *h_axes,
                                 const double *h_values, int flags, int device) {
     BFG_ENTRY();
@@ -260,17 +273,7 @@ extern "C" int bfg_table_create(bfg_table **out, int ndim, const int64_t *shape,
         }
         t->view.v = t->d_values;
     }
-    // radial axis: uniform in ln r (np.geomspace -> np.log) unlocks the closed-form cell index
-    const double *ar = h_axes[2];
-    int64_t nr = shape[2];
-    double step = (ar[nr - 1] - ar[0]) / (double)(nr - 1);
-    bool uni = true;
-    for (int64_t i = 0; i < nr; ++i)
-        if (std::fabs(ar[i] - (ar[0] + step * (double)i)) > 1e-12 * std::fabs(step)) { uni = false; break; }
-    t->view.uniform_r = uni ? 1 : 0;
-    t->view.r0 = ar[0];
-    t->view.r1 = ar[nr - 1];
-    t->view.inv_dr = 1.0 / step;
+    describe_radial_axis(h_axes[2], shape[2], t->view);
     cudaSetDevice(cur);
     if (rc != BFG_OK) { bfg_table_destroy(t); return rc; }
     *out = t;
@@ -333,6 +336,39 @@ extern "C" int bfg_table_readout(const bfg_table *t, double lnz, double lnM, con
     BFG_CUDA_OK(cudaFuncSetAttribute(k_table_readout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_table_readout<<<1, 256, smem, (cudaStream_t)stream>>>(t->view, lnz, lnM, ex, n, d_x, d_out);
     BFG_CUDA_OK(cudaGetLastError());
+    return BFG_OK;
+}
+
+// test entry (pure host, no GPU): the read-out every halo-loop kernel performs -- blend the 2^(ndim-1) corner rows of the
+// non-radial axes into one radial row (RowBlender), then interpolate along ln r (row_lookup) -- with the SAME source on HOST
+// buffers: out[i] = table(lnz, lnM, x[i], extras...) with RegularGridInterpolator(bounds_error=False, fill_value=nan) semantics,
+// exp() applied for BFG_TABLE_LOG_VALUES tables (Tabulate.py:319).  force_search != 0 takes the non-uniform radial branch.
+extern "C" int bfg_test_table_readout_host(int ndim, const int64_t *shape, const double *const *h_axes, const double *h_values,
+                                           int flags, int force_search, double lnz, double lnM, const double *h_extras, int64_t n,
+                                           const double *h_x, double *h_out) {
+    BFG_REQUIRE(shape && h_axes && h_values && (n == 0 || (h_x && h_out)), "null argument");
+    BFG_REQUIRE(ndim >= 3 && ndim <= BFG_MAX_TABLE_DIM, "ndim must be 3..6");
+    BFG_REQUIRE(ndim == 3 || h_extras, "table has extra axes but no extras given");
+    TableView T;
+    memset(&T, 0, sizeof(T));
+    i64 total = 1;
+    for (int d = ndim - 1; d >= 0; --d) {
+        BFG_REQUIRE(shape[d] >= 2, "every axis needs >= 2 nodes");
+        T.n[d] = (int)shape[d]; T.stride[d] = total; total *= shape[d];
+        T.ax[d] = h_axes[d];
+    }
+    T.ndim = ndim; T.flags = flags; T.v = h_values;
+    describe_radial_axis(h_axes[2], shape[2], T);
+    if (force_search) T.uniform_r = 0;
+    const RowBlender B(T, lnz, lnM, h_extras);
+    std::vector<double> row((size_t)B.NR);
+    for (int k = 0; k < B.NR; ++k) row[(size_t)k] = B.node(T, k);
+    for (int64_t i = 0; i < n; ++i) {
+        double v = T.uniform_r ? row_lookup<true>(T, row.data(), h_x[i]) : row_lookup<false>(T, row.data(), h_x[i]);
+        if (!B.valid) v = std::numeric_limits<double>::quiet_NaN();
+        if (T.flags & BFG_TABLE_LOG_VALUES) v = exp(v);
+        h_out[i] = v;
+    }
     return BFG_OK;
 }
 

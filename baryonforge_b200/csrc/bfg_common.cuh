@@ -86,10 +86,20 @@ struct bfg_table {
 
 namespace bfg {
 
+// (the read-out pieces below -- axis_cell, RowBlender, row_lookup -- are __host__ __device__: bfg_test_table_readout_host runs the same
+// source on the CPU against scipy's RegularGridInterpolator; device-only intrinsics get host stand-ins)
+#ifdef __CUDA_ARCH__
+#define BFG_LDG(p) __ldg(p)
+#define BFG_QNAN CUDART_NAN
+#else
+#define BFG_LDG(p) (*(p))
+#define BFG_QNAN (__builtin_nan(""))
+#endif
+
 // Cell index / normalised distance of one coordinate on one axis, scipy find_indices semantics:
 // ax[i] <= x < ax[i+1], last interval right-closed, index clipped to [0, n-2].  Returns false when x is outside
 // [ax[0], ax[n-1]] (RegularGridInterpolator then yields fill_value = nan).  NaN x is "inside" and propagates.
-__device__ __forceinline__ bool axis_cell(const double *__restrict__ ax, int n, double x, int &i, double &t) {
+__host__ __device__ __forceinline__ bool axis_cell(const double *__restrict__ ax, int n, double x, int &i, double &t) {
     bool inside = !(x < ax[0]) && !(x > ax[n - 1]);
     int lo = 0, hi = n - 1;  // invariant: ax[lo] <= x (or lo == 0), x < ax[hi] (or hi == n-1)
     while (hi - lo > 1) {
@@ -122,7 +132,7 @@ struct RowBlender {
     const double *v00, *v01, *v10, *v11;   // the common (z, M, r) table: corner rows ...
     double w00, w01, w10, w11;             // ... and weights hoisted out of the radial loop
 
-    __device__ __forceinline__ RowBlender(const TableView &T, double lnz, double lnM, const double *__restrict__ extras) {
+    __host__ __device__ __forceinline__ RowBlender(const TableView &T, double lnz, double lnM, const double *__restrict__ extras) {
         nd = T.ndim; NR = T.n[2]; sr = T.stride[2];
         bool ok = true;
         int e = 0;
@@ -141,14 +151,14 @@ struct RowBlender {
         w10 = tt[0] * (1.0 - tt[1]); w11 = tt[0] * tt[1];
     }
 
-    __device__ __forceinline__ double node(const TableView &T, int k) const {
+    __host__ __device__ __forceinline__ double node(const TableView &T, int k) const {
         if (nd == 3) {
             const i64 o = (i64)k * sr;
             double acc = 0.0;
-            acc = acc + __ldg(v00 + o) * w00;
-            acc = acc + __ldg(v01 + o) * w01;
-            acc = acc + __ldg(v10 + o) * w10;
-            acc = acc + __ldg(v11 + o) * w11;
+            acc = acc + BFG_LDG(v00 + o) * w00;
+            acc = acc + BFG_LDG(v01 + o) * w01;
+            acc = acc + BFG_LDG(v10 + o) * w10;
+            acc = acc + BFG_LDG(v11 + o) * w11;
             return acc;
         }
         const int nc = 1 << (nd - 1);
@@ -164,7 +174,7 @@ struct RowBlender {
                 off += (i64)(idx[d] + up) * T.stride[d];
                 w = w * (up ? tt[d] : (1.0 - tt[d]));
             }
-            acc = acc + __ldg(T.v + off) * w;
+            acc = acc + BFG_LDG(T.v + off) * w;
         }
         return acc;
     }
@@ -201,9 +211,9 @@ __device__ __forceinline__ void blend_row_pairs(const TableView &T, double lnz, 
 
 // Radial read-out of a blended row at x = ln r (or ln r/R): NaN outside [r0, r1]; (1-t)*v0 + t*v1 as scipy does.
 template <bool UNIFORM>
-__device__ __forceinline__ double row_lookup(const TableView &T, const double *__restrict__ row, double x) {
+__host__ __device__ __forceinline__ double row_lookup(const TableView &T, const double *__restrict__ row, double x) {
     const int NR = T.n[2];
-    if (!(x >= T.r0) || !(x <= T.r1)) return (x != x) ? x : CUDART_NAN;
+    if (!(x >= T.r0) || !(x <= T.r1)) return (x != x) ? x : BFG_QNAN;
     int k;
     double t;
     if (UNIFORM) {
@@ -217,16 +227,16 @@ __device__ __forceinline__ double row_lookup(const TableView &T, const double *_
         // closed-form guess then bounded correction (geomspace axes hit on the first try)
         double u = (x - T.r0) * T.inv_dr;
         int g = min(max((int)u, 0), NR - 2);
-        if (x >= __ldg(ax + g) && x < __ldg(ax + g + 1)) {
+        if (x >= BFG_LDG(ax + g) && x < BFG_LDG(ax + g + 1)) {
             lo = g;
         } else {
             while (hi - lo > 1) {
                 int mid = (lo + hi) >> 1;
-                if (x >= __ldg(ax + mid)) lo = mid; else hi = mid;
+                if (x >= BFG_LDG(ax + mid)) lo = mid; else hi = mid;
             }
         }
         k = lo;
-        double a0 = __ldg(ax + k), a1 = __ldg(ax + k + 1);
+        double a0 = BFG_LDG(ax + k), a1 = BFG_LDG(ax + k + 1);
         t = (x - a0) / (a1 - a0);
     }
     double v0 = row[k], v1 = row[k + 1];

@@ -376,6 +376,12 @@ int bfg_test_regrid_target_host(int nside, int64_t n, const int64_t *h_pix, cons
 int bfg_test_shell_records_host(int64_t n_halo, const double *h_cols, int paint, double eps_run, double eps_model, double pixarea,
                                 int n_DA, const double *h_DA_x, const double *h_DA_c, int n_g, const double *h_g_x,
                                 const double *h_g_run_c, const double *h_g_mod_c, double *h_halos, double *h_aux);
+/* Test entry, pure host (no GPU): the table read-out of the halo-loop kernels (corner rows of the non-radial axes blended into one
+ * radial row, then interpolation along ln r; BaryonCorrection.py:331-419, Tabulate.py:279-327 == scipy RegularGridInterpolator with
+ * bounds_error=False, fill_value=nan) with the kernels' own source on HOST buffers.  force_search != 0: the non-uniform radial branch. */
+int bfg_test_table_readout_host(int ndim, const int64_t *shape, const double *const *h_axes, const double *h_values, int flags,
+                                int force_search, double lnz, double lnM, const double *h_extras, int64_t n, const double *h_x,
+                                double *h_out);
 /* Test entry, pure host (no GPU): index helpers of the grid and particle kernels on the CPU.  what = 0 NGP cell (np.histogramdd edges,
  * utils/io.py:629-677), 1 wrap_once (SnapshotRunner.py:272-273), 2 cell-list cell, 3 cutout coordinates + periodic indices of one axis
  * (n = Nsize, L = res, h_x[0] = centre cell; Map2DRunner.py:400-429, :500-528). */
