@@ -35,6 +35,16 @@ int retain_async_pool() {
     return BFG_OK;
 }
 
+// entry i: (rc, -log2(rc)) with rc = the rounded reciprocal of the centre of the i-th mantissa interval
+static void fill_log2_table(double2 *h) {
+    for (int i = 0; i < BFG_LOG2_TAB; ++i) {
+        long double c = 1.0L + ((long double)i + 0.5L) / (long double)BFG_LOG2_TAB;
+        double rc = (double)(1.0L / c);
+        h[i].x = rc;
+        h[i].y = (double)(-log2l((long double)rc));   // consistent with the ROUNDED reciprocal
+    }
+}
+
 int get_log2_table(const double2 **d_tab) {
     static double2 *tabs[64] = {nullptr};
     int dev = 0;
@@ -42,12 +52,7 @@ int get_log2_table(const double2 **d_tab) {
     BFG_REQUIRE(dev >= 0 && dev < 64, "device index out of range");
     if (!tabs[dev]) {
         double2 h[BFG_LOG2_TAB];
-        for (int i = 0; i < BFG_LOG2_TAB; ++i) {
-            long double c = 1.0L + ((long double)i + 0.5L) / (long double)BFG_LOG2_TAB;
-            double rc = (double)(1.0L / c);
-            h[i].x = rc;
-            h[i].y = (double)(-log2l((long double)rc));   // consistent with the ROUNDED reciprocal
-        }
+        fill_log2_table(h);
         double2 *d = nullptr;
         BFG_CUDA_OK(cudaMalloc(&d, sizeof(h)));
         BFG_CUDA_OK(cudaMemcpy(d, h, sizeof(h), cudaMemcpyHostToDevice));
@@ -172,6 +177,16 @@ extern "C" int bfg_test_healpix_host(int what, int nside, int64_t n, const int64
             BFG_REQUIRE(false, "what must be 0..5");
         }
     }
+    return BFG_OK;
+}
+
+// test entry (pure host, no GPU): fast_log2 -- table + degree-5 series, the log2 of every non-lean read-out -- on the CPU with the
+// table the device gets
+extern "C" int bfg_test_fast_log2_host(int64_t n, const double *h_x, double *h_out) {
+    BFG_REQUIRE(n >= 0 && (n == 0 || (h_x && h_out)), "bad argument");
+    double2 tab[BFG_LOG2_TAB];
+    fill_log2_table(tab);
+    for (int64_t i = 0; i < n; ++i) h_out[i] = fast_log2(h_x[i], tab);
     return BFG_OK;
 }
 

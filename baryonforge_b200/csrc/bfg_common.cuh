@@ -6,6 +6,7 @@
 //    BaryonForge/Profiles/BaryonCorrection.py:322,404-411 and BaryonForge/utils/Tabulate.py:270-271,318-319
 //  * HEALPix RING geometry as device functions (replaces healpy at BaryonForge/Runners/HealpixRunner.py:327-361)
 #pragma once
+#include <cstring>
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <stdint.h>
@@ -755,13 +756,36 @@ __device__ __forceinline__ void load_log2_table(double2 *tab, const double2 *__r
     for (int i = threadIdx.x; i < BFG_LOG2_TAB; i += blockDim.x) tab[i] = g_tab[i];
 }
 
-__device__ __forceinline__ double fast_log2(double x, const double2 *__restrict__ tab) {
-    const int hi = __double2hiint(x);
+// bit access for __host__ __device__ code (fast_log2 runs on the CPU in bfg_test_fast_log2_host)
+__host__ __device__ __forceinline__ int f64_hi(double x) {
+#ifdef __CUDA_ARCH__
+    return __double2hiint(x);
+#else
+    long long b; memcpy(&b, &x, 8); return (int)(b >> 32);
+#endif
+}
+__host__ __device__ __forceinline__ int f64_lo(double x) {
+#ifdef __CUDA_ARCH__
+    return __double2loint(x);
+#else
+    long long b; memcpy(&b, &x, 8); return (int)(b & 0xffffffffLL);
+#endif
+}
+__host__ __device__ __forceinline__ double f64_from(int hi, int lo) {
+#ifdef __CUDA_ARCH__
+    return __hiloint2double(hi, lo);
+#else
+    long long b = ((long long)hi << 32) | (long long)(unsigned int)lo; double x; memcpy(&x, &b, 8); return x;
+#endif
+}
+
+__host__ __device__ __forceinline__ double fast_log2(double x, const double2 *__restrict__ tab) {
+    const int hi = f64_hi(x);
     // zero / denormal / negative / inf / NaN: every caller turns log(0) = -inf, log(inf) and NaN alike into an
     // out-of-table read-out (NaN -> contribution 0), so one NaN stands for all of them
-    if ((unsigned)(hi - 0x00100000) >= (unsigned)(0x7ff00000 - 0x00100000)) return CUDART_NAN;
+    if ((unsigned)(hi - 0x00100000) >= (unsigned)(0x7ff00000 - 0x00100000)) return BFG_QNAN;
     const int idx = (hi >> 13) & (BFG_LOG2_TAB - 1);
-    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
+    const double m = f64_from((hi & 0x000fffff) | 0x3ff00000, f64_lo(x));
     const double2 t = tab[idx];
     const double f = fma(m, t.x, -1.0);
     // log2(1+f) = f * (c1 + f (c2 + f (c3 + f (c4 + f c5)))),  c_k = (-1)^(k+1) / (k ln 2)
@@ -770,7 +794,7 @@ __device__ __forceinline__ double fast_log2(double x, const double2 *__restrict_
     p = fma(f, p, -0.72134752044448170);
     p = fma(f, p, 1.4426950408889634);
     // exponent as a double without I2F: 2^52 + 2^31 + (e + 1023) trick
-    const double ed = __hiloint2double(0x43300000, (hi >> 20) ^ 0x80000000) - 4503601774854144.0 - 1023.0;
+    const double ed = f64_from(0x43300000, (hi >> 20) ^ 0x80000000) - 4503601774854144.0 - 1023.0;
     return fma(f, p, t.y) + ed;
 }
 

@@ -394,6 +394,8 @@ int bfg_test_healpix_host(int what, int nside, int64_t n, const int64_t *h_idx, 
                           int64_t *h_out_i, double *h_out_d);
 /* Unit-test entry for the table-driven log2 used inside the pixel loops: d_out[i] = log2(d_x[i]). */
 int bfg_test_fast_log2(int64_t n, const double *d_x, double *d_out, void *stream);
+/* The same on the CPU (pure host, no GPU): fast_log2's own source with the table the device gets. */
+int bfg_test_fast_log2_host(int64_t n, const double *h_x, double *h_out);
 /* out[i][c] = in[c][i] : component-major offsets -> the reference's (n, ncomp) layout, for tests. */
 int bfg_transpose_offsets(const double *d_in, double *d_out, int64_t n, int ncomp, void *stream);
 
