@@ -35,16 +35,6 @@ int retain_async_pool() {
     return BFG_OK;
 }
 
-// entry i: (rc, -log2(rc)) with rc = the rounded reciprocal of the centre of the i-th mantissa interval
-static void fill_log2_table(double2 *h) {
-    for (int i = 0; i < BFG_LOG2_TAB; ++i) {
-        long double c = 1.0L + ((long double)i + 0.5L) / (long double)BFG_LOG2_TAB;
-        double rc = (double)(1.0L / c);
-        h[i].x = rc;
-        h[i].y = (double)(-log2l((long double)rc));   // consistent with the ROUNDED reciprocal
-    }
-}
-
 int get_log2_table(const double2 **d_tab) {
     static double2 *tabs[64] = {nullptr};
     int dev = 0;
@@ -235,18 +225,6 @@ extern "C" int bfg_device_info(int device, int *sm_count, int64_t *mem_total, in
 }
 
 // ------------------------------------------------------------------------------------------------ tables
-// radial axis: uniform in ln r (np.geomspace -> np.log) unlocks the closed-form cell index
-static void describe_radial_axis(const double *ar, int64_t nr, TableView &view) {
-    double step = (ar[nr - 1] - ar[0]) / (double)(nr - 1);
-    bool uni = true;
-    for (int64_t i = 0; i < nr; ++i)
-        if (std::fabs(ar[i] - (ar[0] + step * (double)i)) > 1e-12 * std::fabs(step)) { uni = false; break; }
-    view.uniform_r = uni ? 1 : 0;
-    view.r0 = ar[0];
-    view.r1 = ar[nr - 1];
-    view.inv_dr = 1.0 / step;
-}
-
 extern "C" int bfg_table_create(bfg_table **out, int ndim, const int64_t *shape, const double *const *h_axes,
                                 const double *h_values, int flags, int device) {
     BFG_ENTRY();
@@ -364,16 +342,9 @@ extern "C" int bfg_test_table_readout_host(int ndim, const int64_t *shape, const
     BFG_REQUIRE(shape && h_axes && h_values && (n == 0 || (h_x && h_out)), "null argument");
     BFG_REQUIRE(ndim >= 3 && ndim <= BFG_MAX_TABLE_DIM, "ndim must be 3..6");
     BFG_REQUIRE(ndim == 3 || h_extras, "table has extra axes but no extras given");
+    for (int d = 0; d < ndim; ++d) BFG_REQUIRE(shape[d] >= 2, "every axis needs >= 2 nodes");
     TableView T;
-    memset(&T, 0, sizeof(T));
-    i64 total = 1;
-    for (int d = ndim - 1; d >= 0; --d) {
-        BFG_REQUIRE(shape[d] >= 2, "every axis needs >= 2 nodes");
-        T.n[d] = (int)shape[d]; T.stride[d] = total; total *= shape[d];
-        T.ax[d] = h_axes[d];
-    }
-    T.ndim = ndim; T.flags = flags; T.v = h_values;
-    describe_radial_axis(h_axes[2], shape[2], T);
+    host_table_view(ndim, shape, h_axes, h_values, flags, T);
     if (force_search) T.uniform_r = 0;
     const RowBlender B(T, lnz, lnM, h_extras);
     std::vector<double> row((size_t)B.NR);

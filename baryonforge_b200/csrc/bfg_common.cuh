@@ -6,6 +6,7 @@
 //    BaryonForge/Profiles/BaryonCorrection.py:322,404-411 and BaryonForge/utils/Tabulate.py:270-271,318-319
 //  * HEALPix RING geometry as device functions (replaces healpy at BaryonForge/Runners/HealpixRunner.py:327-361)
 #pragma once
+#include <cmath>
 #include <cstring>
 #include <cuda_runtime.h>
 #include <math_constants.h>
@@ -14,6 +15,7 @@
 #include "../../include/bfg_b200.h"
 
 typedef long long i64;
+#define BFG_LOG2_TAB 128
 
 namespace bfg {
 
@@ -74,6 +76,43 @@ struct TableView {
     const double *v;
     double r0, r1, inv_dr;  // first/last radial node, 1/step
 };
+
+// radial axis: uniform in ln r (np.geomspace -> np.log) unlocks the closed-form cell index
+inline void describe_radial_axis(const double *ar, int64_t nr, TableView &view) {
+    double step = (ar[nr - 1] - ar[0]) / (double)(nr - 1);
+    bool uni = true;
+    for (int64_t i = 0; i < nr; ++i) {
+        double d = ar[i] - (ar[0] + step * (double)i);
+        if ((d < 0 ? -d : d) > 1e-12 * (step < 0 ? -step : step)) { uni = false; break; }
+    }
+    view.uniform_r = uni ? 1 : 0;
+    view.r0 = ar[0];
+    view.r1 = ar[nr - 1];
+    view.inv_dr = 1.0 / step;
+}
+
+// entry i: (rc, -log2(rc)) with rc = the rounded reciprocal of the centre of the i-th mantissa interval
+inline void fill_log2_table(double2 *h) {
+    for (int i = 0; i < BFG_LOG2_TAB; ++i) {
+        long double c = 1.0L + ((long double)i + 0.5L) / (long double)BFG_LOG2_TAB;
+        double rc = (double)(1.0L / c);
+        h[i].x = rc;
+        h[i].y = (double)(-log2l((long double)rc));   // consistent with the ROUNDED reciprocal
+    }
+}
+
+// TableView over HOST arrays (the host test entries run the kernels' read-out source on the CPU)
+inline void host_table_view(int ndim, const int64_t *shape, const double *const *h_axes, const double *h_values, int flags,
+                            TableView &T) {
+    memset(&T, 0, sizeof(T));
+    i64 total = 1;
+    for (int d = ndim - 1; d >= 0; --d) {
+        T.n[d] = (int)shape[d]; T.stride[d] = total; total *= shape[d];
+        T.ax[d] = h_axes[d];
+    }
+    T.ndim = ndim; T.flags = flags; T.v = h_values;
+    describe_radial_axis(h_axes[2], shape[2], T);
+}
 
 }  // namespace bfg
 
@@ -748,7 +787,6 @@ __host__ __device__ __forceinline__ i64 nest2ring(const Hpx &h, i64 pix) {
 // Absolute error < 2e-15 (tests/test_gpu_parity.py::test_fast_log2).  Zero / denormal / inf / NaN / negative inputs
 // (never a finite, in-table radius) return NaN.  tab = 128 x (rc, lt) in shared memory.
 // ------------------------------------------------------------------------------------------------
-#define BFG_LOG2_TAB 128
 // host: per-device global copy of the table (allocated and filled once); kernels stage it into shared memory
 int get_log2_table(const double2 **d_tab);
 
@@ -873,7 +911,13 @@ __device__ __forceinline__ double row_at_r2(const RowLookup &f, double r2, bool 
 }
 
 // fp64 RED (no return value): RED.E.ADD.F64 on sm_100a
-__device__ __forceinline__ void red_add(double *addr, double v) { atomicAdd(addr, v); }
+__host__ __device__ __forceinline__ void red_add(double *addr, double v) {
+#ifdef __CUDA_ARCH__
+    atomicAdd(addr, v);
+#else
+    *addr += v;      // host test entries are single-threaded
+#endif
+}
 
 __device__ __forceinline__ double warp_sum(double v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

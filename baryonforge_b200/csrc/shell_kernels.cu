@@ -11,6 +11,7 @@
 // lane group hit consecutive addresses of the component-major offsets array.
 #include <algorithm>
 #include <string.h>
+#include <vector>
 #include "bfg_common.cuh"
 
 using namespace bfg;
@@ -30,15 +31,15 @@ struct HaloSph {
     double vx, vy, vz, theta, phi, D, a, radius, lnz, lnM, rcut, lnRcom, scale, theta_ll, phi_ll, skip;
 };
 
-__device__ __forceinline__ HaloSph load_halo(const double *__restrict__ H) {
+__host__ __device__ __forceinline__ HaloSph load_halo(const double *__restrict__ H) {
     HaloSph s;
-    s.vx = __ldg(H + BFG_HS_VX); s.vy = __ldg(H + BFG_HS_VY); s.vz = __ldg(H + BFG_HS_VZ);
-    s.theta = __ldg(H + BFG_HS_THETA); s.phi = __ldg(H + BFG_HS_PHI);
-    s.D = __ldg(H + BFG_HS_D); s.a = __ldg(H + BFG_HS_A); s.radius = __ldg(H + BFG_HS_RADIUS);
-    s.lnz = __ldg(H + BFG_HS_LNZ); s.lnM = __ldg(H + BFG_HS_LNM); s.rcut = __ldg(H + BFG_HS_RCUT);
-    s.lnRcom = __ldg(H + BFG_HS_LNRCOM); s.scale = __ldg(H + BFG_HS_SCALE);
-    s.theta_ll = __ldg(H + BFG_HS_THETA_LL); s.phi_ll = __ldg(H + BFG_HS_PHI_LL);
-    s.skip = __ldg(H + BFG_HS_SKIP);
+    s.vx = BFG_LDG(H + BFG_HS_VX); s.vy = BFG_LDG(H + BFG_HS_VY); s.vz = BFG_LDG(H + BFG_HS_VZ);
+    s.theta = BFG_LDG(H + BFG_HS_THETA); s.phi = BFG_LDG(H + BFG_HS_PHI);
+    s.D = BFG_LDG(H + BFG_HS_D); s.a = BFG_LDG(H + BFG_HS_A); s.radius = BFG_LDG(H + BFG_HS_RADIUS);
+    s.lnz = BFG_LDG(H + BFG_HS_LNZ); s.lnM = BFG_LDG(H + BFG_HS_LNM); s.rcut = BFG_LDG(H + BFG_HS_RCUT);
+    s.lnRcom = BFG_LDG(H + BFG_HS_LNRCOM); s.scale = BFG_LDG(H + BFG_HS_SCALE);
+    s.theta_ll = BFG_LDG(H + BFG_HS_THETA_LL); s.phi_ll = BFG_LDG(H + BFG_HS_PHI_LL);
+    s.skip = BFG_LDG(H + BFG_HS_SKIP);
     return s;
 }
 
@@ -51,7 +52,7 @@ struct HaloUpd {
     double uA, uB, uMax;          // uniform ln r axis: cell coordinate u = log2(r^2) * uA + uB in [0, NR-1]
 };
 
-__device__ __forceinline__ HaloUpd make_upd(const TableView &T, const HaloSph &s) {
+__host__ __device__ __forceinline__ HaloUpd make_upd(const TableView &T, const HaloSph &s) {
     HaloUpd u;
     u.D = s.D; u.a = s.a;
     u.pjx = s.vx * s.D; u.pjy = s.vy * s.D; u.pjz = s.vz * s.D;
@@ -67,12 +68,12 @@ __device__ __forceinline__ HaloUpd make_upd(const TableView &T, const HaloSph &s
 
 // Table value at squared separation r2 (NaN when outside the table / not a positive normal number).
 template <bool UNIFORM>
-__device__ __forceinline__ double table_at_l2(const TableView &T, const double *__restrict__ row, const HaloUpd &u,
+__host__ __device__ __forceinline__ double table_at_l2(const TableView &T, const double *__restrict__ row, const HaloUpd &u,
                                               double l2) {
     if (UNIFORM) {
         const int NR = T.n[2];
         const double uu = fma(l2, u.uA, u.uB);                      // (ln r - r0) / step
-        if (!(uu >= 0.0) || !(uu <= u.uMax)) return CUDART_NAN;
+        if (!(uu >= 0.0) || !(uu <= u.uMax)) return BFG_QNAN;
         const int k = min((int)uu, NR - 2);
         const double t = uu - (double)k;
         return fma(t, row[k + 1], (1.0 - t) * row[k]);              // (1-t) v0 + t v1, as scipy
@@ -81,7 +82,7 @@ __device__ __forceinline__ double table_at_l2(const TableView &T, const double *
 }
 
 template <bool UNIFORM>
-__device__ __forceinline__ double table_at(const TableView &T, const double *__restrict__ row, const HaloUpd &u,
+__host__ __device__ __forceinline__ double table_at(const TableView &T, const double *__restrict__ row, const HaloUpd &u,
                                            double r2, const double2 *__restrict__ l2tab) {
     return table_at_l2<UNIFORM>(T, row, u, fast_log2(r2, l2tab));
 }
@@ -102,7 +103,7 @@ struct AnisArgs {
 // One (halo, pixel) update.  (x, y, z) = pixel unit vector; (px, py, pz) = (x, y, z) * D; p0/p1/p2 = the pixel's slots
 // in the three offset components (paint: p0 only).
 template <int MODE, bool UNIFORM>
-__device__ __forceinline__ void shell_update(const TableView &T, const double *__restrict__ row, const HaloUpd &u,
+__host__ __device__ __forceinline__ void shell_update(const TableView &T, const double *__restrict__ row, const HaloUpd &u,
                                              double x, double y, double z, double px, double py, double pz,
                                              double *__restrict__ p0, double *__restrict__ p1, double *__restrict__ p2,
                                              const double2 *__restrict__ l2tab, const AnisArgs &A,
@@ -1529,3 +1530,40 @@ extern "C" int bfg_shell_regrid_p2p_range(int nside, const double *d_map_in, con
 }
 
 
+
+// ---------------------------------------------------------------------------------------------------- host test entry
+// Pure host, no GPU: ONE halo's updates of a list of pixels with the generic per-pixel update of the shell kernels
+// (shell_update<MODE, UNIFORM> above -- the literal arithmetic of HealpixRunner.py:336-355 / :464-481 the fast loops reorganise),
+// its table read-out and its halo constants, all from the kernels' own source.  h_record = the 16-double halo record
+// (bfg_shell_records), h_vec [n][3] = pixel unit vectors; mode 0: h_out [n][3] += nw_vec - vec, mode 1: h_out [n] += profile.
+extern "C" int bfg_test_shell_update_host(int ndim, const int64_t *shape, const double *const *h_axes, const double *h_values,
+                                          int flags, int force_search, int mode, const double *h_record, const double *h_extras,
+                                          int64_t n, const double *h_vec, double *h_out) {
+    BFG_REQUIRE(shape && h_axes && h_values && h_record && (n == 0 || (h_vec && h_out)), "null argument");
+    BFG_REQUIRE(ndim >= 3 && ndim <= BFG_MAX_TABLE_DIM && (ndim == 3 || h_extras), "bad table / extras");
+    BFG_REQUIRE(mode == 0 || mode == 1, "mode: 0 = baryonify, 1 = paint");
+    TableView T;
+    host_table_view(ndim, shape, h_axes, h_values, flags, T);
+    if (force_search) T.uniform_r = 0;
+    const HaloSph s = load_halo(h_record);
+    const HaloUpd u = make_upd(T, s);
+    const RowBlender B(T, s.lnz, s.lnM, h_extras);
+    std::vector<double> row((size_t)B.NR);
+    for (int k = 0; k < B.NR; ++k) row[(size_t)k] = B.node(T, k);
+    double2 l2tab[BFG_LOG2_TAB];
+    fill_log2_table(l2tab);
+    const AnisArgs A = {};
+    if (!B.valid) return BFG_OK;            // outside the table in (z, M, extras): every read-out is NaN -> adds nothing
+    for (int64_t i = 0; i < n; ++i) {
+        const double x = h_vec[3 * i], y = h_vec[3 * i + 1], z = h_vec[3 * i + 2];
+        double *o = mode == 0 ? h_out + 3 * i : h_out + i;
+        if (mode == 0) {
+            if (T.uniform_r) shell_update<MODE_BARYONIFY, true>(T, row.data(), u, x, y, z, x * u.D, y * u.D, z * u.D, o, o + 1, o + 2, l2tab, A, row.data(), u);
+            else shell_update<MODE_BARYONIFY, false>(T, row.data(), u, x, y, z, x * u.D, y * u.D, z * u.D, o, o + 1, o + 2, l2tab, A, row.data(), u);
+        } else {
+            if (T.uniform_r) shell_update<MODE_PAINT, true>(T, row.data(), u, x, y, z, x * u.D, y * u.D, z * u.D, o, o, o, l2tab, A, row.data(), u);
+            else shell_update<MODE_PAINT, false>(T, row.data(), u, x, y, z, x * u.D, y * u.D, z * u.D, o, o, o, l2tab, A, row.data(), u);
+        }
+    }
+    return BFG_OK;
+}

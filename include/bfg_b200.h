@@ -382,6 +382,12 @@ int bfg_test_shell_records_host(int64_t n_halo, const double *h_cols, int paint,
 int bfg_test_table_readout_host(int ndim, const int64_t *shape, const double *const *h_axes, const double *h_values, int flags,
                                 int force_search, double lnz, double lnM, const double *h_extras, int64_t n, const double *h_x,
                                 double *h_out);
+/* Test entry, pure host (no GPU): one halo's per-pixel updates with the shell kernels' own generic update (HealpixRunner.py:336-355 /
+ * :464-481), read-out and halo constants.  h_record = the 16-double halo record, h_vec [n][3] = pixel unit vectors; mode 0 (baryonify):
+ * h_out [n][3] += nw_vec - vec; mode 1 (paint): h_out [n] += profile * scale.  h_out is accumulated into (zero it first). */
+int bfg_test_shell_update_host(int ndim, const int64_t *shape, const double *const *h_axes, const double *h_values, int flags,
+                               int force_search, int mode, const double *h_record, const double *h_extras, int64_t n,
+                               const double *h_vec, double *h_out);
 /* Test entry, pure host (no GPU): index helpers of the grid and particle kernels on the CPU.  what = 0 NGP cell (np.histogramdd edges,
  * utils/io.py:629-677), 1 wrap_once (SnapshotRunner.py:272-273), 2 cell-list cell, 3 cutout coordinates + periodic indices of one axis
  * (n = Nsize, L = res, h_x[0] = centre cell; Map2DRunner.py:400-429, :500-528). */
