@@ -161,14 +161,14 @@ k_grid_halos(TableView T, int N, double res, double scale, i64 n_halo, const dou
 }
 
 // Python float modulo for a positive modulus
-__device__ __forceinline__ double pymod(double x, double n) {
+__host__ __device__ __forceinline__ double pymod(double x, double n) {
     double r = fmod(x, n);
     if (r != 0.0 && r < 0.0) r += n;
     return r;
 }
 
 // One axis of regrid_pixels_2D/3D: the two cells that overlap [xs, xs+1) and their overlap lengths.
-__device__ __forceinline__ void axis_deposit(double pos, int N, int c[2], double w[2]) {
+__host__ __device__ __forceinline__ void axis_deposit(double pos, int N, int c[2], double w[2]) {
     double xs = pymod(pos, (double)N);
     int f = (int)xs;                       // xs >= 0
     double fp1 = (double)(f + 1);
@@ -323,5 +323,20 @@ extern "C" int bfg_grid_regrid(int ndim, int64_t N, const double *d_map_in, cons
     else
         k_grid_regrid<2><<<blocks, 256, 0, (cudaStream_t)stream>>>((int)N, d_map_in, d_offsets, d_map_out, (int)plane_lo, (int)plane_hi);
     BFG_CUDA_OK(cudaGetLastError());
+    return BFG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------- host test entry
+// Pure host, no GPU: axis_deposit -- one axis of the re-binning kernel (regrid_pixels_2D/3D, Map2DRunner.py:13-162: the two cells
+// that overlap [x, x + 1) after the periodic wrap and their overlap lengths) -- on the CPU: h_c [n][2], h_w [n][2].
+extern "C" int bfg_test_axis_deposit_host(int64_t n, const double *h_pos, int64_t N, int64_t *h_c, double *h_w) {
+    BFG_REQUIRE(n >= 0 && N >= 1 && N <= 2147483647LL && (n == 0 || (h_pos && h_c && h_w)), "bad argument");
+    for (int64_t i = 0; i < n; ++i) {
+        int c[2];
+        double w[2];
+        axis_deposit(h_pos[i], (int)N, c, w);
+        h_c[2 * i] = c[0]; h_c[2 * i + 1] = c[1];
+        h_w[2 * i] = w[0]; h_w[2 * i + 1] = w[1];
+    }
     return BFG_OK;
 }

@@ -69,3 +69,49 @@ def test_cutout_coordinates_and_indices_are_numpy_bit_for_bit():
     for cen in (0, 1, 63):
         idx, _ = helper(3, [float(cen)], 1.0, 64, n=32)
         assert np.array_equal(idx, rp._pick_indices(cen, 16, 64)) and idx.min() >= 0 and idx.max() < 64
+
+
+def test_axis_deposit_rebuilds_the_numba_regrid_loops():
+    """axis_deposit (csrc/grid_kernels.cu, the kernel's own source on the host) gives, per axis, the two cells that overlap [x, x + 1) and
+    their overlap lengths; the products over the axes must reproduce the literal window-scan loops of regrid_pixels_2D / 3D
+    (oracle/grid_deposit.c == Map2DRunner.py:13-162) -- periodic wrap, negative and far-away positions, exact integers."""
+    from baryonforge_b200 import _lib
+    rng = np.random.default_rng(8)
+
+    def axis(pos, N):
+        pos = np.ascontiguousarray(pos, dtype=np.float64)
+        c = np.empty((pos.size, 2), dtype=np.int64)
+        w = np.empty((pos.size, 2), dtype=np.float64)
+        _lib.check(_lib.lib().bfg_test_axis_deposit_host(pos.size, pos.ctypes.data, int(N), c.ctypes.data, w.ctypes.data))
+        return c, w
+
+    for ndim, N, n in ((2, 16, 4000), (2, 37, 4000), (3, 12, 6000), (3, 9, 3000)):
+        pos = rng.uniform(-0.5 * N, 1.5 * N, (n, ndim))
+        pos[:200] = rng.integers(-N, 2 * N, (200, ndim)).astype(float)          # exact integers: one of the two overlaps is 0
+        pos[200:400] = np.round(pos[200:400]) + rng.choice([1e-13, -1e-13], (200, ndim))
+        pos[400:420] = rng.uniform(-50 * N, 50 * N, (20, ndim))                   # many periods away
+        val = rng.uniform(0.1, 10, n)
+        # the oracle applies `pix_offsets[:, k] += grids[k]` to (cell index + offset); hand it absolute positions directly
+        grid = np.zeros((N,) * ndim)
+        lib = rp._gridlib()
+        flat = np.ascontiguousarray(pos)
+        if ndim == 2:
+            lib.grido_regrid_2d(grid, N, n, flat, np.ascontiguousarray(val))
+        else:
+            lib.grido_regrid_3d(grid, N, n, flat, np.ascontiguousarray(val))
+        cw = [axis(pos[:, k], N) for k in range(ndim)]
+        got = np.zeros((N,) * ndim)
+        for bits in range(2 ** ndim):
+            sel = [(bits >> k) & 1 for k in range(ndim)]
+            w = val.copy()
+            ok = np.ones(n, dtype=bool)
+            wprod = np.ones(n)
+            for k in range(ndim):
+                wk = cw[k][1][:, sel[k]]
+                ok &= wk > 0                                                       # the loops' strict `> 0` test
+                wprod = wprod * wk if k else wk.copy()
+            # component 0 rides on array axis 1 (x), component 1 on axis 0 (y), component 2 on axis 2   (grid[i = y][j = x][k = z])
+            idx = (cw[1][0][:, sel[1]], cw[0][0][:, sel[0]]) + ((cw[2][0][:, sel[2]],) if ndim == 3 else ())
+            np.add.at(got, tuple(i[ok] for i in idx), (wprod * val)[ok])
+        assert np.allclose(got, grid, rtol=1e-13, atol=1e-13 * grid.max()), (ndim, N, np.abs(got - grid).max())
+        assert np.isclose(got.sum(), val.sum(), rtol=1e-12)
