@@ -362,3 +362,23 @@ def test_record_layout_and_chunk_fractions(monkeypatch):
             assert fr[-3:] == [0.90, 0.96, 0.99]                                      # the exposed tail is a 1 % piece
     monkeypatch.setenv("BFG_PIPELINE_TAPER", "0")
     assert runners._chunk_fractions(8) == [k / 8 for k in range(8)]
+
+
+def test_host_thread_pool_and_buffer_release_work_without_a_gpu(monkeypatch):
+    """The persistent host thread pool runs every chunk exactly once (ragged tail included, results in place), follows
+    BFG_HOST_THREADS, and release_host_buffers() is safe to call in a process that never touched a GPU."""
+    from baryonforge_b200 import runners
+    out = np.zeros(200003)
+    runners._parallel_chunks(lambda sl: out.__setitem__(sl, out[sl] + np.arange(sl.start, sl.stop)), out.size, chunk=4096)
+    assert np.array_equal(out, np.arange(out.size, dtype=float))
+    monkeypatch.setenv("BFG_HOST_THREADS", "3")
+    assert runners._host_threads() == 3 and runners._pool() is runners._pool()
+    monkeypatch.setenv("BFG_HOST_THREADS", "1")
+    seen = []
+    runners._parallel_chunks(lambda sl: seen.append((sl.start, sl.stop)), 10, chunk=4)
+    assert seen == [(0, 4), (4, 8), (8, 10)]                                  # one thread: in order, on the caller's thread
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "8")
+    monkeypatch.delenv("BFG_HOST_THREADS")
+    assert 1 <= runners._host_threads() <= 16
+    runners.release_host_buffers()
+    assert runners._PINNED_FREE == {} and runners._PINNED_SCRATCH == {}
