@@ -1,9 +1,9 @@
 // sht_kernels.cu -- spherical-harmonic transforms on the HEALPix RING grid for the C_l measurement that follows BaryonifyShell in
 // the reference's workflow: `hp.anafast(map)` (examples/04_Baryonify_Density_Shell.ipynb cell 18).
 //
-// STAGED: written after the GPU budget of round 1 was spent -- compiled, never run.  The algorithm is the one of
-// oracle/anafast_rings.py (checked on the CPU against the dense definition oracle/anafast_port.py); its tests are gated behind
-// BFG_TEST_EXPERIMENTAL=1.  First version: correctness before speed --
+// First run on a B200 in round 2 (tests/test_gpu_harmonics.py green, timings in profiles/r2_anafast.json).  The algorithm is the
+// one of oracle/anafast_rings.py (checked on the CPU against the dense definition oracle/anafast_port.py); parity is UNPINNED at
+// the healpy boundary (healpy absent).  First version: correctness before speed --
 //   k_sht_ring_analysis  : F_m(r) = sum_j f(r, j) exp(-i m phi_j) for every ring r and 0 <= m <= lmax, as a direct sum with exact
 //                          seeds for the twiddle recurrence (m phi_j / pi is a rational number with denominator 4 n_r / 4);
 //   k_sht_leg_analysis   : a_lm += w sum_r lambda_lm(cos theta_r) F_m(r), one warp per (m, 32 ring pairs), north/south rings
