@@ -62,7 +62,7 @@ k_deposit_folded(i64 n, const double *__restrict__ x, const double *__restrict__
 // k_deposit_folded straight from the CELL-ORDERED particles of bfg_snap_build_cells + their accumulated offsets (what
 // k_snap_apply_deposit does for the NGP grid): position = wrap_once(xs + tot) exactly as bfg_snap_apply computes it
 // (SnapshotRunner.py:263-273), then the folded cell.  Lanes walk the particles of one cell-list cell, so their REDs fall
-// into neighbouring grid cells instead of random DRAM sectors.  Staged for measurement.
+// into neighbouring grid cells instead of random DRAM sectors (tests/test_gpu_spectrum.py: the same grid, bit for bit).
 __global__ void __launch_bounds__(256)
 k_apply_deposit_folded(i64 n, const double *__restrict__ xs, const double *__restrict__ ys, const double *__restrict__ zs,
                        const double *__restrict__ tot, double L, double Lfold, i64 N, double *__restrict__ grid,

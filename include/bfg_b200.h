@@ -301,7 +301,7 @@ int bfg_snap_deposit_folded(int64_t n_part, const double *d_x, const double *d_y
 /* bfg_snap_deposit_folded over the CELL-ORDERED particles of bfg_snap_build_cells and their accumulated offsets d_tot
  * [3][n_part] (3-D): position = wrap_once(xs + tot) as bfg_snap_apply computes it (SnapshotRunner.py:263-273), then the
  * folded cell -- the displaced particles are never scattered back to the caller's order.  Same grid as
- * bfg_snap_apply + bfg_snap_deposit_folded.  Staged: not measured in round 1. */
+ * bfg_snap_apply + bfg_snap_deposit_folded (tests/test_gpu_spectrum.py: bit-identical grids). */
 int bfg_snap_apply_deposit_folded(int64_t n_part, const double *d_xs, const double *d_ys, const double *d_zs,
                                   const double *d_tot, double L, double L_fold, int64_t n_grid, double *d_grid,
                                   int64_t *d_ndropped, void *stream);
@@ -322,7 +322,7 @@ int bfg_grid_power_spectrum(int64_t N, const double *d_grid, const double *d_kli
 
 /* ---- C_l of a shell: the measurement that follows BaryonifyShell.process() in the reference's workflow ------------------
  * `hp.anafast(map)` (examples/04_Baryonify_Density_Shell.ipynb cell 18) = healpix_cxx map2alm_iter (lmax = 3 nside - 1, three
- * Jacobi iterations, unit ring weights) + alm2cl.  STAGED: compiled, not yet run on a GPU; the algorithm
+ * Jacobi iterations, unit ring weights) + alm2cl.  First GPU run in round 2 (tests/test_gpu_harmonics.py, parity unpinned: healpy absent); the algorithm
  * is oracle/anafast_rings.py.  a_lm are complex128 in healpy's packing idx(l, m) = m (2 lmax + 1 - m) / 2 + l, m >= 0.
  *   d_ln_mm [lmax + 1]  ln of sqrt((2m+1)/(4 pi) prod_{k<=m} (2k-1)/(2k)), from the host
  *   d_work              complex128 [lmax + 1][4 nside - 1] ring coefficients, bfg_sht_workspace_elems() elements */

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""tools/bench_anafast.py -- device timing of the staged C_l step (harmonics.ShellHarmonics, csrc/sht_kernels.cu), CUDA events.
+"""tools/bench_anafast.py -- device timing of the C_l step (harmonics.ShellHarmonics, csrc/sht_kernels.cu), CUDA events.
 One JSON line: per NSIDE the time of one analysis pass, one synthesis and a full anafast (iter = 3: seven transforms)."""
 import argparse
 import json
