@@ -105,6 +105,8 @@ _SIGNATURES = {
     "bfg_test_shell_update_host": ([C.c_int, C.POINTER(c_i64), C.POINTER(c_ptr), c_ptr, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr,
                                     c_i64, c_ptr, c_ptr], C.c_int),
     "bfg_test_axis_deposit_host": ([c_i64, c_ptr, c_i64, c_ptr, c_ptr], C.c_int),
+    "bfg_test_row_at_r2_host": ([C.c_int, C.POINTER(c_i64), C.POINTER(c_ptr), c_ptr, C.c_int, c_dbl, c_dbl, c_ptr, c_dbl, c_i64, c_ptr,
+                                 c_ptr, c_ptr], C.c_int),
     "bfg_test_index_helpers_host": ([C.c_int, c_i64, c_ptr, c_dbl, c_i64, c_ptr, c_ptr], C.c_int),
     "bfg_test_healpix_host": ([C.c_int, C.c_int, c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_ptr], C.c_int),
     "bfg_test_fast_log2_host": ([c_i64, c_ptr, c_ptr], C.c_int),

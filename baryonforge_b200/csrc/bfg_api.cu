@@ -170,6 +170,41 @@ extern "C" int bfg_test_healpix_host(int what, int nside, int64_t n, const int64
     return BFG_OK;
 }
 
+// test entry (pure host, no GPU): row_at_r2 -- the lean read-out of the default grid / particle / exact shell loops: table value at a
+// SQUARED radius from the blended row, cell coordinate u = log2(r^2) uA + uB with the table-driven log2 -- from the kernels' own
+// source.  offset = ln(1/a) - ln R_com (shells), -ln R_com (R_delta-sampled tables) or 0: what the kernels fold into uB.
+// h_out[i] = value (before any exp), h_ok[i] = 0 outside [r0, r1].
+extern "C" int bfg_test_row_at_r2_host(int ndim, const int64_t *shape, const double *const *h_axes, const double *h_values, int flags,
+                                       double lnz, double lnM, const double *h_extras, double offset, int64_t n, const double *h_r2,
+                                       double *h_out, int *h_ok) {
+    BFG_REQUIRE(shape && h_axes && h_values && (n == 0 || (h_r2 && h_out && h_ok)), "null argument");
+    BFG_REQUIRE(ndim >= 3 && ndim <= BFG_MAX_TABLE_DIM && (ndim == 3 || h_extras), "bad table / extras");
+    TableView T;
+    host_table_view(ndim, shape, h_axes, h_values, flags, T);
+    BFG_REQUIRE(T.uniform_r, "row_at_r2 needs a uniform ln r axis");
+    const RowBlender B(T, lnz, lnM, h_extras);
+    // the "shared memory" of the host build: [row (NR doubles)][log2 table]
+    std::vector<double> arena((size_t)B.NR + 2 * BFG_LOG2_TAB);
+    for (int k = 0; k < B.NR; ++k) arena[(size_t)k] = B.node(T, k);
+    fill_log2_table(reinterpret_cast<double2 *>(arena.data() + B.NR));
+    bfg_host_smem = reinterpret_cast<const char *>(arena.data());
+    RowLookup rl;
+    rl.uA = 0.34657359027997264 * T.inv_dr;
+    rl.uB = (offset - T.r0) * T.inv_dr;
+    rl.uMax = (double)(T.n[2] - 1);
+    rl.nrm2 = T.n[2] - 2;
+    rl.row_s = 0;
+    rl.l2_s = (unsigned)(sizeof(double) * (size_t)B.NR);
+    for (int64_t i = 0; i < n; ++i) {
+        bool ok;
+        const double v = row_at_r2(rl, h_r2[i], ok);
+        h_out[i] = (ok && B.valid) ? v : std::numeric_limits<double>::quiet_NaN();
+        h_ok[i] = (ok && B.valid) ? 1 : 0;
+    }
+    bfg_host_smem = nullptr;
+    return BFG_OK;
+}
+
 // test entry (pure host, no GPU): fast_log2 -- table + degree-5 series, the log2 of every non-lean read-out -- on the CPU with the
 // table the device gets
 extern "C" int bfg_test_fast_log2_host(int64_t n, const double *h_x, double *h_out) {

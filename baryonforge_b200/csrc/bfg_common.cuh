@@ -843,15 +843,34 @@ __host__ __device__ __forceinline__ double fast_log2(double x, const double2 *__
 // ------------------------------------------------------------------------------------------------
 static __constant__ double c_l2p[5] = {0.28853900817779268, -0.36067376022224085, 0.48089834696298783, -0.72134752044448170,
                                 1.4426950408889634};
+// (the host shadow of a __constant__ array does not carry its initialiser: host builds of row_at_r2 read this copy)
+static const double c_l2p_host[5] = {0.28853900817779268, -0.36067376022224085, 0.48089834696298783, -0.72134752044448170,
+                                1.4426950408889634};
+#ifdef __CUDA_ARCH__
+#define BFG_L2P(i) c_l2p[i]
+#else
+#define BFG_L2P(i) c_l2p_host[i]
+#endif
 
-__device__ __forceinline__ double2 lds_f64x2(unsigned addr) {
+// (host build: "shared-window addresses" are byte offsets into bfg_host_smem, the arena bfg_test_row_at_r2_host lays out, so
+// that row_at_r2 -- the read-out of the default grid / particle / exact shell loops -- runs on the CPU from the same source)
+static thread_local const char *bfg_host_smem = nullptr;      // host builds only (never referenced by device code)
+__host__ __device__ __forceinline__ double2 lds_f64x2(unsigned addr) {
     double2 v;
+#ifdef __CUDA_ARCH__
     asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+#else
+    memcpy(&v, bfg_host_smem + addr, sizeof(v));
+#endif
     return v;
 }
-__device__ __forceinline__ double lds_f64(unsigned addr) {
+__host__ __device__ __forceinline__ double lds_f64(unsigned addr) {
     double v;
+#ifdef __CUDA_ARCH__
     asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+#else
+    memcpy(&v, bfg_host_smem + addr, sizeof(v));
+#endif
     return v;
 }
 // 1/sqrt(x) for positive normal x (full double precision: MUFU seed 2^-22, one cubic step); x = 0 -> NaN, never trapped
@@ -886,19 +905,25 @@ __device__ __forceinline__ void launder(RowLookup &f) {
 // Table value at squared radius r2: v0 + t (v1 - v0) in the cell of u (scipy's (1-t) v0 + t v1 up to round-off; a
 // non-finite node makes the result non-finite either way).  ok = false outside [r0, r1] (scipy: fill_value = nan);
 // r2 = 0, inf, NaN fall outside.  log2 is the table-driven one of fast_log2 without its input test.
-__device__ __forceinline__ double row_at_r2(const RowLookup &f, double r2, bool &ok) {
-    const int hi = __double2hiint(r2);
-    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(r2));
+__host__ __device__ __forceinline__ double row_at_r2(const RowLookup &f, double r2, bool &ok) {
+    const int hi = f64_hi(r2);
+    const double m = f64_from((hi & 0x000fffff) | 0x3ff00000, f64_lo(r2));
     const double2 t = lds_f64x2(f.l2_s + (((unsigned)hi >> 9) & 0x7f0u));
     const double fr = fma(m, t.x, -1.0);
-    double p = fma(fr, c_l2p[0], c_l2p[1]);
-    p = fma(fr, p, c_l2p[2]);
-    p = fma(fr, p, c_l2p[3]);
-    p = fma(fr, p, c_l2p[4]);
-    const double ed = __hiloint2double(0x43300000, (hi >> 20) ^ 0x80000000) - 4503601774855167.0;   // unbiased exponent
+    double p = fma(fr, BFG_L2P(0), BFG_L2P(1));
+    p = fma(fr, p, BFG_L2P(2));
+    p = fma(fr, p, BFG_L2P(3));
+    p = fma(fr, p, BFG_L2P(4));
+    const double ed = f64_from(0x43300000, (hi >> 20) ^ 0x80000000) - 4503601774855167.0;   // unbiased exponent
     const double l2 = fma(fr, p, t.y) + ed;
     const double uu = fma(l2, f.uA, f.uB);
+#ifdef __CUDA_ARCH__
     int k = __double2int_rd(uu);
+#else
+    int k = (uu >= -2147483648.0 && uu <= 2147483647.0) ? (int)floor(uu) : (int)0x80000000;   // cvt.rmi.s32.f64 saturates; NaN -> 0
+    if (uu != uu) k = 0;
+    else if (uu > 2147483647.0) k = 2147483647;
+#endif
     ok = true;
     if (__builtin_expect((unsigned)k > (unsigned)f.nrm2, 0)) {   // outside the table, or exactly on its last node
         ok = (uu == f.uMax);

@@ -391,6 +391,12 @@ int bfg_test_shell_update_host(int ndim, const int64_t *shape, const double *con
 /* Test entry, pure host (no GPU): one axis of the grid re-binning (regrid_pixels_2D/3D, Map2DRunner.py:13-162) -- the two cells that
  * overlap [x, x + 1) after the periodic wrap and their overlap lengths -- from the kernel's own source.  h_c, h_w: [n][2]. */
 int bfg_test_axis_deposit_host(int64_t n, const double *h_pos, int64_t N, int64_t *h_c, double *h_w);
+/* Test entry, pure host (no GPU): the lean read-out by SQUARED radius (row_at_r2: uniform ln r axis, table-driven log2) of the default
+ * grid / particle / exact shell loops, from the kernels' own source.  offset = what the kernels add to ln r (ln(1/a), -ln R_com, ...).
+ * h_out[i] = table value (NaN outside), h_ok[i] = inside [r0, r1]. */
+int bfg_test_row_at_r2_host(int ndim, const int64_t *shape, const double *const *h_axes, const double *h_values, int flags, double lnz,
+                            double lnM, const double *h_extras, double offset, int64_t n, const double *h_r2, double *h_out,
+                            int *h_ok);
 /* Test entry, pure host (no GPU): index helpers of the grid and particle kernels on the CPU.  what = 0 NGP cell (np.histogramdd edges,
  * utils/io.py:629-677), 1 wrap_once (SnapshotRunner.py:272-273), 2 cell-list cell, 3 cutout coordinates + periodic indices of one axis
  * (n = Nsize, L = res, h_x[0] = centre cell; Map2DRunner.py:400-429, :500-528). */

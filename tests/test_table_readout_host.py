@@ -86,3 +86,42 @@ def test_readout_source_on_host_matches_scipy_regular_grid_interpolator():
     assert_close(a, bb, "uniform vs search", rtol=1e-11, atol_scale=1e-14)
     want = RGI(axes, vals, bounds_error=False)((np.full_like(xs, axes[0][4] + 0.01), np.full_like(xs, axes[1][5] + 0.1), xs))
     assert_close(bb, want, "search vs scipy", rtol=1e-13, atol_scale=1e-14)
+
+
+def test_lean_readout_by_squared_radius_matches_scipy():
+    """row_at_r2 -- the read-out of the default grid, particle and exact shell loops: value at a SQUARED radius, cell coordinate
+    u = log2(r^2) uA + uB with the table-driven log2, v0 + t (v1 - v0) -- from the kernels' own source on the host, against scipy at
+    ln r = 0.5 ln(r^2) + offset.  Away from exact nodes (deviation (vi)); r^2 = 0, inf, NaN and radii outside the table -> NaN."""
+    axes = synth.table_axes()                                             # the BASELINE table: 10 x 10 x 500, ln r uniform
+    vals = synth.displacement_values(axes, inject_nan=True)
+    rng = np.random.default_rng(12)
+    shape = (C.c_int64 * 3)(*[a.size for a in axes])
+    ax = [np.ascontiguousarray(a) for a in axes]
+    ptrs = (C.c_void_p * 3)(*[a.ctypes.data for a in ax])
+    v = np.ascontiguousarray(vals)
+    rgi = RGI(axes, vals, bounds_error=False, fill_value=np.nan)
+    for lnz, lnM, offset in ((axes[0][3] + 0.02, axes[1][4] + 0.3, 0.0), (axes[0][0], axes[1][-1], 0.35),
+                             (axes[0][1] + 0.01, axes[1][2] + 0.01, -1.7), (axes[0][-1] + 1e-3, axes[1][1], 0.0)):
+        lnr = rng.uniform(axes[2][0] - 1.0, axes[2][-1] + 1.0, 100000) - offset
+        r2 = np.concatenate([np.exp(2 * lnr), [0.0, np.inf, np.nan, -1.0, 5e-324]])
+        out = np.empty_like(r2)
+        ok = np.empty(r2.size, dtype=np.int32)
+        _lib.check(_lib.lib().bfg_test_row_at_r2_host(3, shape, ptrs, v.ctypes.data, 0, float(lnz), float(lnM), None, float(offset),
+                                                      r2.size, r2.ctypes.data, out.ctypes.data, ok.ctypes.data))
+        with np.errstate(divide='ignore', invalid='ignore'):
+            x = 0.5 * np.log(r2) + offset
+            want = rgi((np.full_like(x, lnz), np.full_like(x, lnM), x))
+            u = (x - axes[2][0]) / (axes[2][1] - axes[2][0])
+            keep = ~(np.abs(u - np.round(u)) < 1e-6)                          # node ties
+            edge = (np.abs(x - axes[2][0]) < 1e-9) | (np.abs(x - axes[2][-1]) < 1e-9)
+        keep &= ~edge
+        # a non-finite node (NaN, +-inf) makes the value non-finite on both sides -- inf + t (v1 - inf) is NaN where scipy's
+        # (1 - t) inf + t v1 stays inf -- and every caller turns non-finite into "adds nothing" (HealpixRunner.py:347)
+        fin = np.isfinite(want[keep])
+        assert np.array_equal(np.isfinite(out[keep]), fin)
+        halo_inside = bool(np.isfinite(lnz)) and axes[0][0] <= lnz <= axes[0][-1] and axes[1][0] <= lnM <= axes[1][-1]
+        with np.errstate(invalid='ignore'):
+            inside = halo_inside & (x[keep] >= axes[2][0]) & (x[keep] <= axes[2][-1])
+        assert np.array_equal(ok[keep] == 1, inside)
+        assert_close(out[keep][fin], want[keep][fin], f"row_at_r2 at ({lnz}, {lnM}), offset {offset}", rtol=1e-11, atol_scale=1e-14)
+        assert np.all(np.isnan(out[-5:])) and not ok[-5:].any()
