@@ -159,6 +159,32 @@ def workload_name(args):
             f"epsilon_max={args.eps:g} catalogue={'dn/dlogM~M^-0.9' if args.mass_function else '10^U(12,15.5)'} map=U(0,10)")
 
 
+L2_POLICY = "working set (4.8 GB offsets + 3.2 GB maps per step) >> 126 MB L2; no flush needed"
+# sum_j |query_disc_j| of the seeded workloads, as counted by the device AND by the oracle (tests/test_gpu_parity.py::
+# test_full_size_properties_nside4096): lets the reference arm -- which only runs a sample -- name the same `config`
+N_UPDATES_KNOWN = {
+    "BaryonifyShell NSIDE=4096 npix=201326592 halos=1000000 table=10x10x500 epsilon_max=20 catalogue=10^U(12,15.5) map=U(0,10)":
+        17746618419,
+}
+
+
+def sharding_text(world, p2p=True, gather=False):
+    if world == 1:
+        return "none"
+    return f"RING pixel ranges x{world}, overlap halos replicated, " + (
+        "re-binning fused with the exchange (fp64 REDs into the owner's slice over NVLink peer memory) + " + (
+            "NCCL all-gather of slices" if gather
+            else "new map left distributed over the ranks that own its slices (as in the end-to-end path)")
+        if p2p else "NCCL all-reduce of partial maps")
+
+
+def shell_config(args, world, n_up=None, p2p=True, gather=False):
+    """`config` of the headline line; both arms build it here, so the reference arm runs on the GPU arm's `config` by construction."""
+    w = workload_name(args)
+    return {"workload": w, "n_updates_per_step": int(n_up) if n_up is not None else N_UPDATES_KNOWN.get(w),
+            "l2_policy": L2_POLICY, "sharding": sharding_text(world, p2p, gather)}
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # CPU arms (oracle port)
 # ---------------------------------------------------------------------------------------------------------------
@@ -264,7 +290,7 @@ def run_reference(args):
             "unit": "halo-pixel updates/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * float(np.mean(times)), "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args), "timing": "wall clock around a multiprocessing map"},
+            "config": shell_config(args, max(1, int(args.gpus))), "timing": "wall clock around a multiprocessing map",
             "cpu_baseline": {"value": value, "unit": "halo-pixel updates/s", "cores": workers, "kind": "port",
                              "sample": sample},
             "e2e": {"value": value, "unit": "halo-pixel updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -683,14 +709,7 @@ def run_b200(args):
         line = {"metric": "halo-pixel updates/s (BaryonifyShell)", "value": value, "unit": "halo-pixel updates/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": workload_name(args), "n_updates_per_step": int(n_up),
-                           "l2_policy": "working set (4.8 GB offsets + 3.2 GB maps per step) >> 126 MB L2; no flush needed",
-                           "sharding": "none" if world == 1 else (
-                               f"RING pixel ranges x{world}, overlap halos replicated, " + (
-                                   "re-binning fused with the exchange (fp64 REDs into the owner's slice over NVLink peer memory) + " + (
-                                       "new map left distributed over the ranks that own its slices (as in the end-to-end path)" if (not args.gather_result)
-                                       else "NCCL all-gather of slices")
-                                   if peers is not None else "NCCL all-reduce of partial maps"))},
+                "config": shell_config(args, world, n_up, peers is not None, bool(args.gather_result)),
                 "clocks": clocks, "gpu_launches": n_launch,
                 "roofline": {"bound": "hbm", "kernel": "k_shell_halos<baryonify> (fused disc/separation/table/accumulate)",
                              "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -382,3 +382,26 @@ def test_host_thread_pool_and_buffer_release_work_without_a_gpu(monkeypatch):
     assert 1 <= runners._host_threads() <= 16
     runners.release_host_buffers()
     assert runners._PINNED_FREE == {} and runners._PINNED_SCRATCH == {}
+
+
+def test_both_bench_arms_name_the_same_config():
+    """bench.shell_config builds `config` for the GPU arm and for `--impl reference`: equal dicts by construction, and equal to what
+    the recorded GPU lines of this round carry (profiles/r2_bench_n1_final.json, N = 8 line)."""
+    import json
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    argv, sys.argv = sys.argv, ['bench.py']
+    try:
+        import bench
+        args = bench.parse()
+    finally:
+        sys.argv = argv
+    n1 = json.load(open(os.path.join(root, "profiles", "r2_bench_n1_final.json")))["config"]
+    n8 = json.load(open(os.path.join(root, "profiles", "r2_bench_n8_final_grid_leg_failed.json")))["config"]
+    assert bench.shell_config(args, 1) == n1 == bench.shell_config(args, 1, float(n1["n_updates_per_step"]), False, False)
+    assert bench.shell_config(args, 8) == n8 == bench.shell_config(args, 8, float(n8["n_updates_per_step"]), True, False)
+    assert bench.sharding_text(4, p2p=False) == "RING pixel ranges x4, overlap halos replicated, NCCL all-reduce of partial maps"
+    args.mass_function = True
+    assert bench.shell_config(args, 1)["n_updates_per_step"] is None            # only counted workloads are named
